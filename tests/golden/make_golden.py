@@ -1,0 +1,339 @@
+"""Generate the golden vectors that pin oracle/phc_oracle.py (and through it the CUDA path).
+
+Runs ONLY in the build container (needs /root/reference): imports the UNMODIFIED reference through
+ref_shim.py, drives its real code on seeded synthetic inputs and stores inputs + outputs as .npz:
+
+  python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+
+What is executed on the reference side (no restatement involved):
+  quat.npz     phc/utils/torch_utils.py + isaacgym_torch_utils.py functions
+  motion.npz   MotionLibBase.get_motion_state / _calc_frame_blend (phc/utils/motion_lib_base.py:437-559)
+  envstep.npz  HumanoidIm._compute_reward / _compute_reset / _compute_observations and
+               HumanoidAMP._update_hist_amp_obs / _compute_amp_observations / build_amp_obs_demo, called as bound
+               methods of an instance created with object.__new__ (no Isaac Gym) -- humanoid_im.py:694-948,
+               :1117-1190, humanoid_amp.py:253-284,:662-707
+  learn.npz    CommonAgent.discount_values/_calc_advs/_actor_loss/_critic_loss/bound_loss,
+               AMPAgent._disc_loss/_calc_disc_rewards/_combine_rewards, RunningMeanStd.forward
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import ref_shim  # noqa: E402
+
+ref_shim.install()
+torch.set_num_threads(1)
+
+from phc_b200 import synthetic as syn  # noqa: E402
+
+
+def npify(d):
+    out = {}
+    for k, v in d.items():
+        if torch.is_tensor(v):
+            out[k] = v.detach().cpu().numpy()
+        else:
+            out[k] = np.asarray(v)
+    return out
+
+
+def save(name, d):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **npify(d))
+    print(f"wrote {path}: {os.path.getsize(path) / 1024:.1f} KiB, {len(d)} arrays")
+
+
+# ------------------------------------------------------------------------------------------------
+def gen_quat():
+    import phc.utils.torch_utils as tu
+    g = torch.Generator().manual_seed(7)
+    n = 512
+    a = torch.nn.functional.normalize(torch.randn(n, 4, generator=g), dim=-1)
+    b = torch.nn.functional.normalize(torch.randn(n, 4, generator=g), dim=-1)
+    # near-identity / exactly-equal / antipodal cases
+    b[:32] = a[:32]
+    b[32:64] = -a[32:64]
+    small = torch.nn.functional.normalize(torch.cat((torch.randn(64, 3, generator=g) * 1e-3, torch.ones(64, 1)), -1), dim=-1)
+    b[64:128] = tu.quat_mul(a[64:128], small)
+    v = torch.randn(n, 3, generator=g)
+    t = torch.rand(n, 1, generator=g)
+    t[:8] = 0.0
+    t[8:16] = 1.0
+    e = torch.randn(n, 3, generator=g)
+    e[:8] = 0.0
+    e[8:16] *= 1e-6
+    e[16:32] *= 4.0          # angles beyond pi -> wrap
+    ang, axis = tu.quat_to_angle_axis(a)
+    ang_s, axis_s = tu.quat_to_angle_axis(small)
+    d = dict(a=a, b=b, v=v, t=t, e=e, small=small,
+             quat_mul=tu.quat_mul(a, b), quat_conjugate=tu.quat_conjugate(a), my_quat_rotate=tu.my_quat_rotate(a, v),
+             quat_to_tan_norm=tu.quat_to_tan_norm(a), angle=ang, axis=axis, angle_small=ang_s, axis_small=axis_s,
+             quat_to_exp_map=tu.quat_to_exp_map(a), exp_map_to_quat=tu.exp_map_to_quat(e), slerp=tu.slerp(a, b, t),
+             calc_heading=tu.calc_heading(a), calc_heading_quat=tu.calc_heading_quat(a),
+             calc_heading_quat_inv=tu.calc_heading_quat_inv(a))
+    from phc.env.tasks.humanoid import remove_base_rot
+    d["remove_base_rot"] = remove_base_rot(a)
+    save("quat.npz", d)
+
+
+# ------------------------------------------------------------------------------------------------
+def make_ref_motion_lib(m: syn.MotionData):
+    from phc.utils.motion_lib_base import MotionLibBase
+    lib = object.__new__(MotionLibBase)
+    lib._device = torch.device("cpu")
+    lib.gts, lib.grs, lib.lrs, lib.gvs, lib.gavs, lib.dvs = m.gts, m.grs, m.lrs, m.gvs, m.gavs, m.dvs
+    lib._motion_lengths, lib._motion_num_frames, lib._motion_dt = m.lengths, m.num_frames, m.dts
+    lib.length_starts = m.length_starts
+    lib.num_bodies = m.num_bodies
+    F = m.gts.shape[0]
+    lib._motion_aa = torch.zeros(F, 72)
+    lib._motion_bodies = torch.zeros(m.num_motions, 17)
+    lib._motion_limb_weights = torch.zeros(m.num_motions, 10)
+    lib._motion_fps = 1.0 / m.dts
+    return lib
+
+
+def motion_tables_dict(m: syn.MotionData, prefix="tab_"):
+    return {prefix + f: getattr(m, f) for f in m.__dataclass_fields__}
+
+
+def gen_motion():
+    m = syn.make_motions(6, seed=3, min_frames=20, max_frames=40)
+    lib = make_ref_motion_lib(m)
+    g = torch.Generator().manual_seed(11)
+    n = 96
+    ids = torch.randint(0, m.num_motions, (n,), generator=g)
+    ln = m.lengths[ids]
+    times = torch.rand(n, generator=g) * ln
+    times[:8] = -0.05 * torch.arange(8)                 # negative (history before clip start)
+    times[8:16] = ln[8:16] + 0.03 * torch.arange(8)     # at/after the clip end
+    times[16:32] = ((torch.rand(16, generator=g) * ln[16:32]) / (1 / 30)).long() * (1 / 30)  # on the frame grid
+    offset = torch.randn(n, 3, generator=g)
+    i0, i1, bl = lib._calc_frame_blend(times, ln, m.num_frames[ids], m.dts[ids])
+    res = lib.get_motion_state(ids, times, offset=offset)
+    res_no = lib.get_motion_state(ids, times)
+    d = dict(ids=ids, times=times, offset=offset, idx0=i0, idx1=i1, blend=bl, **motion_tables_dict(m))
+    for k in ("root_pos", "root_rot", "dof_pos", "root_vel", "root_ang_vel", "dof_vel", "rg_pos", "rb_rot", "body_vel", "body_ang_vel"):
+        d["out_" + k] = res[k]
+    d["out_noffset_rg_pos"] = res_no["rg_pos"]
+    save("motion.npz", d)
+
+
+# ------------------------------------------------------------------------------------------------
+def build_ref_env(m: syn.MotionData, st: syn.EnvState, power_coef=0.0005, upright=True, local_root_obs=True,
+                  im_eval=False):
+    """A HumanoidIm instance without Isaac Gym: every attribute the post-physics methods read is set by hand."""
+    from phc.env.tasks.humanoid_im import HumanoidIm
+    from phc.utils.flags import flags
+    flags.test, flags.im_eval, flags.real_traj, flags.no_collision_check = False, im_eval, False, False
+    N, J = st.body_state.shape[0], st.body_state.shape[1]
+    D = (J - 1) * 3
+    env = object.__new__(HumanoidIm)
+    env.device = torch.device("cpu")
+    env.num_envs = N
+    env.num_bodies = J
+    env.dt = 1.0 / 30.0
+    body = st.body_state.clone()
+    env._rigid_body_state_reshaped = body
+    env._rigid_body_pos, env._rigid_body_rot = body[..., 0:3], body[..., 3:7]
+    env._rigid_body_vel, env._rigid_body_ang_vel = body[..., 7:10], body[..., 10:13]
+    dof = st.dof_state.clone()
+    env._dof_pos, env._dof_vel = dof[..., 0], dof[..., 1]
+    env.dof_force_tensor = st.dof_force.clone()
+    env.progress_buf = st.progress.clone()
+    env.reset_buf = torch.zeros(N, dtype=torch.long)
+    env._terminate_buf = torch.zeros(N, dtype=torch.long)
+    env.rew_buf = torch.zeros(N)
+    env._motion_start_times = st.start_times.clone()
+    env._motion_start_times_offset = st.start_offsets.clone()
+    env._sampled_motion_ids = st.motion_ids.clone()
+    env._global_offset = st.global_offset.clone()
+    env.ref_motion_cache = {}
+    env._motion_lib = make_ref_motion_lib(m)
+    env.humanoid_type = "smpl"
+    env.zero_out_far = False
+    env.zero_out_far_train = False
+    env._full_body_reward = True
+    env.reward_specs = {"k_pos": 100, "k_rot": 10, "k_vel": 0.1, "k_ang_vel": 0.1, "w_pos": 0.5, "w_rot": 0.3, "w_vel": 0.1, "w_ang_vel": 0.1}
+    env.power_reward = True
+    env.power_coefficient = power_coef
+    env.max_episode_length = 300
+    env.cycle_motion = False
+    env._reset_bodies_id = torch.tensor(syn.SMPL_RESET_BODIES)
+    env._track_bodies_id = torch.arange(J)
+    env._occl_training = False
+    env._contact_forces = torch.zeros(N, J, 3)
+    env._contact_body_ids = torch.tensor([7, 3, 8, 4])
+    env._enable_early_termination = True
+    env._termination_distances = torch.full((J,), 0.25)
+    env.strict_eval = False
+    env._cycle_counter = torch.zeros(N, dtype=torch.int)
+    # observation side
+    env.self_obs_v, env.obs_v = 1, 6
+    env._local_root_obs, env._root_height_obs, env._has_upright_start = local_root_obs, True, upright
+    env._has_shape_obs, env._has_limb_weight_obs = False, False
+    env.humanoid_shapes = torch.zeros(N, 17)
+    env.humanoid_limb_and_weights = torch.zeros(N, 10)
+    env._enable_task_obs = True
+    env._enable_hist_obs = False
+    env.add_obs_noise = False
+    env._fut_tracks = False
+    env._fut_tracks_dropout = False
+    env._num_traj_samples = 1
+    env._dof_names = syn.SMPL_BODY_NAMES[1:]
+    env.self_obs_buf = torch.zeros(N, 1 + J * 15 - 3)
+    env.obs_buf = torch.zeros(N, 1 + J * 15 - 3 + J * 24)
+    env.ref_body_pos = torch.zeros(N, J, 3)
+    env.ref_body_vel = torch.zeros(N, J, 3)
+    env.ref_body_rot = torch.zeros(N, J, 4)
+    env.ref_body_pos_subset = torch.zeros(N, J, 3)
+    env.ref_dof_pos = torch.zeros(N, D)
+    # AMP side
+    S, A = st.amp_hist.shape[1], st.amp_hist.shape[2]
+    env._num_amp_obs_steps, env._num_amp_obs_per_step = S, A
+    env._amp_obs_buf = st.amp_hist.clone()
+    env._curr_amp_obs_buf = env._amp_obs_buf[:, 0]
+    env._hist_amp_obs_buf = env._amp_obs_buf[:, 1:]
+    env._key_body_ids = torch.tensor(syn.SMPL_KEY_BODIES)
+    env.dof_subset = torch.tensor(syn.SMPL_DOF_SUBSET)
+    env.amp_obs_v = 1
+    env._amp_root_height_obs = True
+    env._has_dof_subset = True
+    env._has_shape_obs_disc, env._has_limb_weight_obs_disc = False, False
+    env._add_amp_input_noise = False
+    env.extras = {}
+    return env
+
+
+def run_ref_step(env):
+    """The body of Humanoid.post_physics_step (humanoid.py:1634-1650) + HumanoidAMP.post_physics_step
+    (humanoid_amp.py:194-210) minus the simulator refresh; progress_buf is already incremented in the inputs."""
+    env._compute_reward(None)
+    env._compute_reset()
+    env._compute_observations()
+    # HumanoidAMP._update_hist_amp_obs (humanoid_amp.py:662-670) first tries `hist[:] = buf[:, 0:S-1]` where hist
+    # aliases buf[:, 1:]; the torch the reference targets rejects that partial overlap and the method falls back to
+    # its `except:` branch (`.clone()` first = a true shift by one slot).  torch 2.11 on CPU raises nothing and
+    # smears slot 0 over the whole window instead, so the golden executes the fallback statement (:667) directly.
+    S = env._num_amp_obs_steps
+    env._hist_amp_obs_buf[:] = env._amp_obs_buf[:, 0:(S - 1)].clone()
+    env._compute_amp_observations()
+    return dict(obs=env.obs_buf.clone(), rew=env.rew_buf.clone(), reward_raw=env.reward_raw.clone(),
+                reset=env.reset_buf.clone(), terminate=env._terminate_buf.clone(),
+                amp_obs_buf=env._amp_obs_buf.clone(), ref_body_pos=env.ref_body_pos.clone(),
+                ref_body_rot=env.ref_body_rot.clone(), ref_body_vel=env.ref_body_vel.clone(),
+                ref_dof_pos=env.ref_dof_pos.clone(), self_obs=env.self_obs_buf.clone())
+
+
+def gen_envstep():
+    m = syn.make_motions(32, seed=1, min_frames=12, max_frames=24)   # one clip per env (humanoid_im.py:1121 compares [N] with [M])
+    cases = {}
+    # case A: the shipped config (frame-grid start times, no offset)
+    stA = syn.make_env_state(m, 32, seed=0, max_progress=20)
+    # case B: generic blend values + global offset
+    stB = syn.make_env_state(m, 32, seed=1, max_progress=20, with_offset=True, blend_jitter=True)
+    for tag, st, kw in (("A", stA, {}), ("B", stB, {}), ("C", stA, dict(upright=False, local_root_obs=False)),
+                        ("D", stB, dict(im_eval=True))):
+        env = build_ref_env(m, st, **kw)
+        out = run_ref_step(env)
+        for k, v in out.items():
+            cases[f"{tag}_out_{k}"] = v
+        if tag in ("A", "B"):
+            for f in st.__dataclass_fields__:
+                cases[f"{tag}_in_{f}"] = getattr(st, f)
+    # AMP demo observation (build_amp_obs_demo) and history init (_init_amp_obs_ref arithmetic) on the reference motion
+    env = build_ref_env(m, stA)
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(0, m.num_motions, (24,), generator=g)
+    t0 = torch.rand(24, generator=g) * m.lengths[ids]
+    t0[:4] = 0.1                                         # history reaches before the clip start (negative times)
+    env.ref_motion_cache = {}
+    demo = env.build_amp_obs_demo(ids, t0).view(24, env._num_amp_obs_steps, -1)
+    cases["demo_ids"], cases["demo_t0"], cases["demo_out"] = ids, t0, demo
+    cases.update(motion_tables_dict(m))
+    save("envstep.npz", cases)
+
+
+# ------------------------------------------------------------------------------------------------
+def gen_learn():
+    import phc.learning.common_agent as ca
+    import phc.learning.amp_agent as aa
+    from phc.utils.running_mean_std import RunningMeanStd
+    T, N = 16, 24
+    fd, val, rew, nval = syn.make_rollout(N, T, seed=0)
+    agent = types.SimpleNamespace(horizon_length=T, gamma=0.99, tau=0.95, normalize_advantage=True, bounds_loss_coef=10)
+    adv = ca.CommonAgent.discount_values(agent, fd, val, rew, nval)
+    ret = adv + val
+    flat = lambda x: x.transpose(0, 1).reshape(T * N, -1)      # a2c_common.swap_and_flatten01
+    advn = ca.CommonAgent._calc_advs(agent, {"returns": flat(ret), "values": flat(val)})
+    g = torch.Generator().manual_seed(21)
+    B, A = 64, 69
+    old_nlp, nlp = torch.randn(B, generator=g) * 0.3 + 60, torch.randn(B, generator=g) * 0.3 + 60
+    advb = torch.randn(B, generator=g)
+    a_info = ca.CommonAgent._actor_loss(agent, old_nlp, nlp, advb, 0.2)
+    v, r = torch.randn(B, 1, generator=g), torch.randn(B, 1, generator=g)
+    c_info = ca.CommonAgent._critic_loss(agent, v, v * 0.9, 0.2, r, False)
+    mu = torch.randn(B, A, generator=g) * 1.5
+    b_loss = ca.CommonAgent.bound_loss(agent, mu)
+
+    # discriminator loss on a tiny real MLP (amp_agent.py:732-789)
+    torch.manual_seed(3)
+    din = 40
+    disc_mlp = torch.nn.Sequential(torch.nn.Linear(din, 32), torch.nn.ReLU(), torch.nn.Linear(32, 16), torch.nn.ReLU())
+    disc_logits = torch.nn.Linear(16, 1)
+    torch.nn.init.uniform_(disc_logits.weight, -1.0, 1.0)
+    net = types.SimpleNamespace(
+        get_disc_logit_weights=lambda: torch.flatten(disc_logits.weight),
+        get_disc_weights=lambda: [torch.flatten(mm.weight) for mm in disc_mlp if isinstance(mm, torch.nn.Linear)] + [torch.flatten(disc_logits.weight)])
+    dagent = types.SimpleNamespace(model=types.SimpleNamespace(a2c_network=net), _disc_logit_reg=0.01, _disc_grad_penalty=5,
+                                   _disc_weight_decay=0.0001)
+    for nm in ("_disc_loss_neg", "_disc_loss_pos", "_compute_disc_acc"):
+        setattr(dagent, nm, types.MethodType(getattr(aa.AMPAgent, nm), dagent))
+    x_agent = torch.randn(48, din, generator=g)
+    x_demo = torch.randn(24, din, generator=g).requires_grad_(True)
+    la = disc_logits(disc_mlp(x_agent))
+    ld = disc_logits(disc_mlp(x_demo))
+    dinfo = aa.AMPAgent._disc_loss(dagent, la, ld, x_demo)
+    params = list(disc_mlp.parameters()) + list(disc_logits.parameters())
+    grads = torch.autograd.grad(dinfo["disc_loss"], params)
+    ragent = types.SimpleNamespace(ppo_device="cpu", _disc_reward_scale=2, _norm_disc_reward=lambda: False,
+                                   _eval_disc=lambda x: disc_logits(disc_mlp(x)), _task_reward_w=0.5, _disc_reward_w=0.5)
+    dr = aa.AMPAgent._calc_disc_rewards(ragent, x_agent)
+    comb = aa.AMPAgent._combine_rewards(ragent, torch.ones(48, 1) * 0.7, {"disc_rewards": dr})
+
+    # running mean/std: normalise + update in train mode, then the un-normalise path
+    rms = RunningMeanStd((12,))
+    rms.train()
+    xs = [torch.randn(32, 12, generator=g) * 3 + 1 for _ in range(3)]
+    ys = [rms(x) for x in xs]
+    rms.eval()
+    yu = rms(xs[0][:, :12] * 0.1, unnorm=True)
+
+    d = dict(gae_fdones=fd, gae_values=val, gae_rewards=rew, gae_next_values=nval, gae_adv=adv, adv_norm=advn,
+             al_old=old_nlp, al_new=nlp, al_adv=advb, al_out=a_info["actor_loss"], cl_v=v * 0.9, cl_r=r,
+             cl_out=c_info["critic_loss"], bl_mu=mu, bl_out=b_loss,
+             d_w1=disc_mlp[0].weight, d_b1=disc_mlp[0].bias, d_w2=disc_mlp[2].weight, d_b2=disc_mlp[2].bias,
+             d_w3=disc_logits.weight, d_b3=disc_logits.bias, d_x_agent=x_agent, d_x_demo=x_demo,
+             d_loss=dinfo["disc_loss"], d_gp=dinfo["disc_grad_penalty"], d_logit_loss=dinfo["disc_logit_loss"],
+             d_agent_acc=dinfo["disc_agent_acc"], d_demo_acc=dinfo["disc_demo_acc"],
+             d_reward=dr, d_combined=comb,
+             rms_x0=xs[0], rms_x1=xs[1], rms_x2=xs[2], rms_y0=ys[0], rms_y1=ys[1], rms_y2=ys[2],
+             rms_mean=rms.running_mean, rms_var=rms.running_var, rms_count=rms.count, rms_unnorm=yu)
+    for i, gr in enumerate(grads):
+        d[f"d_grad{i}"] = gr
+    save("learn.npz", d)
+
+
+if __name__ == "__main__":
+    gen_quat()
+    gen_motion()
+    gen_envstep()
+    gen_learn()

@@ -1,0 +1,148 @@
+"""Pin oracle/phc_oracle.py against the golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  CPU only.  Tolerance: rtol 1e-5 / atol 1e-6 fp32 (north_star), except where a
+comment says otherwise (ill-conditioned acos near identity -- SURVEY.md section 7)."""
+import torch
+
+from oracle import phc_oracle as O
+from tests.helpers import close, env_state_from, load, smpl_step_config, tables_from
+
+
+def test_quaternion_library():
+    g = load("quat.npz")
+    a, b, v, t, e = g["a"], g["b"], g["v"], g["t"], g["e"]
+    close(O.qmul(a, b), g["quat_mul"], what="quat_mul")
+    close(O.qconj(a), g["quat_conjugate"], what="quat_conjugate")
+    close(O.qrot(a, v), g["my_quat_rotate"], what="my_quat_rotate")
+    close(O.tan_norm(a), g["quat_to_tan_norm"], what="tan_norm")
+    ang, axis = O.q_to_angle_axis(a)
+    close(ang, g["angle"], what="angle")
+    close(axis, g["axis"], what="axis")
+    ang_s, axis_s = O.q_to_angle_axis(g["small"])
+    close(ang_s, g["angle_small"], what="angle_small")
+    close(axis_s, g["axis_small"], rtol=1e-4, what="axis_small")
+    close(O.q_to_exp_map(a), g["quat_to_exp_map"], what="exp_map")
+    close(O.exp_map_to_q(e), g["exp_map_to_quat"], what="exp_map_to_quat")
+    close(O.slerp(a, b, t), g["slerp"], what="slerp")
+    close(O.heading_angle(a), g["calc_heading"], what="heading")
+    close(O.heading_q(a, False), g["calc_heading_quat"], what="heading_q")
+    close(O.heading_q(a, True), g["calc_heading_quat_inv"], what="heading_q_inv")
+    close(O.strip_base_rot(a), g["remove_base_rot"], what="remove_base_rot")
+
+
+def test_motion_state():
+    g = load("motion.npz")
+    tab = tables_from(g)
+    ids, times = g["ids"], g["times"]
+    i0, i1, bl = O.frame_blend(times, tab.lengths[ids], tab.num_frames[ids], tab.dts[ids])
+    close(i0, g["idx0"], what="idx0")
+    close(i1, g["idx1"], what="idx1")
+    close(bl, g["blend"], what="blend")
+    res = O.motion_state(tab, ids, times, g["offset"])
+    for k in ("root_pos", "root_rot", "root_vel", "root_ang_vel", "dof_vel", "rg_pos", "rb_rot", "body_vel", "body_ang_vel"):
+        close(res[k], g["out_" + k], what=k)
+    # dof_pos = 2*acos(w)*axis of a slerped quaternion: near-identity joints are ill-conditioned
+    close(res["dof_pos"], g["out_dof_pos"], rtol=1e-4, atol=1e-5, what="dof_pos")
+    close(O.motion_state(tab, ids, times)["rg_pos"], g["out_noffset_rg_pos"], what="rg_pos (no offset)")
+
+
+def _check_step(g, tag, in_tag, cfg):
+    tab = tables_from(g)
+    st = env_state_from(g, in_tag)
+    out = O.env_step(tab, cfg, st.body_state, st.dof_state, st.dof_force, st.progress, st.motion_ids,
+                     st.start_times, st.start_offsets, st.global_offset, st.amp_hist)
+    close(out["obs"], g[f"{tag}_out_obs"], what=f"{tag} obs")
+    close(out["obs"][:, :g[f"{tag}_out_self_obs"].shape[1]], g[f"{tag}_out_self_obs"], what=f"{tag} self_obs")
+    close(out["rew"], g[f"{tag}_out_rew"], what=f"{tag} rew")
+    close(out["reward_raw"], g[f"{tag}_out_reward_raw"], what=f"{tag} reward_raw")
+    close(out["reset"], g[f"{tag}_out_reset"], what=f"{tag} reset")
+    close(out["terminate"], g[f"{tag}_out_terminate"], what=f"{tag} terminate")
+    close(out["amp_obs_buf"], g[f"{tag}_out_amp_obs_buf"], what=f"{tag} amp_obs_buf")
+    close(out["ref_body_pos"], g[f"{tag}_out_ref_body_pos"], what=f"{tag} ref_body_pos")
+    close(out["ref_body_rot"], g[f"{tag}_out_ref_body_rot"], what=f"{tag} ref_body_rot")
+    close(out["ref_body_vel"], g[f"{tag}_out_ref_body_vel"], what=f"{tag} ref_body_vel")
+    close(out["ref_dof_pos"], g[f"{tag}_out_ref_dof_pos"], rtol=1e-4, atol=1e-5, what=f"{tag} ref_dof_pos")
+    return out
+
+
+def test_env_step_shipped_config():
+    g = load("envstep.npz")
+    out = _check_step(g, "A", "A", smpl_step_config())
+    assert out["terminate"].sum() > 0 and out["reset"].sum() >= out["terminate"].sum()   # the case exercises early termination
+    assert (out["reward_raw"][:, 4] == 0).any() and (out["reward_raw"][:, 4] != 0).any()  # power reward mask both ways
+
+
+def test_env_step_generic_blend_and_offset():
+    _check_step(load("envstep.npz"), "B", "B", smpl_step_config())
+
+
+def test_env_step_not_upright_global_root():
+    _check_step(load("envstep.npz"), "C", "A", smpl_step_config(upright=False, local_root_obs=False))
+
+
+def test_env_step_im_eval_mean_termination():
+    _check_step(load("envstep.npz"), "D", "B", smpl_step_config(use_mean=True))
+
+
+def test_amp_obs_demo():
+    g = load("envstep.npz")
+    out = O.amp_obs_demo(tables_from(g), smpl_step_config(), g["demo_ids"], g["demo_t0"])
+    # joint exp-maps of the reference pose go through acos near identity -> looser on those columns
+    close(out, g["demo_out"], rtol=1e-4, atol=2e-5, what="amp_obs_demo")
+
+
+def test_learning_pieces():
+    g = load("learn.npz")
+    adv = O.gae(g["gae_fdones"], g["gae_values"], g["gae_rewards"], g["gae_next_values"], 0.99, 0.95)
+    close(adv, g["gae_adv"], what="gae")
+    T, N = adv.shape[0], adv.shape[1]
+    flat = lambda x: x.transpose(0, 1).reshape(T * N, -1)
+    close(O.normalize_advantages(flat(adv + g["gae_values"]), flat(g["gae_values"])), g["adv_norm"], what="adv_norm")
+    close(O.actor_loss(g["al_old"], g["al_new"], g["al_adv"], 0.2), g["al_out"], what="actor_loss")
+    close(O.critic_loss(g["cl_v"], g["cl_r"]), g["cl_out"], what="critic_loss")
+    close(O.bound_loss(g["bl_mu"]), g["bl_out"], what="bound_loss")
+
+    ws = [g["d_w1"], g["d_w2"], g["d_w3"]]
+    bs = [g["d_b1"], g["d_b2"], g["d_b3"]]
+    params = [p.clone().requires_grad_(True) for p in (ws[0], bs[0], ws[1], bs[1], ws[2], bs[2])]
+    W, B = params[0::2], params[1::2]
+    x_demo = g["d_x_demo"].clone().requires_grad_(True)
+    la = O.mlp_forward(g["d_x_agent"], W, B)
+    ld = O.mlp_forward(x_demo, W, B)
+    info = O.disc_loss(la, ld, x_demo, W[2], W)
+    close(info["disc_loss"], g["d_loss"], what="disc_loss")
+    close(info["disc_grad_penalty"], g["d_gp"], what="disc_gp")
+    close(info["disc_logit_loss"], g["d_logit_loss"], what="disc_logit_loss")
+    close(info["disc_agent_acc"], g["d_agent_acc"], what="acc_a")
+    close(info["disc_demo_acc"], g["d_demo_acc"], what="acc_d")
+    grads = torch.autograd.grad(info["disc_loss"], params)
+    for i, gr in enumerate(grads):
+        close(gr, g[f"d_grad{i}"], rtol=1e-4, atol=1e-6, what=f"disc grad {i}")
+    with torch.no_grad():
+        dr = O.disc_reward(O.mlp_forward(g["d_x_agent"], ws, bs))
+    close(dr, g["d_reward"], what="disc_reward")
+    close(0.5 * torch.ones(48, 1) * 0.7 + 0.5 * dr, g["d_combined"], what="combined")
+
+    mean, var, cnt = torch.zeros(12, dtype=torch.float64), torch.ones(12, dtype=torch.float64), torch.ones((), dtype=torch.float64)
+    for i in range(3):
+        x = g[f"rms_x{i}"]
+        close(O.rms_normalize(x, mean, var), g[f"rms_y{i}"], what=f"rms_y{i}")
+        mean, var, cnt = O.rms_update(mean, var, cnt, x)
+    close(mean, g["rms_mean"], rtol=1e-12, atol=1e-12, what="rms_mean")
+    close(var, g["rms_var"], rtol=1e-12, atol=1e-12, what="rms_var")
+    close(cnt, g["rms_count"], what="rms_count")
+    close(O.rms_unnormalize(g["rms_x0"] * 0.1, mean, var), g["rms_unnorm"], what="rms_unnorm")
+
+
+def test_gaussian_pieces_self_pinned():
+    """rl_games==1.1.4 pieces (absent from /root/reference): pinned against torch.distributions."""
+    gen = torch.Generator().manual_seed(0)
+    mu, a = torch.randn(16, 69, generator=gen), torch.randn(16, 69, generator=gen)
+    logstd = torch.full((69,), -2.9).expand(16, 69)
+    sigma = torch.exp(logstd)
+    ref = -torch.distributions.Normal(mu, sigma).log_prob(a).sum(-1)
+    close(O.gaussian_neglogp(a, mu, sigma, logstd), ref, rtol=1e-5, atol=1e-3, what="neglogp")
+    # KL(new || old); sigma ~ 0.5 so rl_games' +1e-5 regularisers are negligible against the closed form
+    s_new, s_old = torch.full((16, 69), 0.5), torch.full((16, 69), 0.55)
+    mu_old = mu + 0.05
+    kl = torch.distributions.kl_divergence(torch.distributions.Normal(mu, s_new), torch.distributions.Normal(mu_old, s_old)).sum(-1).mean()
+    close(O.policy_kl(mu, s_new, mu_old, s_old), kl, rtol=1e-3, atol=1e-3, what="policy_kl")
