@@ -1,0 +1,198 @@
+/* phc_b200 -- C ABI of the B200-native PHC hot path (libphc_b200.so).
+ *
+ * The reference (ZhengyiLuo/PHC) has NO native boundary: the whole path is Python/TorchScript.  This header is
+ * where one is cut.  Every entry point replaces a group of reference functions (cited file:line, relative to the
+ * reference checkout) and takes plain device pointers + sizes + a CUDA stream -- no torch types.  Ownership never
+ * transfers: every buffer is allocated by the caller (a torch tensor in the Python host), the library allocates
+ * nothing except the workspace objects created by the *_create calls below.
+ *
+ * All functions return 0 (PHC_OK) or a negative PHC_ERR_* code, never throw, never synchronise the device unless
+ * documented.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Quaternions are xyzw fp32.
+ */
+#ifndef PHC_B200_H_
+#define PHC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Exported entry points (the library is built with -fvisibility=hidden). */
+#if defined(_WIN32)
+#define PHC_API __declspec(dllexport)
+#else
+#define PHC_API __attribute__((visibility("default")))
+#endif
+
+#define PHC_OK 0
+#define PHC_ERR_INVALID_ARG (-1)  /* NULL pointer / bad size / misaligned table                          */
+#define PHC_ERR_UNSUPPORTED (-2)  /* configuration outside what the kernels implement (see message)      */
+#define PHC_ERR_CUDA (-3)         /* a CUDA runtime call failed; phc_last_error() has the cudaError text */
+
+/* Library / build information.  phc_version() = 10000*major + 100*minor + patch. */
+PHC_API int phc_version(void);
+/* Thread-local, NUL-terminated description of the last non-zero return on this thread. */
+PHC_API const char* phc_last_error(void);
+/* SM architecture the library was compiled for (100 for sm_100a). */
+PHC_API int phc_compiled_sm(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Motion library, packed device format
+ *   replaces the table set MotionLibBase builds at load time: gts/grs/lrs/gvs/gavs/dvs
+ *   (phc/utils/motion_lib_base.py:300-307).  One frame = one 16-byte aligned record so a frame bracket is two
+ *   TMA bulk copies:  body record  [J][13] = pos3 rot4 vel3 angvel3  (the simulator's rigid-body layout,
+ *   phc/env/tasks/humanoid.py:219-226), padded to body_stride floats (multiple of 4);
+ *   joint record [J][4] local rotation then [J-1][3] dof velocity, padded to joint_stride floats.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct PhcMotionLib {
+  const float* frames_body;         /* [num_frames_total, body_stride]                                       */
+  const float* frames_joint;        /* [num_frames_total, joint_stride] or NULL (dof_pos/dof_vel unavailable) */
+  const float* motion_len;          /* [num_motions] seconds          (_motion_lengths)                       */
+  const float* motion_dt;           /* [num_motions] seconds / frame  (_motion_dt)                            */
+  const int64_t* motion_num_frames; /* [num_motions]                  (_motion_num_frames)                    */
+  const int64_t* length_starts;     /* [num_motions] first table row  (length_starts)                         */
+  int64_t num_frames_total;
+  int32_t num_motions;
+  int32_t num_bodies;   /* J */
+  int32_t body_stride;  /* floats per body record  = round_up(13*J, 4)           */
+  int32_t joint_stride; /* floats per joint record = round_up(4*J + 3*(J-1), 4)  */
+} PhcMotionLib;
+
+PHC_API int phc_motion_body_stride(int32_t num_bodies);
+PHC_API int phc_motion_joint_stride(int32_t num_bodies);
+
+/* Pack the reference's separate tables into the records above (one pass, HBM-bound).
+ * gts[F,J,3] grs[F,J,4] gvs[F,J,3] gavs[F,J,3] -> frames_body[F,body_stride];
+ * lrs[F,J,4] dvs[F,J-1,3] -> frames_joint[F,joint_stride] (skipped when lrs/dvs/frames_joint is NULL). */
+PHC_API int phc_motion_pack(const float* gts, const float* grs, const float* gvs, const float* gavs, const float* lrs,
+                    const float* dvs, int64_t num_frames_total, int32_t num_bodies, float* frames_body,
+                    float* frames_joint, void* stream);
+
+/* MotionLibBase.get_motion_state (motion_lib_base.py:437-520, SMPL variant) for n arbitrary (id, time) queries:
+ * frame bracket (_calc_frame_blend :549-559), lerp of pos/vel/angvel/dof_vel (+offset on pos), slerp of global
+ * and local rotations, dof_pos = exp_map(local_rot[1:]).  Any output pointer may be NULL (skipped).
+ * root_* are body 0 of rg_pos/rb_rot/body_vel/body_ang_vel. */
+typedef struct PhcMotionStateOut {
+  float* rg_pos;       /* [n, J, 3] */
+  float* rb_rot;       /* [n, J, 4] */
+  float* body_vel;     /* [n, J, 3] */
+  float* body_ang_vel; /* [n, J, 3] */
+  float* dof_pos;      /* [n, 3(J-1)] */
+  float* dof_vel;      /* [n, 3(J-1)] */
+  float* root_pos;     /* [n, 3] */
+  float* root_rot;     /* [n, 4] */
+  float* root_vel;     /* [n, 3] */
+  float* root_ang_vel; /* [n, 3] */
+} PhcMotionStateOut;
+
+PHC_API int phc_motion_state(const PhcMotionLib* lib, const int64_t* motion_ids, const float* motion_times,
+                     const float* offset /* [n,3] or NULL */, int64_t n, const PhcMotionStateOut* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused env step after physics: ONE kernel for
+ *   Humanoid.post_physics_step (humanoid.py:1634-1650) ->
+ *     HumanoidIm._compute_reward   (humanoid_im.py:873-948;  compute_imitation_reward :1523-1554, power :939-946)
+ *     HumanoidIm._compute_reset    (humanoid_im.py:1117-1190; compute_humanoid_im_reset :1580-1608)
+ *     HumanoidIm._compute_observations (humanoid_im.py:694-726): self obs compute_humanoid_observations_smpl_max
+ *       (humanoid.py:1994-2050) + task obs compute_imitation_observations_v6 (humanoid_im.py:1308-1358)
+ *     the two MotionLib queries those make (motion_lib_base.py:437-520) at t and t+dt
+ *   HumanoidAMP.post_physics_step (humanoid_amp.py:194-210): _update_hist_amp_obs (:662-670) +
+ *     build_amp_observations_smpl (:966-1011)
+ * progress must already hold the incremented step counter (humanoid.py:1637).
+ * ---------------------------------------------------------------------------------------------------------- */
+#define PHC_FLAG_UPRIGHT (1u << 0)         /* robot.has_upright_start                                   */
+#define PHC_FLAG_LOCAL_ROOT_OBS (1u << 1)  /* env.local_root_obs                                        */
+#define PHC_FLAG_ROOT_HEIGHT_OBS (1u << 2) /* env.root_height_obs (also the AMP root height column)     */
+#define PHC_FLAG_POWER_REWARD (1u << 3)    /* env.power_reward -> reward_raw has 5 columns              */
+#define PHC_FLAG_EARLY_TERM (1u << 4)      /* env.enableEarlyTermination                                */
+#define PHC_FLAG_NO_COLLISION (1u << 5)    /* flags.no_collision_check                                  */
+#define PHC_FLAG_TERM_USE_MEAN (1u << 6)   /* flags.im_eval and not strict_eval: mean-distance criterion */
+
+#define PHC_MAX_KEY_BODIES 8
+
+typedef struct PhcStepArgs {
+  /* ---- simulator state (inputs; contract of Humanoid._setup_tensors, humanoid.py:179-247) ---- */
+  const float* body_state;  /* [N, bodies_per_env, 13]: pos rot vel ang_vel; only the first J bodies are read */
+  const float* dof_state;   /* [N, D, 2] (pos, vel) interleaved, D = 3(J-1)                                    */
+  const float* dof_force;   /* [N, D] or NULL when PHC_FLAG_POWER_REWARD is clear                              */
+  int32_t bodies_per_env;
+  /* ---- per-env motion bookkeeping ---- */
+  const int64_t* progress;       /* [N] progress_buf                    */
+  const int64_t* motion_ids;     /* [N] _sampled_motion_ids             */
+  const float* start_times;      /* [N] _motion_start_times             */
+  const float* start_offsets;    /* [N] _motion_start_times_offset      */
+  const float* global_offset;    /* [N,3] _global_offset                */
+  const int32_t* cycle_counter;  /* [N] _cycle_counter or NULL (is_recovery override, humanoid_im.py:1186-1188) */
+  PhcMotionLib lib;
+  /* ---- configuration ---- */
+  int32_t num_envs;   /* N */
+  int32_t time_steps; /* T = _num_traj_samples (1 unless fut_tracks)  */
+  float dt;           /* control dt (1/30)                            */
+  float traj_dt;      /* _traj_sample_timestep (spacing of the T future samples) */
+  uint32_t flags;     /* PHC_FLAG_*                                   */
+  float k_pos, k_rot, k_vel, k_ang_vel; /* reward_specs (humanoid_im.py:57) */
+  float w_pos, w_rot, w_vel, w_ang_vel;
+  float power_coef;                     /* power_coefficient (humanoid_im.py:107) */
+  const float* term_thresh;  /* [J] termination distance per body, +inf for bodies outside reset_bodies */
+  float term_dist_mean;      /* threshold of the first reset body (used by PHC_FLAG_TERM_USE_MEAN)       */
+  int32_t num_key_bodies;
+  int32_t key_bodies[PHC_MAX_KEY_BODIES]; /* _key_body_ids */
+  const int32_t* amp_joints; /* [num_amp_joints] joint indices (dof_subset / 3) kept in the AMP obs, or NULL = none */
+  int32_t num_amp_joints;
+  /* ---- outputs ---- */
+  float* obs;            /* [N, obs_stride] first 15J-3(+1) self obs then 24*J*T task obs (obs_buf)     */
+  int64_t obs_stride;    /* floats between rows                                                          */
+  float* rew;            /* [N] rew_buf                                                                  */
+  float* reward_raw;     /* [N, 5] (4 when power reward is off)                                          */
+  int64_t* reset;        /* [N] reset_buf                                                                */
+  int64_t* terminate;    /* [N] _terminate_buf                                                           */
+  /* AMP observation.  amp_out[N, amp_out_stride]: the current step's vector (A floats) is written at slot 0.
+   * If amp_hist_in != NULL the kernel also writes slots 1..S-1 = amp_hist_in slots 0..S-2 (newest-first window
+   * shift of _update_hist_amp_obs); amp_hist_in may alias amp_out (in-place, like the reference) or be another
+   * buffer (e.g. previous / current experience-buffer rows).  amp_out == NULL skips the AMP observation. */
+  float* amp_out;
+  const float* amp_hist_in;
+  int64_t amp_out_stride; /* floats between env rows of amp_out and amp_hist_in (>= S*A)                 */
+  int32_t amp_steps;      /* S                                                                            */
+  /* optional side buffers of _compute_task_obs(save_buffer=True) (humanoid_im.py:855-868); NULL = skip */
+  float* ref_body_pos;     /* [N, J, 3] */
+  float* ref_body_rot;     /* [N, J, 4] */
+  float* ref_body_vel;     /* [N, J, 3] */
+  float* ref_body_ang_vel; /* [N, J, 3] */
+} PhcStepArgs;
+
+/* Sizes implied by a configuration (so callers can allocate): */
+PHC_API int phc_self_obs_dim(int32_t num_bodies, uint32_t flags);                    /* 1 + 15J - 3          */
+PHC_API int phc_task_obs_dim(int32_t num_bodies, int32_t time_steps);                /* 24 J T               */
+PHC_API int phc_amp_obs_dim(int32_t num_amp_joints, int32_t num_key_bodies, uint32_t flags); /* 13 + 9 nj + 3 nk */
+
+PHC_API int phc_env_step(const PhcStepArgs* args, void* stream);
+
+/* build_amp_obs_demo (humanoid_amp.py:253-284) and the history re-initialisation of _init_amp_obs_ref
+ * (:575-603): AMP observations of the REFERENCE motion at t0 - (first_step + k)*dt, k = 0..num_steps-1,
+ * written to out[n, num_steps, A] (row stride out_stride floats).  Needs lib->frames_joint. */
+PHC_API int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* motion_ids, const float* times0, int64_t n,
+                     int32_t first_step, int32_t num_steps, float dt, uint32_t flags, const int32_t* key_bodies,
+                     int32_t num_key_bodies, const int32_t* amp_joints, int32_t num_amp_joints, float* out,
+                     int64_t out_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * PPO scalars
+ * ---------------------------------------------------------------------------------------------------------- */
+/* CommonAgent.discount_values (phc/learning/common_agent.py:493-505) + returns = advs + values
+ * (amp_agent.py:384-385).  Time-major [T, N] fp32 inputs (the reference's [T,N,1] tensors are the same memory);
+ * advs / returns may be NULL individually. */
+PHC_API int phc_gae(const float* fdones, const float* values, const float* rewards, const float* next_values, int32_t horizon,
+            int64_t num_envs, float gamma, float tau, float* advs, float* returns, void* stream);
+
+/* CommonAgent._calc_advs (common_agent.py:589-599): adv = returns - values, then (adv-mean)/(std+1e-8) with the
+ * UNBIASED std over all n elements.  workspace: >= phc_adv_norm_workspace_bytes(n) bytes of device scratch. */
+PHC_API int64_t phc_adv_norm_workspace_bytes(int64_t n);
+PHC_API int phc_adv_norm(const float* returns, const float* values, int64_t n, int32_t normalize, float* advs,
+                 void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHC_B200_H_ */

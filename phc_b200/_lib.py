@@ -1,0 +1,103 @@
+"""ctypes binding of libphc_b200.so -- the ONLY compute path of phc_b200 (there is no CPU / eager fallback).
+
+Mirrors include/phc_b200.h one to one.  Loading fails loudly (ImportError naming the build command) when the
+shared object is absent; every wrapper raises PhcError on a non-zero return code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libphc_b200.so")
+
+PHC_FLAG_UPRIGHT = 1 << 0
+PHC_FLAG_LOCAL_ROOT_OBS = 1 << 1
+PHC_FLAG_ROOT_HEIGHT_OBS = 1 << 2
+PHC_FLAG_POWER_REWARD = 1 << 3
+PHC_FLAG_EARLY_TERM = 1 << 4
+PHC_FLAG_NO_COLLISION = 1 << 5
+PHC_FLAG_TERM_USE_MEAN = 1 << 6
+PHC_MAX_KEY_BODIES = 8
+
+_p = C.c_void_p
+
+
+class PhcError(RuntimeError):
+    pass
+
+
+class PhcMotionLib(C.Structure):
+    _fields_ = [("frames_body", _p), ("frames_joint", _p), ("motion_len", _p), ("motion_dt", _p),
+                ("motion_num_frames", _p), ("length_starts", _p), ("num_frames_total", C.c_int64),
+                ("num_motions", C.c_int32), ("num_bodies", C.c_int32), ("body_stride", C.c_int32),
+                ("joint_stride", C.c_int32)]
+
+
+class PhcMotionStateOut(C.Structure):
+    _fields_ = [(n, _p) for n in ("rg_pos", "rb_rot", "body_vel", "body_ang_vel", "dof_pos", "dof_vel", "root_pos",
+                                  "root_rot", "root_vel", "root_ang_vel")]
+
+
+class PhcStepArgs(C.Structure):
+    _fields_ = [
+        ("body_state", _p), ("dof_state", _p), ("dof_force", _p), ("bodies_per_env", C.c_int32),
+        ("progress", _p), ("motion_ids", _p), ("start_times", _p), ("start_offsets", _p), ("global_offset", _p),
+        ("cycle_counter", _p), ("lib", PhcMotionLib),
+        ("num_envs", C.c_int32), ("time_steps", C.c_int32), ("dt", C.c_float), ("traj_dt", C.c_float),
+        ("flags", C.c_uint32),
+        ("k_pos", C.c_float), ("k_rot", C.c_float), ("k_vel", C.c_float), ("k_ang_vel", C.c_float),
+        ("w_pos", C.c_float), ("w_rot", C.c_float), ("w_vel", C.c_float), ("w_ang_vel", C.c_float),
+        ("power_coef", C.c_float), ("term_thresh", _p), ("term_dist_mean", C.c_float),
+        ("num_key_bodies", C.c_int32), ("key_bodies", C.c_int32 * PHC_MAX_KEY_BODIES),
+        ("amp_joints", _p), ("num_amp_joints", C.c_int32),
+        ("obs", _p), ("obs_stride", C.c_int64), ("rew", _p), ("reward_raw", _p), ("reset", _p), ("terminate", _p),
+        ("amp_out", _p), ("amp_hist_in", _p), ("amp_out_stride", C.c_int64), ("amp_steps", C.c_int32),
+        ("ref_body_pos", _p), ("ref_body_rot", _p), ("ref_body_vel", _p), ("ref_body_ang_vel", _p),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/phc_b200.h declares (tests check this)
+SIGNATURES = {
+    "phc_version": (C.c_int, []),
+    "phc_last_error": (C.c_char_p, []),
+    "phc_compiled_sm": (C.c_int, []),
+    "phc_motion_body_stride": (C.c_int, [C.c_int32]),
+    "phc_motion_joint_stride": (C.c_int, [C.c_int32]),
+    "phc_motion_pack": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int64, C.c_int32, _p, _p, _p]),
+    "phc_motion_state": (C.c_int, [C.POINTER(PhcMotionLib), _p, _p, _p, C.c_int64, C.POINTER(PhcMotionStateOut), _p]),
+    "phc_self_obs_dim": (C.c_int, [C.c_int32, C.c_uint32]),
+    "phc_task_obs_dim": (C.c_int, [C.c_int32, C.c_int32]),
+    "phc_amp_obs_dim": (C.c_int, [C.c_int32, C.c_int32, C.c_uint32]),
+    "phc_env_step": (C.c_int, [C.POINTER(PhcStepArgs), _p]),
+    "phc_amp_obs_demo": (C.c_int, [C.POINTER(PhcMotionLib), _p, _p, C.c_int64, C.c_int32, C.c_int32, C.c_float,
+                                   C.c_uint32, _p, C.c_int32, _p, C.c_int32, _p, C.c_int64, _p]),
+    "phc_gae": (C.c_int, [_p, _p, _p, _p, C.c_int32, C.c_int64, C.c_float, C.c_float, _p, _p, _p]),
+    "phc_adv_norm_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "phc_adv_norm": (C.c_int, [_p, _p, C.c_int64, C.c_int32, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load (once) and type the shared library.  No fallback: a missing library is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing -- build it with `python -m phc_b200.build` "
+                          f"(or __graft_entry__.build()); phc_b200 has no CPU / PyTorch fallback path")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError here = header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().phc_last_error().decode(errors="replace")
+        raise PhcError(f"{what or 'phc call'} failed with code {rc}: {msg}")

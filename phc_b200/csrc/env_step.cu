@@ -1,0 +1,442 @@
+// Fused post-physics env step for HumanoidIm: motion-library query (2 brackets) + self obs + task obs v6 +
+// tracking/power reward + reset/terminate + AMP observation (+ window shift) in ONE launch.
+// Reference functions replaced: see include/phc_b200.h (PhcStepArgs).
+//
+// Mapping: one warp per environment, lane j = body j (J <= 32).  Per env the kernel moves, for J = 24 / T = 1:
+//   reads  1248 B simulator state + <= 4 x 1248 B motion frames (3 distinct in steady state: the reward bracket
+//          [k, k+1] and the obs bracket [k+1, k+2] share a frame) + 552 B dof state + 276 B dof force + ~100 B scalars
+//   writes 3736 B observation + 40 B reward/reset + 784 B AMP vector (+ optional window shift / ref_* side buffers)
+// -> HBM-bound (about 250 FLOP per 52-byte body).  Blocks are staged into shared memory with TMA 1-D bulk copies
+// (cp.async.bulk + mbarrier: no register staging, one elected lane issues), de-interleaved from shared memory with
+// stride-13 reads (conflict free), results are staged as one observation row in shared memory and leave with
+// coalesced 8-byte stores.  28 envs are resident per SM at J = 24 so N = 4096 is a single wave on 148 SMs.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/phc_b200.h"
+#include "phc_common.cuh"
+#include "phc_math.cuh"
+
+namespace phc {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kMinCtasPerSm = 7;   // 28 envs resident per SM: 4096 envs = one wave on 148 SMs
+constexpr int kBodyRec = 13;
+
+struct StepLayout {      // per-warp shared-memory carve-up, in floats (all multiples of 4 -> 16-byte aligned)
+  int rslots;            // 2 frame slots of the reward bracket            | the observation row (T == 1) is
+  int state;             // J*13 rounded up: the env's simulator block     | staged over these two regions once
+  int oslots;            // 2T frame slots of the observation bracket(s)     their contents have been consumed
+  int dof;               // 2*D rounded up (pos, vel interleaved as in dof_state)
+  int amp;               // A rounded up
+  int obs;               // separate obs row (0 when it aliases rslots+state)
+  int total;             // sum + 4 (mbarrier)
+};
+
+__host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
+
+__host__ __device__ inline StepLayout make_layout(int J, int T, int body_stride, int A, int obs_dim, bool alias_obs) {
+  StepLayout L;
+  L.rslots = 2 * body_stride;
+  L.state = round4(J * kBodyRec);
+  L.oslots = 2 * T * body_stride;
+  L.dof = round4(2 * 3 * (J - 1));
+  L.amp = round4(A > 0 ? A : 4);
+  L.obs = alias_obs ? 0 : round4(obs_dim);
+  L.total = L.rslots + L.state + L.oslots + L.dof + L.amp + L.obs + 4;
+  return L;
+}
+
+struct BodyRec { V3 p; Q4 q; V3 v; V3 w; };
+
+__device__ __forceinline__ BodyRec load_body(const float* s) {
+  BodyRec b;
+  b.p = v3(s[0], s[1], s[2]);
+  b.q = q4(s[3], s[4], s[5], s[6]);
+  b.v = v3(s[7], s[8], s[9]);
+  b.w = v3(s[10], s[11], s[12]);
+  return b;
+}
+
+// two-frame blend of one body: lerp pos(+offset)/vel/angvel, slerp rot (motion_lib_base.py:474-488)
+__device__ __forceinline__ BodyRec blend_body(const float* s0, const float* s1, float bl, V3 off) {
+  const BodyRec a = load_body(s0), b = load_body(s1);
+  const float omb = 1.0f - bl;
+  BodyRec r;
+  r.p = lerp3(a.p, b.p, omb, bl) + off;
+  r.v = lerp3(a.v, b.v, omb, bl);
+  r.w = lerp3(a.w, b.w, omb, bl);
+  r.q = slerp(a.q, b.q, bl);
+  return r;
+}
+
+__device__ __forceinline__ void st3(float* d, V3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
+__device__ __forceinline__ void st6(float* d, TanNorm t) { st3(d, t.t); st3(d + 3, t.n); }
+
+template <int T_MAX>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm)
+env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const int self_dim, const int amp_dim,
+                const bool alias_obs, const bool state_bulk_ok) {
+  extern __shared__ __align__(128) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * kWarpsPerCta + warp;
+  if (env >= a.num_envs) return;                       // whole warp exits together; no block-level barrier is used
+
+  const int J = a.lib.num_bodies, D = 3 * (J - 1), T = a.time_steps;
+  const int BS = a.lib.body_stride;
+  const StepLayout L = make_layout(J, T, BS, amp_dim, obs_dim, alias_obs);
+  float* const w_base = smem + (size_t)warp * L.total;
+  float* const s_rslots = w_base;
+  float* const s_state = s_rslots + L.rslots;
+  float* const s_oslots = s_state + L.state;
+  float* const s_dof = s_oslots + L.oslots;
+  float* const s_amp = s_dof + L.dof;
+  float* const s_obs = alias_obs ? w_base : (s_amp + L.amp);
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(w_base + L.total - 4);
+
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    mbar_init_fence();
+  }
+  __syncwarp();
+
+  // ---- per-env scalars (warp-uniform broadcast loads) and the frame brackets -------------------------------
+  const int64_t progress = a.progress[env];
+  const int64_t mid = a.motion_ids[env];
+  const float t_start = a.start_times[env], t_off = a.start_offsets[env];
+  const V3 goff = v3(a.global_offset[3 * env + 0], a.global_offset[3 * env + 1], a.global_offset[3 * env + 2]);
+  const float m_len = a.lib.motion_len[mid], m_dt = a.lib.motion_dt[mid];
+  const int64_t m_nf = a.lib.motion_num_frames[mid], m_start = a.lib.length_starts[mid];
+
+  // reward / reset use the CURRENT motion time (humanoid_im.py:879), observations the NEXT one (:752)
+  const float t_now = (float)progress * a.dt + t_start + t_off;
+  const Bracket br_r = frame_bracket(t_now, m_len, m_nf, m_dt);
+  float bl_o[T_MAX];
+  const float* po0[T_MAX];     // shared-memory address of frame i0 / i1 of observation sample t
+  const float* po1[T_MAX];
+  const float* pr0 = s_rslots;
+  const float* pr1 = s_rslots + BS;
+
+  // ---- issue the TMA bulk copies: simulator block + the DISTINCT frames of all brackets ---------------------
+  // Observation slots are always filled; a later slot whose frame row was already requested aliases the earlier
+  // one.  In steady state (30 fps clips, dt = 1/30) the reward bracket is rows (k, k+1) and the observation
+  // bracket (k+1, k+2): 3 distinct frames, the reward slot 1 aliases observation slot 0.
+  {
+    uint32_t tx = 0;
+    const uint32_t frame_bytes = (uint32_t)BS * 4u;
+    int64_t rows_o[2 * T_MAX];
+    bool fresh_o[2 * T_MAX];
+#pragma unroll
+    for (int t = 0; t < T_MAX; ++t) {
+      if (t < T) {
+        // ((progress + 1) * dt [+ t * traj_dt] + start + offset), humanoid_im.py:744-752
+        float tn = (float)(progress + 1) * a.dt;
+        if (T > 1) tn = tn + (float)t * a.traj_dt;
+        tn = tn + t_start + t_off;
+        const Bracket b = frame_bracket(tn, m_len, m_nf, m_dt);
+        bl_o[t] = b.blend;
+        rows_o[2 * t] = m_start + b.i0;
+        rows_o[2 * t + 1] = m_start + b.i1;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * T_MAX; ++k) {
+      if (k < 2 * T) {
+        const float* ptr = s_oslots + k * BS;
+        bool dup = false;
+#pragma unroll
+        for (int p = 0; p < 2 * T_MAX; ++p)          // static indices only: keeps the arrays in registers
+          if (p < k && !dup && rows_o[p] == rows_o[k]) { ptr = (p & 1) ? po1[p >> 1] : po0[p >> 1]; dup = true; }
+        if (k & 1) po1[k >> 1] = ptr; else po0[k >> 1] = ptr;
+        fresh_o[k] = !dup;
+        if (!dup) tx += frame_bytes;
+      }
+    }
+    const int64_t row_r0 = m_start + br_r.i0, row_r1 = m_start + br_r.i1;
+    bool fresh_r0 = true, fresh_r1 = true;
+#pragma unroll
+    for (int p = 0; p < 2 * T_MAX; ++p) {
+      if (p < 2 * T) {
+        const float* ptr = (p & 1) ? po1[p >> 1] : po0[p >> 1];
+        if (fresh_r0 && rows_o[p] == row_r0) { pr0 = ptr; fresh_r0 = false; }
+        if (fresh_r1 && rows_o[p] == row_r1) { pr1 = ptr; fresh_r1 = false; }
+      }
+    }
+    if (fresh_r1 && row_r1 == row_r0) { pr1 = pr0; fresh_r1 = false; }
+    if (fresh_r0) tx += frame_bytes;
+    if (fresh_r1) tx += frame_bytes;
+
+    const float* g_state = a.body_state + (size_t)env * a.bodies_per_env * kBodyRec;
+    const uint32_t state_bytes = (uint32_t)(J * kBodyRec) * 4u;
+    if (lane == 0) {
+      if (state_bulk_ok) tx += state_bytes;
+      mbar_arrive_expect_tx(bar, tx);
+      if (state_bulk_ok) bulk_g2s(s_state, g_state, state_bytes, bar);
+      if (fresh_r0) bulk_g2s(s_rslots, a.lib.frames_body + (size_t)row_r0 * BS, frame_bytes, bar);
+      if (fresh_r1) bulk_g2s(s_rslots + BS, a.lib.frames_body + (size_t)row_r1 * BS, frame_bytes, bar);
+#pragma unroll
+      for (int k = 0; k < 2 * T_MAX; ++k)
+        if (k < 2 * T && fresh_o[k])
+          bulk_g2s(s_oslots + k * BS, a.lib.frames_body + (size_t)rows_o[k] * BS, frame_bytes, bar);
+    }
+    if (!state_bulk_ok) {      // bodies_per_env not a multiple of 4: rows are only 4-byte aligned
+      for (int i = lane; i < J * kBodyRec; i += 32) s_state[i] = g_state[i];
+    }
+  }
+
+  // ---- while the copies fly: dof state / force (power reward + AMP joint inputs) ---------------------------
+  float power = 0.0f;
+  {
+    const float2* g_dof = reinterpret_cast<const float2*>(a.dof_state) + (size_t)env * D;
+    const float* g_force = a.dof_force ? a.dof_force + (size_t)env * D : nullptr;
+    for (int d = lane; d < D; d += 32) {
+      const float2 pv = g_dof[d];
+      s_dof[2 * d] = pv.x;
+      s_dof[2 * d + 1] = pv.y;
+      if (g_force) power += fabsf(g_force[d] * pv.y);
+    }
+  }
+  __syncwarp();
+  mbar_wait(bar, 0);
+
+  // ================= phase A: everything that reads the reward slots / simulator block =======================
+  const bool has_body = lane < J;
+  const int j = has_body ? lane : 0;
+  const BodyRec sim = load_body(s_state + j * kBodyRec);        // stride-13 words: bank-conflict free
+  const V3 root_p = v3(s_state[0], s_state[1], s_state[2]);
+  const bool has_h = a.flags & PHC_FLAG_ROOT_HEIGHT_OBS;
+  const int base0 = has_h ? 1 : 0;
+
+  // heading frame of the simulated root
+  Q4 root_q = q4(s_state[3], s_state[4], s_state[5], s_state[6]);
+  if (!(a.flags & PHC_FLAG_UPRIGHT)) root_q = strip_base_rot(root_q);
+  const float heading = heading_angle(root_q);
+  const Q4 hinv = quat_about_z(-heading);
+  const Q4 hq = quat_about_z(heading);
+
+  // reward + termination against the reference pose at t_now
+  float e_pos = 0.f, e_rot = 0.f, e_vel = 0.f, e_ang = 0.f, dist = 0.f;
+  {
+    const BodyRec ref = blend_body(pr0 + j * kBodyRec, pr1 + j * kBodyRec, br_r.blend, goff);
+    if (has_body) {
+      const V3 dp = ref.p - sim.p, dv = ref.v - sim.v, dw = ref.w - sim.w;
+      const float sp = dp.x * dp.x + dp.y * dp.y + dp.z * dp.z;
+      e_pos = sp / 3.0f;
+      e_vel = (dv.x * dv.x + dv.y * dv.y + dv.z * dv.z) / 3.0f;
+      e_ang = (dw.x * dw.x + dw.y * dw.y + dw.z * dw.z) / 3.0f;
+      const float ang = quat_angle(qmul(ref.q, qconj(sim.q)));
+      e_rot = ang * ang;
+      dist = sqrtf(sp);
+    }
+  }
+  bool fallen;
+  {
+    const float thr = has_body ? a.term_thresh[j] : INFINITY;
+    if (a.flags & PHC_FLAG_TERM_USE_MEAN) {
+      const bool in_set = has_body && thr < INFINITY;
+      const float cnt = warp_sum(in_set ? 1.0f : 0.0f);
+      const float sum = warp_sum(in_set ? dist : 0.0f);
+      fallen = (sum / cnt) > a.term_dist_mean;
+    } else {
+      fallen = __any_sync(0xffffffffu, has_body && dist > thr);
+    }
+  }
+  e_pos = warp_sum(e_pos) / (float)J;
+  e_rot = warp_sum(e_rot) / (float)J;
+  e_vel = warp_sum(e_vel) / (float)J;
+  e_ang = warp_sum(e_ang) / (float)J;
+  power = warp_sum(power);
+
+  if (lane == 0) {
+    const float r_pos = expf(-a.k_pos * e_pos), r_rot = expf(-a.k_rot * e_rot);
+    const float r_vel = expf(-a.k_vel * e_vel), r_ang = expf(-a.k_ang_vel * e_ang);
+    float rew = a.w_pos * r_pos + a.w_rot * r_rot + a.w_vel * r_vel + a.w_ang_vel * r_ang;
+    const bool has_power = a.flags & PHC_FLAG_POWER_REWARD;
+    const int rw = has_power ? 5 : 4;
+    float* raw = a.reward_raw + (size_t)env * rw;
+    raw[0] = r_pos; raw[1] = r_rot; raw[2] = r_vel; raw[3] = r_ang;
+    if (has_power) {
+      float pr = -a.power_coef * power;
+      if (progress <= 3) pr = 0.0f;
+      rew = rew + pr;
+      raw[4] = pr;
+    }
+    a.rew[env] = rew;
+    // compute_humanoid_im_reset + the is_recovery override
+    const bool pass_time = t_now >= m_len;
+    int64_t terminated = 0;
+    if (a.flags & PHC_FLAG_EARLY_TERM) {
+      bool f = fallen && (progress > 1);
+      if (a.flags & PHC_FLAG_NO_COLLISION) f = false;
+      terminated = f ? 1 : 0;
+    }
+    int64_t reset = pass_time ? 1 : terminated;
+    if (a.cycle_counter && !pass_time && a.cycle_counter[env] > 0) { reset = 0; terminated = 0; }
+    a.reset[env] = reset;
+    a.terminate[env] = terminated;
+  }
+
+  // AMP observation of the simulated character (build_amp_observations_smpl) -> its own staging row
+  if (a.amp_out) {
+    const int nj = a.num_amp_joints, nk = a.num_key_bodies;
+    float* o = s_amp + base0;
+    if (lane == 0) {
+      if (has_h) s_amp[0] = root_p.z;
+      st6(o, tan_norm((a.flags & PHC_FLAG_LOCAL_ROOT_OBS) ? qmul(hinv, root_q) : root_q));
+      st3(o + 6, qrot(hinv, sim.v));      // lane 0 holds body 0 = the root
+      st3(o + 9, qrot(hinv, sim.w));
+    }
+    for (int k = lane; k < nj; k += 32) {
+      const int jid = a.amp_joints[k];
+      const float* dj = s_dof + 6 * jid;             // (pos, vel) pairs of the joint's 3 dofs
+      st6(o + 12 + 6 * k, tan_norm(exp_map_to_quat(v3(dj[0], dj[2], dj[4]))));
+      st3(o + 12 + 6 * nj + 3 * k, v3(dj[1], dj[3], dj[5]));
+    }
+    if (lane < nk) {
+      const float* kb = s_state + a.key_bodies[lane] * kBodyRec;
+      st3(o + 12 + 9 * nj + 3 * lane, qrot(hinv, v3(kb[0], kb[1], kb[2]) - root_p));
+    }
+  }
+  __syncwarp();   // the reward slots and the simulator block are consumed: the obs row may overwrite them
+
+  // ================= phase B: observation row (reads only registers + the observation slots) =================
+  if (lane == 0 && has_h) s_obs[0] = root_p.z;
+  if (has_body) {
+    // self observation (compute_humanoid_observations_smpl_max)
+    float* o_pos = s_obs + base0;
+    float* o_rot = o_pos + 3 * (J - 1);
+    float* o_vel = o_rot + 6 * J;
+    float* o_ang = o_vel + 3 * J;
+    if (j > 0) st3(o_pos + 3 * (j - 1), qrot(hinv, sim.p - root_p));
+    TanNorm tn = tan_norm(qmul(hinv, sim.q));
+    if (j == 0 && !(a.flags & PHC_FLAG_LOCAL_ROOT_OBS)) tn = tan_norm(root_q);
+    st6(o_rot + 6 * j, tn);
+    st3(o_vel + 3 * j, qrot(hinv, sim.v));
+    st3(o_ang + 3 * j, qrot(hinv, sim.w));
+  }
+  // task observation v6 for each of the T reference samples
+#pragma unroll
+  for (int t = 0; t < T_MAX; ++t) {
+    if (t < T && has_body) {
+      const BodyRec ref = blend_body(po0[t] + j * kBodyRec, po1[t] + j * kBodyRec, bl_o[t], goff);
+      float* tb = s_obs + self_dim + t * 24 * J;
+      st3(tb + 3 * j, qrot(hinv, ref.p - sim.p));
+      st6(tb + 3 * J + 6 * j, tan_norm(qmul(qmul(hinv, qmul(ref.q, qconj(sim.q))), hq)));
+      st3(tb + 9 * J + 3 * j, qrot(hinv, ref.v - sim.v));
+      st3(tb + 12 * J + 3 * j, qrot(hinv, ref.w - sim.w));
+      st3(tb + 15 * J + 3 * j, qrot(hinv, ref.p - root_p));
+      st6(tb + 18 * J + 6 * j, tan_norm(qmul(hinv, ref.q)));
+      if (t == 0) {     // side buffers of _compute_task_obs(save_buffer=True)
+        const size_t bj = (size_t)env * J + j;
+        if (a.ref_body_pos) st3(a.ref_body_pos + 3 * bj, ref.p);
+        if (a.ref_body_vel) st3(a.ref_body_vel + 3 * bj, ref.v);
+        if (a.ref_body_ang_vel) st3(a.ref_body_ang_vel + 3 * bj, ref.w);
+        if (a.ref_body_rot) { float* d = a.ref_body_rot + 4 * bj; d[0] = ref.q.x; d[1] = ref.q.y; d[2] = ref.q.z; d[3] = ref.q.w; }
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- rows leave shared memory with coalesced stores -------------------------------------------------------
+  {
+    float* g = a.obs + (size_t)env * a.obs_stride;
+    if (((a.obs_stride | (int64_t)obs_dim) & 1) == 0) {          // rows 8-byte aligned: float2 stores
+      float2* g2 = reinterpret_cast<float2*>(g);
+      const float2* s2 = reinterpret_cast<const float2*>(s_obs);
+      for (int i = lane; i < obs_dim / 2; i += 32) g2[i] = s2[i];
+    } else {
+      for (int i = lane; i < obs_dim; i += 32) g[i] = s_obs[i];
+    }
+  }
+  if (a.amp_out) {
+    float* g = a.amp_out + (size_t)env * a.amp_out_stride;
+    if (a.amp_hist_in) {
+      // newest-first window shift: slot s -> s+1, walking from the oldest slot so an in-place shift is safe
+      // (each element is read and later overwritten by the SAME lane, program order keeps it correct)
+      const float* h = a.amp_hist_in + (size_t)env * a.amp_out_stride;
+      for (int s = a.amp_steps - 2; s >= 0; --s)
+        for (int i = lane; i < amp_dim; i += 32) g[(size_t)(s + 1) * amp_dim + i] = h[(size_t)s * amp_dim + i];
+    }
+    for (int i = lane; i < amp_dim; i += 32) g[i] = s_amp[i];
+  }
+}
+
+}  // namespace phc
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" void phc_set_error(const char* msg);   // phc_api.cu
+extern "C" int phc_check_cuda(cudaError_t e, const char* what);
+
+extern "C" int phc_self_obs_dim(int32_t J, uint32_t flags) {
+  return ((flags & PHC_FLAG_ROOT_HEIGHT_OBS) ? 1 : 0) + 15 * J - 3;
+}
+extern "C" int phc_task_obs_dim(int32_t J, int32_t T) { return 24 * J * T; }
+extern "C" int phc_amp_obs_dim(int32_t nj, int32_t nk, uint32_t flags) {
+  return ((flags & PHC_FLAG_ROOT_HEIGHT_OBS) ? 1 : 0) + 12 + 9 * nj + 3 * nk;
+}
+
+extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
+  using namespace phc;
+  if (!a) { phc_set_error("phc_env_step: args is NULL"); return PHC_ERR_INVALID_ARG; }
+  if (a->num_envs == 0) return PHC_OK;
+  const int J = a->lib.num_bodies, T = a->time_steps;
+  if (!a->body_state || !a->dof_state || !a->progress || !a->motion_ids || !a->start_times || !a->start_offsets ||
+      !a->global_offset || !a->lib.frames_body || !a->lib.motion_len || !a->lib.motion_dt ||
+      !a->lib.motion_num_frames || !a->lib.length_starts || !a->obs || !a->rew || !a->reward_raw || !a->reset ||
+      !a->terminate || !a->term_thresh) {
+    phc_set_error("phc_env_step: a required pointer is NULL");
+    return PHC_ERR_INVALID_ARG;
+  }
+  if (a->num_envs < 0 || J < 1 || a->bodies_per_env < J || T < 1) {
+    phc_set_error("phc_env_step: bad sizes (num_envs >= 0, 1 <= J <= bodies_per_env, T >= 1)");
+    return PHC_ERR_INVALID_ARG;
+  }
+  if (J > 32) { phc_set_error("phc_env_step: num_bodies > 32 needs the multi-body-per-lane path (not built yet)"); return PHC_ERR_UNSUPPORTED; }
+  if (T > 4) { phc_set_error("phc_env_step: time_steps > 4 not supported"); return PHC_ERR_UNSUPPORTED; }
+  if ((a->flags & PHC_FLAG_POWER_REWARD) && !a->dof_force) { phc_set_error("phc_env_step: power reward needs dof_force"); return PHC_ERR_INVALID_ARG; }
+  if (a->num_key_bodies < 0 || a->num_key_bodies > PHC_MAX_KEY_BODIES || a->num_amp_joints < 0 || (a->num_amp_joints > 0 && !a->amp_joints)) {
+    phc_set_error("phc_env_step: bad key body / amp joint lists"); return PHC_ERR_INVALID_ARG;
+  }
+  if (a->lib.body_stride != phc_motion_body_stride(J) || (reinterpret_cast<uintptr_t>(a->lib.frames_body) & 15)) {
+    phc_set_error("phc_env_step: frames_body must be 16-byte aligned with body_stride = round_up(13*J,4) (use phc_motion_pack)");
+    return PHC_ERR_INVALID_ARG;
+  }
+  if (reinterpret_cast<uintptr_t>(a->dof_state) & 7) { phc_set_error("phc_env_step: dof_state must be 8-byte aligned"); return PHC_ERR_INVALID_ARG; }
+  const int self_dim = phc_self_obs_dim(J, a->flags);
+  const int obs_dim = self_dim + phc_task_obs_dim(J, T);
+  const int amp_dim = a->amp_out ? phc_amp_obs_dim(a->num_amp_joints, a->num_key_bodies, a->flags) : 0;
+  if (a->obs_stride < obs_dim) { phc_set_error("phc_env_step: obs_stride smaller than the observation"); return PHC_ERR_INVALID_ARG; }
+  if (a->amp_out && (a->amp_steps < 1 || a->amp_out_stride < (int64_t)(a->amp_hist_in ? a->amp_steps : 1) * amp_dim)) {
+    phc_set_error("phc_env_step: amp_out_stride / amp_steps inconsistent"); return PHC_ERR_INVALID_ARG;
+  }
+  // the obs row is staged over [reward slots | simulator block] when it fits (always for T == 1)
+  const bool alias_obs = (2 * a->lib.body_stride + round4(J * kBodyRec) >= obs_dim);
+  const bool obs_row_aligned = ((reinterpret_cast<uintptr_t>(a->obs) & 7) == 0);
+  if (!obs_row_aligned) { phc_set_error("phc_env_step: obs must be 8-byte aligned"); return PHC_ERR_INVALID_ARG; }
+  // TMA bulk copy of the per-env simulator block needs 16-byte aligned rows of a multiple of 16 bytes
+  const bool state_bulk_ok = ((reinterpret_cast<uintptr_t>(a->body_state) & 15) == 0) &&
+                             ((a->bodies_per_env * kBodyRec) % 4 == 0) && ((J * kBodyRec) % 4 == 0);
+  const StepLayout L = make_layout(J, T, a->lib.body_stride, amp_dim, obs_dim, alias_obs);
+  const size_t smem = (size_t)kWarpsPerCta * L.total * sizeof(float);
+  const int grid = (a->num_envs + kWarpsPerCta - 1) / kWarpsPerCta;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+#define PHC_LAUNCH_STEP(TM)                                                                                      \
+  do {                                                                                                           \
+    static bool attr_set = false;                                                                                \
+    if (!attr_set || smem > 48 * 1024) {                                                                         \
+      e = cudaFuncSetAttribute(env_step_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+      if (e != cudaSuccess) return phc_check_cuda(e, "cudaFuncSetAttribute(env_step_kernel)");                   \
+      attr_set = true;                                                                                           \
+    }                                                                                                            \
+    env_step_kernel<TM><<<grid, kWarpsPerCta * 32, smem, st>>>(*a, obs_dim, self_dim, amp_dim, alias_obs,        \
+                                                                state_bulk_ok);                                  \
+  } while (0)
+  if (T == 1) PHC_LAUNCH_STEP(1);
+  else PHC_LAUNCH_STEP(4);
+#undef PHC_LAUNCH_STEP
+  return phc_check_cuda(cudaGetLastError(), "env_step_kernel launch");
+}

@@ -1,0 +1,256 @@
+// Motion-library kernels: table packing, the general get_motion_state query and the AMP "demo" observation of
+// the reference motion.  Reference: phc/utils/motion_lib_base.py:300-307 (tables), :437-520 (get_motion_state),
+// :549-567 (_calc_frame_blend, _local_rotation_to_dof_smpl); phc/env/tasks/humanoid_amp.py:253-284, :575-603, :966-1011.
+//
+// These are the off-step paths (episode resets, discriminator demo batches): one warp per query, lane = body,
+// plain cached loads of the packed records (a frame bracket is 2 x 1.2 KB contiguous).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/phc_b200.h"
+#include "phc_common.cuh"
+#include "phc_math.cuh"
+
+extern "C" void phc_set_error(const char* msg);
+extern "C" int phc_check_cuda(cudaError_t e, const char* what);
+
+namespace phc {
+
+constexpr int kRec = 13;
+
+__global__ void motion_pack_kernel(const float* __restrict__ gts, const float* __restrict__ grs,
+                                   const float* __restrict__ gvs, const float* __restrict__ gavs,
+                                   const float* __restrict__ lrs, const float* __restrict__ dvs, int64_t F, int J,
+                                   int BS, int JS, float* __restrict__ fb, float* __restrict__ fj) {
+  const int64_t total = F * J;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = i / J;
+    const int j = (int)(i - f * J);
+    float* o = fb + f * BS + j * kRec;
+    const float* p = gts + i * 3;
+    const float* q = grs + i * 4;
+    const float* v = gvs + i * 3;
+    const float* w = gavs + i * 3;
+    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+    o[3] = q[0]; o[4] = q[1]; o[5] = q[2]; o[6] = q[3];
+    o[7] = v[0]; o[8] = v[1]; o[9] = v[2];
+    o[10] = w[0]; o[11] = w[1]; o[12] = w[2];
+    if (j == 0) for (int k = J * kRec; k < BS; ++k) fb[f * BS + k] = 0.0f;
+    if (fj) {
+      float* oj = fj + f * JS;
+      const float* lq = lrs + i * 4;
+      oj[4 * j + 0] = lq[0]; oj[4 * j + 1] = lq[1]; oj[4 * j + 2] = lq[2]; oj[4 * j + 3] = lq[3];
+      if (j > 0) {
+        const float* dv = dvs + (f * (J - 1) + (j - 1)) * 3;
+        float* od = oj + 4 * J + 3 * (j - 1);
+        od[0] = dv[0]; od[1] = dv[1]; od[2] = dv[2];
+      } else {
+        for (int k = 4 * J + 3 * (J - 1); k < JS; ++k) oj[k] = 0.0f;
+      }
+    }
+  }
+}
+
+struct BodyS { V3 p; Q4 q; V3 v; V3 w; };
+__device__ __forceinline__ BodyS ld_body(const float* s) {
+  BodyS b;
+  b.p = v3(s[0], s[1], s[2]); b.q = q4(s[3], s[4], s[5], s[6]); b.v = v3(s[7], s[8], s[9]); b.w = v3(s[10], s[11], s[12]);
+  return b;
+}
+
+// One reference-motion sample for lane `j`: blended body record + joint (dof) position/velocity of joint j-1.
+struct MotionSample { BodyS body; V3 dof_pos; V3 dof_vel; };
+
+__device__ __forceinline__ MotionSample sample_motion(const PhcMotionLib& lib, int64_t mid, float time, V3 off, int j,
+                                                      bool want_joint) {
+  const Bracket b = frame_bracket(time, lib.motion_len[mid], lib.motion_num_frames[mid], lib.motion_dt[mid]);
+  const int64_t r0 = lib.length_starts[mid] + b.i0, r1 = lib.length_starts[mid] + b.i1;
+  const float bl = b.blend, omb = 1.0f - bl;
+  const BodyS a0 = ld_body(lib.frames_body + r0 * lib.body_stride + j * kRec);
+  const BodyS a1 = ld_body(lib.frames_body + r1 * lib.body_stride + j * kRec);
+  MotionSample s;
+  s.body.p = lerp3(a0.p, a1.p, omb, bl) + off;
+  s.body.v = lerp3(a0.v, a1.v, omb, bl);
+  s.body.w = lerp3(a0.w, a1.w, omb, bl);
+  s.body.q = slerp(a0.q, a1.q, bl);
+  s.dof_pos = v3(0.f, 0.f, 0.f);
+  s.dof_vel = v3(0.f, 0.f, 0.f);
+  if (want_joint && lib.frames_joint) {
+    const int J = lib.num_bodies;
+    const float* j0 = lib.frames_joint + r0 * lib.joint_stride;
+    const float* j1 = lib.frames_joint + r1 * lib.joint_stride;
+    const Q4 l0 = q4(j0[4 * j], j0[4 * j + 1], j0[4 * j + 2], j0[4 * j + 3]);
+    const Q4 l1 = q4(j1[4 * j], j1[4 * j + 1], j1[4 * j + 2], j1[4 * j + 3]);
+    const Q4 lq = slerp(l0, l1, bl);
+    if (j > 0) {
+      s.dof_pos = quat_to_exp_map(lq);
+      const float* d0 = j0 + 4 * J + 3 * (j - 1);
+      const float* d1 = j1 + 4 * J + 3 * (j - 1);
+      s.dof_vel = lerp3(v3(d0[0], d0[1], d0[2]), v3(d1[0], d1[1], d1[2]), omb, bl);
+    }
+  }
+  return s;
+}
+
+__device__ __forceinline__ void st3g(float* d, V3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
+__device__ __forceinline__ void st4g(float* d, Q4 q) { d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w; }
+
+__global__ void __launch_bounds__(128)
+motion_state_kernel(const __grid_constant__ PhcMotionLib lib, const int64_t* __restrict__ ids,
+                    const float* __restrict__ times, const float* __restrict__ offset, int64_t n,
+                    const __grid_constant__ PhcMotionStateOut out) {
+  const int64_t qi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (qi >= n) return;
+  const int J = lib.num_bodies;
+  if (lane >= J) return;
+  const V3 off = offset ? v3(offset[3 * qi], offset[3 * qi + 1], offset[3 * qi + 2]) : v3(0.f, 0.f, 0.f);
+  const bool want_joint = (out.dof_pos != nullptr) || (out.dof_vel != nullptr);
+  MotionSample s = sample_motion(lib, ids[qi], times[qi], v3(0.f, 0.f, 0.f), lane, want_joint);
+  if (offset) s.body.p = s.body.p + off;          // the reference adds the offset only when one is given
+  const int64_t bj = qi * J + lane;
+  if (out.rg_pos) st3g(out.rg_pos + 3 * bj, s.body.p);
+  if (out.rb_rot) st4g(out.rb_rot + 4 * bj, s.body.q);
+  if (out.body_vel) st3g(out.body_vel + 3 * bj, s.body.v);
+  if (out.body_ang_vel) st3g(out.body_ang_vel + 3 * bj, s.body.w);
+  if (lane > 0) {
+    const int64_t dj = qi * (J - 1) + (lane - 1);
+    if (out.dof_pos) st3g(out.dof_pos + 3 * dj, s.dof_pos);
+    if (out.dof_vel) st3g(out.dof_vel + 3 * dj, s.dof_vel);
+  } else {
+    if (out.root_pos) st3g(out.root_pos + 3 * qi, s.body.p);
+    if (out.root_rot) st4g(out.root_rot + 4 * qi, s.body.q);
+    if (out.root_vel) st3g(out.root_vel + 3 * qi, s.body.v);
+    if (out.root_ang_vel) st3g(out.root_ang_vel + 3 * qi, s.body.w);
+  }
+}
+
+struct AmpDemoArgs {
+  PhcMotionLib lib;
+  const int64_t* ids;
+  const float* times0;
+  int64_t n;
+  int32_t first_step, num_steps;
+  float dt;
+  uint32_t flags;
+  int32_t key_bodies[PHC_MAX_KEY_BODIES];
+  int32_t num_key_bodies;
+  const int32_t* amp_joints;
+  int32_t num_amp_joints;
+  float* out;
+  int64_t out_stride;
+};
+
+// warp per (sample, history step): motion sample at t0 - (first_step + k) dt, then build_amp_observations_smpl
+__global__ void __launch_bounds__(128) amp_demo_kernel(const __grid_constant__ AmpDemoArgs a) {
+  const int64_t wi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wi >= a.n * a.num_steps) return;
+  const int64_t si = wi / a.num_steps;
+  const int k = (int)(wi - si * a.num_steps);
+  const int J = a.lib.num_bodies;
+  // motion_times0 + (-dt * (k + first)) : humanoid_amp.py:257-261 / :577-582
+  const float t = a.times0[si] + (-a.dt * (float)(k + a.first_step));
+  const int j = lane < J ? lane : 0;
+  const MotionSample s = sample_motion(a.lib, a.ids[si], t, v3(0.f, 0.f, 0.f), j, true);
+  // root record broadcast from lane 0
+  BodyS r;
+  r.p = v3(__shfl_sync(0xffffffffu, s.body.p.x, 0), __shfl_sync(0xffffffffu, s.body.p.y, 0), __shfl_sync(0xffffffffu, s.body.p.z, 0));
+  r.q = q4(__shfl_sync(0xffffffffu, s.body.q.x, 0), __shfl_sync(0xffffffffu, s.body.q.y, 0), __shfl_sync(0xffffffffu, s.body.q.z, 0), __shfl_sync(0xffffffffu, s.body.q.w, 0));
+  r.v = v3(__shfl_sync(0xffffffffu, s.body.v.x, 0), __shfl_sync(0xffffffffu, s.body.v.y, 0), __shfl_sync(0xffffffffu, s.body.v.z, 0));
+  r.w = v3(__shfl_sync(0xffffffffu, s.body.w.x, 0), __shfl_sync(0xffffffffu, s.body.w.y, 0), __shfl_sync(0xffffffffu, s.body.w.z, 0));
+  if (lane >= J) return;
+
+  const bool upright = a.flags & PHC_FLAG_UPRIGHT, has_h = a.flags & PHC_FLAG_ROOT_HEIGHT_OBS;
+  const Q4 root_q = upright ? r.q : strip_base_rot(r.q);
+  const Q4 hinv = quat_about_z(-heading_angle(root_q));
+  const int nj = a.num_amp_joints, nk = a.num_key_bodies;
+  float* o = a.out + si * a.out_stride + (int64_t)k * (has_h + 12 + 9 * nj + 3 * nk) + (has_h ? 1 : 0);
+  if (lane == 0) {
+    if (has_h) o[-1] = r.p.z;
+    const TanNorm tn = tan_norm((a.flags & PHC_FLAG_LOCAL_ROOT_OBS) ? qmul(hinv, root_q) : root_q);
+    st3g(o, tn.t); st3g(o + 3, tn.n);
+    st3g(o + 6, qrot(hinv, r.v));
+    st3g(o + 9, qrot(hinv, r.w));
+  } else {
+    for (int kk = 0; kk < nj; ++kk)
+      if (a.amp_joints[kk] == lane - 1) {
+        const TanNorm tn = tan_norm(exp_map_to_quat(s.dof_pos));
+        st3g(o + 12 + 6 * kk, tn.t); st3g(o + 12 + 6 * kk + 3, tn.n);
+        st3g(o + 12 + 6 * nj + 3 * kk, s.dof_vel);
+      }
+  }
+  for (int kk = 0; kk < nk; ++kk)
+    if (a.key_bodies[kk] == lane) st3g(o + 12 + 9 * nj + 3 * kk, qrot(hinv, s.body.p - r.p));
+}
+
+}  // namespace phc
+
+extern "C" int phc_motion_body_stride(int32_t J) { return (13 * J + 3) & ~3; }
+extern "C" int phc_motion_joint_stride(int32_t J) { return (4 * J + 3 * (J - 1) + 3) & ~3; }
+
+extern "C" int phc_motion_pack(const float* gts, const float* grs, const float* gvs, const float* gavs,
+                               const float* lrs, const float* dvs, int64_t F, int32_t J, float* fb, float* fj,
+                               void* stream) {
+  if (!gts || !grs || !gvs || !gavs || !fb || F < 0 || J < 1) { phc_set_error("phc_motion_pack: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  if ((reinterpret_cast<uintptr_t>(fb) & 15) || (fj && (reinterpret_cast<uintptr_t>(fj) & 15))) {
+    phc_set_error("phc_motion_pack: packed tables must be 16-byte aligned"); return PHC_ERR_INVALID_ARG;
+  }
+  if (F == 0) return PHC_OK;
+  const bool joint = fj && lrs && dvs;
+  const int64_t total = F * J;
+  const int block = 256;
+  const int grid = (int)((total + block - 1) / block < 148 * 16 ? (total + block - 1) / block : 148 * 16);
+  phc::motion_pack_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      gts, grs, gvs, gavs, lrs, dvs, F, J, phc_motion_body_stride(J), phc_motion_joint_stride(J), fb, joint ? fj : nullptr);
+  return phc_check_cuda(cudaGetLastError(), "motion_pack_kernel launch");
+}
+
+static int check_lib(const PhcMotionLib* lib, const char* who) {
+  if (!lib || !lib->frames_body || !lib->motion_len || !lib->motion_dt || !lib->motion_num_frames || !lib->length_starts) {
+    phc_set_error("motion library has NULL tables"); return PHC_ERR_INVALID_ARG;
+  }
+  if (lib->num_bodies < 1 || lib->body_stride != phc_motion_body_stride(lib->num_bodies) ||
+      (lib->frames_joint && lib->joint_stride != phc_motion_joint_stride(lib->num_bodies))) {
+    phc_set_error("motion library strides do not match num_bodies (use phc_motion_pack)"); return PHC_ERR_INVALID_ARG;
+  }
+  if (lib->num_bodies > 32) { phc_set_error("num_bodies > 32 not supported yet"); return PHC_ERR_UNSUPPORTED; }
+  (void)who;
+  return PHC_OK;
+}
+
+extern "C" int phc_motion_state(const PhcMotionLib* lib, const int64_t* ids, const float* times, const float* offset,
+                                int64_t n, const PhcMotionStateOut* out, void* stream) {
+  int rc = check_lib(lib, "phc_motion_state");
+  if (rc) return rc;
+  if (!ids || !times || !out || n < 0) { phc_set_error("phc_motion_state: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  if ((out->dof_pos || out->dof_vel) && !lib->frames_joint) { phc_set_error("phc_motion_state: dof outputs need frames_joint"); return PHC_ERR_INVALID_ARG; }
+  if (n == 0) return PHC_OK;
+  const int wpb = 4;
+  const int64_t grid = (n + wpb - 1) / wpb;
+  phc::motion_state_kernel<<<(unsigned)grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(*lib, ids, times, offset, n, *out);
+  return phc_check_cuda(cudaGetLastError(), "motion_state_kernel launch");
+}
+
+extern "C" int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* ids, const float* times0, int64_t n,
+                                int32_t first_step, int32_t num_steps, float dt, uint32_t flags,
+                                const int32_t* key_bodies, int32_t nk, const int32_t* amp_joints, int32_t nj, float* out,
+                                int64_t out_stride, void* stream) {
+  int rc = check_lib(lib, "phc_amp_obs_demo");
+  if (rc) return rc;
+  if (!lib->frames_joint) { phc_set_error("phc_amp_obs_demo: needs frames_joint"); return PHC_ERR_INVALID_ARG; }
+  if (!ids || !times0 || !out || n < 0 || num_steps < 1 || nk < 0 || nk > PHC_MAX_KEY_BODIES || nj < 0 || (nj > 0 && !amp_joints) || (nk > 0 && !key_bodies)) {
+    phc_set_error("phc_amp_obs_demo: bad arguments"); return PHC_ERR_INVALID_ARG;
+  }
+  const int A = phc_amp_obs_dim(nj, nk, flags);
+  if (out_stride < (int64_t)num_steps * A) { phc_set_error("phc_amp_obs_demo: out_stride too small"); return PHC_ERR_INVALID_ARG; }
+  if (n == 0) return PHC_OK;
+  phc::AmpDemoArgs a;
+  a.lib = *lib; a.ids = ids; a.times0 = times0; a.n = n; a.first_step = first_step; a.num_steps = num_steps; a.dt = dt;
+  a.flags = flags; a.num_key_bodies = nk; a.amp_joints = amp_joints; a.num_amp_joints = nj; a.out = out; a.out_stride = out_stride;
+  for (int i = 0; i < PHC_MAX_KEY_BODIES; ++i) a.key_bodies[i] = i < nk ? key_bodies[i] : -1;
+  const int wpb = 4;
+  const int64_t warps = n * num_steps;
+  phc::amp_demo_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return phc_check_cuda(cudaGetLastError(), "amp_demo_kernel launch");
+}

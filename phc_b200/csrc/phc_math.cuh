@@ -1,0 +1,154 @@
+// Quaternion / exp-map arithmetic of the PHC hot path, one scalar op per reference tensor op.
+//
+// Reference: phc/utils/isaacgym_torch_utils.py (quat_mul :25-45, normalize :49-50, quat_conjugate :93-96,
+// quat_from_angle_axis :104-108, normalize_angle :111-112) and phc/utils/torch_utils.py (my_quat_rotate :46-55,
+// quat_to_angle_axis :58-78, quat_to_tan_norm :101-113, exp_map_to_angle_axis :147-166, slerp :176-197,
+// calc_heading* :200-240).  Quaternions are xyzw.
+//
+// Numerics contract: every expression keeps the reference's operation ORDER and this translation unit is
+// compiled with -fmad=false (no FMA contraction), IEEE div/sqrt and the accurate libm entry points (acosf,
+// atan2f, sinf, cosf -- never the __ fast intrinsics): 2*acos(w) is ill-conditioned near identity, so a
+// re-associated product changes per-body angles at the 1e-4 level.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PHC_HD __host__ __device__ __forceinline__
+#else
+#define PHC_HD inline
+#endif
+
+namespace phc {
+
+struct V3 { float x, y, z; };
+struct Q4 { float x, y, z, w; };
+
+PHC_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+PHC_HD Q4 q4(float x, float y, float z, float w) { Q4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+PHC_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+PHC_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+
+// (1-b)*a0 + b*a1, the reference's lerp expression (motion_lib_base.py:474-480)
+PHC_HD float lerp1(float a0, float a1, float omb, float b) { return omb * a0 + b * a1; }
+PHC_HD V3 lerp3(V3 a0, V3 a1, float omb, float b) {
+  return v3(lerp1(a0.x, a1.x, omb, b), lerp1(a0.y, a1.y, omb, b), lerp1(a0.z, a1.z, omb, b));
+}
+
+PHC_HD Q4 qmul(Q4 a, Q4 b) {
+  const float ww = (a.z + a.x) * (b.x + b.y);
+  const float yy = (a.w - a.y) * (b.w + b.z);
+  const float zz = (a.w + a.y) * (b.w - b.z);
+  const float xx = ww + yy + zz;
+  const float qq = 0.5f * (xx + (a.z - a.x) * (b.x - b.y));
+  Q4 r;
+  r.w = qq - ww + (a.z - a.y) * (b.y - b.z);
+  r.x = qq - xx + (a.x + a.w) * (b.x + b.w);
+  r.y = qq - yy + (a.w - a.x) * (b.y + b.z);
+  r.z = qq - zz + (a.z + a.y) * (b.w - b.x);
+  return r;
+}
+
+PHC_HD Q4 qconj(Q4 q) { return q4(-q.x, -q.y, -q.z, q.w); }
+
+// v*(2w^2-1) + (qv x v)*w*2 + qv*(qv.v)*2
+PHC_HD V3 qrot(Q4 q, V3 v) {
+  const float s = 2.0f * (q.w * q.w) - 1.0f;
+  const float cx = q.y * v.z - q.z * v.y;
+  const float cy = q.z * v.x - q.x * v.z;
+  const float cz = q.x * v.y - q.y * v.x;
+  const float d = q.x * v.x + q.y * v.y + q.z * v.z;
+  V3 r;
+  r.x = (v.x * s + cx * q.w * 2.0f) + q.x * d * 2.0f;
+  r.y = (v.y * s + cy * q.w * 2.0f) + q.y * d * 2.0f;
+  r.z = (v.z * s + cz * q.w * 2.0f) + q.z * d * 2.0f;
+  return r;
+}
+
+// heading = atan2 of the rotated x axis; quat_from_angle_axis(+-heading, z) incl. its final re-normalisation
+PHC_HD float heading_angle(Q4 q) {
+  const V3 d = qrot(q, v3(1.0f, 0.0f, 0.0f));
+  return atan2f(d.y, d.x);
+}
+
+PHC_HD Q4 quat_about_z(float angle) {
+  const float th = angle / 2.0f;
+  const float s = sinf(th), c = cosf(th);
+  float n = sqrtf(s * s + c * c);
+  n = n < 1e-9f ? 1e-9f : n;
+  return q4(0.0f, 0.0f, s / n, c / n);
+}
+
+struct TanNorm { V3 t, n; };
+PHC_HD TanNorm tan_norm(Q4 q) {
+  TanNorm r;
+  r.t = qrot(q, v3(1.0f, 0.0f, 0.0f));
+  r.n = qrot(q, v3(0.0f, 0.0f, 1.0f));
+  return r;
+}
+
+PHC_HD float wrap_angle(float x) { return atan2f(sinf(x), cosf(x)); }
+
+// quat_to_angle_axis: angle only (what the tracking reward reads) ...
+PHC_HD float quat_angle(Q4 q) {
+  const float s = sqrtf(1.0f - q.w * q.w);
+  const float ang = wrap_angle(2.0f * acosf(q.w));
+  return (fabsf(s) > 1e-5f) ? ang : 0.0f;        // NaN (|w|>1) compares false -> 0, like torch.where(mask, ...)
+}
+
+// ... and the full exp map angle*axis (dof_pos of the reference pose)
+PHC_HD V3 quat_to_exp_map(Q4 q) {
+  const float s = sqrtf(1.0f - q.w * q.w);
+  const float ang = wrap_angle(2.0f * acosf(q.w));
+  if (fabsf(s) > 1e-5f) return v3(ang * (q.x / s), ang * (q.y / s), ang * (q.z / s));
+  return v3(0.0f * 0.0f, 0.0f * 0.0f, 0.0f * 1.0f);
+}
+
+// exp_map_to_quat (exp_map_to_angle_axis then quat_from_angle_axis with both normalisations)
+PHC_HD Q4 exp_map_to_quat(V3 e) {
+  const float n0 = sqrtf(e.x * e.x + e.y * e.y + e.z * e.z);
+  V3 ax = v3(e.x / n0, e.y / n0, e.z / n0);
+  float ang = wrap_angle(n0);
+  if (!(fabsf(ang) > 1e-5f)) { ang = 0.0f; ax = v3(0.0f, 0.0f, 1.0f); }
+  float an = sqrtf(ax.x * ax.x + ax.y * ax.y + ax.z * ax.z);
+  an = an < 1e-9f ? 1e-9f : an;
+  const float th = ang / 2.0f;
+  const float s = sinf(th), c = cosf(th);
+  const float x = (ax.x / an) * s, y = (ax.y / an) * s, z = (ax.z / an) * s;
+  float qn = sqrtf(x * x + y * y + z * z + c * c);
+  qn = qn < 1e-9f ? 1e-9f : qn;
+  return q4(x / qn, y / qn, z / qn, c / qn);
+}
+
+PHC_HD Q4 slerp(Q4 q0, Q4 q1, float t) {
+  float c = q0.x * q1.x + q0.y * q1.y + q0.z * q1.z + q0.w * q1.w;
+  if (c < 0.0f) q1 = q4(-q1.x, -q1.y, -q1.z, -q1.w);
+  c = fabsf(c);
+  const float half = acosf(c);
+  const float s = sqrtf(1.0f - c * c);
+  const float ra = sinf((1.0f - t) * half) / s;
+  const float rb = sinf(t * half) / s;
+  Q4 r = q4(ra * q0.x + rb * q1.x, ra * q0.y + rb * q1.y, ra * q0.z + rb * q1.z, ra * q0.w + rb * q1.w);
+  if (fabsf(s) < 0.001f) r = q4(0.5f * q0.x + 0.5f * q1.x, 0.5f * q0.y + 0.5f * q1.y, 0.5f * q0.z + 0.5f * q1.z, 0.5f * q0.w + 0.5f * q1.w);
+  if (fabsf(c) >= 1.0f) r = q0;
+  return r;
+}
+
+// remove_base_rot (humanoid.py:1935-1939): q * conj([.5,.5,.5,.5])
+PHC_HD Q4 strip_base_rot(Q4 q) { return qmul(q, q4(-0.5f, -0.5f, -0.5f, 0.5f)); }
+
+// _calc_frame_blend (motion_lib_base.py:549-559): fp32 order time/len -> clip -> *(nf-1) -> trunc
+struct Bracket { int64_t i0, i1; float blend; };
+PHC_HD Bracket frame_bracket(float time, float len, int64_t nf, float dt) {
+  float phase = time / len;
+  phase = fminf(fmaxf(phase, 0.0f), 1.0f);
+  if (time < 0.0f) time = 0.0f;
+  Bracket b;
+  b.i0 = (int64_t)(phase * (float)(nf - 1));
+  b.i1 = (b.i0 + 1 < nf - 1) ? b.i0 + 1 : nf - 1;
+  float bl = (time - (float)b.i0 * dt) / dt;
+  b.blend = fminf(fmaxf(bl, 0.0f), 1.0f);
+  return b;
+}
+
+}  // namespace phc

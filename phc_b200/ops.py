@@ -1,0 +1,340 @@
+"""Torch-facing wrappers over the C ABI (include/phc_b200.h).  PyTorch only provides device memory and streams:
+every function here validates its tensors, hands `data_ptr()`s plus the current CUDA stream to libphc_b200.so and
+returns torch tensors that the caller (or this module) allocated.  There is no non-CUDA path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import (PHC_FLAG_EARLY_TERM, PHC_FLAG_LOCAL_ROOT_OBS, PHC_FLAG_NO_COLLISION, PHC_FLAG_POWER_REWARD,
+                   PHC_FLAG_ROOT_HEIGHT_OBS, PHC_FLAG_TERM_USE_MEAN, PHC_FLAG_UPRIGHT, PhcError)
+
+__all__ = ["PackedMotionLib", "pack_motion_lib", "motion_state", "EnvStepConfig", "EnvStepPlan", "amp_obs_demo",
+           "gae", "adv_norm", "PhcError"]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, dtype, name: str, device=None) -> torch.Tensor:
+    if not torch.is_tensor(t):
+        raise TypeError(f"{name}: expected a torch tensor")
+    if not t.is_cuda:
+        raise PhcError(f"{name}: phc_b200 runs on CUDA tensors only (got {t.device}); there is no CPU fallback")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+    if device is not None and t.device != device:
+        raise ValueError(f"{name}: on {t.device}, expected {device}")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# motion library
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class PackedMotionLib:
+    """Packed device copy of the MotionLib frame tables (PhcMotionLib in the header).  Keeps the tensors alive."""
+    frames_body: torch.Tensor
+    frames_joint: Optional[torch.Tensor]
+    lengths: torch.Tensor
+    dts: torch.Tensor
+    num_frames: torch.Tensor
+    length_starts: torch.Tensor
+    num_bodies: int
+    c: _lib.PhcMotionLib = field(default=None, repr=False)
+
+    @property
+    def device(self):
+        return self.frames_body.device
+
+    @property
+    def num_motions(self) -> int:
+        return int(self.lengths.shape[0])
+
+
+def pack_motion_lib(gts, grs, gvs, gavs, lrs, dvs, lengths, num_frames, dts, length_starts) -> PackedMotionLib:
+    """phc_motion_pack: the reference's separate [F,J,*] tables -> 16-byte aligned per-frame records."""
+    lib = _lib.load()
+    dev = gts.device
+    f32, i64 = torch.float32, torch.int64
+    gts, grs = _req(gts, f32, "gts"), _req(grs, f32, "grs", dev)
+    gvs, gavs = _req(gvs, f32, "gvs", dev), _req(gavs, f32, "gavs", dev)
+    F, J = int(gts.shape[0]), int(gts.shape[1])
+    assert grs.shape == (F, J, 4) and gvs.shape == (F, J, 3) and gavs.shape == (F, J, 3)
+    joint = lrs is not None and dvs is not None
+    if joint:
+        lrs, dvs = _req(lrs, f32, "lrs", dev), _req(dvs, f32, "dvs", dev)
+        assert lrs.shape == (F, J, 4) and dvs.shape == (F, J - 1, 3)
+    bs, js = lib.phc_motion_body_stride(J), lib.phc_motion_joint_stride(J)
+    fb = torch.empty(F, bs, dtype=f32, device=dev)
+    fj = torch.empty(F, js, dtype=f32, device=dev) if joint else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.phc_motion_pack(gts.data_ptr(), grs.data_ptr(), gvs.data_ptr(), gavs.data_ptr(),
+                                       _ptr(lrs) if joint else None, _ptr(dvs) if joint else None, F, J,
+                                       fb.data_ptr(), _ptr(fj), _stream()), "phc_motion_pack")
+    lengths = _req(lengths.contiguous(), f32, "lengths", dev)
+    dts = _req(dts.contiguous(), f32, "dts", dev)
+    num_frames = _req(num_frames.contiguous(), i64, "num_frames", dev)
+    length_starts = _req(length_starts.contiguous(), i64, "length_starts", dev)
+    c = _lib.PhcMotionLib(fb.data_ptr(), _ptr(fj), lengths.data_ptr(), dts.data_ptr(), num_frames.data_ptr(),
+                          length_starts.data_ptr(), F, int(lengths.shape[0]), J, bs, js)
+    return PackedMotionLib(fb, fj, lengths, dts, num_frames, length_starts, J, c)
+
+
+_MS_KEYS = {"rg_pos": 3, "rb_rot": 4, "body_vel": 3, "body_ang_vel": 3}
+
+
+def motion_state(mlib: PackedMotionLib, motion_ids: torch.Tensor, motion_times: torch.Tensor,
+                 offset: Optional[torch.Tensor] = None, want_dof: bool = True) -> Dict[str, torch.Tensor]:
+    """MotionLibBase.get_motion_state (motion_lib_base.py:437-520) on the packed tables."""
+    lib = _lib.load()
+    dev = mlib.device
+    ids = _req(motion_ids, torch.int64, "motion_ids", dev)
+    times = _req(motion_times, torch.float32, "motion_times", dev)
+    n, J = int(ids.shape[0]), mlib.num_bodies
+    if offset is not None:
+        offset = _req(offset, torch.float32, "offset", dev)
+        assert offset.shape == (n, 3)
+    out = {k: torch.empty(n, J, w, dtype=torch.float32, device=dev) for k, w in _MS_KEYS.items()}
+    for k, w in (("root_pos", 3), ("root_rot", 4), ("root_vel", 3), ("root_ang_vel", 3)):
+        out[k] = torch.empty(n, w, dtype=torch.float32, device=dev)
+    if want_dof:
+        if mlib.frames_joint is None:
+            raise PhcError("motion_state: dof_pos/dof_vel need the joint table (lrs/dvs) in the packed library")
+        out["dof_pos"] = torch.empty(n, 3 * (J - 1), dtype=torch.float32, device=dev)
+        out["dof_vel"] = torch.empty(n, 3 * (J - 1), dtype=torch.float32, device=dev)
+    co = _lib.PhcMotionStateOut(**{k: _ptr(out.get(k)) for k, _ in _lib.PhcMotionStateOut._fields_})
+    with torch.cuda.device(dev):
+        _lib.check(lib.phc_motion_state(C.byref(mlib.c), ids.data_ptr(), times.data_ptr(), _ptr(offset), n,
+                                        C.byref(co), _stream()), "phc_motion_state")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fused env step
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class EnvStepConfig:
+    """Static configuration of the fused step (what HumanoidIm reads from cfg at construction time)."""
+    dt: float = 1.0 / 30.0
+    time_steps: int = 1
+    traj_dt: float = 0.0
+    upright: bool = True
+    local_root_obs: bool = True
+    root_height_obs: bool = True
+    power_reward: bool = True
+    power_coef: float = 0.0005
+    early_term: bool = True
+    no_collision: bool = False
+    term_use_mean: bool = False
+    k_pos: float = 100.0
+    k_rot: float = 10.0
+    k_vel: float = 0.1
+    k_ang_vel: float = 0.1
+    w_pos: float = 0.5
+    w_rot: float = 0.3
+    w_vel: float = 0.1
+    w_ang_vel: float = 0.1
+    key_bodies: Sequence[int] = (7, 3, 22, 17)
+    reset_bodies: Optional[Sequence[int]] = None         # None = all bodies
+    term_dist: float = 0.25                              # or a per-body sequence of length J
+    dof_subset: Optional[Sequence[int]] = None           # dof indices kept in the AMP obs (whole joints); None = all
+    amp_steps: int = 10
+
+    def flags(self) -> int:
+        f = 0
+        for on, bit in ((self.upright, PHC_FLAG_UPRIGHT), (self.local_root_obs, PHC_FLAG_LOCAL_ROOT_OBS),
+                        (self.root_height_obs, PHC_FLAG_ROOT_HEIGHT_OBS), (self.power_reward, PHC_FLAG_POWER_REWARD),
+                        (self.early_term, PHC_FLAG_EARLY_TERM), (self.no_collision, PHC_FLAG_NO_COLLISION),
+                        (self.term_use_mean, PHC_FLAG_TERM_USE_MEAN)):
+            if on:
+                f |= bit
+        return f
+
+    def amp_joint_list(self, num_bodies: int):
+        if self.dof_subset is None:
+            return list(range(num_bodies - 1))
+        ds = [int(x) for x in self.dof_subset]
+        if len(ds) % 3 or any(ds[i] % 3 or ds[i + 1] != ds[i] + 1 or ds[i + 2] != ds[i] + 2 for i in range(0, len(ds), 3)):
+            raise ValueError("dof_subset must be made of whole joints (consecutive dof triples), as humanoid.py:409-413 builds it")
+        return [d // 3 for d in ds[::3]]
+
+
+class EnvStepPlan:
+    """A bound launch of phc_env_step: all pointers are captured once (the simulator tensors and the task buffers are
+    persistent, exactly as in the reference), `run()` only launches.  Output buffers not supplied are allocated."""
+
+    def __init__(self, cfg: EnvStepConfig, mlib: PackedMotionLib, body_state: torch.Tensor, dof_state: torch.Tensor,
+                 dof_force: Optional[torch.Tensor], progress: torch.Tensor, motion_ids: torch.Tensor,
+                 start_times: torch.Tensor, start_offsets: torch.Tensor, global_offset: torch.Tensor,
+                 cycle_counter: Optional[torch.Tensor] = None, obs: Optional[torch.Tensor] = None,
+                 rew: Optional[torch.Tensor] = None, reward_raw: Optional[torch.Tensor] = None,
+                 reset: Optional[torch.Tensor] = None, terminate: Optional[torch.Tensor] = None,
+                 amp_obs_buf: Optional[torch.Tensor] = None, amp_hist_in: Optional[torch.Tensor] = None,
+                 amp_shift: bool = True, with_amp: bool = True, with_ref_buffers: bool = False):
+        lib = _lib.load()
+        self._lib = lib
+        self.cfg, self.mlib = cfg, mlib
+        dev = mlib.device
+        self.device = dev
+        f32, i64 = torch.float32, torch.int64
+        J = mlib.num_bodies
+        D = 3 * (J - 1)
+        body_state = _req(body_state, f32, "body_state", dev)
+        N, bpe = int(body_state.shape[0]), int(body_state.shape[1])
+        assert body_state.shape[2] == 13 and bpe >= J
+        dof_state = _req(dof_state, f32, "dof_state", dev)
+        assert dof_state.shape == (N, D, 2)
+        if cfg.power_reward:
+            dof_force = _req(dof_force, f32, "dof_force", dev)
+            assert dof_force.shape == (N, D)
+        self.N, self.J = N, J
+        flags = cfg.flags()
+        self.self_dim = lib.phc_self_obs_dim(J, flags)
+        self.task_dim = lib.phc_task_obs_dim(J, cfg.time_steps)
+        self.obs_dim = self.self_dim + self.task_dim
+        joints = cfg.amp_joint_list(J)
+        self.amp_dim = lib.phc_amp_obs_dim(len(joints), len(cfg.key_bodies), flags)
+        rw = 5 if cfg.power_reward else 4
+
+        def out(t, shape, dtype, name):
+            if t is None:
+                return torch.zeros(shape, dtype=dtype, device=dev)
+            t = _req(t, dtype, name, dev)
+            assert tuple(t.shape) == tuple(shape), f"{name}: shape {tuple(t.shape)} != {tuple(shape)}"
+            return t
+
+        self.obs = out(obs, (N, self.obs_dim), f32, "obs")
+        self.rew = out(rew, (N,), f32, "rew")
+        self.reward_raw = out(reward_raw, (N, rw), f32, "reward_raw")
+        self.reset = out(reset, (N,), i64, "reset")
+        self.terminate = out(terminate, (N,), i64, "terminate")
+        S = cfg.amp_steps
+        self.amp_obs_buf = out(amp_obs_buf, (N, S, self.amp_dim), f32, "amp_obs_buf") if with_amp else None
+        if amp_hist_in is not None:
+            amp_hist_in = _req(amp_hist_in, f32, "amp_hist_in", dev)
+            assert amp_hist_in.shape == (N, S, self.amp_dim)
+        elif with_amp and amp_shift:
+            amp_hist_in = self.amp_obs_buf             # in-place shift, the reference's semantics
+        self.ref_body_pos = torch.zeros(N, J, 3, device=dev) if with_ref_buffers else None
+        self.ref_body_rot = torch.zeros(N, J, 4, device=dev) if with_ref_buffers else None
+        self.ref_body_vel = torch.zeros(N, J, 3, device=dev) if with_ref_buffers else None
+        self.ref_body_ang_vel = torch.zeros(N, J, 3, device=dev) if with_ref_buffers else None
+
+        # per-body termination threshold, +inf outside reset_bodies (compute_humanoid_im_reset is fed the subset)
+        td = torch.as_tensor(cfg.term_dist, dtype=f32).expand(J).clone() if not torch.is_tensor(cfg.term_dist) else cfg.term_dist.float().cpu().clone()
+        rb = list(range(J)) if cfg.reset_bodies is None else [int(b) for b in cfg.reset_bodies]
+        thr = torch.full((J,), float("inf"))
+        thr[rb] = td[rb]
+        self._term_thresh = thr.to(dev)
+        self._amp_joints = torch.tensor(joints, dtype=torch.int32, device=dev) if joints else None
+        self._keep = dict(body_state=body_state, dof_state=dof_state, dof_force=dof_force,
+                          progress=_req(progress, i64, "progress", dev), motion_ids=_req(motion_ids, i64, "motion_ids", dev),
+                          start_times=_req(start_times, f32, "start_times", dev),
+                          start_offsets=_req(start_offsets, f32, "start_offsets", dev),
+                          global_offset=_req(global_offset, f32, "global_offset", dev),
+                          cycle_counter=None if cycle_counter is None else _req(cycle_counter, torch.int32, "cycle_counter", dev),
+                          amp_hist_in=amp_hist_in)
+        k = self._keep
+        a = _lib.PhcStepArgs()
+        a.body_state, a.dof_state, a.dof_force, a.bodies_per_env = body_state.data_ptr(), dof_state.data_ptr(), _ptr(dof_force if cfg.power_reward else None), bpe
+        a.progress, a.motion_ids = k["progress"].data_ptr(), k["motion_ids"].data_ptr()
+        a.start_times, a.start_offsets, a.global_offset = k["start_times"].data_ptr(), k["start_offsets"].data_ptr(), k["global_offset"].data_ptr()
+        a.cycle_counter = _ptr(k["cycle_counter"])
+        a.lib = mlib.c
+        a.num_envs, a.time_steps, a.dt, a.traj_dt, a.flags = N, cfg.time_steps, cfg.dt, cfg.traj_dt, flags
+        a.k_pos, a.k_rot, a.k_vel, a.k_ang_vel = cfg.k_pos, cfg.k_rot, cfg.k_vel, cfg.k_ang_vel
+        a.w_pos, a.w_rot, a.w_vel, a.w_ang_vel = cfg.w_pos, cfg.w_rot, cfg.w_vel, cfg.w_ang_vel
+        a.power_coef = cfg.power_coef
+        a.term_thresh, a.term_dist_mean = self._term_thresh.data_ptr(), float(td[rb[0]])
+        a.num_key_bodies = len(cfg.key_bodies)
+        for i, b in enumerate(cfg.key_bodies):
+            a.key_bodies[i] = int(b)
+        a.amp_joints, a.num_amp_joints = _ptr(self._amp_joints), len(joints)
+        a.obs, a.obs_stride = self.obs.data_ptr(), self.obs.stride(0)
+        a.rew, a.reward_raw, a.reset, a.terminate = self.rew.data_ptr(), self.reward_raw.data_ptr(), self.reset.data_ptr(), self.terminate.data_ptr()
+        a.amp_out = _ptr(self.amp_obs_buf)
+        a.amp_hist_in = _ptr(amp_hist_in) if with_amp else None
+        a.amp_out_stride, a.amp_steps = S * self.amp_dim, S
+        a.ref_body_pos, a.ref_body_rot = _ptr(self.ref_body_pos), _ptr(self.ref_body_rot)
+        a.ref_body_vel, a.ref_body_ang_vel = _ptr(self.ref_body_vel), _ptr(self.ref_body_ang_vel)
+        self.args = a
+        self._args_ref = C.byref(a)
+
+    def run(self, stream: Optional[int] = None) -> None:
+        rc = self._lib.phc_env_step(self._args_ref, _stream() if stream is None else stream)
+        if rc:
+            _lib.check(rc, "phc_env_step")
+
+
+def amp_obs_demo(mlib: PackedMotionLib, cfg: EnvStepConfig, motion_ids: torch.Tensor, times0: torch.Tensor,
+                 first_step: int = 0, num_steps: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """build_amp_obs_demo (humanoid_amp.py:253-284; first_step=0) / _init_amp_obs_ref (:575-603; first_step=1)."""
+    lib = _lib.load()
+    dev = mlib.device
+    ids = _req(motion_ids, torch.int64, "motion_ids", dev)
+    t0 = _req(times0, torch.float32, "times0", dev)
+    n = int(ids.shape[0])
+    S = cfg.amp_steps if num_steps is None else num_steps
+    joints = cfg.amp_joint_list(mlib.num_bodies)
+    A = lib.phc_amp_obs_dim(len(joints), len(cfg.key_bodies), cfg.flags())
+    if out is None:
+        out = torch.empty(n, S, A, dtype=torch.float32, device=dev)
+    else:
+        out = _req(out, torch.float32, "out", dev)
+        assert out.shape == (n, S, A)
+    kb = (C.c_int32 * len(cfg.key_bodies))(*[int(b) for b in cfg.key_bodies])
+    aj = torch.tensor(joints, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.phc_amp_obs_demo(C.byref(mlib.c), ids.data_ptr(), t0.data_ptr(), n, first_step, S, cfg.dt,
+                                        cfg.flags(), C.cast(kb, C.c_void_p), len(cfg.key_bodies), aj.data_ptr(),
+                                        len(joints), out.data_ptr(), S * A, _stream()), "phc_amp_obs_demo")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# PPO scalars
+# ------------------------------------------------------------------------------------------------------------
+def gae(fdones: torch.Tensor, values: torch.Tensor, rewards: torch.Tensor, next_values: torch.Tensor, gamma: float,
+        tau: float, want_returns: bool = True):
+    """CommonAgent.discount_values (+ returns).  Time-major [T,N] or [T,N,1] fp32 tensors."""
+    lib = _lib.load()
+    dev = rewards.device
+    shape = rewards.shape
+    T, N = int(shape[0]), int(shape[1])
+    fd = _req(fdones, torch.float32, "fdones", dev)
+    v, r, nv = _req(values, torch.float32, "values", dev), _req(rewards, torch.float32, "rewards", dev), _req(next_values, torch.float32, "next_values", dev)
+    assert fd.numel() == v.numel() == r.numel() == nv.numel() == T * N
+    advs = torch.empty(shape, dtype=torch.float32, device=dev)
+    rets = torch.empty(shape, dtype=torch.float32, device=dev) if want_returns else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.phc_gae(fd.data_ptr(), v.data_ptr(), r.data_ptr(), nv.data_ptr(), T, N, gamma, tau,
+                               advs.data_ptr(), _ptr(rets), _stream()), "phc_gae")
+    return (advs, rets) if want_returns else advs
+
+
+def adv_norm(returns: torch.Tensor, values: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+    """CommonAgent._calc_advs: [B,1] (or [B]) returns / values -> normalised advantages [B]."""
+    lib = _lib.load()
+    dev = returns.device
+    r, v = _req(returns, torch.float32, "returns", dev), _req(values, torch.float32, "values", dev)
+    n = r.numel()
+    assert v.numel() == n
+    advs = torch.empty(n, dtype=torch.float32, device=dev)
+    ws = torch.empty(max(1, lib.phc_adv_norm_workspace_bytes(n) // 8), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.phc_adv_norm(r.data_ptr(), v.data_ptr(), n, 1 if normalize else 0, advs.data_ptr(),
+                                    ws.data_ptr(), _stream()), "phc_adv_norm")
+    return advs

@@ -1,0 +1,163 @@
+"""GPU parity tests of the env-side hot path: CUDA (through the C ABI) vs the oracle and the committed goldens.
+Tolerance: rtol 1e-5 / atol 1e-6 fp32 on observations and rewards (north_star); integers bit-exact."""
+import pytest
+import torch
+
+from oracle import phc_oracle as O
+from phc_b200 import ops, synthetic as syn
+from tests.helpers import close, env_state_from, load, motion_data_from, oracle_tables, smpl_step_config
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def smpl_cfg(**kw):
+    base = dict(key_bodies=syn.SMPL_KEY_BODIES, reset_bodies=syn.SMPL_RESET_BODIES, dof_subset=syn.SMPL_DOF_SUBSET)
+    base.update(kw)
+    return ops.EnvStepConfig(**base)
+
+
+def pack(m: syn.MotionData):
+    d = m.to(DEV)
+    return ops.pack_motion_lib(d.gts, d.grs, d.gvs, d.gavs, d.lrs, d.dvs, d.lengths, d.num_frames, d.dts, d.length_starts)
+
+
+def run_cuda_step(m, st, cfg, **plan_kw):
+    mlib = pack(m)
+    s = st.to(DEV)
+    plan = ops.EnvStepPlan(cfg, mlib, s.body_state, s.dof_state, s.dof_force, s.progress, s.motion_ids, s.start_times,
+                           s.start_offsets, s.global_offset, amp_obs_buf=s.amp_hist.clone(), with_ref_buffers=True, **plan_kw)
+    plan.run()
+    torch.cuda.synchronize()
+    return plan
+
+
+def check_against(plan, exp, tag=""):
+    close(plan.obs.cpu(), exp["obs"], what=f"{tag} obs")
+    close(plan.rew.cpu(), exp["rew"], what=f"{tag} rew")
+    close(plan.reward_raw.cpu(), exp["reward_raw"], what=f"{tag} reward_raw")
+    close(plan.reset.cpu(), exp["reset"], what=f"{tag} reset")
+    close(plan.terminate.cpu(), exp["terminate"], what=f"{tag} terminate")
+    close(plan.amp_obs_buf.cpu(), exp["amp_obs_buf"], what=f"{tag} amp_obs_buf")
+    close(plan.ref_body_pos.cpu(), exp["ref_body_pos"], what=f"{tag} ref_body_pos")
+    close(plan.ref_body_rot.cpu(), exp["ref_body_rot"], what=f"{tag} ref_body_rot")
+    close(plan.ref_body_vel.cpu(), exp["ref_body_vel"], what=f"{tag} ref_body_vel")
+
+
+@pytest.mark.parametrize("tag,in_tag,kw", [("A", "A", {}), ("B", "B", {}),
+                                            ("C", "A", dict(upright=False, local_root_obs=False)),
+                                            ("D", "B", dict(term_use_mean=True))])
+def test_env_step_vs_reference_golden(tag, in_tag, kw):
+    """CUDA vs outputs of the UNMODIFIED reference classes (tests/golden/envstep.npz)."""
+    g = load("envstep.npz")
+    plan = run_cuda_step(motion_data_from(g), env_state_from(g, in_tag), smpl_cfg(**kw))
+    exp = {k: g[f"{tag}_out_{k}"] for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf",
+                                             "ref_body_pos", "ref_body_rot", "ref_body_vel")}
+    check_against(plan, exp, tag)
+
+
+@pytest.mark.parametrize("n,seed,jitter", [(1, 0, False), (5, 1, True), (257, 2, False), (1024, 3, True)])
+def test_env_step_vs_oracle(n, seed, jitter):
+    """Ragged sizes (1 env, non-multiple of the CTA tile, > one wave of warps) against the oracle."""
+    m = syn.make_motions(n, seed=seed, min_frames=30, max_frames=90)
+    st = syn.make_env_state(m, n, seed=seed, max_progress=80, with_offset=jitter, blend_jitter=jitter)
+    plan = run_cuda_step(m, st, smpl_cfg())
+    exp = O.env_step(oracle_tables(m), smpl_step_config(), st.body_state, st.dof_state, st.dof_force, st.progress,
+                     st.motion_ids, st.start_times, st.start_offsets, st.global_offset, st.amp_hist)
+    check_against(plan, exp, f"n={n}")
+    assert exp["reset"].sum() > 0 or n < 8
+
+
+def test_env_step_shared_clips_and_padded_bodies():
+    """Fewer clips than envs (ids wrap) and bodies_per_env > J with a non-multiple-of-4 row (plain-load path)."""
+    n = 64
+    m = syn.make_motions(7, seed=5, min_frames=100, max_frames=120)
+    st = syn.make_env_state(m, n, seed=5, max_progress=60)
+    exp = O.env_step(oracle_tables(m), smpl_step_config(), st.body_state, st.dof_state, st.dof_force, st.progress,
+                     st.motion_ids, st.start_times, st.start_offsets, st.global_offset, st.amp_hist)
+    check_against(run_cuda_step(m, st, smpl_cfg()), exp, "shared")
+    padded = torch.cat((st.body_state, torch.full((n, 3, 13), 77.0)), dim=1).contiguous()   # 27 bodies per env
+    st2 = syn.EnvState(**{**{k: getattr(st, k) for k in st.__dataclass_fields__}, "body_state": padded})
+    check_against(run_cuda_step(m, st2, smpl_cfg()), exp, "padded")
+
+
+def test_env_step_future_tracks():
+    """T = 3 future reference samples (fut_tracks): observation layout [B, T, J*24]."""
+    n = 96
+    m = syn.make_motions(n, seed=9, min_frames=40, max_frames=80)
+    st = syn.make_env_state(m, n, seed=9, max_progress=30, blend_jitter=True)
+    cfg_o = smpl_step_config(time_steps=3, traj_dt=3 / 30.0)
+    exp = O.env_step(oracle_tables(m), cfg_o, st.body_state, st.dof_state, st.dof_force, st.progress, st.motion_ids,
+                     st.start_times, st.start_offsets, st.global_offset, st.amp_hist)
+    plan = run_cuda_step(m, st, smpl_cfg(time_steps=3, traj_dt=3 / 30.0))
+    assert plan.obs.shape[1] == 358 + 3 * 576
+    check_against(plan, exp, "fut")
+
+
+def test_env_step_other_body_count():
+    """J = 20 (H1-sized tree), all joints in the AMP obs, no power reward, out-of-place AMP window."""
+    n, J = 130, 20
+    m = syn.make_motions(n, seed=4, num_bodies=J, min_frames=30, max_frames=60)
+    A = 1 + 12 + 9 * (J - 1) + 3 * 2
+    st = syn.make_env_state(m, n, seed=4, amp_dim=A, max_progress=40)
+    kw = dict(key_bodies=[5, 9], reset_bodies=None, dof_subset=None, power_reward=False)
+    exp = O.env_step(oracle_tables(m), O.StepConfig(**kw), st.body_state, st.dof_state, st.dof_force, st.progress,
+                     st.motion_ids, st.start_times, st.start_offsets, st.global_offset, st.amp_hist)
+    mlib = pack(m)
+    s = st.to(DEV)
+    hist_in = s.amp_hist.clone()
+    plan = ops.EnvStepPlan(ops.EnvStepConfig(**kw), mlib, s.body_state, s.dof_state, None, s.progress, s.motion_ids,
+                           s.start_times, s.start_offsets, s.global_offset, amp_hist_in=hist_in, with_ref_buffers=True)
+    plan.run()
+    torch.cuda.synchronize()
+    assert plan.reward_raw.shape[1] == 4
+    check_against(plan, exp, "J20")
+    assert torch.equal(hist_in.cpu(), st.amp_hist)          # out-of-place: the input window is untouched
+
+
+def test_env_step_is_idempotent_and_deterministic():
+    """Size-independent property at the bench size: same inputs -> bit-identical outputs, run twice."""
+    n = 4096
+    m = syn.make_motions(n, seed=11, min_frames=60, max_frames=120)
+    st = syn.make_env_state(m, n, seed=11)
+    p1 = run_cuda_step(m, st, smpl_cfg())
+    p2 = run_cuda_step(m, st, smpl_cfg())
+    for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf"):
+        assert torch.equal(getattr(p1, k), getattr(p2, k)), k
+    assert torch.isfinite(p1.obs).all() and torch.isfinite(p1.rew).all()
+    # rotating the whole world about z leaves the (heading-local) observation and the reward unchanged
+    th = 0.7
+    qz = torch.tensor([0.0, 0.0, torch.sin(torch.tensor(th / 2)), torch.cos(torch.tensor(th / 2))])
+    from phc_b200.synthetic import _qmul, _qrot
+    def rot_tab(t, is_q):
+        return _qmul(qz.expand_as(t), t) if is_q else _qrot(qz.expand(*t.shape[:-1], 4), t)
+    m2 = syn.MotionData(gts=rot_tab(m.gts, False), grs=rot_tab(m.grs, True), lrs=m.lrs, gvs=rot_tab(m.gvs, False),
+                        gavs=rot_tab(m.gavs, False), dvs=m.dvs, lengths=m.lengths, num_frames=m.num_frames, dts=m.dts,
+                        length_starts=m.length_starts)
+    b = st.body_state
+    b2 = torch.cat((rot_tab(b[..., 0:3], False), rot_tab(b[..., 3:7], True), rot_tab(b[..., 7:10], False),
+                    rot_tab(b[..., 10:13], False)), dim=-1).contiguous()
+    st2 = syn.EnvState(**{**{k: getattr(st, k) for k in st.__dataclass_fields__}, "body_state": b2})
+    p3 = run_cuda_step(m2, st2, smpl_cfg())
+    close(p3.obs.cpu(), p1.obs.cpu(), rtol=1e-3, atol=2e-4, what="z-rotation invariance of obs")
+    close(p3.rew.cpu(), p1.rew.cpu(), rtol=1e-4, atol=1e-5, what="z-rotation invariance of reward")
+    assert torch.equal(p3.reset, p1.reset)
+
+
+def test_motion_state_and_amp_demo_vs_golden():
+    g = load("motion.npz")
+    mlib = pack(motion_data_from(g))
+    res = ops.motion_state(mlib, g["ids"].to(DEV), g["times"].to(DEV), g["offset"].to(DEV))
+    for k in ("root_pos", "root_rot", "root_vel", "root_ang_vel", "dof_vel", "rg_pos", "rb_rot", "body_vel", "body_ang_vel"):
+        close(res[k].cpu(), g["out_" + k], what=k)
+    close(res["dof_pos"].cpu(), g["out_dof_pos"], rtol=1e-4, atol=2e-5, what="dof_pos (acos near identity)")
+    res_no = ops.motion_state(mlib, g["ids"].to(DEV), g["times"].to(DEV), None, want_dof=False)
+    close(res_no["rg_pos"].cpu(), g["out_noffset_rg_pos"], what="rg_pos no offset")
+
+    e = load("envstep.npz")
+    mlib2 = pack(motion_data_from(e))
+    demo = ops.amp_obs_demo(mlib2, smpl_cfg(), e["demo_ids"].to(DEV), e["demo_t0"].to(DEV))
+    close(demo.cpu(), e["demo_out"], rtol=1e-4, atol=2e-5, what="amp_obs_demo")
+    hist = ops.amp_obs_demo(mlib2, smpl_cfg(), e["demo_ids"].to(DEV), e["demo_t0"].to(DEV), first_step=1, num_steps=9)
+    exp = O.amp_obs_demo(oracle_tables(motion_data_from(e)), smpl_step_config(), e["demo_ids"], e["demo_t0"], 1, 9)
+    close(hist.cpu(), exp, rtol=1e-4, atol=2e-5, what="amp history init")
