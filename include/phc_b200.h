@@ -108,6 +108,7 @@ PHC_API int phc_motion_state(const PhcMotionLib* lib, const int64_t* motion_ids,
 #define PHC_FLAG_EARLY_TERM (1u << 4)      /* env.enableEarlyTermination                                */
 #define PHC_FLAG_NO_COLLISION (1u << 5)    /* flags.no_collision_check                                  */
 #define PHC_FLAG_TERM_USE_MEAN (1u << 6)   /* flags.im_eval and not strict_eval: mean-distance criterion */
+#define PHC_FLAG_OBS_ONLY (1u << 7)        /* _compute_observations(env_ids) of the reset path: write obs (+ref_*) only */
 
 #define PHC_MAX_KEY_BODIES 8
 
@@ -124,6 +125,8 @@ typedef struct PhcStepArgs {
   const float* start_offsets;    /* [N] _motion_start_times_offset      */
   const float* global_offset;    /* [N,3] _global_offset                */
   const int32_t* cycle_counter;  /* [N] _cycle_counter or NULL (is_recovery override, humanoid_im.py:1186-1188) */
+  const int64_t* only_where;     /* [N] or NULL: when given, only envs with only_where[env] != 0 are processed (the
+                                    reference's `env_ids` subset, kept as a mask so no host sync / nonzero() is needed) */
   PhcMotionLib lib;
   /* ---- configuration ---- */
   int32_t num_envs;   /* N */
@@ -175,7 +178,15 @@ PHC_API int phc_env_step(const PhcStepArgs* args, void* stream);
 PHC_API int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* motion_ids, const float* times0, int64_t n,
                      int32_t first_step, int32_t num_steps, float dt, uint32_t flags, const int32_t* key_bodies,
                      int32_t num_key_bodies, const int32_t* amp_joints, int32_t num_amp_joints, float* out,
-                     int64_t out_stride, void* stream);
+                     int64_t out_stride, const int64_t* only_where /* [n] or NULL: skip rows whose entry is 0 */,
+                     void* stream);
+
+/* Reset path (HumanoidAMP._set_env_state, humanoid_amp.py:605-637 fed by _sample_ref_state, humanoid_im.py:1000-1023):
+ * write the reference pose at (motion_ids[e], times[e]) (+offset) into the simulator tensors of every env e with
+ * only_where[e] != 0 (NULL = all): body_state[e, 0:J, 13] and, when dof_state != NULL, dof_state[e, :, (pos, vel)]. */
+PHC_API int phc_set_env_state(const PhcMotionLib* lib, const int64_t* motion_ids, const float* times, const float* offset,
+                      const int64_t* only_where, int64_t n, float* body_state, int32_t bodies_per_env, float* dof_state,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * PPO scalars
@@ -191,6 +202,71 @@ PHC_API int phc_gae(const float* fdones, const float* values, const float* rewar
 PHC_API int64_t phc_adv_norm_workspace_bytes(int64_t n);
 PHC_API int phc_adv_norm(const float* returns, const float* values, int64_t n, int32_t normalize, float* advs,
                  void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * MLP building blocks (actor / critic / discriminator are nn.Linear stacks: phc/learning/network_builder.py:105-124,
+ * amp_network_builder.py:58-249; fp32 in the reference -> computed fp32-equivalent on the tensor cores, 3xTF32)
+ * ---------------------------------------------------------------------------------------------------------- */
+/* C[M,N] (+)= epi(alpha * sum_k A(m,k) B(n,k)).  a_kmajor: A(m,k) = A[m*lda + k] (else A[k*lda + m]); b_kmajor: B(n,k) =
+ * B[n*ldb + k] (else B[k*ldb + n]).  Forward Y = X W^T: (1,1); input gradient dX = dY W: (1,0); weight gradient
+ * dW = dY^T X: (0,0).  Epilogue in order: *alpha, +bias[n], ReLU (relu != 0), *(mask[m*ldmask+n] > 0) (ReLU
+ * backward), then store or atomic accumulate (accumulate != 0; required for k_splits > 1, C pre-zeroed).
+ * A, B 16-byte aligned, lda/ldb multiples of 4 and >= the contiguous extent rounded up to 4 (zero padded). */
+PHC_API int phc_gemm(const float* A, int64_t lda, int32_t a_kmajor, const float* B, int64_t ldb, int32_t b_kmajor, float* C,
+             int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha, const float* bias, int32_t relu,
+             const float* mask, int64_t ldmask, int32_t accumulate, int32_t k_splits, void* stream);
+/* out[n] (+)= alpha * sum_m X[m*ld + n]   (bias gradients) */
+PHC_API int phc_colsum(const float* X, int64_t ld, int32_t M, int32_t N, float alpha, float* out, int32_t accumulate,
+               void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Learner-side element-wise / reduction kernels (between the GEMMs of the PPO + AMP update)
+ * ---------------------------------------------------------------------------------------------------------- */
+/* RunningMeanStd.forward (phc/utils/running_mean_std.py:69-109): y = clamp((x-mean)/sqrt(var+eps), -5, 5), or with
+ * unnorm != 0: y = sqrt(var+eps)*clamp(x,-5,5)+mean.  fp64 stats, fp32 data; only columns [0,d) are written. */
+PHC_API int phc_rms_apply(const float* x, int64_t ldx, int64_t n, int32_t d, const double* mean, const double* var, float eps,
+                  int32_t unnorm, float* y, int64_t ldy, const int64_t* row_idx /* [n] or NULL: y[r] = f(x[row_idx[r]]),
+                  the minibatch gather of AMPDataset._get_item (amp_datasets.py:81-94) fused in */, void* stream);
+/* ... and its train-mode statistics update (parallel-variance merge of the batch mean / unbiased var, :56-68). */
+PHC_API int64_t phc_rms_workspace_bytes(int32_t d);
+PHC_API int phc_rms_update(const float* x, int64_t ldx, int64_t n, int32_t d, double* mean, double* var, double* count,
+                   void* workspace, const int64_t* row_idx /* [n] or NULL, as in phc_rms_apply */, void* stream);
+/* rl_games ModelA2CContinuousLogStd (is_train False): action = mu + exp(logstd)*noise, neglogp of that action;
+ * mus / sigmas (optional) are the copies the experience buffer stores. */
+PHC_API int phc_gaussian_sample(const float* mu, int64_t ldmu, const float* logstd, const float* noise, int64_t n, int32_t A,
+                        float* actions, float* neglogp, float* mus, float* sigmas, void* stream);
+/* Actor side of AMPAgent.calc_gradients (amp_agent.py:604-641): neglogp of the stored actions, CommonAgent._actor_loss
+ * (common_agent.py:564-574), bound_loss (:512-520), policy_kl; writes d(total loss)/d(mu) = inv_batch * (...).
+ * stats (float[16], caller-zeroed, sums over rows): [0] actor loss [1] bound loss [2] clipped count [3] kl [4] entropy */
+PHC_API int phc_ppo_actor_grad(const float* mu, int64_t ldmu, const float* logstd, const float* actions,
+                       const float* old_neglogp, const float* adv, const float* old_mu, const float* old_sigma, int64_t n,
+                       int32_t A, float e_clip, float bound_coef, float inv_batch, float* dmu, int64_t lddmu, float* stats,
+                       void* stream);
+/* CommonAgent._critic_loss with clip_value False (:576-587): dv = coef*2*(v-ret)*inv_batch; stats[5] += sum (ret-v)^2 */
+PHC_API int phc_ppo_critic_grad(const float* v, int64_t ldv, const float* ret, int64_t n, float coef, float inv_batch, float* dv,
+                        int64_t lddv, float* stats, void* stream);
+/* AMPAgent._disc_loss prediction part (amp_agent.py:739-743, :791-804): rows [0,n_agent) are agent+replay logits
+ * (target 0), rows [n_agent, n_agent+n_demo) demo logits (target 1); dlogit = coef*0.5*dBCE/n.
+ * stats[6] += sum softplus(agent) [7] += sum softplus(-demo) [8] += #(agent<0) [9] += #(demo>0) */
+PHC_API int phc_disc_logit_grad(const float* logit, int64_t ld, int64_t n_agent, int64_t n_demo, float coef, float* dlogit,
+                        int64_t ldd, float* stats, void* stream);
+/* AMPAgent._calc_disc_rewards (:864-878) (+ _combine_rewards :848-853 when combined != NULL) */
+PHC_API int phc_disc_reward(const float* logit, int64_t ld, const float* task_rewards, int64_t n, float scale, float w_task,
+                    float w_disc, float* disc_rewards, float* combined, void* stream);
+/* u[b,j] = h[b,j] > 0 ? w[j] : 0 : first factor of d(logit)/d(input) through a ReLU MLP (gradient penalty, :749-768) */
+PHC_API int phc_relu_mask_row(const float* h, int64_t ldh, const float* w, int64_t n, int32_t d, float* u, int64_t ldu, void* stream);
+/* stat += sum x^2 (before scaling); x *= alpha   (turns d(logit)/d(input) into d(penalty)/d(that)) */
+PHC_API int phc_scale_sumsq(float* x, int64_t ld, int64_t n, int32_t d, float alpha, float* stat, void* stream);
+/* y += alpha*x on a strided block; optional stat += sum x^2   (logit regulariser / weight decay, :745-747,:771-775) */
+PHC_API int phc_axpy2d(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int32_t cols, float alpha,
+               float* sumsq_stat, void* stream);
+/* out[0] = sum g^2 (fp64) over the flat gradient bucket */
+PHC_API int phc_grad_sumsq(const float* g, int64_t n, double* out, void* stream);
+/* nn.utils.clip_grad_norm_(max_norm) (amp_agent.py:670,677) + torch.optim.Adam step (common_agent.py:67) fused over
+ * the flat bucket; grad_scale = 1/world_size after the sum all-reduce; max_norm <= 0 disables clipping. */
+PHC_API int phc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  const double* grad_sumsq, float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,
+                  int64_t step, void* stream);
 
 #ifdef __cplusplus
 }

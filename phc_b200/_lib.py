@@ -18,6 +18,7 @@ PHC_FLAG_POWER_REWARD = 1 << 3
 PHC_FLAG_EARLY_TERM = 1 << 4
 PHC_FLAG_NO_COLLISION = 1 << 5
 PHC_FLAG_TERM_USE_MEAN = 1 << 6
+PHC_FLAG_OBS_ONLY = 1 << 7
 PHC_MAX_KEY_BODIES = 8
 
 _p = C.c_void_p
@@ -43,7 +44,7 @@ class PhcStepArgs(C.Structure):
     _fields_ = [
         ("body_state", _p), ("dof_state", _p), ("dof_force", _p), ("bodies_per_env", C.c_int32),
         ("progress", _p), ("motion_ids", _p), ("start_times", _p), ("start_offsets", _p), ("global_offset", _p),
-        ("cycle_counter", _p), ("lib", PhcMotionLib),
+        ("cycle_counter", _p), ("only_where", _p), ("lib", PhcMotionLib),
         ("num_envs", C.c_int32), ("time_steps", C.c_int32), ("dt", C.c_float), ("traj_dt", C.c_float),
         ("flags", C.c_uint32),
         ("k_pos", C.c_float), ("k_rot", C.c_float), ("k_vel", C.c_float), ("k_ang_vel", C.c_float),
@@ -71,10 +72,29 @@ SIGNATURES = {
     "phc_amp_obs_dim": (C.c_int, [C.c_int32, C.c_int32, C.c_uint32]),
     "phc_env_step": (C.c_int, [C.POINTER(PhcStepArgs), _p]),
     "phc_amp_obs_demo": (C.c_int, [C.POINTER(PhcMotionLib), _p, _p, C.c_int64, C.c_int32, C.c_int32, C.c_float,
-                                   C.c_uint32, _p, C.c_int32, _p, C.c_int32, _p, C.c_int64, _p]),
+                                   C.c_uint32, _p, C.c_int32, _p, C.c_int32, _p, C.c_int64, _p, _p]),
+    "phc_set_env_state": (C.c_int, [C.POINTER(PhcMotionLib), _p, _p, _p, _p, C.c_int64, _p, C.c_int32, _p, _p]),
     "phc_gae": (C.c_int, [_p, _p, _p, _p, C.c_int32, C.c_int64, C.c_float, C.c_float, _p, _p, _p]),
     "phc_adv_norm_workspace_bytes": (C.c_int64, [C.c_int64]),
     "phc_adv_norm": (C.c_int, [_p, _p, C.c_int64, C.c_int32, _p, _p, _p]),
+    "phc_gemm": (C.c_int, [_p, C.c_int64, C.c_int32, _p, C.c_int64, C.c_int32, _p, C.c_int64, C.c_int32, C.c_int32,
+                           C.c_int32, C.c_float, _p, C.c_int32, _p, C.c_int64, C.c_int32, C.c_int32, _p]),
+    "phc_colsum": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p, C.c_int32, _p]),
+    "phc_rms_apply": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, _p, _p, C.c_float, C.c_int32, _p, C.c_int64, _p, _p]),
+    "phc_rms_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "phc_rms_update": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, _p, _p, _p, _p, _p, _p]),
+    "phc_gaussian_sample": (C.c_int, [_p, C.c_int64, _p, _p, C.c_int64, C.c_int32, _p, _p, _p, _p, _p]),
+    "phc_ppo_actor_grad": (C.c_int, [_p, C.c_int64, _p, _p, _p, _p, _p, _p, C.c_int64, C.c_int32, C.c_float, C.c_float,
+                                     C.c_float, _p, C.c_int64, _p, _p]),
+    "phc_ppo_critic_grad": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.c_float, C.c_float, _p, C.c_int64, _p, _p]),
+    "phc_disc_logit_grad": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int64, C.c_float, _p, C.c_int64, _p, _p]),
+    "phc_disc_reward": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.c_float, C.c_float, C.c_float, _p, _p, _p]),
+    "phc_relu_mask_row": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.c_int32, _p, C.c_int64, _p]),
+    "phc_scale_sumsq": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, _p, _p]),
+    "phc_axpy2d": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.c_int64, C.c_int32, C.c_float, _p, _p]),
+    "phc_grad_sumsq": (C.c_int, [_p, C.c_int64, _p, _p]),
+    "phc_adam_step": (C.c_int, [_p, _p, _p, _p, C.c_int64, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                C.c_float, C.c_int64, _p]),
 }
 
 _lib = None

@@ -29,6 +29,8 @@ SOURCES = {
     "env_step.cu": ["-fmad=false"],
     "motion.cu": ["-fmad=false"],
     "ppo_scalars.cu": ["-fmad=false"],
+    "gemm.cu": [],
+    "ppo_update.cu": [],
 }
 
 

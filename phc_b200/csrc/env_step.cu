@@ -82,6 +82,8 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int env = blockIdx.x * kWarpsPerCta + warp;
   if (env >= a.num_envs) return;                       // whole warp exits together; no block-level barrier is used
+  if (a.only_where && a.only_where[env] == 0) return;  // masked subset (reset path)
+  const bool obs_only = a.flags & PHC_FLAG_OBS_ONLY;
 
   const int J = a.lib.num_bodies, D = 3 * (J - 1), T = a.time_steps;
   const int BS = a.lib.body_stride;
@@ -248,7 +250,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   e_ang = warp_sum(e_ang) / (float)J;
   power = warp_sum(power);
 
-  if (lane == 0) {
+  if (lane == 0 && !obs_only) {
     const float r_pos = expf(-a.k_pos * e_pos), r_rot = expf(-a.k_rot * e_rot);
     const float r_vel = expf(-a.k_vel * e_vel), r_ang = expf(-a.k_ang_vel * e_ang);
     float rew = a.w_pos * r_pos + a.w_rot * r_rot + a.w_vel * r_vel + a.w_ang_vel * r_ang;
@@ -278,7 +280,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   }
 
   // AMP observation of the simulated character (build_amp_observations_smpl) -> its own staging row
-  if (a.amp_out) {
+  if (a.amp_out && !obs_only) {
     const int nj = a.num_amp_joints, nk = a.num_key_bodies;
     float* o = s_amp + base0;
     if (lane == 0) {
@@ -349,7 +351,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
       for (int i = lane; i < obs_dim; i += 32) g[i] = s_obs[i];
     }
   }
-  if (a.amp_out) {
+  if (a.amp_out && !obs_only) {
     float* g = a.amp_out + (size_t)env * a.amp_out_stride;
     if (a.amp_hist_in) {
       // newest-first window shift: slot s -> s+1, walking from the oldest slot so an in-place shift is safe
@@ -385,8 +387,8 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
   const int J = a->lib.num_bodies, T = a->time_steps;
   if (!a->body_state || !a->dof_state || !a->progress || !a->motion_ids || !a->start_times || !a->start_offsets ||
       !a->global_offset || !a->lib.frames_body || !a->lib.motion_len || !a->lib.motion_dt ||
-      !a->lib.motion_num_frames || !a->lib.length_starts || !a->obs || !a->rew || !a->reward_raw || !a->reset ||
-      !a->terminate || !a->term_thresh) {
+      !a->lib.motion_num_frames || !a->lib.length_starts || !a->obs || !a->term_thresh ||
+      (!(a->flags & PHC_FLAG_OBS_ONLY) && (!a->rew || !a->reward_raw || !a->reset || !a->terminate))) {
     phc_set_error("phc_env_step: a required pointer is NULL");
     return PHC_ERR_INVALID_ARG;
   }

@@ -139,6 +139,7 @@ struct AmpDemoArgs {
   int32_t num_amp_joints;
   float* out;
   int64_t out_stride;
+  const int64_t* only_where;
 };
 
 // warp per (sample, history step): motion sample at t0 - (first_step + k) dt, then build_amp_observations_smpl
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(128) amp_demo_kernel(const __grid_constant__ A
   const int lane = threadIdx.x & 31;
   if (wi >= a.n * a.num_steps) return;
   const int64_t si = wi / a.num_steps;
+  if (a.only_where && a.only_where[si] == 0) return;
   const int k = (int)(wi - si * a.num_steps);
   const int J = a.lib.num_bodies;
   // motion_times0 + (-dt * (k + first)) : humanoid_amp.py:257-261 / :577-582
@@ -182,6 +184,33 @@ __global__ void __launch_bounds__(128) amp_demo_kernel(const __grid_constant__ A
   }
   for (int kk = 0; kk < nk; ++kk)
     if (a.key_bodies[kk] == lane) st3g(o + 12 + 9 * nj + 3 * kk, qrot(hinv, s.body.p - r.p));
+}
+
+// Reset path: write the reference pose at (id, time) of every env with mask != 0 into the simulator tensors
+// (HumanoidAMP._set_env_state, humanoid_amp.py:605-637: rigid-body rows + dof pos/vel), warp per env.
+__global__ void __launch_bounds__(128)
+set_env_state_kernel(const __grid_constant__ PhcMotionLib lib, const int64_t* __restrict__ ids,
+                     const float* __restrict__ times, const float* __restrict__ offset,
+                     const int64_t* __restrict__ only_where, int64_t n, float* __restrict__ body_state, int bpe,
+                     float* __restrict__ dof_state) {
+  const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (env >= n) return;
+  if (only_where && only_where[env] == 0) return;
+  const int J = lib.num_bodies;
+  if (lane >= J) return;
+  const V3 off = offset ? v3(offset[3 * env], offset[3 * env + 1], offset[3 * env + 2]) : v3(0.f, 0.f, 0.f);
+  MotionSample s = sample_motion(lib, ids[env], times[env], v3(0.f, 0.f, 0.f), lane, dof_state != nullptr);
+  if (offset) s.body.p = s.body.p + off;
+  float* o = body_state + ((size_t)env * bpe + lane) * kRec;
+  o[0] = s.body.p.x; o[1] = s.body.p.y; o[2] = s.body.p.z;
+  o[3] = s.body.q.x; o[4] = s.body.q.y; o[5] = s.body.q.z; o[6] = s.body.q.w;
+  o[7] = s.body.v.x; o[8] = s.body.v.y; o[9] = s.body.v.z;
+  o[10] = s.body.w.x; o[11] = s.body.w.y; o[12] = s.body.w.z;
+  if (dof_state && lane > 0) {
+    float* d = dof_state + ((size_t)env * (J - 1) + (lane - 1)) * 6;      // [D, 2] interleaved (pos, vel)
+    d[0] = s.dof_pos.x; d[1] = s.dof_vel.x; d[2] = s.dof_pos.y; d[3] = s.dof_vel.y; d[4] = s.dof_pos.z; d[5] = s.dof_vel.z;
+  }
 }
 
 }  // namespace phc
@@ -235,7 +264,7 @@ extern "C" int phc_motion_state(const PhcMotionLib* lib, const int64_t* ids, con
 extern "C" int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* ids, const float* times0, int64_t n,
                                 int32_t first_step, int32_t num_steps, float dt, uint32_t flags,
                                 const int32_t* key_bodies, int32_t nk, const int32_t* amp_joints, int32_t nj, float* out,
-                                int64_t out_stride, void* stream) {
+                                int64_t out_stride, const int64_t* only_where, void* stream) {
   int rc = check_lib(lib, "phc_amp_obs_demo");
   if (rc) return rc;
   if (!lib->frames_joint) { phc_set_error("phc_amp_obs_demo: needs frames_joint"); return PHC_ERR_INVALID_ARG; }
@@ -247,10 +276,24 @@ extern "C" int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* ids, con
   if (n == 0) return PHC_OK;
   phc::AmpDemoArgs a;
   a.lib = *lib; a.ids = ids; a.times0 = times0; a.n = n; a.first_step = first_step; a.num_steps = num_steps; a.dt = dt;
-  a.flags = flags; a.num_key_bodies = nk; a.amp_joints = amp_joints; a.num_amp_joints = nj; a.out = out; a.out_stride = out_stride;
+  a.flags = flags; a.num_key_bodies = nk; a.amp_joints = amp_joints; a.num_amp_joints = nj; a.out = out; a.out_stride = out_stride; a.only_where = only_where;
   for (int i = 0; i < PHC_MAX_KEY_BODIES; ++i) a.key_bodies[i] = i < nk ? key_bodies[i] : -1;
   const int wpb = 4;
   const int64_t warps = n * num_steps;
   phc::amp_demo_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
   return phc_check_cuda(cudaGetLastError(), "amp_demo_kernel launch");
+}
+
+extern "C" int phc_set_env_state(const PhcMotionLib* lib, const int64_t* ids, const float* times, const float* offset,
+                                 const int64_t* only_where, int64_t n, float* body_state, int32_t bodies_per_env,
+                                 float* dof_state, void* stream) {
+  int rc = check_lib(lib, "phc_set_env_state");
+  if (rc) return rc;
+  if (!ids || !times || !body_state || n < 0 || bodies_per_env < lib->num_bodies) { phc_set_error("phc_set_env_state: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  if (dof_state && !lib->frames_joint) { phc_set_error("phc_set_env_state: dof_state needs frames_joint"); return PHC_ERR_INVALID_ARG; }
+  if (n == 0) return PHC_OK;
+  const int wpb = 4;
+  phc::set_env_state_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      *lib, ids, times, offset, only_where, n, body_state, bodies_per_env, dof_state);
+  return phc_check_cuda(cudaGetLastError(), "set_env_state_kernel launch");
 }

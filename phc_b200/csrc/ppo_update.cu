@@ -1,0 +1,432 @@
+// Learner-side element-wise / reduction kernels of the PPO + AMP update (everything between the GEMMs).
+// Reference (phc/...):  utils/running_mean_std.py:56-109 (RunningMeanStd), learning/common_agent.py:512-587
+// (bound / actor / critic losses), learning/amp_agent.py:554-688 (calc_gradients), :732-804 (_disc_loss),
+// :864-878 (_calc_disc_rewards), :848-853 (_combine_rewards); rl_games==1.1.4 (not in the reference tree):
+// ModelA2CContinuousLogStd (sigma = exp(logstd), neglogp), torch_ext.policy_kl, nn.utils.clip_grad_norm_ + Adam.
+//
+// All of it is HBM-bound streaming over [batch, features] arrays; gradients are written pre-scaled by their loss
+// coefficient and 1/batch so that the backward GEMMs need no extra pass.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/phc_b200.h"
+
+extern "C" void phc_set_error(const char* msg);
+extern "C" int phc_check_cuda(cudaError_t e, const char* what);
+
+namespace phc {
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double wsumd(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// RunningMeanStd
+// ---------------------------------------------------------------------------------------------------------
+// y = clamp((x - mean) / sqrt(var + eps), -5, 5)   (or the un-normalise direction)
+__global__ void rms_apply_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int d,
+                                 const double* __restrict__ mean, const double* __restrict__ var, float eps,
+                                 int unnorm, float* __restrict__ y, int64_t ldy, const int64_t* __restrict__ row_idx) {
+  const int64_t total = n * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / d;
+    const int c = (int)(i - r * d);
+    const float m = (float)mean[c];
+    const float s = sqrtf((float)var[c] + eps);
+    const int64_t rs = row_idx ? row_idx[r] : r;
+    const float v = x[rs * ldx + c];
+    float o;
+    if (unnorm) o = s * fminf(fmaxf(v, -5.0f), 5.0f) + m;
+    else o = fminf(fmaxf((v - m) / s, -5.0f), 5.0f);
+    y[r * ldy + c] = o;
+  }
+}
+
+// column moments in fp64: acc[0:d] += sum, acc[d:2d] += sum of squares   (acc zeroed by the caller)
+__global__ void __launch_bounds__(1024) rms_moments_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int d,
+                                                           double* __restrict__ acc, const int64_t* __restrict__ row_idx) {
+  __shared__ double s1[32][33], s2[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double a = 0.0, b = 0.0;
+  if (c < d)
+    for (int64_t r = (int64_t)blockIdx.y * 32 + threadIdx.y; r < n; r += 32 * (int64_t)gridDim.y) {
+      const double v = (double)x[(row_idx ? row_idx[r] : r) * ldx + c];
+      a += v;
+      b += v * v;
+    }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < d) {
+    double ta = 0.0, tb = 0.0;
+    for (int i = 0; i < 32; ++i) { ta += s1[i][threadIdx.x]; tb += s2[i][threadIdx.x]; }
+    atomicAdd(acc + c, ta);
+    atomicAdd(acc + d + c, tb);
+  }
+}
+
+// parallel-variance merge of the batch moments into the fp64 running stats (running_mean_std.py:56-68, :99-107)
+__global__ void __launch_bounds__(1024) rms_merge_kernel(const double* __restrict__ acc, int64_t n, int d,
+                                                         double* __restrict__ mean, double* __restrict__ var,
+                                                         double* __restrict__ count) {
+  const double cnt = *count;
+  const double bc = (double)n;
+  const double tot = cnt + bc;
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const double bm = acc[c] / bc;
+    double bv = (acc[d + c] - acc[c] * bm) / (bc - 1.0);       // unbiased, torch.var default
+    if (bv < 0.0) bv = 0.0;
+    const double delta = bm - mean[c];
+    const double new_mean = mean[c] + delta * bc / tot;
+    const double m2 = var[c] * cnt + bv * bc + delta * delta * cnt * bc / tot;
+    mean[c] = new_mean;
+    var[c] = m2 / tot;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *count = tot;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Gaussian policy head (rollout): action = mu + sigma * eps, neglogp
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gaussian_sample_kernel(const float* __restrict__ mu, int64_t ldmu,
+                                                              const float* __restrict__ logstd,
+                                                              const float* __restrict__ noise, int64_t n, int A,
+                                                              float* __restrict__ actions, float* __restrict__ neglogp,
+                                                              float* __restrict__ mus, float* __restrict__ sigmas) {
+  const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  float acc = 0.f, ls = 0.f;
+  for (int j = lane; j < A; j += 32) {
+    const float m = mu[r * ldmu + j];
+    const float l = logstd[j];
+    const float sg = expf(l);
+    const float a = m + sg * noise[r * A + j];
+    actions[r * A + j] = a;
+    if (mus) mus[r * A + j] = m;
+    if (sigmas) sigmas[r * A + j] = sg;
+    const float z = (a - m) / sg;
+    acc += z * z;
+    ls += l;
+  }
+  acc = wsum(acc);
+  ls = wsum(ls);
+  if (lane == 0) neglogp[r] = 0.5f * acc + 0.5f * 1.8378770664093453f * (float)A + ls;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// PPO actor loss: neglogp of the stored actions under the new mu, clipped surrogate, bound loss, KL; d(loss)/d(mu)
+// stats[0] += sum a_loss, [1] += sum b_loss, [2] += #clipped, [3] += sum kl, [4] += sum entropy
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+ppo_actor_grad_kernel(const float* __restrict__ mu, int64_t ldmu, const float* __restrict__ logstd,
+                      const float* __restrict__ actions, const float* __restrict__ old_neglogp,
+                      const float* __restrict__ adv, const float* __restrict__ old_mu,
+                      const float* __restrict__ old_sigma, int64_t n, int A, float e_clip, float bound_coef,
+                      float inv_batch, float* __restrict__ dmu, int64_t lddmu, float* __restrict__ stats) {
+  const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  float acc = 0.f, ls = 0.f, bl = 0.f, kl = 0.f;
+  for (int j = lane; j < A; j += 32) {
+    const float m = mu[r * ldmu + j];
+    const float l = logstd[j];
+    const float sg = expf(l);
+    const float z = (actions[r * A + j] - m) / sg;
+    acc += z * z;
+    ls += l;
+    const float hi = fmaxf(m - 1.0f, 0.f), lo = fminf(m + 1.0f, 0.f);
+    bl += lo * lo + hi * hi;
+    const float so = old_sigma[r * A + j], mo = old_mu[r * A + j];
+    kl += logf(so / sg + 1e-5f) + (sg * sg + (mo - m) * (mo - m)) / (2.0f * (so * so + 1e-5f)) - 0.5f;
+  }
+  acc = wsum(acc); ls = wsum(ls); bl = wsum(bl); kl = wsum(kl);
+  const float nlp = 0.5f * acc + 0.5f * 1.8378770664093453f * (float)A + ls;
+  const float ad = adv[r];
+  const float ratio = expf(old_neglogp[r] - nlp);
+  const float s1 = -ad * ratio;
+  const float s2 = -ad * fminf(fmaxf(ratio, 1.0f - e_clip), 1.0f + e_clip);
+  const float a_loss = fmaxf(s1, s2);
+  // d a_loss / d neglogp: the un-clipped branch carries adv*ratio, the clipped one is flat (torch.max tie -> same value)
+  const float g_nlp = (s1 >= s2) ? ad * ratio : 0.f;
+  for (int j = lane; j < A; j += 32) {
+    const float m = mu[r * ldmu + j];
+    const float sg = expf(logstd[j]);
+    const float dn = -(actions[r * A + j] - m) / (sg * sg);            // d neglogp / d mu
+    const float hi = fmaxf(m - 1.0f, 0.f), lo = fminf(m + 1.0f, 0.f);
+    dmu[r * lddmu + j] = inv_batch * (g_nlp * dn + bound_coef * 2.0f * (hi + lo));
+  }
+  if (lane == 0) {
+    atomicAdd(stats + 0, a_loss);
+    atomicAdd(stats + 1, bl);
+    atomicAdd(stats + 2, fabsf(ratio - 1.0f) > e_clip ? 1.0f : 0.0f);
+    atomicAdd(stats + 3, kl);
+    atomicAdd(stats + 4, ls + 0.5f * (1.0f + 1.8378770664093453f) * (float)A);   // Normal entropy summed over actions
+  }
+}
+
+// critic: c_loss = (ret - v)^2 (clip_value False); dv = coef * 2 (v - ret) / batch.   stats[5] += sum c_loss
+__global__ void ppo_critic_grad_kernel(const float* __restrict__ v, int64_t ldv, const float* __restrict__ ret, int64_t n,
+                                       float coef, float inv_batch, float* __restrict__ dv, int64_t lddv,
+                                       float* __restrict__ stats) {
+  float loss = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = v[i * ldv] - ret[i];
+    loss += d * d;
+    dv[i * lddv] = coef * 2.0f * d * inv_batch;
+  }
+  loss = wsum(loss);
+  if ((threadIdx.x & 31) == 0) atomicAdd(stats + 5, loss);
+}
+
+// discriminator prediction loss: BCE-with-logits against 0 (agent + replay rows) / 1 (demo rows), 0.5 * (neg + pos)
+// dl = coef * 0.5 * dBCE/dlogit / rows.  stats[6] += sum softplus(x) agent, [7] += sum softplus(-x) demo,
+// [8] += #(agent logit < 0), [9] += #(demo logit > 0)
+__global__ void disc_logit_grad_kernel(const float* __restrict__ logit, int64_t ld, int64_t n_agent, int64_t n_demo,
+                                       float coef, float* __restrict__ dlogit, int64_t ldd, float* __restrict__ stats) {
+  float la = 0.f, lp = 0.f, ca = 0.f, cd = 0.f;
+  const int64_t n = n_agent + n_demo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = logit[i * ld];
+    const float sp = fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));          // softplus(x)
+    const float sig = 1.0f / (1.0f + expf(-x));
+    if (i < n_agent) {
+      la += sp;
+      ca += (x < 0.f) ? 1.f : 0.f;
+      dlogit[i * ldd] = coef * 0.5f * sig / (float)n_agent;
+    } else {
+      lp += sp - x;                                                    // softplus(-x)
+      cd += (x > 0.f) ? 1.f : 0.f;
+      dlogit[i * ldd] = coef * 0.5f * (sig - 1.0f) / (float)n_demo;
+    }
+  }
+  la = wsum(la); lp = wsum(lp); ca = wsum(ca); cd = wsum(cd);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(stats + 6, la); atomicAdd(stats + 7, lp); atomicAdd(stats + 8, ca); atomicAdd(stats + 9, cd);
+  }
+}
+
+// disc reward (amp_agent.py:864-878) fused with _combine_rewards (:848-853):
+//   r = w_task * task + w_disc * scale * (-log(max(1 - sigmoid(logit), 1e-4)))
+__global__ void disc_reward_kernel(const float* __restrict__ logit, int64_t ld, const float* __restrict__ task, int64_t n,
+                                   float scale, float w_task, float w_disc, float* __restrict__ disc_r,
+                                   float* __restrict__ combined) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float prob = 1.0f / (1.0f + expf(-logit[i * ld]));
+    const float dr = -logf(fmaxf(1.0f - prob, 0.0001f)) * scale;
+    if (disc_r) disc_r[i] = dr;
+    if (combined) combined[i] = w_task * task[i] + w_disc * dr;
+  }
+}
+
+// u[b, j] = (h[b, j] > 0) ? w[j] : 0        (first step of d logit / d input through a ReLU MLP)
+__global__ void relu_mask_row_kernel(const float* __restrict__ h, int64_t ldh, const float* __restrict__ w, int64_t n, int d,
+                                     float* __restrict__ u, int64_t ldu) {
+  const int64_t total = n * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / d;
+    const int c = (int)(i - r * d);
+    u[r * ldu + c] = h[r * ldh + c] > 0.f ? w[c] : 0.f;
+  }
+}
+
+// x *= alpha in place and stats[slot] += sum(x_before^2)      (gradient penalty: g -> dP/dg, keeps sum ||g||^2)
+__global__ void scale_sumsq_kernel(float* __restrict__ x, int64_t ld, int64_t n, int d, float alpha, float* __restrict__ stat) {
+  const int64_t total = n * d;
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / d;
+    const int c = (int)(i - r * d);
+    const float v = x[r * ld + c];
+    s += v * v;
+    x[r * ld + c] = v * alpha;
+  }
+  s = wsum(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(stat, s);
+}
+
+// y += alpha * x over a strided [rows, cols] block (weight decay / logit regulariser gradients)
+__global__ void axpy2d_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, int64_t rows,
+                              int cols, float alpha, float* __restrict__ sumsq_stat) {
+  const int64_t total = rows * cols;
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    const float v = x[r * ldx + c];
+    y[r * ldy + c] += alpha * v;
+    s += v * v;
+  }
+  if (sumsq_stat) {
+    s = wsum(s);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sumsq_stat, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// global-norm clip + Adam on the flat parameter bucket
+// ---------------------------------------------------------------------------------------------------------
+__global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = (double)g[i];
+    s += v * v;
+  }
+  s = wsumd(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+// torch.nn.utils.clip_grad_norm_(max_norm) + torch.optim.Adam(lr, betas, eps, weight_decay=0) in one pass.
+// grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).  sumsq is the squared norm of
+// the UNSCALED g (phc_grad_sumsq).  step_count is the 1-based Adam step.
+__global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, int64_t n, const double* __restrict__ sumsq, float grad_scale,
+                                 float max_norm, float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt) {
+  float clip = 1.0f;
+  if (max_norm > 0.f) {
+    const float total = grad_scale * (float)sqrt(*sumsq);          // norm of the scaled gradient
+    clip = fminf(max_norm / (total + 1e-6f), 1.0f);
+  }
+  const float gs = grad_scale * clip;
+  const float step = lr / bc1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - step * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+
+static inline int ew_grid(int64_t total, int block = 256) {
+  int64_t g = (total + block - 1) / block;
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace phc
+
+using namespace phc;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" int phc_rms_apply(const float* x, int64_t ldx, int64_t n, int32_t d, const double* mean, const double* var,
+                             float eps, int32_t unnorm, float* y, int64_t ldy, const int64_t* row_idx, void* stream) {
+  if (!x || !mean || !var || !y || n < 0 || d < 1 || ldx < d || ldy < d) { phc_set_error("phc_rms_apply: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  if (n == 0) return PHC_OK;
+  rms_apply_kernel<<<ew_grid(n * d), 256, 0, ST(stream)>>>(x, ldx, n, d, mean, var, eps, unnorm, y, ldy, row_idx);
+  return phc_check_cuda(cudaGetLastError(), "rms_apply_kernel");
+}
+
+extern "C" int64_t phc_rms_workspace_bytes(int32_t d) { return (int64_t)2 * d * sizeof(double); }
+
+extern "C" int phc_rms_update(const float* x, int64_t ldx, int64_t n, int32_t d, double* mean, double* var, double* count,
+                              void* workspace, const int64_t* row_idx, void* stream) {
+  if (!x || !mean || !var || !count || !workspace || n < 2 || d < 1 || ldx < d) { phc_set_error("phc_rms_update: bad arguments (needs n >= 2)"); return PHC_ERR_INVALID_ARG; }
+  double* acc = static_cast<double*>(workspace);
+  cudaMemsetAsync(acc, 0, (size_t)2 * d * sizeof(double), ST(stream));
+  int gy = (int)((n + 1023) / 1024); if (gy > 32) gy = 32; if (gy < 1) gy = 1;
+  rms_moments_kernel<<<dim3((d + 31) / 32, gy), dim3(32, 32), 0, ST(stream)>>>(x, ldx, n, d, acc, row_idx);
+  rms_merge_kernel<<<1, 1024, 0, ST(stream)>>>(acc, n, d, mean, var, count);
+  return phc_check_cuda(cudaGetLastError(), "rms_update kernels");
+}
+
+extern "C" int phc_gaussian_sample(const float* mu, int64_t ldmu, const float* logstd, const float* noise, int64_t n,
+                                   int32_t A, float* actions, float* neglogp, float* mus, float* sigmas, void* stream) {
+  if (!mu || !logstd || !noise || !actions || !neglogp || n < 0 || A < 1 || ldmu < A) { phc_set_error("phc_gaussian_sample: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  if (n == 0) return PHC_OK;
+  gaussian_sample_kernel<<<(unsigned)((n + 3) / 4), 128, 0, ST(stream)>>>(mu, ldmu, logstd, noise, n, A, actions, neglogp, mus, sigmas);
+  return phc_check_cuda(cudaGetLastError(), "gaussian_sample_kernel");
+}
+
+extern "C" int phc_ppo_actor_grad(const float* mu, int64_t ldmu, const float* logstd, const float* actions,
+                                  const float* old_neglogp, const float* adv, const float* old_mu, const float* old_sigma,
+                                  int64_t n, int32_t A, float e_clip, float bound_coef, float inv_batch, float* dmu,
+                                  int64_t lddmu, float* stats, void* stream) {
+  if (!mu || !logstd || !actions || !old_neglogp || !adv || !old_mu || !old_sigma || !dmu || !stats || n < 0 || A < 1 || ldmu < A || lddmu < A) {
+    phc_set_error("phc_ppo_actor_grad: bad arguments"); return PHC_ERR_INVALID_ARG;
+  }
+  if (n == 0) return PHC_OK;
+  ppo_actor_grad_kernel<<<(unsigned)((n + 3) / 4), 128, 0, ST(stream)>>>(mu, ldmu, logstd, actions, old_neglogp, adv, old_mu, old_sigma, n, A,
+                                                                         e_clip, bound_coef, inv_batch, dmu, lddmu, stats);
+  return phc_check_cuda(cudaGetLastError(), "ppo_actor_grad_kernel");
+}
+
+extern "C" int phc_ppo_critic_grad(const float* v, int64_t ldv, const float* ret, int64_t n, float coef, float inv_batch,
+                                   float* dv, int64_t lddv, float* stats, void* stream) {
+  if (!v || !ret || !dv || !stats || n < 0 || ldv < 1 || lddv < 1) { phc_set_error("phc_ppo_critic_grad: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  if (n == 0) return PHC_OK;
+  ppo_critic_grad_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(v, ldv, ret, n, coef, inv_batch, dv, lddv, stats);
+  return phc_check_cuda(cudaGetLastError(), "ppo_critic_grad_kernel");
+}
+
+extern "C" int phc_disc_logit_grad(const float* logit, int64_t ld, int64_t n_agent, int64_t n_demo, float coef,
+                                   float* dlogit, int64_t ldd, float* stats, void* stream) {
+  if (!logit || !dlogit || !stats || n_agent < 1 || n_demo < 1 || ld < 1 || ldd < 1) { phc_set_error("phc_disc_logit_grad: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  disc_logit_grad_kernel<<<ew_grid(n_agent + n_demo), 256, 0, ST(stream)>>>(logit, ld, n_agent, n_demo, coef, dlogit, ldd, stats);
+  return phc_check_cuda(cudaGetLastError(), "disc_logit_grad_kernel");
+}
+
+extern "C" int phc_disc_reward(const float* logit, int64_t ld, const float* task_rewards, int64_t n, float scale,
+                               float w_task, float w_disc, float* disc_rewards, float* combined, void* stream) {
+  if (!logit || n < 0 || ld < 1 || (combined && !task_rewards) || (!disc_rewards && !combined)) { phc_set_error("phc_disc_reward: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  if (n == 0) return PHC_OK;
+  disc_reward_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(logit, ld, task_rewards, n, scale, w_task, w_disc, disc_rewards, combined);
+  return phc_check_cuda(cudaGetLastError(), "disc_reward_kernel");
+}
+
+extern "C" int phc_relu_mask_row(const float* h, int64_t ldh, const float* w, int64_t n, int32_t d, float* u, int64_t ldu,
+                                 void* stream) {
+  if (!h || !w || !u || n < 0 || d < 1 || ldh < d || ldu < d) { phc_set_error("phc_relu_mask_row: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  if (n == 0) return PHC_OK;
+  relu_mask_row_kernel<<<ew_grid(n * d), 256, 0, ST(stream)>>>(h, ldh, w, n, d, u, ldu);
+  return phc_check_cuda(cudaGetLastError(), "relu_mask_row_kernel");
+}
+
+extern "C" int phc_scale_sumsq(float* x, int64_t ld, int64_t n, int32_t d, float alpha, float* stat, void* stream) {
+  if (!x || !stat || n < 0 || d < 1 || ld < d) { phc_set_error("phc_scale_sumsq: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  if (n == 0) return PHC_OK;
+  scale_sumsq_kernel<<<ew_grid(n * d), 256, 0, ST(stream)>>>(x, ld, n, d, alpha, stat);
+  return phc_check_cuda(cudaGetLastError(), "scale_sumsq_kernel");
+}
+
+extern "C" int phc_axpy2d(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int32_t cols, float alpha,
+                          float* sumsq_stat, void* stream) {
+  if (!x || !y || rows < 0 || cols < 1 || ldx < cols || ldy < cols) { phc_set_error("phc_axpy2d: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  if (rows == 0) return PHC_OK;
+  axpy2d_kernel<<<ew_grid(rows * cols), 256, 0, ST(stream)>>>(x, ldx, y, ldy, rows, cols, alpha, sumsq_stat);
+  return phc_check_cuda(cudaGetLastError(), "axpy2d_kernel");
+}
+
+extern "C" int phc_grad_sumsq(const float* g, int64_t n, double* out, void* stream) {
+  if (!g || !out || n < 0) { phc_set_error("phc_grad_sumsq: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  cudaMemsetAsync(out, 0, sizeof(double), ST(stream));
+  if (n == 0) return PHC_OK;
+  sumsq_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(g, n, out);
+  return phc_check_cuda(cudaGetLastError(), "sumsq_kernel");
+}
+
+extern "C" int phc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             const double* grad_sumsq, float grad_scale, float max_norm, float lr, float beta1, float beta2,
+                             float eps, int64_t step, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || step < 1 || (max_norm > 0.f && !grad_sumsq)) {
+    phc_set_error("phc_adam_step: bad arguments"); return PHC_ERR_INVALID_ARG;
+  }
+  if (n == 0) return PHC_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_clip_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, grad_sumsq, grad_scale, max_norm, lr,
+                                                       beta1, beta2, eps, (float)bc1, (float)sqrt(bc2));
+  return phc_check_cuda(cudaGetLastError(), "adam_clip_kernel");
+}

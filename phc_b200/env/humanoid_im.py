@@ -1,0 +1,294 @@
+"""HumanoidIm task on the phc_b200 kernels: same buffers, method names and step order as the reference task stack
+
+    BaseTask -> Humanoid -> HumanoidAMP -> HumanoidAMPTask -> HumanoidIm
+    (phc/env/tasks/{base_task,humanoid,humanoid_amp,humanoid_amp_task,humanoid_im}.py)
+
+with the arithmetic of a whole post-physics step in ONE kernel launch (ops.EnvStepPlan -> phc_env_step) and the
+episode-reset path expressed as per-env MASKS instead of `env_ids = dones.nonzero()` index lists, so a rollout step
+needs no device->host synchronisation.
+
+The rigid-body simulator is not part of this package.  `HumanoidIm` talks to it through a small backend object:
+  * `SyntheticSim` (this file): seeded synthetic rigid-body state (bench, tests, smoke -- SURVEY.md section 8d);
+  * an Isaac Gym backend has to expose the same tensors (`rigid_body_state [N, bodies_per_env, 13]`,
+    `dof_state [N, D, 2]`, `dof_force [N, D]`, Humanoid._setup_tensors humanoid.py:179-247) and `simulate(actions)`
+    = pre_physics_step + gym.simulate + refresh (humanoid.py:1522-1619, humanoid_amp.py:639-660); INTEGRATION.md.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from .. import _lib, ops, synthetic as syn
+from ..ops import _ptr, _stream
+
+
+class SyntheticSim:
+    """Stand-in for the simulator: a bank of K seeded rigid-body snapshots that `simulate()` cycles through.
+    With `host_bank=True` the bank lives in pinned host memory and every step pays the host->device copy (the
+    end-to-end measurement of bench.py); otherwise snapshots are device resident."""
+
+    def __init__(self, motion: syn.MotionData, num_envs: int, device, seed: int = 0, bank: int = 4, host_bank: bool = False,
+                 amp_dim: int = 196, amp_steps: int = 10):
+        self.device = torch.device(device)
+        self.num_envs = num_envs
+        states = [syn.make_env_state(motion, num_envs, seed=seed * 100 + k, amp_dim=amp_dim, amp_steps=amp_steps) for k in range(bank)]
+        self.init_state = states[0]
+        keep = lambda ts: torch.stack(ts).pin_memory() if host_bank else torch.stack(ts).to(self.device)
+        self._body = keep([s.body_state for s in states])
+        self._dof = keep([s.dof_state for s in states])
+        self._force = keep([s.dof_force for s in states])
+        self.rigid_body_state = states[0].body_state.to(self.device).clone()
+        self.dof_state = states[0].dof_state.to(self.device).clone()
+        self.dof_force = states[0].dof_force.to(self.device).clone()
+        self.bodies_per_env = self.rigid_body_state.shape[1]
+        self._k = 0
+        self.h2d_bytes_per_step = (self.rigid_body_state.numel() + self.dof_state.numel() + self.dof_force.numel()) * 4 if host_bank else 0
+
+    def simulate(self, actions: Optional[torch.Tensor]) -> None:
+        k = self._k = (self._k + 1) % self._body.shape[0]
+        self.rigid_body_state.copy_(self._body[k], non_blocking=True)
+        self.dof_state.copy_(self._dof[k], non_blocking=True)
+        self.dof_force.copy_(self._force[k], non_blocking=True)
+
+
+class HumanoidIm:
+    """Imitation task.  cfg keys (all optional except the motion data): the `env` block of env_im.yaml plus
+    `motion_data` (synthetic.MotionData or any object with the MotionLibBase table attributes) and `sim` (backend)."""
+
+    def __init__(self, cfg: Dict, sim_params=None, physics_engine=None, device_type: str = "cuda", device_id: int = 0,
+                 headless: bool = True):
+        env = cfg.get("env", cfg)
+        self.cfg = cfg
+        self.device = torch.device(f"{device_type}:{device_id}" if device_type == "cuda" else device_type)
+        torch.cuda.set_device(self.device)
+        self.headless = headless
+        self.num_envs = int(env.get("num_envs", 3072))
+        self.dt = float(env.get("controlFrequencyInv", 2)) * float(cfg.get("sim_dt", 1.0 / 60.0))
+        self.max_episode_length = int(env.get("episode_length", 300))
+        self.humanoid_type = cfg.get("humanoid_type", "smpl")
+        self._num_amp_obs_steps = int(env.get("numAMPObsSteps", 10))
+        self.power_reward = bool(env.get("power_reward", True))
+        self.power_coefficient = float(env.get("power_coefficient", 0.0005))
+        self._fut_tracks = bool(env.get("fut_tracks", False))
+        self._num_traj_samples = int(env.get("numTrajSamples", 3)) if self._fut_tracks else 1
+        self._traj_sample_timestep = 1.0 / float(env.get("trajSampleTimestepInv", 3)) if self._fut_tracks else 0.0
+        self.shape_resampling_interval = int(env.get("shape_resampling_interval", 500))
+        self.temp_running_mean = True
+        self.getup_schedule = False
+        self.kin_lr = False
+        self.fitting = False
+        self.has_task = True
+        self.viewer = None
+        self.cycle_motion = bool(env.get("cycle_motion", False))
+        if self.cycle_motion:
+            raise NotImplementedError("cycle_motion re-basing (humanoid_im.py:1123-1146) is not on the fused path yet")
+
+        # ---- motion library (tables as MotionLibBase keeps them) -> packed device format -----------------------
+        m = cfg["motion_data"]
+        self._motion_data = m
+        d = m.to(self.device) if hasattr(m, "to") else m
+        self._motion_lib = ops.pack_motion_lib(d.gts, d.grs, d.gvs, d.gavs, d.lrs, d.dvs, d.lengths, d.num_frames, d.dts,
+                                               d.length_starts)
+        J = self._motion_lib.num_bodies
+        self.num_bodies = J
+        self.num_dof = 3 * (J - 1)
+        key_bodies = env.get("key_body_ids", syn.SMPL_KEY_BODIES if J == 24 else [J - 1])
+        reset_bodies = env.get("reset_body_ids", syn.SMPL_RESET_BODIES if J == 24 else None)
+        dof_subset = env.get("dof_subset", syn.SMPL_DOF_SUBSET if (J == 24 and cfg.get("has_dof_subset", True)) else None)
+        self.step_cfg = ops.EnvStepConfig(
+            dt=self.dt, time_steps=self._num_traj_samples, traj_dt=self._traj_sample_timestep,
+            upright=bool(cfg.get("has_upright_start", True)), local_root_obs=bool(env.get("local_root_obs", True)),
+            root_height_obs=bool(env.get("root_height_obs", True)), power_reward=self.power_reward,
+            power_coef=self.power_coefficient, early_term=bool(env.get("enableEarlyTermination", True)),
+            key_bodies=key_bodies, reset_bodies=reset_bodies, term_dist=float(env.get("terminationDistance", 0.25)),
+            dof_subset=dof_subset, amp_steps=self._num_amp_obs_steps)
+        self._key_body_ids, self._reset_bodies_id, self.dof_subset = key_bodies, reset_bodies, dof_subset
+
+        # ---- simulator backend and its tensors (Humanoid._setup_tensors) ---------------------------------------
+        self.sim = cfg.get("sim") or SyntheticSim(m, self.num_envs, self.device, seed=int(cfg.get("seed", 0)),
+                                                  host_bank=bool(cfg.get("host_sim_bank", False)))
+        self._rigid_body_state_reshaped = self.sim.rigid_body_state
+        self._rigid_body_pos = self._rigid_body_state_reshaped[..., :J, 0:3]
+        self._rigid_body_rot = self._rigid_body_state_reshaped[..., :J, 3:7]
+        self._rigid_body_vel = self._rigid_body_state_reshaped[..., :J, 7:10]
+        self._rigid_body_ang_vel = self._rigid_body_state_reshaped[..., :J, 10:13]
+        self._dof_state = self.sim.dof_state
+        self._dof_pos, self._dof_vel = self._dof_state[..., 0], self._dof_state[..., 1]
+        self.dof_force_tensor = self.sim.dof_force
+
+        # ---- task buffers (BaseTask buffers base_task.py:99-104 + HumanoidIm extras) ----------------------------
+        N, dev = self.num_envs, self.device
+        i64 = torch.int64
+        self.progress_buf = torch.zeros(N, dtype=i64, device=dev)
+        self._sampled_motion_ids = (torch.arange(N, device=dev) % self._motion_lib.num_motions).to(i64)
+        self._motion_start_times = torch.zeros(N, device=dev)
+        self._motion_start_times_offset = torch.zeros(N, device=dev)
+        self._global_offset = torch.zeros(N, 3, device=dev)
+        self._cycle_counter = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._reset_mask = torch.zeros(N, dtype=i64, device=dev)
+        self.extras: Dict[str, torch.Tensor] = {}
+
+        common = dict(cfg=self.step_cfg, mlib=self._motion_lib, body_state=self._rigid_body_state_reshaped,
+                      dof_state=self._dof_state, dof_force=self.dof_force_tensor, progress=self.progress_buf,
+                      motion_ids=self._sampled_motion_ids, start_times=self._motion_start_times,
+                      start_offsets=self._motion_start_times_offset, global_offset=self._global_offset)
+        self._plan = ops.EnvStepPlan(cycle_counter=self._cycle_counter, with_ref_buffers=True, **common)
+        p = self._plan
+        self.obs_buf, self.rew_buf, self.reward_raw = p.obs, p.rew, p.reward_raw
+        self.reset_buf, self._terminate_buf = p.reset, p.terminate
+        self._amp_obs_buf = p.amp_obs_buf
+        self._curr_amp_obs_buf, self._hist_amp_obs_buf = self._amp_obs_buf[:, 0], self._amp_obs_buf[:, 1:]
+        self.ref_body_pos, self.ref_body_rot, self.ref_body_vel = p.ref_body_pos, p.ref_body_rot, p.ref_body_vel
+        self._num_amp_obs_per_step = p.amp_dim
+        self.self_obs_buf = self.obs_buf[:, :p.self_dim]
+        # observation-only re-computation for just-reset envs (_compute_observations(env_ids))
+        self._plan_reset_obs = ops.EnvStepPlan(obs=self.obs_buf, only_where=self._reset_mask, obs_only=True, with_amp=False, **common)
+        self._lib = _lib.load()
+        self._kb = (C.c_int32 * len(key_bodies))(*[int(b) for b in key_bodies])
+        self.actions = None
+
+    # ---- sizes (Humanoid.get_obs_size & co) --------------------------------------------------------------------
+    def get_obs_size(self):
+        return self._plan.obs_dim
+
+    def get_self_obs_size(self):
+        return self._plan.self_dim
+
+    def get_task_obs_size(self):
+        return self._plan.task_dim
+
+    def get_action_size(self):
+        return self.num_dof
+
+    def get_num_amp_obs(self):
+        return self._num_amp_obs_steps * self._num_amp_obs_per_step
+
+    def get_task_obs_size_detail(self):
+        return [("target", self._plan.task_dim)]
+
+    def get_running_mean_size(self):
+        return (self.get_obs_size(),)
+
+    # ---- step ---------------------------------------------------------------------------------------------------
+    def step(self, actions: torch.Tensor) -> None:
+        """BaseTask.step (base_task.py:216-234): pre-physics + simulate (backend), then post_physics_step."""
+        self.actions = actions
+        self.sim.simulate(actions)
+        self.post_physics_step()
+
+    def post_physics_step(self) -> None:
+        """Humanoid.post_physics_step (humanoid.py:1634-1650) + HumanoidAMP.post_physics_step (humanoid_amp.py:194-210):
+        reward, reset, observations, AMP window -- one launch."""
+        self.progress_buf += 1
+        self._plan.run()
+        self.extras["terminate"] = self._terminate_buf
+        self.extras["reward_raw"] = self.reward_raw
+        self.extras["amp_obs"] = self._amp_obs_buf.view(self.num_envs, self.get_num_amp_obs())
+
+    # kept for API parity: the pieces are produced together by the fused launch
+    def _compute_reward(self, actions=None):
+        self._plan.run()
+
+    def _compute_reset(self):
+        return
+
+    def _compute_observations(self, env_ids=None):
+        self._set_mask(env_ids)
+        self._plan_reset_obs.run()
+        return self.obs_buf
+
+    # ---- reset --------------------------------------------------------------------------------------------------
+    def _set_mask(self, env_ids) -> None:
+        m = self._reset_mask
+        if env_ids is None:
+            m.fill_(1)
+        elif env_ids.dtype == torch.bool or (env_ids.shape == m.shape and env_ids.dtype in (torch.int64, torch.uint8, torch.float32)):
+            m.copy_(env_ids != 0)
+        else:                                           # reference-style index list
+            m.zero_()
+            m[env_ids] = 1
+
+    def _sample_time(self, motion_ids: torch.Tensor) -> torch.Tensor:
+        """MotionLibBase.sample_time_interval (motion_lib_base.py:414-423): start times on the 1/30 s grid."""
+        phase = torch.rand(motion_ids.shape, device=self.device)
+        ln = self._motion_lib.lengths[motion_ids]
+        return ((phase * ln) / (1.0 / 30.0)).long() * (1.0 / 30.0)
+
+    def reset(self, env_ids=None) -> torch.Tensor:
+        """Humanoid.reset -> _reset_envs (humanoid.py:537-621, humanoid_amp.py:378-387,:509-603, humanoid_im.py:955-1023)
+        with reference-state initialisation, for the envs selected by `env_ids` (None = all, a [N] mask, or indices)."""
+        self._set_mask(env_ids)
+        m = self._reset_mask.bool()
+        new_t = self._sample_time(self._sampled_motion_ids).float()
+        self._motion_start_times.copy_(torch.where(m, new_t, self._motion_start_times))
+        self._motion_start_times_offset.masked_fill_(m, 0.0)
+        self._global_offset.masked_fill_(m.unsqueeze(-1), 0.0)
+        self._cycle_counter.masked_fill_(m, 0)
+        self.progress_buf.masked_fill_(m, 0)
+        self.reset_buf.masked_fill_(m, 0)
+        self._terminate_buf.masked_fill_(m, 0)
+        lib, ml, st = self._lib, self._motion_lib, _stream()
+        # _set_env_state: reference pose at the sampled time into the simulator tensors of the reset envs
+        _lib.check(lib.phc_set_env_state(C.byref(ml.c), self._sampled_motion_ids.data_ptr(), self._motion_start_times.data_ptr(),
+                                         self._global_offset.data_ptr(), self._reset_mask.data_ptr(), self.num_envs,
+                                         self._rigid_body_state_reshaped.data_ptr(), self.sim.bodies_per_env,
+                                         self._dof_state.data_ptr(), st), "phc_set_env_state")
+        # _compute_observations(env_ids)
+        self._plan_reset_obs.run()
+        # _init_amp_obs: current + history slots from the reference motion at t0 - k dt
+        ops.amp_obs_demo(ml, self.step_cfg, self._sampled_motion_ids, self._motion_start_times, first_step=0,
+                         num_steps=self._num_amp_obs_steps, out=self._amp_obs_buf, only_where=self._reset_mask)
+        return self.obs_buf
+
+    def resample_motions(self):
+        return
+
+    # ---- discriminator demo observations ------------------------------------------------------------------------
+    def fetch_amp_obs_demo(self, num_samples: int) -> torch.Tensor:
+        """HumanoidAMP.fetch_amp_obs_demo (humanoid_amp.py:215-230): AMP windows of random reference-motion states."""
+        ids = torch.randint(0, self._motion_lib.num_motions, (num_samples,), device=self.device)
+        t0 = (torch.rand(num_samples, device=self.device) * self._motion_lib.lengths[ids]).float()
+        demo = ops.amp_obs_demo(self._motion_lib, self.step_cfg, ids, t0)
+        return demo.view(num_samples, self.get_num_amp_obs())
+
+
+class VecTaskPythonWrapper:
+    """phc/env/tasks/vec_task_wrappers.py:45-81 + VecTaskPython (vec_task.py:150-166)."""
+
+    def __init__(self, task: HumanoidIm, clip_observations: float = float("inf")):
+        self.task = task
+        self.clip_obs = clip_observations
+        self.num_envs = task.num_envs
+
+    def step(self, actions):
+        self.task.step(actions)
+        obs = self.task.obs_buf
+        if self.clip_obs != float("inf"):
+            obs = torch.clamp(obs, -self.clip_obs, self.clip_obs)
+        return obs, self.task.rew_buf, self.task.reset_buf, self.task.extras
+
+    def reset(self, env_ids=None):
+        return self.task.reset(env_ids)
+
+    def fetch_amp_obs_demo(self, num_samples):
+        return self.task.fetch_amp_obs_demo(num_samples)
+
+
+class RLGPUEnv:
+    """phc/run_hydra.py:187-240: the vec-env object the agent holds (`vec_env.env.task` is the HumanoidIm)."""
+
+    def __init__(self, task: HumanoidIm):
+        self.env = VecTaskPythonWrapper(task)
+
+    def step(self, action):
+        obs, rew, reset, extras = self.env.step(action)
+        return {"obs": obs}, rew, reset, extras
+
+    def reset(self, env_ids=None):
+        return {"obs": self.env.reset(env_ids)}
+
+    def get_env_info(self):
+        t = self.env.task
+        return dict(num_obs=t.get_obs_size(), num_actions=t.get_action_size(), num_amp_obs=t.get_num_amp_obs())

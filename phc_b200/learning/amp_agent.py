@@ -1,0 +1,653 @@
+"""AMPAgent: PPO + AMP discriminator training loop on the phc_b200 kernels.
+
+Mirrors the API surface of the reference agent stack so it can stand in for it behind rl_games' runner:
+  CommonAgent (phc/learning/common_agent.py): train / train_epoch / play_steps / discount_values / _calc_advs /
+      prepare_dataset / get_action_values / _eval_critic / bound_loss / _actor_loss / _critic_loss
+  AMPAgent    (phc/learning/amp_agent.py): calc_gradients / _disc_loss / _calc_amp_rewards / _combine_rewards /
+      _preproc_obs / _preproc_amp_obs / get_stats_weights / set_stats_weights / get_full_state_weights / ...
+rl_games==1.1.4 (the real base class, not in the reference tree) is restated where the hot path needs it:
+ExperienceBuffer (time-major [T, N, ...]), swap_and_flatten01, Adam + clip_grad_norm_, Horovod grad averaging
+(-> one NCCL all-reduce on the flat gradient bucket per minibatch).
+
+What runs where: every tensor op on the path is a libphc_b200.so kernel (GEMMs, normalisers, losses, GAE, Adam);
+torch supplies memory, RNG (randn / randperm) and torch.distributed.
+"""
+from __future__ import annotations
+
+import copy
+import os
+import time
+from typing import Dict, Optional
+
+import torch
+
+from .. import _lib, ops
+from ..ops import _ptr, _stream
+from .networks import AMPNetwork, MLPEngine, round4
+
+DEFAULT_CONFIG = dict(          # phc/data/cfg/learning/im.yaml:43-99
+    name="Humanoid", multi_gpu=False, normalize_input=True, normalize_value=True, normalize_advantage=True,
+    gamma=0.99, tau=0.95, learning_rate=2e-5, truncate_grads=True, grad_norm=50.0, e_clip=0.2, horizon_length=32,
+    minibatch_size=16384, mini_epochs=6, critic_coef=5.0, clip_value=False, bounds_loss_coef=10.0, entropy_coef=0.0,
+    amp_obs_demo_buffer_size=200000, amp_replay_buffer_size=200000, amp_replay_keep_prob=0.01, amp_batch_size=512,
+    amp_minibatch_size=4096, disc_coef=5.0, disc_logit_reg=0.01, disc_grad_penalty=5.0, disc_reward_scale=2.0,
+    disc_weight_decay=0.0001, normalize_amp_input=True, task_reward_w=0.5, disc_reward_w=0.5, max_epochs=10000000,
+    save_frequency=2500, save_best_after=100, seed=0,
+    network=dict(mlp=dict(units=[1024, 512], activation="relu"), disc=dict(units=[1024, 512], activation="relu"),
+                 sigma_init=-2.9),
+)
+
+
+class RunningMeanStd:
+    """phc/utils/running_mean_std.py: fp64 running mean / var / count on the device, kernels phc_rms_apply/update."""
+
+    def __init__(self, size: int, device, epsilon: float = 1e-5):
+        self.size, self.epsilon, self.device = int(size), epsilon, torch.device(device)
+        self.running_mean = torch.zeros(size, dtype=torch.float64, device=self.device)
+        self.running_var = torch.ones(size, dtype=torch.float64, device=self.device)
+        self.count = torch.ones((), dtype=torch.float64, device=self.device)
+        self.frozen = False
+        self.training = True
+        self._lib = _lib.load()
+        self._ws = torch.zeros(2 * size, dtype=torch.float64, device=self.device)
+
+    def train(self):
+        self.training = True
+
+    def eval(self):
+        self.training = False
+
+    def freeze(self):
+        self.frozen = True
+
+    def frozen_copy(self) -> "RunningMeanStd":
+        c = RunningMeanStd(self.size, self.device, self.epsilon)
+        c.running_mean.copy_(self.running_mean)
+        c.running_var.copy_(self.running_var)
+        c.count.copy_(self.count)
+        c.frozen = True
+        return c
+
+    def apply(self, x: torch.Tensor, out: torch.Tensor, unnorm: bool = False, row_idx: Optional[torch.Tensor] = None,
+              n: Optional[int] = None) -> torch.Tensor:
+        n = (x.shape[0] if row_idx is None else row_idx.shape[0]) if n is None else n
+        rc = self._lib.phc_rms_apply(x.data_ptr(), x.stride(0), n, self.size, self.running_mean.data_ptr(),
+                                     self.running_var.data_ptr(), self.epsilon, 1 if unnorm else 0, out.data_ptr(),
+                                     out.stride(0), _ptr(row_idx), _stream())
+        if rc:
+            _lib.check(rc, "phc_rms_apply")
+        return out
+
+    def update(self, x: torch.Tensor, n: Optional[int] = None, row_idx: Optional[torch.Tensor] = None) -> None:
+        n = (x.shape[0] if row_idx is None else row_idx.shape[0]) if n is None else n
+        rc = self._lib.phc_rms_update(x.data_ptr(), x.stride(0), n, self.size, self.running_mean.data_ptr(),
+                                      self.running_var.data_ptr(), self.count.data_ptr(), self._ws.data_ptr(),
+                                      _ptr(row_idx), _stream())
+        if rc:
+            _lib.check(rc, "phc_rms_update")
+
+    def __call__(self, x: torch.Tensor, unnorm: bool = False) -> torch.Tensor:
+        """RunningMeanStd.forward: normalise (then, in train mode and not frozen, fold the batch into the stats)."""
+        x2 = x.reshape(-1, self.size)
+        out = torch.empty_like(x2)
+        self.apply(x2, out, unnorm)
+        if self.training and not self.frozen and not unnorm:
+            self.update(x2)
+        return out.view(x.shape)
+
+    def state_dict(self):
+        return {"running_mean": self.running_mean.clone(), "running_var": self.running_var.clone(), "count": self.count.clone()}
+
+    def load_state_dict(self, sd):
+        self.running_mean.copy_(sd["running_mean"].to(self.device))
+        self.running_var.copy_(sd["running_var"].to(self.device))
+        self.count.copy_(sd["count"].to(self.device))
+
+
+class ReplayBuffer:
+    """phc/learning/replay_buffer.py with index-returning sampling (rows are gathered later, once, by the consumer)."""
+
+    def __init__(self, buffer_size: int, width: int, device):
+        self._size, self._head, self._total, self.device = int(buffer_size), 0, 0, torch.device(device)
+        self.data = torch.zeros(self._size, width, dtype=torch.float32, device=self.device)
+        self._sample_idx = torch.randperm(self._size, device=self.device)
+        self._sample_head = 0
+
+    def get_buffer_size(self):
+        return self._size
+
+    def get_total_count(self):
+        return self._total
+
+    def store(self, rows: torch.Tensor) -> None:
+        n = rows.shape[0]
+        assert n <= self._size
+        first = min(n, self._size - self._head)
+        self.data[self._head:self._head + first] = rows[:first]
+        if n > first:
+            self.data[0:n - first] = rows[first:]
+        self._head = (self._head + n) % self._size
+        self._total += n
+
+    def sample_indices(self, n: int) -> torch.Tensor:
+        idx = (torch.arange(self._sample_head, self._sample_head + n, device=self.device)) % self._size
+        rand_idx = self._sample_idx[idx]
+        if self._total < self._size:
+            rand_idx = rand_idx % self._head
+        self._sample_head += n
+        if self._sample_head >= self._size:
+            self._sample_idx = torch.randperm(self._size, device=self.device)
+            self._sample_head = 0
+        return rand_idx
+
+
+class AMPAgent:
+    def __init__(self, base_name: str, config: Dict):
+        cfg = copy.deepcopy(DEFAULT_CONFIG)
+        cfg.update({k: v for k, v in config.items() if k != "network"})
+        if "network" in config:
+            cfg["network"].update(config["network"])
+        self.config = cfg
+        self.base_name = base_name
+        self.vec_env = cfg["vec_env"]
+        task = self.vec_env.env.task
+        self.device = torch.device(cfg.get("device", task.device))
+        self.ppo_device = self.device
+        torch.cuda.set_device(self.device)
+        self._lib = _lib.load()
+
+        self.num_actors = task.num_envs
+        self.num_agents = 1
+        self.horizon_length = int(cfg["horizon_length"])
+        self.batch_size = self.horizon_length * self.num_actors
+        self.minibatch_size = min(int(cfg["minibatch_size"]), self.batch_size)
+        assert self.batch_size % self.minibatch_size == 0
+        self.num_minibatches = self.batch_size // self.minibatch_size
+        self.mini_epochs_num = int(cfg["mini_epochs"])
+        self.gamma, self.tau, self.e_clip = float(cfg["gamma"]), float(cfg["tau"]), float(cfg["e_clip"])
+        self.last_lr = float(cfg["learning_rate"])
+        self.critic_coef, self.bounds_loss_coef = float(cfg["critic_coef"]), float(cfg["bounds_loss_coef"])
+        self.entropy_coef = float(cfg["entropy_coef"])
+        self.truncate_grads, self.grad_norm = bool(cfg["truncate_grads"]), float(cfg["grad_norm"])
+        self.normalize_input, self.normalize_value = bool(cfg["normalize_input"]), bool(cfg["normalize_value"])
+        self.normalize_advantage = bool(cfg["normalize_advantage"])
+        self._task_reward_w, self._disc_reward_w = float(cfg["task_reward_w"]), float(cfg["disc_reward_w"])
+        self._amp_batch_size = int(cfg["amp_batch_size"])
+        self._amp_minibatch_size = min(int(cfg["amp_minibatch_size"]), self.minibatch_size)
+        self._disc_coef, self._disc_logit_reg = float(cfg["disc_coef"]), float(cfg["disc_logit_reg"])
+        self._disc_grad_penalty, self._disc_weight_decay = float(cfg["disc_grad_penalty"]), float(cfg["disc_weight_decay"])
+        self._disc_reward_scale = float(cfg["disc_reward_scale"])
+        self._normalize_amp_input = bool(cfg["normalize_amp_input"])
+        self._amp_replay_keep_prob = float(cfg["amp_replay_keep_prob"])
+        self.temp_running_mean = getattr(task, "temp_running_mean", True)
+
+        self.obs_dim = task.get_obs_size()
+        self.actions_num = task.get_action_size()
+        self.amp_obs_dim = task.get_num_amp_obs()
+        self.obs_pad, self.amp_pad, self.act_pad = round4(self.obs_dim), round4(self.amp_obs_dim), round4(self.actions_num)
+
+        # multi-GPU: one process per GPU, gradients summed over NCCL and scaled by 1/world (replaces Horovod,
+        # phc/run_hydra.py:114-128 / amp_agent.py:668)
+        self.multi_gpu = bool(cfg.get("multi_gpu", False)) and torch.distributed.is_available() and torch.distributed.is_initialized()
+        self.rank = torch.distributed.get_rank() if self.multi_gpu else 0
+        self.world = torch.distributed.get_world_size() if self.multi_gpu else 1
+
+        netcfg = cfg["network"]
+        self.model = AMPNetwork(self.obs_dim, self.actions_num, self.amp_obs_dim, netcfg["mlp"]["units"],
+                                netcfg["disc"]["units"], netcfg["mlp"]["activation"], netcfg.get("sigma_init", -2.9),
+                                device=self.device, seed=int(cfg["seed"]))
+        if self.multi_gpu:
+            torch.distributed.broadcast(self.model.params, 0)
+        self.engine = MLPEngine(self.model)
+        n = self.model.num_floats
+        self.exp_avg = torch.zeros(n, device=self.device)
+        self.exp_avg_sq = torch.zeros(n, device=self.device)
+        self.opt_step = 0
+        self._gsumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
+
+        self.running_mean_std = RunningMeanStd(self.obs_dim, self.device) if self.normalize_input else None
+        self.value_mean_std = RunningMeanStd(1, self.device) if self.normalize_value else None
+        self._amp_input_mean_std = RunningMeanStd(self.amp_obs_dim, self.device) if self._normalize_amp_input else None
+        self.running_mean_std_temp = self.running_mean_std.frozen_copy() if self.normalize_input else None
+
+        self._init_buffers()
+        self.epoch_num = 0
+        self.frame = 0
+        self.obs = None
+        self.train_result = {}
+        self.set_eval()
+
+    # ------------------------------------------------------------------------------------------------------
+    def set_eval(self):
+        for r in (self.running_mean_std, self.value_mean_std, self._amp_input_mean_std):
+            if r is not None:
+                r.eval()
+
+    def set_train(self):
+        for r in (self.running_mean_std, self.value_mean_std, self._amp_input_mean_std):
+            if r is not None:
+                r.train()
+
+    def _init_buffers(self):
+        T, N, dev = self.horizon_length, self.num_actors, self.device
+        z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=dev)
+        # rl_games ExperienceBuffer: time-major [T, N, ...]
+        self.experience_buffer = {
+            "obses": z(T, N, self.obs_dim), "next_obses": z(T, N, self.obs_dim), "rewards": z(T, N, 1),
+            "values": z(T, N, 1), "next_values": z(T, N, 1), "dones": z(T, N), "actions": z(T, N, self.actions_num),
+            "mus": z(T, N, self.actions_num), "sigmas": z(T, N, self.actions_num), "neglogpacs": z(T, N),
+            "amp_obs": z(T, N, self.amp_obs_dim),
+        }
+        self.tensor_list = ["obses", "next_obses", "actions", "mus", "sigmas", "neglogpacs", "values", "amp_obs"]
+        self._amp_obs_demo_buffer = ReplayBuffer(int(self.config["amp_obs_demo_buffer_size"]), self.amp_obs_dim, dev)
+        self._amp_replay_buffer = ReplayBuffer(int(self.config["amp_replay_buffer_size"]), self.amp_obs_dim, dev)
+        # inference workspaces (rollout batch = N)
+        self._x_roll = z(N, self.obs_pad)
+        self._val_roll = z(N, 1)
+        self._noise = z(N, self.actions_num)
+        self._ws_actor_roll = self.engine.workspace("actor_roll", self.model.actor, N)
+        self._ws_critic_roll = self.engine.workspace("critic_roll", self.model.critic, N)
+        # update workspaces (minibatch B, amp minibatch Bd)
+        B, Bd = self.minibatch_size, self._amp_minibatch_size
+        self._x_mb = z(B, self.obs_pad)
+        self._ws_actor = self.engine.workspace("actor", self.model.actor, B)
+        self._ws_critic = self.engine.workspace("critic", self.model.critic, B)
+        self._amp_mb = z(3 * Bd, self.amp_pad)           # rows: [agent | replay | demo]
+        self._ws_disc = self.engine.workspace("disc", self.model.disc, 3 * Bd)
+        du = self.model.disc.hidden
+        self._gp_u = [z(Bd, round4(l.out_dim)) for l in du]
+        self._gp_e = [z(Bd, round4(l.out_dim)) for l in du]
+        self._gp_g = z(Bd, self.amp_pad)
+        self._stats = z(16)
+        # disc reward over the whole rollout, evaluated in chunks of the amp update batch
+        self._ws_disc_r = self.engine.workspace("disc_r", self.model.disc, 3 * Bd)
+        self.game_rewards = z(N)
+        self.current_rewards = z(N)
+        self.current_lengths = z(N)
+
+    # ------------------------------------------------------------------------------------------------------
+    # observation / value pre-processing
+    # ------------------------------------------------------------------------------------------------------
+    def _preproc_obs(self, obs_batch: torch.Tensor, use_temp: bool = False, out: Optional[torch.Tensor] = None,
+                     row_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """AMPAgent._preproc_obs (amp_agent.py:535-552): normalise with the live or the frozen statistics; with
+        use_temp the live statistics are still updated by the batch (train mode)."""
+        n = obs_batch.shape[0] if row_idx is None else row_idx.shape[0]
+        if out is None:
+            out = torch.zeros(n, self.obs_pad, device=self.device)
+        if not self.normalize_input:
+            src = obs_batch if row_idx is None else obs_batch[row_idx]
+            out[:, :self.obs_dim] = src
+            return out
+        rms = self.running_mean_std_temp if use_temp else self.running_mean_std
+        rms.apply(obs_batch, out, row_idx=row_idx)
+        if self.running_mean_std.training and not self.running_mean_std.frozen:
+            self.running_mean_std.update(obs_batch, row_idx=row_idx)      # statistics of the RAW rows, gathered in-kernel
+        return out
+
+    def _preproc_amp_obs(self, amp_obs: torch.Tensor, out: torch.Tensor, row_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self._normalize_amp_input:
+            self._amp_input_mean_std.apply(amp_obs, out, row_idx=row_idx)
+            if self._amp_input_mean_std.training:
+                self._amp_input_mean_std.update(amp_obs, row_idx=row_idx)
+        else:
+            out[:, :self.amp_obs_dim] = amp_obs if row_idx is None else amp_obs[row_idx]
+        return out
+
+    # ------------------------------------------------------------------------------------------------------
+    # rollout
+    # ------------------------------------------------------------------------------------------------------
+    def get_action_values(self, obs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """CommonAgent.get_action_values (common_agent.py:262-288): normalise, actor + critic forward, sample."""
+        N = self.num_actors
+        x = self._preproc_obs(obs["obs"], out=self._x_roll)
+        mu = self.engine.forward(self.model.actor, x, self._ws_actor_roll)
+        val = self.engine.forward(self.model.critic, x, self._ws_critic_roll)
+        torch.randn(self._noise.shape, out=self._noise)
+        res = {"actions": torch.empty(N, self.actions_num, device=self.device),
+               "neglogpacs": torch.empty(N, device=self.device),
+               "mus": torch.empty(N, self.actions_num, device=self.device),
+               "sigmas": torch.empty(N, self.actions_num, device=self.device)}
+        rc = self._lib.phc_gaussian_sample(mu.data_ptr(), mu.stride(0), self.model.sigma.data_ptr(), self._noise.data_ptr(), N,
+                                           self.actions_num, res["actions"].data_ptr(), res["neglogpacs"].data_ptr(),
+                                           res["mus"].data_ptr(), res["sigmas"].data_ptr(), _stream())
+        if rc:
+            _lib.check(rc, "phc_gaussian_sample")
+        res["values"] = self._unnorm_value(val[:, :1])
+        return res
+
+    def _unnorm_value(self, v: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(v.shape[0], 1, device=self.device)
+        if self.normalize_value:
+            self.value_mean_std.apply(v, out, unnorm=True)
+        else:
+            out.copy_(v)
+        return out
+
+    def _eval_critic(self, obs_dict: Dict[str, torch.Tensor]) -> torch.Tensor:
+        x = self._preproc_obs(obs_dict["obs"], out=self._x_roll)
+        val = self.engine.forward(self.model.critic, x, self._ws_critic_roll)
+        return self._unnorm_value(val[:, :1])
+
+    def env_reset(self, env_ids=None):
+        return self.vec_env.reset(env_ids)
+
+    def env_step(self, actions):
+        obs, rewards, dones, infos = self.vec_env.step(actions)
+        return obs, rewards.unsqueeze(1), dones, infos
+
+    def play_steps(self) -> Dict[str, torch.Tensor]:
+        """AMPAgent.play_steps (amp_agent.py:309-397).  Episode resets are handed to the env as the done MASK of the
+        previous step (no nonzero() / host sync on the path)."""
+        self.set_eval()
+        eb = self.experience_buffer
+        terminated_flags = torch.zeros(self.num_actors, device=self.device)
+        reward_raw = None
+        done_mask = None
+        for n in range(self.horizon_length):
+            self.obs = self.env_reset(done_mask)
+            eb["obses"][n].copy_(self.obs["obs"])
+            res = self.get_action_values(self.obs)
+            for k in ("actions", "neglogpacs", "values", "mus", "sigmas"):
+                eb[k][n].copy_(res[k])
+            self.obs, rewards, self.dones, infos = self.env_step(res["actions"])
+            eb["rewards"][n].copy_(rewards)
+            eb["next_obses"][n].copy_(self.obs["obs"])
+            eb["dones"][n].copy_(self.dones)
+            eb["amp_obs"][n].copy_(infos["amp_obs"])
+            terminated = infos["terminate"].float()
+            terminated_flags += terminated
+            rr = infos["reward_raw"].mean(dim=0)
+            reward_raw = rr if reward_raw is None else reward_raw + rr
+            next_vals = self._eval_critic(self.obs)
+            next_vals *= (1.0 - terminated.unsqueeze(-1))
+            eb["next_values"][n].copy_(next_vals)
+            not_dones = 1.0 - self.dones.float()
+            self.current_rewards = (self.current_rewards + rewards.squeeze(1)) * not_dones
+            self.current_lengths = (self.current_lengths + 1) * not_dones
+            done_mask = self.dones
+
+        mb_fdones = eb["dones"]
+        amp_rewards = self._calc_amp_rewards(eb["amp_obs"])
+        mb_rewards = self._combine_rewards(eb["rewards"], amp_rewards)
+        mb_advs = self.discount_values(mb_fdones, eb["values"], mb_rewards, eb["next_values"])
+        mb_returns = self._last_returns
+        flat = lambda t: t.transpose(0, 1).reshape(self.batch_size, *t.shape[2:])      # swap_and_flatten01
+        batch_dict = {k: flat(eb[k]) for k in self.tensor_list}
+        batch_dict["returns"] = flat(mb_returns)
+        batch_dict["terminated_flags"] = terminated_flags
+        batch_dict["reward_raw"] = reward_raw / self.horizon_length
+        batch_dict["played_frames"] = self.batch_size
+        batch_dict["disc_rewards"] = flat(amp_rewards["disc_rewards"])
+        batch_dict["mb_rewards"] = flat(mb_rewards)
+        batch_dict["mb_advs"] = flat(mb_advs)
+        return batch_dict
+
+    # ------------------------------------------------------------------------------------------------------
+    # rewards / GAE / advantages
+    # ------------------------------------------------------------------------------------------------------
+    def _calc_amp_rewards(self, amp_obs: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """AMPAgent._calc_amp_rewards / _calc_disc_rewards (amp_agent.py:859-878) over the whole rollout."""
+        flat = amp_obs.reshape(-1, self.amp_obs_dim)
+        total = flat.shape[0]
+        disc_r = torch.empty(total, device=self.device)
+        chunk = self._amp_mb.shape[0]
+        for s in range(0, total, chunk):
+            n = min(chunk, total - s)
+            if self._normalize_amp_input:
+                self._amp_input_mean_std.apply(flat[s:s + n], self._amp_mb, n=n)
+            else:
+                self._amp_mb[:n, :self.amp_obs_dim].copy_(flat[s:s + n])
+            logits = self.engine.forward(self.model.disc, self._amp_mb, self._ws_disc_r)
+            rc = self._lib.phc_disc_reward(logits.data_ptr(), logits.stride(0), None, n, self._disc_reward_scale, 0.0, 0.0,
+                                           disc_r[s:].data_ptr(), None, _stream())
+            if rc:
+                _lib.check(rc, "phc_disc_reward")
+        return {"disc_rewards": disc_r.view(*amp_obs.shape[:-1], 1)}
+
+    def _combine_rewards(self, task_rewards: torch.Tensor, amp_rewards: Dict[str, torch.Tensor]) -> torch.Tensor:
+        return self._task_reward_w * task_rewards + self._disc_reward_w * amp_rewards["disc_rewards"]
+
+    def discount_values(self, mb_fdones, mb_values, mb_rewards, mb_next_values) -> torch.Tensor:
+        """CommonAgent.discount_values (common_agent.py:493-505) -> phc_gae (also keeps returns = advs + values)."""
+        advs, rets = ops.gae(mb_fdones.float().contiguous(), mb_values.contiguous(), mb_rewards.contiguous(),
+                             mb_next_values.contiguous(), self.gamma, self.tau)
+        self._last_returns = rets
+        return advs
+
+    def _calc_advs(self, batch_dict) -> torch.Tensor:
+        return ops.adv_norm(batch_dict["returns"].contiguous(), batch_dict["values"].contiguous(), self.normalize_advantage)
+
+    def prepare_dataset(self, batch_dict) -> Dict[str, torch.Tensor]:
+        """CommonAgent.prepare_dataset (:357-398) + AMPAgent.prepare_dataset (amp_agent.py:399-411)."""
+        advantages = self._calc_advs(batch_dict)
+        values, returns = batch_dict["values"], batch_dict["returns"]
+        if self.normalize_value:
+            values, returns = self.value_mean_std(values), self.value_mean_std(returns)
+        self.dataset = dict(old_values=values, old_logp_actions=batch_dict["neglogpacs"], advantages=advantages,
+                            returns=returns, actions=batch_dict["actions"], obs=batch_dict["obses"], mu=batch_dict["mus"],
+                            sigma=batch_dict["sigmas"], amp_obs=batch_dict["amp_obs"],
+                            amp_obs_demo_idx=batch_dict["amp_obs_demo_idx"], amp_obs_replay_idx=batch_dict["amp_obs_replay_idx"])
+        self._idx_buf = torch.randperm(self.batch_size, device=self.device)
+        return self.dataset
+
+    # ------------------------------------------------------------------------------------------------------
+    # update
+    # ------------------------------------------------------------------------------------------------------
+    def calc_gradients(self, input_dict: Dict[str, torch.Tensor]) -> None:
+        """One PPO/AMP minibatch: forward, losses, backward into the flat gradient bucket, all-reduce, clip, Adam.
+        input_dict carries `idx` (rows of the epoch dataset) instead of materialised copies of the big tensors
+        (AMPDataset._get_item gathers ~0.5 GB per minibatch of which 3/4 of the AMP rows are dropped afterwards)."""
+        self.set_train()
+        lib, net, eng = self._lib, self.model, self.engine
+        ds = self.dataset
+        idx = input_dict["idx"]
+        B, Bd, A = idx.shape[0], self._amp_minibatch_size, self.actions_num
+        inv_b = 1.0 / B
+        st = _stream()
+        self._stats.zero_()
+        net.grads.zero_()
+
+        # ---- actor / critic ----------------------------------------------------------------------------------
+        x = self._preproc_obs(ds["obs"], use_temp=self.temp_running_mean, out=self._x_mb, row_idx=idx)
+        mu = eng.forward(net.actor, x, self._ws_actor)
+        val = eng.forward(net.critic, x, self._ws_critic)
+        actions, old_nlp, adv = ds["actions"][idx], ds["old_logp_actions"][idx], ds["advantages"][idx]
+        old_mu, old_sigma, rets = ds["mu"][idx], ds["sigma"][idx], ds["returns"][idx].reshape(-1)
+        dmu, dv = self._ws_actor["dout"], self._ws_critic["dout"]
+        _lib.check(lib.phc_ppo_actor_grad(mu.data_ptr(), mu.stride(0), net.sigma.data_ptr(), actions.data_ptr(), old_nlp.data_ptr(),
+                                          adv.data_ptr(), old_mu.data_ptr(), old_sigma.data_ptr(), B, A, self.e_clip,
+                                          self.bounds_loss_coef, inv_b, dmu.data_ptr(), dmu.stride(0), self._stats.data_ptr(), st))
+        _lib.check(lib.phc_ppo_critic_grad(val.data_ptr(), val.stride(0), rets.data_ptr(), B, self.critic_coef, inv_b,
+                                           dv.data_ptr(), dv.stride(0), self._stats.data_ptr(), st))
+        eng.backward(net.actor, x, self._ws_actor)
+        eng.backward(net.critic, x, self._ws_critic)
+
+        # ---- discriminator: rows [agent | replay | demo] of the first Bd minibatch samples ---------------------
+        aidx = idx[:Bd]
+        xa = self._amp_mb
+        self._preproc_amp_obs(ds["amp_obs"], xa[0:Bd], row_idx=aidx)
+        self._preproc_amp_obs(self._amp_replay_src, xa[Bd:2 * Bd], row_idx=ds["amp_obs_replay_idx"][aidx])
+        self._preproc_amp_obs(self._amp_obs_demo_buffer.data, xa[2 * Bd:3 * Bd], row_idx=ds["amp_obs_demo_idx"][aidx])
+        logits = eng.forward(net.disc, xa, self._ws_disc)
+        dl = self._ws_disc["dout"]
+        _lib.check(lib.phc_disc_logit_grad(logits.data_ptr(), logits.stride(0), 2 * Bd, Bd, self._disc_coef, dl.data_ptr(),
+                                           dl.stride(0), self._stats.data_ptr(), st))
+        eng.backward(net.disc, xa, self._ws_disc)
+        self._disc_grad_penalty_backward(xa[2 * Bd:3 * Bd], [h[2 * Bd:3 * Bd] for h in self._ws_disc["h"]], Bd)
+        # logit regulariser and weight decay (amp_agent.py:745-747, :771-775): d/dW (c * sum W^2) = 2 c W
+        head = net.disc.head
+        _lib.check(lib.phc_axpy2d(net.weight(head).data_ptr(), head.in_pad, net.weight(head, True).data_ptr(), head.in_pad, 1,
+                                  head.in_dim, 2.0 * self._disc_coef * self._disc_logit_reg, self._stats[11:].data_ptr(), st))
+        if self._disc_weight_decay != 0:
+            for l in net.disc.layers:
+                _lib.check(lib.phc_axpy2d(net.weight(l).data_ptr(), l.in_pad, net.weight(l, True).data_ptr(), l.in_pad, l.out_dim,
+                                          l.in_dim, 2.0 * self._disc_coef * self._disc_weight_decay, self._stats[12:].data_ptr(), st))
+
+        # ---- all-reduce, clip, Adam -----------------------------------------------------------------------------
+        if self.multi_gpu:
+            torch.distributed.all_reduce(net.grads)
+        self.opt_step += 1
+        _lib.check(lib.phc_grad_sumsq(net.grads.data_ptr(), net.num_floats, self._gsumsq.data_ptr(), st))
+        _lib.check(lib.phc_adam_step(net.params.data_ptr(), net.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                     net.num_floats, self._gsumsq.data_ptr(), 1.0 / self.world,
+                                     self.grad_norm if self.truncate_grads else 0.0, self.last_lr, 0.9, 0.999, 1e-8,
+                                     self.opt_step, st))
+        self._last_B, self._last_Bd = B, Bd
+
+    def _disc_grad_penalty_backward(self, x_demo: torch.Tensor, h_demo, Bd: int) -> None:
+        """Gradient penalty 5 * mean_b ||d logit_b / d x_b||^2 on the demo rows (amp_agent.py:749-768), hand-derived for
+        the ReLU MLP (the reference uses autograd.grad(create_graph=True)):
+            u_L = relu'(z_L) * w_head ; u_{l-1} = relu'(z_{l-1}) * (u_l W_l) ; g = u_1 W_1
+            P = c/B sum ||g||^2 ; dP/dg = 2c/B g ; dP/dW_1 += u_1^T dg ; e_1 = relu'(z_1) * (dg W_1^T) ;
+            dP/dW_l += u_{l-1}^T e_{l-1}... ; dP/dw_head += colsum(relu'(z_L) * (e W^T))
+        second derivatives of ReLU vanish, so the masks are constants."""
+        lib, net, eng, st = self._lib, self.model, self.engine, _stream()
+        hid = net.disc.hidden
+        L = len(hid)
+        head = net.disc.head
+        u, e = self._gp_u, self._gp_e
+        # forward of the input-gradient: top mask times the head weights, then down through the layers
+        _lib.check(lib.phc_relu_mask_row(h_demo[L - 1].data_ptr(), h_demo[L - 1].stride(0), net.weight(head).data_ptr(), Bd,
+                                         hid[L - 1].out_dim, u[L - 1].data_ptr(), u[L - 1].stride(0), st))
+        for li in range(L - 1, 0, -1):
+            l = hid[li]
+            eng.gemm(u[li], True, net.weight(l), False, u[li - 1], Bd, l.in_dim, l.out_dim, mask=h_demo[li - 1])
+        l0 = hid[0]
+        eng.gemm(u[0], True, net.weight(l0), False, self._gp_g, Bd, l0.in_dim, l0.out_dim)
+        c = self._disc_coef * self._disc_grad_penalty
+        _lib.check(lib.phc_scale_sumsq(self._gp_g.data_ptr(), self._gp_g.stride(0), Bd, l0.in_dim, 2.0 * c / Bd,
+                                       self._stats[10:].data_ptr(), st))
+        # backward of that chain
+        tiles = lambda l: ((l.out_dim + 127) // 128) * ((l.in_dim + 127) // 128)
+        from .networks import _splits
+        eng.gemm(u[0], False, self._gp_g, False, net.weight(l0, True), l0.out_dim, l0.in_dim, Bd, accumulate=True,
+                 k_splits=_splits(tiles(l0), Bd))
+        eng.gemm(self._gp_g, True, net.weight(l0), True, e[0], Bd, l0.out_dim, l0.in_dim, mask=h_demo[0])
+        for li in range(1, L):
+            l = hid[li]
+            eng.gemm(u[li], False, e[li - 1], False, net.weight(l, True), l.out_dim, l.in_dim, Bd, accumulate=True,
+                     k_splits=_splits(tiles(l), Bd))
+            eng.gemm(e[li - 1], True, net.weight(l), True, e[li], Bd, l.out_dim, l.in_dim, mask=h_demo[li])
+        eng.colsum(e[L - 1], Bd, hid[L - 1].out_dim, net.weight(head, True))
+
+    def train_result_dict(self) -> Dict[str, float]:
+        """Scalars of the last minibatch (one device->host read; call outside the timed path)."""
+        s = self._stats.tolist()
+        B, Bd = self._last_B, self._last_Bd
+        return dict(actor_loss=s[0] / B, b_loss=s[1] / B, actor_clip_frac=s[2] / B, kl=s[3] / B, entropy=s[4] / B,
+                    critic_loss=s[5] / B, disc_loss_agent=s[6] / (2 * Bd), disc_loss_demo=s[7] / Bd,
+                    disc_agent_acc=s[8] / (2 * Bd), disc_demo_acc=s[9] / Bd, disc_grad_penalty=s[10] / Bd,
+                    disc_logit_loss=s[11])
+
+    def pre_epoch(self, epoch_num: int) -> None:
+        if self.normalize_input:
+            self.running_mean_std_temp = self.running_mean_std.frozen_copy()   # amp_agent.py:527-528
+
+    def post_epoch(self, epoch_num: int) -> None:
+        if self.normalize_input:
+            self.running_mean_std_temp = self.running_mean_std.frozen_copy()
+
+    def _update_amp_demos(self) -> None:
+        self._amp_obs_demo_buffer.store(self.vec_env.env.fetch_amp_obs_demo(self._amp_batch_size))
+
+    def _init_amp_demo_buf(self) -> None:
+        size = self._amp_obs_demo_buffer.get_buffer_size()
+        for _ in range((size + self._amp_batch_size - 1) // self._amp_batch_size):
+            self._update_amp_demos()
+
+    def _store_replay_amp_obs(self, amp_obs: torch.Tensor) -> None:
+        """amp_agent.py:880-894."""
+        buf = self._amp_replay_buffer
+        if buf.get_total_count() > buf.get_buffer_size():
+            keep = torch.rand(amp_obs.shape[0], device=self.device) < self._amp_replay_keep_prob
+            amp_obs = amp_obs[keep]
+        if amp_obs.shape[0] > buf.get_buffer_size():
+            amp_obs = amp_obs[torch.randperm(amp_obs.shape[0], device=self.device)[:buf.get_buffer_size()]]
+        buf.store(amp_obs)
+
+    def train_epoch(self) -> Dict[str, torch.Tensor]:
+        """AMPAgent.train_epoch (amp_agent.py:413-504)."""
+        self.pre_epoch(self.epoch_num)
+        t0 = time.time()
+        batch_dict = self.play_steps()
+        t1 = time.time()
+        self._update_amp_demos()
+        n = batch_dict["amp_obs"].shape[0]
+        batch_dict["amp_obs_demo_idx"] = self._amp_obs_demo_buffer.sample_indices(n)
+        if self._amp_replay_buffer.get_total_count() == 0:
+            self._amp_replay_src = batch_dict["amp_obs"]
+            batch_dict["amp_obs_replay_idx"] = torch.arange(n, device=self.device)
+        else:
+            self._amp_replay_src = self._amp_replay_buffer.data
+            batch_dict["amp_obs_replay_idx"] = self._amp_replay_buffer.sample_indices(n)
+        self.set_train()
+        self.prepare_dataset(batch_dict)
+        for _ in range(self.mini_epochs_num):
+            for i in range(self.num_minibatches):
+                self.calc_gradients({"idx": self._idx_buf[i * self.minibatch_size:(i + 1) * self.minibatch_size]})
+            self._idx_buf = torch.randperm(self.batch_size, device=self.device)
+        self._store_replay_amp_obs(batch_dict["amp_obs"])
+        self.post_epoch(self.epoch_num)
+        t2 = time.time()
+        self.epoch_num += 1
+        self.frame += self.batch_size * self.world
+        return dict(play_time=t1 - t0, update_time=t2 - t1, total_time=t2 - t0, terminated_flags=batch_dict["terminated_flags"],
+                    reward_raw=batch_dict["reward_raw"], mb_rewards=batch_dict["mb_rewards"], returns=batch_dict["returns"],
+                    disc_rewards=batch_dict["disc_rewards"])
+
+    def train(self, max_epochs: Optional[int] = None):
+        """CommonAgent.train (common_agent.py:100-185) without the logging / checkpoint cadence side channels."""
+        self.obs = self.env_reset()
+        self._init_amp_demo_buf()
+        max_epochs = self.config["max_epochs"] if max_epochs is None else max_epochs
+        info = None
+        while self.epoch_num < max_epochs:
+            info = self.train_epoch()
+        return info
+
+    # ------------------------------------------------------------------------------------------------------
+    # checkpoint dict, same keys as the reference (amp_agent.py:69-102,:158-166)
+    # ------------------------------------------------------------------------------------------------------
+    def get_stats_weights(self) -> Dict:
+        st = {}
+        if self.normalize_input:
+            st["running_mean_std"] = self.running_mean_std.state_dict()
+        if self.normalize_value:
+            st["reward_mean_std"] = self.value_mean_std.state_dict()
+        if self._normalize_amp_input:
+            st["amp_input_mean_std"] = self._amp_input_mean_std.state_dict()
+        return st
+
+    def set_stats_weights(self, weights: Dict) -> None:
+        if self.normalize_input and "running_mean_std" in weights:
+            self.running_mean_std.load_state_dict(weights["running_mean_std"])
+            self.running_mean_std_temp = self.running_mean_std.frozen_copy()
+        if self.normalize_value and "reward_mean_std" in weights:
+            self.value_mean_std.load_state_dict(weights["reward_mean_std"])
+        if self._normalize_amp_input and "amp_input_mean_std" in weights:
+            self._amp_input_mean_std.load_state_dict(weights["amp_input_mean_std"])
+
+    def get_full_state_weights(self) -> Dict:
+        state = {"model": self.model.state_dict(), "epoch": self.epoch_num, "frame": self.frame,
+                 "optimizer": {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.opt_step},
+                 "last_mean_rewards": 0}
+        state.update(self.get_stats_weights())
+        return state
+
+    def set_full_state_weights(self, weights: Dict) -> None:
+        self.model.load_state_dict(weights["model"])
+        self.epoch_num = weights.get("epoch", 0)
+        self.frame = weights.get("frame", 0)
+        opt = weights.get("optimizer")
+        if isinstance(opt, dict) and "exp_avg" in opt:
+            self.exp_avg.copy_(opt["exp_avg"].to(self.device))
+            self.exp_avg_sq.copy_(opt["exp_avg_sq"].to(self.device))
+            self.opt_step = int(opt["step"])
+        self.set_stats_weights(weights)
+
+    def save(self, fn: str) -> None:
+        torch.save(self.get_full_state_weights(), fn if fn.endswith(".pth") else fn + ".pth")
+
+    def restore(self, fn: str) -> None:
+        self.set_full_state_weights(torch.load(fn, map_location=self.device, weights_only=False))

@@ -183,7 +183,8 @@ class EnvStepPlan:
                  rew: Optional[torch.Tensor] = None, reward_raw: Optional[torch.Tensor] = None,
                  reset: Optional[torch.Tensor] = None, terminate: Optional[torch.Tensor] = None,
                  amp_obs_buf: Optional[torch.Tensor] = None, amp_hist_in: Optional[torch.Tensor] = None,
-                 amp_shift: bool = True, with_amp: bool = True, with_ref_buffers: bool = False):
+                 amp_shift: bool = True, with_amp: bool = True, with_ref_buffers: bool = False,
+                 only_where: Optional[torch.Tensor] = None, obs_only: bool = False):
         lib = _lib.load()
         self._lib = lib
         self.cfg, self.mlib = cfg, mlib
@@ -201,7 +202,7 @@ class EnvStepPlan:
             dof_force = _req(dof_force, f32, "dof_force", dev)
             assert dof_force.shape == (N, D)
         self.N, self.J = N, J
-        flags = cfg.flags()
+        flags = cfg.flags() | (_lib.PHC_FLAG_OBS_ONLY if obs_only else 0)
         self.self_dim = lib.phc_self_obs_dim(J, flags)
         self.task_dim = lib.phc_task_obs_dim(J, cfg.time_steps)
         self.obs_dim = self.self_dim + self.task_dim
@@ -253,6 +254,8 @@ class EnvStepPlan:
         a.progress, a.motion_ids = k["progress"].data_ptr(), k["motion_ids"].data_ptr()
         a.start_times, a.start_offsets, a.global_offset = k["start_times"].data_ptr(), k["start_offsets"].data_ptr(), k["global_offset"].data_ptr()
         a.cycle_counter = _ptr(k["cycle_counter"])
+        k["only_where"] = None if only_where is None else _req(only_where, i64, "only_where", dev)
+        a.only_where = _ptr(k["only_where"])
         a.lib = mlib.c
         a.num_envs, a.time_steps, a.dt, a.traj_dt, a.flags = N, cfg.time_steps, cfg.dt, cfg.traj_dt, flags
         a.k_pos, a.k_rot, a.k_vel, a.k_ang_vel = cfg.k_pos, cfg.k_rot, cfg.k_vel, cfg.k_ang_vel
@@ -280,7 +283,8 @@ class EnvStepPlan:
 
 
 def amp_obs_demo(mlib: PackedMotionLib, cfg: EnvStepConfig, motion_ids: torch.Tensor, times0: torch.Tensor,
-                 first_step: int = 0, num_steps: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 first_step: int = 0, num_steps: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                 only_where: Optional[torch.Tensor] = None) -> torch.Tensor:
     """build_amp_obs_demo (humanoid_amp.py:253-284; first_step=0) / _init_amp_obs_ref (:575-603; first_step=1)."""
     lib = _lib.load()
     dev = mlib.device
@@ -294,13 +298,15 @@ def amp_obs_demo(mlib: PackedMotionLib, cfg: EnvStepConfig, motion_ids: torch.Te
         out = torch.empty(n, S, A, dtype=torch.float32, device=dev)
     else:
         out = _req(out, torch.float32, "out", dev)
-        assert out.shape == (n, S, A)
+        assert out.shape[0] == n and out.shape[-1] == A and out.stride(0) >= S * A
     kb = (C.c_int32 * len(cfg.key_bodies))(*[int(b) for b in cfg.key_bodies])
     aj = torch.tensor(joints, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.phc_amp_obs_demo(C.byref(mlib.c), ids.data_ptr(), t0.data_ptr(), n, first_step, S, cfg.dt,
                                         cfg.flags(), C.cast(kb, C.c_void_p), len(cfg.key_bodies), aj.data_ptr(),
-                                        len(joints), out.data_ptr(), S * A, _stream()), "phc_amp_obs_demo")
+                                        len(joints), out.data_ptr(), out.stride(0),
+                                        None if only_where is None else _req(only_where, torch.int64, "only_where", dev).data_ptr(),
+                                        _stream()), "phc_amp_obs_demo")
     return out
 
 

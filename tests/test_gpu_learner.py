@@ -1,0 +1,147 @@
+"""GPU parity of the learner path: tensor-core GEMM (3xTF32), running mean/std, loss-gradient kernels and one complete
+PPO + AMP minibatch update (forward, hand-written backward incl. the discriminator gradient penalty, clip, Adam)
+against torch-CPU oracles.  MLP math is fp32-equivalent (3xTF32): tolerances are rtol 1e-4 on gradients (sums over
+16k-row batches re-associated by split-K / atomics) and rtol 2e-5 on forward activations."""
+import math
+
+import pytest
+import torch
+
+from oracle import phc_oracle as O
+from oracle import ppo_oracle as PO
+from phc_b200 import _lib
+from phc_b200.learning.networks import AMPNetwork, MLPEngine, round4
+from tests.helpers import close, load
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def padded(t, ld=None):
+    n, d = t.shape
+    ld = round4(d) if ld is None else ld
+    out = torch.zeros(n, ld, device=DEV)
+    out[:, :d] = t.to(DEV)
+    return out
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 16), (300, 70, 934), (4096, 1024, 936), (130, 1, 512), (257, 69, 512), (5, 3, 7)])
+def test_gemm_forward_form(M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B, bias = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / math.sqrt(K), torch.randn(N, generator=g)
+    net = AMPNetwork(8, 2, 8, (4,), (4,), device=DEV)
+    eng = MLPEngine(net)
+    Ap, Bp = padded(A), padded(B)
+    C = torch.zeros(M, round4(N), device=DEV)
+    eng.gemm(Ap, True, Bp, True, C, M, N, K, bias=bias.to(DEV), relu=True)
+    exp = torch.relu(A.double() @ B.double().T + bias.double()).float()
+    close(C[:, :N].cpu(), exp, rtol=2e-5, atol=2e-5, what="gemm fwd")
+    assert float(C[:, N:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 936, 1024), (100, 72, 69), (64, 1960, 40)])
+def test_gemm_input_grad_form(M, N, K):
+    g = torch.Generator().manual_seed(1)
+    dY, W, H = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g) / math.sqrt(K), torch.randn(M, N, generator=g)
+    eng = MLPEngine(AMPNetwork(8, 2, 8, (4,), (4,), device=DEV))
+    C = torch.zeros(M, round4(N), device=DEV)
+    eng.gemm(padded(dY), True, padded(W), False, C, M, N, K, mask=padded(H))
+    exp = ((dY.double() @ W.double()) * (H > 0)).float()
+    close(C[:, :N].cpu(), exp, rtol=2e-5, atol=2e-5, what="gemm dX")
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(1024, 934, 4096, 4), (69, 512, 2048, 16), (1, 512, 1000, 1), (33, 17, 515, 2)])
+def test_gemm_weight_grad_form(M, N, K, splits):
+    g = torch.Generator().manual_seed(2)
+    dY, X = torch.randn(K, M, generator=g), torch.randn(K, N, generator=g)
+    eng = MLPEngine(AMPNetwork(8, 2, 8, (4,), (4,), device=DEV))
+    C = torch.ones(M, round4(N), device=DEV)            # accumulates on top of existing content
+    eng.gemm(padded(dY), False, padded(X), False, C, M, N, K, alpha=0.5, accumulate=True, k_splits=splits)
+    exp = (1.0 + 0.5 * dY.double().T @ X.double()).float()
+    close(C[:, :N].cpu(), exp, rtol=2e-5, atol=1e-4, what="gemm dW")
+    out = torch.zeros(M, device=DEV)
+    eng.colsum(padded(dY), K, M, out)
+    close(out.cpu(), dY.double().sum(0).float(), rtol=1e-5, atol=1e-4, what="colsum")
+
+
+def test_running_mean_std_vs_reference_golden():
+    from phc_b200.learning.amp_agent import RunningMeanStd
+    g = load("learn.npz")
+    rms = RunningMeanStd(12, DEV)
+    rms.train()
+    for i in range(3):
+        y = rms(g[f"rms_x{i}"].to(DEV))
+        close(y.cpu(), g[f"rms_y{i}"], what=f"rms_y{i}")
+    close(rms.running_mean.cpu(), g["rms_mean"], rtol=1e-6, atol=1e-7, what="mean (fp64 batch moments vs torch's fp32)")
+    close(rms.running_var.cpu(), g["rms_var"], rtol=1e-6, atol=1e-7, what="var")
+    close(rms.count.cpu(), g["rms_count"], what="count")
+    rms.eval()
+    close(rms(g["rms_x0"].to(DEV) * 0.1, unnorm=True).cpu(), g["rms_unnorm"], what="unnorm")
+    # gathered rows
+    idx = torch.tensor([5, 1, 1, 30, 7], device=DEV)
+    out = torch.zeros(5, 12, device=DEV)
+    rms.apply(g["rms_x1"].to(DEV), out, row_idx=idx)
+    close(out.cpu(), O.rms_normalize(g["rms_x1"][idx.cpu()], rms.running_mean.cpu(), rms.running_var.cpu()), what="gather")
+
+
+def test_disc_reward_vs_reference_golden():
+    g = load("learn.npz")
+    lib = _lib.load()
+    ws = [g["d_w1"], g["d_w2"], g["d_w3"]]
+    bs = [g["d_b1"], g["d_b2"], g["d_b3"]]
+    logits = O.mlp_forward(g["d_x_agent"], ws, bs).to(DEV).contiguous()
+    n = logits.shape[0]
+    dr, comb = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    task = torch.full((n,), 0.7, device=DEV)
+    _lib.check(lib.phc_disc_reward(logits.data_ptr(), 1, task.data_ptr(), n, 2.0, 0.5, 0.5, dr.data_ptr(), comb.data_ptr(), None))
+    torch.cuda.synchronize()
+    close(dr.cpu(), g["d_reward"].reshape(-1), what="disc reward")
+    close(comb.cpu(), g["d_combined"].reshape(-1), what="combined reward")
+
+
+def _rand_batch(B, Bd, obs, act, amp, seed):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)
+    logstd = torch.full((act,), -2.9)
+    old_mu = r(B, act) * 0.8
+    old_sigma = torch.exp(logstd).expand(B, act).clone()
+    actions = old_mu + old_sigma * r(B, act)
+    old_nlp = O.gaussian_neglogp(actions, old_mu, old_sigma, logstd.expand(B, act))
+    return dict(obs_n=torch.clamp(r(B, obs) * 1.5, -5, 5), actions=actions, old_neglogp=old_nlp + 0.05 * r(B),
+                advantages=r(B), old_mu=old_mu, old_sigma=old_sigma, returns=r(B, 1),
+                amp_agent=torch.clamp(r(Bd, amp), -5, 5), amp_replay=torch.clamp(r(Bd, amp), -5, 5), amp_demo=torch.clamp(r(Bd, amp), -5, 5))
+
+
+CFG = dict(e_clip=0.2, critic_coef=5.0, entropy_coef=0.0, bounds_loss_coef=10.0, disc_coef=5.0, disc_logit_reg=0.01,
+           disc_grad_penalty=5.0, disc_weight_decay=0.0001, grad_norm=50.0, learning_rate=2e-5, truncate_grads=True)
+
+
+@pytest.mark.parametrize("B,Bd,obs,act,amp,units", [(512, 128, 934, 69, 1960, (256, 128)), (16384, 4096, 934, 69, 1960, (1024, 512)),
+                                                     (300, 100, 50, 7, 30, (64, 32))])
+def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units):
+    """forward values, every parameter gradient, the clipped Adam step: CUDA engine vs torch autograd on the CPU."""
+    from tests.learner_harness import run_cuda_minibatch
+    batch = _rand_batch(B, Bd, obs, act, amp, seed=B)
+    net = AMPNetwork(obs, act, amp, units, units, device=DEV, seed=3)
+    # move the policy off its initialisation so ratios / clipping / bound loss are all active
+    for l in net.actor.layers:
+        net.weight(l).mul_(3.0)
+    sd = {k: v.cpu() for k, v in net.state_dict().items()}
+    exp = PO.minibatch_update(sd, batch, CFG, n_hidden=len(units))
+    got = run_cuda_minibatch(net, batch, CFG)
+    close(got["mu"].cpu(), exp["mu"], rtol=2e-5, atol=2e-5, what="mu")
+    close(got["values"].cpu(), exp["values"], rtol=2e-5, atol=2e-5, what="values")
+    s = got["stats"]
+    close(torch.tensor(s["actor_loss"]), exp["a_loss"], rtol=1e-4, atol=1e-5, what="a_loss")
+    close(torch.tensor(s["critic_loss"]), exp["c_loss"], rtol=1e-4, atol=1e-5, what="c_loss")
+    close(torch.tensor(s["b_loss"]), exp["b_loss"], rtol=1e-4, atol=1e-5, what="b_loss")
+    close(torch.tensor(s["kl"]), exp["kl"], rtol=1e-3, atol=1e-4, what="kl")
+    close(torch.tensor(s["disc_grad_penalty"]), exp["disc"]["disc_grad_penalty"], rtol=1e-4, atol=1e-6, what="grad penalty")
+    close(torch.tensor(s["disc_agent_acc"]), exp["disc"]["disc_agent_acc"], what="disc agent acc")
+    gsd = got["grads"]
+    for k, ge in exp["grads"].items():
+        scale = float(ge.abs().max()) + 1e-12
+        close(gsd[k].cpu(), ge, rtol=2e-4, atol=2e-5 * scale, what=f"grad {k}")
+    close(torch.tensor(got["total_norm"]), exp["total_norm"].float(), rtol=1e-4, atol=1e-6, what="grad norm")
+    for k, pe in exp["new_params"].items():
+        close(got["new_params"][k].cpu(), pe, rtol=1e-5, atol=2e-7, what=f"adam {k}")
