@@ -34,6 +34,8 @@ extern "C" {
 PHC_API int phc_version(void);
 /* Thread-local, NUL-terminated description of the last non-zero return on this thread. */
 PHC_API const char* phc_last_error(void);
+/* Number of CUDA kernels this library has launched in the calling process (monotonic; bench.py reports the delta). */
+PHC_API int64_t phc_launch_count(void);
 /* SM architecture the library was compiled for (100 for sm_100a). */
 PHC_API int phc_compiled_sm(void);
 

@@ -22,10 +22,11 @@ def stack_params(sd: Dict[str, torch.Tensor], prefix: str, head: str, n_hidden: 
 
 
 def minibatch_update(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], cfg: Dict, n_hidden: int = 2,
-                     adam_state=None, step: int = 1) -> Dict:
+                     adam_state=None, step: int = 1, dtype=torch.float32) -> Dict:
     """sd: reference-keyed state dict (fp32, un-padded).  batch: obs_n [B,obs] (already normalised), actions, old_neglogp,
     advantages, old_mu, old_sigma, returns [B,1], amp_agent / amp_replay / amp_demo [Bd, amp] (already normalised)."""
-    p = {k: v.clone().double().float().requires_grad_(k != "a2c_network.sigma") for k, v in sd.items()}
+    p = {k: v.clone().to(dtype).requires_grad_(k != "a2c_network.sigma") for k, v in sd.items()}
+    batch = {k: (v.to(dtype) if v.dtype.is_floating_point else v) for k, v in batch.items()}
     aw, ab = stack_params(p, "actor_mlp", "mu", n_hidden)
     cw, cb = stack_params(p, "critic_mlp", "value", n_hidden)
     dw, db = stack_params(p, "_disc_mlp", "_disc_logits", n_hidden)

@@ -63,6 +63,7 @@ SIGNATURES = {
     "phc_version": (C.c_int, []),
     "phc_last_error": (C.c_char_p, []),
     "phc_compiled_sm": (C.c_int, []),
+    "phc_launch_count": (C.c_int64, []),
     "phc_motion_body_stride": (C.c_int, [C.c_int32]),
     "phc_motion_joint_stride": (C.c_int, [C.c_int32]),
     "phc_motion_pack": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int64, C.c_int32, _p, _p, _p]),

@@ -371,6 +371,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
 // ------------------------------------------------------------------------------------------------------------
 extern "C" void phc_set_error(const char* msg);   // phc_api.cu
 extern "C" int phc_check_cuda(cudaError_t e, const char* what);
+extern "C" void phc_count_launches(int n);
 
 extern "C" int phc_self_obs_dim(int32_t J, uint32_t flags) {
   return ((flags & PHC_FLAG_ROOT_HEIGHT_OBS) ? 1 : 0) + 15 * J - 3;
@@ -435,7 +436,7 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
       attr_set = true;                                                                                           \
     }                                                                                                            \
     env_step_kernel<TM><<<grid, kWarpsPerCta * 32, smem, st>>>(*a, obs_dim, self_dim, amp_dim, alias_obs,        \
-                                                                state_bulk_ok);                                  \
+                                                                state_bulk_ok); phc_count_launches(1);                                  \
   } while (0)
   if (T == 1) PHC_LAUNCH_STEP(1);
   else PHC_LAUNCH_STEP(4);

@@ -23,6 +23,7 @@
 
 extern "C" void phc_set_error(const char* msg);
 extern "C" int phc_check_cuda(cudaError_t e, const char* what);
+extern "C" void phc_count_launches(int n);
 
 namespace phc {
 
@@ -262,7 +263,7 @@ extern "C" int phc_gemm(const float* A, int64_t lda, int32_t a_kmajor, const flo
       if (e != cudaSuccess) return phc_check_cuda(e, "cudaFuncSetAttribute(gemm)");                          \
       done = true;                                                                                           \
     }                                                                                                        \
-    gemm_3xtf32_kernel<AK, BK_><<<grid, GEMM_THREADS, smem, st>>>(g);                                        \
+    gemm_3xtf32_kernel<AK, BK_><<<grid, GEMM_THREADS, smem, st>>>(g); phc_count_launches(1);                                        \
   } while (0)
   if (a_kmajor && b_kmajor) PHC_GEMM_LAUNCH(true, true);
   else if (a_kmajor && !b_kmajor) PHC_GEMM_LAUNCH(true, false);
@@ -279,6 +280,6 @@ extern "C" int phc_colsum(const float* X, int64_t ld, int32_t M, int32_t N, floa
   int gy = (M + 1023) / 1024; if (gy < 1) gy = 1; if (gy > 64) gy = 64;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (gy > 1 && !accumulate) cudaMemsetAsync(out, 0, (size_t)N * 4, st);
-  phc::colsum_kernel<<<dim3((N + 31) / 32, gy), dim3(32, 32), 0, st>>>(X, ld, M, N, alpha, out, accumulate);
+  phc::colsum_kernel<<<dim3((N + 31) / 32, gy), dim3(32, 32), 0, st>>>(X, ld, M, N, alpha, out, accumulate); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "colsum_kernel launch");
 }

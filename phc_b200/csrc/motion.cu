@@ -13,6 +13,7 @@
 
 extern "C" void phc_set_error(const char* msg);
 extern "C" int phc_check_cuda(cudaError_t e, const char* what);
+extern "C" void phc_count_launches(int n);
 
 namespace phc {
 
@@ -231,7 +232,7 @@ extern "C" int phc_motion_pack(const float* gts, const float* grs, const float* 
   const int block = 256;
   const int grid = (int)((total + block - 1) / block < 148 * 16 ? (total + block - 1) / block : 148 * 16);
   phc::motion_pack_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      gts, grs, gvs, gavs, lrs, dvs, F, J, phc_motion_body_stride(J), phc_motion_joint_stride(J), fb, joint ? fj : nullptr);
+      gts, grs, gvs, gavs, lrs, dvs, F, J, phc_motion_body_stride(J), phc_motion_joint_stride(J), fb, joint ? fj : nullptr); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "motion_pack_kernel launch");
 }
 
@@ -257,7 +258,7 @@ extern "C" int phc_motion_state(const PhcMotionLib* lib, const int64_t* ids, con
   if (n == 0) return PHC_OK;
   const int wpb = 4;
   const int64_t grid = (n + wpb - 1) / wpb;
-  phc::motion_state_kernel<<<(unsigned)grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(*lib, ids, times, offset, n, *out);
+  phc::motion_state_kernel<<<(unsigned)grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(*lib, ids, times, offset, n, *out); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "motion_state_kernel launch");
 }
 
@@ -280,7 +281,7 @@ extern "C" int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* ids, con
   for (int i = 0; i < PHC_MAX_KEY_BODIES; ++i) a.key_bodies[i] = i < nk ? key_bodies[i] : -1;
   const int wpb = 4;
   const int64_t warps = n * num_steps;
-  phc::amp_demo_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  phc::amp_demo_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(a); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "amp_demo_kernel launch");
 }
 
@@ -294,6 +295,6 @@ extern "C" int phc_set_env_state(const PhcMotionLib* lib, const int64_t* ids, co
   if (n == 0) return PHC_OK;
   const int wpb = 4;
   phc::set_env_state_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      *lib, ids, times, offset, only_where, n, body_state, bodies_per_env, dof_state);
+      *lib, ids, times, offset, only_where, n, body_state, bodies_per_env, dof_state); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "set_env_state_kernel launch");
 }

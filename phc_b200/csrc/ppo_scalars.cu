@@ -16,6 +16,7 @@
 
 extern "C" void phc_set_error(const char* msg);
 extern "C" int phc_check_cuda(cudaError_t e, const char* what);
+extern "C" void phc_count_launches(int n);
 
 namespace phc {
 
@@ -140,7 +141,7 @@ extern "C" int phc_gae(const float* fdones, const float* values, const float* re
   if (T == 0 || N == 0) return PHC_OK;
   const int64_t grid = (N + 31) / 32;
   phc::gae_kernel<<<(unsigned)grid, 1024, 0, static_cast<cudaStream_t>(stream)>>>(fdones, values, rewards, next_values, T, N,
-                                                                                   gamma, tau, advs, returns);
+                                                                                   gamma, tau, advs, returns); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "gae_kernel launch");
 }
 
@@ -153,7 +154,7 @@ extern "C" int phc_adv_norm(const float* returns, const float* values, int64_t n
   if (normalize && n < 2) { phc_set_error("phc_adv_norm: unbiased std needs n >= 2"); return PHC_ERR_INVALID_ARG; }
   const int g = phc::adv_grid(n);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  phc::adv_partial_kernel<<<g, phc::kAdvBlock, 0, st>>>(returns, values, n, advs, static_cast<double*>(workspace));
-  if (normalize) phc::adv_apply_kernel<<<g, phc::kAdvBlock, 0, st>>>(advs, n, static_cast<const double*>(workspace), g);
+  phc::adv_partial_kernel<<<g, phc::kAdvBlock, 0, st>>>(returns, values, n, advs, static_cast<double*>(workspace)); phc_count_launches(1);
+  if (normalize) phc::adv_apply_kernel<<<g, phc::kAdvBlock, 0, st>>>(advs, n, static_cast<const double*>(workspace), g); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "adv_norm kernels launch");
 }

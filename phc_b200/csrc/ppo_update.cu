@@ -14,6 +14,7 @@
 
 extern "C" void phc_set_error(const char* msg);
 extern "C" int phc_check_cuda(cudaError_t e, const char* what);
+extern "C" void phc_count_launches(int n);
 
 namespace phc {
 
@@ -325,7 +326,7 @@ extern "C" int phc_rms_apply(const float* x, int64_t ldx, int64_t n, int32_t d, 
                              float eps, int32_t unnorm, float* y, int64_t ldy, const int64_t* row_idx, void* stream) {
   if (!x || !mean || !var || !y || n < 0 || d < 1 || ldx < d || ldy < d) { phc_set_error("phc_rms_apply: bad arguments"); return PHC_ERR_INVALID_ARG; }
   if (n == 0) return PHC_OK;
-  rms_apply_kernel<<<ew_grid(n * d), 256, 0, ST(stream)>>>(x, ldx, n, d, mean, var, eps, unnorm, y, ldy, row_idx);
+  rms_apply_kernel<<<ew_grid(n * d), 256, 0, ST(stream)>>>(x, ldx, n, d, mean, var, eps, unnorm, y, ldy, row_idx); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "rms_apply_kernel");
 }
 
@@ -337,8 +338,8 @@ extern "C" int phc_rms_update(const float* x, int64_t ldx, int64_t n, int32_t d,
   double* acc = static_cast<double*>(workspace);
   cudaMemsetAsync(acc, 0, (size_t)2 * d * sizeof(double), ST(stream));
   int gy = (int)((n + 1023) / 1024); if (gy > 32) gy = 32; if (gy < 1) gy = 1;
-  rms_moments_kernel<<<dim3((d + 31) / 32, gy), dim3(32, 32), 0, ST(stream)>>>(x, ldx, n, d, acc, row_idx);
-  rms_merge_kernel<<<1, 1024, 0, ST(stream)>>>(acc, n, d, mean, var, count);
+  rms_moments_kernel<<<dim3((d + 31) / 32, gy), dim3(32, 32), 0, ST(stream)>>>(x, ldx, n, d, acc, row_idx); phc_count_launches(1);
+  rms_merge_kernel<<<1, 1024, 0, ST(stream)>>>(acc, n, d, mean, var, count); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "rms_update kernels");
 }
 
@@ -346,7 +347,7 @@ extern "C" int phc_gaussian_sample(const float* mu, int64_t ldmu, const float* l
                                    int32_t A, float* actions, float* neglogp, float* mus, float* sigmas, void* stream) {
   if (!mu || !logstd || !noise || !actions || !neglogp || n < 0 || A < 1 || ldmu < A) { phc_set_error("phc_gaussian_sample: bad arguments"); return PHC_ERR_INVALID_ARG; }
   if (n == 0) return PHC_OK;
-  gaussian_sample_kernel<<<(unsigned)((n + 3) / 4), 128, 0, ST(stream)>>>(mu, ldmu, logstd, noise, n, A, actions, neglogp, mus, sigmas);
+  gaussian_sample_kernel<<<(unsigned)((n + 3) / 4), 128, 0, ST(stream)>>>(mu, ldmu, logstd, noise, n, A, actions, neglogp, mus, sigmas); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "gaussian_sample_kernel");
 }
 
@@ -359,7 +360,7 @@ extern "C" int phc_ppo_actor_grad(const float* mu, int64_t ldmu, const float* lo
   }
   if (n == 0) return PHC_OK;
   ppo_actor_grad_kernel<<<(unsigned)((n + 3) / 4), 128, 0, ST(stream)>>>(mu, ldmu, logstd, actions, old_neglogp, adv, old_mu, old_sigma, n, A,
-                                                                         e_clip, bound_coef, inv_batch, dmu, lddmu, stats);
+                                                                         e_clip, bound_coef, inv_batch, dmu, lddmu, stats); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "ppo_actor_grad_kernel");
 }
 
@@ -367,14 +368,14 @@ extern "C" int phc_ppo_critic_grad(const float* v, int64_t ldv, const float* ret
                                    float* dv, int64_t lddv, float* stats, void* stream) {
   if (!v || !ret || !dv || !stats || n < 0 || ldv < 1 || lddv < 1) { phc_set_error("phc_ppo_critic_grad: bad arguments"); return PHC_ERR_INVALID_ARG; }
   if (n == 0) return PHC_OK;
-  ppo_critic_grad_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(v, ldv, ret, n, coef, inv_batch, dv, lddv, stats);
+  ppo_critic_grad_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(v, ldv, ret, n, coef, inv_batch, dv, lddv, stats); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "ppo_critic_grad_kernel");
 }
 
 extern "C" int phc_disc_logit_grad(const float* logit, int64_t ld, int64_t n_agent, int64_t n_demo, float coef,
                                    float* dlogit, int64_t ldd, float* stats, void* stream) {
   if (!logit || !dlogit || !stats || n_agent < 1 || n_demo < 1 || ld < 1 || ldd < 1) { phc_set_error("phc_disc_logit_grad: bad arguments"); return PHC_ERR_INVALID_ARG; }
-  disc_logit_grad_kernel<<<ew_grid(n_agent + n_demo), 256, 0, ST(stream)>>>(logit, ld, n_agent, n_demo, coef, dlogit, ldd, stats);
+  disc_logit_grad_kernel<<<ew_grid(n_agent + n_demo), 256, 0, ST(stream)>>>(logit, ld, n_agent, n_demo, coef, dlogit, ldd, stats); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "disc_logit_grad_kernel");
 }
 
@@ -382,7 +383,7 @@ extern "C" int phc_disc_reward(const float* logit, int64_t ld, const float* task
                                float w_task, float w_disc, float* disc_rewards, float* combined, void* stream) {
   if (!logit || n < 0 || ld < 1 || (combined && !task_rewards) || (!disc_rewards && !combined)) { phc_set_error("phc_disc_reward: bad arguments"); return PHC_ERR_INVALID_ARG; }
   if (n == 0) return PHC_OK;
-  disc_reward_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(logit, ld, task_rewards, n, scale, w_task, w_disc, disc_rewards, combined);
+  disc_reward_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(logit, ld, task_rewards, n, scale, w_task, w_disc, disc_rewards, combined); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "disc_reward_kernel");
 }
 
@@ -390,14 +391,14 @@ extern "C" int phc_relu_mask_row(const float* h, int64_t ldh, const float* w, in
                                  void* stream) {
   if (!h || !w || !u || n < 0 || d < 1 || ldh < d || ldu < d) { phc_set_error("phc_relu_mask_row: bad arguments"); return PHC_ERR_INVALID_ARG; }
   if (n == 0) return PHC_OK;
-  relu_mask_row_kernel<<<ew_grid(n * d), 256, 0, ST(stream)>>>(h, ldh, w, n, d, u, ldu);
+  relu_mask_row_kernel<<<ew_grid(n * d), 256, 0, ST(stream)>>>(h, ldh, w, n, d, u, ldu); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "relu_mask_row_kernel");
 }
 
 extern "C" int phc_scale_sumsq(float* x, int64_t ld, int64_t n, int32_t d, float alpha, float* stat, void* stream) {
   if (!x || !stat || n < 0 || d < 1 || ld < d) { phc_set_error("phc_scale_sumsq: bad arguments"); return PHC_ERR_INVALID_ARG; }
   if (n == 0) return PHC_OK;
-  scale_sumsq_kernel<<<ew_grid(n * d), 256, 0, ST(stream)>>>(x, ld, n, d, alpha, stat);
+  scale_sumsq_kernel<<<ew_grid(n * d), 256, 0, ST(stream)>>>(x, ld, n, d, alpha, stat); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "scale_sumsq_kernel");
 }
 
@@ -405,7 +406,7 @@ extern "C" int phc_axpy2d(const float* x, int64_t ldx, float* y, int64_t ldy, in
                           float* sumsq_stat, void* stream) {
   if (!x || !y || rows < 0 || cols < 1 || ldx < cols || ldy < cols) { phc_set_error("phc_axpy2d: bad arguments"); return PHC_ERR_INVALID_ARG; }
   if (rows == 0) return PHC_OK;
-  axpy2d_kernel<<<ew_grid(rows * cols), 256, 0, ST(stream)>>>(x, ldx, y, ldy, rows, cols, alpha, sumsq_stat);
+  axpy2d_kernel<<<ew_grid(rows * cols), 256, 0, ST(stream)>>>(x, ldx, y, ldy, rows, cols, alpha, sumsq_stat); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "axpy2d_kernel");
 }
 
@@ -413,7 +414,7 @@ extern "C" int phc_grad_sumsq(const float* g, int64_t n, double* out, void* stre
   if (!g || !out || n < 0) { phc_set_error("phc_grad_sumsq: bad arguments"); return PHC_ERR_INVALID_ARG; }
   cudaMemsetAsync(out, 0, sizeof(double), ST(stream));
   if (n == 0) return PHC_OK;
-  sumsq_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(g, n, out);
+  sumsq_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(g, n, out); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "sumsq_kernel");
 }
 
@@ -427,6 +428,6 @@ extern "C" int phc_adam_step(float* params, const float* grads, float* exp_avg, 
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_clip_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, grad_sumsq, grad_scale, max_norm, lr,
-                                                       beta1, beta2, eps, (float)bc1, (float)sqrt(bc2));
+                                                       beta1, beta2, eps, (float)bc1, (float)sqrt(bc2)); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "adam_clip_kernel");
 }

@@ -23,6 +23,7 @@ import torch
 
 from .. import _lib, ops
 from ..ops import _ptr, _stream
+from . import dist as D
 from .networks import AMPNetwork, MLPEngine, round4
 
 DEFAULT_CONFIG = dict(          # phc/data/cfg/learning/im.yaml:43-99
@@ -188,16 +189,16 @@ class AMPAgent:
 
         # multi-GPU: one process per GPU, gradients summed over NCCL and scaled by 1/world (replaces Horovod,
         # phc/run_hydra.py:114-128 / amp_agent.py:668)
-        self.multi_gpu = bool(cfg.get("multi_gpu", False)) and torch.distributed.is_available() and torch.distributed.is_initialized()
+        self.multi_gpu = bool(cfg.get("multi_gpu", False)) and D.is_multi()
         self.rank = torch.distributed.get_rank() if self.multi_gpu else 0
-        self.world = torch.distributed.get_world_size() if self.multi_gpu else 1
+        self.world = D.world_size() if self.multi_gpu else 1
 
         netcfg = cfg["network"]
         self.model = AMPNetwork(self.obs_dim, self.actions_num, self.amp_obs_dim, netcfg["mlp"]["units"],
                                 netcfg["disc"]["units"], netcfg["mlp"]["activation"], netcfg.get("sigma_init", -2.9),
                                 device=self.device, seed=int(cfg["seed"]))
         if self.multi_gpu:
-            torch.distributed.broadcast(self.model.params, 0)
+            D.broadcast_params(self.model.params, 0)
         self.engine = MLPEngine(self.model)
         n = self.model.num_floats
         self.exp_avg = torch.zeros(n, device=self.device)
@@ -261,6 +262,7 @@ class AMPAgent:
         self._stats = z(16)
         # disc reward over the whole rollout, evaluated in chunks of the amp update batch
         self._ws_disc_r = self.engine.workspace("disc_r", self.model.disc, 3 * Bd)
+        self._no_dones = torch.zeros(N, dtype=torch.int64, device=dev)
         self.game_rewards = z(N)
         self.current_rewards = z(N)
         self.current_lengths = z(N)
@@ -343,7 +345,7 @@ class AMPAgent:
         eb = self.experience_buffer
         terminated_flags = torch.zeros(self.num_actors, device=self.device)
         reward_raw = None
-        done_mask = None
+        done_mask = self._no_dones          # the reference starts every rollout with done_indices = [] (amp_agent.py:314)
         for n in range(self.horizon_length):
             self.obs = self.env_reset(done_mask)
             eb["obses"][n].copy_(self.obs["obs"])
@@ -485,12 +487,11 @@ class AMPAgent:
                                           l.in_dim, 2.0 * self._disc_coef * self._disc_weight_decay, self._stats[12:].data_ptr(), st))
 
         # ---- all-reduce, clip, Adam -----------------------------------------------------------------------------
-        if self.multi_gpu:
-            torch.distributed.all_reduce(net.grads)
+        grad_scale = D.allreduce_grad_bucket(net.grads) if self.multi_gpu else 1.0
         self.opt_step += 1
         _lib.check(lib.phc_grad_sumsq(net.grads.data_ptr(), net.num_floats, self._gsumsq.data_ptr(), st))
         _lib.check(lib.phc_adam_step(net.params.data_ptr(), net.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                                     net.num_floats, self._gsumsq.data_ptr(), 1.0 / self.world,
+                                     net.num_floats, self._gsumsq.data_ptr(), grad_scale,
                                      self.grad_norm if self.truncate_grads else 0.0, self.last_lr, 0.9, 0.999, 1e-8,
                                      self.opt_step, st))
         self._last_B, self._last_Bd = B, Bd
@@ -545,6 +546,8 @@ class AMPAgent:
             self.running_mean_std_temp = self.running_mean_std.frozen_copy()   # amp_agent.py:527-528
 
     def post_epoch(self, epoch_num: int) -> None:
+        if self.multi_gpu:          # hvd.sync_stats (common_agent.py:126-127)
+            D.sync_running_stats([self.running_mean_std, self.value_mean_std, self._amp_input_mean_std])
         if self.normalize_input:
             self.running_mean_std_temp = self.running_mean_std.frozen_copy()
 

@@ -17,6 +17,19 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+def gemm_close(got, A, B, what, extra=None, tol=4e-6):
+    """fp32-equivalence criterion of a GEMM: |err[m,n]| <= tol * (|A| |B|^T)[m,n] (+tiny), against an fp64 product.
+    (fp32 SGEMM's own bound is K*eps ~ 6e-5 at K=1000; typical sqrt(K)*eps ~ 2e-6.)  Prints the measured ratio."""
+    exp = A.double() @ B.double().T
+    bound = A.double().abs() @ B.double().abs().T
+    if extra is not None:
+        exp, bound = extra(exp, bound)
+    err = (got.double().cpu() - exp).abs()
+    ratio = float((err / (bound + 1e-30)).max())
+    assert ratio <= tol and torch.isfinite(got).all(), f"{what}: max err/(|A||B|) = {ratio:.3e} > {tol}, max abs err {float(err.max()):.3e}"
+    return ratio
+
+
 def padded(t, ld=None):
     n, d = t.shape
     ld = round4(d) if ld is None else ld
@@ -34,8 +47,8 @@ def test_gemm_forward_form(M, N, K):
     Ap, Bp = padded(A), padded(B)
     C = torch.zeros(M, round4(N), device=DEV)
     eng.gemm(Ap, True, Bp, True, C, M, N, K, bias=bias.to(DEV), relu=True)
-    exp = torch.relu(A.double() @ B.double().T + bias.double()).float()
-    close(C[:, :N].cpu(), exp, rtol=2e-5, atol=2e-5, what="gemm fwd")
+    # relu only shrinks errors; compare post-activation against the fp64 value with the pre-activation bound
+    gemm_close(C[:, :N], A, B, "gemm fwd", extra=lambda e, b: (torch.relu(e + bias.double()), b + bias.double().abs()))
     assert float(C[:, N:].abs().sum()) == 0.0
 
 
@@ -46,8 +59,7 @@ def test_gemm_input_grad_form(M, N, K):
     eng = MLPEngine(AMPNetwork(8, 2, 8, (4,), (4,), device=DEV))
     C = torch.zeros(M, round4(N), device=DEV)
     eng.gemm(padded(dY), True, padded(W), False, C, M, N, K, mask=padded(H))
-    exp = ((dY.double() @ W.double()) * (H > 0)).float()
-    close(C[:, :N].cpu(), exp, rtol=2e-5, atol=2e-5, what="gemm dX")
+    gemm_close(C[:, :N], dY, W.T.contiguous(), "gemm dX", extra=lambda e, b: (e * (H > 0), b))
 
 
 @pytest.mark.parametrize("M,N,K,splits", [(1024, 934, 4096, 4), (69, 512, 2048, 16), (1, 512, 1000, 1), (33, 17, 515, 2)])
@@ -57,11 +69,11 @@ def test_gemm_weight_grad_form(M, N, K, splits):
     eng = MLPEngine(AMPNetwork(8, 2, 8, (4,), (4,), device=DEV))
     C = torch.ones(M, round4(N), device=DEV)            # accumulates on top of existing content
     eng.gemm(padded(dY), False, padded(X), False, C, M, N, K, alpha=0.5, accumulate=True, k_splits=splits)
-    exp = (1.0 + 0.5 * dY.double().T @ X.double()).float()
-    close(C[:, :N].cpu(), exp, rtol=2e-5, atol=1e-4, what="gemm dW")
+    gemm_close(C[:, :N], dY.T.contiguous(), X.T.contiguous(), "gemm dW", extra=lambda e, b: (1.0 + 0.5 * e, 1.0 + 0.5 * b))
     out = torch.zeros(M, device=DEV)
     eng.colsum(padded(dY), K, M, out)
-    close(out.cpu(), dY.double().sum(0).float(), rtol=1e-5, atol=1e-4, what="colsum")
+    cerr = (out.double().cpu() - dY.double().sum(0)).abs() / dY.double().abs().sum(0)
+    assert float(cerr.max()) < 2e-6, f"colsum: {float(cerr.max()):.3e}"
 
 
 def test_running_mean_std_vs_reference_golden():
@@ -127,21 +139,29 @@ def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units):
     for l in net.actor.layers:
         net.weight(l).mul_(3.0)
     sd = {k: v.cpu() for k, v in net.state_dict().items()}
-    exp = PO.minibatch_update(sd, batch, CFG, n_hidden=len(units))
+    exp = PO.minibatch_update(sd, batch, CFG, n_hidden=len(units), dtype=torch.float64)      # near-exact reference
     got = run_cuda_minibatch(net, batch, CFG)
-    close(got["mu"].cpu(), exp["mu"], rtol=2e-5, atol=2e-5, what="mu")
-    close(got["values"].cpu(), exp["values"], rtol=2e-5, atol=2e-5, what="values")
+
+    def scaled(a, b, tol, what):       # error relative to the tensor's scale (entries are sums of large cancelling terms)
+        err = float((a.double().cpu() - b.double()).abs().max())
+        sc = float(b.double().abs().max()) + 1e-30
+        assert err <= tol * sc, f"{what}: max abs err {err:.3e} vs scale {sc:.3e} -> {err / sc:.3e} > {tol}"
+
+    scaled(got["mu"], exp["mu"], 2e-5, "mu")
+    scaled(got["values"], exp["values"], 2e-5, "values")
     s = got["stats"]
-    close(torch.tensor(s["actor_loss"]), exp["a_loss"], rtol=1e-4, atol=1e-5, what="a_loss")
-    close(torch.tensor(s["critic_loss"]), exp["c_loss"], rtol=1e-4, atol=1e-5, what="c_loss")
-    close(torch.tensor(s["b_loss"]), exp["b_loss"], rtol=1e-4, atol=1e-5, what="b_loss")
-    close(torch.tensor(s["kl"]), exp["kl"], rtol=1e-3, atol=1e-4, what="kl")
-    close(torch.tensor(s["disc_grad_penalty"]), exp["disc"]["disc_grad_penalty"], rtol=1e-4, atol=1e-6, what="grad penalty")
-    close(torch.tensor(s["disc_agent_acc"]), exp["disc"]["disc_agent_acc"], what="disc agent acc")
+    f32 = lambda t: t.float()
+    close(torch.tensor(s["actor_loss"]), f32(exp["a_loss"]), rtol=2e-4, atol=1e-5, what="a_loss")
+    close(torch.tensor(s["critic_loss"]), f32(exp["c_loss"]), rtol=1e-4, atol=1e-5, what="c_loss")
+    close(torch.tensor(s["b_loss"]), f32(exp["b_loss"]), rtol=1e-4, atol=1e-5, what="b_loss")
+    close(torch.tensor(s["kl"]), f32(exp["kl"]), rtol=1e-3, atol=1e-4, what="kl")
+    close(torch.tensor(s["disc_grad_penalty"]), f32(exp["disc"]["disc_grad_penalty"]), rtol=1e-4, atol=1e-6, what="grad penalty")
+    close(torch.tensor(s["disc_agent_acc"]), f32(exp["disc"]["disc_agent_acc"]), atol=2e-3, what="disc agent acc")
     gsd = got["grads"]
     for k, ge in exp["grads"].items():
-        scale = float(ge.abs().max()) + 1e-12
-        close(gsd[k].cpu(), ge, rtol=2e-4, atol=2e-5 * scale, what=f"grad {k}")
+        scaled(gsd[k], ge, 1e-4, f"grad {k}")
     close(torch.tensor(got["total_norm"]), exp["total_norm"].float(), rtol=1e-4, atol=1e-6, what="grad norm")
     for k, pe in exp["new_params"].items():
-        close(got["new_params"][k].cpu(), pe, rtol=1e-5, atol=2e-7, what=f"adam {k}")
+        # Adam's first step moves every weight by ~lr*sign(g): parameters must agree to a small fraction of one step
+        d = float((got["new_params"][k].double().cpu() - pe.double()).abs().max())
+        assert d <= 0.05 * CFG["learning_rate"] + 1e-7 * float(pe.abs().max()), f"adam {k}: {d:.3e}"
