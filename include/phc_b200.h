@@ -217,6 +217,14 @@ PHC_API int phc_adv_norm(const float* returns, const float* values, int64_t n, i
 PHC_API int phc_gemm(const float* A, int64_t lda, int32_t a_kmajor, const float* B, int64_t ldb, int32_t b_kmajor, float* C,
              int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha, const float* bias, int32_t relu,
              const float* mask, int64_t ldmask, int32_t accumulate, int32_t k_splits, void* stream);
+/* Blackwell-native variant of phc_gemm: tcgen05.mma kind::tf32 (UMMA) fed by TMA, accumulator in TMEM.  Same epilogue
+ * contract.  3xTF32 needs each operand pre-split once by phc_split_tf32 (hi = rna_tf32(x), lo = rna_tf32(x - hi)); hi and
+ * lo share the leading dimension.  All four operand arrays 16-byte aligned, lda/ldb multiples of 4 (TMA strides). */
+PHC_API int phc_split_tf32(const float* x, int64_t ldx, int64_t rows, int32_t cols, float* hi, float* lo, int64_t ldo, void* stream);
+PHC_API int phc_gemm_tc5(const float* A_hi, const float* A_lo, int64_t lda, int32_t a_kmajor, const float* B_hi, const float* B_lo,
+                 int64_t ldb, int32_t b_kmajor, float* C, float* C_hi /* optional: split copies of C for the next GEMM */,
+                 float* C_lo, int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha, const float* bias, int32_t relu,
+                 const float* mask, int64_t ldmask, int32_t accumulate, int32_t k_splits, void* stream);
 /* out[n] (+)= alpha * sum_m X[m*ld + n]   (bias gradients) */
 PHC_API int phc_colsum(const float* X, int64_t ld, int32_t M, int32_t N, float alpha, float* out, int32_t accumulate,
                void* stream);

@@ -30,6 +30,7 @@ SOURCES = {
     "motion.cu": ["-fmad=false"],
     "ppo_scalars.cu": ["-fmad=false"],
     "gemm.cu": [],
+    "gemm_tc5.cu": [],
     "ppo_update.cu": [],
 }
 

@@ -429,14 +429,15 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
   cudaError_t e;
 #define PHC_LAUNCH_STEP(TM)                                                                                      \
   do {                                                                                                           \
-    static bool attr_set = false;                                                                                \
-    if (!attr_set || smem > 48 * 1024) {                                                                         \
+    static size_t smem_limit = 48 * 1024;     /* default opt-out limit; the attribute is only ever RAISED */      \
+    if (smem > smem_limit) {                                                                                     \
       e = cudaFuncSetAttribute(env_step_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
       if (e != cudaSuccess) return phc_check_cuda(e, "cudaFuncSetAttribute(env_step_kernel)");                   \
-      attr_set = true;                                                                                           \
+      smem_limit = smem;                                                                                         \
     }                                                                                                            \
     env_step_kernel<TM><<<grid, kWarpsPerCta * 32, smem, st>>>(*a, obs_dim, self_dim, amp_dim, alias_obs,        \
-                                                                state_bulk_ok); phc_count_launches(1);                                  \
+                                                                state_bulk_ok);                                  \
+    phc_count_launches(1);                                                                                       \
   } while (0)
   if (T == 1) PHC_LAUNCH_STEP(1);
   else PHC_LAUNCH_STEP(4);

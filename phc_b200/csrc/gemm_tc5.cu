@@ -1,0 +1,346 @@
+// Blackwell-native GEMM for the MLPs: tcgen05.mma (kind::tf32) issued by one thread, operands staged by TMA
+// (cp.async.bulk.tensor, 128-byte swizzle), accumulator in TMEM, epilogue warps read it back with tcgen05.ld.
+// Same contract as phc_gemm (gemm.cu) -- C[M,N] (+)= epi(alpha * sum_k A(m,k) B(n,k)), both operand major-nesses --
+// and the same fp32-equivalent numerics: 3xTF32, but with the split done ONCE per operand in global memory
+// (phc_split_tf32: x -> hi = rna_tf32(x), lo = rna_tf32(x - hi)) because UMMA reads its operands straight from shared
+// memory; per k-step the issuing thread launches D += A_lo*B_hi, D += A_hi*B_lo, D += A_hi*B_hi (small terms first).
+//
+// CTA = 192 threads: warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer, warp 5 TMEM owner + MMA
+// issuer.  Tile 128 x 128, BLOCK_K = 32 floats (one 128-byte swizzle atom), 3 pipeline stages x 4 operand tiles x 16 KB.
+// Shared-memory operand layouts (what the descriptors encode, cf. cute/atom/mma_traits_sm100.hpp make_umma_desc):
+//   k-contiguous operand : tile [128 rows][32 floats], SW128; atoms of 8 rows x 128 B, SBO = 1024 B; one UMMA
+//                          (K = 8 floats = 32 B) advances the start address by 32 B inside the atom;
+//   mn-contiguous operand: 4 TMA boxes [32 k-rows][32 floats], each 4096 B; LBO = 4096 B between the MN atoms,
+//                          SBO = 1024 B between groups of 8 k-rows; one UMMA advances the start address by 1024 B.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/phc_b200.h"
+
+extern "C" void phc_set_error(const char* msg);
+extern "C" int phc_check_cuda(cudaError_t e, const char* what);
+extern "C" void phc_count_launches(int n);
+
+namespace phc {
+namespace tc5 {
+
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;               // 16 KB per operand tile (BM == BN)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct Args {
+  float* C; float* C_hi; float* C_lo;       // optional pre-split copies of the result for the next GEMM (same ldc)
+  const float* bias; const float* mask;
+  int M, N, K;
+  int64_t ldc, ldmask;
+  float alpha;
+  int relu, accumulate, k_splits;
+};
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(c) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok = 0;
+  uint32_t spins = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 24)) __trap();      // a protocol bug becomes a launch failure instead of a hung GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(s32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(s32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, LBO, SBO in 16-byte units,
+// version = 1 (bit 46), layout type SWIZZLE_128B = 2 (bits 61-63).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, major-ness bits, N >> 3, M >> 4
+__host__ __device__ constexpr uint32_t instr_desc(bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <bool A_K, bool B_K>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                const __grid_constant__ Args g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb_total = (g.K + BK - 1) / BK;
+  const int kb_per = (kb_total + g.k_splits - 1) / g.k_splits;
+  const int kb_begin = blockIdx.z * kb_per;
+  const int kb_end = min(kb_total, kb_begin + kb_per);
+  const int nkb = kb_end - kb_begin;
+  if (nkb <= 0) return;                                   // uniform per CTA
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, BN);               // whole warp, .sync.aligned
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        if (i >= STAGES) mbar_wait(empty_bar + s, ((i / STAGES) - 1) & 1);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        const int k0 = (kb_begin + i) * BK;
+        mbar_expect_tx(full_bar + s, STAGE_BYTES);
+        if (A_K) {
+          tma_load_2d(st, &tmAh, full_bar + s, k0, m0);
+          tma_load_2d(st + TILE_BYTES, &tmAl, full_bar + s, k0, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 32; ++j) {
+            tma_load_2d(st + j * 4096, &tmAh, full_bar + s, m0 + 32 * j, k0);
+            tma_load_2d(st + TILE_BYTES + j * 4096, &tmAl, full_bar + s, m0 + 32 * j, k0);
+          }
+        }
+        if (B_K) {
+          tma_load_2d(st + 2 * TILE_BYTES, &tmBh, full_bar + s, k0, n0);
+          tma_load_2d(st + 3 * TILE_BYTES, &tmBl, full_bar + s, k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) {
+            tma_load_2d(st + 2 * TILE_BYTES + j * 4096, &tmBh, full_bar + s, n0 + 32 * j, k0);
+            tma_load_2d(st + 3 * TILE_BYTES + j * 4096, &tmBl, full_bar + s, n0 + 32 * j, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc(!A_K, !B_K);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        mbar_wait(full_bar + s, (i / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t st = s32(smem + s * STAGE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < BK / 8; ++kk) {
+          const uint32_t a_off = A_K ? kk * 32 : kk * 1024;
+          const uint32_t b_off = B_K ? kk * 32 : kk * 1024;
+          const uint32_t a_lbo = A_K ? 16 : 4096, b_lbo = B_K ? 16 : 4096;
+          const uint64_t dAh = smem_desc(st + a_off, a_lbo, 1024);
+          const uint64_t dAl = smem_desc(st + TILE_BYTES + a_off, a_lbo, 1024);
+          const uint64_t dBh = smem_desc(st + 2 * TILE_BYTES + b_off, b_lbo, 1024);
+          const uint64_t dBl = smem_desc(st + 3 * TILE_BYTES + b_off, b_lbo, 1024);
+          umma_tf32(tmem_base, dAl, dBh, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          umma_tf32(tmem_base, dAh, dBl, idesc, 1u);
+          umma_tf32(tmem_base, dAh, dBh, idesc, 1u);
+        }
+        umma_commit(empty_bar + s);                       // frees the stage when these MMAs retire
+      }
+      umma_commit(tmem_full);                             // accumulator complete
+    }
+  } else {
+    // ===================== epilogue warps 0..3: TMEM -> registers -> global =====================
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const int m = m0 + row;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      if (m < g.M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < g.N) {
+            float v = g.alpha * __uint_as_float(r[j]);
+            if (g.bias && blockIdx.z == 0) v += g.bias[n];
+            if (g.relu) v = fmaxf(v, 0.f);
+            if (g.mask) v = (g.mask[(int64_t)m * g.ldmask + n] > 0.f) ? v : 0.f;
+            float* dst = g.C + (int64_t)m * g.ldc + n;
+            if (g.accumulate) atomicAdd(dst, v);
+            else {
+              *dst = v;
+              if (g.C_hi) {
+                uint32_t h, l;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+                const float res = v - __uint_as_float(h);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(res));
+                g.C_hi[(int64_t)m * g.ldc + n] = __uint_as_float(h);
+                g.C_lo[(int64_t)m * g.ldc + n] = __uint_as_float(l);
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// x -> hi = rna_tf32(x), lo = rna_tf32(x - hi) over a strided [rows, cols] block
+__global__ void split_tf32_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols, float* __restrict__ hi,
+                                  float* __restrict__ lo, int64_t ldo) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    const float v = x[r * ldx + c];
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    const float res = v - __uint_as_float(h);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(res));
+    hi[r * ldo + c] = __uint_as_float(h);
+    lo[r * ldo + c] = __uint_as_float(l);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map; inner dimension = the contiguous one.  kmajor: dims {K, rows}, box {32, 128};
+// otherwise dims {rows(MN), K}, box {32, 32}.
+static bool make_map(CUtensorMap* tm, const float* base, int64_t ld, int rows_mn, int K, bool kmajor) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2], strides[1];
+  cuuint32_t box[2], estr[2] = {1, 1};
+  if (kmajor) { dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows_mn; box[0] = 32; box[1] = 128; }
+  else { dims[0] = (cuuint64_t)rows_mn; dims[1] = (cuuint64_t)K; box[0] = 32; box[1] = 32; }
+  strides[0] = (cuuint64_t)ld * 4;
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace tc5
+}  // namespace phc
+
+extern "C" int phc_split_tf32(const float* x, int64_t ldx, int64_t rows, int32_t cols, float* hi, float* lo, int64_t ldo,
+                              void* stream) {
+  if (!x || !hi || !lo || rows < 0 || cols < 1 || ldx < cols || ldo < cols) { phc_set_error("phc_split_tf32: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  if (rows == 0) return PHC_OK;
+  int64_t g = (rows * cols + 255) / 256; if (g > 148 * 8) g = 148 * 8;
+  phc::tc5::split_tf32_kernel<<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, rows, cols, hi, lo, ldo); phc_count_launches(1);
+  return phc_check_cuda(cudaGetLastError(), "split_tf32_kernel");
+}
+
+extern "C" int phc_gemm_tc5(const float* A_hi, const float* A_lo, int64_t lda, int32_t a_kmajor, const float* B_hi,
+                            const float* B_lo, int64_t ldb, int32_t b_kmajor, float* C, float* C_hi, float* C_lo, int64_t ldc,
+                            int32_t M, int32_t N, int32_t K, float alpha, const float* bias, int32_t relu, const float* mask,
+                            int64_t ldmask, int32_t accumulate, int32_t k_splits, void* stream) {
+  using namespace phc::tc5;
+  if (!A_hi || !A_lo || !B_hi || !B_lo || !C || M < 0 || N < 0 || K < 1) { phc_set_error("phc_gemm_tc5: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  if (M == 0 || N == 0) return PHC_OK;
+  if ((lda & 3) || (ldb & 3)) { phc_set_error("phc_gemm_tc5: leading dimensions must be multiples of 4 floats (TMA strides are 16-byte multiples)"); return PHC_ERR_INVALID_ARG; }
+  for (const float* p : {A_hi, A_lo, B_hi, B_lo})
+    if (reinterpret_cast<uintptr_t>(p) & 15) { phc_set_error("phc_gemm_tc5: operands must be 16-byte aligned"); return PHC_ERR_INVALID_ARG; }
+  if (k_splits < 1) k_splits = 1;
+  if (k_splits > 1 && (!accumulate || relu || mask)) { phc_set_error("phc_gemm_tc5: split-K needs accumulate=1 and a linear epilogue"); return PHC_ERR_INVALID_ARG; }
+  CUtensorMap tAh, tAl, tBh, tBl;
+  if (!make_map(&tAh, A_hi, lda, M, K, a_kmajor) || !make_map(&tAl, A_lo, lda, M, K, a_kmajor) ||
+      !make_map(&tBh, B_hi, ldb, N, K, b_kmajor) || !make_map(&tBl, B_lo, ldb, N, K, b_kmajor)) {
+    phc_set_error("phc_gemm_tc5: cuTensorMapEncodeTiled failed"); return PHC_ERR_CUDA;
+  }
+  Args g;
+  if ((C_hi == nullptr) != (C_lo == nullptr) || (C_hi && accumulate)) { phc_set_error("phc_gemm_tc5: C_hi/C_lo come as a pair and not with accumulate"); return PHC_ERR_INVALID_ARG; }
+  g.C = C; g.C_hi = C_hi; g.C_lo = C_lo; g.bias = bias; g.mask = mask; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.ldmask = ldmask; g.alpha = alpha;
+  g.relu = relu; g.accumulate = accumulate; g.k_splits = k_splits;
+  const dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, k_splits);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+#define PHC_TC5_LAUNCH(AK, BK_)                                                                                   \
+  do {                                                                                                            \
+    static bool done = false;                                                                                     \
+    if (!done) {                                                                                                  \
+      e = cudaFuncSetAttribute(gemm_tc5_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); \
+      if (e != cudaSuccess) return phc_check_cuda(e, "cudaFuncSetAttribute(gemm_tc5)");                           \
+      done = true;                                                                                                \
+    }                                                                                                             \
+    gemm_tc5_kernel<AK, BK_><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tAh, tAl, tBh, tBl, g);                        \
+    phc_count_launches(1);                                                                                        \
+  } while (0)
+  if (a_kmajor && b_kmajor) PHC_TC5_LAUNCH(true, true);
+  else if (a_kmajor && !b_kmajor) PHC_TC5_LAUNCH(true, false);
+  else if (!a_kmajor && b_kmajor) PHC_TC5_LAUNCH(false, true);
+  else PHC_TC5_LAUNCH(false, false);
+#undef PHC_TC5_LAUNCH
+  return phc_check_cuda(cudaGetLastError(), "gemm_tc5_kernel launch");
+}

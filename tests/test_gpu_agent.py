@@ -1,0 +1,100 @@
+"""GPU tests of the host mirrors: HumanoidIm (reset path with masks, step) against the oracle, and AMPAgent end to end
+(rollout + update on small sizes: finite, parameters move, buffers consistent)."""
+import pytest
+import torch
+
+from oracle import phc_oracle as O
+from phc_b200 import synthetic as syn
+from phc_b200.env.humanoid_im import HumanoidIm, RLGPUEnv
+from phc_b200.learning.amp_agent import AMPAgent
+from tests.helpers import close, oracle_tables, smpl_step_config
+
+pytestmark = pytest.mark.gpu
+
+
+def make_task(n, seed=0):
+    m = syn.make_motions(n, seed=seed, min_frames=40, max_frames=90)
+    return m, HumanoidIm({"env": {"num_envs": n}, "motion_data": m, "seed": seed})
+
+
+def test_reset_then_step_match_oracle():
+    n = 200
+    m, task = make_task(n, seed=1)
+    tab, cfg = oracle_tables(m), smpl_step_config()
+    obs = task.reset()                               # first launch is the (smaller-smem) obs-only plan: regression for the
+    torch.cuda.synchronize()                         # cudaFuncSetAttribute ordering bug found by bench.py
+    ids, t0 = task._sampled_motion_ids.cpu(), task._motion_start_times.cpu()
+    assert int(task.progress_buf.abs().sum()) == 0
+    # reference-state init: the simulator tensors hold the reference pose at the sampled start time
+    st = O.motion_state(tab, ids, t0, torch.zeros(n, 3))
+    body = task._rigid_body_state_reshaped.cpu()
+    close(body[..., 0:3], st["rg_pos"], what="reset pos")
+    close(body[..., 3:7], st["rb_rot"], what="reset rot")
+    close(task._dof_state.cpu()[..., 0], st["dof_pos"], rtol=1e-4, atol=2e-5, what="reset dof_pos")
+    # AMP window re-initialised from the reference motion (current + 9 history slots)
+    close(task._amp_obs_buf.cpu(), O.amp_obs_demo(tab, cfg, ids, t0), rtol=1e-4, atol=2e-5, what="amp window after reset")
+    # observation of the reset envs: self obs + task obs at t0 + dt
+    nxt = O.motion_state(tab, ids, (torch.zeros(n) + 1) * cfg.dt + t0, torch.zeros(n, 3))
+    bp, br, bv, bw = body[..., 0:3], body[..., 3:7], body[..., 7:10], body[..., 10:13]
+    exp_obs = torch.cat((O.self_obs(bp, br, bv, bw), O.task_obs_v6(bp[:, 0], br[:, 0], bp, br, bv, bw, nxt["rg_pos"], nxt["rb_rot"],
+                                                                     nxt["body_vel"], nxt["body_ang_vel"])), dim=-1)
+    close(obs.cpu(), exp_obs, atol=2e-6, what="obs after reset")
+
+    # one env step on a fresh simulator snapshot
+    hist = task._amp_obs_buf.cpu().clone()
+    task.step(None)
+    torch.cuda.synchronize()
+    exp = O.env_step(tab, cfg, task._rigid_body_state_reshaped.cpu(), task._dof_state.cpu(), task.dof_force_tensor.cpu(),
+                     task.progress_buf.cpu(), ids, t0, torch.zeros(n), torch.zeros(n, 3), hist)
+    close(task.obs_buf.cpu(), exp["obs"], atol=2e-6, what="obs")
+    close(task.rew_buf.cpu(), exp["rew"], what="rew")
+    close(task.reset_buf.cpu(), exp["reset"], what="reset")
+    close(task._amp_obs_buf.cpu(), exp["amp_obs_buf"], what="amp window")
+
+    # masked reset: only flagged envs change
+    mask = (torch.arange(n, device=task.device) % 3 == 0).long()
+    before_obs, before_prog, before_start = task.obs_buf.clone(), task.progress_buf.clone(), task._motion_start_times.clone()
+    task.reset(mask)
+    torch.cuda.synchronize()
+    keep = mask == 0
+    assert torch.equal(task.obs_buf[keep], before_obs[keep]) and torch.equal(task.progress_buf[keep], before_prog[keep])
+    assert torch.equal(task._motion_start_times[keep], before_start[keep])
+    assert int(task.progress_buf[mask == 1].abs().sum()) == 0 and not torch.equal(task.obs_buf[mask == 1], before_obs[mask == 1])
+    # reference-style index list selects the same envs
+    task.reset(torch.nonzero(mask).flatten())
+    assert torch.equal(task._reset_mask, mask)
+
+
+def test_agent_epoch_small():
+    n = 64
+    _, task = make_task(n, seed=2)
+    agent = AMPAgent("t", {"vec_env": RLGPUEnv(task), "horizon_length": 8, "minibatch_size": 256, "amp_minibatch_size": 64,
+                           "mini_epochs": 2, "amp_obs_demo_buffer_size": 2048, "amp_replay_buffer_size": 2048,
+                           "amp_batch_size": 128, "network": {"mlp": {"units": [128, 64], "activation": "relu"},
+                                                              "disc": {"units": [128, 64], "activation": "relu"}}})
+    agent.obs = agent.env_reset()
+    agent._init_amp_demo_buf()
+    p0 = agent.model.params.clone()
+    mean0 = agent.running_mean_std.running_mean.clone()
+    info = None
+    for _ in range(2):
+        info = agent.train_epoch()
+    torch.cuda.synchronize()
+    assert torch.isfinite(agent.model.params).all() and not torch.equal(agent.model.params, p0)
+    assert agent.opt_step == 2 * 2 * (8 * n // 256)
+    assert not torch.equal(agent.running_mean_std.running_mean, mean0) and float(agent.running_mean_std.count) > 1
+    assert torch.isfinite(info["returns"]).all() and torch.isfinite(info["disc_rewards"]).all()
+    r = agent.train_result_dict()
+    assert all(v == v for v in r.values())          # no NaN
+    # GAE bookkeeping: returns = advantages + values on the flattened rollout
+    eb = agent.experience_buffer
+    adv = O.gae(eb["dones"].cpu(), eb["values"].cpu(), (0.5 * eb["rewards"] + 0.5 * info["disc_rewards"].view(n, 8, 1).transpose(0, 1)).cpu(),
+                eb["next_values"].cpu(), 0.99, 0.95)
+    close(info["returns"].view(n, 8, 1).transpose(0, 1).cpu(), adv + eb["values"].cpu(), rtol=1e-4, atol=1e-4, what="returns")
+    # checkpoint round trip with the reference's keys
+    sd = agent.get_full_state_weights()
+    assert {"model", "running_mean_std", "reward_mean_std", "amp_input_mean_std"} <= set(sd)
+    assert "a2c_network.actor_mlp.0.weight" in sd["model"] and sd["model"]["a2c_network.actor_mlp.0.weight"].shape == (128, 934)
+    agent.model.params.zero_()
+    agent.set_full_state_weights(sd)
+    assert torch.equal(agent.model.state_dict()["a2c_network._disc_logits.weight"], sd["model"]["a2c_network._disc_logits.weight"])

@@ -111,15 +111,18 @@ def test_disc_reward_vs_reference_golden():
     close(comb.cpu(), g["d_combined"].reshape(-1), what="combined reward")
 
 
-def _rand_batch(B, Bd, obs, act, amp, seed):
+def _rand_batch(B, Bd, obs, act, amp, seed, mu_fn=None):
+    """A PPO minibatch.  With mu_fn (obs_n -> current policy mean) the stored "old" policy sits close to the current one,
+    like real PPO data: ratios are O(1) and both clip branches are hit; without it old_mu is random (stress case)."""
     g = torch.Generator().manual_seed(seed)
     r = lambda *s: torch.randn(*s, generator=g)
     logstd = torch.full((act,), -2.9)
-    old_mu = r(B, act) * 0.8
+    obs_n = torch.clamp(r(B, obs) * 1.5, -5, 5)
     old_sigma = torch.exp(logstd).expand(B, act).clone()
+    old_mu = r(B, act) * 0.8 if mu_fn is None else (mu_fn(obs_n) + 0.3 * old_sigma * r(B, act)).float()
     actions = old_mu + old_sigma * r(B, act)
     old_nlp = O.gaussian_neglogp(actions, old_mu, old_sigma, logstd.expand(B, act))
-    return dict(obs_n=torch.clamp(r(B, obs) * 1.5, -5, 5), actions=actions, old_neglogp=old_nlp + 0.05 * r(B),
+    return dict(obs_n=obs_n, actions=actions, old_neglogp=old_nlp + 0.05 * r(B),
                 advantages=r(B), old_mu=old_mu, old_sigma=old_sigma, returns=r(B, 1),
                 amp_agent=torch.clamp(r(Bd, amp), -5, 5), amp_replay=torch.clamp(r(Bd, amp), -5, 5), amp_demo=torch.clamp(r(Bd, amp), -5, 5))
 
@@ -133,12 +136,12 @@ CFG = dict(e_clip=0.2, critic_coef=5.0, entropy_coef=0.0, bounds_loss_coef=10.0,
 def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units):
     """forward values, every parameter gradient, the clipped Adam step: CUDA engine vs torch autograd on the CPU."""
     from tests.learner_harness import run_cuda_minibatch
-    batch = _rand_batch(B, Bd, obs, act, amp, seed=B)
     net = AMPNetwork(obs, act, amp, units, units, device=DEV, seed=3)
-    # move the policy off its initialisation so ratios / clipping / bound loss are all active
-    for l in net.actor.layers:
-        net.weight(l).mul_(3.0)
+    net.weight(net.actor.head).mul_(6.0)          # |mu| reaches past the +-1 soft bound: bound loss active
     sd = {k: v.cpu() for k, v in net.state_dict().items()}
+    aw, ab = PO.stack_params(sd, "actor_mlp", "mu", len(units))
+    mu_fn = lambda x: O.mlp_forward(x.double(), [w.double() for w in aw], [b.double() for b in ab])
+    batch = _rand_batch(B, Bd, obs, act, amp, seed=B, mu_fn=mu_fn)
     exp = PO.minibatch_update(sd, batch, CFG, n_hidden=len(units), dtype=torch.float64)      # near-exact reference
     got = run_cuda_minibatch(net, batch, CFG)
 
@@ -157,6 +160,7 @@ def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units):
     close(torch.tensor(s["kl"]), f32(exp["kl"]), rtol=1e-3, atol=1e-4, what="kl")
     close(torch.tensor(s["disc_grad_penalty"]), f32(exp["disc"]["disc_grad_penalty"]), rtol=1e-4, atol=1e-6, what="grad penalty")
     close(torch.tensor(s["disc_agent_acc"]), f32(exp["disc"]["disc_agent_acc"]), atol=2e-3, what="disc agent acc")
+    assert 0.02 < s["actor_clip_frac"] < 0.98 and s["b_loss"] > 0, "test batch must exercise both PPO branches and the bound loss"
     gsd = got["grads"]
     for k, ge in exp["grads"].items():
         scaled(gsd[k], ge, 1e-4, f"grad {k}")
