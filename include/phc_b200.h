@@ -181,7 +181,16 @@ PHC_API int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* motion_ids,
                      int32_t first_step, int32_t num_steps, float dt, uint32_t flags, const int32_t* key_bodies,
                      int32_t num_key_bodies, const int32_t* amp_joints, int32_t num_amp_joints, float* out,
                      int64_t out_stride, const int64_t* only_where /* [n] or NULL: skip rows whose entry is 0 */,
+                     int32_t slot_offset /* ring rotation: step k lands in slot (k + slot_offset) % num_steps; 0 = plain */,
                      void* stream);
+
+/* AMP observation ring.  Instead of shifting the [S, A] window of every env each step (2 x 7 KB per env-step,
+ * humanoid_amp.py:662-670) the fused step writes only the newest vector into physical slot `head` of a ring
+ * (phc_env_step with amp_out = ring + head*A, amp_hist_in = NULL), and the newest-first window the agent stores
+ * (extras['amp_obs'], amp_agent.py:341) is produced by this copy straight into its destination:
+ *   out[n, k, :] = ring[n, (head + k) % S, :]. */
+PHC_API int phc_amp_window_export(const float* ring, int64_t ring_stride, int64_t n, int32_t num_steps, int32_t amp_dim,
+                          int32_t head, float* out, int64_t out_stride, void* stream);
 
 /* Reset path (HumanoidAMP._set_env_state, humanoid_amp.py:605-637 fed by _sample_ref_state, humanoid_im.py:1000-1023):
  * write the reference pose at (motion_ids[e], times[e]) (+offset) into the simulator tensors of every env e with

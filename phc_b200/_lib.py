@@ -73,7 +73,8 @@ SIGNATURES = {
     "phc_amp_obs_dim": (C.c_int, [C.c_int32, C.c_int32, C.c_uint32]),
     "phc_env_step": (C.c_int, [C.POINTER(PhcStepArgs), _p]),
     "phc_amp_obs_demo": (C.c_int, [C.POINTER(PhcMotionLib), _p, _p, C.c_int64, C.c_int32, C.c_int32, C.c_float,
-                                   C.c_uint32, _p, C.c_int32, _p, C.c_int32, _p, C.c_int64, _p, _p]),
+                                   C.c_uint32, _p, C.c_int32, _p, C.c_int32, _p, C.c_int64, _p, C.c_int32, _p]),
+    "phc_amp_window_export": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, C.c_int64, _p]),
     "phc_set_env_state": (C.c_int, [C.POINTER(PhcMotionLib), _p, _p, _p, _p, C.c_int64, _p, C.c_int32, _p, _p]),
     "phc_gae": (C.c_int, [_p, _p, _p, _p, C.c_int32, C.c_int64, C.c_float, C.c_float, _p, _p, _p]),
     "phc_adv_norm_workspace_bytes": (C.c_int64, [C.c_int64]),

@@ -10,8 +10,11 @@
 // Shared-memory operand layouts (what the descriptors encode, cf. cute/atom/mma_traits_sm100.hpp make_umma_desc):
 //   k-contiguous operand : tile [128 rows][32 floats], SW128; atoms of 8 rows x 128 B, SBO = 1024 B; one UMMA
 //                          (K = 8 floats = 32 B) advances the start address by 32 B inside the atom;
-//   mn-contiguous operand: 4 TMA boxes [32 k-rows][32 floats], each 4096 B; LBO = 4096 B between the MN atoms,
-//                          SBO = 1024 B between groups of 8 k-rows; one UMMA advances the start address by 1024 B.
+//   mn-contiguous operand: for 32-bit (tf32) data the only UMMA layout is SWIZZLE_128B_BASE32B (32-byte swizzle
+//                          granularity, cute Layout_MN_SW128_32B_Atom = Swizzle<2,5,2>, atoms of 4 k-rows x 128 B), the
+//                          TMA counterpart is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  4 TMA boxes [32 k-rows][32 floats],
+//                          each 4096 B: LBO = 4096 B between MN atoms, SBO = 512 B between groups of 4 k-rows; one UMMA
+//                          (K = 8 = two groups) advances the start address by 1024 B.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -90,14 +93,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, LBO, SBO in 16-byte units,
-// version = 1 (bit 46), layout type SWIZZLE_128B = 2 (bits 61-63).
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// version = 1 (bit 46), layout type in bits 61-63: SWIZZLE_128B = 2 (k-contiguous), SWIZZLE_128B_BASE32B = 1
+// (mn-contiguous 32-bit operands).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 
@@ -185,10 +189,12 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           const uint32_t a_off = A_K ? kk * 32 : kk * 1024;
           const uint32_t b_off = B_K ? kk * 32 : kk * 1024;
           const uint32_t a_lbo = A_K ? 16 : 4096, b_lbo = B_K ? 16 : 4096;
-          const uint64_t dAh = smem_desc(st + a_off, a_lbo, 1024);
-          const uint64_t dAl = smem_desc(st + TILE_BYTES + a_off, a_lbo, 1024);
-          const uint64_t dBh = smem_desc(st + 2 * TILE_BYTES + b_off, b_lbo, 1024);
-          const uint64_t dBl = smem_desc(st + 3 * TILE_BYTES + b_off, b_lbo, 1024);
+          const uint32_t a_sbo = A_K ? 1024 : 512, b_sbo = B_K ? 1024 : 512;
+          const uint32_t a_lt = A_K ? 2 : 1, b_lt = B_K ? 2 : 1;
+          const uint64_t dAh = smem_desc(st + a_off, a_lbo, a_sbo, a_lt);
+          const uint64_t dAl = smem_desc(st + TILE_BYTES + a_off, a_lbo, a_sbo, a_lt);
+          const uint64_t dBh = smem_desc(st + 2 * TILE_BYTES + b_off, b_lbo, b_sbo, b_lt);
+          const uint64_t dBl = smem_desc(st + 3 * TILE_BYTES + b_off, b_lbo, b_sbo, b_lt);
           umma_tf32(tmem_base, dAl, dBh, idesc, (i > 0 || kk > 0) ? 1u : 0u);
           umma_tf32(tmem_base, dAh, dBl, idesc, 1u);
           umma_tf32(tmem_base, dAh, dBh, idesc, 1u);
@@ -285,7 +291,8 @@ static bool make_map(CUtensorMap* tm, const float* base, int64_t ld, int rows_mn
   else { dims[0] = (cuuint64_t)rows_mn; dims[1] = (cuuint64_t)K; box[0] = 32; box[1] = 32; }
   strides[0] = (cuuint64_t)ld * 4;
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }

@@ -141,6 +141,7 @@ struct AmpDemoArgs {
   float* out;
   int64_t out_stride;
   const int64_t* only_where;
+  int32_t slot_offset;      // ring rotation: logical step k is written to physical slot (k + slot_offset) % num_steps
 };
 
 // warp per (sample, history step): motion sample at t0 - (first_step + k) dt, then build_amp_observations_smpl
@@ -168,7 +169,8 @@ __global__ void __launch_bounds__(128) amp_demo_kernel(const __grid_constant__ A
   const Q4 root_q = upright ? r.q : strip_base_rot(r.q);
   const Q4 hinv = quat_about_z(-heading_angle(root_q));
   const int nj = a.num_amp_joints, nk = a.num_key_bodies;
-  float* o = a.out + si * a.out_stride + (int64_t)k * (has_h + 12 + 9 * nj + 3 * nk) + (has_h ? 1 : 0);
+  const int kp = (k + a.slot_offset) % a.num_steps;
+  float* o = a.out + si * a.out_stride + (int64_t)kp * (has_h + 12 + 9 * nj + 3 * nk) + (has_h ? 1 : 0);
   if (lane == 0) {
     if (has_h) o[-1] = r.p.z;
     const TanNorm tn = tan_norm((a.flags & PHC_FLAG_LOCAL_ROOT_OBS) ? qmul(hinv, root_q) : root_q);
@@ -211,6 +213,30 @@ set_env_state_kernel(const __grid_constant__ PhcMotionLib lib, const int64_t* __
   if (dof_state && lane > 0) {
     float* d = dof_state + ((size_t)env * (J - 1) + (lane - 1)) * 6;      // [D, 2] interleaved (pos, vel)
     d[0] = s.dof_pos.x; d[1] = s.dof_vel.x; d[2] = s.dof_pos.y; d[3] = s.dof_vel.y; d[4] = s.dof_pos.z; d[5] = s.dof_vel.z;
+  }
+}
+
+// AMP ring -> newest-first window: out[n, k, :] = ring[n, (head + k) % S, :]   (pure copy, float4 when A % 4 == 0)
+__global__ void amp_window_export_kernel(const float* __restrict__ ring, int64_t ring_stride, int64_t n, int S, int A, int head,
+                                         float* __restrict__ out, int64_t out_stride) {
+  if ((A & 3) == 0 && (ring_stride & 3) == 0 && (out_stride & 3) == 0) {
+    const int A4 = A >> 2;
+    const int64_t total = n * S * A4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t e = i / (S * A4);
+      const int r = (int)(i - e * S * A4);
+      const int k = r / A4, c = r - k * A4;
+      const int kp = (head + k) % S;
+      reinterpret_cast<float4*>(out + e * out_stride)[k * A4 + c] = reinterpret_cast<const float4*>(ring + e * ring_stride)[kp * A4 + c];
+    }
+  } else {
+    const int64_t total = n * S * A;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t e = i / (S * A);
+      const int r = (int)(i - e * S * A);
+      const int k = r / A, c = r - k * A;
+      out[e * out_stride + k * A + c] = ring[e * ring_stride + ((head + k) % S) * A + c];
+    }
   }
 }
 
@@ -265,7 +291,7 @@ extern "C" int phc_motion_state(const PhcMotionLib* lib, const int64_t* ids, con
 extern "C" int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* ids, const float* times0, int64_t n,
                                 int32_t first_step, int32_t num_steps, float dt, uint32_t flags,
                                 const int32_t* key_bodies, int32_t nk, const int32_t* amp_joints, int32_t nj, float* out,
-                                int64_t out_stride, const int64_t* only_where, void* stream) {
+                                int64_t out_stride, const int64_t* only_where, int32_t slot_offset, void* stream) {
   int rc = check_lib(lib, "phc_amp_obs_demo");
   if (rc) return rc;
   if (!lib->frames_joint) { phc_set_error("phc_amp_obs_demo: needs frames_joint"); return PHC_ERR_INVALID_ARG; }
@@ -278,6 +304,7 @@ extern "C" int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* ids, con
   phc::AmpDemoArgs a;
   a.lib = *lib; a.ids = ids; a.times0 = times0; a.n = n; a.first_step = first_step; a.num_steps = num_steps; a.dt = dt;
   a.flags = flags; a.num_key_bodies = nk; a.amp_joints = amp_joints; a.num_amp_joints = nj; a.out = out; a.out_stride = out_stride; a.only_where = only_where;
+  a.slot_offset = ((slot_offset % num_steps) + num_steps) % num_steps;
   for (int i = 0; i < PHC_MAX_KEY_BODIES; ++i) a.key_bodies[i] = i < nk ? key_bodies[i] : -1;
   const int wpb = 4;
   const int64_t warps = n * num_steps;
@@ -297,4 +324,17 @@ extern "C" int phc_set_env_state(const PhcMotionLib* lib, const int64_t* ids, co
   phc::set_env_state_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       *lib, ids, times, offset, only_where, n, body_state, bodies_per_env, dof_state); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "set_env_state_kernel launch");
+}
+
+extern "C" int phc_amp_window_export(const float* ring, int64_t ring_stride, int64_t n, int32_t num_steps, int32_t amp_dim,
+                                     int32_t head, float* out, int64_t out_stride, void* stream) {
+  if (!ring || !out || n < 0 || num_steps < 1 || amp_dim < 1 || head < 0 || head >= num_steps ||
+      ring_stride < (int64_t)num_steps * amp_dim || out_stride < (int64_t)num_steps * amp_dim) {
+    phc_set_error("phc_amp_window_export: bad arguments"); return PHC_ERR_INVALID_ARG;
+  }
+  if (n == 0) return PHC_OK;
+  if ((reinterpret_cast<uintptr_t>(ring) | reinterpret_cast<uintptr_t>(out)) & 15) { phc_set_error("phc_amp_window_export: buffers must be 16-byte aligned"); return PHC_ERR_INVALID_ARG; }
+  int64_t g = (n * num_steps * amp_dim / 4 + 255) / 256; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1;
+  phc::amp_window_export_kernel<<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(ring, ring_stride, n, num_steps, amp_dim, head, out, out_stride); phc_count_launches(1);
+  return phc_check_cuda(cudaGetLastError(), "amp_window_export_kernel launch");
 }

@@ -134,14 +134,19 @@ class HumanoidIm:
                       dof_state=self._dof_state, dof_force=self.dof_force_tensor, progress=self.progress_buf,
                       motion_ids=self._sampled_motion_ids, start_times=self._motion_start_times,
                       start_offsets=self._motion_start_times_offset, global_offset=self._global_offset)
-        self._plan = ops.EnvStepPlan(cycle_counter=self._cycle_counter, with_ref_buffers=True, **common)
+        # AMP history: a RING [N, S, A] (one 784-byte slot written per step) instead of the reference's per-step shift of
+        # the whole window (humanoid_amp.py:662-670); the newest-first window is exported on demand (`_amp_obs_buf`,
+        # `export_amp_obs`).  amp_window_shift=True in cfg restores the in-kernel reference-style shift.
+        self._amp_use_ring = not bool(cfg.get("amp_window_shift", False))
+        self._plan = ops.EnvStepPlan(cycle_counter=self._cycle_counter, with_ref_buffers=True, amp_ring=self._amp_use_ring, **common)
         p = self._plan
         self.obs_buf, self.rew_buf, self.reward_raw = p.obs, p.rew, p.reward_raw
         self.reset_buf, self._terminate_buf = p.reset, p.terminate
-        self._amp_obs_buf = p.amp_obs_buf
-        self._curr_amp_obs_buf, self._hist_amp_obs_buf = self._amp_obs_buf[:, 0], self._amp_obs_buf[:, 1:]
+        self._amp_store = p.amp_obs_buf                              # ring (or the shifted window itself)
+        self._amp_window = torch.zeros_like(self._amp_store) if self._amp_use_ring else self._amp_store
         self.ref_body_pos, self.ref_body_rot, self.ref_body_vel = p.ref_body_pos, p.ref_body_rot, p.ref_body_vel
         self._num_amp_obs_per_step = p.amp_dim
+        self._curr_amp_obs_buf = self._hist_amp_obs_buf = None        # reference views of the shifted window; not kept with the ring
         self.self_obs_buf = self.obs_buf[:, :p.self_dim]
         # observation-only re-computation for just-reset envs (_compute_observations(env_ids))
         self._plan_reset_obs = ops.EnvStepPlan(obs=self.obs_buf, only_where=self._reset_mask, obs_only=True, with_amp=False, **common)
@@ -178,14 +183,30 @@ class HumanoidIm:
         self.sim.simulate(actions)
         self.post_physics_step()
 
+    @property
+    def _amp_obs_buf(self) -> torch.Tensor:
+        """Newest-first AMP window [N, S, A] (the reference attribute of that name), materialised from the ring."""
+        if self._amp_use_ring:
+            ops.amp_window_export(self._amp_store, self._plan.ring_head, self._amp_window)
+        return self._amp_window
+
+    def export_amp_obs(self, out: torch.Tensor) -> torch.Tensor:
+        """Write extras['amp_obs'] ([N, S*A], newest first) straight into `out` (e.g. the agent's experience-buffer row)."""
+        if self._amp_use_ring:
+            return ops.amp_window_export(self._amp_store, self._plan.ring_head, out)
+        out.copy_(self._amp_store.view(out.shape))
+        return out
+
     def post_physics_step(self) -> None:
         """Humanoid.post_physics_step (humanoid.py:1634-1650) + HumanoidAMP.post_physics_step (humanoid_amp.py:194-210):
-        reward, reset, observations, AMP window -- one launch."""
+        reward, reset, observations, AMP observation -- one launch."""
         self.progress_buf += 1
+        if self._amp_use_ring:
+            self._plan.advance_ring()
         self._plan.run()
         self.extras["terminate"] = self._terminate_buf
         self.extras["reward_raw"] = self.reward_raw
-        self.extras["amp_obs"] = self._amp_obs_buf.view(self.num_envs, self.get_num_amp_obs())
+        self.extras["amp_obs_export"] = self.export_amp_obs          # lazily materialised window (see export_amp_obs)
 
     # kept for API parity: the pieces are produced together by the fused launch
     def _compute_reward(self, actions=None):
@@ -239,7 +260,8 @@ class HumanoidIm:
         self._plan_reset_obs.run()
         # _init_amp_obs: current + history slots from the reference motion at t0 - k dt
         ops.amp_obs_demo(ml, self.step_cfg, self._sampled_motion_ids, self._motion_start_times, first_step=0,
-                         num_steps=self._num_amp_obs_steps, out=self._amp_obs_buf, only_where=self._reset_mask)
+                         num_steps=self._num_amp_obs_steps, out=self._amp_store, only_where=self._reset_mask,
+                         slot_offset=self._plan.ring_head if self._amp_use_ring else 0)
         return self.obs_buf
 
     def resample_motions(self):
@@ -284,7 +306,7 @@ class RLGPUEnv:
 
     def step(self, action):
         obs, rew, reset, extras = self.env.step(action)
-        return {"obs": obs}, rew, reset, extras
+        return {"obs": obs}, rew, reset, extras      # extras['amp_obs_export'](dst) fills the AMP window (amp_agent.py:341)
 
     def reset(self, env_ids=None):
         return {"obs": self.env.reset(env_ids)}

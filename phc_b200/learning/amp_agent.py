@@ -356,7 +356,10 @@ class AMPAgent:
             eb["rewards"][n].copy_(rewards)
             eb["next_obses"][n].copy_(self.obs["obs"])
             eb["dones"][n].copy_(self.dones)
-            eb["amp_obs"][n].copy_(infos["amp_obs"])
+            if "amp_obs_export" in infos:
+                infos["amp_obs_export"](eb["amp_obs"][n])            # AMP ring -> newest-first window, written in place
+            else:
+                eb["amp_obs"][n].copy_(infos["amp_obs"])
             terminated = infos["terminate"].float()
             terminated_flags += terminated
             rr = infos["reward_raw"].mean(dim=0)
@@ -494,6 +497,8 @@ class AMPAgent:
                                      net.num_floats, self._gsumsq.data_ptr(), grad_scale,
                                      self.grad_norm if self.truncate_grads else 0.0, self.last_lr, 0.9, 0.999, 1e-8,
                                      self.opt_step, st))
+        if eng.backend == "tc5":
+            net.refresh_split()                    # hi/lo operand copies of the updated weights
         self._last_B, self._last_Bd = B, Bd
 
     def _disc_grad_penalty_backward(self, x_demo: torch.Tensor, h_demo, Bd: int) -> None:

@@ -14,6 +14,7 @@ multiple of 4 floats (934 -> 936) because the GEMM loads 16-byte chunks; pad col
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -84,13 +85,22 @@ class AMPNetwork:
         self.num_floats = off
         self.params = torch.zeros(off, dtype=torch.float32, device=self.device)
         self.grads = torch.zeros(off, dtype=torch.float32, device=self.device)
+        # 3xTF32 operand split of the weights for the tcgen05 GEMM (refreshed after every optimiser step)
+        self.params_hi = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.params_lo = torch.zeros(off, dtype=torch.float32, device=self.device)
         self.sigma = torch.full((action_dim,), float(sigma_init), dtype=torch.float32, device=self.device)
         self._init_default(seed)
 
     # ---- views -------------------------------------------------------------------------------------------
-    def weight(self, l: LinearSpec, grad: bool = False) -> torch.Tensor:
-        buf = self.grads if grad else self.params
+    def weight(self, l: LinearSpec, grad: bool = False, part: Optional[str] = None) -> torch.Tensor:
+        buf = self.grads if grad else {None: self.params, "hi": self.params_hi, "lo": self.params_lo}[part]
         return buf[l.w_off:l.w_off + l.out_dim * l.in_pad].view(l.out_dim, l.in_pad)
+
+    def refresh_split(self) -> None:
+        """hi = rna_tf32(W), lo = rna_tf32(W - hi) over the whole bucket (one streaming pass, 5.5 M floats)."""
+        n = self.num_floats
+        _lib.check(_lib.load().phc_split_tf32(self.params.data_ptr(), n, 1, n, self.params_hi.data_ptr(), self.params_lo.data_ptr(),
+                                              n, _stream()), "phc_split_tf32")
 
     def bias(self, l: LinearSpec, grad: bool = False) -> torch.Tensor:
         buf = self.grads if grad else self.params
@@ -149,16 +159,66 @@ def _splits(tiles: int, K: int) -> int:
 class MLPEngine:
     """Forward / backward of the MLP stacks through phc_gemm, with per-batch-size activation workspaces."""
 
-    def __init__(self, net: AMPNetwork):
+    def __init__(self, net: AMPNetwork, backend: Optional[str] = None):
         self.net = net
         self.lib = _lib.load()
         self.dev = net.device
         self._ws: Dict[Tuple[str, int], Dict[str, torch.Tensor]] = {}
+        # "mma": warp-level mma.sync 3xTF32 (gemm.cu); "tc5": tcgen05 / TMEM / TMA 3xTF32 (gemm_tc5.cu)
+        self.backend = backend or os.environ.get("PHC_GEMM", "mma")
+        assert self.backend in ("mma", "tc5")
+        self._companions: Dict[Tuple[int, Tuple[int, ...], Tuple[int, ...]], Tuple[torch.Tensor, torch.Tensor]] = {}
+        if self.backend == "tc5":
+            net.refresh_split()
+
+    # -- operand split bookkeeping for the tcgen05 path --------------------------------------------------------------
+    def companions(self, t: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(hi, lo) buffers that shadow activation tensor `t` (same shape / strides)."""
+        key = (t.data_ptr(), tuple(t.shape), tuple(t.stride()))
+        c = self._companions.get(key)
+        if c is None:
+            base_rows, ld = t.shape[0], t.stride(0)
+            c = (torch.zeros(base_rows, ld, device=self.dev)[:, :t.shape[1]], torch.zeros(base_rows, ld, device=self.dev)[:, :t.shape[1]])
+            self._companions[key] = c
+        return c
+
+    def split(self, t: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        hi, lo = self.companions(t)
+        rc = self.lib.phc_split_tf32(t.data_ptr(), t.stride(0), t.shape[0], t.shape[1], hi.data_ptr(), lo.data_ptr(), hi.stride(0), _stream())
+        if rc:
+            _lib.check(rc, "phc_split_tf32")
+        return hi, lo
+
+    def _weight_parts(self, W: torch.Tensor) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+        """If W is a view into the parameter bucket, the matching views of the pre-split buckets."""
+        p = self.net.params
+        off = (W.data_ptr() - p.data_ptr()) // 4
+        if 0 <= off < p.numel() and W.data_ptr() >= p.data_ptr():
+            n = W.shape[0] * W.stride(0)
+            return (self.net.params_hi[off:off + n].view(W.shape[0], W.stride(0))[:, :W.shape[1]],
+                    self.net.params_lo[off:off + n].view(W.shape[0], W.stride(0))[:, :W.shape[1]])
+        return None
 
     # -- raw GEMM ------------------------------------------------------------------------------------------------
-    def gemm(self, A, a_k, B, b_k, C, M, N, K, alpha=1.0, bias=None, relu=False, mask=None, accumulate=False, k_splits=1):
+    def gemm(self, A, a_k, B, b_k, C, M, N, K, alpha=1.0, bias=None, relu=False, mask=None, accumulate=False, k_splits=1,
+             a_split=None, b_split=None, split_out: bool = False):
+        """a_split / b_split: already up-to-date (hi, lo) companions of the operand (skips the split pass);
+        split_out: also produce C's companions in the epilogue (tc5 only)."""
         lda = A.stride(0)
         ldb = B.stride(0)
+        if self.backend == "tc5":
+            Ah, Al = a_split or self._weight_parts(A) or self.split(A)
+            Bh, Bl = b_split or self._weight_parts(B) or self.split(B)
+            Ch = Cl = None
+            if split_out and not accumulate:
+                Ch, Cl = self.companions(C)
+            rc = self.lib.phc_gemm_tc5(Ah.data_ptr(), Al.data_ptr(), lda, 1 if a_k else 0, Bh.data_ptr(), Bl.data_ptr(), ldb,
+                                       1 if b_k else 0, C.data_ptr(), _ptr(Ch), _ptr(Cl), C.stride(0), M, N, K, alpha, _ptr(bias),
+                                       1 if relu else 0, _ptr(mask), mask.stride(0) if mask is not None else 0,
+                                       1 if accumulate else 0, k_splits, _stream())
+            if rc:
+                _lib.check(rc, "phc_gemm_tc5")
+            return (Ch, Cl) if Ch is not None else None
         rc = self.lib.phc_gemm(A.data_ptr(), lda, 1 if a_k else 0, B.data_ptr(), ldb, 1 if b_k else 0, C.data_ptr(),
                                C.stride(0), M, N, K, alpha, _ptr(bias), 1 if relu else 0, _ptr(mask),
                                mask.stride(0) if mask is not None else 0, 1 if accumulate else 0, k_splits, _stream())
@@ -184,30 +244,39 @@ class MLPEngine:
     # -- forward: x is [B, in_pad] (zero padded) -------------------------------------------------------------------
     def forward(self, st: MLPStack, x: torch.Tensor, ws: Dict[str, torch.Tensor]) -> torch.Tensor:
         net, B = self.net, x.shape[0]
-        cur = x
+        tc5 = self.backend == "tc5"
+        cur, cur_split = x, (self.split(x) if tc5 else None)
+        ws["x_split"] = cur_split
+        ws["h_split"] = []
         for l, h in zip(st.hidden, ws["h"]):
-            self.gemm(cur, True, net.weight(l), True, h, B, l.out_dim, l.in_dim, bias=net.bias(l), relu=True)
+            cur_split = self.gemm(cur, True, net.weight(l), True, h, B, l.out_dim, l.in_dim, bias=net.bias(l), relu=True,
+                                  a_split=cur_split, split_out=True)
+            ws["h_split"].append(cur_split)
             cur = h
         l = st.head
-        self.gemm(cur, True, net.weight(l), True, ws["out"], B, l.out_dim, l.in_dim, bias=net.bias(l))
+        self.gemm(cur, True, net.weight(l), True, ws["out"], B, l.out_dim, l.in_dim, bias=net.bias(l), a_split=cur_split)
         return ws["out"]
 
     # -- backward: ws["dout"] holds d(loss)/d(out) [B, round4(out)]; accumulates into net.grads --------------------
     def backward(self, st: MLPStack, x: torch.Tensor, ws: Dict[str, torch.Tensor], dx: Optional[torch.Tensor] = None) -> None:
         net, B = self.net, x.shape[0]
+        tc5 = self.backend == "tc5"
         acts = [x] + ws["h"]
+        act_splits = ([ws.get("x_split")] + list(ws.get("h_split", []))) if tc5 else [None] * len(acts)
         dcur = ws["dout"]
+        dsplit = self.split(dcur) if tc5 else None          # the loss kernels wrote dout: split it once for both GEMMs
         for li in range(len(st.layers) - 1, -1, -1):
             l = st.layers[li]
             a_in = acts[li]
             tiles = ((l.out_dim + 127) // 128) * ((l.in_dim + 127) // 128)
             # dW[out, in] += dY^T X
             self.gemm(dcur, False, a_in, False, net.weight(l, grad=True), l.out_dim, l.in_dim, B, accumulate=True,
-                      k_splits=_splits(tiles, B))
+                      k_splits=_splits(tiles, B), a_split=dsplit, b_split=act_splits[li])
             self.colsum(dcur, B, l.out_dim, net.bias(l, grad=True))
             if li > 0:
                 # dX = dY W, masked by the ReLU of the layer below
-                self.gemm(dcur, True, net.weight(l), False, ws["dh"][li - 1], B, l.in_dim, l.out_dim, mask=acts[li])
-                dcur = ws["dh"][li - 1]
+                nsplit = self.gemm(dcur, True, net.weight(l), False, ws["dh"][li - 1], B, l.in_dim, l.out_dim, mask=acts[li],
+                                   a_split=dsplit, split_out=True)
+                dcur, dsplit = ws["dh"][li - 1], nsplit
             elif dx is not None:
-                self.gemm(dcur, True, net.weight(l), False, dx, B, l.in_dim, l.out_dim)
+                self.gemm(dcur, True, net.weight(l), False, dx, B, l.in_dim, l.out_dim, a_split=dsplit)

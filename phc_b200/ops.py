@@ -184,7 +184,9 @@ class EnvStepPlan:
                  reset: Optional[torch.Tensor] = None, terminate: Optional[torch.Tensor] = None,
                  amp_obs_buf: Optional[torch.Tensor] = None, amp_hist_in: Optional[torch.Tensor] = None,
                  amp_shift: bool = True, with_amp: bool = True, with_ref_buffers: bool = False,
-                 only_where: Optional[torch.Tensor] = None, obs_only: bool = False):
+                 only_where: Optional[torch.Tensor] = None, obs_only: bool = False, amp_ring: bool = False):
+        """amp_ring=True: `amp_obs_buf` is a ring -- each run() writes only the newest vector into slot `ring_head`
+        (advance with advance_ring() before the step); otherwise the reference's window shift is done in the kernel."""
         lib = _lib.load()
         self._lib = lib
         self.cfg, self.mlib = cfg, mlib
@@ -227,8 +229,10 @@ class EnvStepPlan:
         if amp_hist_in is not None:
             amp_hist_in = _req(amp_hist_in, f32, "amp_hist_in", dev)
             assert amp_hist_in.shape == (N, S, self.amp_dim)
-        elif with_amp and amp_shift:
+        elif with_amp and amp_shift and not amp_ring:
             amp_hist_in = self.amp_obs_buf             # in-place shift, the reference's semantics
+        self.amp_ring = bool(amp_ring and with_amp)
+        self.ring_head = 0
         self.ref_body_pos = torch.zeros(N, J, 3, device=dev) if with_ref_buffers else None
         self.ref_body_rot = torch.zeros(N, J, 4, device=dev) if with_ref_buffers else None
         self.ref_body_vel = torch.zeros(N, J, 3, device=dev) if with_ref_buffers else None
@@ -276,6 +280,13 @@ class EnvStepPlan:
         self.args = a
         self._args_ref = C.byref(a)
 
+    def advance_ring(self) -> int:
+        """Move the ring head one slot back (the slot that will receive this step's AMP vector) and re-point amp_out."""
+        S = self.cfg.amp_steps
+        self.ring_head = (self.ring_head - 1) % S
+        self.args.amp_out = self.amp_obs_buf.data_ptr() + self.ring_head * self.amp_dim * 4
+        return self.ring_head
+
     def run(self, stream: Optional[int] = None) -> None:
         rc = self._lib.phc_env_step(self._args_ref, _stream() if stream is None else stream)
         if rc:
@@ -284,7 +295,7 @@ class EnvStepPlan:
 
 def amp_obs_demo(mlib: PackedMotionLib, cfg: EnvStepConfig, motion_ids: torch.Tensor, times0: torch.Tensor,
                  first_step: int = 0, num_steps: Optional[int] = None, out: Optional[torch.Tensor] = None,
-                 only_where: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 only_where: Optional[torch.Tensor] = None, slot_offset: int = 0) -> torch.Tensor:
     """build_amp_obs_demo (humanoid_amp.py:253-284; first_step=0) / _init_amp_obs_ref (:575-603; first_step=1)."""
     lib = _lib.load()
     dev = mlib.device
@@ -306,7 +317,18 @@ def amp_obs_demo(mlib: PackedMotionLib, cfg: EnvStepConfig, motion_ids: torch.Te
                                         cfg.flags(), C.cast(kb, C.c_void_p), len(cfg.key_bodies), aj.data_ptr(),
                                         len(joints), out.data_ptr(), out.stride(0),
                                         None if only_where is None else _req(only_where, torch.int64, "only_where", dev).data_ptr(),
-                                        _stream()), "phc_amp_obs_demo")
+                                        int(slot_offset), _stream()), "phc_amp_obs_demo")
+    return out
+
+
+def amp_window_export(ring: torch.Tensor, head: int, out: torch.Tensor) -> torch.Tensor:
+    """out[n, k, :] = ring[n, (head + k) % S, :] -- newest-first AMP window from the ring (phc_amp_window_export)."""
+    lib = _lib.load()
+    n, S, A = ring.shape
+    _req(ring, torch.float32, "ring")
+    assert out.dtype == torch.float32 and out.is_cuda and out.shape[0] == n and out.stride(-1) == 1 and out.numel() == n * S * A
+    _lib.check(lib.phc_amp_window_export(ring.data_ptr(), ring.stride(0), n, S, A, int(head), out.data_ptr(), out.stride(0), _stream()),
+               "phc_amp_window_export")
     return out
 
 

@@ -163,3 +163,27 @@ def test_motion_state_and_amp_demo_vs_golden():
     hist = ops.amp_obs_demo(mlib2, smpl_cfg(), e["demo_ids"].to(DEV), e["demo_t0"].to(DEV), first_step=1, num_steps=9)
     exp = O.amp_obs_demo(oracle_tables(motion_data_from(e)), smpl_step_config(), e["demo_ids"], e["demo_t0"], 1, 9)
     close(hist.cpu(), exp, rtol=1e-4, atol=2e-5, what="amp history init")
+
+
+def test_amp_ring_equals_reference_window_shift():
+    """The AMP ring (one slot written per step + export) reproduces the reference's per-step window shift."""
+    n = 70
+    m = syn.make_motions(n, seed=21, min_frames=60, max_frames=90)
+    st = syn.make_env_state(m, n, seed=21, max_progress=10)
+    mlib = pack(m)
+    s = st.to(DEV)
+    common = (mlib, s.body_state, s.dof_state, s.dof_force, s.progress, s.motion_ids, s.start_times, s.start_offsets, s.global_offset)
+    shift = ops.EnvStepPlan(smpl_cfg(), *common, amp_obs_buf=s.amp_hist.clone())
+    ring = ops.EnvStepPlan(smpl_cfg(), *common, amp_obs_buf=s.amp_hist.clone(), amp_ring=True)
+    window = torch.zeros_like(ring.amp_obs_buf)
+    for step in range(13):                                 # more than one full revolution of the 10-slot ring
+        s.body_state.add_(0.01 * torch.randn_like(s.body_state))
+        s.body_state[..., 3:7] = torch.nn.functional.normalize(s.body_state[..., 3:7], dim=-1)
+        s.progress.add_(1)
+        shift.run()
+        ring.advance_ring()
+        ring.run()
+        ops.amp_window_export(ring.amp_obs_buf, ring.ring_head, window)
+        torch.cuda.synchronize()
+        assert torch.equal(window, shift.amp_obs_buf), f"step {step}"
+        assert torch.equal(ring.obs, shift.obs) and torch.equal(ring.rew, shift.rew)

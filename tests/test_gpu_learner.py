@@ -127,6 +127,26 @@ def _rand_batch(B, Bd, obs, act, amp, seed, mu_fn=None):
                 amp_agent=torch.clamp(r(Bd, amp), -5, 5), amp_replay=torch.clamp(r(Bd, amp), -5, 5), amp_demo=torch.clamp(r(Bd, amp), -5, 5))
 
 
+def make_lattice(net, seed=0):
+    """Put the HIDDEN layers of all three MLPs on a dyadic lattice (weights in {-1,0,1}/8, biases an odd multiple of half the
+    pre-activation granularity) so that, with inputs that are multiples of 1/4, every hidden pre-activation is computed
+    EXACTLY by any arithmetic (fp64, fp32, 3xTF32) and is never zero: the ReLU masks are then identical on both sides and
+    every remaining gradient difference is arithmetic error, not a flipped borderline unit (16.7 M pre-activations per
+    minibatch otherwise contain a few |z| < 1e-6 whose mask legitimately differs between fp64 and fp32-class math)."""
+    g = torch.Generator().manual_seed(seed)
+    for st in (net.actor, net.critic, net.disc):
+        gran = 1.0 / 4
+        for l in st.hidden:
+            w = torch.randint(-1, 2, (l.out_dim, l.in_dim), generator=g).float() / 8
+            gran = gran / 8
+            b = (torch.randint(0, 2, (l.out_dim,), generator=g).float() * 2 - 1) * gran / 2
+            net.set_layer(l, w, b)
+
+
+def lattice_inputs(t):
+    return torch.round(t * 4) / 4
+
+
 CFG = dict(e_clip=0.2, critic_coef=5.0, entropy_coef=0.0, bounds_loss_coef=10.0, disc_coef=5.0, disc_logit_reg=0.01,
            disc_grad_penalty=5.0, disc_weight_decay=0.0001, grad_norm=50.0, learning_rate=2e-5, truncate_grads=True)
 
@@ -137,11 +157,14 @@ def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units):
     """forward values, every parameter gradient, the clipped Adam step: CUDA engine vs torch autograd on the CPU."""
     from tests.learner_harness import run_cuda_minibatch
     net = AMPNetwork(obs, act, amp, units, units, device=DEV, seed=3)
-    net.weight(net.actor.head).mul_(6.0)          # |mu| reaches past the +-1 soft bound: bound loss active
+    make_lattice(net, seed=B)
+    net.weight(net.actor.head).mul_(0.5)          # |mu| straddles the +-1 soft bound: bound loss active on part of the batch
     sd = {k: v.cpu() for k, v in net.state_dict().items()}
     aw, ab = PO.stack_params(sd, "actor_mlp", "mu", len(units))
     mu_fn = lambda x: O.mlp_forward(x.double(), [w.double() for w in aw], [b.double() for b in ab])
-    batch = _rand_batch(B, Bd, obs, act, amp, seed=B, mu_fn=mu_fn)
+    batch = _rand_batch(B, Bd, obs, act, amp, seed=B, mu_fn=lambda x: mu_fn(lattice_inputs(x)))
+    for k in ("obs_n", "amp_agent", "amp_replay", "amp_demo"):
+        batch[k] = lattice_inputs(batch[k])
     exp = PO.minibatch_update(sd, batch, CFG, n_hidden=len(units), dtype=torch.float64)      # near-exact reference
     got = run_cuda_minibatch(net, batch, CFG)
 
