@@ -286,8 +286,8 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     if (lane == 0) {
       if (has_h) s_amp[0] = root_p.z;
       st6(o, tan_norm((a.flags & PHC_FLAG_LOCAL_ROOT_OBS) ? qmul(hinv, root_q) : root_q));
-      st3(o + 6, qrot(hinv, sim.v));      // lane 0 holds body 0 = the root
-      st3(o + 9, qrot(hinv, sim.w));
+      st3(o + 6, qrot_z(hinv, sim.v));      // lane 0 holds body 0 = the root
+      st3(o + 9, qrot_z(hinv, sim.w));
     }
     for (int k = lane; k < nj; k += 32) {
       const int jid = a.amp_joints[k];
@@ -297,7 +297,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     }
     if (lane < nk) {
       const float* kb = s_state + a.key_bodies[lane] * kBodyRec;
-      st3(o + 12 + 9 * nj + 3 * lane, qrot(hinv, v3(kb[0], kb[1], kb[2]) - root_p));
+      st3(o + 12 + 9 * nj + 3 * lane, qrot_z(hinv, v3(kb[0], kb[1], kb[2]) - root_p));
     }
   }
   __syncwarp();   // the reward slots and the simulator block are consumed: the obs row may overwrite them
@@ -310,12 +310,12 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     float* o_rot = o_pos + 3 * (J - 1);
     float* o_vel = o_rot + 6 * J;
     float* o_ang = o_vel + 3 * J;
-    if (j > 0) st3(o_pos + 3 * (j - 1), qrot(hinv, sim.p - root_p));
+    if (j > 0) st3(o_pos + 3 * (j - 1), qrot_z(hinv, sim.p - root_p));
     TanNorm tn = tan_norm(qmul(hinv, sim.q));
     if (j == 0 && !(a.flags & PHC_FLAG_LOCAL_ROOT_OBS)) tn = tan_norm(root_q);
     st6(o_rot + 6 * j, tn);
-    st3(o_vel + 3 * j, qrot(hinv, sim.v));
-    st3(o_ang + 3 * j, qrot(hinv, sim.w));
+    st3(o_vel + 3 * j, qrot_z(hinv, sim.v));
+    st3(o_ang + 3 * j, qrot_z(hinv, sim.w));
   }
   // task observation v6 for each of the T reference samples
 #pragma unroll
@@ -323,11 +323,11 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     if (t < T && has_body) {
       const BodyRec ref = blend_body(po0[t] + j * kBodyRec, po1[t] + j * kBodyRec, bl_o[t], goff);
       float* tb = s_obs + self_dim + t * 24 * J;
-      st3(tb + 3 * j, qrot(hinv, ref.p - sim.p));
+      st3(tb + 3 * j, qrot_z(hinv, ref.p - sim.p));
       st6(tb + 3 * J + 6 * j, tan_norm(qmul(qmul(hinv, qmul(ref.q, qconj(sim.q))), hq)));
-      st3(tb + 9 * J + 3 * j, qrot(hinv, ref.v - sim.v));
-      st3(tb + 12 * J + 3 * j, qrot(hinv, ref.w - sim.w));
-      st3(tb + 15 * J + 3 * j, qrot(hinv, ref.p - root_p));
+      st3(tb + 9 * J + 3 * j, qrot_z(hinv, ref.v - sim.v));
+      st3(tb + 12 * J + 3 * j, qrot_z(hinv, ref.w - sim.w));
+      st3(tb + 15 * J + 3 * j, qrot_z(hinv, ref.p - root_p));
       st6(tb + 18 * J + 6 * j, tan_norm(qmul(hinv, ref.q)));
       if (t == 0) {     // side buffers of _compute_task_obs(save_buffer=True)
         const size_t bj = (size_t)env * J + j;

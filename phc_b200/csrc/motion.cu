@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(128) amp_demo_kernel(const __grid_constant__ A
     if (has_h) o[-1] = r.p.z;
     const TanNorm tn = tan_norm((a.flags & PHC_FLAG_LOCAL_ROOT_OBS) ? qmul(hinv, root_q) : root_q);
     st3g(o, tn.t); st3g(o + 3, tn.n);
-    st3g(o + 6, qrot(hinv, r.v));
-    st3g(o + 9, qrot(hinv, r.w));
+    st3g(o + 6, qrot_z(hinv, r.v));
+    st3g(o + 9, qrot_z(hinv, r.w));
   } else {
     for (int kk = 0; kk < nj; ++kk)
       if (a.amp_joints[kk] == lane - 1) {
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(128) amp_demo_kernel(const __grid_constant__ A
       }
   }
   for (int kk = 0; kk < nk; ++kk)
-    if (a.key_bodies[kk] == lane) st3g(o + 12 + 9 * nj + 3 * kk, qrot(hinv, s.body.p - r.p));
+    if (a.key_bodies[kk] == lane) st3g(o + 12 + 9 * nj + 3 * kk, qrot_z(hinv, s.body.p - r.p));
 }
 
 // Reset path: write the reference pose at (id, time) of every env with mask != 0 into the simulator tensors

@@ -67,8 +67,10 @@ PHC_HD V3 qrot(Q4 q, V3 v) {
 
 // heading = atan2 of the rotated x axis; quat_from_angle_axis(+-heading, z) incl. its final re-normalisation
 PHC_HD float heading_angle(Q4 q) {
-  const V3 d = qrot(q, v3(1.0f, 0.0f, 0.0f));
-  return atan2f(d.y, d.x);
+  const float s = 2.0f * (q.w * q.w) - 1.0f;            // x and y of qrot(q, (1,0,0)), zero terms folded
+  const float dx = s + q.x * q.x * 2.0f;
+  const float dy = q.z * q.w * 2.0f + q.y * q.x * 2.0f;
+  return atan2f(dy, dx);
 }
 
 PHC_HD Q4 quat_about_z(float angle) {
@@ -79,11 +81,32 @@ PHC_HD Q4 quat_about_z(float angle) {
   return q4(0.0f, 0.0f, s / n, c / n);
 }
 
+// qrot(h, v) for a quaternion about z (h.x == h.y == 0: the heading quaternions).  Every product with an exact zero and
+// every "+ 0" of the general expression is dropped; for finite inputs the result is bit-identical to qrot (only the
+// sign of a zero result can differ), at half the instructions.  The compiler may not do this itself under IEEE rules.
+PHC_HD V3 qrot_z(Q4 h, V3 v) {
+  const float s = 2.0f * (h.w * h.w) - 1.0f;
+  const float cx = -(h.z * v.y);
+  const float cy = h.z * v.x;
+  const float d = h.z * v.z;
+  V3 r;
+  r.x = v.x * s + cx * h.w * 2.0f;
+  r.y = v.y * s + cy * h.w * 2.0f;
+  r.z = v.z * s + h.z * d * 2.0f;
+  return r;
+}
+
+// quat_to_tan_norm: q * (1,0,0) and q * (0,0,1) with the same zero-folding (bit-identical to two general qrot calls)
 struct TanNorm { V3 t, n; };
 PHC_HD TanNorm tan_norm(Q4 q) {
+  const float s = 2.0f * (q.w * q.w) - 1.0f;
   TanNorm r;
-  r.t = qrot(q, v3(1.0f, 0.0f, 0.0f));
-  r.n = qrot(q, v3(0.0f, 0.0f, 1.0f));
+  r.t.x = s + q.x * q.x * 2.0f;
+  r.t.y = q.z * q.w * 2.0f + q.y * q.x * 2.0f;
+  r.t.z = -(q.y * q.w) * 2.0f + q.z * q.x * 2.0f;
+  r.n.x = q.y * q.w * 2.0f + q.x * q.z * 2.0f;
+  r.n.y = -(q.x * q.w) * 2.0f + q.y * q.z * 2.0f;
+  r.n.z = s + q.z * q.z * 2.0f;
   return r;
 }
 
