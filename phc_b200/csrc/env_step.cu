@@ -113,7 +113,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
 
   // reward / reset use the CURRENT motion time (humanoid_im.py:879), observations the NEXT one (:752)
   const float t_now = (float)progress * a.dt + t_start + t_off;
-  const Bracket br_r = frame_bracket(t_now, m_len, m_nf, m_dt);
+  const Bracket32 br_r = frame_bracket32(t_now, m_len, (int)m_nf, m_dt);
   float bl_o[T_MAX];
   const float* po0[T_MAX];     // shared-memory address of frame i0 / i1 of observation sample t
   const float* po1[T_MAX];
@@ -136,7 +136,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
         float tn = (float)(progress + 1) * a.dt;
         if (T > 1) tn = tn + (float)t * a.traj_dt;
         tn = tn + t_start + t_off;
-        const Bracket b = frame_bracket(tn, m_len, m_nf, m_dt);
+        const Bracket32 b = frame_bracket32(tn, m_len, (int)m_nf, m_dt);
         bl_o[t] = b.blend;
         rows_o[2 * t] = m_start + b.i0;
         rows_o[2 * t + 1] = m_start + b.i1;
@@ -214,8 +214,8 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   Q4 root_q = q4(s_state[3], s_state[4], s_state[5], s_state[6]);
   if (!(a.flags & PHC_FLAG_UPRIGHT)) root_q = strip_base_rot(root_q);
   const float heading = heading_angle(root_q);
-  const Q4 hinv = quat_about_z(-heading);
   const Q4 hq = quat_about_z(heading);
+  const Q4 hinv = q4(0.0f, 0.0f, -hq.z, hq.w);     // quat_about_z(-heading): sin is odd, cos even -> the exact conjugate
 
   // reward + termination against the reference pose at t_now
   float e_pos = 0.f, e_rot = 0.f, e_vel = 0.f, e_ang = 0.f, dist = 0.f;

@@ -73,9 +73,18 @@ PHC_HD float heading_angle(Q4 q) {
   return atan2f(dy, dx);
 }
 
+PHC_HD void sin_cos(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+  sincosf(x, s, c);          // one shared range reduction, same 2-ulp accuracy class as sinf / cosf
+#else
+  *s = sinf(x); *c = cosf(x);
+#endif
+}
+
 PHC_HD Q4 quat_about_z(float angle) {
   const float th = angle / 2.0f;
-  const float s = sinf(th), c = cosf(th);
+  float s, c;
+  sin_cos(th, &s, &c);
   float n = sqrtf(s * s + c * c);
   n = n < 1e-9f ? 1e-9f : n;
   return q4(0.0f, 0.0f, s / n, c / n);
@@ -112,10 +121,16 @@ PHC_HD TanNorm tan_norm(Q4 q) {
 
 PHC_HD float wrap_angle(float x) { return atan2f(sinf(x), cosf(x)); }
 
+// normalize_angle for an argument already known to lie in [0, 2*pi]: atan2(sin x, cos x) = x (x <= pi) or x - 2*pi.
+// Used on the per-step path (2*acos(w) and joint angles), where it replaces sinf + cosf + atan2f (~100 instructions per
+// lane) by one compare; it agrees with wrap_angle to fp32 rounding of the result (the reference's own atan2(sin, cos)
+// carries the same ~1e-7 relative rounding).
+PHC_HD float wrap_angle_0_2pi(float x) { return x > 3.14159265358979323846f ? x - 6.28318530717958647692f : x; }
+
 // quat_to_angle_axis: angle only (what the tracking reward reads) ...
 PHC_HD float quat_angle(Q4 q) {
   const float s = sqrtf(1.0f - q.w * q.w);
-  const float ang = wrap_angle(2.0f * acosf(q.w));
+  const float ang = wrap_angle_0_2pi(2.0f * acosf(q.w));
   return (fabsf(s) > 1e-5f) ? ang : 0.0f;        // NaN (|w|>1) compares false -> 0, like torch.where(mask, ...)
 }
 
@@ -131,12 +146,13 @@ PHC_HD V3 quat_to_exp_map(Q4 q) {
 PHC_HD Q4 exp_map_to_quat(V3 e) {
   const float n0 = sqrtf(e.x * e.x + e.y * e.y + e.z * e.z);
   V3 ax = v3(e.x / n0, e.y / n0, e.z / n0);
-  float ang = wrap_angle(n0);
+  float ang = (n0 <= 6.28318530717958647692f) ? wrap_angle_0_2pi(n0) : wrap_angle(n0);   // joint angles are < 2*pi
   if (!(fabsf(ang) > 1e-5f)) { ang = 0.0f; ax = v3(0.0f, 0.0f, 1.0f); }
   float an = sqrtf(ax.x * ax.x + ax.y * ax.y + ax.z * ax.z);
   an = an < 1e-9f ? 1e-9f : an;
   const float th = ang / 2.0f;
-  const float s = sinf(th), c = cosf(th);
+  float s, c;
+  sin_cos(th, &s, &c);
   const float x = (ax.x / an) * s, y = (ax.y / an) * s, z = (ax.z / an) * s;
   float qn = sqrtf(x * x + y * y + z * z + c * c);
   qn = qn < 1e-9f ? 1e-9f : qn;
@@ -168,6 +184,21 @@ PHC_HD Bracket frame_bracket(float time, float len, int64_t nf, float dt) {
   if (time < 0.0f) time = 0.0f;
   Bracket b;
   b.i0 = (int64_t)(phase * (float)(nf - 1));
+  b.i1 = (b.i0 + 1 < nf - 1) ? b.i0 + 1 : nf - 1;
+  float bl = (time - (float)b.i0 * dt) / dt;
+  b.blend = fminf(fmaxf(bl, 0.0f), 1.0f);
+  return b;
+}
+
+// Same bracket with 32-bit frame indices (every clip has far fewer than 2^31 frames): avoids the emulated 64-bit
+// float<->int conversions on the per-step path.  Identical results.
+struct Bracket32 { int i0, i1; float blend; };
+PHC_HD Bracket32 frame_bracket32(float time, float len, int nf, float dt) {
+  float phase = time / len;
+  phase = fminf(fmaxf(phase, 0.0f), 1.0f);
+  if (time < 0.0f) time = 0.0f;
+  Bracket32 b;
+  b.i0 = (int)(phase * (float)(nf - 1));
   b.i1 = (b.i0 + 1 < nf - 1) ? b.i0 + 1 : nf - 1;
   float bl = (time - (float)b.i0 * dt) / dt;
   b.blend = fminf(fmaxf(bl, 0.0f), 1.0f);

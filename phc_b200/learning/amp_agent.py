@@ -645,6 +645,8 @@ class AMPAgent:
 
     def set_full_state_weights(self, weights: Dict) -> None:
         self.model.load_state_dict(weights["model"])
+        if self.engine.backend == "tc5":
+            self.model.refresh_split()
         self.epoch_num = weights.get("epoch", 0)
         self.frame = weights.get("frame", 0)
         opt = weights.get("optimizer")

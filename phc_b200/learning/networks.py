@@ -164,8 +164,9 @@ class MLPEngine:
         self.lib = _lib.load()
         self.dev = net.device
         self._ws: Dict[Tuple[str, int], Dict[str, torch.Tensor]] = {}
-        # "mma": warp-level mma.sync 3xTF32 (gemm.cu); "tc5": tcgen05 / TMEM / TMA 3xTF32 (gemm_tc5.cu)
-        self.backend = backend or os.environ.get("PHC_GEMM", "mma")
+        # "tc5" (default): tcgen05 / TMEM / TMA 3xTF32 (gemm_tc5.cu); "mma": warp-level mma.sync 3xTF32 (gemm.cu), kept as
+        # the cross-check implementation (PHC_GEMM=mma)
+        self.backend = backend or os.environ.get("PHC_GEMM", "tc5")
         assert self.backend in ("mma", "tc5")
         self._companions: Dict[Tuple[int, Tuple[int, ...], Tuple[int, ...]], Tuple[torch.Tensor, torch.Tensor]] = {}
         if self.backend == "tc5":

@@ -6,11 +6,11 @@ from phc_b200 import _lib
 from phc_b200.learning.networks import MLPEngine, round4, _splits
 
 
-def run_cuda_minibatch(net, batch, cfg):
+def run_cuda_minibatch(net, batch, cfg, backend=None):
     from phc_b200.learning.amp_agent import AMPAgent
     dev = net.device
     lib = _lib.load()
-    eng = MLPEngine(net)
+    eng = MLPEngine(net, backend=backend)
     B, Bd, A = batch["obs_n"].shape[0], batch["amp_agent"].shape[0], net.action_dim
     z = lambda *s: torch.zeros(*s, device=dev)
     x = z(B, round4(net.obs_dim)); x[:, :net.obs_dim] = batch["obs_n"].to(dev)

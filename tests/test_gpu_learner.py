@@ -43,7 +43,7 @@ def test_gemm_forward_form(M, N, K):
     g = torch.Generator().manual_seed(M + N + K)
     A, B, bias = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / math.sqrt(K), torch.randn(N, generator=g)
     net = AMPNetwork(8, 2, 8, (4,), (4,), device=DEV)
-    eng = MLPEngine(net)
+    eng = MLPEngine(net, backend="mma")           # the tcgen05 kernel has its own file (test_gpu_gemm_tc5.py)
     Ap, Bp = padded(A), padded(B)
     C = torch.zeros(M, round4(N), device=DEV)
     eng.gemm(Ap, True, Bp, True, C, M, N, K, bias=bias.to(DEV), relu=True)
@@ -56,7 +56,7 @@ def test_gemm_forward_form(M, N, K):
 def test_gemm_input_grad_form(M, N, K):
     g = torch.Generator().manual_seed(1)
     dY, W, H = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g) / math.sqrt(K), torch.randn(M, N, generator=g)
-    eng = MLPEngine(AMPNetwork(8, 2, 8, (4,), (4,), device=DEV))
+    eng = MLPEngine(AMPNetwork(8, 2, 8, (4,), (4,), device=DEV), backend="mma")
     C = torch.zeros(M, round4(N), device=DEV)
     eng.gemm(padded(dY), True, padded(W), False, C, M, N, K, mask=padded(H))
     gemm_close(C[:, :N], dY, W.T.contiguous(), "gemm dX", extra=lambda e, b: (e * (H > 0), b))
@@ -66,7 +66,7 @@ def test_gemm_input_grad_form(M, N, K):
 def test_gemm_weight_grad_form(M, N, K, splits):
     g = torch.Generator().manual_seed(2)
     dY, X = torch.randn(K, M, generator=g), torch.randn(K, N, generator=g)
-    eng = MLPEngine(AMPNetwork(8, 2, 8, (4,), (4,), device=DEV))
+    eng = MLPEngine(AMPNetwork(8, 2, 8, (4,), (4,), device=DEV), backend="mma")
     C = torch.ones(M, round4(N), device=DEV)            # accumulates on top of existing content
     eng.gemm(padded(dY), False, padded(X), False, C, M, N, K, alpha=0.5, accumulate=True, k_splits=splits)
     gemm_close(C[:, :N], dY.T.contiguous(), X.T.contiguous(), "gemm dW", extra=lambda e, b: (1.0 + 0.5 * e, 1.0 + 0.5 * b))
@@ -119,7 +119,7 @@ def _rand_batch(B, Bd, obs, act, amp, seed, mu_fn=None):
     logstd = torch.full((act,), -2.9)
     obs_n = torch.clamp(r(B, obs) * 1.5, -5, 5)
     old_sigma = torch.exp(logstd).expand(B, act).clone()
-    old_mu = r(B, act) * 0.8 if mu_fn is None else (mu_fn(obs_n) + 0.3 * old_sigma * r(B, act)).float()
+    old_mu = r(B, act) * 0.8 if mu_fn is None else (mu_fn(obs_n) + 0.03 * old_sigma * r(B, act)).float()
     actions = old_mu + old_sigma * r(B, act)
     old_nlp = O.gaussian_neglogp(actions, old_mu, old_sigma, logstd.expand(B, act))
     return dict(obs_n=obs_n, actions=actions, old_neglogp=old_nlp + 0.05 * r(B),
@@ -151,9 +151,10 @@ CFG = dict(e_clip=0.2, critic_coef=5.0, entropy_coef=0.0, bounds_loss_coef=10.0,
            disc_grad_penalty=5.0, disc_weight_decay=0.0001, grad_norm=50.0, learning_rate=2e-5, truncate_grads=True)
 
 
+@pytest.mark.parametrize("backend", ["tc5", "mma"])
 @pytest.mark.parametrize("B,Bd,obs,act,amp,units", [(512, 128, 934, 69, 1960, (256, 128)), (16384, 4096, 934, 69, 1960, (1024, 512)),
                                                      (300, 100, 50, 7, 30, (64, 32))])
-def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units):
+def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units, backend):
     """forward values, every parameter gradient, the clipped Adam step: CUDA engine vs torch autograd on the CPU."""
     from tests.learner_harness import run_cuda_minibatch
     net = AMPNetwork(obs, act, amp, units, units, device=DEV, seed=3)
@@ -166,7 +167,7 @@ def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units):
     for k in ("obs_n", "amp_agent", "amp_replay", "amp_demo"):
         batch[k] = lattice_inputs(batch[k])
     exp = PO.minibatch_update(sd, batch, CFG, n_hidden=len(units), dtype=torch.float64)      # near-exact reference
-    got = run_cuda_minibatch(net, batch, CFG)
+    got = run_cuda_minibatch(net, batch, CFG, backend=backend)
 
     def scaled(a, b, tol, what):       # error relative to the tensor's scale (entries are sums of large cancelling terms)
         err = float((a.double().cpu() - b.double()).abs().max())
@@ -183,7 +184,7 @@ def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units):
     close(torch.tensor(s["kl"]), f32(exp["kl"]), rtol=1e-3, atol=1e-4, what="kl")
     close(torch.tensor(s["disc_grad_penalty"]), f32(exp["disc"]["disc_grad_penalty"]), rtol=1e-4, atol=1e-6, what="grad penalty")
     close(torch.tensor(s["disc_agent_acc"]), f32(exp["disc"]["disc_agent_acc"]), atol=2e-3, what="disc agent acc")
-    assert 0.02 < s["actor_clip_frac"] < 0.98 and s["b_loss"] > 0, "test batch must exercise both PPO branches and the bound loss"
+    assert 0.02 < s["actor_clip_frac"] < 0.98 and s["b_loss"] > 0, f"test batch must exercise both PPO branches and the bound loss: {s}"
     gsd = got["grads"]
     for k, ge in exp["grads"].items():
         scaled(gsd[k], ge, 1e-4, f"grad {k}")
