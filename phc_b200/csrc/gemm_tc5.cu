@@ -5,6 +5,12 @@
 // (phc_split_tf32: x -> hi = rna_tf32(x), lo = rna_tf32(x - hi)) because UMMA reads its operands straight from shared
 // memory; per k-step the issuing thread launches D += A_lo*B_hi, D += A_hi*B_lo, D += A_hi*B_hi (small terms first).
 //
+// Two tile configurations share the code (template parameter CTAS):
+//   CTAS = 1: 128 x 128 tile per CTA (small / skinny problems);
+//   CTAS = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) computes a 256 x 256 tile: each CTA stages its own 128 rows
+//             of A and its own 128 of the 256 B rows (same 64 KB per stage), the leader CTA issues M = 256, N = 256 MMAs
+//             that read both CTAs' shared memory, each CTA keeps its 128 x 256 accumulator half in its own TMEM.
+//             Twice the flops per byte fetched from L2 -- the 128 x 128 tile is L2-bandwidth bound at ~50 % of the MMA rate.
 // CTA = 192 threads: warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer, warp 5 TMEM owner + MMA
 // issuer.  Tile 128 x 128, BLOCK_K = 32 floats (one 128-byte swizzle atom), 3 pipeline stages x 4 operand tiles x 16 KB.
 // Shared-memory operand layouts (what the descriptors encode, cf. cute/atom/mma_traits_sm100.hpp make_umma_desc):
@@ -18,6 +24,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/phc_b200.h"
 
@@ -92,6 +99,40 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- cta_group::2 (CTA pair) variants ----
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> the even (leader) CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_leader(uint64_t* b) {     // arrive (no tx) on the leader CTA's copy of barrier b
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(s32(b) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  // data lands in THIS CTA's shared memory, the transaction bytes are credited to the LEADER's barrier
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(s32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(s32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {              // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(s32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+
 // 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, LBO, SBO in 16-byte units,
 // version = 1 (bit 46), layout type in bits 61-63: SWIZZLE_128B = 2 (k-contiguous), SWIZZLE_128B_BASE32B = 1
 // (mn-contiguous 32-bit operands).
@@ -106,12 +147,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, major-ness bits, N >> 3, M >> 4
-__host__ __device__ constexpr uint32_t instr_desc(bool a_mn, bool b_mn) {
+__host__ __device__ constexpr uint32_t instr_desc(bool a_mn, bool b_mn, int mma_m, int mma_n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+         ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(mma_m >> 4) << 24);
 }
 
-template <bool A_K, bool B_K>
+template <bool A_K, bool B_K, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -124,7 +165,13 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  constexpr int TN = BN * CTAS;                            // accumulator columns per CTA (= MMA N)
+  const uint32_t rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  // CTAS == 2: blockIdx.x enumerates the CTAs of the pairs along M; both CTAs of a pair share the 256-column N range
+  const int m0 = (CTAS == 2) ? ((int)(blockIdx.x >> 1) * 2 * BM + (int)rank * BM) : (int)blockIdx.y * BM;
+  const int n0 = (CTAS == 2) ? (int)blockIdx.y * TN : (int)blockIdx.x * BN;
+  const int nb0 = n0 + (int)rank * BN;                     // first B row this CTA stages
   const int kb_total = (g.K + BK - 1) / BK;
   const int kb_per = (kb_total + g.k_splits - 1) / g.k_splits;
   const int kb_begin = blockIdx.z * kb_per;
@@ -133,14 +180,16 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   if (nkb <= 0) return;                                   // uniform per CTA
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    // full barrier: the pair's two producers arrive (the leader's arrival carries the byte count of both CTAs)
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, CTAS); mbar_init(empty_bar + s, 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 5) tmem_alloc(tmem_slot, BN);               // whole warp, .sync.aligned
+  if (warp == 5) { if (CTAS == 2) tmem_alloc_2cta(tmem_slot, TN); else tmem_alloc(tmem_slot, TN); }   // whole warp, .sync.aligned
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();                       // peer barriers initialised, both TMEM halves allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -152,33 +201,38 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         if (i >= STAGES) mbar_wait(empty_bar + s, ((i / STAGES) - 1) & 1);
         uint8_t* st = smem + s * STAGE_BYTES;
         const int k0 = (kb_begin + i) * BK;
-        mbar_expect_tx(full_bar + s, STAGE_BYTES);
+        if (leader) mbar_expect_tx(full_bar + s, CTAS * STAGE_BYTES);
+        else mbar_arrive_remote_leader(full_bar + s);
+        auto ld = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
+          if (CTAS == 2) tma_load_2d_2cta(dst, tm, full_bar + s, c0, c1);
+          else tma_load_2d(dst, tm, full_bar + s, c0, c1);
+        };
         if (A_K) {
-          tma_load_2d(st, &tmAh, full_bar + s, k0, m0);
-          tma_load_2d(st + TILE_BYTES, &tmAl, full_bar + s, k0, m0);
+          ld(st, &tmAh, k0, m0);
+          ld(st + TILE_BYTES, &tmAl, k0, m0);
         } else {
 #pragma unroll
           for (int j = 0; j < BM / 32; ++j) {
-            tma_load_2d(st + j * 4096, &tmAh, full_bar + s, m0 + 32 * j, k0);
-            tma_load_2d(st + TILE_BYTES + j * 4096, &tmAl, full_bar + s, m0 + 32 * j, k0);
+            ld(st + j * 4096, &tmAh, m0 + 32 * j, k0);
+            ld(st + TILE_BYTES + j * 4096, &tmAl, m0 + 32 * j, k0);
           }
         }
         if (B_K) {
-          tma_load_2d(st + 2 * TILE_BYTES, &tmBh, full_bar + s, k0, n0);
-          tma_load_2d(st + 3 * TILE_BYTES, &tmBl, full_bar + s, k0, n0);
+          ld(st + 2 * TILE_BYTES, &tmBh, k0, nb0);
+          ld(st + 3 * TILE_BYTES, &tmBl, k0, nb0);
         } else {
 #pragma unroll
           for (int j = 0; j < BN / 32; ++j) {
-            tma_load_2d(st + 2 * TILE_BYTES + j * 4096, &tmBh, full_bar + s, n0 + 32 * j, k0);
-            tma_load_2d(st + 3 * TILE_BYTES + j * 4096, &tmBl, full_bar + s, n0 + 32 * j, k0);
+            ld(st + 2 * TILE_BYTES + j * 4096, &tmBh, nb0 + 32 * j, k0);
+            ld(st + 3 * TILE_BYTES + j * 4096, &tmBl, nb0 + 32 * j, k0);
           }
         }
       }
     }
   } else if (warp == 5) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc(!A_K, !B_K);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = instr_desc(!A_K, !B_K, BM * CTAS, TN);
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
         mbar_wait(full_bar + s, (i / STAGES) & 1);
@@ -195,13 +249,19 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           const uint64_t dAl = smem_desc(st + TILE_BYTES + a_off, a_lbo, a_sbo, a_lt);
           const uint64_t dBh = smem_desc(st + 2 * TILE_BYTES + b_off, b_lbo, b_sbo, b_lt);
           const uint64_t dBl = smem_desc(st + 3 * TILE_BYTES + b_off, b_lbo, b_sbo, b_lt);
-          umma_tf32(tmem_base, dAl, dBh, idesc, (i > 0 || kk > 0) ? 1u : 0u);
-          umma_tf32(tmem_base, dAh, dBl, idesc, 1u);
-          umma_tf32(tmem_base, dAh, dBh, idesc, 1u);
+          if (CTAS == 2) {
+            umma_tf32_2cta(tmem_base, dAl, dBh, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+            umma_tf32_2cta(tmem_base, dAh, dBl, idesc, 1u);
+            umma_tf32_2cta(tmem_base, dAh, dBh, idesc, 1u);
+          } else {
+            umma_tf32(tmem_base, dAl, dBh, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+            umma_tf32(tmem_base, dAh, dBl, idesc, 1u);
+            umma_tf32(tmem_base, dAh, dBh, idesc, 1u);
+          }
         }
-        umma_commit(empty_bar + s);                       // frees the stage when these MMAs retire
+        if (CTAS == 2) umma_commit_2cta(empty_bar + s); else umma_commit(empty_bar + s);   // frees the stage (in both CTAs)
       }
-      umma_commit(tmem_full);                             // accumulator complete
+      if (CTAS == 2) umma_commit_2cta(tmem_full); else umma_commit(tmem_full);             // accumulator complete
     }
   } else {
     // ===================== epilogue warps 0..3: TMEM -> registers -> global =====================
@@ -210,29 +270,64 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     const int row = warp * 32 + lane;
     const int m = m0 + row;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = 0; c0 < TN; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
       if (m < g.M) {
+        float* crow = g.C + (int64_t)m * g.ldc;
+        const float* mrow = g.mask ? g.mask + (int64_t)m * g.ldmask : nullptr;
+        // 16-byte vector path when the row segment is aligned and fully inside the matrix (always for interior tiles)
+        const bool vec = !g.accumulate && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
+                         (!mrow || (((g.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0)));
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 32; j += 4) {
           const int n = n0 + c0 + j;
-          if (n < g.N) {
-            float v = g.alpha * __uint_as_float(r[j]);
-            if (g.bias && blockIdx.z == 0) v += g.bias[n];
-            if (g.relu) v = fmaxf(v, 0.f);
-            if (g.mask) v = (g.mask[(int64_t)m * g.ldmask + n] > 0.f) ? v : 0.f;
-            float* dst = g.C + (int64_t)m * g.ldc + n;
-            if (g.accumulate) atomicAdd(dst, v);
-            else {
-              *dst = v;
-              if (g.C_hi) {
+          if (n >= g.N) break;
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = g.alpha * __uint_as_float(r[j + e]);
+            if (g.bias && blockIdx.z == 0 && n + e < g.N) x += g.bias[n + e];
+            if (g.relu) x = fmaxf(x, 0.f);
+            v[e] = x;
+          }
+          if (vec && n + 3 < g.N) {
+            if (mrow) {
+              const float4 mk = *reinterpret_cast<const float4*>(mrow + n);
+              v[0] = mk.x > 0.f ? v[0] : 0.f; v[1] = mk.y > 0.f ? v[1] : 0.f;
+              v[2] = mk.z > 0.f ? v[2] : 0.f; v[3] = mk.w > 0.f ? v[3] : 0.f;
+            }
+            *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+            if (g.C_hi) {
+              float hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
                 uint32_t h, l;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-                const float res = v - __uint_as_float(h);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v[e]));
+                const float res = v[e] - __uint_as_float(h);
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(res));
-                g.C_hi[(int64_t)m * g.ldc + n] = __uint_as_float(h);
-                g.C_lo[(int64_t)m * g.ldc + n] = __uint_as_float(l);
+                hi[e] = __uint_as_float(h); lo[e] = __uint_as_float(l);
+              }
+              *reinterpret_cast<float4*>(g.C_hi + (int64_t)m * g.ldc + n) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<float4*>(g.C_lo + (int64_t)m * g.ldc + n) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (n + e >= g.N) break;
+              float x = v[e];
+              if (mrow) x = (mrow[n + e] > 0.f) ? x : 0.f;
+              if (g.accumulate) atomicAdd(crow + n + e, x);
+              else {
+                crow[n + e] = x;
+                if (g.C_hi) {
+                  uint32_t h, l;
+                  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+                  const float res = x - __uint_as_float(h);
+                  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(res));
+                  g.C_hi[(int64_t)m * g.ldc + n + e] = __uint_as_float(h);
+                  g.C_lo[(int64_t)m * g.ldc + n + e] = __uint_as_float(l);
+                }
               }
             }
           }
@@ -242,9 +337,10 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     tc_fence_before();
   }
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();                       // the peer may still be reading / the leader still issuing
   if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    if (CTAS == 2) tmem_dealloc_2cta(tmem_base, TN); else tmem_dealloc(tmem_base, TN);
   }
 }
 
@@ -330,24 +426,45 @@ extern "C" int phc_gemm_tc5(const float* A_hi, const float* A_lo, int64_t lda, i
   if ((C_hi == nullptr) != (C_lo == nullptr) || (C_hi && accumulate)) { phc_set_error("phc_gemm_tc5: C_hi/C_lo come as a pair and not with accumulate"); return PHC_ERR_INVALID_ARG; }
   g.C = C; g.C_hi = C_hi; g.C_lo = C_lo; g.bias = bias; g.mask = mask; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.ldmask = ldmask; g.alpha = alpha;
   g.relu = relu; g.accumulate = accumulate; g.k_splits = k_splits;
-  const dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, k_splits);
+  // CTA-pair tiles (256 x 256) when the problem is big enough in both dimensions, else single-CTA 128 x 128 tiles
+  const bool pair = (M > BM) && (N > BN + BN / 2) && !getenv("PHC_TC5_NO_PAIR");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-#define PHC_TC5_LAUNCH(AK, BK_)                                                                                   \
-  do {                                                                                                            \
-    static bool done = false;                                                                                     \
-    if (!done) {                                                                                                  \
-      e = cudaFuncSetAttribute(gemm_tc5_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); \
-      if (e != cudaSuccess) return phc_check_cuda(e, "cudaFuncSetAttribute(gemm_tc5)");                           \
-      done = true;                                                                                                \
-    }                                                                                                             \
-    gemm_tc5_kernel<AK, BK_><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tAh, tAl, tBh, tBl, g);                        \
-    phc_count_launches(1);                                                                                        \
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  if (pair) {
+    cfg.gridDim = dim3(2 * ((M + 2 * BM - 1) / (2 * BM)), (N + 2 * BN - 1) / (2 * BN), k_splits);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3((N + BN - 1) / BN, (M + BM - 1) / BM, k_splits);
+    cfg.attrs = nullptr; cfg.numAttrs = 0;
+  }
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+#define PHC_TC5_LAUNCH(AK, BK_, NC)                                                                                     \
+  do {                                                                                                                  \
+    static bool done = false;                                                                                           \
+    if (!done) {                                                                                                        \
+      e = cudaFuncSetAttribute(gemm_tc5_kernel<AK, BK_, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);  \
+      if (e != cudaSuccess) return phc_check_cuda(e, "cudaFuncSetAttribute(gemm_tc5)");                                 \
+      done = true;                                                                                                      \
+    }                                                                                                                   \
+    e = cudaLaunchKernelEx(&cfg, gemm_tc5_kernel<AK, BK_, NC>, tAh, tAl, tBh, tBl, g);                                  \
+    if (e != cudaSuccess) return phc_check_cuda(e, "cudaLaunchKernelEx(gemm_tc5)");                                     \
+    phc_count_launches(1);                                                                                              \
   } while (0)
-  if (a_kmajor && b_kmajor) PHC_TC5_LAUNCH(true, true);
-  else if (a_kmajor && !b_kmajor) PHC_TC5_LAUNCH(true, false);
-  else if (!a_kmajor && b_kmajor) PHC_TC5_LAUNCH(false, true);
-  else PHC_TC5_LAUNCH(false, false);
+#define PHC_TC5_DISPATCH(NC)                                       \
+  do {                                                             \
+    if (a_kmajor && b_kmajor) PHC_TC5_LAUNCH(true, true, NC);      \
+    else if (a_kmajor && !b_kmajor) PHC_TC5_LAUNCH(true, false, NC); \
+    else if (!a_kmajor && b_kmajor) PHC_TC5_LAUNCH(false, true, NC); \
+    else PHC_TC5_LAUNCH(false, false, NC);                         \
+  } while (0)
+  if (pair) PHC_TC5_DISPATCH(2); else PHC_TC5_DISPATCH(1);
+#undef PHC_TC5_DISPATCH
 #undef PHC_TC5_LAUNCH
   return phc_check_cuda(cudaGetLastError(), "gemm_tc5_kernel launch");
 }

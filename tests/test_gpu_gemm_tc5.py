@@ -38,7 +38,8 @@ def test_split_is_exact_to_2_pow_minus_21():
     assert int((hi.view(torch.int32) & 0x1FFF).abs().sum()) == 0 and int((lo.view(torch.int32) & 0x1FFF).abs().sum()) == 0
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (300, 70, 934), (4096, 1024, 936), (130, 1, 512), (257, 69, 512)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (300, 70, 934), (4096, 1024, 936), (130, 1, 512), (257, 69, 512),
+                                   (260, 200, 100), (256, 256, 32), (1000, 520, 2048)])      # the last rows use CTA-pair tiles
 def test_tc5_forward_form(M, N, K):
     g = torch.Generator().manual_seed(M + N + K)
     A, B, bias = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / math.sqrt(K), torch.randn(N, generator=g)

@@ -159,7 +159,14 @@ def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units, backen
     from tests.learner_harness import run_cuda_minibatch
     net = AMPNetwork(obs, act, amp, units, units, device=DEV, seed=3)
     make_lattice(net, seed=B)
-    net.weight(net.actor.head).mul_(0.5)          # |mu| straddles the +-1 soft bound: bound loss active on part of the batch
+    # rescale the mu head so that mu has unit spread: part of the batch sits beyond the +-1 soft bound (bound loss active)
+    g0 = torch.Generator().manual_seed(99)
+    x0 = lattice_inputs(torch.clamp(torch.randn(256, obs, generator=g0) * 1.5, -5, 5))
+    sd0 = {k: v.cpu() for k, v in net.state_dict().items()}
+    aw0, ab0 = PO.stack_params(sd0, "actor_mlp", "mu", len(units))
+    spread = float(O.mlp_forward(x0.double(), [w.double() for w in aw0], [b.double() for b in ab0]).std())
+    net.weight(net.actor.head).mul_(1.0 / spread)
+    net.bias(net.actor.head).mul_(1.0 / spread)
     sd = {k: v.cpu() for k, v in net.state_dict().items()}
     aw, ab = PO.stack_params(sd, "actor_mlp", "mu", len(units))
     mu_fn = lambda x: O.mlp_forward(x.double(), [w.double() for w in aw], [b.double() for b in ab])
