@@ -304,6 +304,11 @@ def main():
         sampler.start()
     sec_per_step, launches = timed_epochs(agent, args.steps, args.warmup, world, read_result=False)
     clocks = sampler.stop() if rank == 0 else None
+    if os.environ.get("PHC_PHASE_TIMING", "0") == "1" and rank == 0:       # diagnostic only: CUDA-event phase breakdown of one epoch
+        agent.timer.report()
+        agent.train_epoch()
+        rep = agent.timer.report()
+        print(json.dumps({"phase_ms": {k: round(v, 3) for k, v in sorted(rep.items(), key=lambda kv: -kv[1])}, "sum_ms": round(sum(rep.values()), 2)}), file=sys.stderr, flush=True)
     env_steps = HORIZON * args.num_envs * world
     value = env_steps / (sec_per_step * 1e-3)
 

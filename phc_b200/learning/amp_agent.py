@@ -39,6 +39,41 @@ DEFAULT_CONFIG = dict(          # phc/data/cfg/learning/im.yaml:43-99
 )
 
 
+class PhaseTimer:
+    """Optional CUDA-event phase breakdown of an epoch (PHC_PHASE_TIMING=1): `with timer("name"):` records an event pair on
+    the current stream; `report()` synchronises once and returns {name: milliseconds}.  Disabled = zero overhead."""
+
+    class _Span:
+        def __init__(self, owner, name):
+            self.o, self.n = owner, name
+
+        def __enter__(self):
+            if self.o.enabled:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+
+        def __exit__(self, *a):
+            if self.o.enabled:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                self.o.spans.append((self.n, self.e0, e1))
+
+    def __init__(self, enabled: bool):
+        self.enabled = enabled
+        self.spans = []
+
+    def __call__(self, name):
+        return PhaseTimer._Span(self, name)
+
+    def report(self):
+        torch.cuda.synchronize()
+        out = {}
+        for n, a, b in self.spans:
+            out[n] = out.get(n, 0.0) + a.elapsed_time(b)
+        self.spans = []
+        return out
+
+
 class RunningMeanStd:
     """phc/utils/running_mean_std.py: fp64 running mean / var / count on the device, kernels phc_rms_apply/update."""
 
@@ -212,6 +247,7 @@ class AMPAgent:
         self.running_mean_std_temp = self.running_mean_std.frozen_copy() if self.normalize_input else None
 
         self._init_buffers()
+        self.timer = PhaseTimer(os.environ.get("PHC_PHASE_TIMING", "0") == "1")
         self.epoch_num = 0
         self.frame = 0
         self.obs = None
@@ -346,36 +382,44 @@ class AMPAgent:
         terminated_flags = torch.zeros(self.num_actors, device=self.device)
         reward_raw = None
         done_mask = self._no_dones          # the reference starts every rollout with done_indices = [] (amp_agent.py:314)
+        T = self.timer
         for n in range(self.horizon_length):
-            self.obs = self.env_reset(done_mask)
-            eb["obses"][n].copy_(self.obs["obs"])
-            res = self.get_action_values(self.obs)
-            for k in ("actions", "neglogpacs", "values", "mus", "sigmas"):
-                eb[k][n].copy_(res[k])
-            self.obs, rewards, self.dones, infos = self.env_step(res["actions"])
-            eb["rewards"][n].copy_(rewards)
-            eb["next_obses"][n].copy_(self.obs["obs"])
-            eb["dones"][n].copy_(self.dones)
-            if "amp_obs_export" in infos:
-                infos["amp_obs_export"](eb["amp_obs"][n])            # AMP ring -> newest-first window, written in place
-            else:
-                eb["amp_obs"][n].copy_(infos["amp_obs"])
-            terminated = infos["terminate"].float()
-            terminated_flags += terminated
-            rr = infos["reward_raw"].mean(dim=0)
-            reward_raw = rr if reward_raw is None else reward_raw + rr
-            next_vals = self._eval_critic(self.obs)
-            next_vals *= (1.0 - terminated.unsqueeze(-1))
-            eb["next_values"][n].copy_(next_vals)
+            with T("rollout.env_reset"):
+                self.obs = self.env_reset(done_mask)
+            with T("rollout.policy"):
+                eb["obses"][n].copy_(self.obs["obs"])
+                res = self.get_action_values(self.obs)
+                for k in ("actions", "neglogpacs", "values", "mus", "sigmas"):
+                    eb[k][n].copy_(res[k])
+            with T("rollout.env_step"):
+                self.obs, rewards, self.dones, infos = self.env_step(res["actions"])
+            with T("rollout.store"):
+                eb["rewards"][n].copy_(rewards)
+                eb["next_obses"][n].copy_(self.obs["obs"])
+                eb["dones"][n].copy_(self.dones)
+                if "amp_obs_export" in infos:
+                    infos["amp_obs_export"](eb["amp_obs"][n])            # AMP ring -> newest-first window, written in place
+                else:
+                    eb["amp_obs"][n].copy_(infos["amp_obs"])
+                terminated = infos["terminate"].float()
+                terminated_flags += terminated
+                rr = infos["reward_raw"].mean(dim=0)
+                reward_raw = rr if reward_raw is None else reward_raw + rr
+            with T("rollout.critic_next"):
+                next_vals = self._eval_critic(self.obs)
+                next_vals *= (1.0 - terminated.unsqueeze(-1))
+                eb["next_values"][n].copy_(next_vals)
             not_dones = 1.0 - self.dones.float()
             self.current_rewards = (self.current_rewards + rewards.squeeze(1)) * not_dones
             self.current_lengths = (self.current_lengths + 1) * not_dones
             done_mask = self.dones
 
         mb_fdones = eb["dones"]
-        amp_rewards = self._calc_amp_rewards(eb["amp_obs"])
-        mb_rewards = self._combine_rewards(eb["rewards"], amp_rewards)
-        mb_advs = self.discount_values(mb_fdones, eb["values"], mb_rewards, eb["next_values"])
+        with T("rollout.disc_reward"):
+            amp_rewards = self._calc_amp_rewards(eb["amp_obs"])
+            mb_rewards = self._combine_rewards(eb["rewards"], amp_rewards)
+        with T("rollout.gae"):
+            mb_advs = self.discount_values(mb_fdones, eb["values"], mb_rewards, eb["next_values"])
         mb_returns = self._last_returns
         flat = lambda t: t.transpose(0, 1).reshape(self.batch_size, *t.shape[2:])      # swap_and_flatten01
         batch_dict = {k: flat(eb[k]) for k in self.tensor_list}
@@ -453,43 +497,54 @@ class AMPAgent:
         self._stats.zero_()
         net.grads.zero_()
 
+        T = self.timer
         # ---- actor / critic ----------------------------------------------------------------------------------
-        x = self._preproc_obs(ds["obs"], use_temp=self.temp_running_mean, out=self._x_mb, row_idx=idx)
-        mu = eng.forward(net.actor, x, self._ws_actor)
-        val = eng.forward(net.critic, x, self._ws_critic)
-        actions, old_nlp, adv = ds["actions"][idx], ds["old_logp_actions"][idx], ds["advantages"][idx]
-        old_mu, old_sigma, rets = ds["mu"][idx], ds["sigma"][idx], ds["returns"][idx].reshape(-1)
-        dmu, dv = self._ws_actor["dout"], self._ws_critic["dout"]
-        _lib.check(lib.phc_ppo_actor_grad(mu.data_ptr(), mu.stride(0), net.sigma.data_ptr(), actions.data_ptr(), old_nlp.data_ptr(),
-                                          adv.data_ptr(), old_mu.data_ptr(), old_sigma.data_ptr(), B, A, self.e_clip,
-                                          self.bounds_loss_coef, inv_b, dmu.data_ptr(), dmu.stride(0), self._stats.data_ptr(), st))
-        _lib.check(lib.phc_ppo_critic_grad(val.data_ptr(), val.stride(0), rets.data_ptr(), B, self.critic_coef, inv_b,
-                                           dv.data_ptr(), dv.stride(0), self._stats.data_ptr(), st))
-        eng.backward(net.actor, x, self._ws_actor)
-        eng.backward(net.critic, x, self._ws_critic)
+        with T("update.preproc_obs"):
+            x = self._preproc_obs(ds["obs"], use_temp=self.temp_running_mean, out=self._x_mb, row_idx=idx)
+        with T("update.ac_forward"):
+            mu = eng.forward(net.actor, x, self._ws_actor)
+            val = eng.forward(net.critic, x, self._ws_critic)
+        with T("update.ac_loss"):
+            actions, old_nlp, adv = ds["actions"][idx], ds["old_logp_actions"][idx], ds["advantages"][idx]
+            old_mu, old_sigma, rets = ds["mu"][idx], ds["sigma"][idx], ds["returns"][idx].reshape(-1)
+            dmu, dv = self._ws_actor["dout"], self._ws_critic["dout"]
+            _lib.check(lib.phc_ppo_actor_grad(mu.data_ptr(), mu.stride(0), net.sigma.data_ptr(), actions.data_ptr(), old_nlp.data_ptr(),
+                                              adv.data_ptr(), old_mu.data_ptr(), old_sigma.data_ptr(), B, A, self.e_clip,
+                                              self.bounds_loss_coef, inv_b, dmu.data_ptr(), dmu.stride(0), self._stats.data_ptr(), st))
+            _lib.check(lib.phc_ppo_critic_grad(val.data_ptr(), val.stride(0), rets.data_ptr(), B, self.critic_coef, inv_b,
+                                               dv.data_ptr(), dv.stride(0), self._stats.data_ptr(), st))
+        with T("update.ac_backward"):
+            eng.backward(net.actor, x, self._ws_actor)
+            eng.backward(net.critic, x, self._ws_critic)
 
         # ---- discriminator: rows [agent | replay | demo] of the first Bd minibatch samples ---------------------
-        aidx = idx[:Bd]
-        xa = self._amp_mb
-        self._preproc_amp_obs(ds["amp_obs"], xa[0:Bd], row_idx=aidx)
-        self._preproc_amp_obs(self._amp_replay_src, xa[Bd:2 * Bd], row_idx=ds["amp_obs_replay_idx"][aidx])
-        self._preproc_amp_obs(self._amp_obs_demo_buffer.data, xa[2 * Bd:3 * Bd], row_idx=ds["amp_obs_demo_idx"][aidx])
-        logits = eng.forward(net.disc, xa, self._ws_disc)
-        dl = self._ws_disc["dout"]
-        _lib.check(lib.phc_disc_logit_grad(logits.data_ptr(), logits.stride(0), 2 * Bd, Bd, self._disc_coef, dl.data_ptr(),
-                                           dl.stride(0), self._stats.data_ptr(), st))
-        eng.backward(net.disc, xa, self._ws_disc)
-        self._disc_grad_penalty_backward(xa[2 * Bd:3 * Bd], [h[2 * Bd:3 * Bd] for h in self._ws_disc["h"]], Bd)
-        # logit regulariser and weight decay (amp_agent.py:745-747, :771-775): d/dW (c * sum W^2) = 2 c W
-        head = net.disc.head
-        _lib.check(lib.phc_axpy2d(net.weight(head).data_ptr(), head.in_pad, net.weight(head, True).data_ptr(), head.in_pad, 1,
-                                  head.in_dim, 2.0 * self._disc_coef * self._disc_logit_reg, self._stats[11:].data_ptr(), st))
-        if self._disc_weight_decay != 0:
-            for l in net.disc.layers:
-                _lib.check(lib.phc_axpy2d(net.weight(l).data_ptr(), l.in_pad, net.weight(l, True).data_ptr(), l.in_pad, l.out_dim,
-                                          l.in_dim, 2.0 * self._disc_coef * self._disc_weight_decay, self._stats[12:].data_ptr(), st))
+        with T("update.disc_preproc"):
+            aidx = idx[:Bd]
+            xa = self._amp_mb
+            self._preproc_amp_obs(ds["amp_obs"], xa[0:Bd], row_idx=aidx)
+            self._preproc_amp_obs(self._amp_replay_src, xa[Bd:2 * Bd], row_idx=ds["amp_obs_replay_idx"][aidx])
+            self._preproc_amp_obs(self._amp_obs_demo_buffer.data, xa[2 * Bd:3 * Bd], row_idx=ds["amp_obs_demo_idx"][aidx])
+        with T("update.disc_forward"):
+            logits = eng.forward(net.disc, xa, self._ws_disc)
+        with T("update.disc_backward"):
+            dl = self._ws_disc["dout"]
+            _lib.check(lib.phc_disc_logit_grad(logits.data_ptr(), logits.stride(0), 2 * Bd, Bd, self._disc_coef, dl.data_ptr(),
+                                               dl.stride(0), self._stats.data_ptr(), st))
+            eng.backward(net.disc, xa, self._ws_disc)
+        with T("update.disc_grad_penalty"):
+            self._disc_grad_penalty_backward(xa[2 * Bd:3 * Bd], [h[2 * Bd:3 * Bd] for h in self._ws_disc["h"]], Bd)
+            # logit regulariser and weight decay (amp_agent.py:745-747, :771-775): d/dW (c * sum W^2) = 2 c W
+            head = net.disc.head
+            _lib.check(lib.phc_axpy2d(net.weight(head).data_ptr(), head.in_pad, net.weight(head, True).data_ptr(), head.in_pad, 1,
+                                      head.in_dim, 2.0 * self._disc_coef * self._disc_logit_reg, self._stats[11:].data_ptr(), st))
+            if self._disc_weight_decay != 0:
+                for l in net.disc.layers:
+                    _lib.check(lib.phc_axpy2d(net.weight(l).data_ptr(), l.in_pad, net.weight(l, True).data_ptr(), l.in_pad, l.out_dim,
+                                              l.in_dim, 2.0 * self._disc_coef * self._disc_weight_decay, self._stats[12:].data_ptr(), st))
 
         # ---- all-reduce, clip, Adam -----------------------------------------------------------------------------
+        t_opt = T("update.optim")
+        t_opt.__enter__()
         grad_scale = D.allreduce_grad_bucket(net.grads) if self.multi_gpu else 1.0
         self.opt_step += 1
         _lib.check(lib.phc_grad_sumsq(net.grads.data_ptr(), net.num_floats, self._gsumsq.data_ptr(), st))
@@ -499,6 +554,7 @@ class AMPAgent:
                                      self.opt_step, st))
         if eng.backend == "tc5":
             net.refresh_split()                    # hi/lo operand copies of the updated weights
+        t_opt.__exit__()
         self._last_B, self._last_Bd = B, Bd
 
     def _disc_grad_penalty_backward(self, x_demo: torch.Tensor, h_demo, Bd: int) -> None:
@@ -580,6 +636,8 @@ class AMPAgent:
         t0 = time.time()
         batch_dict = self.play_steps()
         t1 = time.time()
+        _prep = self.timer("epoch.prepare")
+        _prep.__enter__()
         self._update_amp_demos()
         n = batch_dict["amp_obs"].shape[0]
         batch_dict["amp_obs_demo_idx"] = self._amp_obs_demo_buffer.sample_indices(n)
@@ -591,11 +649,13 @@ class AMPAgent:
             batch_dict["amp_obs_replay_idx"] = self._amp_replay_buffer.sample_indices(n)
         self.set_train()
         self.prepare_dataset(batch_dict)
+        _prep.__exit__()
         for _ in range(self.mini_epochs_num):
             for i in range(self.num_minibatches):
                 self.calc_gradients({"idx": self._idx_buf[i * self.minibatch_size:(i + 1) * self.minibatch_size]})
             self._idx_buf = torch.randperm(self.batch_size, device=self.device)
-        self._store_replay_amp_obs(batch_dict["amp_obs"])
+        with self.timer("epoch.replay_store"):
+            self._store_replay_amp_obs(batch_dict["amp_obs"])
         self.post_epoch(self.epoch_num)
         t2 = time.time()
         self.epoch_num += 1
