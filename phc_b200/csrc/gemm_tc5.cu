@@ -152,6 +152,70 @@ __host__ __device__ constexpr uint32_t instr_desc(bool a_mn, bool b_mn, int mma_
          ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(mma_m >> 4) << 24);
 }
 
+// epilogue of one 32-column chunk of row m held in r[] (alpha, bias, ReLU, ReLU-backward mask, store / atomic add, optional
+// pre-split copies).  n_base = first column of the chunk.
+__device__ __forceinline__ void epilogue_store(const Args& g, const uint32_t (&r)[32], int m, int n_base, bool add_bias) {
+  const int n0 = n_base, c0 = 0;
+        float* crow = g.C + (int64_t)m * g.ldc;
+        const float* mrow = g.mask ? g.mask + (int64_t)m * g.ldmask : nullptr;
+        // 16-byte vector path when the row segment is aligned and fully inside the matrix (always for interior tiles)
+        const bool vec = !g.accumulate && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
+                         (!mrow || (((g.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0)));
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + c0 + j;
+          if (n >= g.N) break;
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = g.alpha * __uint_as_float(r[j + e]);
+            if (g.bias && add_bias && n + e < g.N) x += g.bias[n + e];
+            if (g.relu) x = fmaxf(x, 0.f);
+            v[e] = x;
+          }
+          if (vec && n + 3 < g.N) {
+            if (mrow) {
+              const float4 mk = *reinterpret_cast<const float4*>(mrow + n);
+              v[0] = mk.x > 0.f ? v[0] : 0.f; v[1] = mk.y > 0.f ? v[1] : 0.f;
+              v[2] = mk.z > 0.f ? v[2] : 0.f; v[3] = mk.w > 0.f ? v[3] : 0.f;
+            }
+            *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+            if (g.C_hi) {
+              float hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                uint32_t h, l;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v[e]));
+                const float res = v[e] - __uint_as_float(h);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(res));
+                hi[e] = __uint_as_float(h); lo[e] = __uint_as_float(l);
+              }
+              *reinterpret_cast<float4*>(g.C_hi + (int64_t)m * g.ldc + n) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<float4*>(g.C_lo + (int64_t)m * g.ldc + n) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (n + e >= g.N) break;
+              float x = v[e];
+              if (mrow) x = (mrow[n + e] > 0.f) ? x : 0.f;
+              if (g.accumulate) atomicAdd(crow + n + e, x);
+              else {
+                crow[n + e] = x;
+                if (g.C_hi) {
+                  uint32_t h, l;
+                  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+                  const float res = x - __uint_as_float(h);
+                  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(res));
+                  g.C_hi[(int64_t)m * g.ldc + n + e] = __uint_as_float(h);
+                  g.C_lo[(int64_t)m * g.ldc + n + e] = __uint_as_float(l);
+                }
+              }
+            }
+          }
+        }
+}
+
 template <bool A_K, bool B_K, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
@@ -273,66 +337,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     for (int c0 = 0; c0 < TN; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-      if (m < g.M) {
-        float* crow = g.C + (int64_t)m * g.ldc;
-        const float* mrow = g.mask ? g.mask + (int64_t)m * g.ldmask : nullptr;
-        // 16-byte vector path when the row segment is aligned and fully inside the matrix (always for interior tiles)
-        const bool vec = !g.accumulate && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
-                         (!mrow || (((g.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0)));
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + c0 + j;
-          if (n >= g.N) break;
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = g.alpha * __uint_as_float(r[j + e]);
-            if (g.bias && blockIdx.z == 0 && n + e < g.N) x += g.bias[n + e];
-            if (g.relu) x = fmaxf(x, 0.f);
-            v[e] = x;
-          }
-          if (vec && n + 3 < g.N) {
-            if (mrow) {
-              const float4 mk = *reinterpret_cast<const float4*>(mrow + n);
-              v[0] = mk.x > 0.f ? v[0] : 0.f; v[1] = mk.y > 0.f ? v[1] : 0.f;
-              v[2] = mk.z > 0.f ? v[2] : 0.f; v[3] = mk.w > 0.f ? v[3] : 0.f;
-            }
-            *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
-            if (g.C_hi) {
-              float hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                uint32_t h, l;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v[e]));
-                const float res = v[e] - __uint_as_float(h);
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(res));
-                hi[e] = __uint_as_float(h); lo[e] = __uint_as_float(l);
-              }
-              *reinterpret_cast<float4*>(g.C_hi + (int64_t)m * g.ldc + n) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<float4*>(g.C_lo + (int64_t)m * g.ldc + n) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (n + e >= g.N) break;
-              float x = v[e];
-              if (mrow) x = (mrow[n + e] > 0.f) ? x : 0.f;
-              if (g.accumulate) atomicAdd(crow + n + e, x);
-              else {
-                crow[n + e] = x;
-                if (g.C_hi) {
-                  uint32_t h, l;
-                  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-                  const float res = x - __uint_as_float(h);
-                  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(res));
-                  g.C_hi[(int64_t)m * g.ldc + n + e] = __uint_as_float(h);
-                  g.C_lo[(int64_t)m * g.ldc + n + e] = __uint_as_float(l);
-                }
-              }
-            }
-          }
-        }
-      }
+      if (m < g.M) epilogue_store(g, r, m, n0 + c0, blockIdx.z == 0);
     }
     tc_fence_before();
   }
@@ -341,6 +346,163 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   if (warp == 5) {
     tc_fence_after();
     if (CTAS == 2) tmem_dealloc_2cta(tmem_base, TN); else tmem_dealloc(tmem_base, TN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent variant (single-CTA 128 x 128 tiles): one CTA per SM walks a static list of tiles.  The shared-memory operand
+// pipeline runs continuously across tiles and the accumulator is double-buffered in TMEM (2 x 128 columns), so the
+// epilogue of tile i (TMEM -> registers -> global) overlaps the MMAs of tile i+1:
+//   TMA warp  : for every (tile, k-block): wait empty[s] -> arm full[s] -> bulk-tensor loads
+//   MMA thread: for every tile: wait tmem_empty[acc] -> for every k-block: wait full[s] -> 12 UMMAs -> commit empty[s];
+//               commit tmem_full[acc]
+//   epilogue  : wait tmem_full[acc] -> tcgen05.ld / epilogue math / stores -> arrive tmem_empty[acc] (one lane per warp)
+// Tiles are ordered m-major inside an n-column block run so that CTAs working at the same time share the A row block in L2.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+}
+
+template <bool A_K, bool B_K>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc5_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                        const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                        const __grid_constant__ Args g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
+  const int kb_total = (g.K + BK - 1) / BK;
+  const int kb_per = (kb_total + g.k_splits - 1) / g.k_splits;
+  const int num_tiles = tiles_m * tiles_n * g.k_splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (z, n, m): m fastest
+  auto decode = [&](int t, int& m0, int& n0, int& kb_begin, int& nkb, int& z) {
+    const int mi = t % tiles_m;
+    const int r = t / tiles_m;
+    const int ni = r % tiles_n;
+    z = r / tiles_n;
+    m0 = mi * BM; n0 = ni * BN;
+    kb_begin = z * kb_per;
+    const int kb_end = min(kb_total, kb_begin + kb_per);
+    nkb = max(0, kb_end - kb_begin);
+  };
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t it = 0;                                        // global k-block counter (continues across tiles)
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int m0, n0, kb_begin, nkb, z;
+        decode(t, m0, n0, kb_begin, nkb, z);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          if (it >= STAGES) mbar_wait(empty_bar + s, ((it / STAGES) - 1) & 1);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          const int k0 = (kb_begin + i) * BK;
+          mbar_expect_tx(full_bar + s, STAGE_BYTES);
+          if (A_K) {
+            tma_load_2d(st, &tmAh, full_bar + s, k0, m0);
+            tma_load_2d(st + TILE_BYTES, &tmAl, full_bar + s, k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 32; ++j) {
+              tma_load_2d(st + j * 4096, &tmAh, full_bar + s, m0 + 32 * j, k0);
+              tma_load_2d(st + TILE_BYTES + j * 4096, &tmAl, full_bar + s, m0 + 32 * j, k0);
+            }
+          }
+          if (B_K) {
+            tma_load_2d(st + 2 * TILE_BYTES, &tmBh, full_bar + s, k0, n0);
+            tma_load_2d(st + 3 * TILE_BYTES, &tmBl, full_bar + s, k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j) {
+              tma_load_2d(st + 2 * TILE_BYTES + j * 4096, &tmBh, full_bar + s, n0 + 32 * j, k0);
+              tma_load_2d(st + 3 * TILE_BYTES + j * 4096, &tmBl, full_bar + s, n0 + 32 * j, k0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc(!A_K, !B_K, BM, BN);
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+        int m0, n0, kb_begin, nkb, z;
+        decode(t, m0, n0, kb_begin, nkb, z);
+        const uint32_t acc = lt & 1, use = lt >> 1;
+        if (use > 0) mbar_wait(tmem_empty + acc, (use - 1) & 1);    // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(full_bar + s, (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t st = s32(smem + s * STAGE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint32_t a_off = A_K ? kk * 32 : kk * 1024;
+            const uint32_t b_off = B_K ? kk * 32 : kk * 1024;
+            const uint32_t a_lbo = A_K ? 16 : 4096, b_lbo = B_K ? 16 : 4096;
+            const uint32_t a_sbo = A_K ? 1024 : 512, b_sbo = B_K ? 1024 : 512;
+            const uint32_t a_lt = A_K ? 2 : 1, b_lt = B_K ? 2 : 1;
+            const uint64_t dAh = smem_desc(st + a_off, a_lbo, a_sbo, a_lt);
+            const uint64_t dAl = smem_desc(st + TILE_BYTES + a_off, a_lbo, a_sbo, a_lt);
+            const uint64_t dBh = smem_desc(st + 2 * TILE_BYTES + b_off, b_lbo, b_sbo, b_lt);
+            const uint64_t dBl = smem_desc(st + 3 * TILE_BYTES + b_off, b_lbo, b_sbo, b_lt);
+            umma_tf32(tmem_d, dAl, dBh, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+            umma_tf32(tmem_d, dAh, dBl, idesc, 1u);
+            umma_tf32(tmem_d, dAh, dBh, idesc, 1u);
+          }
+          umma_commit(empty_bar + s);
+        }
+        umma_commit(tmem_full + acc);        // also fires (immediately) for an empty k-range: the epilogue then sees nkb == 0
+      }
+    }
+  } else {
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+      int m0, n0, kb_begin, nkb, z;
+      decode(t, m0, n0, kb_begin, nkb, z);
+      const uint32_t acc = lt & 1, use = lt >> 1;
+      mbar_wait(tmem_full + acc, use & 1);
+      tc_fence_after();
+      const int m = m0 + warp * 32 + lane;
+      if (nkb > 0) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + acc * BN + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+          if (m < g.M) epilogue_store(g, r, m, n0 + c0, z == 0);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + acc);
+    }
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -427,7 +589,10 @@ extern "C" int phc_gemm_tc5(const float* A_hi, const float* A_lo, int64_t lda, i
   g.C = C; g.C_hi = C_hi; g.C_lo = C_lo; g.bias = bias; g.mask = mask; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.ldmask = ldmask; g.alpha = alpha;
   g.relu = relu; g.accumulate = accumulate; g.k_splits = k_splits;
   // CTA-pair tiles (256 x 256) when the problem is big enough in both dimensions, else single-CTA 128 x 128 tiles
-  const bool pair = (M > BM) && (N > BN + BN / 2) && !getenv("PHC_TC5_NO_PAIR");
+  // measured on the PPO shapes (bench.py): single-CTA tiles with the persistent, epilogue-overlapped kernel beat the pair
+  // tiles, so the pair path is opt-in (PHC_TC5_PAIR=1) and the persistent kernel is the default (PHC_TC5_PERSIST=0 disables)
+  const bool pair = (M > BM) && (N > BN + BN / 2) && getenv("PHC_TC5_PAIR") && getenv("PHC_TC5_PAIR")[0] == '1';
+  const bool persist = !pair && !(getenv("PHC_TC5_PERSIST") && getenv("PHC_TC5_PERSIST")[0] == '0');
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   cudaLaunchConfig_t cfg = {};
@@ -463,7 +628,30 @@ extern "C" int phc_gemm_tc5(const float* A_hi, const float* A_lo, int64_t lda, i
     else if (!a_kmajor && b_kmajor) PHC_TC5_LAUNCH(false, true, NC); \
     else PHC_TC5_LAUNCH(false, false, NC);                         \
   } while (0)
-  if (pair) PHC_TC5_DISPATCH(2); else PHC_TC5_DISPATCH(1);
+  if (persist) {
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * k_splits;
+    cfg.gridDim = dim3(tiles < num_sms ? tiles : num_sms);
+#define PHC_TC5_PLAUNCH(AK, BK_)                                                                                            \
+  do {                                                                                                                      \
+    static bool done = false;                                                                                               \
+    if (!done) {                                                                                                            \
+      e = cudaFuncSetAttribute(gemm_tc5_persist_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);  \
+      if (e != cudaSuccess) return phc_check_cuda(e, "cudaFuncSetAttribute(gemm_tc5_persist)");                             \
+      done = true;                                                                                                          \
+    }                                                                                                                       \
+    e = cudaLaunchKernelEx(&cfg, gemm_tc5_persist_kernel<AK, BK_>, tAh, tAl, tBh, tBl, g);                                  \
+    if (e != cudaSuccess) return phc_check_cuda(e, "cudaLaunchKernelEx(gemm_tc5_persist)");                                 \
+    phc_count_launches(1);                                                                                                  \
+  } while (0)
+    if (a_kmajor && b_kmajor) PHC_TC5_PLAUNCH(true, true);
+    else if (a_kmajor && !b_kmajor) PHC_TC5_PLAUNCH(true, false);
+    else if (!a_kmajor && b_kmajor) PHC_TC5_PLAUNCH(false, true);
+    else PHC_TC5_PLAUNCH(false, false);
+#undef PHC_TC5_PLAUNCH
+  } else if (pair) PHC_TC5_DISPATCH(2);
+  else PHC_TC5_DISPATCH(1);
 #undef PHC_TC5_DISPATCH
 #undef PHC_TC5_LAUNCH
   return phc_check_cuda(cudaGetLastError(), "gemm_tc5_kernel launch");
