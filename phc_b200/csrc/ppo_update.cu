@@ -129,50 +129,61 @@ __global__ void __launch_bounds__(128) gaussian_sample_kernel(const float* __res
 // PPO actor loss: neglogp of the stored actions under the new mu, clipped surrogate, bound loss, KL; d(loss)/d(mu)
 // stats[0] += sum a_loss, [1] += sum b_loss, [2] += #clipped, [3] += sum kl, [4] += sum entropy
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 ppo_actor_grad_kernel(const float* __restrict__ mu, int64_t ldmu, const float* __restrict__ logstd,
                       const float* __restrict__ actions, const float* __restrict__ old_neglogp,
                       const float* __restrict__ adv, const float* __restrict__ old_mu,
                       const float* __restrict__ old_sigma, int64_t n, int A, float e_clip, float bound_coef,
                       float inv_batch, float* __restrict__ dmu, int64_t lddmu, float* __restrict__ stats) {
-  const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (r >= n) return;
-  float acc = 0.f, ls = 0.f, bl = 0.f, kl = 0.f;
-  for (int j = lane; j < A; j += 32) {
-    const float m = mu[r * ldmu + j];
-    const float l = logstd[j];
-    const float sg = expf(l);
-    const float z = (actions[r * A + j] - m) / sg;
-    acc += z * z;
-    ls += l;
-    const float hi = fmaxf(m - 1.0f, 0.f), lo = fminf(m + 1.0f, 0.f);
-    bl += lo * lo + hi * hi;
-    const float so = old_sigma[r * A + j], mo = old_mu[r * A + j];
-    kl += logf(so / sg + 1e-5f) + (sg * sg + (mo - m) * (mo - m)) / (2.0f * (so * so + 1e-5f)) - 0.5f;
+  // one warp per row, rows strided over the grid; the five batch statistics are accumulated per warp, folded per block in
+  // shared memory and leave with ONE atomic per block and statistic (per-row atomics on five addresses serialise: 140 us)
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float st[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; r < n; r += warps_total) {
+    float acc = 0.f, ls = 0.f, bl = 0.f, kl = 0.f;
+    for (int j = lane; j < A; j += 32) {
+      const float m = mu[r * ldmu + j];
+      const float l = logstd[j];
+      const float sg = expf(l);
+      const float z = (actions[r * A + j] - m) / sg;
+      acc += z * z;
+      ls += l;
+      const float hi = fmaxf(m - 1.0f, 0.f), lo = fminf(m + 1.0f, 0.f);
+      bl += lo * lo + hi * hi;
+      const float so = old_sigma[r * A + j], mo = old_mu[r * A + j];
+      kl += logf(so / sg + 1e-5f) + (sg * sg + (mo - m) * (mo - m)) / (2.0f * (so * so + 1e-5f)) - 0.5f;
+    }
+    acc = wsum(acc); ls = wsum(ls); bl = wsum(bl); kl = wsum(kl);
+    const float nlp = 0.5f * acc + 0.5f * 1.8378770664093453f * (float)A + ls;
+    const float ad = adv[r];
+    const float ratio = expf(old_neglogp[r] - nlp);
+    const float s1 = -ad * ratio;
+    const float s2 = -ad * fminf(fmaxf(ratio, 1.0f - e_clip), 1.0f + e_clip);
+    const float a_loss = fmaxf(s1, s2);
+    // d a_loss / d neglogp: the un-clipped branch carries adv*ratio, the clipped one is flat (torch.max tie -> same value)
+    const float g_nlp = (s1 >= s2) ? ad * ratio : 0.f;
+    for (int j = lane; j < A; j += 32) {
+      const float m = mu[r * ldmu + j];
+      const float sg = expf(logstd[j]);
+      const float dn = -(actions[r * A + j] - m) / (sg * sg);            // d neglogp / d mu
+      const float hi = fmaxf(m - 1.0f, 0.f), lo = fminf(m + 1.0f, 0.f);
+      dmu[r * lddmu + j] = inv_batch * (g_nlp * dn + bound_coef * 2.0f * (hi + lo));
+    }
+    st[0] += a_loss;
+    st[1] += bl;
+    st[2] += fabsf(ratio - 1.0f) > e_clip ? 1.0f : 0.0f;
+    st[3] += kl;
+    st[4] += ls + 0.5f * (1.0f + 1.8378770664093453f) * (float)A;          // Normal entropy summed over actions
   }
-  acc = wsum(acc); ls = wsum(ls); bl = wsum(bl); kl = wsum(kl);
-  const float nlp = 0.5f * acc + 0.5f * 1.8378770664093453f * (float)A + ls;
-  const float ad = adv[r];
-  const float ratio = expf(old_neglogp[r] - nlp);
-  const float s1 = -ad * ratio;
-  const float s2 = -ad * fminf(fmaxf(ratio, 1.0f - e_clip), 1.0f + e_clip);
-  const float a_loss = fmaxf(s1, s2);
-  // d a_loss / d neglogp: the un-clipped branch carries adv*ratio, the clipped one is flat (torch.max tie -> same value)
-  const float g_nlp = (s1 >= s2) ? ad * ratio : 0.f;
-  for (int j = lane; j < A; j += 32) {
-    const float m = mu[r * ldmu + j];
-    const float sg = expf(logstd[j]);
-    const float dn = -(actions[r * A + j] - m) / (sg * sg);            // d neglogp / d mu
-    const float hi = fmaxf(m - 1.0f, 0.f), lo = fminf(m + 1.0f, 0.f);
-    dmu[r * lddmu + j] = inv_batch * (g_nlp * dn + bound_coef * 2.0f * (hi + lo));
-  }
-  if (lane == 0) {
-    atomicAdd(stats + 0, a_loss);
-    atomicAdd(stats + 1, bl);
-    atomicAdd(stats + 2, fabsf(ratio - 1.0f) > e_clip ? 1.0f : 0.0f);
-    atomicAdd(stats + 3, kl);
-    atomicAdd(stats + 4, ls + 0.5f * (1.0f + 1.8378770664093453f) * (float)A);   // Normal entropy summed over actions
+  __shared__ float sh[8][5];
+  if (lane == 0)
+    for (int k = 0; k < 5; ++k) sh[wib][k] = st[k];
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w][threadIdx.x];
+    atomicAdd(stats + threadIdx.x, t);
   }
 }
 
@@ -359,7 +370,7 @@ extern "C" int phc_ppo_actor_grad(const float* mu, int64_t ldmu, const float* lo
     phc_set_error("phc_ppo_actor_grad: bad arguments"); return PHC_ERR_INVALID_ARG;
   }
   if (n == 0) return PHC_OK;
-  ppo_actor_grad_kernel<<<(unsigned)((n + 3) / 4), 128, 0, ST(stream)>>>(mu, ldmu, logstd, actions, old_neglogp, adv, old_mu, old_sigma, n, A,
+  ppo_actor_grad_kernel<<<(unsigned)((n + 7) / 8 < 148 * 4 ? (n + 7) / 8 : 148 * 4), 256, 0, ST(stream)>>>(mu, ldmu, logstd, actions, old_neglogp, adv, old_mu, old_sigma, n, A,
                                                                          e_clip, bound_coef, inv_batch, dmu, lddmu, stats); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "ppo_actor_grad_kernel");
 }
