@@ -22,7 +22,7 @@ def stack_params(sd: Dict[str, torch.Tensor], prefix: str, head: str, n_hidden: 
 
 
 def minibatch_update(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], cfg: Dict, n_hidden: int = 2,
-                     adam_state=None, step: int = 1, dtype=torch.float32) -> Dict:
+                     adam_state=None, step: int = 1, dtype=torch.float32, mu_override=None) -> Dict:
     """sd: reference-keyed state dict (fp32, un-padded).  batch: obs_n [B,obs] (already normalised), actions, old_neglogp,
     advantages, old_mu, old_sigma, returns [B,1], amp_agent / amp_replay / amp_demo [Bd, amp] (already normalised)."""
     p = {k: v.clone().to(dtype).requires_grad_(k != "a2c_network.sigma") for k, v in sd.items()}
@@ -33,6 +33,11 @@ def minibatch_update(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor]
     logstd = p["a2c_network.sigma"]
 
     mu = O.mlp_forward(batch["obs_n"], aw, ab)
+    mu_exact = mu.detach().clone()
+    if mu_override is not None:
+        # evaluate the loss AT the given policy mean (same gradient path): with sigma = exp(-2.9) an fp32-level difference in
+        # mu moves neglogp by ~150x that, so loss/backward arithmetic can only be compared tightly at identical mu
+        mu = mu + (mu_override.to(dtype) - mu).detach()
     values = O.mlp_forward(batch["obs_n"], cw, cb)
     sigma = torch.exp(mu * 0.0 + logstd)
     neglogp = O.gaussian_neglogp(batch["actions"], mu, sigma, (mu * 0.0 + logstd))
@@ -67,5 +72,5 @@ def minibatch_update(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor]
     opt.step()
     new_sd = {k: l.detach() for k, l in zip(names, leaves)}
     return dict(loss=loss.detach(), a_loss=a_loss.detach(), c_loss=c_loss.detach(), b_loss=b_loss.detach(), kl=kl,
-                entropy=entropy.detach(), disc=dinfo, grads=gdict, new_params=new_sd, total_norm=total_norm, mu=mu.detach(),
+                entropy=entropy.detach(), disc=dinfo, grads=gdict, new_params=new_sd, total_norm=total_norm, mu=mu_exact,
                 values=values.detach(), logits_agent=la.detach(), logits_demo=ld.detach())

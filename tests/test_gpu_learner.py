@@ -173,8 +173,10 @@ def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units, backen
     batch = _rand_batch(B, Bd, obs, act, amp, seed=B, mu_fn=lambda x: mu_fn(lattice_inputs(x)))
     for k in ("obs_n", "amp_agent", "amp_replay", "amp_demo"):
         batch[k] = lattice_inputs(batch[k])
-    exp = PO.minibatch_update(sd, batch, CFG, n_hidden=len(units), dtype=torch.float64)      # near-exact reference
     got = run_cuda_minibatch(net, batch, CFG, backend=backend)
+    # near-exact (fp64) reference; the loss is evaluated at OUR policy mean (see ppo_oracle.minibatch_update: sigma = e^-2.9
+    # turns an fp32-level difference in mu into a 150x larger one in neglogp), the forward pass itself is compared below
+    exp = PO.minibatch_update(sd, batch, CFG, n_hidden=len(units), dtype=torch.float64, mu_override=got["mu"].cpu().double())
 
     def scaled(a, b, tol, what):       # error relative to the tensor's scale (entries are sums of large cancelling terms)
         err = float((a.double().cpu() - b.double()).abs().max())
@@ -193,10 +195,21 @@ def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units, backen
     close(torch.tensor(s["disc_agent_acc"]), f32(exp["disc"]["disc_agent_acc"]), atol=2e-3, what="disc agent acc")
     assert 0.02 < s["actor_clip_frac"] < 0.98 and s["b_loss"] > 0, f"test batch must exercise both PPO branches and the bound loss: {s}"
     gsd = got["grads"]
+    report = []
     for k, ge in exp["grads"].items():
-        scaled(gsd[k], ge, 1e-4, f"grad {k}")
+        err = float((gsd[k].double().cpu() - ge.double()).abs().max())
+        sc = float(ge.double().abs().max()) + 1e-30
+        report.append((err / sc, k, err, sc))
+    bad = [f"{k}: {e:.2e}/{sc:.2e}={r:.2e}" for r, k, e, sc in report if r > 1e-4]
+    assert not bad, "gradient mismatches (max abs err / max abs value): " + "; ".join(bad) + " || ok: " + \
+        "; ".join(f"{k.split('.', 1)[1]}={r:.1e}" for r, k, e, sc in report if r <= 1e-4)
     close(torch.tensor(got["total_norm"]), exp["total_norm"].float(), rtol=1e-4, atol=1e-6, what="grad norm")
+    lr = CFG["learning_rate"]
     for k, pe in exp["new_params"].items():
-        # Adam's first step moves every weight by ~lr*sign(g): parameters must agree to a small fraction of one step
-        d = float((got["new_params"][k].double().cpu() - pe.double()).abs().max())
-        assert d <= 0.05 * CFG["learning_rate"] + 1e-7 * float(pe.abs().max()), f"adam {k}: {d:.3e}"
+        # Adam's first step is lr * g / (|g| + 1e-8 * sqrt(bias corr.)) ~ lr * sign(g): well determined only where |g| is well
+        # above the gradient's own rounding error; compare those entries to 2 % of a step, bound the rest by one full step
+        ge = exp["grads"][k].double()
+        well = ge.abs() > 1e-3 * ge.abs().max()
+        d = (got["new_params"][k].double().cpu() - pe.double()).abs()
+        assert float(d[well].max()) <= 0.02 * lr + 1e-7 * float(pe.abs().max()), f"adam {k}: {float(d[well].max()):.3e}"
+        assert float(d.max()) <= 2.1 * lr, f"adam (near-zero gradient entries) {k}: {float(d.max()):.3e}"
