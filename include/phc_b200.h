@@ -113,6 +113,8 @@ PHC_API int phc_motion_state(const PhcMotionLib* lib, const int64_t* motion_ids,
 #define PHC_FLAG_OBS_ONLY (1u << 7)        /* _compute_observations(env_ids) of the reset path: write obs (+ref_*) only */
 
 #define PHC_MAX_KEY_BODIES 8
+#define PHC_MAX_BODIES 32      /* one body per lane in the fused step kernel */
+#define PHC_MAX_AMP_JOINTS 32
 
 typedef struct PhcStepArgs {
   /* ---- simulator state (inputs; contract of Humanoid._setup_tensors, humanoid.py:179-247) ---- */
@@ -139,11 +141,12 @@ typedef struct PhcStepArgs {
   float k_pos, k_rot, k_vel, k_ang_vel; /* reward_specs (humanoid_im.py:57) */
   float w_pos, w_rot, w_vel, w_ang_vel;
   float power_coef;                     /* power_coefficient (humanoid_im.py:107) */
-  const float* term_thresh;  /* [J] termination distance per body, +inf for bodies outside reset_bodies */
+  float term_thresh[PHC_MAX_BODIES]; /* [J] termination distance per body, +inf for bodies outside reset_bodies (by
+                                        value: configuration travels in the kernel parameters, not through a dependent load) */
   float term_dist_mean;      /* threshold of the first reset body (used by PHC_FLAG_TERM_USE_MEAN)       */
   int32_t num_key_bodies;
   int32_t key_bodies[PHC_MAX_KEY_BODIES]; /* _key_body_ids */
-  const int32_t* amp_joints; /* [num_amp_joints] joint indices (dof_subset / 3) kept in the AMP obs, or NULL = none */
+  int32_t amp_joints[PHC_MAX_AMP_JOINTS]; /* [num_amp_joints] joint indices (dof_subset / 3) kept in the AMP obs */
   int32_t num_amp_joints;
   /* ---- outputs ---- */
   float* obs;            /* [N, obs_stride] first 15J-3(+1) self obs then 24*J*T task obs (obs_buf)     */
@@ -178,8 +181,8 @@ PHC_API int phc_env_step(const PhcStepArgs* args, void* stream);
  * (:575-603): AMP observations of the REFERENCE motion at t0 - (first_step + k)*dt, k = 0..num_steps-1,
  * written to out[n, num_steps, A] (row stride out_stride floats).  Needs lib->frames_joint. */
 PHC_API int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* motion_ids, const float* times0, int64_t n,
-                     int32_t first_step, int32_t num_steps, float dt, uint32_t flags, const int32_t* key_bodies,
-                     int32_t num_key_bodies, const int32_t* amp_joints, int32_t num_amp_joints, float* out,
+                     int32_t first_step, int32_t num_steps, float dt, uint32_t flags, const int32_t* key_bodies /* host */,
+                     int32_t num_key_bodies, const int32_t* amp_joints /* host */, int32_t num_amp_joints, float* out,
                      int64_t out_stride, const int64_t* only_where /* [n] or NULL: skip rows whose entry is 0 */,
                      int32_t slot_offset /* ring rotation: step k lands in slot (k + slot_offset) % num_steps; 0 = plain */,
                      void* stream);

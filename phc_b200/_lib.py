@@ -20,6 +20,8 @@ PHC_FLAG_NO_COLLISION = 1 << 5
 PHC_FLAG_TERM_USE_MEAN = 1 << 6
 PHC_FLAG_OBS_ONLY = 1 << 7
 PHC_MAX_KEY_BODIES = 8
+PHC_MAX_BODIES = 32
+PHC_MAX_AMP_JOINTS = 32
 
 _p = C.c_void_p
 
@@ -49,9 +51,9 @@ class PhcStepArgs(C.Structure):
         ("flags", C.c_uint32),
         ("k_pos", C.c_float), ("k_rot", C.c_float), ("k_vel", C.c_float), ("k_ang_vel", C.c_float),
         ("w_pos", C.c_float), ("w_rot", C.c_float), ("w_vel", C.c_float), ("w_ang_vel", C.c_float),
-        ("power_coef", C.c_float), ("term_thresh", _p), ("term_dist_mean", C.c_float),
+        ("power_coef", C.c_float), ("term_thresh", C.c_float * PHC_MAX_BODIES), ("term_dist_mean", C.c_float),
         ("num_key_bodies", C.c_int32), ("key_bodies", C.c_int32 * PHC_MAX_KEY_BODIES),
-        ("amp_joints", _p), ("num_amp_joints", C.c_int32),
+        ("amp_joints", C.c_int32 * PHC_MAX_AMP_JOINTS), ("num_amp_joints", C.c_int32),
         ("obs", _p), ("obs_stride", C.c_int64), ("rew", _p), ("reward_raw", _p), ("reset", _p), ("terminate", _p),
         ("amp_out", _p), ("amp_hist_in", _p), ("amp_out_stride", C.c_int64), ("amp_steps", C.c_int32),
         ("ref_body_pos", _p), ("ref_body_rot", _p), ("ref_body_vel", _p), ("ref_body_ang_vel", _p),

@@ -74,7 +74,9 @@ __device__ __forceinline__ BodyRec blend_body(const float* s0, const float* s1, 
 __device__ __forceinline__ void st3(float* d, V3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
 __device__ __forceinline__ void st6(float* d, TanNorm t) { st3(d, t.t); st3(d + 3, t.n); }
 
-template <int T_MAX>
+// JT > 0: the body count is a compile-time constant (24 = SMPL, 20 = H1): record strides, segment offsets of the observation
+// row and the shared-memory carve-up fold into immediates; JT == 0 is the generic runtime-J build.
+template <int T_MAX, int JT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm)
 env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const int self_dim, const int amp_dim,
                 const bool alias_obs, const bool state_bulk_ok) {
@@ -85,8 +87,9 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   if (a.only_where && a.only_where[env] == 0) return;  // masked subset (reset path)
   const bool obs_only = a.flags & PHC_FLAG_OBS_ONLY;
 
-  const int J = a.lib.num_bodies, D = 3 * (J - 1), T = a.time_steps;
-  const int BS = a.lib.body_stride;
+  const int J = JT > 0 ? JT : a.lib.num_bodies, D = 3 * (J - 1);
+  const int T = (T_MAX == 1) ? 1 : a.time_steps;
+  const int BS = JT > 0 ? round4(JT * kBodyRec) : a.lib.body_stride;
   const StepLayout L = make_layout(J, T, BS, amp_dim, obs_dim, alias_obs);
   float* const w_base = smem + (size_t)warp * L.total;
   float* const s_rslots = w_base;
@@ -388,7 +391,7 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
   const int J = a->lib.num_bodies, T = a->time_steps;
   if (!a->body_state || !a->dof_state || !a->progress || !a->motion_ids || !a->start_times || !a->start_offsets ||
       !a->global_offset || !a->lib.frames_body || !a->lib.motion_len || !a->lib.motion_dt ||
-      !a->lib.motion_num_frames || !a->lib.length_starts || !a->obs || !a->term_thresh ||
+      !a->lib.motion_num_frames || !a->lib.length_starts || !a->obs ||
       (!(a->flags & PHC_FLAG_OBS_ONLY) && (!a->rew || !a->reward_raw || !a->reset || !a->terminate))) {
     phc_set_error("phc_env_step: a required pointer is NULL");
     return PHC_ERR_INVALID_ARG;
@@ -397,10 +400,10 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
     phc_set_error("phc_env_step: bad sizes (num_envs >= 0, 1 <= J <= bodies_per_env, T >= 1)");
     return PHC_ERR_INVALID_ARG;
   }
-  if (J > 32) { phc_set_error("phc_env_step: num_bodies > 32 needs the multi-body-per-lane path (not built yet)"); return PHC_ERR_UNSUPPORTED; }
+  if (J > PHC_MAX_BODIES) { phc_set_error("phc_env_step: num_bodies > 32 needs the multi-body-per-lane path (not built yet)"); return PHC_ERR_UNSUPPORTED; }
   if (T > 4) { phc_set_error("phc_env_step: time_steps > 4 not supported"); return PHC_ERR_UNSUPPORTED; }
   if ((a->flags & PHC_FLAG_POWER_REWARD) && !a->dof_force) { phc_set_error("phc_env_step: power reward needs dof_force"); return PHC_ERR_INVALID_ARG; }
-  if (a->num_key_bodies < 0 || a->num_key_bodies > PHC_MAX_KEY_BODIES || a->num_amp_joints < 0 || (a->num_amp_joints > 0 && !a->amp_joints)) {
+  if (a->num_key_bodies < 0 || a->num_key_bodies > PHC_MAX_KEY_BODIES || a->num_amp_joints < 0 || a->num_amp_joints > PHC_MAX_AMP_JOINTS) {
     phc_set_error("phc_env_step: bad key body / amp joint lists"); return PHC_ERR_INVALID_ARG;
   }
   if (a->lib.body_stride != phc_motion_body_stride(J) || (reinterpret_cast<uintptr_t>(a->lib.frames_body) & 15)) {
@@ -427,20 +430,22 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
   const int grid = (a->num_envs + kWarpsPerCta - 1) / kWarpsPerCta;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-#define PHC_LAUNCH_STEP(TM)                                                                                      \
+#define PHC_LAUNCH_STEP(TM, JJ)                                                                                  \
   do {                                                                                                           \
     static size_t smem_limit = 48 * 1024;     /* default opt-out limit; the attribute is only ever RAISED */      \
     if (smem > smem_limit) {                                                                                     \
-      e = cudaFuncSetAttribute(env_step_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+      e = cudaFuncSetAttribute(env_step_kernel<TM, JJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return phc_check_cuda(e, "cudaFuncSetAttribute(env_step_kernel)");                   \
       smem_limit = smem;                                                                                         \
     }                                                                                                            \
-    env_step_kernel<TM><<<grid, kWarpsPerCta * 32, smem, st>>>(*a, obs_dim, self_dim, amp_dim, alias_obs,        \
-                                                                state_bulk_ok);                                  \
+    env_step_kernel<TM, JJ><<<grid, kWarpsPerCta * 32, smem, st>>>(*a, obs_dim, self_dim, amp_dim, alias_obs,    \
+                                                                    state_bulk_ok);                              \
     phc_count_launches(1);                                                                                       \
   } while (0)
-  if (T == 1) PHC_LAUNCH_STEP(1);
-  else PHC_LAUNCH_STEP(4);
+  if (T == 1 && J == 24) PHC_LAUNCH_STEP(1, 24);          // SMPL
+  else if (T == 1 && J == 20) PHC_LAUNCH_STEP(1, 20);     // H1
+  else if (T == 1) PHC_LAUNCH_STEP(1, 0);
+  else PHC_LAUNCH_STEP(4, 0);
 #undef PHC_LAUNCH_STEP
   return phc_check_cuda(cudaGetLastError(), "env_step_kernel launch");
 }

@@ -136,7 +136,7 @@ struct AmpDemoArgs {
   uint32_t flags;
   int32_t key_bodies[PHC_MAX_KEY_BODIES];
   int32_t num_key_bodies;
-  const int32_t* amp_joints;
+  int32_t amp_joints[PHC_MAX_AMP_JOINTS];
   int32_t num_amp_joints;
   float* out;
   int64_t out_stride;
@@ -295,7 +295,7 @@ extern "C" int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* ids, con
   int rc = check_lib(lib, "phc_amp_obs_demo");
   if (rc) return rc;
   if (!lib->frames_joint) { phc_set_error("phc_amp_obs_demo: needs frames_joint"); return PHC_ERR_INVALID_ARG; }
-  if (!ids || !times0 || !out || n < 0 || num_steps < 1 || nk < 0 || nk > PHC_MAX_KEY_BODIES || nj < 0 || (nj > 0 && !amp_joints) || (nk > 0 && !key_bodies)) {
+  if (!ids || !times0 || !out || n < 0 || num_steps < 1 || nk < 0 || nk > PHC_MAX_KEY_BODIES || nj < 0 || nj > PHC_MAX_AMP_JOINTS || (nj > 0 && !amp_joints) || (nk > 0 && !key_bodies)) {
     phc_set_error("phc_amp_obs_demo: bad arguments"); return PHC_ERR_INVALID_ARG;
   }
   const int A = phc_amp_obs_dim(nj, nk, flags);
@@ -303,7 +303,8 @@ extern "C" int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* ids, con
   if (n == 0) return PHC_OK;
   phc::AmpDemoArgs a;
   a.lib = *lib; a.ids = ids; a.times0 = times0; a.n = n; a.first_step = first_step; a.num_steps = num_steps; a.dt = dt;
-  a.flags = flags; a.num_key_bodies = nk; a.amp_joints = amp_joints; a.num_amp_joints = nj; a.out = out; a.out_stride = out_stride; a.only_where = only_where;
+  a.flags = flags; a.num_key_bodies = nk; a.num_amp_joints = nj;
+  for (int i = 0; i < PHC_MAX_AMP_JOINTS; ++i) a.amp_joints[i] = i < nj ? amp_joints[i] : -1; a.out = out; a.out_stride = out_stride; a.only_where = only_where;
   a.slot_offset = ((slot_offset % num_steps) + num_steps) % num_steps;
   for (int i = 0; i < PHC_MAX_KEY_BODIES; ++i) a.key_bodies[i] = i < nk ? key_bodies[i] : -1;
   const int wpb = 4;

@@ -87,7 +87,8 @@ PHC_HD Q4 quat_about_z(float angle) {
   sin_cos(th, &s, &c);
   float n = sqrtf(s * s + c * c);
   n = n < 1e-9f ? 1e-9f : n;
-  return q4(0.0f, 0.0f, s / n, c / n);
+  const float inv = 1.0f / n;               // one IEEE division shared by both components (n == 1 up to rounding)
+  return q4(0.0f, 0.0f, s * inv, c * inv);
 }
 
 // qrot(h, v) for a quaternion about z (h.x == h.y == 0: the heading quaternions).  Every product with an exact zero and
@@ -145,7 +146,8 @@ PHC_HD V3 quat_to_exp_map(Q4 q) {
 // exp_map_to_quat (exp_map_to_angle_axis then quat_from_angle_axis with both normalisations)
 PHC_HD Q4 exp_map_to_quat(V3 e) {
   const float n0 = sqrtf(e.x * e.x + e.y * e.y + e.z * e.z);
-  V3 ax = v3(e.x / n0, e.y / n0, e.z / n0);
+  const float inv0 = 1.0f / n0;             // shared reciprocals: 3 IEEE divisions in this function instead of 10
+  V3 ax = v3(e.x * inv0, e.y * inv0, e.z * inv0);
   float ang = (n0 <= 6.28318530717958647692f) ? wrap_angle_0_2pi(n0) : wrap_angle(n0);   // joint angles are < 2*pi
   if (!(fabsf(ang) > 1e-5f)) { ang = 0.0f; ax = v3(0.0f, 0.0f, 1.0f); }
   float an = sqrtf(ax.x * ax.x + ax.y * ax.y + ax.z * ax.z);
@@ -153,10 +155,12 @@ PHC_HD Q4 exp_map_to_quat(V3 e) {
   const float th = ang / 2.0f;
   float s, c;
   sin_cos(th, &s, &c);
-  const float x = (ax.x / an) * s, y = (ax.y / an) * s, z = (ax.z / an) * s;
+  const float inva = 1.0f / an;
+  const float x = (ax.x * inva) * s, y = (ax.y * inva) * s, z = (ax.z * inva) * s;
   float qn = sqrtf(x * x + y * y + z * z + c * c);
   qn = qn < 1e-9f ? 1e-9f : qn;
-  return q4(x / qn, y / qn, z / qn, c / qn);
+  const float invq = 1.0f / qn;
+  return q4(x * invq, y * invq, z * invq, c * invq);
 }
 
 PHC_HD Q4 slerp(Q4 q0, Q4 q1, float t) {
@@ -165,8 +169,9 @@ PHC_HD Q4 slerp(Q4 q0, Q4 q1, float t) {
   c = fabsf(c);
   const float half = acosf(c);
   const float s = sqrtf(1.0f - c * c);
-  const float ra = sinf((1.0f - t) * half) / s;
-  const float rb = sinf(t * half) / s;
+  const float inv_s = 1.0f / s;             // one IEEE division for both weights
+  const float ra = sinf((1.0f - t) * half) * inv_s;
+  const float rb = sinf(t * half) * inv_s;
   Q4 r = q4(ra * q0.x + rb * q1.x, ra * q0.y + rb * q1.y, ra * q0.z + rb * q1.z, ra * q0.w + rb * q1.w);
   if (fabsf(s) < 0.001f) r = q4(0.5f * q0.x + 0.5f * q1.x, 0.5f * q0.y + 0.5f * q1.y, 0.5f * q0.z + 0.5f * q1.z, 0.5f * q0.w + 0.5f * q1.w);
   if (fabsf(c) >= 1.0f) r = q0;

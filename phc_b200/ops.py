@@ -243,8 +243,9 @@ class EnvStepPlan:
         rb = list(range(J)) if cfg.reset_bodies is None else [int(b) for b in cfg.reset_bodies]
         thr = torch.full((J,), float("inf"))
         thr[rb] = td[rb]
-        self._term_thresh = thr.to(dev)
-        self._amp_joints = torch.tensor(joints, dtype=torch.int32, device=dev) if joints else None
+        if J > _lib.PHC_MAX_BODIES or len(joints) > _lib.PHC_MAX_AMP_JOINTS:
+            raise PhcError(f"phc_env_step supports at most {_lib.PHC_MAX_BODIES} bodies / {_lib.PHC_MAX_AMP_JOINTS} AMP joints")
+        self._term_thresh = thr
         self._keep = dict(body_state=body_state, dof_state=dof_state, dof_force=dof_force,
                           progress=_req(progress, i64, "progress", dev), motion_ids=_req(motion_ids, i64, "motion_ids", dev),
                           start_times=_req(start_times, f32, "start_times", dev),
@@ -265,11 +266,15 @@ class EnvStepPlan:
         a.k_pos, a.k_rot, a.k_vel, a.k_ang_vel = cfg.k_pos, cfg.k_rot, cfg.k_vel, cfg.k_ang_vel
         a.w_pos, a.w_rot, a.w_vel, a.w_ang_vel = cfg.w_pos, cfg.w_rot, cfg.w_vel, cfg.w_ang_vel
         a.power_coef = cfg.power_coef
-        a.term_thresh, a.term_dist_mean = self._term_thresh.data_ptr(), float(td[rb[0]])
+        for i in range(J):
+            a.term_thresh[i] = float(thr[i])
+        a.term_dist_mean = float(td[rb[0]])
         a.num_key_bodies = len(cfg.key_bodies)
         for i, b in enumerate(cfg.key_bodies):
             a.key_bodies[i] = int(b)
-        a.amp_joints, a.num_amp_joints = _ptr(self._amp_joints), len(joints)
+        for i, jt in enumerate(joints):
+            a.amp_joints[i] = int(jt)
+        a.num_amp_joints = len(joints)
         a.obs, a.obs_stride = self.obs.data_ptr(), self.obs.stride(0)
         a.rew, a.reward_raw, a.reset, a.terminate = self.rew.data_ptr(), self.reward_raw.data_ptr(), self.reset.data_ptr(), self.terminate.data_ptr()
         a.amp_out = _ptr(self.amp_obs_buf)
@@ -311,10 +316,10 @@ def amp_obs_demo(mlib: PackedMotionLib, cfg: EnvStepConfig, motion_ids: torch.Te
         out = _req(out, torch.float32, "out", dev)
         assert out.shape[0] == n and out.shape[-1] == A and out.stride(0) >= S * A
     kb = (C.c_int32 * len(cfg.key_bodies))(*[int(b) for b in cfg.key_bodies])
-    aj = torch.tensor(joints, dtype=torch.int32, device=dev)
+    aj = (C.c_int32 * max(1, len(joints)))(*[int(j) for j in joints])
     with torch.cuda.device(dev):
         _lib.check(lib.phc_amp_obs_demo(C.byref(mlib.c), ids.data_ptr(), t0.data_ptr(), n, first_step, S, cfg.dt,
-                                        cfg.flags(), C.cast(kb, C.c_void_p), len(cfg.key_bodies), aj.data_ptr(),
+                                        cfg.flags(), C.cast(kb, C.c_void_p), len(cfg.key_bodies), C.cast(aj, C.c_void_p),
                                         len(joints), out.data_ptr(), out.stride(0),
                                         None if only_where is None else _req(only_where, torch.int64, "only_where", dev).data_ptr(),
                                         int(slot_offset), _stream()), "phc_amp_obs_demo")
