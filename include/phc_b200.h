@@ -61,6 +61,18 @@ typedef struct PhcMotionLib {
   int32_t joint_stride; /* floats per joint record = round_up(4*J + 3*(J-1), 4)  */
 } PhcMotionLib;
 
+/* Per-env copy of the motion parameters the step needs, gathered once by phc_env_motion_gather whenever motion_ids change
+ * (HumanoidIm re-samples clips every `shape_resampling_interval` epochs, amp_agent.py:509-515): one 16-byte load per env
+ * instead of motion_ids -> 4 dependent table look-ups on the per-step critical path. */
+typedef struct PhcEnvMotion {
+  float len;         /* _motion_lengths[motion_ids[e]]     */
+  float dt;          /* _motion_dt[motion_ids[e]]          */
+  int32_t num_frames;/* _motion_num_frames[motion_ids[e]]  */
+  int32_t start_row; /* length_starts[motion_ids[e]]       */
+} PhcEnvMotion;
+
+PHC_API int phc_env_motion_gather(const PhcMotionLib* lib, const int64_t* motion_ids, int64_t n, PhcEnvMotion* out, void* stream);
+
 PHC_API int phc_motion_body_stride(int32_t num_bodies);
 PHC_API int phc_motion_joint_stride(int32_t num_bodies);
 
@@ -125,6 +137,7 @@ typedef struct PhcStepArgs {
   /* ---- per-env motion bookkeeping ---- */
   const int64_t* progress;       /* [N] progress_buf                    */
   const int64_t* motion_ids;     /* [N] _sampled_motion_ids             */
+  const PhcEnvMotion* env_motion;/* [N] optional pre-gathered parameters of motion_ids (phc_env_motion_gather); NULL = look up */
   const float* start_times;      /* [N] _motion_start_times             */
   const float* start_offsets;    /* [N] _motion_start_times_offset      */
   const float* global_offset;    /* [N,3] _global_offset                */

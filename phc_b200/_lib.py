@@ -45,7 +45,7 @@ class PhcMotionStateOut(C.Structure):
 class PhcStepArgs(C.Structure):
     _fields_ = [
         ("body_state", _p), ("dof_state", _p), ("dof_force", _p), ("bodies_per_env", C.c_int32),
-        ("progress", _p), ("motion_ids", _p), ("start_times", _p), ("start_offsets", _p), ("global_offset", _p),
+        ("progress", _p), ("motion_ids", _p), ("env_motion", _p), ("start_times", _p), ("start_offsets", _p), ("global_offset", _p),
         ("cycle_counter", _p), ("only_where", _p), ("lib", PhcMotionLib),
         ("num_envs", C.c_int32), ("time_steps", C.c_int32), ("dt", C.c_float), ("traj_dt", C.c_float),
         ("flags", C.c_uint32),
@@ -66,6 +66,7 @@ SIGNATURES = {
     "phc_last_error": (C.c_char_p, []),
     "phc_compiled_sm": (C.c_int, []),
     "phc_launch_count": (C.c_int64, []),
+    "phc_env_motion_gather": (C.c_int, [C.POINTER(PhcMotionLib), _p, C.c_int64, _p, _p]),
     "phc_motion_body_stride": (C.c_int, [C.c_int32]),
     "phc_motion_joint_stride": (C.c_int, [C.c_int32]),
     "phc_motion_pack": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int64, C.c_int32, _p, _p, _p]),

@@ -106,13 +106,30 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   }
   __syncwarp();
 
-  // ---- per-env scalars (warp-uniform broadcast loads) and the frame brackets -------------------------------
+  // ---- every load that depends only on the env index is issued first (one DRAM round trip for all of them) ----------
+  const float2* g_dof = reinterpret_cast<const float2*>(a.dof_state) + (size_t)env * D;
+  const float* g_force = a.dof_force ? a.dof_force + (size_t)env * D : nullptr;
+  float2 dof_pv[3];                                   // D <= 93 for J <= 32: at most 3 dofs per lane
+  float dof_f[3];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int d = lane + 32 * u;
+    dof_pv[u] = (d < D) ? g_dof[d] : make_float2(0.f, 0.f);
+    dof_f[u] = (g_force && d < D) ? g_force[d] : 0.f;
+  }
   const int64_t progress = a.progress[env];
-  const int64_t mid = a.motion_ids[env];
   const float t_start = a.start_times[env], t_off = a.start_offsets[env];
   const V3 goff = v3(a.global_offset[3 * env + 0], a.global_offset[3 * env + 1], a.global_offset[3 * env + 2]);
-  const float m_len = a.lib.motion_len[mid], m_dt = a.lib.motion_dt[mid];
-  const int64_t m_nf = a.lib.motion_num_frames[mid], m_start = a.lib.length_starts[mid];
+  float m_len, m_dt;
+  int64_t m_nf, m_start;
+  if (a.env_motion) {                                 // pre-gathered per-env record: no motion_ids -> table dependency
+    const int4 em = *reinterpret_cast<const int4*>(a.env_motion + env);
+    m_len = __int_as_float(em.x); m_dt = __int_as_float(em.y); m_nf = em.z; m_start = em.w;
+  } else {
+    const int64_t mid = a.motion_ids[env];
+    m_len = a.lib.motion_len[mid]; m_dt = a.lib.motion_dt[mid];
+    m_nf = a.lib.motion_num_frames[mid]; m_start = a.lib.length_starts[mid];
+  }
 
   // reward / reset use the CURRENT motion time (humanoid_im.py:879), observations the NEXT one (:752)
   const float t_now = (float)progress * a.dt + t_start + t_off;
@@ -192,14 +209,13 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
 
   // ---- while the copies fly: dof state / force (power reward + AMP joint inputs) ---------------------------
   float power = 0.0f;
-  {
-    const float2* g_dof = reinterpret_cast<const float2*>(a.dof_state) + (size_t)env * D;
-    const float* g_force = a.dof_force ? a.dof_force + (size_t)env * D : nullptr;
-    for (int d = lane; d < D; d += 32) {
-      const float2 pv = g_dof[d];
-      s_dof[2 * d] = pv.x;
-      s_dof[2 * d + 1] = pv.y;
-      if (g_force) power += fabsf(g_force[d] * pv.y);
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int d = lane + 32 * u;
+    if (d < D) {
+      s_dof[2 * d] = dof_pv[u].x;
+      s_dof[2 * d + 1] = dof_pv[u].y;
+      power += fabsf(dof_f[u] * dof_pv[u].y);
     }
   }
   __syncwarp();
@@ -349,6 +365,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     if (((a.obs_stride | (int64_t)obs_dim) & 1) == 0) {          // rows 8-byte aligned: float2 stores
       float2* g2 = reinterpret_cast<float2*>(g);
       const float2* s2 = reinterpret_cast<const float2*>(s_obs);
+#pragma unroll 5
       for (int i = lane; i < obs_dim / 2; i += 32) g2[i] = s2[i];
     } else {
       for (int i = lane; i < obs_dim; i += 32) g[i] = s_obs[i];
@@ -363,6 +380,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
       for (int s = a.amp_steps - 2; s >= 0; --s)
         for (int i = lane; i < amp_dim; i += 32) g[(size_t)(s + 1) * amp_dim + i] = h[(size_t)s * amp_dim + i];
     }
+#pragma unroll 7
     for (int i = lane; i < amp_dim; i += 32) g[i] = s_amp[i];
   }
 }
@@ -410,6 +428,7 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
     phc_set_error("phc_env_step: frames_body must be 16-byte aligned with body_stride = round_up(13*J,4) (use phc_motion_pack)");
     return PHC_ERR_INVALID_ARG;
   }
+  if (a->env_motion && (reinterpret_cast<uintptr_t>(a->env_motion) & 15)) { phc_set_error("phc_env_step: env_motion must be 16-byte aligned"); return PHC_ERR_INVALID_ARG; }
   if (reinterpret_cast<uintptr_t>(a->dof_state) & 7) { phc_set_error("phc_env_step: dof_state must be 8-byte aligned"); return PHC_ERR_INVALID_ARG; }
   const int self_dim = phc_self_obs_dim(J, a->flags);
   const int obs_dim = self_dim + phc_task_obs_dim(J, T);

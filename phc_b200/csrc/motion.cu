@@ -189,6 +189,17 @@ __global__ void __launch_bounds__(128) amp_demo_kernel(const __grid_constant__ A
     if (a.key_bodies[kk] == lane) st3g(o + 12 + 9 * nj + 3 * kk, qrot_z(hinv, s.body.p - r.p));
 }
 
+__global__ void env_motion_gather_kernel(const __grid_constant__ PhcMotionLib lib, const int64_t* __restrict__ ids, int64_t n,
+                                         PhcEnvMotion* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t m = ids[i];
+  PhcEnvMotion e;
+  e.len = lib.motion_len[m]; e.dt = lib.motion_dt[m];
+  e.num_frames = (int32_t)lib.motion_num_frames[m]; e.start_row = (int32_t)lib.length_starts[m];
+  out[i] = e;
+}
+
 // Reset path: write the reference pose at (id, time) of every env with mask != 0 into the simulator tensors
 // (HumanoidAMP._set_env_state, humanoid_amp.py:605-637: rigid-body rows + dof pos/vel), warp per env.
 __global__ void __launch_bounds__(128)
@@ -338,4 +349,14 @@ extern "C" int phc_amp_window_export(const float* ring, int64_t ring_stride, int
   int64_t g = (n * num_steps * amp_dim / 4 + 255) / 256; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1;
   phc::amp_window_export_kernel<<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(ring, ring_stride, n, num_steps, amp_dim, head, out, out_stride); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "amp_window_export_kernel launch");
+}
+
+extern "C" int phc_env_motion_gather(const PhcMotionLib* lib, const int64_t* ids, int64_t n, PhcEnvMotion* out, void* stream) {
+  int rc = check_lib(lib, "phc_env_motion_gather");
+  if (rc) return rc;
+  if (!ids || !out || n < 0 || (reinterpret_cast<uintptr_t>(out) & 15)) { phc_set_error("phc_env_motion_gather: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  if (lib->num_frames_total >= (int64_t)1 << 31) { phc_set_error("phc_env_motion_gather: frame table too large for 32-bit rows"); return PHC_ERR_UNSUPPORTED; }
+  if (n == 0) return PHC_OK;
+  phc::env_motion_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*lib, ids, n, out); phc_count_launches(1);
+  return phc_check_cuda(cudaGetLastError(), "env_motion_gather_kernel launch");
 }

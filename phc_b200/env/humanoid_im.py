@@ -265,7 +265,9 @@ class HumanoidIm:
         return self.obs_buf
 
     def resample_motions(self):
-        return
+        """After `_sampled_motion_ids` changed: refresh the per-env motion parameter records of both launch plans."""
+        self._plan.refresh_motion_params()
+        self._plan_reset_obs.refresh_motion_params()
 
     # ---- discriminator demo observations ------------------------------------------------------------------------
     def fetch_amp_obs_demo(self, num_samples: int) -> torch.Tensor:

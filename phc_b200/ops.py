@@ -257,6 +257,8 @@ class EnvStepPlan:
         a = _lib.PhcStepArgs()
         a.body_state, a.dof_state, a.dof_force, a.bodies_per_env = body_state.data_ptr(), dof_state.data_ptr(), _ptr(dof_force if cfg.power_reward else None), bpe
         a.progress, a.motion_ids = k["progress"].data_ptr(), k["motion_ids"].data_ptr()
+        self._env_motion = torch.zeros(N, 4, dtype=torch.int32, device=dev)      # PhcEnvMotion records (16 B each)
+        a.env_motion = self._env_motion.data_ptr()
         a.start_times, a.start_offsets, a.global_offset = k["start_times"].data_ptr(), k["start_offsets"].data_ptr(), k["global_offset"].data_ptr()
         a.cycle_counter = _ptr(k["cycle_counter"])
         k["only_where"] = None if only_where is None else _req(only_where, i64, "only_where", dev)
@@ -284,6 +286,12 @@ class EnvStepPlan:
         a.ref_body_vel, a.ref_body_ang_vel = _ptr(self.ref_body_vel), _ptr(self.ref_body_ang_vel)
         self.args = a
         self._args_ref = C.byref(a)
+        self.refresh_motion_params()
+
+    def refresh_motion_params(self) -> None:
+        """Re-gather the per-env motion parameters; call whenever `motion_ids` (HumanoidIm._sampled_motion_ids) changes."""
+        _lib.check(self._lib.phc_env_motion_gather(C.byref(self.mlib.c), self._keep["motion_ids"].data_ptr(), self.N,
+                                                   self._env_motion.data_ptr(), _stream()), "phc_env_motion_gather")
 
     def advance_ring(self) -> int:
         """Move the ring head one slot back (the slot that will receive this step's AMP vector) and re-point amp_out."""
