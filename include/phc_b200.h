@@ -295,6 +295,13 @@ PHC_API int phc_scale_sumsq(float* x, int64_t ld, int64_t n, int32_t d, float al
 /* y += alpha*x on a strided block; optional stat += sum x^2   (logit regulariser / weight decay, :745-747,:771-775) */
 PHC_API int phc_axpy2d(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int32_t cols, float alpha,
                float* sumsq_stat, void* stream);
+/* HumanoidImMCP.step action mixing (phc/env/tasks/humanoid_im_mcp.py:79-82): out[n,a] = sum_k weights[n,k] * prim_k[n,a];
+ * the K primitive outputs are matrices with row stride ldp placed prim_stride floats apart.
+ * discrete != 0: weights are replaced by the one-hot of their arg-max (discrete_moe, humanoid_im_mcp.py:70-72). */
+PHC_API int phc_mcp_combine(const float* weights, int64_t ldw, const float* prim, int64_t ldp, int64_t prim_stride, int64_t n,
+                    int32_t K, int32_t A, int32_t discrete, float* out, int64_t ldo, void* stream);
+/* dy *= (y > 0): backward of the ReLU that ends the MCP composer (amp_network_mcp_builder.py:57-63, ending_act: True) */
+PHC_API int phc_relu_backward(float* dy, int64_t ldd, const float* y, int64_t ldy, int64_t n, int32_t d, void* stream);
 /* out[0] = sum g^2 (fp64) over the flat gradient bucket */
 PHC_API int phc_grad_sumsq(const float* g, int64_t n, double* out, void* stream);
 /* nn.utils.clip_grad_norm_(max_norm) (amp_agent.py:670,677) + torch.optim.Adam step (common_agent.py:67) fused over

@@ -321,6 +321,38 @@ __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict_
   }
 }
 
+// HumanoidImMCP.step (phc/env/tasks/humanoid_im_mcp.py:79-82): actions[n, a] = sum_k weights[n, k] * prim[k][n, a]
+// prim: K activation matrices with a common row stride, stacked `prim_stride` floats apart.
+__global__ void mcp_combine_kernel(const float* __restrict__ w, int64_t ldw, const float* __restrict__ prim, int64_t ldp,
+                                   int64_t prim_stride, int64_t n, int K, int A, int discrete, float* __restrict__ out, int64_t ldo) {
+  const int64_t total = n * A;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / A;
+    const int c = (int)(i - r * A);
+    float acc = 0.f;
+    if (discrete) {      // discrete_moe (humanoid_im_mcp.py:70-72): one-hot of the first arg-max weight
+      int best = 0;
+      float bw = w[r * ldw];
+      for (int k = 1; k < K; ++k) { const float v = w[r * ldw + k]; if (v > bw) { bw = v; best = k; } }
+      for (int k = 0; k < K; ++k) acc = __fadd_rn(acc, __fmul_rn(k == best ? 1.f : 0.f, prim[k * prim_stride + r * ldp + c]));
+    } else {
+      for (int k = 0; k < K; ++k)      // product rounded, then added: the reference's weights[:, :, None] * x_all followed by sum(dim=1)
+        acc = __fadd_rn(acc, __fmul_rn(w[r * ldw + k], prim[k * prim_stride + r * ldp + c]));
+    }
+    out[r * ldo + c] = acc;
+  }
+}
+
+// dy[r, c] = y[r, c] > 0 ? dy[r, c] : 0     (ReLU that ends the MCP composer, amp_network_mcp_builder.py:57-63)
+__global__ void relu_backward_kernel(float* __restrict__ dy, int64_t ldd, const float* __restrict__ y, int64_t ldy, int64_t n, int d) {
+  const int64_t total = n * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / d;
+    const int c = (int)(i - r * d);
+    if (!(y[r * ldy + c] > 0.f)) dy[r * ldd + c] = 0.f;
+  }
+}
+
 static inline int ew_grid(int64_t total, int block = 256) {
   int64_t g = (total + block - 1) / block;
   if (g > 148 * 8) g = 148 * 8;
@@ -441,4 +473,19 @@ extern "C" int phc_adam_step(float* params, const float* grads, float* exp_avg, 
   adam_clip_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, grad_sumsq, grad_scale, max_norm, lr,
                                                        beta1, beta2, eps, (float)bc1, (float)sqrt(bc2)); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "adam_clip_kernel");
+}
+
+extern "C" int phc_mcp_combine(const float* weights, int64_t ldw, const float* prim, int64_t ldp, int64_t prim_stride, int64_t n,
+                               int32_t K, int32_t A, int32_t discrete, float* out, int64_t ldo, void* stream) {
+  if (n == 0) return PHC_OK;                       // empty batch: nothing to validate, nothing to launch
+  if (!weights || !prim || !out || n < 0 || K < 1 || A < 1 || ldw < K || ldp < A || ldo < A) { phc_set_error("phc_mcp_combine: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  mcp_combine_kernel<<<ew_grid(n * A), 256, 0, ST(stream)>>>(weights, ldw, prim, ldp, prim_stride, n, K, A, discrete, out, ldo); phc_count_launches(1);
+  return phc_check_cuda(cudaGetLastError(), "mcp_combine_kernel");
+}
+
+extern "C" int phc_relu_backward(float* dy, int64_t ldd, const float* y, int64_t ldy, int64_t n, int32_t d, void* stream) {
+  if (!dy || !y || n < 0 || d < 1 || ldd < d || ldy < d) { phc_set_error("phc_relu_backward: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  if (n == 0) return PHC_OK;
+  relu_backward_kernel<<<ew_grid(n * d), 256, 0, ST(stream)>>>(dy, ldd, y, ldy, n, d); phc_count_launches(1);
+  return phc_check_cuda(cudaGetLastError(), "relu_backward_kernel");
 }

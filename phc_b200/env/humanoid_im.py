@@ -171,7 +171,12 @@ class HumanoidIm:
         return self._num_amp_obs_steps * self._num_amp_obs_per_step
 
     def get_task_obs_size_detail(self):
-        return [("target", self._plan.task_dim)]
+        """humanoid_im.py:522-537: what the network builders read from the task."""
+        env = self.cfg.get("env", self.cfg)
+        return {"target": self._plan.task_dim, "fut_tracks": False, "num_traj_samples": 1, "obs_v": env.get("obs_v", 6),
+                "models_path": env.get("models", []), "num_prim": env.get("num_prim", 2),
+                "training_prim": env.get("training_prim", 1), "actors_to_load": env.get("actors_to_load", 2),
+                "has_lateral": env.get("has_lateral", True)}
 
     def get_running_mean_size(self):
         return (self.get_obs_size(),)

@@ -177,6 +177,13 @@ class ReplayBuffer:
         return rand_idx
 
 
+def task_detail(task, key: str, default: int) -> int:
+    """AMPPNNBuilder / AMPMCPBuilder read num_prim / training_prim from the task's obs-size detail
+    (amp_network_pnn_builder.py:33-36, amp_network_mcp_builder.py:40)."""
+    fn = getattr(task, "get_task_obs_size_detail", None)
+    return int(fn().get(key, default)) if fn is not None else default
+
+
 class AMPAgent:
     def __init__(self, base_name: str, config: Dict):
         cfg = copy.deepcopy(DEFAULT_CONFIG)
@@ -231,7 +238,10 @@ class AMPAgent:
         netcfg = cfg["network"]
         self.model = AMPNetwork(self.obs_dim, self.actions_num, self.amp_obs_dim, netcfg["mlp"]["units"],
                                 netcfg["disc"]["units"], netcfg["mlp"]["activation"], netcfg.get("sigma_init", -2.9),
-                                device=self.device, seed=int(cfg["seed"]))
+                                device=self.device, seed=int(cfg["seed"]),
+                                # network.name of the yaml: amp (im.yaml), amp_pnn (im_pnn.yaml), amp_mcp (im_mcp.yaml)
+                                kind=netcfg.get("name", "amp"), num_prim=int(netcfg.get("num_prim", task_detail(task, "num_prim", 4))),
+                                training_prim=int(netcfg.get("training_prim", task_detail(task, "training_prim", 0))))
         if self.multi_gpu:
             D.broadcast_params(self.model.params, 0)
         self.engine = MLPEngine(self.model)

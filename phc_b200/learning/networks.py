@@ -44,7 +44,7 @@ class LinearSpec:
 class MLPStack:
     """One MLP = hidden Linear+act layers followed by a linear head."""
 
-    def __init__(self, prefix: str, head: str, in_dim: int, units: Sequence[int], out_dim: int):
+    def __init__(self, prefix: str, head: str, in_dim: int, units: Sequence[int], out_dim: int, head_relu: bool = False):
         self.layers: List[LinearSpec] = []
         d = in_dim
         for i, u in enumerate(units):
@@ -52,6 +52,7 @@ class MLPStack:
             d = u
         self.layers.append(LinearSpec(head, d, out_dim))
         self.in_dim, self.out_dim = in_dim, out_dim
+        self.head_relu = head_relu          # MCP composer: the last Linear is followed by the activation too (ending_act)
 
     @property
     def hidden(self) -> List[LinearSpec]:
@@ -67,16 +68,33 @@ class AMPNetwork:
 
     def __init__(self, obs_dim: int, action_dim: int, amp_dim: int, units: Sequence[int] = (1024, 512),
                  disc_units: Sequence[int] = (1024, 512), activation: str = "relu", sigma_init: float = -2.9,
-                 device="cuda:0", seed: int = 0):
+                 device="cuda:0", seed: int = 0, kind: str = "amp", num_prim: int = 4, training_prim: int = 0):
+        """kind: 'amp' (AMPBuilder, actor_mlp + mu), 'amp_pnn' (AMPPNNBuilder: `num_prim` independent actor columns
+        `pnn.actors.K`, column `training_prim` is the one evaluated / trained -- pnn.py:11-131, amp_network_pnn_builder.py:23-87)
+        or 'amp_mcp' (AMPMCPBuilder: `composer` MLP whose `action_dim` = num_prim outputs keep the final ReLU --
+        amp_network_mcp_builder.py:23-91)."""
         if activation != "relu":
             raise NotImplementedError("only the relu MLPs of im.yaml are built so far (silu of im_big.yaml: next)")
+        assert kind in ("amp", "amp_pnn", "amp_mcp")
         self.device = torch.device(device)
+        self.kind, self.num_prim, self.training_prim = kind, num_prim, training_prim
         self.obs_dim, self.action_dim, self.amp_dim = obs_dim, action_dim, amp_dim
-        self.actor = MLPStack("actor_mlp", "mu", obs_dim, units, action_dim)
+        n_h = len(units)
+        if kind == "amp_pnn":
+            self.pnn_actors = [MLPStack(f"pnn.actors.{k}", f"pnn.actors.{k}.{2 * n_h}", obs_dim, units, action_dim) for k in range(num_prim)]
+            self.actor = self.pnn_actors[training_prim]
+            actor_stacks = self.pnn_actors
+        elif kind == "amp_mcp":
+            st = MLPStack("composer", f"composer.{2 * n_h}", obs_dim, units, action_dim, head_relu=True)
+            self.actor, actor_stacks = st, [st]
+        else:
+            self.actor = MLPStack("actor_mlp", "mu", obs_dim, units, action_dim)
+            actor_stacks = [self.actor]
+        self.actor_stacks = actor_stacks
         self.critic = MLPStack("critic_mlp", "value", obs_dim, units, 1)
         self.disc = MLPStack("_disc_mlp", "_disc_logits", amp_dim, disc_units, 1)
         off = 0
-        for st in (self.actor, self.critic, self.disc):
+        for st in (*actor_stacks, self.critic, self.disc):
             for l in st.layers:
                 l.w_off = off
                 off += l.out_dim * l.in_pad
@@ -107,12 +125,19 @@ class AMPNetwork:
         return buf[l.b_off:l.b_off + l.out_dim]
 
     def all_layers(self) -> List[LinearSpec]:
-        return self.actor.layers + self.critic.layers + self.disc.layers
+        return [l for st in self.actor_stacks for l in st.layers] + self.critic.layers + self.disc.layers
+
+    def load_actor_column(self, checkpoint_model: Dict[str, torch.Tensor], idx: int = 0) -> None:
+        """PNN.load_actor (pnn.py:53-60): copy a single-policy checkpoint (actor_mlp.* / mu.*) into primitive column idx."""
+        col = self.pnn_actors[idx]
+        names = [f"a2c_network.actor_mlp.{2 * i}" for i in range(len(col.hidden))] + ["a2c_network.mu"]
+        for l, n in zip(col.layers, names):
+            self.set_layer(l, checkpoint_model[n + ".weight"], checkpoint_model[n + ".bias"])
 
     # ---- init: PyTorch's default nn.Linear init (`initializer: default`), disc biases zero, logits U(-1, 1) --------
     def _init_default(self, seed: int) -> None:
         g = torch.Generator().manual_seed(seed)
-        for st in (self.actor, self.critic, self.disc):
+        for st in (*self.actor_stacks, self.critic, self.disc):
             for l in st.layers:
                 bound = 1.0 / math.sqrt(l.in_dim)
                 w = (torch.rand(l.out_dim, l.in_dim, generator=g) * 2 - 1) * bound     # kaiming_uniform(a=sqrt(5))
@@ -255,7 +280,8 @@ class MLPEngine:
             ws["h_split"].append(cur_split)
             cur = h
         l = st.head
-        self.gemm(cur, True, net.weight(l), True, ws["out"], B, l.out_dim, l.in_dim, bias=net.bias(l), a_split=cur_split)
+        self.gemm(cur, True, net.weight(l), True, ws["out"], B, l.out_dim, l.in_dim, bias=net.bias(l), a_split=cur_split,
+                  relu=st.head_relu)
         return ws["out"]
 
     # -- backward: ws["dout"] holds d(loss)/d(out) [B, round4(out)]; accumulates into net.grads --------------------
@@ -265,6 +291,10 @@ class MLPEngine:
         acts = [x] + ws["h"]
         act_splits = ([ws.get("x_split")] + list(ws.get("h_split", []))) if tc5 else [None] * len(acts)
         dcur = ws["dout"]
+        if st.head_relu:                                    # MCP composer: ReLU after the head (ending_act)
+            rc = self.lib.phc_relu_backward(dcur.data_ptr(), dcur.stride(0), ws["out"].data_ptr(), ws["out"].stride(0), B, st.out_dim, _stream())
+            if rc:
+                _lib.check(rc, "phc_relu_backward")
         dsplit = self.split(dcur) if tc5 else None          # the loss kernels wrote dout: split it once for both GEMMs
         for li in range(len(st.layers) - 1, -1, -1):
             l = st.layers[li]

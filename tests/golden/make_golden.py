@@ -12,6 +12,9 @@ What is executed on the reference side (no restatement involved):
                HumanoidAMP._update_hist_amp_obs / _compute_amp_observations / build_amp_obs_demo, called as bound
                methods of an instance created with object.__new__ (no Isaac Gym) -- humanoid_im.py:694-948,
                :1117-1190, humanoid_amp.py:253-284,:662-707
+  mcp.npz      PNN.__init__/forward/load_actor/freeze_pnn (phc/learning/pnn.py), load_pnn / load_mcp_mlp
+               (phc/learning/network_loader.py:11-73) and HumanoidImMCP.step (phc/env/tasks/humanoid_im_mcp.py:56-90) with the
+               three simulator hooks replaced by recorders
   learn.npz    CommonAgent.discount_values/_calc_advs/_actor_loss/_critic_loss/bound_loss,
                AMPAgent._disc_loss/_calc_disc_rewards/_combine_rewards, RunningMeanStd.forward
 """
@@ -332,7 +335,77 @@ def gen_learn():
     save("learn.npz", d)
 
 
+def gen_mcp():
+    from phc.learning.pnn import PNN
+    from phc.learning.network_loader import load_pnn, load_mcp_mlp
+    from phc.env.tasks.humanoid_im_mcp import HumanoidImMCP
+    torch.manual_seed(23)
+    obs_dim, units, act_dim, K, N = 40, [48, 32], 12, 3, 64
+    d = dict(obs_dim=np.int64(obs_dim), units=np.array(units), act_dim=np.int64(act_dim), num_prim=np.int64(K))
+    mlp_args = {'input_size': obs_dim, 'units': units, 'activation': "relu", 'dense_func': torch.nn.Linear}
+    pnn = PNN(mlp_args, output_size=act_dim, numCols=K, has_lateral=False)
+    with torch.no_grad():
+        for p in pnn.parameters():                         # PNN's default init leaves biases at their Linear defaults; spread them
+            p.add_(0.05 * torch.randn_like(p))
+    # a single-policy checkpoint folded into column 1 by the reference's own loader (pnn.py:53-60)
+    single = {"a2c_network.actor_mlp.0.weight": torch.randn(units[0], obs_dim) * 0.2, "a2c_network.actor_mlp.0.bias": torch.randn(units[0]) * 0.1,
+              "a2c_network.actor_mlp.2.weight": torch.randn(units[1], units[0]) * 0.2, "a2c_network.actor_mlp.2.bias": torch.randn(units[1]) * 0.1,
+              "a2c_network.mu.weight": torch.randn(act_dim, units[1]) * 0.2, "a2c_network.mu.bias": torch.randn(act_dim) * 0.1}
+    pnn.load_actor({"model": single}, idx=1)
+    for k, v in single.items():
+        d["single/" + k] = v
+    sd = {"a2c_network.pnn." + k: v.clone() for k, v in pnn.state_dict().items()}
+    sd["a2c_network.mu.bias"] = torch.zeros(act_dim)       # load_pnn reads the action width from this key
+    for k, v in sd.items():
+        d["model/" + k] = v
+    x = torch.randn(N, obs_dim)
+    d["x"] = x
+    with torch.no_grad():
+        for k in range(K):
+            _, a = pnn(x, idx=k)
+            d[f"col{k}"] = a
+        _, allc = pnn(x)
+        d["all"] = torch.stack(allc, dim=0)
+    # freeze_pnn(idx): which parameters stay trainable when training column idx (pnn.py:45-51)
+    pnn.freeze_pnn(1)
+    d["trainable_after_freeze1"] = np.array([int(p.requires_grad) for _, p in pnn.named_parameters()])
+    d["param_names"] = np.array([n for n, _ in pnn.named_parameters()])
+
+    # HumanoidImMCP.step with recorders for the simulator hooks
+    rms = {"running_mean": torch.randn(obs_dim, dtype=torch.float64) * 0.3, "running_var": torch.rand(obs_dim, dtype=torch.float64) + 0.2}
+    ck = {"model": sd, "running_mean_std": rms}
+    env = object.__new__(HumanoidImMCP)
+    env.device = torch.device("cpu")
+    env.num_prim, env.has_pnn, env.mlp_bypass = K, True, False
+    env.pnn = load_pnn(ck, num_prim=K, has_lateral=False, activation="relu", device="cpu")
+    env.running_mean, env.running_var = rms["running_mean"], rms["running_var"]
+    env.obs_buf = torch.randn(N, obs_dim) * 2.5            # wide enough that the +-5 clamp bites on some entries
+    got = {}
+    env.pre_physics_step = lambda a: got.__setitem__("actions", a.clone())
+    env._physics_step = lambda: None
+    env.post_physics_step = lambda: None
+    env.dr_randomizations = {}
+    weights = torch.relu(torch.randn(N, K))                # composer output ends in a ReLU
+    d["rms_mean"], d["rms_var"], d["obs_buf"], d["weights"] = rms["running_mean"], rms["running_var"], env.obs_buf, weights
+    for disc in (False, True):
+        env.discrete_mcp = disc
+        env.step(weights)
+        d["actions_discrete" if disc else "actions"] = got["actions"]
+
+    # composer (amp_network_mcp_builder.py:57-63) rebuilt by the reference's own loader: ReLU after the last Linear
+    comp = {"a2c_network.composer.0.weight": torch.randn(units[0], obs_dim) * 0.2, "a2c_network.composer.0.bias": torch.randn(units[0]) * 0.1,
+            "a2c_network.composer.2.weight": torch.randn(units[1], units[0]) * 0.2, "a2c_network.composer.2.bias": torch.randn(units[1]) * 0.1,
+            "a2c_network.composer.4.weight": torch.randn(K, units[1]) * 0.3, "a2c_network.composer.4.bias": torch.randn(K) * 0.1}
+    mlp = load_mcp_mlp({"model": comp}, activation="relu", device="cpu", mlp_name="composer")
+    for k, v in comp.items():
+        d["composer/" + k] = v
+    with torch.no_grad():
+        d["composer_out"] = mlp(x)
+    save("mcp.npz", d)
+
+
 if __name__ == "__main__":
+    gen_mcp()
     gen_quat()
     gen_motion()
     gen_envstep()

@@ -50,6 +50,26 @@ class _StubModule(types.ModuleType):
         return MagicMock(name=self.__name__ + "()")
 
 
+class ObjectFactory:
+    """rl_games==1.1.4 rl_games/common/object_factory.py (third-party, absent here): a name -> builder registry.
+    The reference's network_builder.BaseNetwork registers activations / initialisers in it and `create`s them by name."""
+
+    def __init__(self):
+        self._builders = {}
+
+    def register_builder(self, name, builder):
+        self._builders[name] = builder
+
+    def set_builders(self, builders):
+        self._builders = builders
+
+    def create(self, name, **kwargs):
+        builder = self._builders.get(name)
+        if not builder:
+            raise ValueError(name)
+        return builder(**kwargs)
+
+
 class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
     def find_spec(self, fullname, path, target=None):
         root = fullname.split(".")[0]
@@ -78,6 +98,8 @@ def install():
     sys.modules["isaacgym.torch_utils"] = real
     ig = importlib.import_module("isaacgym")
     ig.torch_utils = real
+    of = importlib.import_module("rl_games.common.object_factory")
+    of.ObjectFactory = ObjectFactory
     # the reference sets the legacy TorchScript executor (phc/env/tasks/base_task.py:95-96)
     torch._C._jit_set_profiling_mode(False)
     torch._C._jit_set_profiling_executor(False)

@@ -1,6 +1,7 @@
 """Pin oracle/phc_oracle.py against the golden vectors produced by the UNMODIFIED reference
 (tests/golden/make_golden.py).  CPU only.  Tolerance: rtol 1e-5 / atol 1e-6 fp32 (north_star), except where a
 comment says otherwise (ill-conditioned acos near identity -- SURVEY.md section 7)."""
+import numpy as np
 import torch
 
 from oracle import phc_oracle as O
@@ -146,3 +147,53 @@ def test_gaussian_pieces_self_pinned():
     mu_old = mu + 0.05
     kl = torch.distributions.kl_divergence(torch.distributions.Normal(mu, s_new), torch.distributions.Normal(mu_old, s_old)).sum(-1).mean()
     close(O.policy_kl(mu, s_new, mu_old, s_old), kl, rtol=1e-3, atol=1e-3, what="policy_kl")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# PNN / MCP (row a19): oracle/mcp_oracle.py against the real PNN / load_pnn / load_mcp_mlp / HumanoidImMCP.step
+# ------------------------------------------------------------------------------------------------------------------
+def _mcp():
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "mcp.npz"))
+    g = {k: z[k] for k in z.files}
+    sd = {k[len("model/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("model/")}
+    return g, sd
+
+
+def test_pnn_forward_matches_reference():
+    from oracle import mcp_oracle as mo
+    g, sd = _mcp()
+    K = int(g["num_prim"])
+    x = torch.from_numpy(g["x"])
+    for k in range(K):
+        torch.testing.assert_close(mo.pnn_forward(sd, x, K, idx=k), torch.from_numpy(g[f"col{k}"])[0], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(torch.stack(mo.pnn_forward(sd, x, K), 0), torch.from_numpy(g["all"]), rtol=1e-6, atol=1e-6)
+
+
+def test_pnn_load_actor_and_freeze_match_reference():
+    from oracle import mcp_oracle as mo
+    g, sd = _mcp()
+    single = {k[len("single/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("single/")}
+    for k, v in mo.pnn_load_actor(single, n_hidden=len(g["units"]), idx=1).items():
+        assert torch.equal(sd[k], v), k
+    names = [str(n) for n in g["param_names"]]
+    assert mo.pnn_trainable(names, 1) == [bool(v) for v in g["trainable_after_freeze1"]]
+
+
+def test_mcp_step_actions_match_reference():
+    from oracle import mcp_oracle as mo
+    g, sd = _mcp()
+    K = int(g["num_prim"])
+    args = (torch.from_numpy(g["obs_buf"]), torch.from_numpy(g["rms_mean"]), torch.from_numpy(g["rms_var"]), sd, torch.from_numpy(g["weights"]), K)
+    assert (np.abs(g["obs_buf"]) > 5).any()
+    torch.testing.assert_close(mo.mcp_step_actions(*args), torch.from_numpy(g["actions"]), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(mo.mcp_step_actions(*args, discrete=True), torch.from_numpy(g["actions_discrete"]), rtol=1e-6, atol=1e-6)
+
+
+def test_mcp_composer_keeps_final_relu():
+    from oracle import mcp_oracle as mo
+    g, _ = _mcp()
+    comp = {k[len("composer/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("composer/")}
+    out = mo.mlp_forward(comp, "a2c_network.composer.", torch.from_numpy(g["x"]), ending_act=True)
+    torch.testing.assert_close(out, torch.from_numpy(g["composer_out"]), rtol=1e-6, atol=1e-6)
+    assert (g["composer_out"] == 0).any() and (g["composer_out"] >= 0).all()
