@@ -22,11 +22,12 @@ LIB_PATH = os.path.join(OUT_DIR, "libphc_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr"]
-# per-file extra flags.  The env-side arithmetic mirrors the reference expression by expression, so FMA
-# contraction is off there (phc_math.cuh explains why); GEMM / optimiser kernels keep FMA.
+# per-file extra flags.  The env-side arithmetic mirrors the reference expression by expression: FMA contraction is off
+# in the off-step kernels and, in the fused step kernel, pinned off at the ill-conditioned spots by explicit intrinsics
+# (phc_math.cuh explains which and why; PHC_ENV_FMAD=0 builds the step kernel without any contraction for A/B checks).
 SOURCES = {
     "phc_api.cu": [],
-    "env_step.cu": ["-fmad=false"],
+    "env_step.cu": ["-fmad=false"] if os.environ.get("PHC_ENV_FMAD", "1") == "0" else [],
     "motion.cu": ["-fmad=false"],
     "ppo_scalars.cu": ["-fmad=false"],
     "gemm.cu": [],

@@ -132,7 +132,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   }
 
   // reward / reset use the CURRENT motion time (humanoid_im.py:879), observations the NEXT one (:752)
-  const float t_now = (float)progress * a.dt + t_start + t_off;
+  const float t_now = PHC_ADD(PHC_ADD(PHC_MUL((float)progress, a.dt), t_start), t_off);   // motion times: never contracted
   const Bracket32 br_r = frame_bracket32(t_now, m_len, (int)m_nf, m_dt);
   float bl_o[T_MAX];
   const float* po0[T_MAX];     // shared-memory address of frame i0 / i1 of observation sample t
@@ -153,9 +153,9 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     for (int t = 0; t < T_MAX; ++t) {
       if (t < T) {
         // ((progress + 1) * dt [+ t * traj_dt] + start + offset), humanoid_im.py:744-752
-        float tn = (float)(progress + 1) * a.dt;
-        if (T > 1) tn = tn + (float)t * a.traj_dt;
-        tn = tn + t_start + t_off;
+        float tn = PHC_MUL((float)(progress + 1), a.dt);
+        if (T > 1) tn = PHC_ADD(tn, PHC_MUL((float)t, a.traj_dt));
+        tn = PHC_ADD(PHC_ADD(tn, t_start), t_off);
         const Bracket32 b = frame_bracket32(tn, m_len, (int)m_nf, m_dt);
         bl_o[t] = b.blend;
         rows_o[2 * t] = m_start + b.i0;
@@ -319,7 +319,16 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
       st3(o + 12 + 9 * nj + 3 * lane, qrot_z(hinv, v3(kb[0], kb[1], kb[2]) - root_p));
     }
   }
+  // rows leave shared memory as TMA bulk stores (one instruction per row) when source, destination and size are 16-byte
+  // granular; otherwise with per-lane coalesced stores.  The AMP row goes first so its store overlaps phase B.
+  float* const g_amp = (a.amp_out && !obs_only) ? a.amp_out + (size_t)env * a.amp_out_stride : nullptr;
+  const bool amp_bulk = g_amp && !a.amp_hist_in && (amp_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(g_amp) & 15) == 0;
+  if (amp_bulk) fence_async_smem();
   __syncwarp();   // the reward slots and the simulator block are consumed: the obs row may overwrite them
+  if (amp_bulk && lane == 0) {
+    bulk_s2g(g_amp, s_amp, (uint32_t)amp_dim * 4u);
+    bulk_commit();
+  }
 
   // ================= phase B: observation row (reads only registers + the observation slots) =================
   if (lane == 0 && has_h) s_obs[0] = root_p.z;
@@ -357,32 +366,41 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
       }
     }
   }
-  __syncwarp();
-
-  // ---- rows leave shared memory with coalesced stores -------------------------------------------------------
-  {
-    float* g = a.obs + (size_t)env * a.obs_stride;
-    if (((a.obs_stride | (int64_t)obs_dim) & 1) == 0) {          // rows 8-byte aligned: float2 stores
-      float2* g2 = reinterpret_cast<float2*>(g);
-      const float2* s2 = reinterpret_cast<const float2*>(s_obs);
-#pragma unroll 5
-      for (int i = lane; i < obs_dim / 2; i += 32) g2[i] = s2[i];
-    } else {
-      for (int i = lane; i < obs_dim; i += 32) g[i] = s_obs[i];
-    }
+  // ---- rows leave shared memory ---------------------------------------------------------------------------------
+  float* const g_obs = a.obs + (size_t)env * a.obs_stride;
+  const int obs_pad = round4(obs_dim);
+  const bool obs_bulk = a.obs_stride >= obs_pad && (reinterpret_cast<uintptr_t>(g_obs) & 15) == 0;
+  if (obs_bulk) {
+    if (lane < obs_pad - obs_dim) s_obs[obs_dim + lane] = 0.f;      // the row's pad columns are written as zeros
+    fence_async_smem();
   }
-  if (a.amp_out && !obs_only) {
-    float* g = a.amp_out + (size_t)env * a.amp_out_stride;
+  __syncwarp();
+  if (obs_bulk) {
+    if (lane == 0) {
+      bulk_s2g(g_obs, s_obs, (uint32_t)obs_pad * 4u);
+      bulk_commit();
+    }
+  } else if (((a.obs_stride | (int64_t)obs_dim) & 1) == 0) {      // rows 8-byte aligned: float2 stores
+    float2* g2 = reinterpret_cast<float2*>(g_obs);
+    const float2* s2 = reinterpret_cast<const float2*>(s_obs);
+#pragma unroll 5
+    for (int i = lane; i < obs_dim / 2; i += 32) g2[i] = s2[i];
+  } else {
+    for (int i = lane; i < obs_dim; i += 32) g_obs[i] = s_obs[i];
+  }
+  if (g_amp && !amp_bulk) {
     if (a.amp_hist_in) {
       // newest-first window shift: slot s -> s+1, walking from the oldest slot so an in-place shift is safe
       // (each element is read and later overwritten by the SAME lane, program order keeps it correct)
       const float* h = a.amp_hist_in + (size_t)env * a.amp_out_stride;
       for (int s = a.amp_steps - 2; s >= 0; --s)
-        for (int i = lane; i < amp_dim; i += 32) g[(size_t)(s + 1) * amp_dim + i] = h[(size_t)s * amp_dim + i];
+        for (int i = lane; i < amp_dim; i += 32) g_amp[(size_t)(s + 1) * amp_dim + i] = h[(size_t)s * amp_dim + i];
     }
 #pragma unroll 7
-    for (int i = lane; i < amp_dim; i += 32) g[i] = s_amp[i];
+    for (int i = lane; i < amp_dim; i += 32) g_amp[i] = s_amp[i];
   }
+  // the shared-memory rows must outlive the bulk reads: the issuing lane waits before the warp (and so the CTA) may retire
+  if (lane == 0 && (amp_bulk || obs_bulk)) bulk_wait_read0();
 }
 
 }  // namespace phc
@@ -438,7 +456,7 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
     phc_set_error("phc_env_step: amp_out_stride / amp_steps inconsistent"); return PHC_ERR_INVALID_ARG;
   }
   // the obs row is staged over [reward slots | simulator block] when it fits (always for T == 1)
-  const bool alias_obs = (2 * a->lib.body_stride + round4(J * kBodyRec) >= obs_dim);
+  const bool alias_obs = (2 * a->lib.body_stride + round4(J * kBodyRec) >= round4(obs_dim));   // incl. the row pad
   const bool obs_row_aligned = ((reinterpret_cast<uintptr_t>(a->obs) & 7) == 0);
   if (!obs_row_aligned) { phc_set_error("phc_env_step: obs must be 8-byte aligned"); return PHC_ERR_INVALID_ARG; }
   // TMA bulk copy of the per-env simulator block needs 16-byte aligned rows of a multiple of 16 bytes

@@ -33,6 +33,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// TMA 1-D bulk copy shared -> global (bulk async-group completion).  Writers of the shared-memory source call
+// fence_async_smem() before the barrier that precedes the issue; the issuer commits and, before the shared memory may be
+// reused or the CTA may exit, waits for the READS of the group with bulk_wait_read0().
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"((uint32_t)__cvta_generic_to_shared(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar`.
 // src, dst 16-byte aligned; bytes a multiple of 16.
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {

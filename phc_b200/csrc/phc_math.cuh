@@ -5,10 +5,14 @@
 // quat_to_angle_axis :58-78, quat_to_tan_norm :101-113, exp_map_to_angle_axis :147-166, slerp :176-197,
 // calc_heading* :200-240).  Quaternions are xyzw.
 //
-// Numerics contract: every expression keeps the reference's operation ORDER and this translation unit is
-// compiled with -fmad=false (no FMA contraction), IEEE div/sqrt and the accurate libm entry points (acosf,
-// atan2f, sinf, cosf -- never the __ fast intrinsics): 2*acos(w) is ill-conditioned near identity, so a
-// re-associated product changes per-body angles at the 1e-4 level.
+// Numerics contract: every expression keeps the reference's operation ORDER, IEEE div/sqrt and the accurate libm entry
+// points (acosf, atan2f, sinf, cosf -- never the __ fast intrinsics).  motion.cu / ppo_scalars.cu are compiled with
+// -fmad=false (no FMA contraction at all).  env_step.cu allows contraction in the well-conditioned arithmetic (quaternion
+// products, rotations, lerps: an FMA moves a result by <= 1 ulp of its operands, ~1e-7 of an O(1) value) and pins the
+// ill-conditioned spots to the reference's separately rounded mul / add with the PHC_MUL / PHC_ADD / PHC_SUB intrinsics,
+// which the compiler never contracts: the frame-bracket / blend arithmetic (a half-ulp change of i0*dt moves the blend by
+// 1e-5), slerp's dot product and 1 - c*c (sin(acos c) cancels catastrophically for neighbouring frames: the weights would
+// move at the 1e-4 level) and the 1 - w*w of the angle extraction.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -17,6 +21,16 @@
 #define PHC_HD __host__ __device__ __forceinline__
 #else
 #define PHC_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define PHC_MUL(a, b) __fmul_rn((a), (b))
+#define PHC_ADD(a, b) __fadd_rn((a), (b))
+#define PHC_SUB(a, b) __fsub_rn((a), (b))
+#else
+#define PHC_MUL(a, b) ((a) * (b))
+#define PHC_ADD(a, b) ((a) + (b))
+#define PHC_SUB(a, b) ((a) - (b))
 #endif
 
 namespace phc {
@@ -130,14 +144,14 @@ PHC_HD float wrap_angle_0_2pi(float x) { return x > 3.14159265358979323846f ? x 
 
 // quat_to_angle_axis: angle only (what the tracking reward reads) ...
 PHC_HD float quat_angle(Q4 q) {
-  const float s = sqrtf(1.0f - q.w * q.w);
+  const float s = sqrtf(PHC_SUB(1.0f, PHC_MUL(q.w, q.w)));
   const float ang = wrap_angle_0_2pi(2.0f * acosf(q.w));
   return (fabsf(s) > 1e-5f) ? ang : 0.0f;        // NaN (|w|>1) compares false -> 0, like torch.where(mask, ...)
 }
 
 // ... and the full exp map angle*axis (dof_pos of the reference pose)
 PHC_HD V3 quat_to_exp_map(Q4 q) {
-  const float s = sqrtf(1.0f - q.w * q.w);
+  const float s = sqrtf(PHC_SUB(1.0f, PHC_MUL(q.w, q.w)));
   const float ang = wrap_angle(2.0f * acosf(q.w));
   if (fabsf(s) > 1e-5f) return v3(ang * (q.x / s), ang * (q.y / s), ang * (q.z / s));
   return v3(0.0f * 0.0f, 0.0f * 0.0f, 0.0f * 1.0f);
@@ -164,11 +178,11 @@ PHC_HD Q4 exp_map_to_quat(V3 e) {
 }
 
 PHC_HD Q4 slerp(Q4 q0, Q4 q1, float t) {
-  float c = q0.x * q1.x + q0.y * q1.y + q0.z * q1.z + q0.w * q1.w;
+  float c = PHC_ADD(PHC_ADD(PHC_ADD(PHC_MUL(q0.x, q1.x), PHC_MUL(q0.y, q1.y)), PHC_MUL(q0.z, q1.z)), PHC_MUL(q0.w, q1.w));
   if (c < 0.0f) q1 = q4(-q1.x, -q1.y, -q1.z, -q1.w);
   c = fabsf(c);
   const float half = acosf(c);
-  const float s = sqrtf(1.0f - c * c);
+  const float s = sqrtf(PHC_SUB(1.0f, PHC_MUL(c, c)));
   const float inv_s = 1.0f / s;             // one IEEE division for both weights
   const float ra = sinf((1.0f - t) * half) * inv_s;
   const float rb = sinf(t * half) * inv_s;
@@ -190,7 +204,7 @@ PHC_HD Bracket frame_bracket(float time, float len, int64_t nf, float dt) {
   Bracket b;
   b.i0 = (int64_t)(phase * (float)(nf - 1));
   b.i1 = (b.i0 + 1 < nf - 1) ? b.i0 + 1 : nf - 1;
-  float bl = (time - (float)b.i0 * dt) / dt;
+  float bl = PHC_SUB(time, PHC_MUL((float)b.i0, dt)) / dt;
   b.blend = fminf(fmaxf(bl, 0.0f), 1.0f);
   return b;
 }
@@ -205,7 +219,7 @@ PHC_HD Bracket32 frame_bracket32(float time, float len, int nf, float dt) {
   Bracket32 b;
   b.i0 = (int)(phase * (float)(nf - 1));
   b.i1 = (b.i0 + 1 < nf - 1) ? b.i0 + 1 : nf - 1;
-  float bl = (time - (float)b.i0 * dt) / dt;
+  float bl = PHC_SUB(time, PHC_MUL((float)b.i0, dt)) / dt;
   b.blend = fminf(fmaxf(bl, 0.0f), 1.0f);
   return b;
 }

@@ -219,7 +219,13 @@ class EnvStepPlan:
             assert tuple(t.shape) == tuple(shape), f"{name}: shape {tuple(t.shape)} != {tuple(shape)}"
             return t
 
-        self.obs = out(obs, (N, self.obs_dim), f32, "obs")
+        if obs is None:      # rows padded to 16 bytes so the kernel can store them with one TMA bulk copy (pad columns = 0)
+            obs = torch.zeros((N, (self.obs_dim + 3) // 4 * 4), dtype=f32, device=dev)[:, :self.obs_dim]
+        else:
+            if not (torch.is_tensor(obs) and obs.is_cuda and obs.dtype == f32 and obs.dim() == 2 and obs.stride(1) == 1):
+                obs = _req(obs, f32, "obs", dev)
+            assert tuple(obs.shape) == (N, self.obs_dim), f"obs: shape {tuple(obs.shape)} != {(N, self.obs_dim)}"
+        self.obs = obs
         self.rew = out(rew, (N,), f32, "rew")
         self.reward_raw = out(reward_raw, (N, rw), f32, "reward_raw")
         self.reset = out(reset, (N,), i64, "reset")
