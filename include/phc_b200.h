@@ -123,6 +123,7 @@ PHC_API int phc_motion_state(const PhcMotionLib* lib, const int64_t* motion_ids,
 #define PHC_FLAG_NO_COLLISION (1u << 5)    /* flags.no_collision_check                                  */
 #define PHC_FLAG_TERM_USE_MEAN (1u << 6)   /* flags.im_eval and not strict_eval: mean-distance criterion */
 #define PHC_FLAG_OBS_ONLY (1u << 7)        /* _compute_observations(env_ids) of the reset path: write obs (+ref_*) only */
+#define PHC_FLAG_REWARD_FROM_CACHE (1u << 8) /* reward / reset read the reference pose from ref_cache (see PhcStepArgs) */
 
 #define PHC_MAX_KEY_BODIES 8
 #define PHC_MAX_BODIES 32      /* one body per lane in the fused step kernel */
@@ -181,6 +182,15 @@ typedef struct PhcStepArgs {
   float* ref_body_rot;     /* [N, J, 4] */
   float* ref_body_vel;     /* [N, J, 3] */
   float* ref_body_ang_vel; /* [N, J, 3] */
+  /* Interpolated reference pose kept across steps ("ref for reward time = 1248 B if the interpolated
+   * pose from the previous step is kept").  [N, body_stride] rows of 13-float body records (pos3 rot4 vel3 angvel3, global
+   * offset included), 16-byte aligned.  When non-NULL every launch writes the pose it interpolated for the FIRST observation
+   * sample, i.e. for motion time (progress+1)*dt + start + offset.  With PHC_FLAG_REWARD_FROM_CACHE the launch takes the
+   * reference pose of the reward / reset test from here instead of interpolating the bracket of progress*dt + start +
+   * offset: valid exactly when the previous launch (step or PHC_FLAG_OBS_ONLY reset launch) of that env ran with
+   * progress-1 and the same start / offset / clip -- which HumanoidIm's step / reset sequence guarantees.  The values
+   * are bit-identical to re-interpolating.  ref_body_* above are then strided views of it (columns 0:3, 3:7, 7:10, 10:13). */
+  float* ref_cache;
 } PhcStepArgs;
 
 /* Sizes implied by a configuration (so callers can allocate): */

@@ -19,6 +19,7 @@ PHC_FLAG_EARLY_TERM = 1 << 4
 PHC_FLAG_NO_COLLISION = 1 << 5
 PHC_FLAG_TERM_USE_MEAN = 1 << 6
 PHC_FLAG_OBS_ONLY = 1 << 7
+PHC_FLAG_REWARD_FROM_CACHE = 1 << 8
 PHC_MAX_KEY_BODIES = 8
 PHC_MAX_BODIES = 32
 PHC_MAX_AMP_JOINTS = 32
@@ -57,6 +58,7 @@ class PhcStepArgs(C.Structure):
         ("obs", _p), ("obs_stride", C.c_int64), ("rew", _p), ("reward_raw", _p), ("reset", _p), ("terminate", _p),
         ("amp_out", _p), ("amp_hist_in", _p), ("amp_out_stride", C.c_int64), ("amp_steps", C.c_int32),
         ("ref_body_pos", _p), ("ref_body_rot", _p), ("ref_body_vel", _p), ("ref_body_ang_vel", _p),
+        ("ref_cache", _p),
     ]
 
 

@@ -98,11 +98,27 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   float* const s_dof = s_oslots + L.oslots;
   float* const s_amp = s_dof + L.dof;
   float* const s_obs = alias_obs ? w_base : (s_amp + L.amp);
-  uint64_t* const bar = reinterpret_cast<uint64_t*>(w_base + L.total - 4);
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(w_base + L.total - 4);     // state + reward-time reference
+  uint64_t* const bar_o = bar + 1;                                             // observation bracket(s)
+  const bool from_cache = (a.flags & PHC_FLAG_REWARD_FROM_CACHE) && !obs_only;
 
+  // The simulator block (and the cached reference pose) depend only on the env index: their TMA copies are issued before
+  // anything else, so this DRAM round trip overlaps the scalar loads -> bracket -> frame-copy chain below.
+  const float* g_state = a.body_state + (size_t)env * a.bodies_per_env * kBodyRec;
+  const uint32_t state_bytes = (uint32_t)(J * kBodyRec) * 4u;
+  const uint32_t frame_bytes = (uint32_t)BS * 4u;
   if (lane == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar_o, 1);
     mbar_init_fence();
+    if (state_bulk_ok) {
+      mbar_expect_tx(bar, state_bytes);
+      bulk_g2s(s_state, g_state, state_bytes, bar);
+    }
+    if (from_cache) {
+      mbar_expect_tx(bar, frame_bytes);
+      bulk_g2s(s_rslots, a.ref_cache + (size_t)env * BS, frame_bytes, bar);
+    }
   }
   __syncwarp();
 
@@ -145,8 +161,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   // one.  In steady state (30 fps clips, dt = 1/30) the reward bracket is rows (k, k+1) and the observation
   // bracket (k+1, k+2): 3 distinct frames, the reward slot 1 aliases observation slot 0.
   {
-    uint32_t tx = 0;
-    const uint32_t frame_bytes = (uint32_t)BS * 4u;
+    uint32_t tx_o = 0, tx_r = 0;
     int64_t rows_o[2 * T_MAX];
     bool fresh_o[2 * T_MAX];
 #pragma unroll
@@ -172,35 +187,35 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
           if (p < k && !dup && rows_o[p] == rows_o[k]) { ptr = (p & 1) ? po1[p >> 1] : po0[p >> 1]; dup = true; }
         if (k & 1) po1[k >> 1] = ptr; else po0[k >> 1] = ptr;
         fresh_o[k] = !dup;
-        if (!dup) tx += frame_bytes;
+        if (!dup) tx_o += frame_bytes;
       }
     }
     const int64_t row_r0 = m_start + br_r.i0, row_r1 = m_start + br_r.i1;
-    bool fresh_r0 = true, fresh_r1 = true;
+    bool fresh_r0 = !from_cache && !obs_only, fresh_r1 = fresh_r0;
+    if (fresh_r0) {
 #pragma unroll
-    for (int p = 0; p < 2 * T_MAX; ++p) {
-      if (p < 2 * T) {
-        const float* ptr = (p & 1) ? po1[p >> 1] : po0[p >> 1];
-        if (fresh_r0 && rows_o[p] == row_r0) { pr0 = ptr; fresh_r0 = false; }
-        if (fresh_r1 && rows_o[p] == row_r1) { pr1 = ptr; fresh_r1 = false; }
+      for (int p = 0; p < 2 * T_MAX; ++p) {
+        if (p < 2 * T) {
+          const float* ptr = (p & 1) ? po1[p >> 1] : po0[p >> 1];
+          if (fresh_r0 && rows_o[p] == row_r0) { pr0 = ptr; fresh_r0 = false; }
+          if (fresh_r1 && rows_o[p] == row_r1) { pr1 = ptr; fresh_r1 = false; }
+        }
       }
+      if (fresh_r1 && row_r1 == row_r0) { pr1 = pr0; fresh_r1 = false; }
+      if (fresh_r0) tx_r += frame_bytes;
+      if (fresh_r1) tx_r += frame_bytes;
     }
-    if (fresh_r1 && row_r1 == row_r0) { pr1 = pr0; fresh_r1 = false; }
-    if (fresh_r0) tx += frame_bytes;
-    if (fresh_r1) tx += frame_bytes;
 
-    const float* g_state = a.body_state + (size_t)env * a.bodies_per_env * kBodyRec;
-    const uint32_t state_bytes = (uint32_t)(J * kBodyRec) * 4u;
     if (lane == 0) {
-      if (state_bulk_ok) tx += state_bytes;
-      mbar_arrive_expect_tx(bar, tx);
-      if (state_bulk_ok) bulk_g2s(s_state, g_state, state_bytes, bar);
+      if (tx_r) mbar_expect_tx(bar, tx_r);
       if (fresh_r0) bulk_g2s(s_rslots, a.lib.frames_body + (size_t)row_r0 * BS, frame_bytes, bar);
       if (fresh_r1) bulk_g2s(s_rslots + BS, a.lib.frames_body + (size_t)row_r1 * BS, frame_bytes, bar);
+      mbar_arrive(bar);
+      mbar_arrive_expect_tx(bar_o, tx_o);
 #pragma unroll
       for (int k = 0; k < 2 * T_MAX; ++k)
         if (k < 2 * T && fresh_o[k])
-          bulk_g2s(s_oslots + k * BS, a.lib.frames_body + (size_t)rows_o[k] * BS, frame_bytes, bar);
+          bulk_g2s(s_oslots + k * BS, a.lib.frames_body + (size_t)rows_o[k] * BS, frame_bytes, bar_o);
     }
     if (!state_bulk_ok) {      // bodies_per_env not a multiple of 4: rows are only 4-byte aligned
       for (int i = lane; i < J * kBodyRec; i += 32) s_state[i] = g_state[i];
@@ -220,6 +235,8 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   }
   __syncwarp();
   mbar_wait(bar, 0);
+  // without the cache the reward bracket may alias observation slots: phase A then needs those copies too
+  if (!from_cache && !obs_only) mbar_wait(bar_o, 0);
 
   // ================= phase A: everything that reads the reward slots / simulator block =======================
   const bool has_body = lane < J;
@@ -236,66 +253,69 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   const Q4 hq = quat_about_z(heading);
   const Q4 hinv = q4(0.0f, 0.0f, -hq.z, hq.w);     // quat_about_z(-heading): sin is odd, cos even -> the exact conjugate
 
-  // reward + termination against the reference pose at t_now
-  float e_pos = 0.f, e_rot = 0.f, e_vel = 0.f, e_ang = 0.f, dist = 0.f;
-  {
-    const BodyRec ref = blend_body(pr0 + j * kBodyRec, pr1 + j * kBodyRec, br_r.blend, goff);
-    if (has_body) {
-      const V3 dp = ref.p - sim.p, dv = ref.v - sim.v, dw = ref.w - sim.w;
-      const float sp = dp.x * dp.x + dp.y * dp.y + dp.z * dp.z;
-      e_pos = sp / 3.0f;
-      e_vel = (dv.x * dv.x + dv.y * dv.y + dv.z * dv.z) / 3.0f;
-      e_ang = (dw.x * dw.x + dw.y * dw.y + dw.z * dw.z) / 3.0f;
-      const float ang = quat_angle(qmul(ref.q, qconj(sim.q)));
-      e_rot = ang * ang;
-      dist = sqrtf(sp);
+  if (!obs_only) {   // the reset-path launch writes observations (and the pose cache) only
+    // reward + termination against the reference pose at t_now
+    float e_pos = 0.f, e_rot = 0.f, e_vel = 0.f, e_ang = 0.f, dist = 0.f;
+    {
+      const BodyRec ref = from_cache ? load_body(s_rslots + j * kBodyRec)
+                                     : blend_body(pr0 + j * kBodyRec, pr1 + j * kBodyRec, br_r.blend, goff);
+      if (has_body) {
+        const V3 dp = ref.p - sim.p, dv = ref.v - sim.v, dw = ref.w - sim.w;
+        const float sp = dp.x * dp.x + dp.y * dp.y + dp.z * dp.z;
+        e_pos = sp / 3.0f;
+        e_vel = (dv.x * dv.x + dv.y * dv.y + dv.z * dv.z) / 3.0f;
+        e_ang = (dw.x * dw.x + dw.y * dw.y + dw.z * dw.z) / 3.0f;
+        const float ang = quat_angle(qmul(ref.q, qconj(sim.q)));
+        e_rot = ang * ang;
+        dist = sqrtf(sp);
+      }
     }
-  }
-  bool fallen;
-  {
-    const float thr = has_body ? a.term_thresh[j] : INFINITY;
-    if (a.flags & PHC_FLAG_TERM_USE_MEAN) {
-      const bool in_set = has_body && thr < INFINITY;
-      const float cnt = warp_sum(in_set ? 1.0f : 0.0f);
-      const float sum = warp_sum(in_set ? dist : 0.0f);
-      fallen = (sum / cnt) > a.term_dist_mean;
-    } else {
-      fallen = __any_sync(0xffffffffu, has_body && dist > thr);
+    bool fallen;
+    {
+      const float thr = has_body ? a.term_thresh[j] : INFINITY;
+      if (a.flags & PHC_FLAG_TERM_USE_MEAN) {
+        const bool in_set = has_body && thr < INFINITY;
+        const float cnt = warp_sum(in_set ? 1.0f : 0.0f);
+        const float sum = warp_sum(in_set ? dist : 0.0f);
+        fallen = (sum / cnt) > a.term_dist_mean;
+      } else {
+        fallen = __any_sync(0xffffffffu, has_body && dist > thr);
+      }
     }
-  }
-  e_pos = warp_sum(e_pos) / (float)J;
-  e_rot = warp_sum(e_rot) / (float)J;
-  e_vel = warp_sum(e_vel) / (float)J;
-  e_ang = warp_sum(e_ang) / (float)J;
-  power = warp_sum(power);
+    e_pos = warp_sum(e_pos) / (float)J;
+    e_rot = warp_sum(e_rot) / (float)J;
+    e_vel = warp_sum(e_vel) / (float)J;
+    e_ang = warp_sum(e_ang) / (float)J;
+    power = warp_sum(power);
 
-  if (lane == 0 && !obs_only) {
-    const float r_pos = expf(-a.k_pos * e_pos), r_rot = expf(-a.k_rot * e_rot);
-    const float r_vel = expf(-a.k_vel * e_vel), r_ang = expf(-a.k_ang_vel * e_ang);
-    float rew = a.w_pos * r_pos + a.w_rot * r_rot + a.w_vel * r_vel + a.w_ang_vel * r_ang;
-    const bool has_power = a.flags & PHC_FLAG_POWER_REWARD;
-    const int rw = has_power ? 5 : 4;
-    float* raw = a.reward_raw + (size_t)env * rw;
-    raw[0] = r_pos; raw[1] = r_rot; raw[2] = r_vel; raw[3] = r_ang;
-    if (has_power) {
-      float pr = -a.power_coef * power;
-      if (progress <= 3) pr = 0.0f;
-      rew = rew + pr;
-      raw[4] = pr;
+    if (lane == 0) {
+      const float r_pos = expf(-a.k_pos * e_pos), r_rot = expf(-a.k_rot * e_rot);
+      const float r_vel = expf(-a.k_vel * e_vel), r_ang = expf(-a.k_ang_vel * e_ang);
+      float rew = a.w_pos * r_pos + a.w_rot * r_rot + a.w_vel * r_vel + a.w_ang_vel * r_ang;
+      const bool has_power = a.flags & PHC_FLAG_POWER_REWARD;
+      const int rw = has_power ? 5 : 4;
+      float* raw = a.reward_raw + (size_t)env * rw;
+      raw[0] = r_pos; raw[1] = r_rot; raw[2] = r_vel; raw[3] = r_ang;
+      if (has_power) {
+        float pr = -a.power_coef * power;
+        if (progress <= 3) pr = 0.0f;
+        rew = rew + pr;
+        raw[4] = pr;
+      }
+      a.rew[env] = rew;
+      // compute_humanoid_im_reset + the is_recovery override
+      const bool pass_time = t_now >= m_len;
+      int64_t terminated = 0;
+      if (a.flags & PHC_FLAG_EARLY_TERM) {
+        bool f = fallen && (progress > 1);
+        if (a.flags & PHC_FLAG_NO_COLLISION) f = false;
+        terminated = f ? 1 : 0;
+      }
+      int64_t reset = pass_time ? 1 : terminated;
+      if (a.cycle_counter && !pass_time && a.cycle_counter[env] > 0) { reset = 0; terminated = 0; }
+      a.reset[env] = reset;
+      a.terminate[env] = terminated;
     }
-    a.rew[env] = rew;
-    // compute_humanoid_im_reset + the is_recovery override
-    const bool pass_time = t_now >= m_len;
-    int64_t terminated = 0;
-    if (a.flags & PHC_FLAG_EARLY_TERM) {
-      bool f = fallen && (progress > 1);
-      if (a.flags & PHC_FLAG_NO_COLLISION) f = false;
-      terminated = f ? 1 : 0;
-    }
-    int64_t reset = pass_time ? 1 : terminated;
-    if (a.cycle_counter && !pass_time && a.cycle_counter[env] > 0) { reset = 0; terminated = 0; }
-    a.reset[env] = reset;
-    a.terminate[env] = terminated;
   }
 
   // AMP observation of the simulated character (build_amp_observations_smpl) -> its own staging row
@@ -345,11 +365,19 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     st3(o_vel + 3 * j, qrot_z(hinv, sim.v));
     st3(o_ang + 3 * j, qrot_z(hinv, sim.w));
   }
-  // task observation v6 for each of the T reference samples
+  // task observation v6 for each of the T reference samples (the self observation above did not need the frames)
+  mbar_wait(bar_o, 0);
+  float* const g_cache = a.ref_cache ? a.ref_cache + (size_t)env * BS : nullptr;
+  const bool cache_bulk = g_cache && T_MAX == 1;     // single sample: the blended pose is staged over its own frame slot
 #pragma unroll
   for (int t = 0; t < T_MAX; ++t) {
     if (t < T && has_body) {
       const BodyRec ref = blend_body(po0[t] + j * kBodyRec, po1[t] + j * kBodyRec, bl_o[t], goff);
+      if (t == 0 && g_cache) {
+        // lane j has consumed records j of both frames: slot 0 of the bracket becomes the row of the pose cache
+        float* c = (cache_bulk ? s_oslots : g_cache) + j * kBodyRec;
+        st3(c, ref.p); c[3] = ref.q.x; c[4] = ref.q.y; c[5] = ref.q.z; c[6] = ref.q.w; st3(c + 7, ref.v); st3(c + 10, ref.w);
+      }
       float* tb = s_obs + self_dim + t * 24 * J;
       st3(tb + 3 * j, qrot_z(hinv, ref.p - sim.p));
       st6(tb + 3 * J + 6 * j, tan_norm(qmul(qmul(hinv, qmul(ref.q, qconj(sim.q))), hq)));
@@ -370,16 +398,15 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   float* const g_obs = a.obs + (size_t)env * a.obs_stride;
   const int obs_pad = round4(obs_dim);
   const bool obs_bulk = a.obs_stride >= obs_pad && (reinterpret_cast<uintptr_t>(g_obs) & 15) == 0;
-  if (obs_bulk) {
-    if (lane < obs_pad - obs_dim) s_obs[obs_dim + lane] = 0.f;      // the row's pad columns are written as zeros
-    fence_async_smem();
-  }
+  if (obs_bulk && lane < obs_pad - obs_dim) s_obs[obs_dim + lane] = 0.f;      // the row's pad columns are written as zeros
+  if (obs_bulk || cache_bulk) fence_async_smem();
   __syncwarp();
+  if (lane == 0 && (obs_bulk || cache_bulk)) {
+    if (obs_bulk) bulk_s2g(g_obs, s_obs, (uint32_t)obs_pad * 4u);
+    if (cache_bulk) bulk_s2g(g_cache, s_oslots, frame_bytes);
+    bulk_commit();
+  }
   if (obs_bulk) {
-    if (lane == 0) {
-      bulk_s2g(g_obs, s_obs, (uint32_t)obs_pad * 4u);
-      bulk_commit();
-    }
   } else if (((a.obs_stride | (int64_t)obs_dim) & 1) == 0) {      // rows 8-byte aligned: float2 stores
     float2* g2 = reinterpret_cast<float2*>(g_obs);
     const float2* s2 = reinterpret_cast<const float2*>(s_obs);
@@ -400,7 +427,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     for (int i = lane; i < amp_dim; i += 32) g_amp[i] = s_amp[i];
   }
   // the shared-memory rows must outlive the bulk reads: the issuing lane waits before the warp (and so the CTA) may retire
-  if (lane == 0 && (amp_bulk || obs_bulk)) bulk_wait_read0();
+  if (lane == 0 && (amp_bulk || obs_bulk || cache_bulk)) bulk_wait_read0();
 }
 
 }  // namespace phc

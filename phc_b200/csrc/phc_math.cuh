@@ -44,7 +44,8 @@ PHC_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
 PHC_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
 
 // (1-b)*a0 + b*a1, the reference's lerp expression (motion_lib_base.py:474-480)
-PHC_HD float lerp1(float a0, float a1, float omb, float b) { return omb * a0 + b * a1; }
+// (pinned: the interpolated reference pose is bit-identical at every call site, in every kernel, cached or recomputed)
+PHC_HD float lerp1(float a0, float a1, float omb, float b) { return PHC_ADD(PHC_MUL(omb, a0), PHC_MUL(b, a1)); }
 PHC_HD V3 lerp3(V3 a0, V3 a1, float omb, float b) {
   return v3(lerp1(a0.x, a1.x, omb, b), lerp1(a0.y, a1.y, omb, b), lerp1(a0.z, a1.z, omb, b));
 }
@@ -186,8 +187,8 @@ PHC_HD Q4 slerp(Q4 q0, Q4 q1, float t) {
   const float inv_s = 1.0f / s;             // one IEEE division for both weights
   const float ra = sinf((1.0f - t) * half) * inv_s;
   const float rb = sinf(t * half) * inv_s;
-  Q4 r = q4(ra * q0.x + rb * q1.x, ra * q0.y + rb * q1.y, ra * q0.z + rb * q1.z, ra * q0.w + rb * q1.w);
-  if (fabsf(s) < 0.001f) r = q4(0.5f * q0.x + 0.5f * q1.x, 0.5f * q0.y + 0.5f * q1.y, 0.5f * q0.z + 0.5f * q1.z, 0.5f * q0.w + 0.5f * q1.w);
+  Q4 r = q4(lerp1(q0.x, q1.x, ra, rb), lerp1(q0.y, q1.y, ra, rb), lerp1(q0.z, q1.z, ra, rb), lerp1(q0.w, q1.w, ra, rb));
+  if (fabsf(s) < 0.001f) r = q4(lerp1(q0.x, q1.x, 0.5f, 0.5f), lerp1(q0.y, q1.y, 0.5f, 0.5f), lerp1(q0.z, q1.z, 0.5f, 0.5f), lerp1(q0.w, q1.w, 0.5f, 0.5f));
   if (fabsf(c) >= 1.0f) r = q0;
   return r;
 }

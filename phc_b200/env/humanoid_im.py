@@ -138,8 +138,20 @@ class HumanoidIm:
         # the whole window (humanoid_amp.py:662-670); the newest-first window is exported on demand (`_amp_obs_buf`,
         # `export_amp_obs`).  amp_window_shift=True in cfg restores the in-kernel reference-style shift.
         self._amp_use_ring = not bool(cfg.get("amp_window_shift", False))
-        self._plan = ops.EnvStepPlan(cycle_counter=self._cycle_counter, with_ref_buffers=True, amp_ring=self._amp_use_ring, **common)
+        # Interpolated reference pose kept across steps: the pose a launch blends for its observation (time t + dt) is the
+        # pose the next launch needs for reward / reset (SURVEY.md 8d counts it that way).  Rows are 13-float body records;
+        # ref_body_pos / rot / vel / ang_vel (humanoid_im.py:855-868) are strided views of it.  ref_pose_cache=False in cfg
+        # re-interpolates every step and keeps separate ref_* buffers.
+        self._use_ref_cache = bool(cfg.get("ref_pose_cache", True))
+        J = self._motion_lib.num_bodies
+        self._ref_cache = torch.zeros(N, int(self._motion_lib.frames_body.shape[1]), device=dev) if self._use_ref_cache else None
+        self._plan = ops.EnvStepPlan(cycle_counter=self._cycle_counter, with_ref_buffers=not self._use_ref_cache,
+                                     amp_ring=self._amp_use_ring, ref_cache=self._ref_cache,
+                                     reward_from_cache=self._use_ref_cache, **common)
         p = self._plan
+        if self._use_ref_cache:
+            rec = self._ref_cache[:, :13 * J].view(N, J, 13)
+            p.ref_body_pos, p.ref_body_rot, p.ref_body_vel, p.ref_body_ang_vel = rec[..., 0:3], rec[..., 3:7], rec[..., 7:10], rec[..., 10:13]
         self.obs_buf, self.rew_buf, self.reward_raw = p.obs, p.rew, p.reward_raw
         self.reset_buf, self._terminate_buf = p.reset, p.terminate
         self._amp_store = p.amp_obs_buf                              # ring (or the shifted window itself)
@@ -149,7 +161,8 @@ class HumanoidIm:
         self._curr_amp_obs_buf = self._hist_amp_obs_buf = None        # reference views of the shifted window; not kept with the ring
         self.self_obs_buf = self.obs_buf[:, :p.self_dim]
         # observation-only re-computation for just-reset envs (_compute_observations(env_ids))
-        self._plan_reset_obs = ops.EnvStepPlan(obs=self.obs_buf, only_where=self._reset_mask, obs_only=True, with_amp=False, **common)
+        self._plan_reset_obs = ops.EnvStepPlan(obs=self.obs_buf, only_where=self._reset_mask, obs_only=True, with_amp=False,
+                                               ref_cache=self._ref_cache, **common)
         self._lib = _lib.load()
         self._kb = (C.c_int32 * len(key_bodies))(*[int(b) for b in key_bodies])
         self.actions = None

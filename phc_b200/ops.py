@@ -184,8 +184,12 @@ class EnvStepPlan:
                  reset: Optional[torch.Tensor] = None, terminate: Optional[torch.Tensor] = None,
                  amp_obs_buf: Optional[torch.Tensor] = None, amp_hist_in: Optional[torch.Tensor] = None,
                  amp_shift: bool = True, with_amp: bool = True, with_ref_buffers: bool = False,
-                 only_where: Optional[torch.Tensor] = None, obs_only: bool = False, amp_ring: bool = False):
-        """amp_ring=True: `amp_obs_buf` is a ring -- each run() writes only the newest vector into slot `ring_head`
+                 only_where: Optional[torch.Tensor] = None, obs_only: bool = False, amp_ring: bool = False,
+                 ref_cache: Optional[torch.Tensor] = None, reward_from_cache: bool = False):
+        """ref_cache: [N, body_stride] pose cache (PhcStepArgs.ref_cache): every run() stores the reference pose interpolated
+        for the first observation sample; reward_from_cache=True makes run() take the reward-time reference pose from it
+        (valid for HumanoidIm's step / reset sequence, see include/phc_b200.h).
+        amp_ring=True: `amp_obs_buf` is a ring -- each run() writes only the newest vector into slot `ring_head`
         (advance with advance_ring() before the step); otherwise the reference's window shift is done in the kernel."""
         lib = _lib.load()
         self._lib = lib
@@ -205,6 +209,9 @@ class EnvStepPlan:
             assert dof_force.shape == (N, D)
         self.N, self.J = N, J
         flags = cfg.flags() | (_lib.PHC_FLAG_OBS_ONLY if obs_only else 0)
+        if reward_from_cache:
+            assert ref_cache is not None and not obs_only
+            flags |= _lib.PHC_FLAG_REWARD_FROM_CACHE
         self.self_dim = lib.phc_self_obs_dim(J, flags)
         self.task_dim = lib.phc_task_obs_dim(J, cfg.time_steps)
         self.obs_dim = self.self_dim + self.task_dim
@@ -290,6 +297,11 @@ class EnvStepPlan:
         a.amp_out_stride, a.amp_steps = S * self.amp_dim, S
         a.ref_body_pos, a.ref_body_rot = _ptr(self.ref_body_pos), _ptr(self.ref_body_rot)
         a.ref_body_vel, a.ref_body_ang_vel = _ptr(self.ref_body_vel), _ptr(self.ref_body_ang_vel)
+        if ref_cache is not None:
+            ref_cache = _req(ref_cache, f32, "ref_cache", dev)
+            assert tuple(ref_cache.shape) == (N, int(mlib.frames_body.shape[1])), f"ref_cache: expected {(N, int(mlib.frames_body.shape[1]))}"
+        self.ref_cache = ref_cache
+        a.ref_cache = _ptr(ref_cache)
         self.args = a
         self._args_ref = C.byref(a)
         self.refresh_motion_params()

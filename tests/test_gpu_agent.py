@@ -98,3 +98,32 @@ def test_agent_epoch_small():
     agent.model.params.zero_()
     agent.set_full_state_weights(sd)
     assert torch.equal(agent.model.state_dict()["a2c_network._disc_logits.weight"], sd["model"]["a2c_network._disc_logits.weight"])
+
+
+def test_ref_pose_cache_is_bit_identical_to_reinterpolation():
+    """PHC_FLAG_REWARD_FROM_CACHE (the pose interpolated for the observation of step s is the reward-time pose of step
+    s+1) against re-interpolating every step: identical bits over a rollout with resets in between."""
+    n = 160
+    m = syn.make_motions(n, seed=3, min_frames=20, max_frames=40)          # short clips: some envs run past the end
+    tasks = [HumanoidIm({"env": {"num_envs": n}, "motion_data": m, "seed": 3, "ref_pose_cache": c}) for c in (True, False)]
+    assert tasks[0]._use_ref_cache and not tasks[1]._use_ref_cache
+    for t in tasks:
+        torch.manual_seed(99)                    # start times are drawn from the global generator: same draws for both
+        t.reset()
+    for step in range(12):
+        for t in tasks:
+            t.step(None)
+        torch.cuda.synchronize()
+        a, b = tasks
+        for name in ("obs_buf", "rew_buf", "reward_raw", "reset_buf", "_terminate_buf", "progress_buf"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), f"step {step}: {name} differs"
+        assert torch.equal(a._amp_obs_buf, b._amp_obs_buf), f"step {step}: AMP window differs"
+        assert torch.equal(a.ref_body_pos, b.ref_body_pos) and torch.equal(a.ref_body_rot, b.ref_body_rot)
+        assert torch.equal(a.ref_body_vel, b.ref_body_vel)
+        if step % 3 == 2:            # the agent's env_reset(done_indices) (here: done envs plus every 5th env)
+            mask = ((a.reset_buf != 0) | (torch.arange(n, device=a.device) % 5 == step % 5)).long()
+            for t in tasks:
+                torch.manual_seed(100 + step)
+                t.reset(mask.clone())
+            assert torch.equal(a.obs_buf, b.obs_buf) and torch.equal(a._motion_start_times, b._motion_start_times)
+    assert int((tasks[0].reset_buf != 0).sum()) >= 0
