@@ -270,12 +270,13 @@ def env_kernel_roofline(task, peak_gbs: float, peak_src: str, iters: int = 40):
     t = statistics.median(times)
     N = task.num_envs
     achieved = ALGO_BYTES_PER_ENV_STEP * N / t / 1e9
-    # what the launch really moves per env at J=24: inputs 1248 (state) + 3 x 1248 (distinct frames) + 552 + 276 (dof) + 56
-    # (scalars, env_motion); outputs 3736 (obs) + 40 (reward/reset) + 784 (AMP ring slot) + 1248 (ref_* side buffers)
-    actual = 1248 + 3 * 1248 + 552 + 276 + 56 + 3736 + 40 + 784 + 1248
+    # what the launch really moves per env at J=24: inputs 1248 (state) + 1248 (cached reference pose of the reward time)
+    # + 2 x 1248 (observation bracket) + 552 + 276 (dof) + 56 (scalars, env_motion); outputs 3744 (obs row incl. 8 pad bytes)
+    # + 40 (reward/reset) + 784 (AMP ring slot) + 1248 (pose cache for the next step = the ref_* buffers)
+    actual = 1248 + 1248 + 2 * 1248 + 552 + 276 + 56 + 3744 + 40 + 784 + 1248
     return {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
             "kernel": "phc::env_step_kernel<1>", "kernel_us": t * 1e6, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * N,
-            "bytes_moved_per_launch_incl_amp_slot_and_ref_buffers": actual * N, "achieved_incl_extras_gbs": actual * N / t / 1e9,
+            "bytes_moved_per_launch_incl_amp_slot_and_pose_cache": actual * N, "achieved_incl_extras_gbs": actual * N / t / 1e9,
             "peak_source": peak_src, "timing": "median of %d launches, L2 flushed before each, cuda events on the launch stream" % iters}
 
 
