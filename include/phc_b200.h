@@ -244,22 +244,31 @@ PHC_API int phc_adv_norm(const float* returns, const float* values, int64_t n, i
  * MLP building blocks (actor / critic / discriminator are nn.Linear stacks: phc/learning/network_builder.py:105-124,
  * amp_network_builder.py:58-249; fp32 in the reference -> computed fp32-equivalent on the tensor cores, 3xTF32)
  * ---------------------------------------------------------------------------------------------------------- */
+/* Activation codes of the GEMM epilogues (`act` argument; nn.ReLU of im.yaml, nn.SiLU of im_big.yaml / im_pnn_big.yaml /
+ * im_mcp_big.yaml).  `aux` [M, ldaux] is optional:
+ *   PHC_ACT_NONE / PHC_ACT_RELU with aux : ReLU backward, out *= (aux > 0)        (aux = the layer's output, read)
+ *   PHC_ACT_SILU                         : out = x * sigmoid(x); aux (if given) receives the pre-activation x (written)
+ *   PHC_ACT_SILU_BWD (aux required)      : out *= d silu / dx at x = aux          (aux = the saved pre-activation, read) */
+#define PHC_ACT_NONE 0
+#define PHC_ACT_RELU 1
+#define PHC_ACT_SILU 2
+#define PHC_ACT_SILU_BWD 3
 /* C[M,N] (+)= epi(alpha * sum_k A(m,k) B(n,k)).  a_kmajor: A(m,k) = A[m*lda + k] (else A[k*lda + m]); b_kmajor: B(n,k) =
  * B[n*ldb + k] (else B[k*ldb + n]).  Forward Y = X W^T: (1,1); input gradient dX = dY W: (1,0); weight gradient
- * dW = dY^T X: (0,0).  Epilogue in order: *alpha, +bias[n], ReLU (relu != 0), *(mask[m*ldmask+n] > 0) (ReLU
- * backward), then store or atomic accumulate (accumulate != 0; required for k_splits > 1, C pre-zeroed).
+ * dW = dY^T X: (0,0).  Epilogue in order: *alpha, +bias[n], activation `act` / aux (above), then store or atomic
+ * accumulate (accumulate != 0; required for k_splits > 1, C pre-zeroed, linear epilogue only).
  * A, B 16-byte aligned, lda/ldb multiples of 4 and >= the contiguous extent rounded up to 4 (zero padded). */
 PHC_API int phc_gemm(const float* A, int64_t lda, int32_t a_kmajor, const float* B, int64_t ldb, int32_t b_kmajor, float* C,
-             int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha, const float* bias, int32_t relu,
-             const float* mask, int64_t ldmask, int32_t accumulate, int32_t k_splits, void* stream);
+             int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha, const float* bias, int32_t act,
+             float* aux, int64_t ldaux, int32_t accumulate, int32_t k_splits, void* stream);
 /* Blackwell-native variant of phc_gemm: tcgen05.mma kind::tf32 (UMMA) fed by TMA, accumulator in TMEM.  Same epilogue
  * contract.  3xTF32 needs each operand pre-split once by phc_split_tf32 (hi = rna_tf32(x), lo = rna_tf32(x - hi)); hi and
  * lo share the leading dimension.  All four operand arrays 16-byte aligned, lda/ldb multiples of 4 (TMA strides). */
 PHC_API int phc_split_tf32(const float* x, int64_t ldx, int64_t rows, int32_t cols, float* hi, float* lo, int64_t ldo, void* stream);
 PHC_API int phc_gemm_tc5(const float* A_hi, const float* A_lo, int64_t lda, int32_t a_kmajor, const float* B_hi, const float* B_lo,
                  int64_t ldb, int32_t b_kmajor, float* C, float* C_hi /* optional: split copies of C for the next GEMM */,
-                 float* C_lo, int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha, const float* bias, int32_t relu,
-                 const float* mask, int64_t ldmask, int32_t accumulate, int32_t k_splits, void* stream);
+                 float* C_lo, int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha, const float* bias, int32_t act,
+                 float* aux, int64_t ldaux, int32_t accumulate, int32_t k_splits, void* stream);
 /* out[n] (+)= alpha * sum_m X[m*ld + n]   (bias gradients) */
 PHC_API int phc_colsum(const float* X, int64_t ld, int32_t M, int32_t N, float alpha, float* out, int32_t accumulate,
                void* stream);
@@ -310,8 +319,9 @@ PHC_API int phc_axpy2d(const float* x, int64_t ldx, float* y, int64_t ldy, int64
  * discrete != 0: weights are replaced by the one-hot of their arg-max (discrete_moe, humanoid_im_mcp.py:70-72). */
 PHC_API int phc_mcp_combine(const float* weights, int64_t ldw, const float* prim, int64_t ldp, int64_t prim_stride, int64_t n,
                     int32_t K, int32_t A, int32_t discrete, float* out, int64_t ldo, void* stream);
-/* dy *= (y > 0): backward of the ReLU that ends the MCP composer (amp_network_mcp_builder.py:57-63, ending_act: True) */
-PHC_API int phc_relu_backward(float* dy, int64_t ldd, const float* y, int64_t ldy, int64_t n, int32_t d, void* stream);
+/* backward of the activation that ends the MCP composer (amp_network_mcp_builder.py:57-63, ending_act: True):
+ * act = PHC_ACT_RELU: dy *= (aux > 0), aux = the composer output; act = PHC_ACT_SILU: dy *= silu'(aux), aux = pre-activation */
+PHC_API int phc_act_backward(float* dy, int64_t ldd, const float* aux, int64_t ldaux, int64_t n, int32_t d, int32_t act, void* stream);
 /* out[0] = sum g^2 (fp64) over the flat gradient bucket */
 PHC_API int phc_grad_sumsq(const float* g, int64_t n, double* out, void* stream);
 /* nn.utils.clip_grad_norm_(max_norm) (amp_agent.py:670,677) + torch.optim.Adam step (common_agent.py:67) fused over

@@ -13,16 +13,17 @@ def _layer_ids(sd: Dict[str, torch.Tensor], prefix: str) -> List[int]:
     return sorted({int(k[len(prefix):].split(".")[0]) for k in sd if k.startswith(prefix) and k.endswith(".weight")})
 
 
-def mlp_forward(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, ending_act: bool = False) -> torch.Tensor:
+def mlp_forward(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, ending_act: bool = False, act: str = "relu") -> torch.Tensor:
     """nn.Sequential(Linear, ReLU, ..., Linear[, ReLU]) stored under `prefix` + '<2i>.weight/bias'.
     PNN column: pnn.py:22-31 (no activation after the last Linear); composer: amp_network_mcp_builder.py:57-63 and
     network_loader.py:38-40 (activation kept after the last Linear)."""
     ids = _layer_ids(sd, prefix)
+    f = {"relu": torch.relu, "silu": torch.nn.functional.silu}[act]
     h = x
     for n, i in enumerate(ids):
         h = h @ sd[f"{prefix}{i}.weight"].to(h.dtype).T + sd[f"{prefix}{i}.bias"].to(h.dtype)
         if n < len(ids) - 1 or ending_act:
-            h = torch.relu(h)
+            h = f(h)
     return h
 
 

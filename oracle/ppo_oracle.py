@@ -22,23 +22,24 @@ def stack_params(sd: Dict[str, torch.Tensor], prefix: str, head: str, n_hidden: 
 
 
 def minibatch_update(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], cfg: Dict, n_hidden: int = 2,
-                     adam_state=None, step: int = 1, dtype=torch.float32, mu_override=None) -> Dict:
+                     adam_state=None, step: int = 1, dtype=torch.float32, mu_override=None, mlp_act: str = "relu",
+                     n_hidden_disc=None) -> Dict:
     """sd: reference-keyed state dict (fp32, un-padded).  batch: obs_n [B,obs] (already normalised), actions, old_neglogp,
     advantages, old_mu, old_sigma, returns [B,1], amp_agent / amp_replay / amp_demo [Bd, amp] (already normalised)."""
     p = {k: v.clone().to(dtype).requires_grad_(k != "a2c_network.sigma") for k, v in sd.items()}
     batch = {k: (v.to(dtype) if v.dtype.is_floating_point else v) for k, v in batch.items()}
     aw, ab = stack_params(p, "actor_mlp", "mu", n_hidden)
     cw, cb = stack_params(p, "critic_mlp", "value", n_hidden)
-    dw, db = stack_params(p, "_disc_mlp", "_disc_logits", n_hidden)
+    dw, db = stack_params(p, "_disc_mlp", "_disc_logits", n_hidden if n_hidden_disc is None else n_hidden_disc)
     logstd = p["a2c_network.sigma"]
 
-    mu = O.mlp_forward(batch["obs_n"], aw, ab)
+    mu = O.mlp_forward(batch["obs_n"], aw, ab, act=mlp_act)      # mlp.activation of the yaml; the discriminator is relu
     mu_exact = mu.detach().clone()
     if mu_override is not None:
         # evaluate the loss AT the given policy mean (same gradient path): with sigma = exp(-2.9) an fp32-level difference in
         # mu moves neglogp by ~150x that, so loss/backward arithmetic can only be compared tightly at identical mu
         mu = mu + (mu_override.to(dtype) - mu).detach()
-    values = O.mlp_forward(batch["obs_n"], cw, cb)
+    values = O.mlp_forward(batch["obs_n"], cw, cb, act=mlp_act)
     sigma = torch.exp(mu * 0.0 + logstd)
     neglogp = O.gaussian_neglogp(batch["actions"], mu, sigma, (mu * 0.0 + logstd))
     a_loss = O.actor_loss(batch["old_neglogp"], neglogp, batch["advantages"], cfg["e_clip"]).mean()

@@ -20,6 +20,7 @@ PHC_FLAG_NO_COLLISION = 1 << 5
 PHC_FLAG_TERM_USE_MEAN = 1 << 6
 PHC_FLAG_OBS_ONLY = 1 << 7
 PHC_FLAG_REWARD_FROM_CACHE = 1 << 8
+PHC_ACT_NONE, PHC_ACT_RELU, PHC_ACT_SILU, PHC_ACT_SILU_BWD = 0, 1, 2, 3
 PHC_MAX_KEY_BODIES = 8
 PHC_MAX_BODIES = 32
 PHC_MAX_AMP_JOINTS = 32
@@ -103,7 +104,7 @@ SIGNATURES = {
     "phc_scale_sumsq": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, _p, _p]),
     "phc_axpy2d": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.c_int64, C.c_int32, C.c_float, _p, _p]),
     "phc_mcp_combine": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, C.c_int64, _p]),
-    "phc_relu_backward": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.c_int64, C.c_int32, _p]),
+    "phc_act_backward": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _p]),
     "phc_grad_sumsq": (C.c_int, [_p, C.c_int64, _p, _p]),
     "phc_adam_step": (C.c_int, [_p, _p, _p, _p, C.c_int64, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_int64, _p]),

@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include "../../include/phc_b200.h"
+#include "phc_common.cuh"
 
 extern "C" void phc_set_error(const char* msg);
 extern "C" int phc_check_cuda(cudaError_t e, const char* what);
@@ -36,11 +37,11 @@ constexpr int TILE_FLOATS = (BM * (BK + KPAD) > BK * (BM + MPAD)) ? BM * (BK + K
 struct GemmArgs {
   const float* A; const float* B; float* C;
   const float* bias;      // [N] or null
-  const float* mask;      // [M, ldmask] or null: out *= (mask > 0)
+  float* mask;            // `aux` of the C ABI: [M, ldmask] or null (read by the backward modes, written by SiLU forward)
   int M, N, K;
   int64_t lda, ldb, ldc, ldmask;
   float alpha;
-  int relu;               // apply max(x, 0)
+  int relu;               // PHC_ACT_* activation code
   int accumulate;         // atomicAdd into C instead of store
   int k_splits;           // gridDim.z
 };
@@ -198,8 +199,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_3xtf32_kernel(const __gr
           if (n + e >= g.N) continue;
           float v = g.alpha * acc[i][j][2 * h + e];
           if (g.bias && blockIdx.z == 0) v += g.bias[n + e];
-          if (g.relu) v = fmaxf(v, 0.f);
-          if (g.mask) v = (g.mask[(int64_t)m * g.ldmask + n + e] > 0.f) ? v : 0.f;
+          float* aux = g.mask ? g.mask + (int64_t)m * g.ldmask + n + e : nullptr;
+          if (g.relu == PHC_ACT_RELU) v = fmaxf(v, 0.f);
+          if (g.relu == PHC_ACT_SILU) {
+            if (aux) *aux = v;                                   // pre-activation, read back by PHC_ACT_SILU_BWD
+            v = silu_f(v);
+          } else if (aux) {
+            v = (g.relu == PHC_ACT_SILU_BWD) ? v * silu_grad_f(*aux) : ((*aux > 0.f) ? v : 0.f);
+          }
           float* dst = g.C + (int64_t)m * g.ldc + n + e;
           if (g.accumulate) atomicAdd(dst, v);
           else *dst = v;
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
 
 extern "C" int phc_gemm(const float* A, int64_t lda, int32_t a_kmajor, const float* B, int64_t ldb, int32_t b_kmajor,
                         float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha, const float* bias,
-                        int32_t relu, const float* mask, int64_t ldmask, int32_t accumulate, int32_t k_splits,
+                        int32_t relu, float* mask, int64_t ldmask, int32_t accumulate, int32_t k_splits,
                         void* stream) {
   using namespace phc;
   if (!A || !B || !C || M < 0 || N < 0 || K < 0) { phc_set_error("phc_gemm: bad arguments"); return PHC_ERR_INVALID_ARG; }
@@ -247,6 +254,7 @@ extern "C" int phc_gemm(const float* A, int64_t lda, int32_t a_kmajor, const flo
   if (k_splits < 1) k_splits = 1;
   if (k_splits > 1 && !accumulate) { phc_set_error("phc_gemm: split-K needs accumulate=1 (C pre-zeroed)"); return PHC_ERR_INVALID_ARG; }
   if (k_splits > 1 && (relu || mask)) { phc_set_error("phc_gemm: split-K cannot be combined with a non-linear epilogue"); return PHC_ERR_INVALID_ARG; }
+  if (relu < 0 || relu > PHC_ACT_SILU_BWD || (relu == PHC_ACT_SILU_BWD && !mask)) { phc_set_error("phc_gemm: bad activation code"); return PHC_ERR_INVALID_ARG; }
   if (K == 0) { if (!accumulate) cudaMemset2DAsync(C, ldc * 4, 0, (size_t)N * 4, M, static_cast<cudaStream_t>(stream)); return PHC_OK; }
   GemmArgs g;
   g.A = A; g.B = B; g.C = C; g.bias = bias; g.mask = mask; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;

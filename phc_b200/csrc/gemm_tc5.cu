@@ -27,6 +27,7 @@
 #include <stdlib.h>
 
 #include "../../include/phc_b200.h"
+#include "phc_common.cuh"
 
 extern "C" void phc_set_error(const char* msg);
 extern "C" int phc_check_cuda(cudaError_t e, const char* what);
@@ -43,7 +44,7 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*b
 
 struct Args {
   float* C; float* C_hi; float* C_lo;       // optional pre-split copies of the result for the next GEMM (same ldc)
-  const float* bias; const float* mask;
+  const float* bias; float* mask;        // mask = `aux` of the C ABI (read for the backward modes, written by SiLU forward)
   int M, N, K;
   int64_t ldc, ldmask;
   float alpha;
@@ -157,7 +158,8 @@ __host__ __device__ constexpr uint32_t instr_desc(bool a_mn, bool b_mn, int mma_
 __device__ __forceinline__ void epilogue_store(const Args& g, const uint32_t (&r)[32], int m, int n_base, bool add_bias) {
   const int n0 = n_base, c0 = 0;
         float* crow = g.C + (int64_t)m * g.ldc;
-        const float* mrow = g.mask ? g.mask + (int64_t)m * g.ldmask : nullptr;
+        float* mrow = g.mask ? g.mask + (int64_t)m * g.ldmask : nullptr;
+        const int act = g.relu;                               // PHC_ACT_*
         // 16-byte vector path when the row segment is aligned and fully inside the matrix (always for interior tiles)
         const bool vec = !g.accumulate && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
                          (!mrow || (((g.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0)));
@@ -170,14 +172,22 @@ __device__ __forceinline__ void epilogue_store(const Args& g, const uint32_t (&r
           for (int e = 0; e < 4; ++e) {
             float x = g.alpha * __uint_as_float(r[j + e]);
             if (g.bias && add_bias && n + e < g.N) x += g.bias[n + e];
-            if (g.relu) x = fmaxf(x, 0.f);
+            if (act == PHC_ACT_RELU) x = fmaxf(x, 0.f);
             v[e] = x;
           }
           if (vec && n + 3 < g.N) {
-            if (mrow) {
+            if (act == PHC_ACT_SILU) {
+              if (mrow) *reinterpret_cast<float4*>(mrow + n) = make_float4(v[0], v[1], v[2], v[3]);     // pre-activation
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = silu_f(v[e]);
+            } else if (mrow) {
               const float4 mk = *reinterpret_cast<const float4*>(mrow + n);
-              v[0] = mk.x > 0.f ? v[0] : 0.f; v[1] = mk.y > 0.f ? v[1] : 0.f;
-              v[2] = mk.z > 0.f ? v[2] : 0.f; v[3] = mk.w > 0.f ? v[3] : 0.f;
+              if (act == PHC_ACT_SILU_BWD) {
+                v[0] *= silu_grad_f(mk.x); v[1] *= silu_grad_f(mk.y); v[2] *= silu_grad_f(mk.z); v[3] *= silu_grad_f(mk.w);
+              } else {
+                v[0] = mk.x > 0.f ? v[0] : 0.f; v[1] = mk.y > 0.f ? v[1] : 0.f;
+                v[2] = mk.z > 0.f ? v[2] : 0.f; v[3] = mk.w > 0.f ? v[3] : 0.f;
+              }
             }
             *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
             if (g.C_hi) {
@@ -198,7 +208,12 @@ __device__ __forceinline__ void epilogue_store(const Args& g, const uint32_t (&r
             for (int e = 0; e < 4; ++e) {
               if (n + e >= g.N) break;
               float x = v[e];
-              if (mrow) x = (mrow[n + e] > 0.f) ? x : 0.f;
+              if (act == PHC_ACT_SILU) {
+                if (mrow) mrow[n + e] = x;
+                x = silu_f(x);
+              } else if (mrow) {
+                x = (act == PHC_ACT_SILU_BWD) ? x * silu_grad_f(mrow[n + e]) : ((mrow[n + e] > 0.f) ? x : 0.f);
+              }
               if (g.accumulate) atomicAdd(crow + n + e, x);
               else {
                 crow[n + e] = x;
@@ -569,7 +584,7 @@ extern "C" int phc_split_tf32(const float* x, int64_t ldx, int64_t rows, int32_t
 
 extern "C" int phc_gemm_tc5(const float* A_hi, const float* A_lo, int64_t lda, int32_t a_kmajor, const float* B_hi,
                             const float* B_lo, int64_t ldb, int32_t b_kmajor, float* C, float* C_hi, float* C_lo, int64_t ldc,
-                            int32_t M, int32_t N, int32_t K, float alpha, const float* bias, int32_t relu, const float* mask,
+                            int32_t M, int32_t N, int32_t K, float alpha, const float* bias, int32_t relu, float* mask,
                             int64_t ldmask, int32_t accumulate, int32_t k_splits, void* stream) {
   using namespace phc::tc5;
   if (!A_hi || !A_lo || !B_hi || !B_lo || !C || M < 0 || N < 0 || K < 1) { phc_set_error("phc_gemm_tc5: bad arguments"); return PHC_ERR_INVALID_ARG; }
@@ -578,6 +593,7 @@ extern "C" int phc_gemm_tc5(const float* A_hi, const float* A_lo, int64_t lda, i
   for (const float* p : {A_hi, A_lo, B_hi, B_lo})
     if (reinterpret_cast<uintptr_t>(p) & 15) { phc_set_error("phc_gemm_tc5: operands must be 16-byte aligned"); return PHC_ERR_INVALID_ARG; }
   if (k_splits < 1) k_splits = 1;
+  if (relu < 0 || relu > PHC_ACT_SILU_BWD || (relu == PHC_ACT_SILU_BWD && !mask)) { phc_set_error("phc_gemm_tc5: bad activation code"); return PHC_ERR_INVALID_ARG; }
   if (k_splits > 1 && (!accumulate || relu || mask)) { phc_set_error("phc_gemm_tc5: split-K needs accumulate=1 and a linear epilogue"); return PHC_ERR_INVALID_ARG; }
   CUtensorMap tAh, tAl, tBh, tBl;
   if (!make_map(&tAh, A_hi, lda, M, K, a_kmajor) || !make_map(&tAl, A_lo, lda, M, K, a_kmajor) ||

@@ -61,6 +61,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// Activation codes of the GEMM epilogues (include/phc_b200.h PHC_ACT_*): SiLU x*sigmoid(x) with accurate expf + IEEE division
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float silu_grad_f(float z) {        // d/dz z*s(z) = s(z) * (1 + z * (1 - s(z)))
+  const float sg = 1.0f / (1.0f + expf(-z));
+  return sg * (1.0f + z * (1.0f - sg));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

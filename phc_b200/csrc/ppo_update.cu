@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #include "../../include/phc_b200.h"
+#include "phc_common.cuh"
 
 extern "C" void phc_set_error(const char* msg);
 extern "C" int phc_check_cuda(cudaError_t e, const char* what);
@@ -343,13 +344,16 @@ __global__ void mcp_combine_kernel(const float* __restrict__ w, int64_t ldw, con
   }
 }
 
-// dy[r, c] = y[r, c] > 0 ? dy[r, c] : 0     (ReLU that ends the MCP composer, amp_network_mcp_builder.py:57-63)
-__global__ void relu_backward_kernel(float* __restrict__ dy, int64_t ldd, const float* __restrict__ y, int64_t ldy, int64_t n, int d) {
+// backward of the activation that ends the MCP composer (amp_network_mcp_builder.py:57-63, ending_act):
+// ReLU: dy[r, c] = aux[r, c] > 0 ? dy[r, c] : 0 (aux = output);  SiLU: dy[r, c] *= silu'(aux[r, c]) (aux = pre-activation)
+__global__ void act_backward_kernel(float* __restrict__ dy, int64_t ldd, const float* __restrict__ y, int64_t ldy, int64_t n, int d,
+                                    int act) {
   const int64_t total = n * d;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / d;
     const int c = (int)(i - r * d);
-    if (!(y[r * ldy + c] > 0.f)) dy[r * ldd + c] = 0.f;
+    if (act == PHC_ACT_SILU) dy[r * ldd + c] *= silu_grad_f(y[r * ldy + c]);
+    else if (!(y[r * ldy + c] > 0.f)) dy[r * ldd + c] = 0.f;
   }
 }
 
@@ -483,9 +487,9 @@ extern "C" int phc_mcp_combine(const float* weights, int64_t ldw, const float* p
   return phc_check_cuda(cudaGetLastError(), "mcp_combine_kernel");
 }
 
-extern "C" int phc_relu_backward(float* dy, int64_t ldd, const float* y, int64_t ldy, int64_t n, int32_t d, void* stream) {
-  if (!dy || !y || n < 0 || d < 1 || ldd < d || ldy < d) { phc_set_error("phc_relu_backward: bad arguments"); return PHC_ERR_INVALID_ARG; }
+extern "C" int phc_act_backward(float* dy, int64_t ldd, const float* aux, int64_t ldaux, int64_t n, int32_t d, int32_t act, void* stream) {
   if (n == 0) return PHC_OK;
-  relu_backward_kernel<<<ew_grid(n * d), 256, 0, ST(stream)>>>(dy, ldd, y, ldy, n, d); phc_count_launches(1);
-  return phc_check_cuda(cudaGetLastError(), "relu_backward_kernel");
+  if (!dy || !aux || n < 0 || d < 1 || ldd < d || ldaux < d || (act != PHC_ACT_RELU && act != PHC_ACT_SILU)) { phc_set_error("phc_act_backward: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  act_backward_kernel<<<ew_grid(n * d), 256, 0, ST(stream)>>>(dy, ldd, aux, ldaux, n, d, act); phc_count_launches(1);
+  return phc_check_cuda(cudaGetLastError(), "act_backward_kernel");
 }

@@ -44,7 +44,8 @@ class LinearSpec:
 class MLPStack:
     """One MLP = hidden Linear+act layers followed by a linear head."""
 
-    def __init__(self, prefix: str, head: str, in_dim: int, units: Sequence[int], out_dim: int, head_relu: bool = False):
+    def __init__(self, prefix: str, head: str, in_dim: int, units: Sequence[int], out_dim: int, head_relu: bool = False,
+                 activation: str = "relu"):
         self.layers: List[LinearSpec] = []
         d = in_dim
         for i, u in enumerate(units):
@@ -52,7 +53,10 @@ class MLPStack:
             d = u
         self.layers.append(LinearSpec(head, d, out_dim))
         self.in_dim, self.out_dim = in_dim, out_dim
-        self.head_relu = head_relu          # MCP composer: the last Linear is followed by the activation too (ending_act)
+        self.head_relu = head_relu          # MCP composer: the last Linear is followed by the activation too (ending_act;
+                                            # the name is historical: it is the stack's own activation, relu or silu)
+        assert activation in ("relu", "silu")
+        self.activation = activation        # hidden activation: nn.ReLU (im.yaml) or nn.SiLU (im_big / im_pnn_big / im_mcp_big)
 
     @property
     def hidden(self) -> List[LinearSpec]:
@@ -73,25 +77,27 @@ class AMPNetwork:
         `pnn.actors.K`, column `training_prim` is the one evaluated / trained -- pnn.py:11-131, amp_network_pnn_builder.py:23-87)
         or 'amp_mcp' (AMPMCPBuilder: `composer` MLP whose `action_dim` = num_prim outputs keep the final ReLU --
         amp_network_mcp_builder.py:23-91)."""
-        if activation != "relu":
-            raise NotImplementedError("only the relu MLPs of im.yaml are built so far (silu of im_big.yaml: next)")
+        if activation not in ("relu", "silu"):
+            raise NotImplementedError(f"activation {activation!r}: the shipped configs use relu and silu")
+        self.activation = activation        # mlp.activation; the discriminator is relu in every shipped config
         assert kind in ("amp", "amp_pnn", "amp_mcp")
         self.device = torch.device(device)
         self.kind, self.num_prim, self.training_prim = kind, num_prim, training_prim
         self.obs_dim, self.action_dim, self.amp_dim = obs_dim, action_dim, amp_dim
         n_h = len(units)
         if kind == "amp_pnn":
-            self.pnn_actors = [MLPStack(f"pnn.actors.{k}", f"pnn.actors.{k}.{2 * n_h}", obs_dim, units, action_dim) for k in range(num_prim)]
+            self.pnn_actors = [MLPStack(f"pnn.actors.{k}", f"pnn.actors.{k}.{2 * n_h}", obs_dim, units, action_dim, activation=activation)
+                               for k in range(num_prim)]
             self.actor = self.pnn_actors[training_prim]
             actor_stacks = self.pnn_actors
         elif kind == "amp_mcp":
-            st = MLPStack("composer", f"composer.{2 * n_h}", obs_dim, units, action_dim, head_relu=True)
+            st = MLPStack("composer", f"composer.{2 * n_h}", obs_dim, units, action_dim, head_relu=True, activation=activation)
             self.actor, actor_stacks = st, [st]
         else:
-            self.actor = MLPStack("actor_mlp", "mu", obs_dim, units, action_dim)
+            self.actor = MLPStack("actor_mlp", "mu", obs_dim, units, action_dim, activation=activation)
             actor_stacks = [self.actor]
         self.actor_stacks = actor_stacks
-        self.critic = MLPStack("critic_mlp", "value", obs_dim, units, 1)
+        self.critic = MLPStack("critic_mlp", "value", obs_dim, units, 1, activation=activation)
         self.disc = MLPStack("_disc_mlp", "_disc_logits", amp_dim, disc_units, 1)
         off = 0
         for st in (*actor_stacks, self.critic, self.disc):
@@ -227,11 +233,14 @@ class MLPEngine:
 
     # -- raw GEMM ------------------------------------------------------------------------------------------------
     def gemm(self, A, a_k, B, b_k, C, M, N, K, alpha=1.0, bias=None, relu=False, mask=None, accumulate=False, k_splits=1,
-             a_split=None, b_split=None, split_out: bool = False):
-        """a_split / b_split: already up-to-date (hi, lo) companions of the operand (skips the split pass);
+             a_split=None, b_split=None, split_out: bool = False, act: Optional[int] = None):
+        """act: PHC_ACT_* code (default: RELU if relu else NONE); mask: the epilogue's `aux` matrix (see include/phc_b200.h).
+        a_split / b_split: already up-to-date (hi, lo) companions of the operand (skips the split pass);
         split_out: also produce C's companions in the epilogue (tc5 only)."""
         lda = A.stride(0)
         ldb = B.stride(0)
+        if act is None:
+            act = _lib.PHC_ACT_RELU if relu else _lib.PHC_ACT_NONE
         if self.backend == "tc5":
             Ah, Al = a_split or self._weight_parts(A) or self.split(A)
             Bh, Bl = b_split or self._weight_parts(B) or self.split(B)
@@ -240,13 +249,13 @@ class MLPEngine:
                 Ch, Cl = self.companions(C)
             rc = self.lib.phc_gemm_tc5(Ah.data_ptr(), Al.data_ptr(), lda, 1 if a_k else 0, Bh.data_ptr(), Bl.data_ptr(), ldb,
                                        1 if b_k else 0, C.data_ptr(), _ptr(Ch), _ptr(Cl), C.stride(0), M, N, K, alpha, _ptr(bias),
-                                       1 if relu else 0, _ptr(mask), mask.stride(0) if mask is not None else 0,
+                                       act, _ptr(mask), mask.stride(0) if mask is not None else 0,
                                        1 if accumulate else 0, k_splits, _stream())
             if rc:
                 _lib.check(rc, "phc_gemm_tc5")
             return (Ch, Cl) if Ch is not None else None
         rc = self.lib.phc_gemm(A.data_ptr(), lda, 1 if a_k else 0, B.data_ptr(), ldb, 1 if b_k else 0, C.data_ptr(),
-                               C.stride(0), M, N, K, alpha, _ptr(bias), 1 if relu else 0, _ptr(mask),
+                               C.stride(0), M, N, K, alpha, _ptr(bias), act, _ptr(mask),
                                mask.stride(0) if mask is not None else 0, 1 if accumulate else 0, k_splits, _stream())
         if rc:
             _lib.check(rc, "phc_gemm")
@@ -264,6 +273,10 @@ class MLPEngine:
             z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.dev)
             ws = {"h": [z(batch, round4(l.out_dim)) for l in st.hidden], "out": z(batch, round4(st.out_dim)),
                   "dh": [z(batch, round4(l.out_dim)) for l in st.hidden], "dout": z(batch, round4(st.out_dim))}
+            if st.activation == "silu":          # SiLU backward needs the pre-activations
+                ws["z"] = [z(batch, round4(l.out_dim)) for l in st.hidden]
+                if st.head_relu:
+                    ws["z_out"] = z(batch, round4(st.out_dim))
             self._ws[key] = ws
         return ws
 
@@ -274,14 +287,17 @@ class MLPEngine:
         cur, cur_split = x, (self.split(x) if tc5 else None)
         ws["x_split"] = cur_split
         ws["h_split"] = []
-        for l, h in zip(st.hidden, ws["h"]):
-            cur_split = self.gemm(cur, True, net.weight(l), True, h, B, l.out_dim, l.in_dim, bias=net.bias(l), relu=True,
+        silu = st.activation == "silu"
+        for i, (l, h) in enumerate(zip(st.hidden, ws["h"])):
+            cur_split = self.gemm(cur, True, net.weight(l), True, h, B, l.out_dim, l.in_dim, bias=net.bias(l),
+                                  act=_lib.PHC_ACT_SILU if silu else _lib.PHC_ACT_RELU, mask=ws["z"][i] if silu else None,
                                   a_split=cur_split, split_out=True)
             ws["h_split"].append(cur_split)
             cur = h
         l = st.head
+        head_act = _lib.PHC_ACT_NONE if not st.head_relu else (_lib.PHC_ACT_SILU if silu else _lib.PHC_ACT_RELU)
         self.gemm(cur, True, net.weight(l), True, ws["out"], B, l.out_dim, l.in_dim, bias=net.bias(l), a_split=cur_split,
-                  relu=st.head_relu)
+                  act=head_act, mask=ws["z_out"] if (st.head_relu and silu) else None)
         return ws["out"]
 
     # -- backward: ws["dout"] holds d(loss)/d(out) [B, round4(out)]; accumulates into net.grads --------------------
@@ -291,10 +307,13 @@ class MLPEngine:
         acts = [x] + ws["h"]
         act_splits = ([ws.get("x_split")] + list(ws.get("h_split", []))) if tc5 else [None] * len(acts)
         dcur = ws["dout"]
-        if st.head_relu:                                    # MCP composer: ReLU after the head (ending_act)
-            rc = self.lib.phc_relu_backward(dcur.data_ptr(), dcur.stride(0), ws["out"].data_ptr(), ws["out"].stride(0), B, st.out_dim, _stream())
+        if st.head_relu:                                    # MCP composer: activation after the head (ending_act)
+            silu = st.activation == "silu"
+            aux = ws["z_out"] if silu else ws["out"]
+            rc = self.lib.phc_act_backward(dcur.data_ptr(), dcur.stride(0), aux.data_ptr(), aux.stride(0), B, st.out_dim,
+                                           _lib.PHC_ACT_SILU if silu else _lib.PHC_ACT_RELU, _stream())
             if rc:
-                _lib.check(rc, "phc_relu_backward")
+                _lib.check(rc, "phc_act_backward")
         dsplit = self.split(dcur) if tc5 else None          # the loss kernels wrote dout: split it once for both GEMMs
         for li in range(len(st.layers) - 1, -1, -1):
             l = st.layers[li]
@@ -305,9 +324,13 @@ class MLPEngine:
                       k_splits=_splits(tiles, B), a_split=dsplit, b_split=act_splits[li])
             self.colsum(dcur, B, l.out_dim, net.bias(l, grad=True))
             if li > 0:
-                # dX = dY W, masked by the ReLU of the layer below
-                nsplit = self.gemm(dcur, True, net.weight(l), False, ws["dh"][li - 1], B, l.in_dim, l.out_dim, mask=acts[li],
-                                   a_split=dsplit, split_out=True)
+                # dX = dY W, times the derivative of the activation of the layer below (ReLU: its output > 0; SiLU: at z)
+                if st.activation == "silu":
+                    nsplit = self.gemm(dcur, True, net.weight(l), False, ws["dh"][li - 1], B, l.in_dim, l.out_dim,
+                                       mask=ws["z"][li - 1], act=_lib.PHC_ACT_SILU_BWD, a_split=dsplit, split_out=True)
+                else:
+                    nsplit = self.gemm(dcur, True, net.weight(l), False, ws["dh"][li - 1], B, l.in_dim, l.out_dim, mask=acts[li],
+                                       a_split=dsplit, split_out=True)
                 dcur, dsplit = ws["dh"][li - 1], nsplit
             elif dx is not None:
                 self.gemm(dcur, True, net.weight(l), False, dx, B, l.in_dim, l.out_dim, a_split=dsplit)

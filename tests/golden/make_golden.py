@@ -401,6 +401,8 @@ def gen_mcp():
         d["composer/" + k] = v
     with torch.no_grad():
         d["composer_out"] = mlp(x)
+        # im_mcp_big.yaml: activation silu, ending_act true -> SiLU after the last Linear as well
+        d["composer_out_silu"] = load_mcp_mlp({"model": comp}, activation="silu", device="cpu", mlp_name="composer")(x)
     save("mcp.npz", d)
 
 

@@ -135,6 +135,8 @@ def make_lattice(net, seed=0):
     minibatch otherwise contain a few |z| < 1e-6 whose mask legitimately differs between fp64 and fp32-class math)."""
     g = torch.Generator().manual_seed(seed)
     for st in (net.actor, net.critic, net.disc):
+        if st.activation != "relu":      # SiLU is smooth: no borderline units, the default initialisation is kept
+            continue
         gran = 1.0 / 4
         for l in st.hidden:
             w = torch.randint(-1, 2, (l.out_dim, l.in_dim), generator=g).float() / 8
@@ -152,31 +154,36 @@ CFG = dict(e_clip=0.2, critic_coef=5.0, entropy_coef=0.0, bounds_loss_coef=10.0,
 
 
 @pytest.mark.parametrize("backend", ["tc5", "mma"])
-@pytest.mark.parametrize("B,Bd,obs,act,amp,units", [(512, 128, 934, 69, 1960, (256, 128)), (16384, 4096, 934, 69, 1960, (1024, 512)),
-                                                     (300, 100, 50, 7, 30, (64, 32))])
-def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units, backend):
+@pytest.mark.parametrize("B,Bd,obs,act,amp,units,activation",
+                         [(512, 128, 934, 69, 1960, (256, 128), "relu"), (16384, 4096, 934, 69, 1960, (1024, 512), "relu"),
+                          (300, 100, 50, 7, 30, (64, 32), "relu"),
+                          # nn.SiLU actor / critic of im_big.yaml, im_pnn_big.yaml, im_mcp_big.yaml (disc stays relu), 3 and 6 hidden layers
+                          (512, 128, 934, 69, 1960, (256, 192, 128), "silu"), (300, 100, 50, 7, 30, (96, 80, 64, 64, 32, 32), "silu")])
+def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units, activation, backend):
     """forward values, every parameter gradient, the clipped Adam step: CUDA engine vs torch autograd on the CPU."""
     from tests.learner_harness import run_cuda_minibatch
-    net = AMPNetwork(obs, act, amp, units, units, device=DEV, seed=3)
+    disc_units = units[-2:]
+    net = AMPNetwork(obs, act, amp, units, disc_units, activation=activation, device=DEV, seed=3)
     make_lattice(net, seed=B)
     # rescale the mu head so that mu has unit spread: part of the batch sits beyond the +-1 soft bound (bound loss active)
     g0 = torch.Generator().manual_seed(99)
     x0 = lattice_inputs(torch.clamp(torch.randn(256, obs, generator=g0) * 1.5, -5, 5))
     sd0 = {k: v.cpu() for k, v in net.state_dict().items()}
     aw0, ab0 = PO.stack_params(sd0, "actor_mlp", "mu", len(units))
-    spread = float(O.mlp_forward(x0.double(), [w.double() for w in aw0], [b.double() for b in ab0]).std())
+    spread = float(O.mlp_forward(x0.double(), [w.double() for w in aw0], [b.double() for b in ab0], act=activation).std())
     net.weight(net.actor.head).mul_(1.0 / spread)
     net.bias(net.actor.head).mul_(1.0 / spread)
     sd = {k: v.cpu() for k, v in net.state_dict().items()}
     aw, ab = PO.stack_params(sd, "actor_mlp", "mu", len(units))
-    mu_fn = lambda x: O.mlp_forward(x.double(), [w.double() for w in aw], [b.double() for b in ab])
+    mu_fn = lambda x: O.mlp_forward(x.double(), [w.double() for w in aw], [b.double() for b in ab], act=activation)
     batch = _rand_batch(B, Bd, obs, act, amp, seed=B, mu_fn=lambda x: mu_fn(lattice_inputs(x)))
     for k in ("obs_n", "amp_agent", "amp_replay", "amp_demo"):
         batch[k] = lattice_inputs(batch[k])
     got = run_cuda_minibatch(net, batch, CFG, backend=backend)
     # near-exact (fp64) reference; the loss is evaluated at OUR policy mean (see ppo_oracle.minibatch_update: sigma = e^-2.9
     # turns an fp32-level difference in mu into a 150x larger one in neglogp), the forward pass itself is compared below
-    exp = PO.minibatch_update(sd, batch, CFG, n_hidden=len(units), dtype=torch.float64, mu_override=got["mu"].cpu().double())
+    exp = PO.minibatch_update(sd, batch, CFG, n_hidden=len(units), dtype=torch.float64, mu_override=got["mu"].cpu().double(),
+                              mlp_act=activation, n_hidden_disc=len(disc_units))
 
     def scaled(a, b, tol, what):       # error relative to the tensor's scale (entries are sums of large cancelling terms)
         err = float((a.double().cpu() - b.double()).abs().max())

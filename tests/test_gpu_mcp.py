@@ -139,13 +139,15 @@ def test_pnn_training_column_forward_backward(backend):
                 close_scale(gb, sd64[f"a2c_network.{l.name}.bias"].grad, tol=2e-5, what=f"{l.name}.bias grad")
 
 
+@pytest.mark.parametrize("activation", ["relu", "silu"])
 @pytest.mark.parametrize("backend", ["tc5", "mma"])
-def test_mcp_composer_forward_backward(backend):
-    """amp_mcp network: composer keeps the ReLU after its last Linear (ending_act) in forward and backward."""
+def test_mcp_composer_forward_backward(backend, activation):
+    """amp_mcp network: composer keeps the activation after its last Linear (ending_act) in forward and backward
+    (ReLU: im_mcp.yaml, SiLU: im_mcp_big.yaml)."""
     g, _ = golden()
     comp = {k[len("composer/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("composer/")}
     K, D, units = int(g["num_prim"]), int(g["obs_dim"]), [int(u) for u in g["units"]]
-    net = AMPNetwork(D, K, 8, units=units, disc_units=(8,), device=DEV, kind="amp_mcp", num_prim=K)
+    net = AMPNetwork(D, K, 8, units=units, disc_units=(8,), activation=activation, device=DEV, kind="amp_mcp", num_prim=K)
     _load_columns(net, comp)
     assert set(k for k in net.state_dict() if "composer" in k) == set(comp)
     eng = MLPEngine(net, backend)
@@ -155,10 +157,11 @@ def test_mcp_composer_forward_backward(backend):
     x[:, :D] = x_ref.to(DEV)
     ws = eng.workspace("a", net.actor, B)
     out = eng.forward(net.actor, x, ws)
-    ref = torch.from_numpy(g["composer_out"])
+    ref = torch.from_numpy(g["composer_out" if activation == "relu" else "composer_out_silu"])
     close_scale(out[:, :K], ref, what="composer forward")
-    live = ref.abs() > 1e-4                                            # away from the ReLU kink the zero pattern must agree
-    assert torch.equal((out[:, :K].cpu() > 0)[live], (ref > 0)[live])
+    if activation == "relu":
+        live = ref.abs() > 1e-4                                        # away from the ReLU kink the zero pattern must agree
+        assert torch.equal((out[:, :K].cpu() > 0)[live], (ref > 0)[live])
     dout = torch.randn(B, K, generator=torch.Generator().manual_seed(6))
     ws["dout"].zero_()
     ws["dout"][:, :K] = dout.to(DEV)
@@ -166,7 +169,7 @@ def test_mcp_composer_forward_backward(backend):
     eng.backward(net.actor, x, ws)
     torch.cuda.synchronize()
     c64 = {k: v.double().requires_grad_(True) for k, v in comp.items()}
-    (mo.mlp_forward(c64, "a2c_network.composer.", x_ref.double(), ending_act=True) * dout.double()).sum().backward()
+    (mo.mlp_forward(c64, "a2c_network.composer.", x_ref.double(), ending_act=True, act=activation) * dout.double()).sum().backward()
     for l in net.actor.layers:
         close_scale(net.weight(l, True)[:, :l.in_dim], c64[f"a2c_network.{l.name}.weight"].grad, tol=2e-5, what=f"{l.name}.weight grad")
         close_scale(net.bias(l, True), c64[f"a2c_network.{l.name}.bias"].grad, tol=2e-5, what=f"{l.name}.bias grad")

@@ -197,3 +197,5 @@ def test_mcp_composer_keeps_final_relu():
     out = mo.mlp_forward(comp, "a2c_network.composer.", torch.from_numpy(g["x"]), ending_act=True)
     torch.testing.assert_close(out, torch.from_numpy(g["composer_out"]), rtol=1e-6, atol=1e-6)
     assert (g["composer_out"] == 0).any() and (g["composer_out"] >= 0).all()
+    out = mo.mlp_forward(comp, "a2c_network.composer.", torch.from_numpy(g["x"]), ending_act=True, act="silu")
+    torch.testing.assert_close(out, torch.from_numpy(g["composer_out_silu"]), rtol=1e-6, atol=1e-6)
