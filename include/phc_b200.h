@@ -57,8 +57,13 @@ typedef struct PhcMotionLib {
   int64_t num_frames_total;
   int32_t num_motions;
   int32_t num_bodies;   /* J */
-  int32_t body_stride;  /* floats per body record  = round_up(13*J, 4)           */
-  int32_t joint_stride; /* floats per joint record = round_up(4*J + 3*(J-1), 4)  */
+  int32_t body_stride;  /* floats per body record  = round_up(13*(J+E), 4)       */
+  int32_t joint_stride; /* floats per joint record = round_up(4*J + 3*(J-1), 4), or round_up(2*D, 4) for hinge-joint robots */
+  /* Robots (humanoid_type h1 / g1: phc/utils/motion_lib_real.py:236-361, humanoid_im.py:74-82, :916-923).  Zero for SMPL. */
+  int32_t num_ext_bodies; /* E: "extend" bodies (head, hands ...) carried as records J..J+E-1 of every frame (the *_t tables);
+                             they enter the tracking reward only                                                        */
+  int32_t num_dofs;       /* D > 0: every joint is one hinge dof; the joint record is [dof_pos[D] | dof_vel[D]] and dof_pos is
+                             interpolated linearly (motion_lib_real.py:283-285); 0: SMPL, D = 3(J-1) via local rotations   */
 } PhcMotionLib;
 
 /* Per-env copy of the motion parameters the step needs, gathered once by phc_env_motion_gather whenever motion_ids change
@@ -73,8 +78,13 @@ typedef struct PhcEnvMotion {
 
 PHC_API int phc_env_motion_gather(const PhcMotionLib* lib, const int64_t* motion_ids, int64_t n, PhcEnvMotion* out, void* stream);
 
-PHC_API int phc_motion_body_stride(int32_t num_bodies);
+PHC_API int phc_motion_body_stride(int32_t num_bodies);        /* pass J + E for robots */
 PHC_API int phc_motion_joint_stride(int32_t num_bodies);
+PHC_API int phc_motion_dof_stride(int32_t num_dofs);           /* joint_stride of a hinge-joint robot: round_up(2*D, 4) */
+/* Robot joint records: dof_pos[F, D], dof_vel[F, D] (motion_lib_real's dof_pos / dvs tables) -> frames_joint[F, dof_stride].
+ * The body records of a robot are packed with phc_motion_pack(gts_t, grs_t, gvs_t, gavs_t, NULL, NULL, F, J + E, ...). */
+PHC_API int phc_motion_pack_dofs(const float* dof_pos, const float* dof_vel, int64_t num_frames_total, int32_t num_dofs,
+                         float* frames_joint, void* stream);
 
 /* Pack the reference's separate tables into the records above (one pass, HBM-bound).
  * gts[F,J,3] grs[F,J,4] gvs[F,J,3] gavs[F,J,3] -> frames_body[F,body_stride];
@@ -92,12 +102,17 @@ typedef struct PhcMotionStateOut {
   float* rb_rot;       /* [n, J, 4] */
   float* body_vel;     /* [n, J, 3] */
   float* body_ang_vel; /* [n, J, 3] */
-  float* dof_pos;      /* [n, 3(J-1)] */
-  float* dof_vel;      /* [n, 3(J-1)] */
+  float* dof_pos;      /* [n, 3(J-1)] (SMPL) or [n, D] (robot) */
+  float* dof_vel;      /* [n, 3(J-1)] (SMPL) or [n, D] (robot) */
   float* root_pos;     /* [n, 3] */
   float* root_rot;     /* [n, 4] */
   float* root_vel;     /* [n, 3] */
   float* root_ang_vel; /* [n, 3] */
+  /* robots: the same four quantities for all J + E bodies (rg_pos_t, rg_rot_t, body_vel_t, body_ang_vel_t) */
+  float* rg_pos_t;       /* [n, J+E, 3] */
+  float* rg_rot_t;       /* [n, J+E, 4] */
+  float* body_vel_t;     /* [n, J+E, 3] */
+  float* body_ang_vel_t; /* [n, J+E, 3] */
 } PhcMotionStateOut;
 
 PHC_API int phc_motion_state(const PhcMotionLib* lib, const int64_t* motion_ids, const float* motion_times,
@@ -115,6 +130,7 @@ PHC_API int phc_motion_state(const PhcMotionLib* lib, const int64_t* motion_ids,
  *     build_amp_observations_smpl (:966-1011)
  * progress must already hold the incremented step counter (humanoid.py:1637).
  * ---------------------------------------------------------------------------------------------------------- */
+#define PHC_MAX_EXT_BODIES 8
 #define PHC_FLAG_UPRIGHT (1u << 0)         /* robot.has_upright_start                                   */
 #define PHC_FLAG_LOCAL_ROOT_OBS (1u << 1)  /* env.local_root_obs                                        */
 #define PHC_FLAG_ROOT_HEIGHT_OBS (1u << 2) /* env.root_height_obs (also the AMP root height column)     */
@@ -132,7 +148,7 @@ PHC_API int phc_motion_state(const PhcMotionLib* lib, const int64_t* motion_ids,
 typedef struct PhcStepArgs {
   /* ---- simulator state (inputs; contract of Humanoid._setup_tensors, humanoid.py:179-247) ---- */
   const float* body_state;  /* [N, bodies_per_env, 13]: pos rot vel ang_vel; only the first J bodies are read */
-  const float* dof_state;   /* [N, D, 2] (pos, vel) interleaved, D = 3(J-1)                                    */
+  const float* dof_state;   /* [N, D, 2] (pos, vel) interleaved, D = 3(J-1), or lib.num_dofs for robots          */
   const float* dof_force;   /* [N, D] or NULL when PHC_FLAG_POWER_REWARD is clear                              */
   int32_t bodies_per_env;
   /* ---- per-env motion bookkeeping ---- */
@@ -158,6 +174,10 @@ typedef struct PhcStepArgs {
   float term_thresh[PHC_MAX_BODIES]; /* [J] termination distance per body, +inf for bodies outside reset_bodies (by
                                         value: configuration travels in the kernel parameters, not through a dependent load) */
   float term_dist_mean;      /* threshold of the first reset body (used by PHC_FLAG_TERM_USE_MEAN)       */
+  /* robots: simulated pose of extend body e = body_rot[parent] * pos_in_parent + body_pos[parent], rotation = parent's
+   * (humanoid_im.py:917-919); lib.num_ext_bodies entries */
+  int32_t ext_parent[PHC_MAX_EXT_BODIES];
+  float ext_pos[PHC_MAX_EXT_BODIES][3];
   int32_t num_key_bodies;
   int32_t key_bodies[PHC_MAX_KEY_BODIES]; /* _key_body_ids */
   int32_t amp_joints[PHC_MAX_AMP_JOINTS]; /* [num_amp_joints] joint indices (dof_subset / 3) kept in the AMP obs */
@@ -197,6 +217,8 @@ typedef struct PhcStepArgs {
 PHC_API int phc_self_obs_dim(int32_t num_bodies, uint32_t flags);                    /* 1 + 15J - 3          */
 PHC_API int phc_task_obs_dim(int32_t num_bodies, int32_t time_steps);                /* 24 J T               */
 PHC_API int phc_amp_obs_dim(int32_t num_amp_joints, int32_t num_key_bodies, uint32_t flags); /* 13 + 9 nj + 3 nk */
+/* build_amp_observations_robot (humanoid_amp.py:1062-1104): [root_h?, rot6, vel3, ang_vel3, dof_pos[D], dof_vel[D], key 3 nk] */
+PHC_API int phc_amp_obs_dim_robot(int32_t num_dofs, int32_t num_key_bodies, uint32_t flags); /* 13 + 2 D + 3 nk */
 
 PHC_API int phc_env_step(const PhcStepArgs* args, void* stream);
 

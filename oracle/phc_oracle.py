@@ -402,6 +402,113 @@ def amp_obs_demo(tab: MotionTables, cfg: StepConfig, motion_ids: Tensor, times0:
 
 
 # ----------------------------------------------------------------------------------------------
+# Hinge-joint robots (H1 / G1): phc/utils/motion_lib_real.py:236-361, humanoid_im.py:74-82 and :916-923 (extend bodies in
+# the reward), humanoid_amp.py:1062-1104 (build_amp_observations_robot)
+# ----------------------------------------------------------------------------------------------
+class RobotTables:
+    """motion_lib_real's tables: gts/grs/gvs/gavs over the J simulated bodies, the *_t tables over J + E (bodies then
+    extend bodies), dof_pos / dvs [F, D]."""
+
+    def __init__(self, gts_t, grs_t, gvs_t, gavs_t, dof_pos, dvs, lengths, num_frames, dts, length_starts, num_bodies):
+        self.gts_t, self.grs_t, self.gvs_t, self.gavs_t, self.dof_pos, self.dvs = gts_t, grs_t, gvs_t, gavs_t, dof_pos, dvs
+        self.lengths, self.num_frames, self.dts, self.length_starts, self.num_bodies = lengths, num_frames, dts, length_starts, num_bodies
+
+
+def motion_state_robot(tab: RobotTables, ids: Tensor, times: Tensor, offset: Optional[Tensor] = None) -> Dict[str, Tensor]:
+    """MotionLibReal.get_motion_state (motion_lib_real.py:236-361): dof_pos is interpolated linearly like dof_vel."""
+    J = tab.num_bodies
+    i0, i1, blend = frame_blend(times, tab.lengths[ids], tab.num_frames[ids], tab.dts[ids])
+    f0 = i0 + tab.length_starts[ids]
+    f1 = i1 + tab.length_starts[ids]
+    b1 = blend.view(-1, 1)
+    b = blend.view(-1, 1, 1)
+    lerp = lambda t: (1.0 - b) * t[f0] + b * t[f1]
+    pos_t = lerp(tab.gts_t)
+    if offset is not None:
+        pos_t = pos_t + offset[:, None, :]
+    vel_t, ang_t = lerp(tab.gvs_t), lerp(tab.gavs_t)
+    rot_t = slerp(tab.grs_t[f0], tab.grs_t[f1], b)
+    dof_vel = (1.0 - b1) * tab.dvs[f0] + b1 * tab.dvs[f1]
+    dof_pos = (1.0 - b1) * tab.dof_pos[f0] + b1 * tab.dof_pos[f1]
+    pos, rot, vel, ang = pos_t[:, :J], rot_t[:, :J], vel_t[:, :J], ang_t[:, :J]
+    return dict(root_pos=pos[:, 0].clone(), root_rot=rot[:, 0].clone(), dof_pos=dof_pos, root_vel=vel[:, 0].clone(),
+                root_ang_vel=ang[:, 0].clone(), dof_vel=dof_vel, rg_pos=pos, rb_rot=rot, body_vel=vel, body_ang_vel=ang,
+                rg_pos_t=pos_t, rg_rot_t=rot_t, body_vel_t=vel_t, body_ang_vel_t=ang_t)
+
+
+def amp_obs_robot(root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_pos, local_root_obs=True,
+                  root_height_obs=True, upright=True) -> Tensor:
+    """build_amp_observations_robot (humanoid_amp.py:1062-1104)."""
+    if not upright:
+        root_rot = strip_base_rot(root_rot)
+    hinv = heading_q(root_rot, inverse=True)
+    rr = tan_norm(qmul(hinv, root_rot) if local_root_obs else root_rot)
+    lv, lw = qrot(hinv, root_vel), qrot(hinv, root_ang_vel)
+    lk = key_pos - root_pos[:, None, :]
+    K = lk.shape[1]
+    lk = qrot(hinv[:, None, :].expand(-1, K, -1).reshape(-1, 4), lk.reshape(-1, 3)).view(lk.shape[0], K * 3)
+    parts = ([root_pos[:, 2:3]] if root_height_obs else []) + [rr, lv, lw, dof_pos, dof_vel, lk]
+    return torch.cat(parts, dim=-1)
+
+
+def env_step_robot(tab: RobotTables, cfg: "StepConfig", ext_parents, ext_pos, body_state: Tensor, dof_state: Tensor,
+                   dof_force: Tensor, progress: Tensor, motion_ids: Tensor, start_times: Tensor, start_offsets: Tensor,
+                   global_offset: Tensor, amp_hist: Tensor) -> Dict[str, Tensor]:
+    """env_step for humanoid_type h1 / g1: the tracking reward also sees the extend bodies (humanoid_im.py:916-923); AMP
+    observation from build_amp_observations_robot; observations and reset as for SMPL on the J simulated bodies."""
+    N, J, _ = body_state.shape
+    bp, br, bv, bw = body_state[..., 0:3], body_state[..., 3:7], body_state[..., 7:10], body_state[..., 10:13]
+    dof_pos, dof_vel = dof_state[..., 0], dof_state[..., 1]
+    par = torch.as_tensor(list(ext_parents))
+    off = torch.as_tensor(ext_pos, dtype=torch.float32)
+    E = len(par)
+    out: Dict[str, Tensor] = {}
+    t_now = progress * cfg.dt + start_times + start_offsets
+    ref = motion_state_robot(tab, motion_ids, t_now, global_offset)
+    ext_cur = qrot(br[:, par].reshape(-1, 4), off[None].expand(N, E, 3).reshape(-1, 3)).view(N, E, 3) + bp[:, par]
+    bp_e = torch.cat((bp, ext_cur), dim=1)
+    br_e = torch.cat((br, br[:, par]), dim=1)
+    rp_e = torch.cat((ref["rg_pos"], ref["rg_pos_t"][:, J:]), dim=1)
+    rr_e = torch.cat((ref["rb_rot"], ref["rg_rot_t"][:, J:]), dim=1)
+    rew, raw = imitation_reward(bp_e, br_e, bv, bw, rp_e, rr_e, ref["body_vel"], ref["body_ang_vel"], cfg.rwd)
+    if cfg.power_reward:
+        pw = power_reward(dof_force, dof_vel, progress, cfg.power_coef)
+        rew = rew + pw
+        raw = torch.cat((raw, pw[:, None]), dim=-1)
+    out["rew"], out["reward_raw"] = rew, raw
+    rb = list(range(J)) if cfg.reset_bodies is None else list(cfg.reset_bodies)
+    td = torch.full((J,), cfg.term_dist) if not torch.is_tensor(cfg.term_dist) else cfg.term_dist
+    pass_time = t_now >= tab.lengths[motion_ids]
+    out["reset"], out["terminate"] = im_reset(progress, bp[:, rb], ref["rg_pos"][:, rb], pass_time, td[rb],
+                                              cfg.early_term, cfg.no_collision, cfg.use_mean)
+    t_next = (progress + 1) * cfg.dt + start_times + start_offsets
+    refn = motion_state_robot(tab, motion_ids, t_next, global_offset)
+    so = self_obs(bp, br, bv, bw, cfg.local_root_obs, cfg.root_height_obs, cfg.upright)
+    to = task_obs_v6(bp[:, 0], br[:, 0], bp, br, bv, bw, refn["rg_pos"], refn["rb_rot"], refn["body_vel"], refn["body_ang_vel"],
+                     1, cfg.upright)
+    out["obs"] = torch.cat((so, to), dim=-1)
+    out["ref_body_pos"], out["ref_body_rot"], out["ref_body_vel"] = refn["rg_pos"], refn["rb_rot"], refn["body_vel"]
+    out["ref_pose_t"] = torch.cat((refn["rg_pos_t"], refn["rg_rot_t"], refn["body_vel_t"], refn["body_ang_vel_t"]), dim=-1)
+    cur = amp_obs_robot(bp[:, 0], br[:, 0], bv[:, 0], bw[:, 0], dof_pos, dof_vel, bp[:, cfg.key_bodies], cfg.local_root_obs,
+                        cfg.root_height_obs, cfg.upright)
+    out["amp_obs"] = cur
+    out["amp_obs_buf"] = torch.cat((cur[:, None], amp_hist[:, :-1]), dim=1)
+    return out
+
+
+def amp_obs_demo_robot(tab: RobotTables, cfg: "StepConfig", motion_ids: Tensor, times0: Tensor, first_step: int = 0,
+                       num_steps: Optional[int] = None) -> Tensor:
+    S = cfg.num_amp_steps if num_steps is None else num_steps
+    n = len(motion_ids)
+    k = -cfg.dt * (torch.arange(0, S) + first_step)
+    times = (times0[:, None] + k[None, :]).flatten()
+    st = motion_state_robot(tab, motion_ids.repeat_interleave(S), times)
+    a = amp_obs_robot(st["root_pos"], st["root_rot"], st["root_vel"], st["root_ang_vel"], st["dof_pos"], st["dof_vel"],
+                      st["rg_pos"][:, cfg.key_bodies], cfg.local_root_obs, cfg.root_height_obs, cfg.upright)
+    return a.view(n, S, -1)
+
+
+# ----------------------------------------------------------------------------------------------
 # K8  running mean/std   (reference: phc/utils/running_mean_std.py:56-109)
 # ----------------------------------------------------------------------------------------------
 def rms_normalize(x: Tensor, mean64: Tensor, var64: Tensor, eps: float = 1e-5) -> Tensor:

@@ -24,6 +24,7 @@ PHC_ACT_NONE, PHC_ACT_RELU, PHC_ACT_SILU, PHC_ACT_SILU_BWD = 0, 1, 2, 3
 PHC_MAX_KEY_BODIES = 8
 PHC_MAX_BODIES = 32
 PHC_MAX_AMP_JOINTS = 32
+PHC_MAX_EXT_BODIES = 8
 
 _p = C.c_void_p
 
@@ -36,12 +37,12 @@ class PhcMotionLib(C.Structure):
     _fields_ = [("frames_body", _p), ("frames_joint", _p), ("motion_len", _p), ("motion_dt", _p),
                 ("motion_num_frames", _p), ("length_starts", _p), ("num_frames_total", C.c_int64),
                 ("num_motions", C.c_int32), ("num_bodies", C.c_int32), ("body_stride", C.c_int32),
-                ("joint_stride", C.c_int32)]
+                ("joint_stride", C.c_int32), ("num_ext_bodies", C.c_int32), ("num_dofs", C.c_int32)]
 
 
 class PhcMotionStateOut(C.Structure):
     _fields_ = [(n, _p) for n in ("rg_pos", "rb_rot", "body_vel", "body_ang_vel", "dof_pos", "dof_vel", "root_pos",
-                                  "root_rot", "root_vel", "root_ang_vel")]
+                                  "root_rot", "root_vel", "root_ang_vel", "rg_pos_t", "rg_rot_t", "body_vel_t", "body_ang_vel_t")]
 
 
 class PhcStepArgs(C.Structure):
@@ -54,6 +55,7 @@ class PhcStepArgs(C.Structure):
         ("k_pos", C.c_float), ("k_rot", C.c_float), ("k_vel", C.c_float), ("k_ang_vel", C.c_float),
         ("w_pos", C.c_float), ("w_rot", C.c_float), ("w_vel", C.c_float), ("w_ang_vel", C.c_float),
         ("power_coef", C.c_float), ("term_thresh", C.c_float * PHC_MAX_BODIES), ("term_dist_mean", C.c_float),
+        ("ext_parent", C.c_int32 * PHC_MAX_EXT_BODIES), ("ext_pos", (C.c_float * 3) * PHC_MAX_EXT_BODIES),
         ("num_key_bodies", C.c_int32), ("key_bodies", C.c_int32 * PHC_MAX_KEY_BODIES),
         ("amp_joints", C.c_int32 * PHC_MAX_AMP_JOINTS), ("num_amp_joints", C.c_int32),
         ("obs", _p), ("obs_stride", C.c_int64), ("rew", _p), ("reward_raw", _p), ("reset", _p), ("terminate", _p),
@@ -71,6 +73,9 @@ SIGNATURES = {
     "phc_launch_count": (C.c_int64, []),
     "phc_env_motion_gather": (C.c_int, [C.POINTER(PhcMotionLib), _p, C.c_int64, _p, _p]),
     "phc_motion_body_stride": (C.c_int, [C.c_int32]),
+    "phc_motion_dof_stride": (C.c_int, [C.c_int32]),
+    "phc_motion_pack_dofs": (C.c_int, [_p, _p, C.c_int64, C.c_int32, _p, _p]),
+    "phc_amp_obs_dim_robot": (C.c_int, [C.c_int32, C.c_int32, C.c_uint32]),
     "phc_motion_joint_stride": (C.c_int, [C.c_int32]),
     "phc_motion_pack": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int64, C.c_int32, _p, _p, _p]),
     "phc_motion_state": (C.c_int, [C.POINTER(PhcMotionLib), _p, _p, _p, C.c_int64, C.POINTER(PhcMotionStateOut), _p]),

@@ -36,12 +36,12 @@ struct StepLayout {      // per-warp shared-memory carve-up, in floats (all mult
 
 __host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
 
-__host__ __device__ inline StepLayout make_layout(int J, int T, int body_stride, int A, int obs_dim, bool alias_obs) {
+__host__ __device__ inline StepLayout make_layout(int J, int T, int body_stride, int A, int obs_dim, bool alias_obs, int D = 0) {
   StepLayout L;
   L.rslots = 2 * body_stride;
   L.state = round4(J * kBodyRec);
   L.oslots = 2 * T * body_stride;
-  L.dof = round4(2 * 3 * (J - 1));
+  L.dof = round4(2 * (D > 0 ? D : 3 * (J - 1)));
   L.amp = round4(A > 0 ? A : 4);
   L.obs = alias_obs ? 0 : round4(obs_dim);
   L.total = L.rslots + L.state + L.oslots + L.dof + L.amp + L.obs + 4;
@@ -87,10 +87,15 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   if (a.only_where && a.only_where[env] == 0) return;  // masked subset (reset path)
   const bool obs_only = a.flags & PHC_FLAG_OBS_ONLY;
 
-  const int J = JT > 0 ? JT : a.lib.num_bodies, D = 3 * (J - 1);
+  // JT > 0 is the SMPL specialisation (spherical joints, no extend bodies); robots (hinge joints, E extend bodies that enter
+  // the tracking reward as lanes J..J+E-1) take the run-time build
+  const int J = JT > 0 ? JT : a.lib.num_bodies;
+  const int E = JT > 0 ? 0 : a.lib.num_ext_bodies;
+  const bool robot = JT > 0 ? false : a.lib.num_dofs > 0;
+  const int D = robot ? a.lib.num_dofs : 3 * (J - 1);
   const int T = (T_MAX == 1) ? 1 : a.time_steps;
   const int BS = JT > 0 ? round4(JT * kBodyRec) : a.lib.body_stride;
-  const StepLayout L = make_layout(J, T, BS, amp_dim, obs_dim, alias_obs);
+  const StepLayout L = make_layout(J, T, BS, amp_dim, obs_dim, alias_obs, robot ? D : 0);
   float* const w_base = smem + (size_t)warp * L.total;
   float* const s_rslots = w_base;
   float* const s_state = s_rslots + L.rslots;
@@ -248,8 +253,14 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
 
   // ================= phase A: everything that reads the reward slots / simulator block =======================
   const bool has_body = lane < J;
+  const bool has_ext = E > 0 && lane >= J && lane < J + E;   // robots: lanes J..J+E-1 carry the "extend" bodies (reward only)
   const int j = has_body ? lane : 0;
-  const BodyRec sim = load_body(s_state + j * kBodyRec);        // stride-13 words: bank-conflict free
+  const int jr = (has_body || has_ext) ? lane : 0;           // record of the reference pose this lane tracks
+  BodyRec sim = load_body(s_state + (has_ext ? a.ext_parent[lane - J] : j) * kBodyRec);   // stride-13 words: bank-conflict free
+  if (has_ext) {   // parent_rot * pos_in_parent + parent_pos, rotation = the parent's (humanoid_im.py:917-919)
+    const V3 off = v3(a.ext_pos[lane - J][0], a.ext_pos[lane - J][1], a.ext_pos[lane - J][2]);
+    sim.p = qrot(sim.q, off) + sim.p;
+  }
   const V3 root_p = v3(s_state[0], s_state[1], s_state[2]);
   const bool has_h = a.flags & PHC_FLAG_ROOT_HEIGHT_OBS;
   const int base0 = has_h ? 1 : 0;
@@ -265,17 +276,20 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     // reward + termination against the reference pose at t_now
     float e_pos = 0.f, e_rot = 0.f, e_vel = 0.f, e_ang = 0.f, dist = 0.f;
     {
-      const BodyRec ref = from_cache ? load_body(s_rslots + j * kBodyRec)
-                                     : blend_body(pr0 + j * kBodyRec, pr1 + j * kBodyRec, bl_r, goff);
-      if (has_body) {
-        const V3 dp = ref.p - sim.p, dv = ref.v - sim.v, dw = ref.w - sim.w;
+      const BodyRec ref = from_cache ? load_body(s_rslots + jr * kBodyRec)
+                                     : blend_body(pr0 + jr * kBodyRec, pr1 + jr * kBodyRec, bl_r, goff);
+      if (has_body || has_ext) {      // position / rotation terms: all J + E bodies; velocity terms: the J simulated ones
+        const V3 dp = ref.p - sim.p;
         const float sp = dp.x * dp.x + dp.y * dp.y + dp.z * dp.z;
         e_pos = sp / 3.0f;
-        e_vel = (dv.x * dv.x + dv.y * dv.y + dv.z * dv.z) / 3.0f;
-        e_ang = (dw.x * dw.x + dw.y * dw.y + dw.z * dw.z) / 3.0f;
         const float ang = quat_angle(qmul(ref.q, qconj(sim.q)));
         e_rot = ang * ang;
-        dist = sqrtf(sp);
+        if (has_body) {
+          const V3 dv = ref.v - sim.v, dw = ref.w - sim.w;
+          e_vel = (dv.x * dv.x + dv.y * dv.y + dv.z * dv.z) / 3.0f;
+          e_ang = (dw.x * dw.x + dw.y * dw.y + dw.z * dw.z) / 3.0f;
+          dist = sqrtf(sp);
+        }
       }
     }
     bool fallen;
@@ -290,8 +304,8 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
         fallen = __any_sync(0xffffffffu, has_body && dist > thr);
       }
     }
-    e_pos = warp_sum(e_pos) / (float)J;
-    e_rot = warp_sum(e_rot) / (float)J;
+    e_pos = warp_sum(e_pos) / (float)(J + E);
+    e_rot = warp_sum(e_rot) / (float)(J + E);
     e_vel = warp_sum(e_vel) / (float)J;
     e_ang = warp_sum(e_ang) / (float)J;
     power = warp_sum(power);
@@ -337,7 +351,10 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
       st3(o + 6, qrot_z(hinv, sim.v));      // lane 0 holds body 0 = the root
       st3(o + 9, qrot_z(hinv, sim.w));
     }
-    for (int k = lane; k < nj; k += 32) {
+    if (robot) {       // build_amp_observations_robot (humanoid_amp.py:1062-1104): raw hinge angles, then velocities
+      for (int d = lane; d < D; d += 32) { o[12 + d] = s_dof[2 * d]; o[12 + D + d] = s_dof[2 * d + 1]; }
+    }
+    for (int k = lane; k < (robot ? 0 : nj); k += 32) {
       const int jid = a.amp_joints[k];
       const float* dj = s_dof + 6 * jid;             // (pos, vel) pairs of the joint's 3 dofs
       st6(o + 12 + 6 * k, tan_norm(exp_map_to_quat(v3(dj[0], dj[2], dj[4]))));
@@ -345,7 +362,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     }
     if (lane < nk) {
       const float* kb = s_state + a.key_bodies[lane] * kBodyRec;
-      st3(o + 12 + 9 * nj + 3 * lane, qrot_z(hinv, v3(kb[0], kb[1], kb[2]) - root_p));
+      st3(o + 12 + (robot ? 2 * D : 9 * nj) + 3 * lane, qrot_z(hinv, v3(kb[0], kb[1], kb[2]) - root_p));
     }
   }
   // rows leave shared memory as TMA bulk stores (one instruction per row) when source, destination and size are 16-byte
@@ -380,13 +397,14 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   const bool cache_bulk = g_cache && T_MAX == 1;     // single sample: the blended pose is staged over its own frame slot
 #pragma unroll
   for (int t = 0; t < T_MAX; ++t) {
-    if (t < T && has_body) {
-      const BodyRec ref = blend_body(po0[t] + j * kBodyRec, po1[t] + j * kBodyRec, bl_o[t], goff);
+    if (t < T && (has_body || (has_ext && t == 0 && g_cache))) {
+      const BodyRec ref = blend_body(po0[t] + jr * kBodyRec, po1[t] + jr * kBodyRec, bl_o[t], goff);
       if (t == 0 && g_cache) {
         // lane j has consumed records j of both frames: slot 0 of the bracket becomes the row of the pose cache
-        float* c = (cache_bulk ? s_oslots : g_cache) + j * kBodyRec;
+        float* c = (cache_bulk ? s_oslots : g_cache) + jr * kBodyRec;
         st3(c, ref.p); c[3] = ref.q.x; c[4] = ref.q.y; c[5] = ref.q.z; c[6] = ref.q.w; st3(c + 7, ref.v); st3(c + 10, ref.w);
       }
+      if (!has_body) continue;         // extend bodies: reward only, no observation columns
       float* tb = s_obs + self_dim + t * 24 * J;
       st3(tb + 3 * j, qrot_z(hinv, ref.p - sim.p));
       st6(tb + 3 * J + 6 * j, tan_norm(qmul(qmul(hinv, qmul(ref.q, qconj(sim.q))), hq)));
@@ -455,6 +473,9 @@ extern "C" int phc_task_obs_dim(int32_t J, int32_t T) { return 24 * J * T; }
 extern "C" int phc_amp_obs_dim(int32_t nj, int32_t nk, uint32_t flags) {
   return ((flags & PHC_FLAG_ROOT_HEIGHT_OBS) ? 1 : 0) + 12 + 9 * nj + 3 * nk;
 }
+extern "C" int phc_amp_obs_dim_robot(int32_t D, int32_t nk, uint32_t flags) {
+  return ((flags & PHC_FLAG_ROOT_HEIGHT_OBS) ? 1 : 0) + 12 + 2 * D + 3 * nk;
+}
 
 extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
   using namespace phc;
@@ -472,21 +493,26 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
     phc_set_error("phc_env_step: bad sizes (num_envs >= 0, 1 <= J <= bodies_per_env, T >= 1)");
     return PHC_ERR_INVALID_ARG;
   }
-  if (J > PHC_MAX_BODIES) { phc_set_error("phc_env_step: num_bodies > 32 needs the multi-body-per-lane path (not built yet)"); return PHC_ERR_UNSUPPORTED; }
+  const int E = a->lib.num_ext_bodies, DR = a->lib.num_dofs;
+  if (E < 0 || E > PHC_MAX_EXT_BODIES || DR < 0) { phc_set_error("phc_env_step: bad num_ext_bodies / num_dofs"); return PHC_ERR_INVALID_ARG; }
+  if (J + E > PHC_MAX_BODIES || DR > 3 * 32) { phc_set_error("phc_env_step: more than 32 bodies (incl. extend bodies) needs the multi-body-per-lane path (not built yet)"); return PHC_ERR_UNSUPPORTED; }
+  for (int e2 = 0; e2 < E; ++e2)
+    if (a->ext_parent[e2] < 0 || a->ext_parent[e2] >= J) { phc_set_error("phc_env_step: ext_parent out of range"); return PHC_ERR_INVALID_ARG; }
   if (T > 4) { phc_set_error("phc_env_step: time_steps > 4 not supported"); return PHC_ERR_UNSUPPORTED; }
   if ((a->flags & PHC_FLAG_POWER_REWARD) && !a->dof_force) { phc_set_error("phc_env_step: power reward needs dof_force"); return PHC_ERR_INVALID_ARG; }
   if (a->num_key_bodies < 0 || a->num_key_bodies > PHC_MAX_KEY_BODIES || a->num_amp_joints < 0 || a->num_amp_joints > PHC_MAX_AMP_JOINTS) {
     phc_set_error("phc_env_step: bad key body / amp joint lists"); return PHC_ERR_INVALID_ARG;
   }
-  if (a->lib.body_stride != phc_motion_body_stride(J) || (reinterpret_cast<uintptr_t>(a->lib.frames_body) & 15)) {
-    phc_set_error("phc_env_step: frames_body must be 16-byte aligned with body_stride = round_up(13*J,4) (use phc_motion_pack)");
+  if (a->lib.body_stride != phc_motion_body_stride(J + E) || (reinterpret_cast<uintptr_t>(a->lib.frames_body) & 15)) {
+    phc_set_error("phc_env_step: frames_body must be 16-byte aligned with body_stride = round_up(13*(J+E),4) (use phc_motion_pack)");
     return PHC_ERR_INVALID_ARG;
   }
   if (a->env_motion && (reinterpret_cast<uintptr_t>(a->env_motion) & 15)) { phc_set_error("phc_env_step: env_motion must be 16-byte aligned"); return PHC_ERR_INVALID_ARG; }
   if (reinterpret_cast<uintptr_t>(a->dof_state) & 7) { phc_set_error("phc_env_step: dof_state must be 8-byte aligned"); return PHC_ERR_INVALID_ARG; }
   const int self_dim = phc_self_obs_dim(J, a->flags);
   const int obs_dim = self_dim + phc_task_obs_dim(J, T);
-  const int amp_dim = a->amp_out ? phc_amp_obs_dim(a->num_amp_joints, a->num_key_bodies, a->flags) : 0;
+  const int amp_dim = !a->amp_out ? 0 : (DR > 0 ? phc_amp_obs_dim_robot(DR, a->num_key_bodies, a->flags)
+                                                 : phc_amp_obs_dim(a->num_amp_joints, a->num_key_bodies, a->flags));
   if (a->obs_stride < obs_dim) { phc_set_error("phc_env_step: obs_stride smaller than the observation"); return PHC_ERR_INVALID_ARG; }
   if (a->amp_out && (a->amp_steps < 1 || a->amp_out_stride < (int64_t)(a->amp_hist_in ? a->amp_steps : 1) * amp_dim)) {
     phc_set_error("phc_env_step: amp_out_stride / amp_steps inconsistent"); return PHC_ERR_INVALID_ARG;
@@ -498,7 +524,7 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
   // TMA bulk copy of the per-env simulator block needs 16-byte aligned rows of a multiple of 16 bytes
   const bool state_bulk_ok = ((reinterpret_cast<uintptr_t>(a->body_state) & 15) == 0) &&
                              ((a->bodies_per_env * kBodyRec) % 4 == 0) && ((J * kBodyRec) % 4 == 0);
-  const StepLayout L = make_layout(J, T, a->lib.body_stride, amp_dim, obs_dim, alias_obs);
+  const StepLayout L = make_layout(J, T, a->lib.body_stride, amp_dim, obs_dim, alias_obs, DR);
   const size_t smem = (size_t)kWarpsPerCta * L.total * sizeof(float);
   const int grid = (a->num_envs + kWarpsPerCta - 1) / kWarpsPerCta;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -515,9 +541,8 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
                                                                     state_bulk_ok);                              \
     phc_count_launches(1);                                                                                       \
   } while (0)
-  if (T == 1 && J == 24) PHC_LAUNCH_STEP(1, 24);          // SMPL
-  else if (T == 1 && J == 20) PHC_LAUNCH_STEP(1, 20);     // H1
-  else if (T == 1) PHC_LAUNCH_STEP(1, 0);
+  if (T == 1 && J == 24 && E == 0 && DR == 0) PHC_LAUNCH_STEP(1, 24);          // SMPL
+  else if (T == 1) PHC_LAUNCH_STEP(1, 0);                                       // H1 (J = 20, E = 3, 19 hinge dofs) and others
   else PHC_LAUNCH_STEP(4, 0);
 #undef PHC_LAUNCH_STEP
   return phc_check_cuda(cudaGetLastError(), "env_step_kernel launch");

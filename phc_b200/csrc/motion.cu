@@ -52,6 +52,16 @@ __global__ void motion_pack_kernel(const float* __restrict__ gts, const float* _
   }
 }
 
+__global__ void motion_pack_dofs_kernel(const float* __restrict__ dof_pos, const float* __restrict__ dof_vel, int64_t F, int D, int JS,
+                                        float* __restrict__ fj) {
+  const int64_t total = F * JS;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = i / JS;
+    const int c = (int)(i - f * JS);
+    fj[i] = c < D ? dof_pos[f * D + c] : (c < 2 * D ? dof_vel[f * D + (c - D)] : 0.0f);
+  }
+}
+
 struct BodyS { V3 p; Q4 q; V3 v; V3 w; };
 __device__ __forceinline__ BodyS ld_body(const float* s) {
   BodyS b;
@@ -67,8 +77,9 @@ __device__ __forceinline__ MotionSample sample_motion(const PhcMotionLib& lib, i
   const Bracket b = frame_bracket(time, lib.motion_len[mid], lib.motion_num_frames[mid], lib.motion_dt[mid]);
   const int64_t r0 = lib.length_starts[mid] + b.i0, r1 = lib.length_starts[mid] + b.i1;
   const float bl = b.blend, omb = 1.0f - bl;
-  const BodyS a0 = ld_body(lib.frames_body + r0 * lib.body_stride + j * kRec);
-  const BodyS a1 = ld_body(lib.frames_body + r1 * lib.body_stride + j * kRec);
+  const int jb = j < lib.num_bodies + lib.num_ext_bodies ? j : 0;     // lanes that only carry a dof read body 0 (unused)
+  const BodyS a0 = ld_body(lib.frames_body + r0 * lib.body_stride + jb * kRec);
+  const BodyS a1 = ld_body(lib.frames_body + r1 * lib.body_stride + jb * kRec);
   MotionSample s;
   s.body.p = lerp3(a0.p, a1.p, omb, bl) + off;
   s.body.v = lerp3(a0.v, a1.v, omb, bl);
@@ -76,7 +87,15 @@ __device__ __forceinline__ MotionSample sample_motion(const PhcMotionLib& lib, i
   s.body.q = slerp(a0.q, a1.q, bl);
   s.dof_pos = v3(0.f, 0.f, 0.f);
   s.dof_vel = v3(0.f, 0.f, 0.f);
-  if (want_joint && lib.frames_joint) {
+  if (want_joint && lib.frames_joint && lib.num_dofs > 0) {
+    // hinge-joint robot: lane j carries dof j; dof_pos and dof_vel are both interpolated linearly (motion_lib_real.py:283-285)
+    if (j < lib.num_dofs) {
+      const float* j0 = lib.frames_joint + r0 * lib.joint_stride;
+      const float* j1 = lib.frames_joint + r1 * lib.joint_stride;
+      s.dof_pos.x = lerp1(j0[j], j1[j], omb, bl);
+      s.dof_vel.x = lerp1(j0[lib.num_dofs + j], j1[lib.num_dofs + j], omb, bl);
+    }
+  } else if (want_joint && lib.frames_joint) {
     const int J = lib.num_bodies;
     const float* j0 = lib.frames_joint + r0 * lib.joint_stride;
     const float* j1 = lib.frames_joint + r1 * lib.joint_stride;
@@ -103,22 +122,37 @@ motion_state_kernel(const __grid_constant__ PhcMotionLib lib, const int64_t* __r
   const int64_t qi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (qi >= n) return;
-  const int J = lib.num_bodies;
-  if (lane >= J) return;
+  const int J = lib.num_bodies, JE = J + lib.num_ext_bodies, D = lib.num_dofs;
+  if (lane >= JE && lane >= D) return;
   const V3 off = offset ? v3(offset[3 * qi], offset[3 * qi + 1], offset[3 * qi + 2]) : v3(0.f, 0.f, 0.f);
   const bool want_joint = (out.dof_pos != nullptr) || (out.dof_vel != nullptr);
   MotionSample s = sample_motion(lib, ids[qi], times[qi], v3(0.f, 0.f, 0.f), lane, want_joint);
   if (offset) s.body.p = s.body.p + off;          // the reference adds the offset only when one is given
-  const int64_t bj = qi * J + lane;
-  if (out.rg_pos) st3g(out.rg_pos + 3 * bj, s.body.p);
-  if (out.rb_rot) st4g(out.rb_rot + 4 * bj, s.body.q);
-  if (out.body_vel) st3g(out.body_vel + 3 * bj, s.body.v);
-  if (out.body_ang_vel) st3g(out.body_ang_vel + 3 * bj, s.body.w);
-  if (lane > 0) {
+  if (lane < JE) {                                 // robots: all J + E bodies (the *_t outputs)
+    const int64_t bt = qi * JE + lane;
+    if (out.rg_pos_t) st3g(out.rg_pos_t + 3 * bt, s.body.p);
+    if (out.rg_rot_t) st4g(out.rg_rot_t + 4 * bt, s.body.q);
+    if (out.body_vel_t) st3g(out.body_vel_t + 3 * bt, s.body.v);
+    if (out.body_ang_vel_t) st3g(out.body_ang_vel_t + 3 * bt, s.body.w);
+  }
+  if (lane < J) {
+    const int64_t bj = qi * J + lane;
+    if (out.rg_pos) st3g(out.rg_pos + 3 * bj, s.body.p);
+    if (out.rb_rot) st4g(out.rb_rot + 4 * bj, s.body.q);
+    if (out.body_vel) st3g(out.body_vel + 3 * bj, s.body.v);
+    if (out.body_ang_vel) st3g(out.body_ang_vel + 3 * bj, s.body.w);
+  }
+  if (D > 0) {
+    if (lane < D) {
+      if (out.dof_pos) out.dof_pos[qi * D + lane] = s.dof_pos.x;
+      if (out.dof_vel) out.dof_vel[qi * D + lane] = s.dof_vel.x;
+    }
+  } else if (lane > 0 && lane < J) {
     const int64_t dj = qi * (J - 1) + (lane - 1);
     if (out.dof_pos) st3g(out.dof_pos + 3 * dj, s.dof_pos);
     if (out.dof_vel) st3g(out.dof_vel + 3 * dj, s.dof_vel);
-  } else {
+  }
+  if (lane == 0) {
     if (out.root_pos) st3g(out.root_pos + 3 * qi, s.body.p);
     if (out.root_rot) st4g(out.root_rot + 4 * qi, s.body.q);
     if (out.root_vel) st3g(out.root_vel + 3 * qi, s.body.v);
@@ -155,7 +189,8 @@ __global__ void __launch_bounds__(128) amp_demo_kernel(const __grid_constant__ A
   const int J = a.lib.num_bodies;
   // motion_times0 + (-dt * (k + first)) : humanoid_amp.py:257-261 / :577-582
   const float t = a.times0[si] + (-a.dt * (float)(k + a.first_step));
-  const int j = lane < J ? lane : 0;
+  const int D = a.lib.num_dofs;
+  const int j = (lane < J || lane < D) ? lane : 0;
   const MotionSample s = sample_motion(a.lib, a.ids[si], t, v3(0.f, 0.f, 0.f), j, true);
   // root record broadcast from lane 0
   BodyS r;
@@ -163,14 +198,29 @@ __global__ void __launch_bounds__(128) amp_demo_kernel(const __grid_constant__ A
   r.q = q4(__shfl_sync(0xffffffffu, s.body.q.x, 0), __shfl_sync(0xffffffffu, s.body.q.y, 0), __shfl_sync(0xffffffffu, s.body.q.z, 0), __shfl_sync(0xffffffffu, s.body.q.w, 0));
   r.v = v3(__shfl_sync(0xffffffffu, s.body.v.x, 0), __shfl_sync(0xffffffffu, s.body.v.y, 0), __shfl_sync(0xffffffffu, s.body.v.z, 0));
   r.w = v3(__shfl_sync(0xffffffffu, s.body.w.x, 0), __shfl_sync(0xffffffffu, s.body.w.y, 0), __shfl_sync(0xffffffffu, s.body.w.z, 0));
-  if (lane >= J) return;
+  if (lane >= J && lane >= D) return;
 
   const bool upright = a.flags & PHC_FLAG_UPRIGHT, has_h = a.flags & PHC_FLAG_ROOT_HEIGHT_OBS;
   const Q4 root_q = upright ? r.q : strip_base_rot(r.q);
   const Q4 hinv = quat_about_z(-heading_angle(root_q));
   const int nj = a.num_amp_joints, nk = a.num_key_bodies;
   const int kp = (k + a.slot_offset) % a.num_steps;
-  float* o = a.out + si * a.out_stride + (int64_t)kp * (has_h + 12 + 9 * nj + 3 * nk) + (has_h ? 1 : 0);
+  const int row = has_h + 12 + (D > 0 ? 2 * D : 9 * nj) + 3 * nk;
+  float* o = a.out + si * a.out_stride + (int64_t)kp * row + (has_h ? 1 : 0);
+  if (D > 0) {       // build_amp_observations_robot (humanoid_amp.py:1062-1104): raw hinge angles and velocities
+    if (lane == 0) {
+      if (has_h) o[-1] = r.p.z;
+      const TanNorm tn = tan_norm((a.flags & PHC_FLAG_LOCAL_ROOT_OBS) ? qmul(hinv, root_q) : root_q);
+      st3g(o, tn.t); st3g(o + 3, tn.n);
+      st3g(o + 6, qrot_z(hinv, r.v));
+      st3g(o + 9, qrot_z(hinv, r.w));
+    }
+    if (lane < D) { o[12 + lane] = s.dof_pos.x; o[12 + D + lane] = s.dof_vel.x; }
+    if (lane < J)
+      for (int kk = 0; kk < nk; ++kk)
+        if (a.key_bodies[kk] == lane) st3g(o + 12 + 2 * D + 3 * kk, qrot_z(hinv, s.body.p - r.p));
+    return;
+  }
   if (lane == 0) {
     if (has_h) o[-1] = r.p.z;
     const TanNorm tn = tan_norm((a.flags & PHC_FLAG_LOCAL_ROOT_OBS) ? qmul(hinv, root_q) : root_q);
@@ -211,17 +261,22 @@ set_env_state_kernel(const __grid_constant__ PhcMotionLib lib, const int64_t* __
   const int lane = threadIdx.x & 31;
   if (env >= n) return;
   if (only_where && only_where[env] == 0) return;
-  const int J = lib.num_bodies;
-  if (lane >= J) return;
+  const int J = lib.num_bodies, D = lib.num_dofs;
+  if (lane >= J && lane >= D) return;
   const V3 off = offset ? v3(offset[3 * env], offset[3 * env + 1], offset[3 * env + 2]) : v3(0.f, 0.f, 0.f);
   MotionSample s = sample_motion(lib, ids[env], times[env], v3(0.f, 0.f, 0.f), lane, dof_state != nullptr);
   if (offset) s.body.p = s.body.p + off;
+  if (D > 0 && dof_state && lane < D) {                       // hinge joints: [D, 2] (pos, vel)
+    float* d = dof_state + ((size_t)env * D + lane) * 2;
+    d[0] = s.dof_pos.x; d[1] = s.dof_vel.x;
+  }
+  if (lane >= J) return;
   float* o = body_state + ((size_t)env * bpe + lane) * kRec;
   o[0] = s.body.p.x; o[1] = s.body.p.y; o[2] = s.body.p.z;
   o[3] = s.body.q.x; o[4] = s.body.q.y; o[5] = s.body.q.z; o[6] = s.body.q.w;
   o[7] = s.body.v.x; o[8] = s.body.v.y; o[9] = s.body.v.z;
   o[10] = s.body.w.x; o[11] = s.body.w.y; o[12] = s.body.w.z;
-  if (dof_state && lane > 0) {
+  if (D == 0 && dof_state && lane > 0) {
     float* d = dof_state + ((size_t)env * (J - 1) + (lane - 1)) * 6;      // [D, 2] interleaved (pos, vel)
     d[0] = s.dof_pos.x; d[1] = s.dof_vel.x; d[2] = s.dof_pos.y; d[3] = s.dof_vel.y; d[4] = s.dof_pos.z; d[5] = s.dof_vel.z;
   }
@@ -255,6 +310,16 @@ __global__ void amp_window_export_kernel(const float* __restrict__ ring, int64_t
 
 extern "C" int phc_motion_body_stride(int32_t J) { return (13 * J + 3) & ~3; }
 extern "C" int phc_motion_joint_stride(int32_t J) { return (4 * J + 3 * (J - 1) + 3) & ~3; }
+extern "C" int phc_motion_dof_stride(int32_t D) { return (2 * D + 3) & ~3; }
+
+extern "C" int phc_motion_pack_dofs(const float* dof_pos, const float* dof_vel, int64_t F, int32_t D, float* fj, void* stream) {
+  if (!dof_pos || !dof_vel || !fj || F < 0 || D < 1 || (reinterpret_cast<uintptr_t>(fj) & 15)) { phc_set_error("phc_motion_pack_dofs: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  if (F == 0) return PHC_OK;
+  const int JS = phc_motion_dof_stride(D);
+  int64_t g = (F * JS + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+  phc::motion_pack_dofs_kernel<<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(dof_pos, dof_vel, F, D, JS, fj); phc_count_launches(1);
+  return phc_check_cuda(cudaGetLastError(), "motion_pack_dofs_kernel launch");
+}
 
 extern "C" int phc_motion_pack(const float* gts, const float* grs, const float* gvs, const float* gavs,
                                const float* lrs, const float* dvs, int64_t F, int32_t J, float* fb, float* fj,
@@ -277,11 +342,13 @@ static int check_lib(const PhcMotionLib* lib, const char* who) {
   if (!lib || !lib->frames_body || !lib->motion_len || !lib->motion_dt || !lib->motion_num_frames || !lib->length_starts) {
     phc_set_error("motion library has NULL tables"); return PHC_ERR_INVALID_ARG;
   }
-  if (lib->num_bodies < 1 || lib->body_stride != phc_motion_body_stride(lib->num_bodies) ||
-      (lib->frames_joint && lib->joint_stride != phc_motion_joint_stride(lib->num_bodies))) {
-    phc_set_error("motion library strides do not match num_bodies (use phc_motion_pack)"); return PHC_ERR_INVALID_ARG;
+  if (lib->num_bodies < 1 || lib->num_ext_bodies < 0 || lib->num_ext_bodies > PHC_MAX_EXT_BODIES || lib->num_dofs < 0 ||
+      lib->body_stride != phc_motion_body_stride(lib->num_bodies + lib->num_ext_bodies) ||
+      (lib->frames_joint && lib->joint_stride != (lib->num_dofs > 0 ? phc_motion_dof_stride(lib->num_dofs)
+                                                                     : phc_motion_joint_stride(lib->num_bodies)))) {
+    phc_set_error("motion library strides do not match num_bodies / num_ext_bodies / num_dofs (use phc_motion_pack[_dofs])"); return PHC_ERR_INVALID_ARG;
   }
-  if (lib->num_bodies > 32) { phc_set_error("num_bodies > 32 not supported yet"); return PHC_ERR_UNSUPPORTED; }
+  if (lib->num_bodies + lib->num_ext_bodies > 32 || lib->num_dofs > 32) { phc_set_error("more than 32 bodies (incl. extend bodies) or hinge dofs: not supported yet"); return PHC_ERR_UNSUPPORTED; }
   (void)who;
   return PHC_OK;
 }
@@ -309,7 +376,7 @@ extern "C" int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* ids, con
   if (!ids || !times0 || !out || n < 0 || num_steps < 1 || nk < 0 || nk > PHC_MAX_KEY_BODIES || nj < 0 || nj > PHC_MAX_AMP_JOINTS || (nj > 0 && !amp_joints) || (nk > 0 && !key_bodies)) {
     phc_set_error("phc_amp_obs_demo: bad arguments"); return PHC_ERR_INVALID_ARG;
   }
-  const int A = phc_amp_obs_dim(nj, nk, flags);
+  const int A = lib->num_dofs > 0 ? phc_amp_obs_dim_robot(lib->num_dofs, nk, flags) : phc_amp_obs_dim(nj, nk, flags);
   if (out_stride < (int64_t)num_steps * A) { phc_set_error("phc_amp_obs_demo: out_stride too small"); return PHC_ERR_INVALID_ARG; }
   if (n == 0) return PHC_OK;
   phc::AmpDemoArgs a;

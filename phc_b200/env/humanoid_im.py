@@ -33,7 +33,8 @@ class SyntheticSim:
                  amp_dim: int = 196, amp_steps: int = 10):
         self.device = torch.device(device)
         self.num_envs = num_envs
-        states = [syn.make_env_state(motion, num_envs, seed=seed * 100 + k, amp_dim=amp_dim, amp_steps=amp_steps) for k in range(bank)]
+        make = syn.make_robot_env_state if isinstance(motion, syn.RobotMotionData) else syn.make_env_state
+        states = [make(motion, num_envs, seed=seed * 100 + k, amp_dim=amp_dim, amp_steps=amp_steps) for k in range(bank)]
         self.init_state = states[0]
         keep = lambda ts: torch.stack(ts).pin_memory() if host_bank else torch.stack(ts).to(self.device)
         self._body = keep([s.body_state for s in states])
@@ -89,26 +90,42 @@ class HumanoidIm:
         m = cfg["motion_data"]
         self._motion_data = m
         d = m.to(self.device) if hasattr(m, "to") else m
-        self._motion_lib = ops.pack_motion_lib(d.gts, d.grs, d.gvs, d.gavs, d.lrs, d.dvs, d.lengths, d.num_frames, d.dts,
-                                               d.length_starts)
+        robot = hasattr(d, "gts_t")            # hinge-joint robot tables (phc/utils/motion_lib_real.py): h1 / g1
+        if robot:
+            dev = self.device
+            self._motion_lib = ops.pack_robot_motion_lib(d.gts_t.to(dev), d.grs_t.to(dev), d.gvs_t.to(dev), d.gavs_t.to(dev),
+                                                         d.dof_pos.to(dev), d.dvs.to(dev), d.num_bodies, d.lengths.to(dev),
+                                                         d.num_frames.to(dev), d.dts.to(dev), d.length_starts.to(dev))
+            if self.humanoid_type == "smpl":
+                self.humanoid_type = "h1"
+        else:
+            self._motion_lib = ops.pack_motion_lib(d.gts, d.grs, d.gvs, d.gavs, d.lrs, d.dvs, d.lengths, d.num_frames, d.dts,
+                                                   d.length_starts)
         J = self._motion_lib.num_bodies
         self.num_bodies = J
-        self.num_dof = 3 * (J - 1)
-        key_bodies = env.get("key_body_ids", syn.SMPL_KEY_BODIES if J == 24 else [J - 1])
-        reset_bodies = env.get("reset_body_ids", syn.SMPL_RESET_BODIES if J == 24 else None)
-        dof_subset = env.get("dof_subset", syn.SMPL_DOF_SUBSET if (J == 24 and cfg.get("has_dof_subset", True)) else None)
+        self.num_dof = self._motion_lib.dofs
+        # cfg.robot.extend_config (humanoid_im.py:74-82): parent body index + position in the parent frame
+        ext = cfg.get("extend_config", [dict(parent=p, pos=q) for p, q in zip(syn.H1_EXT_PARENTS, syn.H1_EXT_POS)] if robot else [])
+        self.extend_body_parent_ids = [int(e["parent"]) for e in ext]
+        self.extend_body_pos_in_parent = [list(e["pos"]) for e in ext]
+        self.num_extend_bodies = len(ext)
+        key_bodies = env.get("key_body_ids", syn.H1_KEY_BODIES if robot else (syn.SMPL_KEY_BODIES if J == 24 else [J - 1]))
+        reset_bodies = env.get("reset_body_ids", syn.SMPL_RESET_BODIES if (J == 24 and not robot) else None)
+        dof_subset = env.get("dof_subset", syn.SMPL_DOF_SUBSET if (J == 24 and not robot and cfg.get("has_dof_subset", True)) else None)
         self.step_cfg = ops.EnvStepConfig(
             dt=self.dt, time_steps=self._num_traj_samples, traj_dt=self._traj_sample_timestep,
             upright=bool(cfg.get("has_upright_start", True)), local_root_obs=bool(env.get("local_root_obs", True)),
             root_height_obs=bool(env.get("root_height_obs", True)), power_reward=self.power_reward,
             power_coef=self.power_coefficient, early_term=bool(env.get("enableEarlyTermination", True)),
             key_bodies=key_bodies, reset_bodies=reset_bodies, term_dist=float(env.get("terminationDistance", 0.25)),
-            dof_subset=dof_subset, amp_steps=self._num_amp_obs_steps)
+            dof_subset=dof_subset, amp_steps=self._num_amp_obs_steps, ext_parents=self.extend_body_parent_ids,
+            ext_pos=self.extend_body_pos_in_parent)
         self._key_body_ids, self._reset_bodies_id, self.dof_subset = key_bodies, reset_bodies, dof_subset
 
         # ---- simulator backend and its tensors (Humanoid._setup_tensors) ---------------------------------------
         self.sim = cfg.get("sim") or SyntheticSim(m, self.num_envs, self.device, seed=int(cfg.get("seed", 0)),
-                                                  host_bank=bool(cfg.get("host_sim_bank", False)))
+                                                  host_bank=bool(cfg.get("host_sim_bank", False)),
+                                                  amp_dim=13 + 2 * self.num_dof + 3 * len(key_bodies) if robot else 196)
         self._rigid_body_state_reshaped = self.sim.rigid_body_state
         self._rigid_body_pos = self._rigid_body_state_reshaped[..., :J, 0:3]
         self._rigid_body_rot = self._rigid_body_state_reshaped[..., :J, 3:7]

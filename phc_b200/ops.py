@@ -54,6 +54,12 @@ class PackedMotionLib:
     length_starts: torch.Tensor
     num_bodies: int
     c: _lib.PhcMotionLib = field(default=None, repr=False)
+    num_ext_bodies: int = 0          # robots: "extend" bodies stored as records J..J+E-1
+    num_dofs: int = 0                # robots: hinge dofs (0 = SMPL spherical joints, D = 3(J-1))
+
+    @property
+    def dofs(self) -> int:
+        return self.num_dofs if self.num_dofs > 0 else 3 * (self.num_bodies - 1)
 
     @property
     def device(self):
@@ -93,6 +99,37 @@ def pack_motion_lib(gts, grs, gvs, gavs, lrs, dvs, lengths, num_frames, dts, len
     return PackedMotionLib(fb, fj, lengths, dts, num_frames, length_starts, J, c)
 
 
+def pack_robot_motion_lib(gts_t, grs_t, gvs_t, gavs_t, dof_pos, dof_vel, num_bodies: int, lengths, num_frames, dts,
+                          length_starts) -> PackedMotionLib:
+    """Hinge-joint robots (H1 / G1, phc/utils/motion_lib_real.py): the *_t tables hold all J + E bodies (J simulated ones
+    first, then the "extend" bodies), dof_pos / dof_vel are [F, D].  Body records via phc_motion_pack(J + E), joint records via
+    phc_motion_pack_dofs."""
+    lib = _lib.load()
+    dev = gts_t.device
+    f32, i64 = torch.float32, torch.int64
+    gts_t, grs_t = _req(gts_t, f32, "gts_t"), _req(grs_t, f32, "grs_t", dev)
+    gvs_t, gavs_t = _req(gvs_t, f32, "gvs_t", dev), _req(gavs_t, f32, "gavs_t", dev)
+    dof_pos, dof_vel = _req(dof_pos, f32, "dof_pos", dev), _req(dof_vel, f32, "dof_vel", dev)
+    F, JE = int(gts_t.shape[0]), int(gts_t.shape[1])
+    J, E, D = int(num_bodies), JE - int(num_bodies), int(dof_pos.shape[1])
+    assert 0 <= E <= _lib.PHC_MAX_EXT_BODIES and grs_t.shape == (F, JE, 4) and gvs_t.shape == (F, JE, 3) and gavs_t.shape == (F, JE, 3)
+    assert dof_pos.shape == (F, D) and dof_vel.shape == (F, D)
+    bs, js = lib.phc_motion_body_stride(JE), lib.phc_motion_dof_stride(D)
+    fb = torch.empty(F, bs, dtype=f32, device=dev)
+    fj = torch.empty(F, js, dtype=f32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.phc_motion_pack(gts_t.data_ptr(), grs_t.data_ptr(), gvs_t.data_ptr(), gavs_t.data_ptr(), None, None, F, JE,
+                                       fb.data_ptr(), None, _stream()), "phc_motion_pack")
+        _lib.check(lib.phc_motion_pack_dofs(dof_pos.data_ptr(), dof_vel.data_ptr(), F, D, fj.data_ptr(), _stream()), "phc_motion_pack_dofs")
+    lengths = _req(lengths.contiguous(), f32, "lengths", dev)
+    dts = _req(dts.contiguous(), f32, "dts", dev)
+    num_frames = _req(num_frames.contiguous(), i64, "num_frames", dev)
+    length_starts = _req(length_starts.contiguous(), i64, "length_starts", dev)
+    c = _lib.PhcMotionLib(fb.data_ptr(), fj.data_ptr(), lengths.data_ptr(), dts.data_ptr(), num_frames.data_ptr(),
+                          length_starts.data_ptr(), F, int(lengths.shape[0]), J, bs, js, E, D)
+    return PackedMotionLib(fb, fj, lengths, dts, num_frames, length_starts, J, c, E, D)
+
+
 _MS_KEYS = {"rg_pos": 3, "rb_rot": 4, "body_vel": 3, "body_ang_vel": 3}
 
 
@@ -113,8 +150,12 @@ def motion_state(mlib: PackedMotionLib, motion_ids: torch.Tensor, motion_times: 
     if want_dof:
         if mlib.frames_joint is None:
             raise PhcError("motion_state: dof_pos/dof_vel need the joint table (lrs/dvs) in the packed library")
-        out["dof_pos"] = torch.empty(n, 3 * (J - 1), dtype=torch.float32, device=dev)
-        out["dof_vel"] = torch.empty(n, 3 * (J - 1), dtype=torch.float32, device=dev)
+        out["dof_pos"] = torch.empty(n, mlib.dofs, dtype=torch.float32, device=dev)
+        out["dof_vel"] = torch.empty(n, mlib.dofs, dtype=torch.float32, device=dev)
+    if mlib.num_ext_bodies > 0:          # robots: rg_pos_t / rg_rot_t / body_vel_t / body_ang_vel_t over all J + E bodies
+        JE = J + mlib.num_ext_bodies
+        for k, w in (("rg_pos_t", 3), ("rg_rot_t", 4), ("body_vel_t", 3), ("body_ang_vel_t", 3)):
+            out[k] = torch.empty(n, JE, w, dtype=torch.float32, device=dev)
     co = _lib.PhcMotionStateOut(**{k: _ptr(out.get(k)) for k, _ in _lib.PhcMotionStateOut._fields_})
     with torch.cuda.device(dev):
         _lib.check(lib.phc_motion_state(C.byref(mlib.c), ids.data_ptr(), times.data_ptr(), _ptr(offset), n,
@@ -152,6 +193,10 @@ class EnvStepConfig:
     term_dist: float = 0.25                              # or a per-body sequence of length J
     dof_subset: Optional[Sequence[int]] = None           # dof indices kept in the AMP obs (whole joints); None = all
     amp_steps: int = 10
+    # robots (cfg.robot.extend_config, humanoid_im.py:74-82): parent body index and position in the parent frame of every
+    # "extend" body; must match the E extra records of the packed motion library
+    ext_parents: Sequence[int] = ()
+    ext_pos: Sequence[Sequence[float]] = ()
 
     def flags(self) -> int:
         f = 0
@@ -198,7 +243,7 @@ class EnvStepPlan:
         self.device = dev
         f32, i64 = torch.float32, torch.int64
         J = mlib.num_bodies
-        D = 3 * (J - 1)
+        D = mlib.dofs
         body_state = _req(body_state, f32, "body_state", dev)
         N, bpe = int(body_state.shape[0]), int(body_state.shape[1])
         assert body_state.shape[2] == 13 and bpe >= J
@@ -215,8 +260,13 @@ class EnvStepPlan:
         self.self_dim = lib.phc_self_obs_dim(J, flags)
         self.task_dim = lib.phc_task_obs_dim(J, cfg.time_steps)
         self.obs_dim = self.self_dim + self.task_dim
-        joints = cfg.amp_joint_list(J)
-        self.amp_dim = lib.phc_amp_obs_dim(len(joints), len(cfg.key_bodies), flags)
+        robot = mlib.num_dofs > 0
+        joints = [] if robot else cfg.amp_joint_list(J)
+        self.amp_dim = (lib.phc_amp_obs_dim_robot(D, len(cfg.key_bodies), flags) if robot
+                        else lib.phc_amp_obs_dim(len(joints), len(cfg.key_bodies), flags))
+        E = mlib.num_ext_bodies
+        if len(cfg.ext_parents) != E or len(cfg.ext_pos) != E:
+            raise PhcError(f"EnvStepConfig.ext_parents / ext_pos must list the {E} extend bodies of the motion library")
         rw = 5 if cfg.power_reward else 4
 
         def out(t, shape, dtype, name):
@@ -284,6 +334,10 @@ class EnvStepPlan:
         for i in range(J):
             a.term_thresh[i] = float(thr[i])
         a.term_dist_mean = float(td[rb[0]])
+        for i in range(E):
+            a.ext_parent[i] = int(cfg.ext_parents[i])
+            for c in range(3):
+                a.ext_pos[i][c] = float(cfg.ext_pos[i][c])
         a.num_key_bodies = len(cfg.key_bodies)
         for i, b in enumerate(cfg.key_bodies):
             a.key_bodies[i] = int(b)
@@ -334,8 +388,10 @@ def amp_obs_demo(mlib: PackedMotionLib, cfg: EnvStepConfig, motion_ids: torch.Te
     t0 = _req(times0, torch.float32, "times0", dev)
     n = int(ids.shape[0])
     S = cfg.amp_steps if num_steps is None else num_steps
-    joints = cfg.amp_joint_list(mlib.num_bodies)
-    A = lib.phc_amp_obs_dim(len(joints), len(cfg.key_bodies), cfg.flags())
+    robot = mlib.num_dofs > 0
+    joints = [] if robot else cfg.amp_joint_list(mlib.num_bodies)
+    A = (lib.phc_amp_obs_dim_robot(mlib.num_dofs, len(cfg.key_bodies), cfg.flags()) if robot
+         else lib.phc_amp_obs_dim(len(joints), len(cfg.key_bodies), cfg.flags()))
     if out is None:
         out = torch.empty(n, S, A, dtype=torch.float32, device=dev)
     else:

@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
-from typing import Optional
+from typing import Optional, Sequence
 
 import torch
 
@@ -246,3 +246,110 @@ def make_rollout(num_envs: int, horizon: int, seed: int = 0):
     next_values = torch.randn(T, N, 1, generator=g)
     dones = (torch.rand(T, N, generator=g) < 0.03)
     return dones.float(), values, rewards, next_values
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Hinge-joint robots (Unitree H1: phc/data/cfg/robot/unitree_h1.yaml:27-67): 20 bodies, 19 one-dof joints, 3 "extend"
+# bodies (hands, head) rigidly attached to a parent; reference motion in the layout of phc/utils/motion_lib_real.py
+# ----------------------------------------------------------------------------------------------------------------------
+H1_NUM_BODIES, H1_NUM_DOFS = 20, 19
+H1_EXT_PARENTS = [15, 19, 0]                                   # left_elbow_link, right_elbow_link, pelvis
+H1_EXT_POS = [[0.3, 0.0, 0.0], [0.3, 0.0, 0.0], [0.0, 0.0, 0.6]]
+H1_KEY_BODIES = [5, 10, 15, 19]                                # ankles and elbows
+
+
+@dataclass
+class RobotMotionData:
+    gts_t: torch.Tensor          # [F, J+E, 3]  bodies then extend bodies (the *_t tables of motion_lib_real)
+    grs_t: torch.Tensor          # [F, J+E, 4]
+    gvs_t: torch.Tensor          # [F, J+E, 3]
+    gavs_t: torch.Tensor         # [F, J+E, 3]
+    dof_pos: torch.Tensor        # [F, D]
+    dvs: torch.Tensor            # [F, D] dof velocity
+    lengths: torch.Tensor
+    num_frames: torch.Tensor
+    dts: torch.Tensor
+    length_starts: torch.Tensor
+    num_bodies: int = H1_NUM_BODIES
+
+    @property
+    def num_motions(self):
+        return int(self.lengths.shape[0])
+
+    @property
+    def num_ext(self):
+        return int(self.gts_t.shape[1]) - self.num_bodies
+
+    @property
+    def num_dofs(self):
+        return int(self.dof_pos.shape[1])
+
+
+def make_robot_motions(num_motions: int, seed: int = 0, num_bodies: int = H1_NUM_BODIES, num_dofs: int = H1_NUM_DOFS,
+                       ext_parents: Sequence[int] = tuple(H1_EXT_PARENTS), ext_pos=H1_EXT_POS, min_frames: int = 60,
+                       max_frames: int = 300) -> RobotMotionData:
+    m = make_motions(num_motions, seed=seed, num_bodies=num_bodies, min_frames=min_frames, max_frames=max_frames)
+    F, J, E = m.gts.shape[0], num_bodies, len(ext_parents)
+    par = torch.tensor(list(ext_parents))
+    off = torch.tensor(ext_pos, dtype=torch.float32)
+    ep = m.gts[:, par] + _qrot(m.grs[:, par], off[None].expand(F, E, 3))
+    eq = m.grs[:, par]
+    dt = float(m.dts[0])
+    clip_id = torch.repeat_interleave(torch.arange(num_motions), m.num_frames)
+    last = torch.zeros(F, dtype=torch.bool)
+    last[m.length_starts + m.num_frames - 1] = True
+    nxt = torch.where(last, torch.arange(F), torch.arange(F) + 1)
+    prv = torch.where(last, torch.arange(F) - 1, torch.arange(F))
+    ev = (ep[nxt] - ep[prv]) / dt
+    ew = m.gavs[:, par]
+    g = torch.Generator().manual_seed(7000 + seed)
+    step = torch.randn(F, num_dofs, generator=g) * 0.03
+    first = torch.zeros(F, dtype=torch.bool)
+    first[m.length_starts] = True
+    step[first] = torch.randn(num_motions, num_dofs, generator=g) * 0.4
+    cs = torch.cumsum(step, 0)
+    dof_pos = cs - (cs[m.length_starts] - step[m.length_starts])[clip_id]
+    dvs = (dof_pos[nxt] - dof_pos[prv]) / dt
+    cat = lambda a, b: torch.cat((a, b), dim=1).contiguous()
+    return RobotMotionData(gts_t=cat(m.gts, ep), grs_t=cat(m.grs, eq), gvs_t=cat(m.gvs, ev), gavs_t=cat(m.gavs, ew),
+                           dof_pos=dof_pos.float().contiguous(), dvs=dvs.float().contiguous(), lengths=m.lengths,
+                           num_frames=m.num_frames, dts=m.dts, length_starts=m.length_starts, num_bodies=J)
+
+
+def make_robot_env_state(m: RobotMotionData, num_envs: int, seed: int = 0, amp_dim: int = 63, amp_steps: int = 10,
+                         dt: float = 1.0 / 30.0, max_progress: int = 299, with_offset: bool = False,
+                         blend_jitter: bool = False) -> EnvState:
+    """Simulator state of a hinge-joint robot around its reference pose: [N, J, 13] bodies, [N, D, 2] dofs."""
+    g = torch.Generator().manual_seed(3000 + seed)
+    N, J, D = num_envs, m.num_bodies, m.num_dofs
+    ids = (torch.arange(N) % m.num_motions).long()
+    ln = m.lengths[ids]
+    start = (((torch.rand(N, generator=g) * ln) / (1 / 30)).long() * (1 / 30)).float()
+    if blend_jitter:
+        start = start + torch.rand(N, generator=g) * (1 / 30)
+    progress = torch.randint(0, max_progress + 1, (N,), generator=g).long()
+    progress[: max(1, N // 16)] = torch.arange(max(1, N // 16)) % 5
+    off, goff = torch.zeros(N), torch.zeros(N, 3)
+    if with_offset:
+        goff[:, :2] = torch.randn(N, 2, generator=g)
+    t_now = progress * dt + start + off
+    f = (torch.clip(t_now / ln, 0, 1) * (m.num_frames[ids] - 1)).long() + m.length_starts[ids]
+    p, q, v, w = m.gts_t[f, :J] + goff[:, None, :], m.grs_t[f, :J], m.gvs_t[f, :J], m.gavs_t[f, :J]
+    pos = p + torch.randn(N, J, 3, generator=g) * 0.05
+    small = _unit(torch.cat((torch.randn(N, J, 3, generator=g) * 0.05, torch.ones(N, J, 1)), dim=-1))
+    rot = _unit(_qmul(q, small))
+    u = torch.rand(N, J, generator=g)
+    rot = torch.where((u < 0.05)[..., None], q, rot)
+    rot = torch.where((u > 0.95)[..., None], _unit(torch.randn(N, J, 4, generator=g)), rot)
+    vel = v + torch.randn(N, J, 3, generator=g) * 0.5
+    ang = w + torch.randn(N, J, 3, generator=g) * 0.5
+    far = torch.rand(N, generator=g) < 0.1
+    pos = pos + far[:, None, None] * torch.randn(N, J, 3, generator=g) * 0.3
+    body = torch.cat((pos, rot, vel, ang), dim=-1).contiguous()
+    dof_pos = m.dof_pos[f] + torch.randn(N, D, generator=g) * 0.05
+    dof_vel = m.dvs[f] + torch.randn(N, D, generator=g) * 0.5
+    dof_state = torch.stack((dof_pos, dof_vel), dim=-1).contiguous()
+    dof_force = torch.randn(N, D, generator=g) * 50.0
+    amp_hist = torch.randn(N, amp_steps, amp_dim, generator=g)
+    return EnvState(body_state=body.float(), dof_state=dof_state.float(), dof_force=dof_force.float(), progress=progress,
+                    motion_ids=ids, start_times=start, start_offsets=off, global_offset=goff, amp_hist=amp_hist.float())

@@ -15,6 +15,9 @@ What is executed on the reference side (no restatement involved):
   mcp.npz      PNN.__init__/forward/load_actor/freeze_pnn (phc/learning/pnn.py), load_pnn / load_mcp_mlp
                (phc/learning/network_loader.py:11-73) and HumanoidImMCP.step (phc/env/tasks/humanoid_im_mcp.py:56-90) with the
                three simulator hooks replaced by recorders
+  h1.npz       the hinge-joint robot path (humanoid_type 'h1'): MotionLibReal.get_motion_state (phc/utils/motion_lib_real.py:236-361),
+               HumanoidIm._compute_reward with the extend bodies (humanoid_im.py:916-923), _compute_reset, _compute_observations,
+               build_amp_observations_robot through _compute_amp_observations / build_amp_obs_demo
   learn.npz    CommonAgent.discount_values/_calc_advs/_actor_loss/_critic_loss/bound_loss,
                AMPAgent._disc_loss/_calc_disc_rewards/_combine_rewards, RunningMeanStd.forward
 """
@@ -406,8 +409,82 @@ def gen_mcp():
     save("mcp.npz", d)
 
 
+def make_ref_robot_lib(m):
+    from phc.utils.motion_lib_real import MotionLibReal
+    J = m.num_bodies
+    lib = object.__new__(MotionLibReal)
+    lib._device = torch.device("cpu")
+    lib.gts, lib.grs, lib.gvs, lib.gavs = (t[:, :J].contiguous() for t in (m.gts_t, m.grs_t, m.gvs_t, m.gavs_t))
+    lib.gts_t, lib.grs_t, lib.gvs_t, lib.gavs_t = m.gts_t, m.grs_t, m.gvs_t, m.gavs_t
+    lib.dof_pos, lib.dvs = m.dof_pos, m.dvs
+    lib._motion_lengths, lib._motion_num_frames, lib._motion_dt = m.lengths, m.num_frames, m.dts
+    lib.length_starts = m.length_starts
+    lib.num_bodies = J
+    lib._get_num_bodies = lambda: J
+    F = m.gts_t.shape[0]
+    lib._motion_aa = torch.zeros(F, 72)
+    lib._motion_bodies = torch.zeros(m.num_motions, 17)
+    lib._motion_limb_weights = torch.zeros(m.num_motions, 10)
+    lib._motion_fps = 1.0 / m.dts
+    return lib
+
+
+def gen_h1():
+    m = syn.make_robot_motions(24, seed=2, min_frames=12, max_frames=24)
+    J, D, E = m.num_bodies, m.num_dofs, m.num_ext
+    lib = make_ref_robot_lib(m)
+    d = {"tab_" + f: getattr(m, f) for f in ("gts_t", "grs_t", "gvs_t", "gavs_t", "dof_pos", "dvs", "lengths", "num_frames", "dts", "length_starts")}
+    d["ext_parents"], d["ext_pos"], d["key_bodies"] = np.array(syn.H1_EXT_PARENTS), np.array(syn.H1_EXT_POS, dtype=np.float32), np.array(syn.H1_KEY_BODIES)
+    # --- MotionLibReal.get_motion_state
+    g = torch.Generator().manual_seed(31)
+    n = 64
+    ids = torch.randint(0, m.num_motions, (n,), generator=g)
+    ln = m.lengths[ids]
+    times = torch.rand(n, generator=g) * ln
+    times[:6] = -0.05 * torch.arange(6)
+    times[6:12] = ln[6:12] + 0.03 * torch.arange(6)
+    offset = torch.randn(n, 3, generator=g)
+    res = lib.get_motion_state(ids, times, offset=offset)
+    d.update(ms_ids=ids, ms_times=times, ms_offset=offset)
+    for k in ("root_pos", "root_rot", "dof_pos", "root_vel", "root_ang_vel", "dof_vel", "rg_pos", "rb_rot", "body_vel", "body_ang_vel",
+              "rg_pos_t", "rg_rot_t", "body_vel_t", "body_ang_vel_t"):
+        d["ms_out_" + k] = res[k]
+    # --- env step (two cases: frame-grid starts; generic blend + global offset)
+    A = 13 + 2 * D + 3 * len(syn.H1_KEY_BODIES)
+    for tag, kw in (("A", {}), ("B", dict(with_offset=True, blend_jitter=True))):
+        st = syn.make_robot_env_state(m, 24, seed=4, amp_dim=A, max_progress=20, **kw)
+        base = syn.MotionData(gts=lib.gts, grs=lib.grs, lrs=lib.grs, gvs=lib.gvs, gavs=lib.gavs, dvs=torch.zeros(1), lengths=m.lengths,
+                              num_frames=m.num_frames, dts=m.dts, length_starts=m.length_starts)
+        env = build_ref_env(base, st)
+        env._motion_lib = lib
+        env.humanoid_type = "h1"
+        env.extend_body_parent_ids = torch.tensor(syn.H1_EXT_PARENTS)
+        env.extend_body_pos_in_parent = torch.tensor(syn.H1_EXT_POS).repeat(env.num_envs, 1, 1)
+        env.num_extend_bodies = E
+        env._reset_bodies_id = torch.arange(J)
+        env._key_body_ids = torch.tensor(syn.H1_KEY_BODIES)
+        env.dof_subset, env._has_dof_subset = None, False
+        env._dof_names = [f"d{i}" for i in range(D)]
+        env._contact_body_ids = torch.tensor([5, 10])
+        env.ref_dof_pos = torch.zeros(env.num_envs, D)
+        out = run_ref_step(env)
+        for k, v in out.items():
+            d[f"{tag}_out_{k}"] = v
+        for f in st.__dataclass_fields__:
+            d[f"{tag}_in_{f}"] = getattr(st, f)
+    # --- AMP demo observation of the reference motion
+    ids = torch.randint(0, m.num_motions, (16,), generator=g)
+    t0 = torch.rand(16, generator=g) * m.lengths[ids]
+    t0[:3] = 0.1
+    env.ref_motion_cache = {}
+    d["demo_ids"], d["demo_t0"] = ids, t0
+    d["demo_out"] = env.build_amp_obs_demo(ids, t0).view(16, env._num_amp_obs_steps, -1)
+    save("h1.npz", d)
+
+
 if __name__ == "__main__":
     gen_mcp()
+    gen_h1()
     gen_quat()
     gen_motion()
     gen_envstep()

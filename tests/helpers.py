@@ -52,3 +52,23 @@ def close(a, b, rtol=1e-5, atol=1e-6, what=""):
                                  f"first at {i}: {a[tuple(i)].item()} vs {b[tuple(i)].item()}")
     else:
         assert torch.equal(a, b), f"{what}: integer mismatch ({int((a != b).sum())} elements)"
+
+
+# ---- hinge-joint robot (H1) fixtures: tests/golden/h1.npz ---------------------------------------------------------
+def robot_tables_from(d, prefix="tab_"):
+    f = lambda k: d[prefix + k]
+    return O.RobotTables(f("gts_t"), f("grs_t"), f("gvs_t"), f("gavs_t"), f("dof_pos"), f("dvs"), f("lengths"), f("num_frames"),
+                         f("dts"), f("length_starts"), syn.H1_NUM_BODIES)
+
+
+def robot_motion_data_from(d, prefix="tab_"):
+    f = lambda k: d[prefix + k]
+    return syn.RobotMotionData(gts_t=f("gts_t"), grs_t=f("grs_t"), gvs_t=f("gvs_t"), gavs_t=f("gavs_t"), dof_pos=f("dof_pos"), dvs=f("dvs"),
+                               lengths=f("lengths"), num_frames=f("num_frames"), dts=f("dts"), length_starts=f("length_starts"),
+                               num_bodies=syn.H1_NUM_BODIES)
+
+
+def h1_step_config(**kw):
+    base = dict(key_bodies=syn.H1_KEY_BODIES, reset_bodies=None, dof_subset=None)
+    base.update(kw)
+    return O.StepConfig(**base)

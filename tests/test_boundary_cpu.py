@@ -44,7 +44,7 @@ def test_ctypes_struct_layout_matches_header_order():
             if not decl:
                 continue
             for part in decl.split(","):
-                m = re.search(r"(\w+)\s*(\[\w+\])?\s*$", part.strip())
+                m = re.search(r"(\w+)\s*(\[\w+\])*\s*$", part.strip())
                 names.append(m.group(1))
         assert names == [f[0] for f in cls._fields_], cname
 

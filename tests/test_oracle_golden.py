@@ -199,3 +199,36 @@ def test_mcp_composer_keeps_final_relu():
     assert (g["composer_out"] == 0).any() and (g["composer_out"] >= 0).all()
     out = mo.mlp_forward(comp, "a2c_network.composer.", torch.from_numpy(g["x"]), ending_act=True, act="silu")
     torch.testing.assert_close(out, torch.from_numpy(g["composer_out_silu"]), rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Hinge-joint robot (H1, config 5 of BASELINE.json): oracle against the real MotionLibReal / HumanoidIm h1 branches
+# ------------------------------------------------------------------------------------------------------------------
+def test_h1_motion_state_matches_motion_lib_real():
+    from tests.helpers import robot_tables_from
+    g = load("h1.npz")
+    out = O.motion_state_robot(robot_tables_from(g), g["ms_ids"], g["ms_times"], g["ms_offset"])
+    for k in ("root_pos", "root_rot", "dof_pos", "root_vel", "root_ang_vel", "dof_vel", "rg_pos", "rb_rot", "body_vel", "body_ang_vel",
+              "rg_pos_t", "rg_rot_t", "body_vel_t", "body_ang_vel_t"):
+        close(out[k], g["ms_out_" + k], what="h1 motion_state " + k)
+
+
+def test_h1_env_step_matches_reference():
+    from tests.helpers import robot_tables_from, h1_step_config
+    g = load("h1.npz")
+    tab = robot_tables_from(g)
+    for tag in ("A", "B"):
+        st = env_state_from(g, tag)
+        out = O.env_step_robot(tab, h1_step_config(), g["ext_parents"].tolist(), g["ext_pos"], st.body_state, st.dof_state, st.dof_force,
+                               st.progress, st.motion_ids, st.start_times, st.start_offsets, st.global_offset, st.amp_hist)
+        assert out["obs"].shape[1] == 778 and out["amp_obs"].shape[1] == 63          # H1 row of SURVEY.md section 0
+        for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf", "ref_body_pos", "ref_body_rot", "ref_body_vel"):
+            close(out[k], g[f"{tag}_out_{k}"], what=f"h1 {tag} {k}")
+    assert g["A_out_terminate"].sum() > 0
+
+
+def test_h1_amp_obs_demo_matches_reference():
+    from tests.helpers import robot_tables_from, h1_step_config
+    g = load("h1.npz")
+    out = O.amp_obs_demo_robot(robot_tables_from(g), h1_step_config(), g["demo_ids"], g["demo_t0"])
+    close(out, g["demo_out"], what="h1 amp_obs_demo")
