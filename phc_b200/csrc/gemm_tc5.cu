@@ -372,7 +372,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 //   MMA thread: for every tile: wait tmem_empty[acc] -> for every k-block: wait full[s] -> 12 UMMAs -> commit empty[s];
 //               commit tmem_full[acc]
 //   epilogue  : wait tmem_full[acc] -> tcgen05.ld / epilogue math / stores -> arrive tmem_empty[acc] (one lane per warp)
-// Tiles are ordered m-major inside an n-column block run so that CTAs working at the same time share the A row block in L2.
+// Tiles are ordered n fastest (see decode below).
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
@@ -409,12 +409,15 @@ gemm_tc5_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // tile -> (z, n, m): m fastest
+  // tile -> (z, m, n): n fastest.  The CTAs that run at the same time then share a few A row blocks (read once from HBM,
+  // re-used out of L2 by the other n tiles right away) and sweep the B operand, which for the MLP shapes is the weight
+  // matrix and stays L2 resident.  (m fastest made every concurrent tile stream a different A block and re-read the
+  // whole activation matrix from HBM once per n tile: 372 vs 433 TFLOP/s against the one-tile-per-CTA launch.)
   auto decode = [&](int t, int& m0, int& n0, int& kb_begin, int& nkb, int& z) {
-    const int mi = t % tiles_m;
-    const int r = t / tiles_m;
-    const int ni = r % tiles_n;
-    z = r / tiles_n;
+    const int ni = t % tiles_n;
+    const int r = t / tiles_n;
+    const int mi = r % tiles_m;
+    z = r / tiles_m;
     m0 = mi * BM; n0 = ni * BN;
     kb_begin = z * kb_per;
     const int kb_end = min(kb_total, kb_begin + kb_per);
@@ -521,6 +524,171 @@ gemm_tc5_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent CTA-pair variant: a cluster of two CTAs walks a static list of 256 x 256 tiles with cta_group::2 MMAs
+// (M = 256 split over the two SMs, N = 256).  Each CTA stages only ITS 128 rows of A and ITS 128 of the 256 B rows per
+// k-block -- half the L2 -> shared-memory traffic per flop of the 128 x 128 kernel, which is what bounds 3xTF32 (four
+// operand tiles feed three MMAs).  Accumulators are double-buffered in TMEM (2 x 256 of the 512 columns), so the
+// epilogue of tile i overlaps the MMAs of tile i+1 as in the single-CTA persistent kernel.
+//   TMA warp (both CTAs): wait own empty[s] -> leader arms full[s] with the bytes of BOTH CTAs, the peer arrives remotely
+//                         -> bulk-tensor loads that credit the leader's barrier
+//   MMA thread (leader) : wait tmem_empty[acc] (8 arrivals: 4 epilogue warps x 2 CTAs) -> per k-block: wait full[s] ->
+//                         12 UMMAs -> multicast commit to empty[s] of both CTAs; multicast commit to tmem_full[acc]
+//   epilogue (both CTAs): wait own tmem_full[acc] -> tcgen05.ld / math / stores of its 128 rows -> arrive on the leader's
+//                         tmem_empty[acc]
+// ------------------------------------------------------------------------------------------------------------------
+template <bool A_K, bool B_K>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc5_persist_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                             const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                             const __grid_constant__ Args g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2] (the leader's copies are the ones waited on)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  constexpr int PM = 2 * BM, PN = 2 * BN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int tiles_m = (g.M + PM - 1) / PM, tiles_n = (g.N + PN - 1) / PN;
+  const int kb_total = (g.K + BK - 1) / BK;
+  const int kb_per = (kb_total + g.k_splits - 1) / g.k_splits;
+  const int num_tiles = tiles_m * tiles_n * g.k_splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 2); mbar_init(empty_bar + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 5) tmem_alloc_2cta(tmem_slot, 2 * PN);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (z, m, n): n fastest (see the single-CTA kernel).  m0 = first row of THIS CTA, n0 = first column of the pair
+  auto decode = [&](int t, int& m0, int& n0, int& kb_begin, int& nkb, int& z) {
+    const int ni = t % tiles_n;
+    const int r = t / tiles_n;
+    const int mi = r % tiles_m;
+    z = r / tiles_m;
+    m0 = mi * PM + (int)rank * BM; n0 = ni * PN;
+    kb_begin = z * kb_per;
+    const int kb_end = min(kb_total, kb_begin + kb_per);
+    nkb = max(0, kb_end - kb_begin);
+  };
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = pair_id; t < num_tiles; t += num_pairs) {
+        int m0, n0, kb_begin, nkb, z;
+        decode(t, m0, n0, kb_begin, nkb, z);
+        const int nb0 = n0 + (int)rank * BN;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          if (it >= STAGES) mbar_wait(empty_bar + s, ((it / STAGES) - 1) & 1);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          const int k0 = (kb_begin + i) * BK;
+          if (leader) mbar_expect_tx(full_bar + s, 2 * STAGE_BYTES);
+          else mbar_arrive_remote_leader(full_bar + s);
+          if (A_K) {
+            tma_load_2d_2cta(st, &tmAh, full_bar + s, k0, m0);
+            tma_load_2d_2cta(st + TILE_BYTES, &tmAl, full_bar + s, k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 32; ++j) {
+              tma_load_2d_2cta(st + j * 4096, &tmAh, full_bar + s, m0 + 32 * j, k0);
+              tma_load_2d_2cta(st + TILE_BYTES + j * 4096, &tmAl, full_bar + s, m0 + 32 * j, k0);
+            }
+          }
+          if (B_K) {
+            tma_load_2d_2cta(st + 2 * TILE_BYTES, &tmBh, full_bar + s, k0, nb0);
+            tma_load_2d_2cta(st + 3 * TILE_BYTES, &tmBl, full_bar + s, k0, nb0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j) {
+              tma_load_2d_2cta(st + 2 * TILE_BYTES + j * 4096, &tmBh, full_bar + s, nb0 + 32 * j, k0);
+              tma_load_2d_2cta(st + 3 * TILE_BYTES + j * 4096, &tmBl, full_bar + s, nb0 + 32 * j, k0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = instr_desc(!A_K, !B_K, PM, PN);
+      uint32_t it = 0, lt = 0;
+      for (int t = pair_id; t < num_tiles; t += num_pairs, ++lt) {
+        int m0, n0, kb_begin, nkb, z;
+        decode(t, m0, n0, kb_begin, nkb, z);
+        const uint32_t acc = lt & 1, use = lt >> 1;
+        if (use > 0) mbar_wait(tmem_empty + acc, (use - 1) & 1);    // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * PN;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(full_bar + s, (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t st = s32(smem + s * STAGE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint32_t a_off = A_K ? kk * 32 : kk * 1024;
+            const uint32_t b_off = B_K ? kk * 32 : kk * 1024;
+            const uint32_t a_lbo = A_K ? 16 : 4096, b_lbo = B_K ? 16 : 4096;
+            const uint32_t a_sbo = A_K ? 1024 : 512, b_sbo = B_K ? 1024 : 512;
+            const uint32_t a_lt = A_K ? 2 : 1, b_lt = B_K ? 2 : 1;
+            const uint64_t dAh = smem_desc(st + a_off, a_lbo, a_sbo, a_lt);
+            const uint64_t dAl = smem_desc(st + TILE_BYTES + a_off, a_lbo, a_sbo, a_lt);
+            const uint64_t dBh = smem_desc(st + 2 * TILE_BYTES + b_off, b_lbo, b_sbo, b_lt);
+            const uint64_t dBl = smem_desc(st + 3 * TILE_BYTES + b_off, b_lbo, b_sbo, b_lt);
+            umma_tf32_2cta(tmem_d, dAl, dBh, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+            umma_tf32_2cta(tmem_d, dAh, dBl, idesc, 1u);
+            umma_tf32_2cta(tmem_d, dAh, dBh, idesc, 1u);
+          }
+          umma_commit_2cta(empty_bar + s);       // frees the stage in both CTAs
+        }
+        umma_commit_2cta(tmem_full + acc);
+      }
+    }
+  } else {
+    uint32_t lt = 0;
+    for (int t = pair_id; t < num_tiles; t += num_pairs, ++lt) {
+      int m0, n0, kb_begin, nkb, z;
+      decode(t, m0, n0, kb_begin, nkb, z);
+      const uint32_t acc = lt & 1, use = lt >> 1;
+      mbar_wait(tmem_full + acc, use & 1);
+      tc_fence_after();
+      const int m = m0 + warp * 32 + lane;
+      if (nkb > 0) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < PN; c0 += 32) {
+          if (n0 + c0 >= g.N) break;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + acc * PN + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+          if (m < g.M) epilogue_store(g, r, m, n0 + c0, z == 0);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { if (leader) mbar_arrive(tmem_empty + acc); else mbar_arrive_remote_leader(tmem_empty + acc); }
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();                            // the peer may still be reading / the leader still issuing
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 2 * PN);
+  }
+}
+
 // x -> hi = rna_tf32(x), lo = rna_tf32(x - hi) over a strided [rows, cols] block
 __global__ void split_tf32_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols, float* __restrict__ hi,
                                   float* __restrict__ lo, int64_t ldo) {
@@ -608,7 +776,8 @@ extern "C" int phc_gemm_tc5(const float* A_hi, const float* A_lo, int64_t lda, i
   // measured on the PPO shapes (bench.py): single-CTA tiles with the persistent, epilogue-overlapped kernel beat the pair
   // tiles, so the pair path is opt-in (PHC_TC5_PAIR=1) and the persistent kernel is the default (PHC_TC5_PERSIST=0 disables)
   const bool pair = (M > BM) && (N > BN + BN / 2) && getenv("PHC_TC5_PAIR") && getenv("PHC_TC5_PAIR")[0] == '1';
-  const bool persist = !pair && !(getenv("PHC_TC5_PERSIST") && getenv("PHC_TC5_PERSIST")[0] == '0');
+  const bool pairp = !pair && (M > BM) && (N > BN) && getenv("PHC_TC5_PAIRP") && getenv("PHC_TC5_PAIRP")[0] == '1';
+  const bool persist = !pair && !pairp && !(getenv("PHC_TC5_PERSIST") && getenv("PHC_TC5_PERSIST")[0] == '0');
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   cudaLaunchConfig_t cfg = {};
@@ -644,7 +813,33 @@ extern "C" int phc_gemm_tc5(const float* A_hi, const float* A_lo, int64_t lda, i
     else if (!a_kmajor && b_kmajor) PHC_TC5_LAUNCH(false, true, NC); \
     else PHC_TC5_LAUNCH(false, false, NC);                         \
   } while (0)
-  if (persist) {
+  if (pairp) {
+    static int num_sms2 = 0;
+    if (!num_sms2) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms2, cudaDevAttrMultiProcessorCount, dev); if (num_sms2 <= 0) num_sms2 = 148; }
+    const int tiles2 = ((M + 2 * BM - 1) / (2 * BM)) * ((N + 2 * BN - 1) / (2 * BN)) * k_splits;
+    const int pairs = tiles2 < num_sms2 / 2 ? tiles2 : num_sms2 / 2;
+    cfg.gridDim = dim3(2 * pairs);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+#define PHC_TC5_PPLAUNCH(AK, BK_)                                                                                                \
+  do {                                                                                                                           \
+    static bool done = false;                                                                                                    \
+    if (!done) {                                                                                                                 \
+      e = cudaFuncSetAttribute(gemm_tc5_persist_pair_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);  \
+      if (e != cudaSuccess) return phc_check_cuda(e, "cudaFuncSetAttribute(gemm_tc5_persist_pair)");                             \
+      done = true;                                                                                                               \
+    }                                                                                                                            \
+    e = cudaLaunchKernelEx(&cfg, gemm_tc5_persist_pair_kernel<AK, BK_>, tAh, tAl, tBh, tBl, g);                                  \
+    if (e != cudaSuccess) return phc_check_cuda(e, "cudaLaunchKernelEx(gemm_tc5_persist_pair)");                                 \
+    phc_count_launches(1);                                                                                                       \
+  } while (0)
+    if (a_kmajor && b_kmajor) PHC_TC5_PPLAUNCH(true, true);
+    else if (a_kmajor && !b_kmajor) PHC_TC5_PPLAUNCH(true, false);
+    else if (!a_kmajor && b_kmajor) PHC_TC5_PPLAUNCH(false, true);
+    else PHC_TC5_PPLAUNCH(false, false);
+#undef PHC_TC5_PPLAUNCH
+  } else if (persist) {
     static int num_sms = 0;
     if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * k_splits;

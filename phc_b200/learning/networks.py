@@ -183,7 +183,7 @@ class AMPNetwork:
 
 def _splits(tiles: int, K: int) -> int:
     """split-K factor for the weight-gradient GEMMs (M, N are layer widths, K is the batch)."""
-    want = max(1, (2 * 148 + tiles - 1) // tiles)
+    want = max(1, (4 * 148 + tiles - 1) // tiles)      # ~4 tiles per SM: measured 176 vs 211 us (1024x934, K=16384) against 2 per SM
     return int(max(1, min(want, K // 512, 64)))
 
 

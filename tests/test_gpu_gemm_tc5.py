@@ -13,15 +13,18 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.fixture(params=["persistent", "one_tile_per_cta", "cta_pair"], autouse=True)
+@pytest.fixture(params=["persistent", "one_tile_per_cta", "cta_pair", "cta_pair_persistent"], autouse=True)
 def tc5_mode(request, monkeypatch):
-    """The three launch variants of the same kernel family (selected by environment variables read per call)."""
+    """The four launch variants of the same kernel family (selected by environment variables read per call)."""
     monkeypatch.delenv("PHC_TC5_PERSIST", raising=False)
     monkeypatch.delenv("PHC_TC5_PAIR", raising=False)
+    monkeypatch.delenv("PHC_TC5_PAIRP", raising=False)
     if request.param == "one_tile_per_cta":
         monkeypatch.setenv("PHC_TC5_PERSIST", "0")
     elif request.param == "cta_pair":
         monkeypatch.setenv("PHC_TC5_PAIR", "1")
+    elif request.param == "cta_pair_persistent":
+        monkeypatch.setenv("PHC_TC5_PAIRP", "1")
     return request.param
 
 

@@ -34,12 +34,13 @@ def run(name, M, N, K, a_k, b_k, splits=1, mask=False, split_out=False):
     Ah, Al = split(A)
     Bh, Bl = split(B)
     acc = 1 if splits > 1 else 0
-    variants = [("persist", {}), ("plain", {"PHC_TC5_PERSIST": "0"}), ("pair", {"PHC_TC5_PAIR": "1"}), ("mma.sync", None)]
+    variants = [("persist", {}), ("plain", {"PHC_TC5_PERSIST": "0"}), ("pair", {"PHC_TC5_PAIR": "1"}),
+                ("pairp", {"PHC_TC5_PAIRP": "1"}), ("mma.sync", None)]
     out = []
     for vname, env in variants:
         if only and vname != only:
             continue
-        for k in ("PHC_TC5_PERSIST", "PHC_TC5_PAIR"):
+        for k in ("PHC_TC5_PERSIST", "PHC_TC5_PAIR", "PHC_TC5_PAIRP"):
             os.environ.pop(k, None)
         if env:
             os.environ.update(env)
@@ -70,6 +71,8 @@ run("fwd  1024->512 (B=16384)", 16384, 512, 1024, True, True, split_out=True)
 run("fwd  amp->1024 (B=12288)", 12288, 1024, 1960, True, True, split_out=True)
 run("dX   512->1024 (B=16384) +mask", 16384, 1024, 512, True, False, mask=True, split_out=True)
 run("dW   1024x934  (K=16384) s=5", 1024, 934, 16384, False, False, splits=5)
+run("dW   1024x934  (K=16384) s=9", 1024, 934, 16384, False, False, splits=9)
 run("dW   512x1024  (K=16384) s=10", 512, 1024, 16384, False, False, splits=10)
+run("dW   512x1024  (K=16384) s=18", 512, 1024, 16384, False, False, splits=18)
 run("fwd  rollout obs->1024 (B=4096)", 4096, 1024, 934, True, True, split_out=True)
 run("fwd  big square 8192^3/8", 8192, 8192, 1024, True, True)
