@@ -78,6 +78,14 @@ typedef struct PhcEnvMotion {
 
 PHC_API int phc_env_motion_gather(const PhcMotionLib* lib, const int64_t* motion_ids, int64_t n, PhcEnvMotion* out, void* stream);
 
+/* Reset bookkeeping of the envs with mask != 0 in one launch (Humanoid._reset_envs / HumanoidIm._reset_task,
+ * humanoid_im.py:955-1023): start_times = trunc(phase * len / (1/30)) * (1/30) (MotionLibBase.sample_time_interval,
+ * motion_lib_base.py:414-423; phase = caller-supplied uniform [0,1) numbers), start_offsets / global_offset /
+ * cycle_counter / progress / reset / terminate = 0.  cycle_counter, reset, terminate may be NULL. */
+PHC_API int phc_reset_bookkeeping(const int64_t* mask, const float* phase, const PhcEnvMotion* env_motion, int64_t n,
+                          float* start_times, float* start_offsets, float* global_offset /* [n,3] */, int32_t* cycle_counter,
+                          int64_t* progress, int64_t* reset, int64_t* terminate, void* stream);
+
 PHC_API int phc_motion_body_stride(int32_t num_bodies);        /* pass J + E for robots */
 PHC_API int phc_motion_joint_stride(int32_t num_bodies);
 PHC_API int phc_motion_dof_stride(int32_t num_dofs);           /* joint_stride of a hinge-joint robot: round_up(2*D, 4) */

@@ -73,6 +73,7 @@ SIGNATURES = {
     "phc_launch_count": (C.c_int64, []),
     "phc_env_motion_gather": (C.c_int, [C.POINTER(PhcMotionLib), _p, C.c_int64, _p, _p]),
     "phc_motion_body_stride": (C.c_int, [C.c_int32]),
+    "phc_reset_bookkeeping": (C.c_int, [_p, _p, _p, C.c_int64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "phc_motion_dof_stride": (C.c_int, [C.c_int32]),
     "phc_motion_pack_dofs": (C.c_int, [_p, _p, C.c_int64, C.c_int32, _p, _p]),
     "phc_amp_obs_dim_robot": (C.c_int, [C.c_int32, C.c_int32, C.c_uint32]),

@@ -250,6 +250,27 @@ __global__ void env_motion_gather_kernel(const __grid_constant__ PhcMotionLib li
   out[i] = e;
 }
 
+// Reset bookkeeping of the selected envs in one pass (Humanoid._reset_envs / HumanoidIm._reset_task, humanoid_im.py:955-1023):
+// new start time on the 1/30 s grid from a uniform phase (MotionLibBase.sample_time_interval, motion_lib_base.py:414-423),
+// start offset / global offset / cycle counter / progress / reset / terminate cleared.
+__global__ void reset_bookkeeping_kernel(const int64_t* __restrict__ mask, const float* __restrict__ phase,
+                                         const PhcEnvMotion* __restrict__ em, int64_t n, float* __restrict__ start_times,
+                                         float* __restrict__ start_offsets, float* __restrict__ global_offset,
+                                         int32_t* __restrict__ cycle_counter, int64_t* __restrict__ progress,
+                                         int64_t* __restrict__ reset, int64_t* __restrict__ terminate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || mask[i] == 0) return;
+  const float grid = 1.0f / 30.0f;
+  const long long k = (long long)((phase[i] * em[i].len) / grid);          // .long(): truncation
+  start_times[i] = (float)k * grid;
+  start_offsets[i] = 0.0f;
+  global_offset[3 * i] = 0.0f; global_offset[3 * i + 1] = 0.0f; global_offset[3 * i + 2] = 0.0f;
+  if (cycle_counter) cycle_counter[i] = 0;
+  progress[i] = 0;
+  if (reset) reset[i] = 0;
+  if (terminate) terminate[i] = 0;
+}
+
 // Reset path: write the reference pose at (id, time) of every env with mask != 0 into the simulator tensors
 // (HumanoidAMP._set_env_state, humanoid_amp.py:605-637: rigid-body rows + dof pos/vel), warp per env.
 __global__ void __launch_bounds__(128)
@@ -426,4 +447,16 @@ extern "C" int phc_env_motion_gather(const PhcMotionLib* lib, const int64_t* ids
   if (n == 0) return PHC_OK;
   phc::env_motion_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*lib, ids, n, out); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "env_motion_gather_kernel launch");
+}
+
+extern "C" int phc_reset_bookkeeping(const int64_t* mask, const float* phase, const PhcEnvMotion* env_motion, int64_t n,
+                                     float* start_times, float* start_offsets, float* global_offset, int32_t* cycle_counter,
+                                     int64_t* progress, int64_t* reset, int64_t* terminate, void* stream) {
+  if (n == 0) return PHC_OK;
+  if (!mask || !phase || !env_motion || n < 0 || !start_times || !start_offsets || !global_offset || !progress) {
+    phc_set_error("phc_reset_bookkeeping: bad arguments"); return PHC_ERR_INVALID_ARG;
+  }
+  phc::reset_bookkeeping_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      mask, phase, env_motion, n, start_times, start_offsets, global_offset, cycle_counter, progress, reset, terminate); phc_count_launches(1);
+  return phc_check_cuda(cudaGetLastError(), "reset_bookkeeping_kernel launch");
 }

@@ -276,16 +276,13 @@ class HumanoidIm:
         """Humanoid.reset -> _reset_envs (humanoid.py:537-621, humanoid_amp.py:378-387,:509-603, humanoid_im.py:955-1023)
         with reference-state initialisation, for the envs selected by `env_ids` (None = all, a [N] mask, or indices)."""
         self._set_mask(env_ids)
-        m = self._reset_mask.bool()
-        new_t = self._sample_time(self._sampled_motion_ids).float()
-        self._motion_start_times.copy_(torch.where(m, new_t, self._motion_start_times))
-        self._motion_start_times_offset.masked_fill_(m, 0.0)
-        self._global_offset.masked_fill_(m.unsqueeze(-1), 0.0)
-        self._cycle_counter.masked_fill_(m, 0)
-        self.progress_buf.masked_fill_(m, 0)
-        self.reset_buf.masked_fill_(m, 0)
-        self._terminate_buf.masked_fill_(m, 0)
         lib, ml, st = self._lib, self._motion_lib, _stream()
+        # new start time (sample_time_interval) + cleared counters of the selected envs: one launch
+        phase = torch.rand(self.num_envs, device=self.device)
+        _lib.check(lib.phc_reset_bookkeeping(self._reset_mask.data_ptr(), phase.data_ptr(), self._plan._env_motion.data_ptr(), self.num_envs,
+                                             self._motion_start_times.data_ptr(), self._motion_start_times_offset.data_ptr(),
+                                             self._global_offset.data_ptr(), self._cycle_counter.data_ptr(), self.progress_buf.data_ptr(),
+                                             self.reset_buf.data_ptr(), self._terminate_buf.data_ptr(), st), "phc_reset_bookkeeping")
         # _set_env_state: reference pose at the sampled time into the simulator tensors of the reset envs
         _lib.check(lib.phc_set_env_state(C.byref(ml.c), self._sampled_motion_ids.data_ptr(), self._motion_start_times.data_ptr(),
                                          self._global_offset.data_ptr(), self._reset_mask.data_ptr(), self.num_envs,
