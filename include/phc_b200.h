@@ -101,6 +101,26 @@ PHC_API int phc_motion_pack(const float* gts, const float* grs, const float* gvs
                     const float* dvs, int64_t num_frames_total, int32_t num_bodies, float* frames_body,
                     float* frames_joint, void* stream);
 
+/* Motion LOADER: the per-clip CPU work of MotionLibSMPL.load_motion_with_skeleton
+ * (phc/utils/motion_lib_smpl.py:101-180) for all clips of a (re)load in two launches -- heading randomisation (:141-149),
+ * local rotations + forward kinematics (poselib/poselib/skeleton/skeleton3d.py:390-461), np.gradient / frame-to-frame
+ * angle-axis velocities with scipy's gaussian_filter1d(sigma 2, "nearest") (skeleton3d.py:1100-1121) and
+ * compute_motion_dof_vels (phc/utils/motion_lib_base.py:47-70).  Inputs are the on-disk clip arrays, concatenated over
+ * clips, float64 as joblib yields them:
+ *   pose_quat_global [F, J, 4] xyzw, root_trans [F, 3] ("root_trans_offset"), offsets [M, J, 3] = every clip's
+ *   skeleton_tree.local_translation, parents [J] (-1 = root, parents[j] < j), heading [M] = angle about z in radians
+ *   (the reference draws pi * (2 u - 1); NULL = flags.im_eval / flags.test: no randomisation), fps [M],
+ *   length_starts / num_frames [M] (every clip needs >= 2 frames, as np.gradient does).
+ * Outputs are the reference's float32 tables gts[F,J,3] grs[F,J,4] lrs[F,J,4] gvs[F,J,3] gavs[F,J,3] dvs[F,J-1,3]; feed them
+ * to phc_motion_pack.  workspace: phc_motion_load_workspace_bytes(F, J) bytes, 16-byte aligned.  fix_trans_height (needs
+ * the SMPL mesh model) is not part of this entry point: pass height-fixed translations. */
+#define PHC_LOAD_MAX_BODIES 64
+PHC_API int64_t phc_motion_load_workspace_bytes(int64_t num_frames_total, int32_t num_bodies);
+PHC_API int phc_motion_load(const double* pose_quat_global, const double* root_trans, const double* offsets,
+                    const int32_t* parents, const double* heading, const int64_t* length_starts, const int64_t* num_frames,
+                    const double* fps, int64_t num_frames_total, int32_t num_motions, int32_t num_bodies, float* gts,
+                    float* grs, float* lrs, float* gvs, float* gavs, float* dvs, void* workspace, void* stream);
+
 /* MotionLibBase.get_motion_state (motion_lib_base.py:437-520, SMPL variant) for n arbitrary (id, time) queries:
  * frame bracket (_calc_frame_blend :549-559), lerp of pos/vel/angvel/dof_vel (+offset on pos), slerp of global
  * and local rotations, dof_pos = exp_map(local_rot[1:]).  Any output pointer may be NULL (skipped).

@@ -79,6 +79,8 @@ SIGNATURES = {
     "phc_amp_obs_dim_robot": (C.c_int, [C.c_int32, C.c_int32, C.c_uint32]),
     "phc_motion_joint_stride": (C.c_int, [C.c_int32]),
     "phc_motion_pack": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int64, C.c_int32, _p, _p, _p]),
+    "phc_motion_load_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
+    "phc_motion_load": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, C.c_int64, C.c_int32, C.c_int32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "phc_motion_state": (C.c_int, [C.POINTER(PhcMotionLib), _p, _p, _p, C.c_int64, C.POINTER(PhcMotionStateOut), _p]),
     "phc_self_obs_dim": (C.c_int, [C.c_int32, C.c_uint32]),
     "phc_task_obs_dim": (C.c_int, [C.c_int32, C.c_int32]),

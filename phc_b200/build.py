@@ -29,6 +29,7 @@ SOURCES = {
     "phc_api.cu": [],
     "env_step.cu": ["-fmad=false"] if os.environ.get("PHC_ENV_FMAD", "1") == "0" else [],
     "motion.cu": ["-fmad=false"],
+    "motion_load.cu": ["-fmad=false"],
     "ppo_scalars.cu": ["-fmad=false"],
     "gemm.cu": [],
     "gemm_tc5.cu": [],

@@ -98,6 +98,8 @@ class HumanoidIm:
                                                          d.num_frames.to(dev), d.dts.to(dev), d.length_starts.to(dev))
             if self.humanoid_type == "smpl":
                 self.humanoid_type = "h1"
+        elif isinstance(getattr(d, "packed", None), ops.PackedMotionLib):
+            self._motion_lib = d.packed           # phc_b200.motion_lib.MotionLibSMPL: loaded and packed on the device already
         else:
             self._motion_lib = ops.pack_motion_lib(d.gts, d.grs, d.gvs, d.gavs, d.lrs, d.dvs, d.lengths, d.num_frames, d.dts,
                                                    d.length_starts)

@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import (PHC_FLAG_EARLY_TERM, PHC_FLAG_LOCAL_ROOT_OBS, PHC_FLAG_NO_COLLISION, PHC_FLAG_POWER_REWARD,
                    PHC_FLAG_ROOT_HEIGHT_OBS, PHC_FLAG_TERM_USE_MEAN, PHC_FLAG_UPRIGHT, PhcError)
 
-__all__ = ["PackedMotionLib", "pack_motion_lib", "motion_state", "EnvStepConfig", "EnvStepPlan", "amp_obs_demo",
+__all__ = ["PackedMotionLib", "pack_motion_lib", "load_motion_tables", "motion_state", "EnvStepConfig", "EnvStepPlan", "amp_obs_demo",
            "gae", "adv_norm", "PhcError"]
 
 
@@ -128,6 +128,45 @@ def pack_robot_motion_lib(gts_t, grs_t, gvs_t, gavs_t, dof_pos, dof_vel, num_bod
     c = _lib.PhcMotionLib(fb.data_ptr(), fj.data_ptr(), lengths.data_ptr(), dts.data_ptr(), num_frames.data_ptr(),
                           length_starts.data_ptr(), F, int(lengths.shape[0]), J, bs, js, E, D)
     return PackedMotionLib(fb, fj, lengths, dts, num_frames, length_starts, J, c, E, D)
+
+
+def load_motion_tables(pose_quat_global: torch.Tensor, root_trans: torch.Tensor, offsets: torch.Tensor, parents: torch.Tensor,
+                       num_frames: torch.Tensor, fps: torch.Tensor, heading: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """phc_motion_load: concatenated on-disk clip arrays (float64, on the device) -> the reference's float32 tables
+    gts / grs / lrs / gvs / gavs / dvs plus lengths / dts / length_starts (motion_lib_base.py:262-313)."""
+    lib = _lib.load()
+    f64, i64 = torch.float64, torch.int64
+    q = _req(pose_quat_global, f64, "pose_quat_global")
+    dev = q.device
+    F, J = int(q.shape[0]), int(q.shape[1])
+    t = _req(root_trans, f64, "root_trans", dev)
+    off = _req(offsets, f64, "offsets", dev)
+    par = _req(parents, torch.int32, "parents", dev)
+    nf = _req(num_frames, i64, "num_frames", dev)
+    fps = _req(fps, f64, "fps", dev)
+    M = int(nf.shape[0])
+    assert q.shape == (F, J, 4) and t.shape == (F, 3) and off.shape == (M, J, 3) and par.shape == (J,) and fps.shape == (M,)
+    if heading is not None:
+        heading = _req(heading, f64, "heading", dev)
+        assert heading.shape == (M,)
+    starts = (torch.cumsum(nf, 0) - nf).contiguous()
+    f32 = torch.float32
+    out = dict(gts=torch.empty(F, J, 3, dtype=f32, device=dev), grs=torch.empty(F, J, 4, dtype=f32, device=dev),
+               lrs=torch.empty(F, J, 4, dtype=f32, device=dev), gvs=torch.empty(F, J, 3, dtype=f32, device=dev),
+               gavs=torch.empty(F, J, 3, dtype=f32, device=dev), dvs=torch.empty(F, J - 1, 3, dtype=f32, device=dev))
+    ws = torch.empty(max(16, int(lib.phc_motion_load_workspace_bytes(F, J))), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.phc_motion_load(q.data_ptr(), t.data_ptr(), off.data_ptr(), par.data_ptr(), _ptr(heading),
+                                       starts.data_ptr(), nf.data_ptr(), fps.data_ptr(), F, M, J, out["gts"].data_ptr(),
+                                       out["grs"].data_ptr(), out["lrs"].data_ptr(), out["gvs"].data_ptr(),
+                                       out["gavs"].data_ptr(), out["dvs"].data_ptr(), ws.data_ptr(), _stream()),
+                   "phc_motion_load")
+    ws.record_stream(torch.cuda.current_stream(dev))
+    out["num_frames"] = nf
+    out["length_starts"] = starts
+    out["dts"] = (1.0 / fps).to(f32)                                      # curr_dt = 1.0 / motion_fps
+    out["lengths"] = ((1.0 / fps) * (nf - 1).to(f64)).to(f32)            # curr_len = 1.0 / motion_fps * (num_frames - 1)
+    return out
 
 
 _MS_KEYS = {"rg_pos": 3, "rb_rot": 4, "body_vel": 3, "body_ang_vel": 3}

@@ -482,7 +482,70 @@ def gen_h1():
     save("h1.npz", d)
 
 
+# ------------------------------------------------------------------------------------------------
+def gen_load():
+    """MotionLibSMPL.load_motion_with_skeleton (phc/utils/motion_lib_smpl.py:101-180) executed UNMODIFIED on synthetic
+    clips in the on-disk format ({pose_quat_global [T,J,4], root_trans_offset [T,3], pose_aa, fps}): heading randomisation
+    (scipy), SkeletonState.from_rotation_and_root_translation(is_local=False), SkeletonMotion.from_skeleton_state (FK +
+    gaussian-filtered finite differences, poselib skeleton3d.py:1000-1121) and compute_motion_dof_vels
+    (motion_lib_base.py:47-70).  The heading angle of clip f is pi*(2u-1) with u the f-th np.random.random() after
+    np.random.seed(0) (pid 0 seeds with randint(5000)*0) -- recorded here as an input."""
+    from poselib.poselib.skeleton.skeleton3d import SkeletonTree, SkeletonState
+    import phc.utils.motion_lib_smpl as mls
+    from phc.utils.motion_lib_smpl import MotionLibSMPL
+    # smpl_sim (unpinned git dependency, absent here) supplies to_torch: tensor -> itself, ndarray -> torch.from_numpy
+    mls.to_torch = lambda x: x if torch.is_tensor(x) else torch.from_numpy(np.asarray(x))
+    from phc.utils import flags as flags_mod
+    flags = flags_mod.flags
+    flags.im_eval, flags.test, flags.real_traj = False, False, False
+    J = 24
+    g = torch.Generator().manual_seed(5)
+    frames = [2, 3, 9, 17, 18, 45]                    # shorter than / equal to / longer than the 17-tap filter window
+    fps_list = [30, 30, 30, 60, 30, 30]
+    parents = torch.tensor(syn.SMPL_PARENTS)
+    base_off = torch.tensor(syn._SMPL_OFFSETS, dtype=torch.float64)
+    trees, clips = [], []
+    for F, fps in zip(frames, fps_list):
+        scale = 0.8 + 0.4 * torch.rand(J, 1, generator=g, dtype=torch.float64)     # per-clip body shape: own bone lengths
+        off = base_off * scale
+        tree = SkeletonTree([f"b{j}" for j in range(J)], parents, off)
+        walk = torch.cumsum(torch.randn(F, J, 3, generator=g, dtype=torch.float64) * 0.08, 0) + torch.randn(1, J, 3, generator=g, dtype=torch.float64) * 0.5
+        ang = walk.norm(dim=-1, keepdim=True).clamp(min=1e-12)
+        lr = torch.cat([walk / ang * torch.sin(ang / 2), torch.cos(ang / 2)], -1)
+        if F >= 9:
+            lr[4, 7] = lr[3, 7]                       # a joint that does not move between two frames (zero angle branch)
+        trans = torch.cumsum(torch.randn(F, 3, generator=g, dtype=torch.float64) * 0.03, 0) + torch.tensor([0.3, -0.2, 0.9], dtype=torch.float64)
+        st = SkeletonState.from_rotation_and_root_translation(tree, lr, trans, is_local=True)
+        gq = st.global_rotation.clone()
+        if F >= 9:
+            gq[5] = -gq[5]                            # on-disk quaternions carry arbitrary signs
+        clips.append({"pose_quat_global": gq.numpy().copy(), "root_trans_offset": trans.clone(),
+                      "pose_aa": np.zeros((F, J * 3)), "fps": fps})
+        trees.append(tree)
+    cfg = types.SimpleNamespace(max_length=-1, fix_height=0, multi_thread=False)
+    np.random.seed(0)
+    heading = np.array([np.pi * (2 * np.random.random() - 1.0) for _ in frames])
+    shape_params = [torch.zeros(17) for _ in frames]
+    res = MotionLibSMPL.load_motion_with_skeleton(np.arange(len(frames)), clips, trees, shape_params, None, cfg, None, 0)
+    d = dict(parents=parents, heading=heading, num_frames=np.array(frames), fps=np.array(fps_list, dtype=np.float64),
+             offsets=torch.stack([t.local_translation.double() for t in trees]),
+             pose_quat_global=np.concatenate([c["pose_quat_global"] for c in clips]),
+             root_trans=torch.cat([c["root_trans_offset"] for c in clips]))
+    ms = [res[i][1] for i in range(len(frames))]
+    d["gts"] = torch.cat([m.global_translation for m in ms]).float()
+    d["grs"] = torch.cat([m.global_rotation for m in ms]).float()
+    d["lrs"] = torch.cat([m.local_rotation for m in ms]).float()
+    d["gvs"] = torch.cat([m.global_velocity for m in ms]).float()
+    d["gavs"] = torch.cat([m.global_angular_velocity for m in ms]).float()
+    d["dvs"] = torch.cat([m.dof_vels for m in ms]).float()
+    save("load.npz", d)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        for name in sys.argv[1:]:
+            globals()["gen_" + name]()
+        sys.exit(0)
     gen_mcp()
     gen_h1()
     gen_quat()

@@ -1,6 +1,8 @@
 """Pin oracle/phc_oracle.py against the golden vectors produced by the UNMODIFIED reference
 (tests/golden/make_golden.py).  CPU only.  Tolerance: rtol 1e-5 / atol 1e-6 fp32 (north_star), except where a
 comment says otherwise (ill-conditioned acos near identity -- SURVEY.md section 7)."""
+import os
+
 import numpy as np
 import torch
 
@@ -232,3 +234,24 @@ def test_h1_amp_obs_demo_matches_reference():
     g = load("h1.npz")
     out = O.amp_obs_demo_robot(robot_tables_from(g), h1_step_config(), g["demo_ids"], g["demo_t0"])
     close(out, g["demo_out"], what="h1 amp_obs_demo")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# motion LOADER: oracle/motion_load_oracle.py against the real MotionLibSMPL.load_motion_with_skeleton
+# ----------------------------------------------------------------------------------------------------------------
+def test_motion_loader_matches_reference():
+    import numpy as np
+    from oracle import motion_load_oracle as ML
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "load.npz"))
+    out = ML.load_clips(z["pose_quat_global"], z["root_trans"], z["num_frames"], z["fps"], z["parents"], z["offsets"], z["heading"])
+    for k in ("gts", "grs", "lrs", "gvs", "gavs"):          # float64 pipeline: identical after the float32 cast
+        close(out[k], z[k], rtol=1e-6, atol=1e-7, what=f"load {k}")
+    close(out["dvs"], z["dvs"], rtol=1e-5, atol=2e-5, what="load dvs")   # float32 2*acos(w) of frame-to-frame rotations
+
+
+def test_motion_loader_filter_taps_are_scipys():
+    import numpy as np
+    from scipy.ndimage import gaussian_filter1d
+    from oracle import motion_load_oracle as ML
+    x = np.random.default_rng(0).standard_normal((23, 3, 2))
+    np.testing.assert_allclose(ML.filter_time(x), gaussian_filter1d(x, 2, axis=0, mode="nearest"), rtol=1e-13, atol=1e-14)
