@@ -168,6 +168,11 @@ PHC_API int phc_motion_state(const PhcMotionLib* lib, const int64_t* motion_ids,
 #define PHC_FLAG_TERM_USE_MEAN (1u << 6)   /* flags.im_eval and not strict_eval: mean-distance criterion */
 #define PHC_FLAG_OBS_ONLY (1u << 7)        /* _compute_observations(env_ids) of the reset path: write obs (+ref_*) only */
 #define PHC_FLAG_REWARD_FROM_CACHE (1u << 8) /* reward / reset read the reference pose from ref_cache (see PhcStepArgs) */
+/* env_im_getup_mcp.yaml -- the configuration HumanoidImMCP trains in (time_steps 1, SMPL joints): */
+#define PHC_FLAG_ZERO_OUT_FAR (1u << 9)   /* env.zero_out_far (zero_out_far_train False): point-goal reward mix (humanoid_im.py:890-905),
+                                             task-obs overwrites for far references and the _point_goal update (:783-796) */
+#define PHC_FLAG_CYCLE_MOTION (1u << 10)  /* env.cycle_motion: the launch runs _update_cycle_count (:1076-1079) and the clip
+                                             wrap-around of _compute_reset (:1120-1146); pass_time = progress >= max_len - 1 */
 
 #define PHC_MAX_KEY_BODIES 8
 #define PHC_MAX_BODIES 32      /* one body per lane in the fused step kernel */
@@ -183,10 +188,11 @@ typedef struct PhcStepArgs {
   const int64_t* progress;       /* [N] progress_buf                    */
   const int64_t* motion_ids;     /* [N] _sampled_motion_ids             */
   const PhcEnvMotion* env_motion;/* [N] optional pre-gathered parameters of motion_ids (phc_env_motion_gather); NULL = look up */
-  const float* start_times;      /* [N] _motion_start_times             */
-  const float* start_offsets;    /* [N] _motion_start_times_offset      */
-  const float* global_offset;    /* [N,3] _global_offset                */
-  const int32_t* cycle_counter;  /* [N] _cycle_counter or NULL (is_recovery override, humanoid_im.py:1186-1188) */
+  /* read-only unless PHC_FLAG_CYCLE_MOTION is set: then a clip that wraps this step gets its re-based values written back */
+  float* start_times;            /* [N] _motion_start_times             */
+  float* start_offsets;          /* [N] _motion_start_times_offset      */
+  float* global_offset;          /* [N,3] _global_offset                */
+  int32_t* cycle_counter;        /* [N] _cycle_counter or NULL (is_recovery override, humanoid_im.py:1186-1188) */
   const int64_t* only_where;     /* [N] or NULL: when given, only envs with only_where[env] != 0 are processed (the
                                     reference's `env_ids` subset, kept as a mask so no host sync / nonzero() is needed) */
   PhcMotionLib lib;
@@ -239,6 +245,12 @@ typedef struct PhcStepArgs {
    * progress-1 and the same start / offset / clip -- which HumanoidIm's step / reset sequence guarantees.  The values
    * are bit-identical to re-interpolating.  ref_body_* above are then strided views of it (columns 0:3, 3:7, 7:10, 10:13). */
   float* ref_cache;
+  /* ---- PHC_FLAG_ZERO_OUT_FAR / PHC_FLAG_CYCLE_MOTION (appended; ignored when both flags are clear) ---- */
+  float close_distance;        /* env.close_distance (0.25): beyond it the task obs sees the simulated pose as reference   */
+  float far_distance;          /* env.far_distance (3): beyond it the reference root becomes a direction of this length    */
+  int32_t max_episode_length;  /* env.episode_length                                                                       */
+  float* point_goal;           /* [N] _point_goal: read by the reward (previous distance), rewritten by the observation    */
+  const float* cycle_phase;    /* [N] uniform [0,1) numbers: sample_time_interval's draw for a clip that wraps this step   */
 } PhcStepArgs;
 
 /* Sizes implied by a configuration (so callers can allocate): */

@@ -387,6 +387,98 @@ def env_step(tab: MotionTables, cfg: StepConfig, body_state: Tensor, dof_state: 
     return out
 
 
+def env_step_getup(tab: MotionTables, cfg: StepConfig, body_state: Tensor, dof_state: Tensor, dof_force: Tensor,
+                   progress: Tensor, motion_ids: Tensor, start_times: Tensor, start_offsets: Tensor, global_offset: Tensor,
+                   amp_hist: Tensor, point_goal: Tensor, cycle_counter: Tensor, cycle_phase: Tensor, zero_out_far: bool = True,
+                   cycle_motion: bool = True, close_distance: float = 0.25, far_distance: float = 3.0,
+                   max_episode_length: int = 300) -> Dict[str, Tensor]:
+    """The env step of env_im_getup_mcp.yaml (`zero_out_far: True`, `zero_out_far_train: False`, `cycle_motion: True`) -- the
+    configuration HumanoidImMCP trains in:
+      * pre_physics `_update_cycle_count` (humanoid_im.py:1076-1079): `cycle_counter` is the value BEFORE the decrement;
+      * `_compute_reward` with the point-goal mix (:890-905, compute_point_goal_reward :1557-1562);
+      * `_compute_reset` with clip wrap-around (:1120-1146): an env whose motion time passed the clip length gets a new start
+        time (`cycle_phase` = the uniform numbers sample_time_interval draws, motion_lib_base.py:414-423), offset -progress*dt,
+        a global offset that puts the clip's root under the humanoid, cycle_counter 60; pass_time = progress >= max_len - 1;
+      * `_compute_task_obs` overwrites for far references (:783-796) and `_point_goal` update (:792).
+    Returns env_step's dict plus the re-based bookkeeping tensors."""
+    N, J, _ = body_state.shape
+    bp, br, bv, bw = body_state[..., 0:3], body_state[..., 3:7], body_state[..., 7:10], body_state[..., 10:13]
+    dof_pos, dof_vel = dof_state[..., 0], dof_state[..., 1]
+    out: Dict[str, Tensor] = {}
+    cc = torch.clamp_min(cycle_counter - 1, 0)
+    start_times, start_offsets, global_offset = start_times.clone(), start_offsets.clone(), global_offset.clone()
+
+    t_now = progress * cfg.dt + start_times + start_offsets
+    ref = motion_state(tab, motion_ids, t_now, global_offset)
+    im_rew, im_raw = imitation_reward(bp, br, bv, bw, ref["rg_pos"], ref["rb_rot"], ref["body_vel"], ref["body_ang_vel"], cfg.rwd)
+    if zero_out_far:
+        distance = torch.norm(bp[:, 0] - ref["root_pos"], dim=-1)
+        far = distance > 0.25                                                # transition_distance (a literal in the reference)
+        pg = torch.clamp(point_goal - distance, max=1 / 3) * 9
+        raw = torch.zeros(N, 4)
+        raw[:, 0] = pg
+        rew = torch.where(far, pg, pg + im_rew * 0.5)
+        raw = torch.where(far[:, None], raw, raw + im_raw * 0.5)
+    else:
+        rew, raw = im_rew, im_raw
+    if cfg.power_reward:
+        pw = power_reward(dof_force, dof_vel, progress, cfg.power_coef)
+        rew = rew + pw
+        raw = torch.cat((raw, pw[:, None]), dim=-1)
+    out["rew"], out["reward_raw"] = rew, raw
+
+    pass_len = t_now >= tab.lengths[motion_ids]
+    if cycle_motion:
+        pass_time = progress >= max_episode_length - 1
+        if bool(pass_len.any()):
+            w = pass_len
+            start_offsets[w] = -progress[w] * cfg.dt
+            curr_fps = 1 / 30
+            start_times[w] = ((cycle_phase[w] * tab.lengths[motion_ids[w]]) / curr_fps).long() * curr_fps
+            # get_root_pos_smpl (motion_lib_base.py:522-547): root position of the clip at the new start time, no offset
+            i0, i1, bl = frame_blend(start_times[w], tab.lengths[motion_ids[w]], tab.num_frames[motion_ids[w]], tab.dts[motion_ids[w]])
+            f0, f1 = i0 + tab.length_starts[motion_ids[w]], i1 + tab.length_starts[motion_ids[w]]
+            b = bl.view(-1, 1, 1)
+            root = ((1.0 - b) * tab.gts[f0] + b * tab.gts[f1])[:, 0]
+            global_offset[w, :2] = bp[w, 0, :2] - root[:, :2]
+            cc[w] = 60
+            t_now = progress * cfg.dt + start_times + start_offsets
+            ref = motion_state(tab, motion_ids, t_now, global_offset)
+    else:
+        pass_time = pass_len
+    rb = list(range(J)) if cfg.reset_bodies is None else list(cfg.reset_bodies)
+    td = torch.full((J,), cfg.term_dist) if not torch.is_tensor(cfg.term_dist) else cfg.term_dist
+    reset, term = im_reset(progress, bp[:, rb], ref["rg_pos"][:, rb], pass_time, td[rb], cfg.early_term, cfg.no_collision, cfg.use_mean)
+    rec = (~pass_time) & (cc > 0)
+    out["reset"] = torch.where(rec, torch.zeros_like(reset), reset)
+    out["terminate"] = torch.where(rec, torch.zeros_like(term), term)
+
+    t_next = (progress + 1) * cfg.dt + start_times + start_offsets
+    refn = motion_state(tab, motion_ids, t_next, global_offset)
+    rp, rr, rv, rw = refn["rg_pos"].clone(), refn["rb_rot"].clone(), refn["body_vel"].clone(), refn["body_ang_vel"].clone()
+    new_goal = point_goal.clone()
+    if zero_out_far:
+        distance = torch.norm(bp[:, 0] - rp[:, 0], dim=-1)
+        z = distance > close_distance
+        rp[z, 1:], rr[z, 1:] = bp[z, 1:], br[z, 1:]
+        rv[z], rw[z] = bv[z], bw[z]
+        new_goal = distance
+        vz = distance > far_distance
+        rp[vz, 0] = ((rp[vz, 0] - bp[vz, 0]) / distance[vz, None] * far_distance) + bp[vz, 0]
+    so = self_obs(bp, br, bv, bw, cfg.local_root_obs, cfg.root_height_obs, cfg.upright)
+    to = task_obs_v6(bp[:, 0], br[:, 0], bp, br, bv, bw, rp, rr, rv, rw, 1, cfg.upright)
+    out["obs"] = torch.cat((so, to), dim=-1)
+    out["ref_body_pos"], out["ref_body_rot"], out["ref_body_vel"] = refn["rg_pos"], refn["rb_rot"], refn["body_vel"]
+    out["ref_body_ang_vel"] = refn["body_ang_vel"]
+    cur = amp_obs(bp[:, 0], br[:, 0], bv[:, 0], bw[:, 0], dof_pos, dof_vel, bp[:, cfg.key_bodies],
+                  cfg.dof_subset, cfg.local_root_obs, cfg.root_height_obs, cfg.upright)
+    out["amp_obs"] = cur
+    out["amp_obs_buf"] = torch.cat((cur[:, None], amp_hist[:, :-1]), dim=1)
+    out.update(start_times=start_times, start_offsets=start_offsets, global_offset=global_offset, cycle_counter=cc,
+               point_goal=new_goal)
+    return out
+
+
 def amp_obs_demo(tab: MotionTables, cfg: StepConfig, motion_ids: Tensor, times0: Tensor,
                  first_step: int = 0, num_steps: Optional[int] = None) -> Tensor:
     """build_amp_obs_demo (humanoid_amp.py:253-284) / _init_amp_obs_ref (:575-603, first_step=1): AMP

@@ -20,6 +20,8 @@ PHC_FLAG_NO_COLLISION = 1 << 5
 PHC_FLAG_TERM_USE_MEAN = 1 << 6
 PHC_FLAG_OBS_ONLY = 1 << 7
 PHC_FLAG_REWARD_FROM_CACHE = 1 << 8
+PHC_FLAG_ZERO_OUT_FAR = 1 << 9
+PHC_FLAG_CYCLE_MOTION = 1 << 10
 PHC_ACT_NONE, PHC_ACT_RELU, PHC_ACT_SILU, PHC_ACT_SILU_BWD = 0, 1, 2, 3
 PHC_MAX_KEY_BODIES = 8
 PHC_MAX_BODIES = 32
@@ -62,6 +64,8 @@ class PhcStepArgs(C.Structure):
         ("amp_out", _p), ("amp_hist_in", _p), ("amp_out_stride", C.c_int64), ("amp_steps", C.c_int32),
         ("ref_body_pos", _p), ("ref_body_rot", _p), ("ref_body_vel", _p), ("ref_body_ang_vel", _p),
         ("ref_cache", _p),
+        ("close_distance", C.c_float), ("far_distance", C.c_float), ("max_episode_length", C.c_int32), ("point_goal", _p),
+        ("cycle_phase", _p),
     ]
 
 

@@ -76,7 +76,9 @@ __device__ __forceinline__ void st6(float* d, TanNorm t) { st3(d, t.t); st3(d + 
 
 // JT > 0: the body count is a compile-time constant (24 = SMPL, 20 = H1): record strides, segment offsets of the observation
 // row and the shared-memory carve-up fold into immediates; JT == 0 is the generic runtime-J build.
-template <int T_MAX, int JT>
+// GETUP: the env_im_getup_mcp.yaml extras (PHC_FLAG_ZERO_OUT_FAR / PHC_FLAG_CYCLE_MOTION, T == 1, spherical joints).  A template
+// parameter so the plain instantiations keep exactly the instruction stream they had without it.
+template <int T_MAX, int JT, bool GETUP = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm)
 env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const int self_dim, const int amp_dim,
                 const bool alias_obs, const bool state_bulk_ok) {
@@ -153,6 +155,42 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     m_nf = a.lib.motion_num_frames[mid]; m_start = a.lib.length_starts[mid];
   }
 
+  // Motion parameters of the OBSERVATION time: the step's own, unless the clip wraps this step (cycle_motion) -- then the
+  // reward still reads the old clip position while the observation (and every later step) follows the re-based one.
+  float t_start_o = t_start, t_off_o = t_off;
+  V3 goff_o = goff;
+  const bool zof = GETUP && (a.flags & PHC_FLAG_ZERO_OUT_FAR);
+  const bool cyc = GETUP && (a.flags & PHC_FLAG_CYCLE_MOTION) && !obs_only;
+  int cc = 0;                                        // _cycle_counter as the reset test sees it
+  if (GETUP) {
+    if (a.cycle_counter) cc = a.cycle_counter[env];
+    if (cyc) {
+      cc = cc - 1 < 0 ? 0 : cc - 1;                  // _update_cycle_count of pre_physics_step (humanoid_im.py:1076-1079)
+      const float t_now0 = PHC_ADD(PHC_ADD(PHC_MUL((float)progress, a.dt), t_start), t_off);
+      if (t_now0 >= m_len) {                         // pass_time_motion_len (humanoid_im.py:1121-1146)
+        t_off_o = -PHC_MUL((float)progress, a.dt);   // progress * dt cancels: the clip restarts at the sampled time
+        const float grid = 1.0f / 30.0f;             // sample_time_interval (motion_lib_base.py:414-423)
+        const long long k = (long long)((a.cycle_phase[env] * m_len) / grid);
+        t_start_o = (float)k * grid;
+        // get_root_pos_smpl (motion_lib_base.py:522-547): the clip's root at the new start time, no offset
+        const Bracket32 b = frame_bracket32(t_start_o, m_len, (int)m_nf, m_dt);
+        const float* r0 = a.lib.frames_body + (size_t)(m_start + b.i0) * BS;
+        const float* r1 = a.lib.frames_body + (size_t)(m_start + b.i1) * BS;
+        const float omb = 1.0f - b.blend;
+        goff_o.x = g_state[0] - lerp1(r0[0], r1[0], omb, b.blend);     // _humanoid_root_states[:, :2] = body 0 of the state block
+        goff_o.y = g_state[1] - lerp1(r0[1], r1[1], omb, b.blend);
+        cc = 60;
+        if (lane == 0) {
+          a.start_times[env] = t_start_o;
+          a.start_offsets[env] = t_off_o;
+          a.global_offset[3 * env + 0] = goff_o.x;
+          a.global_offset[3 * env + 1] = goff_o.y;
+        }
+      }
+      if (lane == 0 && a.cycle_counter) a.cycle_counter[env] = cc;
+    }
+  }
+
   // reward / reset use the CURRENT motion time (humanoid_im.py:879), observations the NEXT one (:752)
   float bl_r = 0.f;
   float bl_o[T_MAX];
@@ -180,7 +218,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
         // ((progress + 1) * dt [+ t * traj_dt] + start + offset), humanoid_im.py:744-752
         float tn = PHC_MUL((float)(progress + 1), a.dt);
         if (T > 1) tn = PHC_ADD(tn, PHC_MUL((float)t, a.traj_dt));
-        tn = PHC_ADD(PHC_ADD(tn, t_start), t_off);
+        tn = PHC_ADD(PHC_ADD(tn, t_start_o), t_off_o);
         const Bracket32 b = frame_bracket32(tn, m_len, (int)m_nf, m_dt);
         bl_o[t] = b.blend;
         rows_o[2 * t] = m_start + b.i0;
@@ -317,7 +355,15 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
       const bool has_power = a.flags & PHC_FLAG_POWER_REWARD;
       const int rw = has_power ? 5 : 4;
       float* raw = a.reward_raw + (size_t)env * rw;
-      raw[0] = r_pos; raw[1] = r_rot; raw[2] = r_vel; raw[3] = r_ang;
+      float w0 = r_pos, w1 = r_rot, w2 = r_vel, w3 = r_ang;
+      if (zof) {
+        // point-goal mix (humanoid_im.py:890-905): lane 0 tracks the root, `dist` is |root_pos - ref_root_pos|.  Everywhere:
+        // clamp(previous distance - distance, max = 1/3) * 9; within the 0.25 m transition distance half the imitation reward on top
+        const float pg = fminf(a.point_goal[env] - dist, 1.0f / 3.0f) * 9.0f;
+        if (dist > 0.25f) { rew = pg; w0 = pg; w1 = 0.0f; w2 = 0.0f; w3 = 0.0f; }
+        else { rew = pg + rew * 0.5f; w0 = pg + r_pos * 0.5f; w1 = 0.0f + r_rot * 0.5f; w2 = 0.0f + r_vel * 0.5f; w3 = 0.0f + r_ang * 0.5f; }
+      }
+      raw[0] = w0; raw[1] = w1; raw[2] = w2; raw[3] = w3;
       if (has_power) {
         float pr = -a.power_coef * power;
         if (progress <= 3) pr = 0.0f;
@@ -327,7 +373,8 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
       a.rew[env] = rew;
       // compute_humanoid_im_reset + the is_recovery override
       const float t_now = PHC_ADD(PHC_ADD(PHC_MUL((float)progress, a.dt), t_start), t_off);
-      const bool pass_time = t_now >= m_len;
+      bool pass_time = t_now >= m_len;
+      if (cyc) pass_time = progress >= (int64_t)a.max_episode_length - 1;      // pass_time_max (humanoid_im.py:1120-1124)
       int64_t terminated = 0;
       if (a.flags & PHC_FLAG_EARLY_TERM) {
         bool f = fallen && (progress > 1);
@@ -335,7 +382,8 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
         terminated = f ? 1 : 0;
       }
       int64_t reset = pass_time ? 1 : terminated;
-      if (a.cycle_counter && !pass_time && a.cycle_counter[env] > 0) { reset = 0; terminated = 0; }
+      if (GETUP) { if (!pass_time && cc > 0) { reset = 0; terminated = 0; } }
+      else if (a.cycle_counter && !pass_time && a.cycle_counter[env] > 0) { reset = 0; terminated = 0; }
       a.reset[env] = reset;
       a.terminate[env] = terminated;
     }
@@ -395,23 +443,45 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   mbar_wait(bar_o, 0);
   float* const g_cache = a.ref_cache ? a.ref_cache + (size_t)env * BS : nullptr;
   const bool cache_bulk = g_cache && T_MAX == 1;     // single sample: the blended pose is staged over its own frame slot
+  V3 rroot = v3(0.f, 0.f, 0.f);
+  if (zof) {
+    // zero_out_far needs |root_pos - reference root| in every lane: each lane blends the reference ROOT position itself (the
+    // same shared-memory words for all lanes: a broadcast read, bit-identical to lane 0's blend_body) ...
+    const float* s0 = po0[0];
+    const float* s1 = po1[0];
+    rroot = lerp3(v3(s0[0], s0[1], s0[2]), v3(s1[0], s1[1], s1[2]), 1.0f - bl_o[0], bl_o[0]) + goff_o;
+    __syncwarp();      // ... before lane 0 may overwrite record 0 of the slot with the cached pose
+  }
 #pragma unroll
   for (int t = 0; t < T_MAX; ++t) {
     if (t < T && (has_body || (has_ext && t == 0 && g_cache))) {
-      const BodyRec ref = blend_body(po0[t] + jr * kBodyRec, po1[t] + jr * kBodyRec, bl_o[t], goff);
+      const BodyRec ref = blend_body(po0[t] + jr * kBodyRec, po1[t] + jr * kBodyRec, bl_o[t], goff_o);
       if (t == 0 && g_cache) {
         // lane j has consumed records j of both frames: slot 0 of the bracket becomes the row of the pose cache
         float* c = (cache_bulk ? s_oslots : g_cache) + jr * kBodyRec;
         st3(c, ref.p); c[3] = ref.q.x; c[4] = ref.q.y; c[5] = ref.q.z; c[6] = ref.q.w; st3(c + 7, ref.v); st3(c + 10, ref.w);
       }
       if (!has_body) continue;         // extend bodies: reward only, no observation columns
+      BodyRec ro = ref;                // what the observation sees as reference (the cache / ref_* buffers keep `ref`)
+      if (zof && t == 0) {             // humanoid_im.py:783-796
+        const V3 dr = root_p - rroot;
+        const float dist = sqrtf(dr.x * dr.x + dr.y * dr.y + dr.z * dr.z);
+        if (dist > a.close_distance) {       // far from the reference: it collapses onto the simulated pose (root position excepted)
+          if (j > 0) { ro.p = sim.p; ro.q = sim.q; }
+          ro.v = sim.v; ro.w = sim.w;
+        }
+        if (dist > a.far_distance && j == 0)   // very far: the root target becomes a direction of length far_distance
+          ro.p = v3((ref.p.x - sim.p.x) / dist * a.far_distance + sim.p.x, (ref.p.y - sim.p.y) / dist * a.far_distance + sim.p.y,
+                    (ref.p.z - sim.p.z) / dist * a.far_distance + sim.p.z);
+        if (lane == 0) a.point_goal[env] = dist;
+      }
       float* tb = s_obs + self_dim + t * 24 * J;
-      st3(tb + 3 * j, qrot_z(hinv, ref.p - sim.p));
-      st6(tb + 3 * J + 6 * j, tan_norm(qmul(qmul(hinv, qmul(ref.q, qconj(sim.q))), hq)));
-      st3(tb + 9 * J + 3 * j, qrot_z(hinv, ref.v - sim.v));
-      st3(tb + 12 * J + 3 * j, qrot_z(hinv, ref.w - sim.w));
-      st3(tb + 15 * J + 3 * j, qrot_z(hinv, ref.p - root_p));
-      st6(tb + 18 * J + 6 * j, tan_norm(qmul(hinv, ref.q)));
+      st3(tb + 3 * j, qrot_z(hinv, ro.p - sim.p));
+      st6(tb + 3 * J + 6 * j, tan_norm(qmul(qmul(hinv, qmul(ro.q, qconj(sim.q))), hq)));
+      st3(tb + 9 * J + 3 * j, qrot_z(hinv, ro.v - sim.v));
+      st3(tb + 12 * J + 3 * j, qrot_z(hinv, ro.w - sim.w));
+      st3(tb + 15 * J + 3 * j, qrot_z(hinv, ro.p - root_p));
+      st6(tb + 18 * J + 6 * j, tan_norm(qmul(hinv, ro.q)));
       if (t == 0) {     // side buffers of _compute_task_obs(save_buffer=True)
         const size_t bj = (size_t)env * J + j;
         if (a.ref_body_pos) st3(a.ref_body_pos + 3 * bj, ref.p);
@@ -499,6 +569,14 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
   for (int e2 = 0; e2 < E; ++e2)
     if (a->ext_parent[e2] < 0 || a->ext_parent[e2] >= J) { phc_set_error("phc_env_step: ext_parent out of range"); return PHC_ERR_INVALID_ARG; }
   if (T > 4) { phc_set_error("phc_env_step: time_steps > 4 not supported"); return PHC_ERR_UNSUPPORTED; }
+  const bool getup = (a->flags & (PHC_FLAG_ZERO_OUT_FAR | PHC_FLAG_CYCLE_MOTION)) != 0;
+  if (getup) {
+    if (T != 1 || E != 0 || DR != 0) { phc_set_error("phc_env_step: zero_out_far / cycle_motion are built for time_steps 1 and spherical-joint humanoids"); return PHC_ERR_UNSUPPORTED; }
+    if ((a->flags & PHC_FLAG_ZERO_OUT_FAR) && (!a->point_goal || !(a->far_distance > 0.0f))) { phc_set_error("phc_env_step: zero_out_far needs point_goal and far_distance > 0"); return PHC_ERR_INVALID_ARG; }
+    if ((a->flags & PHC_FLAG_CYCLE_MOTION) && (!a->cycle_phase || !a->cycle_counter || a->max_episode_length < 1)) {
+      phc_set_error("phc_env_step: cycle_motion needs cycle_phase, cycle_counter and max_episode_length >= 1"); return PHC_ERR_INVALID_ARG;
+    }
+  }
   if ((a->flags & PHC_FLAG_POWER_REWARD) && !a->dof_force) { phc_set_error("phc_env_step: power reward needs dof_force"); return PHC_ERR_INVALID_ARG; }
   if (a->num_key_bodies < 0 || a->num_key_bodies > PHC_MAX_KEY_BODIES || a->num_amp_joints < 0 || a->num_amp_joints > PHC_MAX_AMP_JOINTS) {
     phc_set_error("phc_env_step: bad key body / amp joint lists"); return PHC_ERR_INVALID_ARG;
@@ -529,21 +607,23 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
   const int grid = (a->num_envs + kWarpsPerCta - 1) / kWarpsPerCta;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-#define PHC_LAUNCH_STEP(TM, JJ)                                                                                  \
-  do {                                                                                                           \
-    static size_t smem_limit = 48 * 1024;     /* default opt-out limit; the attribute is only ever RAISED */      \
-    if (smem > smem_limit) {                                                                                     \
-      e = cudaFuncSetAttribute(env_step_kernel<TM, JJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      if (e != cudaSuccess) return phc_check_cuda(e, "cudaFuncSetAttribute(env_step_kernel)");                   \
-      smem_limit = smem;                                                                                         \
-    }                                                                                                            \
-    env_step_kernel<TM, JJ><<<grid, kWarpsPerCta * 32, smem, st>>>(*a, obs_dim, self_dim, amp_dim, alias_obs,    \
-                                                                    state_bulk_ok);                              \
-    phc_count_launches(1);                                                                                       \
+#define PHC_LAUNCH_STEP(TM, JJ, GU)                                                                                  \
+  do {                                                                                                               \
+    static size_t smem_limit = 48 * 1024;     /* default opt-out limit; the attribute is only ever RAISED */          \
+    if (smem > smem_limit) {                                                                                         \
+      e = cudaFuncSetAttribute(env_step_kernel<TM, JJ, GU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return phc_check_cuda(e, "cudaFuncSetAttribute(env_step_kernel)");                       \
+      smem_limit = smem;                                                                                             \
+    }                                                                                                                \
+    env_step_kernel<TM, JJ, GU><<<grid, kWarpsPerCta * 32, smem, st>>>(*a, obs_dim, self_dim, amp_dim, alias_obs,    \
+                                                                        state_bulk_ok);                              \
+    phc_count_launches(1);                                                                                           \
   } while (0)
-  if (T == 1 && J == 24 && E == 0 && DR == 0) PHC_LAUNCH_STEP(1, 24);          // SMPL
-  else if (T == 1) PHC_LAUNCH_STEP(1, 0);                                       // H1 (J = 20, E = 3, 19 hinge dofs) and others
-  else PHC_LAUNCH_STEP(4, 0);
+  if (getup && J == 24) PHC_LAUNCH_STEP(1, 24, true);                           // env_im_getup_mcp.yaml
+  else if (getup) PHC_LAUNCH_STEP(1, 0, true);
+  else if (T == 1 && J == 24 && E == 0 && DR == 0) PHC_LAUNCH_STEP(1, 24, false);   // SMPL
+  else if (T == 1) PHC_LAUNCH_STEP(1, 0, false);                                // H1 (J = 20, E = 3, 19 hinge dofs) and others
+  else PHC_LAUNCH_STEP(4, 0, false);
 #undef PHC_LAUNCH_STEP
   return phc_check_cuda(cudaGetLastError(), "env_step_kernel launch");
 }

@@ -82,9 +82,18 @@ class HumanoidIm:
         self.fitting = False
         self.has_task = True
         self.viewer = None
+        # env_im_getup_mcp.yaml (humanoid.py:294-330): clip wrap-around and the far-reference handling, both inside the fused launch
         self.cycle_motion = bool(env.get("cycle_motion", False))
-        if self.cycle_motion:
-            raise NotImplementedError("cycle_motion re-basing (humanoid_im.py:1123-1146) is not on the fused path yet")
+        self.cycle_motion_xp = bool(env.get("cycle_motion_xp", False))
+        self.zero_out_far = bool(env.get("zero_out_far", False))
+        self.zero_out_far_train = bool(env.get("zero_out_far_train", True)) and self.zero_out_far
+        self.close_distance = float(env.get("close_distance", 0.25))
+        self.far_distance = float(env.get("far_distance", 3))
+        self._zero_out_far_steps = int(env.get("zero_out_far_steps", 90))
+        self.max_episode_length = int(env.get("episode_length", 300))
+        if self.cycle_motion_xp or self.zero_out_far_train:
+            raise NotImplementedError("cycle_motion_xp / zero_out_far_train (random re-placement, humanoid_im.py:966-980, :1131-1140) "
+                                      "are not on the fused path; the shipped getup config has both off")
 
         # ---- motion library (tables as MotionLibBase keeps them) -> packed device format -----------------------
         m = cfg["motion_data"]
@@ -121,7 +130,8 @@ class HumanoidIm:
             power_coef=self.power_coefficient, early_term=bool(env.get("enableEarlyTermination", True)),
             key_bodies=key_bodies, reset_bodies=reset_bodies, term_dist=float(env.get("terminationDistance", 0.25)),
             dof_subset=dof_subset, amp_steps=self._num_amp_obs_steps, ext_parents=self.extend_body_parent_ids,
-            ext_pos=self.extend_body_pos_in_parent)
+            ext_pos=self.extend_body_pos_in_parent, zero_out_far=self.zero_out_far, close_distance=self.close_distance,
+            far_distance=self.far_distance, cycle_motion=self.cycle_motion, max_episode_length=self.max_episode_length)
         self._key_body_ids, self._reset_bodies_id, self.dof_subset = key_bodies, reset_bodies, dof_subset
 
         # ---- simulator backend and its tensors (Humanoid._setup_tensors) ---------------------------------------
@@ -147,12 +157,15 @@ class HumanoidIm:
         self._global_offset = torch.zeros(N, 3, device=dev)
         self._cycle_counter = torch.zeros(N, dtype=torch.int32, device=dev)
         self._reset_mask = torch.zeros(N, dtype=i64, device=dev)
+        self._point_goal = torch.zeros(N, device=dev)                 # humanoid_im.py:95
+        self._cycle_phase = torch.zeros(N, device=dev)                # uniform numbers for clips that wrap this step
         self.extras: Dict[str, torch.Tensor] = {}
 
         common = dict(cfg=self.step_cfg, mlib=self._motion_lib, body_state=self._rigid_body_state_reshaped,
                       dof_state=self._dof_state, dof_force=self.dof_force_tensor, progress=self.progress_buf,
                       motion_ids=self._sampled_motion_ids, start_times=self._motion_start_times,
-                      start_offsets=self._motion_start_times_offset, global_offset=self._global_offset)
+                      start_offsets=self._motion_start_times_offset, global_offset=self._global_offset,
+                      point_goal=self._point_goal, cycle_phase=self._cycle_phase)
         # AMP history: a RING [N, S, A] (one 784-byte slot written per step) instead of the reference's per-step shift of
         # the whole window (humanoid_amp.py:662-670); the newest-first window is exported on demand (`_amp_obs_buf`,
         # `export_amp_obs`).  amp_window_shift=True in cfg restores the in-kernel reference-style shift.
@@ -181,7 +194,7 @@ class HumanoidIm:
         self.self_obs_buf = self.obs_buf[:, :p.self_dim]
         # observation-only re-computation for just-reset envs (_compute_observations(env_ids))
         self._plan_reset_obs = ops.EnvStepPlan(obs=self.obs_buf, only_where=self._reset_mask, obs_only=True, with_amp=False,
-                                               ref_cache=self._ref_cache, **common)
+                                               ref_cache=self._ref_cache, cycle_counter=self._cycle_counter, **common)
         self._lib = _lib.load()
         self._kb = (C.c_int32 * len(key_bodies))(*[int(b) for b in key_bodies])
         self.actions = None
@@ -240,6 +253,8 @@ class HumanoidIm:
         self.progress_buf += 1
         if self._amp_use_ring:
             self._plan.advance_ring()
+        if self.cycle_motion:
+            self._cycle_phase.uniform_()        # what sample_time_interval would draw for the clips that wrap (motion_lib_base.py:415)
         self._plan.run()
         self.extras["terminate"] = self._terminate_buf
         self.extras["reward_raw"] = self.reward_raw

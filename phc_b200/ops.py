@@ -236,13 +236,20 @@ class EnvStepConfig:
     # "extend" body; must match the E extra records of the packed motion library
     ext_parents: Sequence[int] = ()
     ext_pos: Sequence[Sequence[float]] = ()
+    # env_im_getup_mcp.yaml (the configuration HumanoidImMCP trains in)
+    zero_out_far: bool = False         # env.zero_out_far (with zero_out_far_train False)
+    close_distance: float = 0.25       # env.close_distance
+    far_distance: float = 3.0          # env.far_distance
+    cycle_motion: bool = False         # env.cycle_motion
+    max_episode_length: int = 300      # env.episode_length
 
     def flags(self) -> int:
         f = 0
         for on, bit in ((self.upright, PHC_FLAG_UPRIGHT), (self.local_root_obs, PHC_FLAG_LOCAL_ROOT_OBS),
                         (self.root_height_obs, PHC_FLAG_ROOT_HEIGHT_OBS), (self.power_reward, PHC_FLAG_POWER_REWARD),
                         (self.early_term, PHC_FLAG_EARLY_TERM), (self.no_collision, PHC_FLAG_NO_COLLISION),
-                        (self.term_use_mean, PHC_FLAG_TERM_USE_MEAN)):
+                        (self.term_use_mean, PHC_FLAG_TERM_USE_MEAN), (self.zero_out_far, _lib.PHC_FLAG_ZERO_OUT_FAR),
+                        (self.cycle_motion, _lib.PHC_FLAG_CYCLE_MOTION)):
             if on:
                 f |= bit
         return f
@@ -269,7 +276,8 @@ class EnvStepPlan:
                  amp_obs_buf: Optional[torch.Tensor] = None, amp_hist_in: Optional[torch.Tensor] = None,
                  amp_shift: bool = True, with_amp: bool = True, with_ref_buffers: bool = False,
                  only_where: Optional[torch.Tensor] = None, obs_only: bool = False, amp_ring: bool = False,
-                 ref_cache: Optional[torch.Tensor] = None, reward_from_cache: bool = False):
+                 ref_cache: Optional[torch.Tensor] = None, reward_from_cache: bool = False,
+                 point_goal: Optional[torch.Tensor] = None, cycle_phase: Optional[torch.Tensor] = None):
         """ref_cache: [N, body_stride] pose cache (PhcStepArgs.ref_cache): every run() stores the reference pose interpolated
         for the first observation sample; reward_from_cache=True makes run() take the reward-time reference pose from it
         (valid for HumanoidIm's step / reset sequence, see include/phc_b200.h).
@@ -363,6 +371,16 @@ class EnvStepPlan:
         a.env_motion = self._env_motion.data_ptr()
         a.start_times, a.start_offsets, a.global_offset = k["start_times"].data_ptr(), k["start_offsets"].data_ptr(), k["global_offset"].data_ptr()
         a.cycle_counter = _ptr(k["cycle_counter"])
+        # zero_out_far / cycle_motion state: _point_goal [N] (in/out) and the per-step uniform numbers for wrapping clips
+        if cfg.zero_out_far:
+            k["point_goal"] = _req(point_goal, f32, "point_goal", dev)
+            assert k["point_goal"].shape == (N,)
+            a.point_goal = k["point_goal"].data_ptr()
+        if cfg.cycle_motion:
+            k["cycle_phase"] = _req(cycle_phase, f32, "cycle_phase", dev)
+            assert k["cycle_phase"].shape == (N,) and cycle_counter is not None
+            a.cycle_phase = k["cycle_phase"].data_ptr()
+        a.close_distance, a.far_distance, a.max_episode_length = cfg.close_distance, cfg.far_distance, int(cfg.max_episode_length)
         k["only_where"] = None if only_where is None else _req(only_where, i64, "only_where", dev)
         a.only_where = _ptr(k["only_where"])
         a.lib = mlib.c

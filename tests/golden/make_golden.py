@@ -483,6 +483,57 @@ def gen_h1():
 
 
 # ------------------------------------------------------------------------------------------------
+def gen_getup():
+    """env_im_getup_mcp.yaml (the configuration HumanoidImMCP trains in): zero_out_far + cycle_motion, zero_out_far_train False.
+    The real HumanoidIm._compute_reward (:873-948), _compute_reset (:1117-1190 incl. the clip wrap-around :1123-1146) and
+    _compute_observations (zero_out_far overwrites :783-796).  The uniform numbers sample_time_interval draws for the wrapping
+    envs are reproduced by re-seeding torch's generator and stored as the `cycle_phase` input."""
+    m = syn.make_motions(48, seed=4, min_frames=16, max_frames=40)
+    N = 48
+    st = syn.make_env_state(m, N, seed=2, max_progress=20, with_offset=True)
+    g = torch.Generator().manual_seed(9)
+    # the simulated state was generated around reference + global_offset: moving the offset moves the reference away
+    st.global_offset[0:10, :2] += torch.randn(10, 2, generator=g) * 4.0        # far: beyond far_distance for most
+    st.global_offset[10:20, :2] += torch.randn(10, 2, generator=g) * 0.8       # between close and far
+    st.global_offset[20:24, :2] += torch.randn(4, 2, generator=g) * 0.15       # around the 0.25 m transition
+    cc_in = torch.tensor([0, 0, 0, 1, 2, 7], dtype=torch.int)[torch.randint(0, 6, (N,), generator=g)]
+    point_goal = torch.rand(N, generator=g) * 6
+    env = build_ref_env(m, st)
+    env.zero_out_far, env.zero_out_far_train, env.cycle_motion, env.cycle_motion_xp = True, False, True, False
+    env.close_distance, env.far_distance = 0.25, 3
+    env.max_episode_length = 15
+    env._cycle_counter = torch.clamp_min(cc_in - 1, 0)             # pre_physics_step ran _update_cycle_count (:1076-1079)
+    env._point_goal = point_goal.clone()
+    env._humanoid_root_states = env._rigid_body_state_reshaped[:, 0, :]
+    env._motion_lib._device = torch.device("cpu")
+    # the wrapping envs, as _compute_reset will find them, and the numbers it will draw for them
+    t_now = st.progress * env.dt + st.start_times + st.start_offsets
+    wrap = t_now >= m.lengths[st.motion_ids]
+    torch.manual_seed(77)
+    phase = torch.zeros(N)
+    phase[wrap] = torch.rand(int(wrap.sum()))
+    env._compute_reward(None)
+    torch.manual_seed(77)
+    env._compute_reset()
+    env._compute_observations()
+    S = env._num_amp_obs_steps
+    env._hist_amp_obs_buf[:] = env._amp_obs_buf[:, 0:(S - 1)].clone()
+    env._compute_amp_observations()
+    d = dict(in_cycle_counter=cc_in, in_point_goal=point_goal, in_cycle_phase=phase, in_wrap=wrap,
+             out_obs=env.obs_buf, out_rew=env.rew_buf, out_reward_raw=env.reward_raw, out_reset=env.reset_buf,
+             out_terminate=env._terminate_buf, out_amp_obs_buf=env._amp_obs_buf, out_ref_body_pos=env.ref_body_pos,
+             out_ref_body_rot=env.ref_body_rot, out_ref_body_vel=env.ref_body_vel, out_start_times=env._motion_start_times,
+             out_start_offsets=env._motion_start_times_offset, out_global_offset=env._global_offset,
+             out_cycle_counter=env._cycle_counter, out_point_goal=env._point_goal)
+    for f in st.__dataclass_fields__:
+        d[f"in_{f}"] = getattr(st, f)
+    d.update(motion_tables_dict(m))
+    print("getup golden: wrapping envs", int(wrap.sum()), "far (reward)", int((d["out_reward_raw"][:, 1] == 0).sum()),
+          "resets", int(env.reset_buf.sum()))
+    save("getup.npz", d)
+
+
+# ------------------------------------------------------------------------------------------------
 def gen_load():
     """MotionLibSMPL.load_motion_with_skeleton (phc/utils/motion_lib_smpl.py:101-180) executed UNMODIFIED on synthetic
     clips in the on-disk format ({pose_quat_global [T,J,4], root_trans_offset [T,3], pose_aa, fps}): heading randomisation

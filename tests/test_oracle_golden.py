@@ -255,3 +255,26 @@ def test_motion_loader_filter_taps_are_scipys():
     from oracle import motion_load_oracle as ML
     x = np.random.default_rng(0).standard_normal((23, 3, 2))
     np.testing.assert_allclose(ML.filter_time(x), gaussian_filter1d(x, 2, axis=0, mode="nearest"), rtol=1e-13, atol=1e-14)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# env_im_getup_mcp.yaml: zero_out_far + cycle_motion (the configuration HumanoidImMCP trains in)
+# ----------------------------------------------------------------------------------------------------------------
+def getup_oracle_step(g):
+    st = {k[3:]: v for k, v in g.items() if k.startswith("in_")}
+    return O.env_step_getup(tables_from(g), smpl_step_config(), st["body_state"], st["dof_state"], st["dof_force"], st["progress"],
+                            st["motion_ids"], st["start_times"], st["start_offsets"], st["global_offset"], st["amp_hist"],
+                            st["point_goal"], st["cycle_counter"], st["cycle_phase"], max_episode_length=15)
+
+
+def test_env_step_getup_zero_out_far_cycle_motion():
+    g = load("getup.npz")
+    out = getup_oracle_step(g)
+    assert int(g["in_wrap"].sum()) >= 8 and 8 <= int((g["out_reward_raw"][:, 1] == 0).sum()) <= 40      # both branches exercised
+    for k in ("start_times", "start_offsets", "global_offset", "point_goal", "rew", "reward_raw", "ref_body_pos", "ref_body_rot",
+              "ref_body_vel", "amp_obs_buf"):
+        close(out[k], g["out_" + k], what=f"getup {k}")
+    close(out["obs"], g["out_obs"], atol=2e-6, what="getup obs")
+    for k in ("reset", "terminate"):
+        close(out[k], g["out_" + k], what=f"getup {k}")
+    close(out["cycle_counter"].long(), g["out_cycle_counter"].long(), what="getup cycle_counter")
