@@ -20,8 +20,11 @@
 
 namespace phc {
 
-constexpr int kWarpsPerCta = 4;
-constexpr int kMinCtasPerSm = 7;   // 28 envs resident per SM: 4096 envs = one wave on 148 SMs
+#ifndef PHC_EXP_WARPS            // experiment knob (tools/ab_env.sh): warps (= envs) per CTA
+#define PHC_EXP_WARPS 4
+#endif
+constexpr int kWarpsPerCta = PHC_EXP_WARPS;
+constexpr int kMinCtasPerSm = 28 / PHC_EXP_WARPS;   // 28 envs resident per SM: 4096 envs = one wave on 148 SMs
 constexpr int kBodyRec = 13;
 
 struct StepLayout {      // per-warp shared-memory carve-up, in floats (all multiples of 4 -> 16-byte aligned)
@@ -206,8 +209,14 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   // (Measured: issuing the observation-bracket copies here, before phase A, beats issuing them after phase A -- 19.5 vs
   // 20.5 us at 4096 envs: the self observation alone is too short to cover their DRAM latency.)
   auto issue_frames = [&]() {
-    const float t_now = PHC_ADD(PHC_ADD(PHC_MUL((float)progress, a.dt), t_start), t_off);   // motion times: never contracted
-    const Bracket32 br_r = frame_bracket32(t_now, m_len, (int)m_nf, m_dt);
+    // the reward bracket is only needed when the reward pose is interpolated here (no pose cache, not the obs-only launch)
+    const bool need_r = !from_cache && !obs_only;
+    Bracket32 br_r;
+    br_r.i0 = 0; br_r.i1 = 0; br_r.blend = 0.f;
+    if (need_r) {
+      const float t_now = PHC_ADD(PHC_ADD(PHC_MUL((float)progress, a.dt), t_start), t_off);   // motion times: never contracted
+      br_r = frame_bracket32(t_now, m_len, (int)m_nf, m_dt);
+    }
     bl_r = br_r.blend;
     uint32_t tx_o = 0, tx_r = 0;
     int64_t rows_o[2 * T_MAX];
@@ -239,7 +248,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
       }
     }
     const int64_t row_r0 = m_start + br_r.i0, row_r1 = m_start + br_r.i1;
-    bool fresh_r0 = !from_cache && !obs_only, fresh_r1 = fresh_r0;
+    bool fresh_r0 = need_r, fresh_r1 = fresh_r0;
     if (fresh_r0) {
 #pragma unroll
       for (int p = 0; p < 2 * T_MAX; ++p) {
