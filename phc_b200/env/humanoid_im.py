@@ -272,6 +272,27 @@ class HumanoidIm:
         self._plan_reset_obs.run()
         return self.obs_buf
 
+    def _compute_humanoid_obs(self, env_ids=None):
+        """Humanoid._compute_humanoid_obs (humanoid.py:1441-1477): the self observation of the selected envs.  Produced by the
+        same observation-only launch as the task observation; returns the `self_obs_buf` rows."""
+        self._compute_observations(env_ids)
+        return self.self_obs_buf if env_ids is None else self.self_obs_buf[self._reset_mask.bool()]
+
+    def _compute_task_obs(self, env_ids=None, save_buffer=True):
+        """HumanoidIm._compute_task_obs (humanoid_im.py:728-871): task observation (v6) of the selected envs; the ref_body_*
+        side buffers are views of the pose cache the launch refreshes (save_buffer is therefore always honoured)."""
+        self._compute_observations(env_ids)
+        t = self.obs_buf[:, self._plan.self_dim:]
+        return t if env_ids is None else t[self._reset_mask.bool()]
+
+    def _compute_amp_observations(self, env_ids=None):
+        """HumanoidAMP._compute_amp_observations (humanoid_amp.py:672-707).  The step launch writes the current AMP vector
+        itself; outside a step this re-runs it for the current simulator state (all envs, as the reference's env_ids=None)."""
+        if env_ids is not None:
+            raise NotImplementedError("per-env AMP recomputation outside the fused step: reset paths use phc_amp_obs_demo")
+        self._plan.run()
+        return self._amp_obs_buf[:, 0]
+
     # ---- reset --------------------------------------------------------------------------------------------------
     def _set_mask(self, env_ids) -> None:
         m = self._reset_mask

@@ -612,6 +612,19 @@ class AMPAgent:
                     disc_agent_acc=s[8] / (2 * Bd), disc_demo_acc=s[9] / Bd, disc_grad_penalty=s[10] / Bd,
                     disc_logit_loss=s[11])
 
+    def _disc_loss(self, disc_agent_logit=None, disc_demo_logit=None, obs_demo=None) -> Dict[str, float]:
+        """AMPAgent._disc_loss (amp_agent.py:732-789).  The loss and its gradient (incl. the gradient penalty) are produced
+        inside calc_gradients by phc_disc_logit_grad + the GEMM chain; this returns the reference's info dict for the LAST
+        minibatch from the statistics those kernels accumulated (arguments are accepted for signature parity and ignored)."""
+        r = self.train_result_dict()
+        bce = 0.5 * (r["disc_loss_agent"] + r["disc_loss_demo"])
+        wd = 0.0
+        if self._disc_weight_decay != 0:
+            wd = self._disc_weight_decay * float(sum((self.model.weight(l)[:, :l.in_dim] ** 2).sum() for l in self.model.disc.layers))
+        total = bce + self._disc_logit_reg * r["disc_logit_loss"] + self._disc_grad_penalty * r["disc_grad_penalty"] + wd
+        return dict(disc_loss=total, disc_grad_penalty=r["disc_grad_penalty"], disc_logit_loss=r["disc_logit_loss"],
+                    disc_agent_acc=r["disc_agent_acc"], disc_demo_acc=r["disc_demo_acc"])
+
     def pre_epoch(self, epoch_num: int) -> None:
         if self.normalize_input:
             self.running_mean_std_temp = self.running_mean_std.frozen_copy()   # amp_agent.py:527-528
