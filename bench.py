@@ -40,6 +40,14 @@ ALGO_BYTES_PER_ENV_STEP = 9384          # core algorithm
 METRIC = "env-steps/sec (fused obs+reward+PPO) at 4096 envs/GPU"
 
 
+_T0 = time.perf_counter()
+
+
+def note(msg: str) -> None:
+    """Progress line on stderr (stdout carries exactly one JSON line)."""
+    print(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -302,11 +310,14 @@ def main():
         torch.distributed.barrier()
 
     sampler = ClockSampler(local)
+    note("building agent (device-resident simulator snapshots)")
     agent, task = build_agent(args.num_envs, device, rank, world, host_bank=False)
+    note("agent built; timed epochs")
     if rank == 0:
         sampler.start()
     sec_per_step, launches = timed_epochs(agent, args.steps, args.warmup, world, read_result=False)
     clocks = sampler.stop() if rank == 0 else None
+    note(f"value arm done: {sec_per_step:.1f} ms/epoch")
     if os.environ.get("PHC_PHASE_TIMING", "0") == "1" and rank == 0:       # diagnostic only: CUDA-event phase breakdown of one epoch
         agent.timer.report()
         agent.train_epoch()
@@ -317,6 +328,7 @@ def main():
 
     peak, peak_src = measured_peak_gbs()
     roof = env_kernel_roofline(task, peak, peak_src) if rank == 0 else None
+    note("roofline kernel timed")
     if world > 1:
         torch.distributed.barrier()
     del agent, task
@@ -325,17 +337,20 @@ def main():
     e2e = None
     if not args.no_e2e:
         agent2, task2 = build_agent(args.num_envs, device, rank, world, host_bank=True)
+        note("e2e agent built (pinned host snapshots)")
         ms2, _ = timed_epochs(agent2, max(1, args.steps), max(3, args.warmup) if args.warmup >= 3 else args.warmup, world, read_result=True)
         e2e = {"value": env_steps / (ms2 * 1e-3), "unit": "env-steps/s", "ms_per_step": ms2,
                "h2d_bytes_per_step": HORIZON * task2.sim.h2d_bytes_per_step, "d2h_bytes_per_step": 16 * 4,
                "note": "simulator state (rigid bodies, dof state, dof forces) copied from pinned host memory every env step; epoch losses read back"}
         del agent2, task2
         torch.cuda.empty_cache()
+        note(f"e2e arm done: {ms2:.1f} ms/epoch")
 
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             est = cpu_epoch_estimate(args.num_envs)
+            note(f"cpu baseline sample done: {est['t_epoch']:.1f} s/epoch estimated on {est['cores']} threads")
             cpu = {"value": HORIZON * args.num_envs / est["t_epoch"], "unit": "env-steps/s", "cores": est["cores"], "kind": "port",
                    "sample": est["sample"], "ms_per_step": 1e3 * est["t_epoch"]}
         line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

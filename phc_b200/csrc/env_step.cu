@@ -165,6 +165,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   const bool zof = GETUP && (a.flags & PHC_FLAG_ZERO_OUT_FAR);
   const bool cyc = GETUP && (a.flags & PHC_FLAG_CYCLE_MOTION) && !obs_only;
   int cc = 0;                                        // _cycle_counter as the reset test sees it
+  bool rebased = false;                              // the clip wrapped this step
   if (GETUP) {
     if (a.cycle_counter) cc = a.cycle_counter[env];
     if (cyc) {
@@ -183,6 +184,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
         goff_o.x = g_state[0] - lerp1(r0[0], r1[0], omb, b.blend);     // _humanoid_root_states[:, :2] = body 0 of the state block
         goff_o.y = g_state[1] - lerp1(r0[1], r1[1], omb, b.blend);
         cc = 60;
+        rebased = true;
         if (lane == 0) {
           a.start_times[env] = t_start_o;
           a.start_offsets[env] = t_off_o;
@@ -339,16 +341,28 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
         }
       }
     }
+    float dist_t = dist;           // the distance the termination test sees
+    if (GETUP && rebased) {
+      // the clip wrapped this step: the reference's reset test re-queries the pose at the re-based time (humanoid_im.py:1142,
+      // :1148).  Rare (once per clip length): positions straight from the frame table, no staging.
+      const float t_re = PHC_ADD(PHC_ADD(PHC_MUL((float)progress, a.dt), t_start_o), t_off_o);
+      const Bracket32 b = frame_bracket32(t_re, m_len, (int)m_nf, m_dt);
+      const float* r0 = a.lib.frames_body + (size_t)(m_start + b.i0) * BS + jr * kBodyRec;
+      const float* r1 = a.lib.frames_body + (size_t)(m_start + b.i1) * BS + jr * kBodyRec;
+      const V3 pr = lerp3(v3(r0[0], r0[1], r0[2]), v3(r1[0], r1[1], r1[2]), 1.0f - b.blend, b.blend) + goff_o;
+      const V3 d2 = pr - sim.p;
+      dist_t = has_body ? sqrtf(d2.x * d2.x + d2.y * d2.y + d2.z * d2.z) : 0.f;
+    }
     bool fallen;
     {
       const float thr = has_body ? a.term_thresh[j] : INFINITY;
       if (a.flags & PHC_FLAG_TERM_USE_MEAN) {
         const bool in_set = has_body && thr < INFINITY;
         const float cnt = warp_sum(in_set ? 1.0f : 0.0f);
-        const float sum = warp_sum(in_set ? dist : 0.0f);
+        const float sum = warp_sum(in_set ? dist_t : 0.0f);
         fallen = (sum / cnt) > a.term_dist_mean;
       } else {
-        fallen = __any_sync(0xffffffffu, has_body && dist > thr);
+        fallen = __any_sync(0xffffffffu, has_body && dist_t > thr);
       }
     }
     e_pos = warp_sum(e_pos) / (float)(J + E);
