@@ -261,6 +261,11 @@ PHC_API int phc_amp_obs_dim(int32_t num_amp_joints, int32_t num_key_bodies, uint
 PHC_API int phc_amp_obs_dim_robot(int32_t num_dofs, int32_t num_key_bodies, uint32_t flags); /* 13 + 2 D + 3 nk */
 
 PHC_API int phc_env_step(const PhcStepArgs* args, void* stream);
+/* How many phc_env_step calls of this process took the compile-time specialised kernel of the shipped SMPL steady state
+ * (flags = UPRIGHT | LOCAL_ROOT_OBS | ROOT_HEIGHT_OBS | POWER_REWARD | EARLY_TERM | REWARD_FROM_CACHE, env_motion and ref_cache
+ * given, no env mask, no ref_body_* buffers, AMP ring slot / obs rows / pose cache movable as 16-byte granular bulk copies).
+ * Diagnostic: lets a caller (and the tests) see that its buffers qualify.  PHC_ENV_FAST=0 in the environment disables it. */
+PHC_API int64_t phc_env_step_fast_launches(void);
 
 /* build_amp_obs_demo (humanoid_amp.py:253-284) and the history re-initialisation of _init_amp_obs_ref
  * (:575-603): AMP observations of the REFERENCE motion at t0 - (first_step + k)*dt, k = 0..num_steps-1,

@@ -91,6 +91,7 @@ SIGNATURES = {
     "phc_task_obs_dim": (C.c_int, [C.c_int32, C.c_int32]),
     "phc_amp_obs_dim": (C.c_int, [C.c_int32, C.c_int32, C.c_uint32]),
     "phc_env_step": (C.c_int, [C.POINTER(PhcStepArgs), _p]),
+    "phc_env_step_fast_launches": (C.c_int64, []),
     "phc_amp_obs_demo": (C.c_int, [C.POINTER(PhcMotionLib), _p, _p, C.c_int64, C.c_int32, C.c_int32, C.c_float,
                                    C.c_uint32, _p, C.c_int32, _p, C.c_int32, _p, C.c_int64, _p, C.c_int32, _p]),
     "phc_amp_window_export": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, C.c_int64, _p]),

@@ -74,4 +74,23 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Four per-lane values summed over the warp with 6 shuffles instead of 20: after exchanging halves (xor 16: two values each
+// way) and quarters (xor 8) every lane carries ONE of the four partial sums, three more butterfly steps finish it.
+// Returns, in lanes 8k .. 8k+7, the warp total of value k (k = 0: a, 1: b, 2: c, 3: d).
+__device__ __forceinline__ float warp_sum4(float a, float b, float c, float d, int lane) {
+  const bool h16 = (lane & 16) != 0;
+  float k0 = h16 ? c : a, k1 = h16 ? d : b;
+  const float s0 = h16 ? a : c, s1 = h16 ? b : d;
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  const bool h8 = (lane & 8) != 0;
+  float k = h8 ? k1 : k0;
+  const float s = h8 ? k0 : k1;
+  k += __shfl_xor_sync(0xffffffffu, s, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  return k;
+}
+
 }  // namespace phc

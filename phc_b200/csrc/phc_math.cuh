@@ -66,6 +66,36 @@ PHC_HD Q4 qmul(Q4 a, Q4 b) {
 
 PHC_HD Q4 qconj(Q4 q) { return q4(-q.x, -q.y, -q.z, q.w); }
 
+// qmul with a quaternion about z on the left (a.x == a.y == 0: the heading quaternions).  Every "+ 0" / "- 0" of the general
+// expression is dropped (x + 0 == x exactly), so for finite inputs the result equals qmul(a, b) operation by operation.
+PHC_HD Q4 qmul_zl(Q4 a, Q4 b) {
+  const float ww = a.z * (b.x + b.y);
+  const float yy = a.w * (b.w + b.z);
+  const float zz = a.w * (b.w - b.z);
+  const float xx = ww + yy + zz;
+  const float qq = 0.5f * (xx + a.z * (b.x - b.y));
+  Q4 r;
+  r.w = qq - ww + a.z * (b.y - b.z);
+  r.x = qq - xx + a.w * (b.x + b.w);
+  r.y = qq - yy + a.w * (b.y + b.z);
+  r.z = qq - zz + a.z * (b.w - b.x);
+  return r;
+}
+
+// ... and on the right (b.x == b.y == 0): ww = (a.z + a.x) * 0 and (a.z - a.x) * 0 vanish, b.x + b.w == b.w etc.
+PHC_HD Q4 qmul_zr(Q4 a, Q4 b) {
+  const float yy = (a.w - a.y) * (b.w + b.z);
+  const float zz = (a.w + a.y) * (b.w - b.z);
+  const float xx = yy + zz;
+  const float qq = 0.5f * xx;
+  Q4 r;
+  r.w = qq + (a.z - a.y) * (-b.z);
+  r.x = qq - xx + (a.x + a.w) * b.w;
+  r.y = qq - yy + (a.w - a.x) * b.z;
+  r.z = qq - zz + (a.z + a.y) * b.w;
+  return r;
+}
+
 // v*(2w^2-1) + (qv x v)*w*2 + qv*(qv.v)*2
 PHC_HD V3 qrot(Q4 q, V3 v) {
   const float s = 2.0f * (q.w * q.w) - 1.0f;

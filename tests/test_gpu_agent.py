@@ -127,3 +127,37 @@ def test_ref_pose_cache_is_bit_identical_to_reinterpolation():
                 t.reset(mask.clone())
             assert torch.equal(a.obs_buf, b.obs_buf) and torch.equal(a._motion_start_times, b._motion_start_times)
     assert int((tasks[0].reset_buf != 0).sum()) >= 0
+
+
+def test_shipped_config_takes_the_specialised_step_kernel():
+    """HumanoidIm's default (shipped im.yaml / env_im.yaml) steady-state launch must qualify for the compile-time specialised
+    kernel (phc_env_step_fast_launches), and that kernel must agree with the generic instantiation on the same inputs."""
+    from phc_b200 import _lib
+    from phc_b200.env.humanoid_im import HumanoidIm
+    lib = _lib.load()
+    n = 300
+    m = syn.make_motions(n, seed=31, min_frames=40, max_frames=80)
+    env = HumanoidIm({"env": {"num_envs": n}, "motion_data": m, "seed": 5}, device_type="cuda", device_id=0)
+    env.reset()
+    before = lib.phc_env_step_fast_launches()
+    cache_in = env._ref_cache.clone()               # the launch consumes the cached pose and replaces it
+    env.step(None)
+    torch.cuda.synchronize()
+    assert lib.phc_env_step_fast_launches() == before + 1
+    fast = {k: getattr(env, k).clone() for k in ("obs_buf", "rew_buf", "reward_raw", "reset_buf", "_terminate_buf")}
+    fast["amp"] = env._amp_obs_buf.clone()
+    fast["cache"] = env._ref_cache.clone()
+    # the same step through the generic instantiation: an all-ones env mask disqualifies the launch from the fast variant
+    p = env._plan
+    ones = torch.ones(n, dtype=torch.int64, device=env.device)
+    env._ref_cache.copy_(cache_in)
+    p.args.only_where = ones.data_ptr()
+    p.run()
+    torch.cuda.synchronize()
+    p.args.only_where = None
+    assert lib.phc_env_step_fast_launches() == before + 1
+    for k in ("obs_buf", "rew_buf", "reward_raw"):
+        close(getattr(env, k).cpu(), fast[k].cpu(), atol=2e-6, what=f"fast vs generic {k}")
+    assert torch.equal(env.reset_buf, fast["reset_buf"]) and torch.equal(env._terminate_buf, fast["_terminate_buf"])
+    close(env._amp_obs_buf.cpu(), fast["amp"].cpu(), what="fast vs generic amp")
+    close(env._ref_cache.cpu(), fast["cache"].cpu(), what="fast vs generic pose cache")
