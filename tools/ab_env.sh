@@ -5,11 +5,12 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 {
-  echo "== default"; python tools/time_env.py 4096 60; python tools/time_env.py 16384 40
+  echo "== default (FAST specialisation)"; python tools/time_env.py 4096 60; python tools/time_env.py 16384 40
+  echo "== default, PHC_ENV_FAST=0 (generic instantiation)"; PHC_ENV_FAST=0 python tools/time_env.py 4096 60
   for d in phc_b200/lib/alt_*/; do
     v=$(basename "$d")
     echo "== $v"
-    PHC_LIB_PATH="$PWD/$d/libphc_b200.so" timeout 120 python -m pytest tests/test_gpu_env_step.py -q -x -m gpu 2>&1 | tail -1
+    PHC_LIB_PATH="$PWD/$d/libphc_b200.so" timeout 120 python -m pytest tests/test_gpu_env_step.py tests/test_gpu_agent.py -q -m gpu -p no:cacheprovider 2>&1 | tail -3
     PHC_LIB_PATH="$PWD/$d/libphc_b200.so" python tools/time_env.py 4096 60
   done
 } > gpurun_out/ab_env.log 2>&1
