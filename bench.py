@@ -117,9 +117,14 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # the reference algorithm on the CPU (oracle port) -- cpu_baseline and --impl reference
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_epoch_estimate(num_envs: int, rollout_steps: int = 2, minibatches: int = 1):
+def cpu_epoch_estimate(num_envs: int, rollout_steps: int = 1, minibatches: int = 1, rollout_envs: int = 0, mb_rows: int = 0):
     """Time a bounded SAMPLE of one epoch with the torch-CPU oracle (the reference's algorithm, all host threads) and
-    scale it to a whole epoch: 32 x rollout step + GAE/adv + 48 x minibatch update."""
+    scale it to a whole epoch: 32 x rollout step + GAE/adv + 48 x minibatch update.  rollout_envs / mb_rows shrink the sample
+    (envs of the sampled rollout step, rows of the sampled minibatch); both parts are per-row work and are scaled linearly to
+    num_envs envs / 16384 rows."""
+    full_envs = num_envs
+    if rollout_envs and rollout_envs < num_envs:
+        num_envs = rollout_envs
     from oracle import phc_oracle as O
     from oracle import ppo_oracle as PO
     from phc_b200 import synthetic as syn
@@ -166,7 +171,8 @@ def cpu_epoch_estimate(num_envs: int, rollout_steps: int = 2, minibatches: int =
     t0 = time.perf_counter()
     for _ in range(rollout_steps):
         rollout_step()
-    t_roll = (time.perf_counter() - t0) / rollout_steps
+    t_roll = (time.perf_counter() - t0) / rollout_steps * (full_envs / num_envs)
+    sampled_envs, num_envs = num_envs, full_envs
 
     fd, v, r, nv = syn.make_rollout(num_envs, HORIZON, seed=0)
     t0 = time.perf_counter()
@@ -174,7 +180,9 @@ def cpu_epoch_estimate(num_envs: int, rollout_steps: int = 2, minibatches: int =
     O.normalize_advantages((adv + v).reshape(-1, 1), v.reshape(-1, 1))
     t_gae = time.perf_counter() - t0
 
-    B, Bd = min(16384, HORIZON * num_envs), min(4096, HORIZON * num_envs)
+    B_full = min(16384, HORIZON * num_envs)
+    B = min(B_full, mb_rows) if mb_rows else B_full
+    Bd = max(1, B // 4)
     gen = torch.Generator().manual_seed(1)
     rn = lambda *s: torch.randn(*s, generator=gen)
     batch = dict(obs_n=rn(B, obs_dim), actions=rn(B, act) * 0.1, old_neglogp=rn(B) * 0.1 + 60, advantages=rn(B),
@@ -185,12 +193,13 @@ def cpu_epoch_estimate(num_envs: int, rollout_steps: int = 2, minibatches: int =
     t0 = time.perf_counter()
     for _ in range(minibatches):
         PO.minibatch_update(sd, batch, pcfg)
-    t_mb = (time.perf_counter() - t0) / minibatches
-    n_mb = 6 * (HORIZON * num_envs // B)
+    t_mb = (time.perf_counter() - t0) / minibatches * (B_full / B)
+    n_mb = 6 * (HORIZON * num_envs // B_full)
     t_epoch = HORIZON * t_roll + t_gae + n_mb * t_mb
     return dict(t_epoch=t_epoch, t_rollout_step=t_roll, t_gae=t_gae, t_minibatch=t_mb, cores=cores,
-                sample=f"{rollout_steps} rollout steps of {num_envs} envs (env step + actor/critic) + GAE(32x{num_envs}) + "
-                       f"{minibatches} of {n_mb} minibatch updates (B={B}), scaled to one epoch; torch {torch.__version__} CPU, {cores} threads")
+                sample=f"{rollout_steps} rollout step(s) of {sampled_envs} envs (env step + actor/critic, x{full_envs / sampled_envs:g}) + GAE(32x{num_envs}) + "
+                       f"{minibatches} of {n_mb} minibatch updates on {B} of {B_full} rows (x{B_full / B:g}), scaled to one epoch of {full_envs} envs; "
+                       f"torch {torch.__version__} CPU, {cores} threads")
 
 
 def run_reference_arm(args):
@@ -200,7 +209,7 @@ def run_reference_arm(args):
     t_all = []
     est = None
     for i in range(args.warmup + args.steps):
-        est = cpu_epoch_estimate(args.num_envs, rollout_steps=1, minibatches=1)
+        est = cpu_epoch_estimate(args.num_envs, rollout_steps=1, minibatches=1, rollout_envs=1024, mb_rows=2048)   # ~5-10 s per step
         if i >= args.warmup:
             t_all.append(est["t_epoch"])
     t = sum(t_all) / len(t_all)
@@ -377,7 +386,7 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            est = cpu_epoch_estimate(args.num_envs)
+            est = cpu_epoch_estimate(args.num_envs, rollout_steps=1, minibatches=1, mb_rows=4096)     # ~15-25 s of CPU work
             note(f"cpu baseline sample done: {est['t_epoch']:.1f} s/epoch estimated on {est['cores']} threads")
             cpu = {"value": HORIZON * args.num_envs / est["t_epoch"], "unit": "env-steps/s", "cores": est["cores"], "kind": "port",
                    "sample": est["sample"], "ms_per_step": 1e3 * est["t_epoch"]}
