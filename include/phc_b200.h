@@ -251,6 +251,9 @@ typedef struct PhcStepArgs {
   int32_t max_episode_length;  /* env.episode_length                                                                       */
   float* point_goal;           /* [N] _point_goal: read by the reward (previous distance), rewritten by the observation    */
   const float* cycle_phase;    /* [N] uniform [0,1) numbers: sample_time_interval's draw for a clip that wraps this step   */
+  /* ---- flags.im_eval extras of HumanoidIm.post_physics_step (humanoid_im.py:674-680); NULL = skip ---- */
+  float* mpjpe;                /* [N] mean over the J bodies of |body_pos - reference pos| at the current motion time      */
+  float* body_pos_gt;          /* [N, J, 3] that reference pose's positions (extras['body_pos_gt'])                        */
 } PhcStepArgs;
 
 /* Sizes implied by a configuration (so callers can allocate): */

@@ -358,6 +358,9 @@ def env_step(tab: MotionTables, cfg: StepConfig, body_state: Tensor, dof_state: 
         rew = rew + pw
         raw = torch.cat((raw, pw[:, None]), dim=-1)
     out["rew"], out["reward_raw"] = rew, raw
+    # flags.im_eval extras of HumanoidIm.post_physics_step (humanoid_im.py:674-680)
+    out["mpjpe"] = (bp - ref["rg_pos"]).norm(dim=-1).mean(dim=-1)
+    out["body_pos_gt"] = ref["rg_pos"]
     rb = list(range(J)) if cfg.reset_bodies is None else list(cfg.reset_bodies)
     td = torch.full((J,), cfg.term_dist) if not torch.is_tensor(cfg.term_dist) else cfg.term_dist
     pass_time = t_now >= tab.lengths[motion_ids]

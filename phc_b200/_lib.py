@@ -66,7 +66,7 @@ class PhcStepArgs(C.Structure):
         ("ref_body_pos", _p), ("ref_body_rot", _p), ("ref_body_vel", _p), ("ref_body_ang_vel", _p),
         ("ref_cache", _p),
         ("close_distance", C.c_float), ("far_distance", C.c_float), ("max_episode_length", C.c_int32), ("point_goal", _p),
-        ("cycle_phase", _p),
+        ("cycle_phase", _p), ("mpjpe", _p), ("body_pos_gt", _p),
     ]
 
 

@@ -342,6 +342,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     {
       const BodyRec ref = from_cache ? load_body(s_rslots + jr * kBodyRec)
                                      : blend_body(pr0 + jr * kBodyRec, pr1 + jr * kBodyRec, bl_r, goff);
+      if (!FAST && a.body_pos_gt && has_body) st3(a.body_pos_gt + ((size_t)env * J + j) * 3, ref.p);
       if (has_body || has_ext) {      // position / rotation terms: all J + E bodies; velocity terms: the J simulated ones
         const V3 dp = ref.p - sim.p;
         const float sp = dp.x * dp.x + dp.y * dp.y + dp.z * dp.z;
@@ -355,6 +356,10 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
           dist = sqrtf(sp);
         }
       }
+    }
+    if (!FAST && a.mpjpe) {        // flags.im_eval extras (humanoid_im.py:674-680): mean per-joint position error + the pose it is against
+      const float mp = warp_sum(has_body ? dist : 0.0f) / (float)J;
+      if (lane == 0) a.mpjpe[env] = mp;
     }
     float dist_t = dist;           // the distance the termination test sees
     if (GETUP && rebased) {

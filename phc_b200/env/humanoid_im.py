@@ -131,7 +131,8 @@ class HumanoidIm:
             key_bodies=key_bodies, reset_bodies=reset_bodies, term_dist=float(env.get("terminationDistance", 0.25)),
             dof_subset=dof_subset, amp_steps=self._num_amp_obs_steps, ext_parents=self.extend_body_parent_ids,
             ext_pos=self.extend_body_pos_in_parent, zero_out_far=self.zero_out_far, close_distance=self.close_distance,
-            far_distance=self.far_distance, cycle_motion=self.cycle_motion, max_episode_length=self.max_episode_length)
+            far_distance=self.far_distance, cycle_motion=self.cycle_motion, max_episode_length=self.max_episode_length,
+            term_use_mean=bool(cfg.get("im_eval", False)) and not bool(env.get("strict_eval", False)))   # humanoid_im.py:1180
         self._key_body_ids, self._reset_bodies_id, self.dof_subset = key_bodies, reset_bodies, dof_subset
 
         # ---- simulator backend and its tensors (Humanoid._setup_tensors) ---------------------------------------
@@ -177,7 +178,10 @@ class HumanoidIm:
         self._use_ref_cache = bool(cfg.get("ref_pose_cache", True))
         J = self._motion_lib.num_bodies
         self._ref_cache = torch.zeros(N, int(self._motion_lib.frames_body.shape[1]), device=dev) if self._use_ref_cache else None
+        # flags.im_eval (humanoid_im.py:674-680; also selects the mean-distance termination, :1180): extras['mpjpe'], body_pos(_gt)
+        self.im_eval = bool(cfg.get("im_eval", False))
         self._plan = ops.EnvStepPlan(cycle_counter=self._cycle_counter, with_ref_buffers=not self._use_ref_cache,
+                                     with_eval_extras=self.im_eval,
                                      amp_ring=self._amp_use_ring, ref_cache=self._ref_cache,
                                      reward_from_cache=self._use_ref_cache, **common)
         p = self._plan
@@ -259,6 +263,10 @@ class HumanoidIm:
         self.extras["terminate"] = self._terminate_buf
         self.extras["reward_raw"] = self.reward_raw
         self.extras["amp_obs_export"] = self.export_amp_obs          # lazily materialised window (see export_amp_obs)
+        if self.im_eval:              # kept on the device: the reference's .cpu().numpy() of body_pos / body_pos_gt is the caller's choice
+            self.extras["mpjpe"] = self._plan.mpjpe
+            self.extras["body_pos"] = self._rigid_body_pos
+            self.extras["body_pos_gt"] = self._plan.body_pos_gt
 
     # kept for API parity: the pieces are produced together by the fused launch
     def _compute_reward(self, actions=None):

@@ -277,7 +277,8 @@ class EnvStepPlan:
                  amp_shift: bool = True, with_amp: bool = True, with_ref_buffers: bool = False,
                  only_where: Optional[torch.Tensor] = None, obs_only: bool = False, amp_ring: bool = False,
                  ref_cache: Optional[torch.Tensor] = None, reward_from_cache: bool = False,
-                 point_goal: Optional[torch.Tensor] = None, cycle_phase: Optional[torch.Tensor] = None):
+                 point_goal: Optional[torch.Tensor] = None, cycle_phase: Optional[torch.Tensor] = None,
+                 with_eval_extras: bool = False):
         """ref_cache: [N, body_stride] pose cache (PhcStepArgs.ref_cache): every run() stores the reference pose interpolated
         for the first observation sample; reward_from_cache=True makes run() take the reward-time reference pose from it
         (valid for HumanoidIm's step / reset sequence, see include/phc_b200.h).
@@ -380,6 +381,10 @@ class EnvStepPlan:
             k["cycle_phase"] = _req(cycle_phase, f32, "cycle_phase", dev)
             assert k["cycle_phase"].shape == (N,) and cycle_counter is not None
             a.cycle_phase = k["cycle_phase"].data_ptr()
+        # flags.im_eval extras (humanoid_im.py:674-680): mpjpe [N] and the reference positions it is measured against [N, J, 3]
+        self.mpjpe = torch.zeros(N, dtype=f32, device=dev) if with_eval_extras else None
+        self.body_pos_gt = torch.zeros(N, J, 3, dtype=f32, device=dev) if with_eval_extras else None
+        a.mpjpe, a.body_pos_gt = _ptr(self.mpjpe), _ptr(self.body_pos_gt)
         a.close_distance, a.far_distance, a.max_episode_length = cfg.close_distance, cfg.far_distance, int(cfg.max_episode_length)
         k["only_where"] = None if only_where is None else _req(only_where, i64, "only_where", dev)
         a.only_where = _ptr(k["only_where"])

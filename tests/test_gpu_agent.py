@@ -161,3 +161,29 @@ def test_shipped_config_takes_the_specialised_step_kernel():
     assert torch.equal(env.reset_buf, fast["reset_buf"]) and torch.equal(env._terminate_buf, fast["_terminate_buf"])
     close(env._amp_obs_buf.cpu(), fast["amp"].cpu(), what="fast vs generic amp")
     close(env._ref_cache.cpu(), fast["cache"].cpu(), what="fast vs generic pose cache")
+
+
+def test_im_eval_extras_match_oracle():
+    """flags.im_eval: extras['mpjpe'] / 'body_pos_gt' (humanoid_im.py:674-680) and the mean-distance termination, against the oracle."""
+    n = 130
+    m = syn.make_motions(n, seed=17, min_frames=40, max_frames=90)
+    task = HumanoidIm({"env": {"num_envs": n}, "motion_data": m, "seed": 2, "im_eval": True})
+    task.reset()
+    for _ in range(3):
+        task.step(None)
+    torch.cuda.synchronize()
+    st_in = dict(body=task._rigid_body_state_reshaped[:, :24].cpu().clone(), dof=task._dof_state.cpu().clone(), force=task.dof_force_tensor.cpu().clone(),
+                 prog=task.progress_buf.cpu().clone() + 1, ids=task._sampled_motion_ids.cpu(), st=task._motion_start_times.cpu().clone(),
+                 off=task._motion_start_times_offset.cpu().clone(), goff=task._global_offset.cpu().clone(), hist=task._amp_obs_buf.cpu().clone())
+    task.sim.simulate(None)
+    st_in["body"] = task._rigid_body_state_reshaped[:, :24].cpu().clone()
+    st_in["dof"], st_in["force"] = task._dof_state.cpu().clone(), task.dof_force_tensor.cpu().clone()
+    task.post_physics_step()
+    torch.cuda.synchronize()
+    exp = O.env_step(oracle_tables(m), smpl_step_config(use_mean=True), st_in["body"], st_in["dof"], st_in["force"], st_in["prog"], st_in["ids"],
+                     st_in["st"], st_in["off"], st_in["goff"], st_in["hist"])
+    close(task.extras["mpjpe"].cpu(), exp["mpjpe"], what="mpjpe")
+    close(task.extras["body_pos_gt"].cpu(), exp["body_pos_gt"], what="body_pos_gt")
+    close(task.rew_buf.cpu(), exp["rew"], what="rew (im_eval)")
+    assert torch.equal(task.reset_buf.cpu(), exp["reset"]) and torch.equal(task._terminate_buf.cpu(), exp["terminate"])
+    assert torch.equal(task.extras["body_pos"], task._rigid_body_pos)
