@@ -23,6 +23,7 @@ PHC_FLAG_OBS_ONLY = 1 << 7
 PHC_FLAG_REWARD_FROM_CACHE = 1 << 8
 PHC_FLAG_ZERO_OUT_FAR = 1 << 9
 PHC_FLAG_CYCLE_MOTION = 1 << 10
+PHC_FLAG_NO_SPECIALISE = 1 << 11
 PHC_ACT_NONE, PHC_ACT_RELU, PHC_ACT_SILU, PHC_ACT_SILU_BWD = 0, 1, 2, 3
 PHC_MAX_KEY_BODIES = 8
 PHC_MAX_BODIES = 32

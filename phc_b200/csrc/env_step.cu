@@ -328,12 +328,8 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   // heading frame of the simulated root
   Q4 root_q = q4(s_state[3], s_state[4], s_state[5], s_state[6]);
   if (!(flags & PHC_FLAG_UPRIGHT)) root_q = strip_base_rot(root_q);
-#ifdef PHC_EXP_HEADING_ALG      // experiment build only (tools/ab_env.sh)
-  const Q4 hq = heading_quat_alg(root_q);
-#else
   const float heading = heading_angle(root_q);
   const Q4 hq = quat_about_z(heading);
-#endif
   const Q4 hinv = q4(0.0f, 0.0f, -hq.z, hq.w);     // quat_about_z(-heading): sin is odd, cos even -> the exact conjugate
 
   if (!obs_only) {   // the reset-path launch writes observations (and the pose cache) only

@@ -118,22 +118,6 @@ PHC_HD float heading_angle(Q4 q) {
   return atan2f(dy, dx);
 }
 
-// EXPERIMENT (PHC_EXP_HEADING_ALG builds only, tools/ab_env.sh): the heading quaternion (0, 0, sin(h/2), cos(h/2)) straight from
-// the rotated x axis (dx, dy) = r (cos h, sin h) with half-angle identities in their well-conditioned branches, instead of
-// atan2f followed by sincosf -- same function, not the reference's operation sequence (a few ulp apart).
-PHC_HD Q4 heading_quat_alg(Q4 q) {
-  const float s = 2.0f * (q.w * q.w) - 1.0f;
-  const float dx = s + q.x * q.x * 2.0f;
-  const float dy = q.z * q.w * 2.0f + q.y * q.x * 2.0f;
-  const float r = sqrtf(dx * dx + dy * dy);
-  if (!(r > 0.0f)) return q4(0.0f, 0.0f, 0.0f, 1.0f);       // atan2(0, 0) = 0
-  const float c = dx / r, sn = dy / r;
-  float s2, c2;
-  if (c >= 0.0f) { c2 = sqrtf((1.0f + c) * 0.5f); s2 = sn / (2.0f * c2); }
-  else { s2 = copysignf(sqrtf((1.0f - c) * 0.5f), sn); c2 = sn / (2.0f * s2); }
-  return q4(0.0f, 0.0f, s2, c2);
-}
-
 PHC_HD void sin_cos(float x, float* s, float* c) {
 #if defined(__CUDA_ARCH__)
   sincosf(x, s, c);          // one shared range reduction, same 2-ulp accuracy class as sinf / cosf

@@ -132,6 +132,7 @@ class HumanoidIm:
             dof_subset=dof_subset, amp_steps=self._num_amp_obs_steps, ext_parents=self.extend_body_parent_ids,
             ext_pos=self.extend_body_pos_in_parent, zero_out_far=self.zero_out_far, close_distance=self.close_distance,
             far_distance=self.far_distance, cycle_motion=self.cycle_motion, max_episode_length=self.max_episode_length,
+            specialise=bool(cfg.get("specialised_step", True)),
             term_use_mean=bool(cfg.get("im_eval", False)) and not bool(env.get("strict_eval", False)))   # humanoid_im.py:1180
         self._key_body_ids, self._reset_bodies_id, self.dof_subset = key_bodies, reset_bodies, dof_subset
 

@@ -242,6 +242,7 @@ class EnvStepConfig:
     far_distance: float = 3.0          # env.far_distance
     cycle_motion: bool = False         # env.cycle_motion
     max_episode_length: int = 300      # env.episode_length
+    specialise: bool = True            # False: PHC_FLAG_NO_SPECIALISE (always the generic kernel instantiation)
 
     def flags(self) -> int:
         f = 0
@@ -249,7 +250,7 @@ class EnvStepConfig:
                         (self.root_height_obs, PHC_FLAG_ROOT_HEIGHT_OBS), (self.power_reward, PHC_FLAG_POWER_REWARD),
                         (self.early_term, PHC_FLAG_EARLY_TERM), (self.no_collision, PHC_FLAG_NO_COLLISION),
                         (self.term_use_mean, PHC_FLAG_TERM_USE_MEAN), (self.zero_out_far, _lib.PHC_FLAG_ZERO_OUT_FAR),
-                        (self.cycle_motion, _lib.PHC_FLAG_CYCLE_MOTION)):
+                        (self.cycle_motion, _lib.PHC_FLAG_CYCLE_MOTION), (not self.specialise, _lib.PHC_FLAG_NO_SPECIALISE)):
             if on:
                 f |= bit
         return f

@@ -105,7 +105,8 @@ def test_ref_pose_cache_is_bit_identical_to_reinterpolation():
     s+1) against re-interpolating every step: identical bits over a rollout with resets in between."""
     n = 160
     m = syn.make_motions(n, seed=3, min_frames=20, max_frames=40)          # short clips: some envs run past the end
-    tasks = [HumanoidIm({"env": {"num_envs": n}, "motion_data": m, "seed": 3, "ref_pose_cache": c}) for c in (True, False)]
+    # both through the SAME (generic) kernel instantiation: the property is the cache, not the code generation of two templates
+    tasks = [HumanoidIm({"env": {"num_envs": n}, "motion_data": m, "seed": 3, "ref_pose_cache": c, "specialised_step": False}) for c in (True, False)]
     assert tasks[0]._use_ref_cache and not tasks[1]._use_ref_cache
     for t in tasks:
         torch.manual_seed(99)                    # start times are drawn from the global generator: same draws for both
