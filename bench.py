@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 NUM_ENVS = 4096
+MAX_CPU_THREADS = 64                    # threads of the CPU arm: batches this small stop scaling (and start thrashing) beyond that
 HORIZON = 32
 ALGO_BYTES_PER_ENV_STEP = 9384          # core algorithmic bytes of the fused obs+reward kernel, J=24
 METRIC = "env-steps/sec (fused obs+reward+PPO) at 4096 envs/GPU"
@@ -129,7 +130,7 @@ def cpu_epoch_estimate(num_envs: int, rollout_steps: int = 1, minibatches: int =
     from oracle import ppo_oracle as PO
     from phc_b200 import synthetic as syn
     import math
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, MAX_CPU_THREADS)
     torch.set_num_threads(cores)
     torch._C._jit_set_profiling_mode(False)          # as phc/env/tasks/base_task.py:95-96
     torch._C._jit_set_profiling_executor(False)
@@ -202,6 +203,23 @@ def cpu_epoch_estimate(num_envs: int, rollout_steps: int = 1, minibatches: int =
                        f"torch {torch.__version__} CPU, {cores} threads")
 
 
+def cpu_epoch_estimate_bounded(num_envs: int, budget_s: float):
+    """cpu_epoch_estimate on the largest sample that fits a wall-clock budget: the sample grows (256 -> 1024 -> 4096 envs of a
+    rollout step, 512 -> 2048 -> 4096 minibatch rows) only while the next size is predicted (x4) to fit what is left.  Host CPUs of
+    the GPU boxes differ by an order of magnitude in this workload; the first size takes a second or two on any of them."""
+    cpu_epoch_estimate(num_envs, rollout_steps=1, minibatches=1, rollout_envs=min(64, num_envs), mb_rows=128)   # untimed warm-up:
+    # thread pool, TorchScript specialisation and autograd's first pass cost seconds once and would dominate a small sample
+    t0 = time.perf_counter()
+    est = None
+    for n_roll, rows in ((256, 512), (1024, 2048), (4096, 4096)):
+        t1 = time.perf_counter()
+        est = cpu_epoch_estimate(num_envs, rollout_steps=1, minibatches=1, rollout_envs=min(n_roll, num_envs), mb_rows=rows)
+        took = time.perf_counter() - t1
+        if 4.0 * took > budget_s - (time.perf_counter() - t0):
+            break
+    return est
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -209,7 +227,7 @@ def run_reference_arm(args):
     t_all = []
     est = None
     for i in range(args.warmup + args.steps):
-        est = cpu_epoch_estimate(args.num_envs, rollout_steps=1, minibatches=1, rollout_envs=1024, mb_rows=2048)   # ~5-10 s per step
+        est = cpu_epoch_estimate_bounded(args.num_envs, budget_s=max(4.0, 150.0 / (args.warmup + args.steps)))   # whole run: a few minutes
         if i >= args.warmup:
             t_all.append(est["t_epoch"])
     t = sum(t_all) / len(t_all)
@@ -386,7 +404,7 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            est = cpu_epoch_estimate(args.num_envs, rollout_steps=1, minibatches=1, mb_rows=4096)     # ~15-25 s of CPU work
+            est = cpu_epoch_estimate_bounded(args.num_envs, budget_s=30.0)
             note(f"cpu baseline sample done: {est['t_epoch']:.1f} s/epoch estimated on {est['cores']} threads")
             cpu = {"value": HORIZON * args.num_envs / est["t_epoch"], "unit": "env-steps/s", "cores": est["cores"], "kind": "port",
                    "sample": est["sample"], "ms_per_step": 1e3 * est["t_epoch"]}
