@@ -328,12 +328,19 @@ def env_kernel_roofline(task, peak_gbs: float, peak_src: str, iters: int = 40):
     if not (0.2 * t_pair < t < t_pair):          # the differential estimate must be sane; otherwise report the conservative one
         t = t_pair
     N = task.num_envs
+    traffic = None            # DRAM bytes per launch from the committed ncu --set full capture of this kernel at this size
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "env_step_traffic.json")))
+        if int(tj.get("num_envs", -1)) == N:
+            traffic = int(tj["dram_bytes_per_launch"])
+    except Exception:
+        traffic = None
     achieved = ALGO_BYTES_PER_ENV_STEP * N / t / 1e9
     # what the launch really moves per env at J=24: inputs 1248 (state) + 1248 (cached reference pose of the reward time)
     # + 2 x 1248 (observation bracket) + 552 + 276 (dof) + 56 (scalars, env_motion); outputs 3744 (obs row incl. 8 pad bytes)
     # + 40 (reward/reset) + 784 (AMP ring slot) + 1248 (pose cache for the next step = the ref_* buffers)
     actual = 1248 + 1248 + 2 * 1248 + 552 + 276 + 56 + 3744 + 40 + 784 + 1248
-    return {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
+    return {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
             "kernel": "phc::env_step_kernel<1, 24, false, true>", "kernel_us": t * 1e6, "kernel_us_event_pair": t_pair * 1e6,
             "frac_event_pair": ALGO_BYTES_PER_ENV_STEP * N / t_pair / 1e9 / peak_gbs,
             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * N,
