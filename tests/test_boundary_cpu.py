@@ -78,3 +78,29 @@ def test_synthetic_generator_is_deterministic_and_unit():
     assert a.length_starts[0] == 0 and int(a.num_frames.sum()) == a.gts.shape[0]
     assert torch.allclose(a.lengths, a.dts * (a.num_frames - 1))
     assert len(syn.SMPL_DOF_SUBSET) == 57 and syn.SMPL_DOF_SUBSET[9] == 12
+
+
+def test_header_is_plain_c_and_c_host_runs(tmp_path):
+    """The boundary is a C ABI: the header compiles as pedantic C99, a C program (examples/c_host.c) links against the library and
+    runs its no-device entry points, and the struct sizes the C compiler sees equal the ctypes mirrors'."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from phc_b200 import _lib, build
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    lib_path = build.build()
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", os.path.join(inc, "phc_b200.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exe = str(tmp_path / "c_host")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-I" + inc, os.path.join(ROOT, "examples", "c_host.c"), "-o", exe,
+                        "-L" + os.path.dirname(lib_path), "-lphc_b200", "-Wl,-rpath," + os.path.dirname(lib_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"sizeof\(PhcStepArgs\) = (\d+), sizeof\(PhcMotionLib\) = (\d+)", r.stdout)
+    assert (int(m.group(1)), int(m.group(2))) == (C.sizeof(_lib.PhcStepArgs), C.sizeof(_lib.PhcMotionLib))
+    assert "phc_env_step(NULL) -> -1" in r.stdout
