@@ -307,8 +307,13 @@ class HumanoidIm:
         m = self._reset_mask
         if env_ids is None:
             m.fill_(1)
-        elif env_ids.dtype == torch.bool or (env_ids.shape == m.shape and env_ids.dtype in (torch.int64, torch.uint8, torch.float32)):
-            m.copy_(env_ids != 0)
+        elif env_ids.dtype in (torch.bool, torch.uint8, torch.float32) and env_ids.shape == m.shape:
+            m.copy_(env_ids != 0)                       # a [N] mask (e.g. dones)
+        elif env_ids.dtype == torch.int64 and env_ids.shape == m.shape and m.numel() > 0:
+            # [N] int64 is either our own 0/1 mask (reset_buf) or the reference's index list naming every env
+            # (`torch.arange(num_envs)`): told apart on the device, without a host sync, by the largest entry
+            as_index = torch.zeros_like(m).index_fill_(0, env_ids.clamp(0, m.numel() - 1), 1)
+            m.copy_(torch.where(env_ids.max() <= 1, (env_ids != 0).to(m.dtype), as_index))
         else:                                           # reference-style index list
             m.zero_()
             m[env_ids] = 1
