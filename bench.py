@@ -417,10 +417,11 @@ def main():
                    "sample": est["sample"], "ms_per_step": 1e3 * est["t_epoch"]}
         line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": sec_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (3xTF32 tensor-core GEMMs, fp32 accumulate; env kernels fp32)", "data": "synthetic",
+                "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"PPO epoch: {args.num_envs} envs/GPU x 32 steps, SMPL 24 bodies, obs 934, AMP 10x196, im.yaml nets "
                                        f"(1024-512), minibatch 16384 x 6 mini-epochs, one synthetic clip per env",
                            "parallelism": f"dp{world} (env shards, 1 NCCL all-reduce per minibatch)",
+                           "arithmetic": "fp32 throughout (the reference trains with mixed_precision: False): env kernels fp32, MLP GEMMs 3xTF32 on tcgen05 with fp32 accumulation",
                            "l2": "inputs larger than L2: 2.1 GB experience buffer + ~1 GB frame tables per epoch; the roofline kernel is timed with an explicit L2 flush"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
