@@ -256,6 +256,12 @@ H1_NUM_BODIES, H1_NUM_DOFS = 20, 19
 H1_EXT_PARENTS = [15, 19, 0]                                   # left_elbow_link, right_elbow_link, pelvis
 H1_EXT_POS = [[0.3, 0.0, 0.0], [0.3, 0.0, 0.0], [0.0, 0.0, 0.6]]
 H1_KEY_BODIES = [5, 10, 15, 19]                                # ankles and elbows
+# Unitree G1 (phc/data/cfg/robot/unitree_g1.yaml): 38 bodies, 37 hinge dofs, one extend body above the pelvis
+G1_NUM_BODIES, G1_NUM_DOFS = 38, 37
+G1_EXT_PARENTS = [0]
+G1_EXT_POS = [[0.0, 0.0, 0.4]]
+G1_KEY_BODIES = [6, 12, 18, 30]                                # ankle roll links and elbow roll links
+SMPLX_KEY_BODIES = [8, 4, 41, 26]                              # four end-effector-like bodies of a 52-body tree
 
 
 @dataclass

@@ -429,12 +429,13 @@ def make_ref_robot_lib(m):
     return lib
 
 
-def gen_h1():
-    m = syn.make_robot_motions(24, seed=2, min_frames=12, max_frames=24)
+def _gen_robot(name, m, ext_parents, ext_pos, key_bodies, n_env=24):
+    """Hinge-joint robot goldens (h1.npz / g1.npz): MotionLibReal.get_motion_state, the HumanoidIm step with extend bodies,
+    build_amp_observations_robot through _compute_amp_observations / build_amp_obs_demo."""
     J, D, E = m.num_bodies, m.num_dofs, m.num_ext
     lib = make_ref_robot_lib(m)
     d = {"tab_" + f: getattr(m, f) for f in ("gts_t", "grs_t", "gvs_t", "gavs_t", "dof_pos", "dvs", "lengths", "num_frames", "dts", "length_starts")}
-    d["ext_parents"], d["ext_pos"], d["key_bodies"] = np.array(syn.H1_EXT_PARENTS), np.array(syn.H1_EXT_POS, dtype=np.float32), np.array(syn.H1_KEY_BODIES)
+    d["ext_parents"], d["ext_pos"], d["key_bodies"] = np.array(ext_parents), np.array(ext_pos, dtype=np.float32), np.array(key_bodies)
     # --- MotionLibReal.get_motion_state
     g = torch.Generator().manual_seed(31)
     n = 64
@@ -450,19 +451,19 @@ def gen_h1():
               "rg_pos_t", "rg_rot_t", "body_vel_t", "body_ang_vel_t"):
         d["ms_out_" + k] = res[k]
     # --- env step (two cases: frame-grid starts; generic blend + global offset)
-    A = 13 + 2 * D + 3 * len(syn.H1_KEY_BODIES)
+    A = 13 + 2 * D + 3 * len(key_bodies)
     for tag, kw in (("A", {}), ("B", dict(with_offset=True, blend_jitter=True))):
-        st = syn.make_robot_env_state(m, 24, seed=4, amp_dim=A, max_progress=20, **kw)
+        st = syn.make_robot_env_state(m, n_env, seed=4, amp_dim=A, max_progress=20, **kw)
         base = syn.MotionData(gts=lib.gts, grs=lib.grs, lrs=lib.grs, gvs=lib.gvs, gavs=lib.gavs, dvs=torch.zeros(1), lengths=m.lengths,
                               num_frames=m.num_frames, dts=m.dts, length_starts=m.length_starts)
         env = build_ref_env(base, st)
         env._motion_lib = lib
-        env.humanoid_type = "h1"
-        env.extend_body_parent_ids = torch.tensor(syn.H1_EXT_PARENTS)
-        env.extend_body_pos_in_parent = torch.tensor(syn.H1_EXT_POS).repeat(env.num_envs, 1, 1)
+        env.humanoid_type = name
+        env.extend_body_parent_ids = torch.tensor(ext_parents)
+        env.extend_body_pos_in_parent = torch.tensor(ext_pos).repeat(env.num_envs, 1, 1)
         env.num_extend_bodies = E
         env._reset_bodies_id = torch.arange(J)
-        env._key_body_ids = torch.tensor(syn.H1_KEY_BODIES)
+        env._key_body_ids = torch.tensor(key_bodies)
         env.dof_subset, env._has_dof_subset = None, False
         env._dof_names = [f"d{i}" for i in range(D)]
         env._contact_body_ids = torch.tensor([5, 10])
@@ -479,7 +480,43 @@ def gen_h1():
     env.ref_motion_cache = {}
     d["demo_ids"], d["demo_t0"] = ids, t0
     d["demo_out"] = env.build_amp_obs_demo(ids, t0).view(16, env._num_amp_obs_steps, -1)
-    save("h1.npz", d)
+    save(name + ".npz", d)
+
+
+def gen_h1():
+    m = syn.make_robot_motions(24, seed=2, min_frames=12, max_frames=24)
+    _gen_robot("h1", m, syn.H1_EXT_PARENTS, syn.H1_EXT_POS, syn.H1_KEY_BODIES)
+
+
+def gen_g1():
+    """Unitree G1 shapes (phc/data/cfg/robot/unitree_g1.yaml: 38 bodies, 37 hinge dofs, one extend body 0.4 m above the pelvis):
+    more than 32 bodies incl. the extend body -- the case the fused step kernel does not take yet (oracle pinned ahead of it)."""
+    m = syn.make_robot_motions(12, seed=6, num_bodies=syn.G1_NUM_BODIES, num_dofs=syn.G1_NUM_DOFS, ext_parents=syn.G1_EXT_PARENTS,
+                               ext_pos=syn.G1_EXT_POS, min_frames=12, max_frames=20)
+    _gen_robot("g1", m, syn.G1_EXT_PARENTS, syn.G1_EXT_POS, syn.G1_KEY_BODIES, n_env=12)
+
+
+def gen_smplx():
+    """SMPL-X shapes (phc/data/cfg/robot/smplx_humanoid.yaml: 52 bodies, spherical joints) through the same HumanoidIm methods as
+    envstep.npz -- more than 32 bodies, not taken by the fused step kernel yet (oracle pinned ahead of it)."""
+    J = 52
+    m = syn.make_motions(8, seed=13, num_bodies=J, min_frames=12, max_frames=20)
+    A = 1 + 12 + 9 * (J - 1) + 3 * 4
+    st = syn.make_env_state(m, 8, seed=13, amp_dim=A, max_progress=16, with_offset=True, blend_jitter=True)
+    env = build_ref_env(m, st)
+    env.humanoid_type = "smplx"
+    env._reset_bodies_id = torch.arange(J)
+    env._key_body_ids = torch.tensor(syn.SMPLX_KEY_BODIES)
+    # Humanoid always holds a (possibly empty) tensor here (humanoid.py:413,:435); `None` would switch on the in-place zeroing of
+    # four SMPL joints in _compute_amp_observations (humanoid_amp.py:676-679), which no shipped configuration reaches
+    env.dof_subset, env._has_dof_subset = torch.tensor([]).long(), False
+    env._dof_names = [f"j{i}" for i in range(1, J)]
+    out = run_ref_step(env)
+    d = {f"out_{k}": v for k, v in out.items()}
+    for f in st.__dataclass_fields__:
+        d[f"in_{f}"] = getattr(st, f)
+    d.update(motion_tables_dict(m))
+    save("smplx.npz", d)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -278,3 +278,43 @@ def test_env_step_getup_zero_out_far_cycle_motion():
     for k in ("reset", "terminate"):
         close(out[k], g["out_" + k], what=f"getup {k}")
     close(out["cycle_counter"].long(), g["out_cycle_counter"].long(), what="getup cycle_counter")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Shapes with more than 32 bodies (Unitree G1: 38 + 1 extend body; SMPL-X: 52): the oracle is pinned ahead of the fused step
+# kernel, which returns PHC_ERR_UNSUPPORTED for them today (one body per lane)
+# ----------------------------------------------------------------------------------------------------------------
+def _g1_tables(g):
+    f = lambda k: g["tab_" + k]
+    return O.RobotTables(f("gts_t"), f("grs_t"), f("gvs_t"), f("gavs_t"), f("dof_pos"), f("dvs"), f("lengths"), f("num_frames"), f("dts"),
+                         f("length_starts"), 38)
+
+
+def test_g1_shapes_match_reference():
+    from phc_b200 import synthetic as syn
+    g = load("g1.npz")
+    tab = _g1_tables(g)
+    out = O.motion_state_robot(tab, g["ms_ids"], g["ms_times"], g["ms_offset"])
+    for k in ("rg_pos", "rb_rot", "body_vel", "body_ang_vel", "dof_pos", "dof_vel", "rg_pos_t", "rg_rot_t"):
+        close(out[k], g["ms_out_" + k], what="g1 motion_state " + k)
+    cfg = O.StepConfig(key_bodies=syn.G1_KEY_BODIES, reset_bodies=None, dof_subset=None)
+    for tag in ("A", "B"):
+        st = env_state_from(g, tag)
+        o = O.env_step_robot(tab, cfg, g["ext_parents"].tolist(), g["ext_pos"], st.body_state, st.dof_state, st.dof_force, st.progress,
+                             st.motion_ids, st.start_times, st.start_offsets, st.global_offset, st.amp_hist)
+        assert o["obs"].shape[1] == 1 + 15 * 38 - 3 + 24 * 38 and o["amp_obs"].shape[1] == 13 + 2 * 37 + 12
+        for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf", "ref_body_pos", "ref_body_rot", "ref_body_vel"):
+            close(o[k], g[f"{tag}_out_{k}"], atol=2e-6, what=f"g1 {tag} {k}")
+    close(O.amp_obs_demo_robot(tab, cfg, g["demo_ids"], g["demo_t0"]), g["demo_out"], what="g1 amp_obs_demo")
+
+
+def test_smplx_shapes_match_reference():
+    from phc_b200 import synthetic as syn
+    g = load("smplx.npz")
+    st = syn.EnvState(**{k: g[f"in_{k}"] for k in syn.EnvState.__dataclass_fields__})
+    cfg = O.StepConfig(key_bodies=syn.SMPLX_KEY_BODIES, reset_bodies=None, dof_subset=None)
+    o = O.env_step(tables_from(g), cfg, st.body_state, st.dof_state, st.dof_force, st.progress, st.motion_ids, st.start_times,
+                   st.start_offsets, st.global_offset, st.amp_hist)
+    assert o["obs"].shape[1] == 1 + 15 * 52 - 3 + 24 * 52
+    for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf", "ref_body_pos", "ref_body_rot", "ref_body_vel"):
+        close(o[k], g[f"out_{k}"], atol=2e-6, what=f"smplx {k}")
