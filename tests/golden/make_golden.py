@@ -520,6 +520,25 @@ def gen_smplx():
 
 
 # ------------------------------------------------------------------------------------------------
+def gen_fut():
+    """env.fut_tracks: True with numTrajSamples 3, trajSampleTimestepInv 10 -- the T = 3 future reference samples of
+    _compute_task_obs (humanoid_im.py:743-749) through compute_imitation_observations_v6 ([B, T, J*24] layout, :1308-1358), and the
+    save_buffer branch that keeps sample 0 (:856-861).  The fused kernel's T_MAX = 4 instantiation."""
+    m = syn.make_motions(24, seed=21, min_frames=30, max_frames=50)
+    st = syn.make_env_state(m, 24, seed=21, max_progress=25, with_offset=True, blend_jitter=True)
+    env = build_ref_env(m, st)
+    J = st.body_state.shape[1]
+    env._fut_tracks, env._num_traj_samples, env._traj_sample_timestep = True, 3, 1 / 10
+    env.obs_buf = torch.zeros(env.num_envs, 1 + J * 15 - 3 + 3 * J * 24)
+    out = run_ref_step(env)
+    d = {f"out_{k}": v for k, v in out.items()}
+    for f in st.__dataclass_fields__:
+        d[f"in_{f}"] = getattr(st, f)
+    d.update(motion_tables_dict(m))
+    save("fut.npz", d)
+
+
+# ------------------------------------------------------------------------------------------------
 def gen_getup():
     """env_im_getup_mcp.yaml (the configuration HumanoidImMCP trains in): zero_out_far + cycle_motion, zero_out_far_train False.
     The real HumanoidIm._compute_reward (:873-948), _compute_reset (:1117-1190 incl. the clip wrap-around :1123-1146) and

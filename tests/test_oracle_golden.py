@@ -318,3 +318,22 @@ def test_smplx_shapes_match_reference():
     assert o["obs"].shape[1] == 1 + 15 * 52 - 3 + 24 * 52
     for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf", "ref_body_pos", "ref_body_rot", "ref_body_vel"):
         close(o[k], g[f"out_{k}"], atol=2e-6, what=f"smplx {k}")
+
+
+def test_env_step_future_tracks_matches_reference():
+    """fut_tracks with 3 future samples 0.1 s apart (tests/golden/fut.npz from the real _compute_task_obs / v6)."""
+    from phc_b200 import synthetic as syn
+    g = load("fut.npz")
+    st = syn.EnvState(**{k: g[f"in_{k}"] for k in syn.EnvState.__dataclass_fields__})
+    o = O.env_step(tables_from(g), smpl_step_config(time_steps=3, traj_dt=1 / 10), st.body_state, st.dof_state, st.dof_force, st.progress,
+                   st.motion_ids, st.start_times, st.start_offsets, st.global_offset, st.amp_hist)
+    assert o["obs"].shape[1] == 358 + 3 * 576
+    for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf"):
+        close(o[k], g[f"out_{k}"], atol=2e-6, what=f"fut {k}")
+    # Reference quirk, not mirrored: under fut_tracks `self.ref_body_pos[env_ids] = ref_rb_pos[..., 0, :, :]` (humanoid_im.py:857-861)
+    # indexes the FLAT [B*T, J, 3] tensor, so every env receives env 0's first sample.  Oracle and kernel keep each env's own
+    # first sample (what the non-fut branch stores); env 0 is where the two agree.
+    for k in ("ref_body_pos", "ref_body_rot", "ref_body_vel"):
+        ref = g[f"out_{k}"]
+        assert float((ref - ref[0:1]).abs().max()) == 0.0
+        close(o[k][0], ref[0], atol=2e-6, what=f"fut {k} (env 0)")
