@@ -539,6 +539,31 @@ def gen_fut():
 
 
 # ------------------------------------------------------------------------------------------------
+def gen_reset():
+    """Reset-path pieces with the real methods: HumanoidAMP._init_amp_obs_ref (humanoid_amp.py:575-603: history slots 1..S-1 =
+    AMP observations of the reference motion at t0 - k dt) and MotionLibBase.sample_time_interval (motion_lib_base.py:414-423)
+    with the uniform numbers it draws recorded as the `phase` input."""
+    m = syn.make_motions(16, seed=8, min_frames=12, max_frames=30)
+    st = syn.make_env_state(m, 16, seed=8, max_progress=10)
+    env = build_ref_env(m, st)
+    g = torch.Generator().manual_seed(3)
+    env_ids = torch.tensor([0, 3, 4, 9, 15])
+    ids = st.motion_ids[env_ids]
+    t0 = torch.rand(5, generator=g) * m.lengths[ids]
+    t0[0] = 0.0                                          # history entirely before the clip start
+    before = env._hist_amp_obs_buf.clone()
+    env._init_amp_obs_ref(env_ids, ids, t0)
+    d = dict(env_ids=env_ids, motion_ids=ids, t0=t0, hist_before=before, hist_after=env._hist_amp_obs_buf.clone())
+    torch.manual_seed(41)
+    phase = torch.rand(ids.shape)
+    torch.manual_seed(41)
+    env._motion_lib._device = torch.device("cpu")
+    d["phase"], d["sampled_times"] = phase, env._motion_lib.sample_time_interval(ids)
+    d.update(motion_tables_dict(m))
+    save("reset.npz", d)
+
+
+# ------------------------------------------------------------------------------------------------
 def gen_getup():
     """env_im_getup_mcp.yaml (the configuration HumanoidImMCP trains in): zero_out_far + cycle_motion, zero_out_far_train False.
     The real HumanoidIm._compute_reward (:873-948), _compute_reset (:1117-1190 incl. the clip wrap-around :1123-1146) and

@@ -204,3 +204,36 @@ def test_env_step_future_tracks_vs_reference_golden():
     close(plan.terminate.cpu(), g["out_terminate"], what="fut terminate")
     close(plan.amp_obs_buf.cpu(), g["out_amp_obs_buf"], what="fut amp_obs_buf")
     close(plan.ref_body_pos.cpu()[0], g["out_ref_body_pos"][0], atol=2e-6, what="fut ref_body_pos (env 0)")
+
+
+def test_reset_path_pieces_vs_reference_golden():
+    """History initialisation of freshly reset envs (HumanoidAMP._init_amp_obs_ref) and the start-time draw
+    (MotionLibBase.sample_time_interval) against outputs of the unmodified reference (tests/golden/reset.npz)."""
+    import ctypes as C
+    from phc_b200 import _lib
+    g = load("reset.npz")
+    mlib = pack(motion_data_from(g))
+    ids, t0 = g["motion_ids"].to(DEV), g["t0"].to(DEV)
+    hist = ops.amp_obs_demo(mlib, smpl_cfg(), ids, t0, first_step=1, num_steps=9)
+    close(hist.cpu(), g["hist_after"][g["env_ids"]], rtol=1e-4, atol=2e-5, what="_init_amp_obs_ref")
+    # phc_reset_bookkeeping: start_times = trunc(phase * len / (1/30)) * (1/30) for the masked envs, counters cleared
+    lib = _lib.load()
+    n = int(ids.shape[0])
+    em = torch.zeros(n, 4, dtype=torch.int32, device=DEV)
+    _lib.check(lib.phc_env_motion_gather(C.byref(mlib.c), ids.data_ptr(), n, em.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    mask = torch.tensor([1, 1, 0, 1, 1], dtype=torch.int64, device=DEV)
+    phase = g["phase"].to(DEV).contiguous()
+    start = torch.full((n,), -1.0, device=DEV)
+    off, goff = torch.full((n,), 7.0, device=DEV), torch.full((n, 3), 7.0, device=DEV)
+    cc = torch.full((n,), 5, dtype=torch.int32, device=DEV)
+    prog = torch.full((n,), 9, dtype=torch.int64, device=DEV)
+    rst, term = torch.ones(n, dtype=torch.int64, device=DEV), torch.ones(n, dtype=torch.int64, device=DEV)
+    _lib.check(lib.phc_reset_bookkeeping(mask.data_ptr(), phase.data_ptr(), em.data_ptr(), n, start.data_ptr(), off.data_ptr(), goff.data_ptr(),
+                                         cc.data_ptr(), prog.data_ptr(), rst.data_ptr(), term.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    m = mask.bool().cpu()
+    close(start.cpu()[m], g["sampled_times"][m], rtol=0, atol=1e-6, what="sample_time_interval")
+    assert float(start.cpu()[~m][0]) == -1.0
+    assert bool((off.cpu()[m] == 0).all()) and bool((goff.cpu()[m] == 0).all()) and bool((cc.cpu()[m] == 0).all())
+    assert bool((prog.cpu()[m] == 0).all()) and bool((rst.cpu()[m] == 0).all()) and bool((term.cpu()[m] == 0).all())
+    assert float(off.cpu()[~m][0]) == 7.0 and int(prog.cpu()[~m][0]) == 9

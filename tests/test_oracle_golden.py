@@ -337,3 +337,16 @@ def test_env_step_future_tracks_matches_reference():
         ref = g[f"out_{k}"]
         assert float((ref - ref[0:1]).abs().max()) == 0.0
         close(o[k][0], ref[0], atol=2e-6, what=f"fut {k} (env 0)")
+
+
+def test_reset_path_pieces_match_reference():
+    """_init_amp_obs_ref (history slots of freshly reset envs) and sample_time_interval, tests/golden/reset.npz."""
+    g = load("reset.npz")
+    hist = O.amp_obs_demo(tables_from(g), smpl_step_config(), g["motion_ids"], g["t0"], first_step=1, num_steps=9)
+    close(hist, g["hist_after"][g["env_ids"]], rtol=1e-4, atol=2e-5, what="_init_amp_obs_ref")
+    untouched = torch.ones(g["hist_after"].shape[0], dtype=torch.bool)
+    untouched[g["env_ids"]] = False
+    assert torch.equal(g["hist_after"][untouched], g["hist_before"][untouched])
+    ln = g["tab_lengths"][g["motion_ids"]]
+    t = ((g["phase"] * ln) / (1 / 30)).long() * (1 / 30)          # the arithmetic phc_reset_bookkeeping implements
+    assert torch.equal(t, g["sampled_times"])
