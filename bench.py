@@ -414,7 +414,10 @@ def main():
             est = cpu_epoch_estimate_bounded(args.num_envs, budget_s=30.0)
             note(f"cpu baseline sample done: {est['t_epoch']:.1f} s/epoch estimated on {est['cores']} threads")
             cpu = {"value": HORIZON * args.num_envs / est["t_epoch"], "unit": "env-steps/s", "cores": est["cores"], "kind": "port",
-                   "sample": est["sample"], "ms_per_step": 1e3 * est["t_epoch"]}
+                   "sample": est["sample"], "ms_per_step": 1e3 * est["t_epoch"],
+                   # the parts of the estimate, in seconds, each already scaled to the full sizes
+                   "breakdown_s": {"rollout_step_4096_envs (env step + get_motion_state + actor/critic)": est["t_rollout_step"],
+                                   "gae_and_adv_norm_32x4096": est["t_gae"], "minibatch_update_16384_rows": est["t_minibatch"]}}
         line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": sec_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",

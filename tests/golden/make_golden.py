@@ -20,6 +20,14 @@ What is executed on the reference side (no restatement involved):
                build_amp_observations_robot through _compute_amp_observations / build_amp_obs_demo
   learn.npz    CommonAgent.discount_values/_calc_advs/_actor_loss/_critic_loss/bound_loss,
                AMPAgent._disc_loss/_calc_disc_rewards/_combine_rewards, RunningMeanStd.forward
+  load.npz     MotionLibSMPL.load_motion_with_skeleton (phc/utils/motion_lib_smpl.py:101-180): heading randomisation, poselib FK,
+               gaussian-filtered velocities, compute_motion_dof_vels -- the loader
+  getup.npz    env_im_getup_mcp.yaml: zero_out_far + cycle_motion through _compute_reward / _compute_reset / _compute_observations
+  fut.npz      fut_tracks with 3 future samples (the [B, T, J*24] layout of compute_imitation_observations_v6)
+  reset.npz    HumanoidAMP._init_amp_obs_ref, MotionLibBase.sample_time_interval
+  g1.npz, smplx.npz   the h1.npz / envstep.npz recipes at the shipped shapes beyond 32 bodies (Unitree G1 38 + 1, SMPL-X 52)
+
+  python tests/golden/make_golden.py load getup      # regenerate selected files only
 """
 import os
 import sys
@@ -684,3 +692,9 @@ if __name__ == "__main__":
     gen_motion()
     gen_envstep()
     gen_learn()
+    gen_load()
+    gen_getup()
+    gen_fut()
+    gen_reset()
+    gen_g1()
+    gen_smplx()
