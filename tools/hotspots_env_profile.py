@@ -29,7 +29,7 @@ for l in txt[start:end]:
     if m:
         cur = (os.path.basename(m.group(1)), int(m.group(2)))
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(.*?);", l)
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?);", l)
     if m:
         ins.append((m.group(1).strip(), cur))
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
