@@ -196,6 +196,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
         goff_o.y = g_state[1] - lerp1(r0[1], r1[1], omb, b.blend);
         cc = 60;
         rebased = true;
+        __syncwarp();          // every lane has read the old start / offset values before lane 0 replaces them
         if (lane == 0) {
           a.start_times[env] = t_start_o;
           a.start_offsets[env] = t_off_o;

@@ -1,0 +1,67 @@
+// TEST INFRASTRUCTURE -- a minimal host emulation of the CUDA constructs phc_b200/csrc/env_step.cu uses, so that the KERNEL
+// SOURCE ITSELF (not a restatement) can be compiled with g++ and run on the CPU against the goldens of the unmodified
+// reference (tests/test_env_step_emu_cpu.py).  One warp = 32 std::threads; warp collectives (__shfl*_sync, __any_sync,
+// __syncwarp) are barrier + exchange array (the kernel only uses them in warp-uniform code with a full mask); mbarriers are
+// two atomics (pending arrivals, pending bytes); TMA bulk copies are memcpy executed by the issuing lane.  What this checks:
+// indexing, staging / aliasing of shared memory, the bracket / dedupe logic, every arithmetic expression (with the host's libm,
+// -ffp-contract=off).  What it cannot check: alignment / async-proxy rules of the real TMA, timing, register pressure.
+#pragma once
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __restrict__
+#define __align__(x)
+#define __shared__
+
+struct EmuDim3 { unsigned x, y, z; };
+static thread_local EmuDim3 threadIdx, blockIdx;
+static thread_local int emu_lane;
+
+struct float2 { float x, y; };
+static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
+struct int4 { int x, y, z, w; };
+static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+
+struct EmuWarp {
+  std::barrier<> bar{32};
+  uint32_t xch[32];
+};
+static EmuWarp* emu_warp = nullptr;          // warps run one at a time (the kernel has no block-level synchronisation)
+
+static inline void __syncwarp() { emu_warp->bar.arrive_and_wait(); }
+template <class T>
+static inline T emu_exchange(T v, int src) {
+  static_assert(sizeof(T) == 4, "32-bit shuffles only");
+  uint32_t u;
+  std::memcpy(&u, &v, 4);
+  emu_warp->xch[emu_lane] = u;
+  emu_warp->bar.arrive_and_wait();
+  const uint32_t r = emu_warp->xch[src & 31];
+  emu_warp->bar.arrive_and_wait();
+  T o;
+  std::memcpy(&o, &r, 4);
+  return o;
+}
+static inline float __shfl_xor_sync(unsigned, float v, int o) { return emu_exchange(v, emu_lane ^ o); }
+static inline int __shfl_xor_sync(unsigned, int v, int o) { return emu_exchange(v, emu_lane ^ o); }
+static inline float __shfl_sync(unsigned, float v, int src) { return emu_exchange(v, src); }
+static inline int __shfl_sync(unsigned, int v, int src) { return emu_exchange(v, src); }
+static inline bool __any_sync(unsigned, bool p) {
+  emu_warp->xch[emu_lane] = p ? 1u : 0u;
+  emu_warp->bar.arrive_and_wait();
+  uint32_t any = 0;
+  for (int i = 0; i < 32; ++i) any |= emu_warp->xch[i];
+  emu_warp->bar.arrive_and_wait();
+  return any != 0;
+}

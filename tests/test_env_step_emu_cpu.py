@@ -1,0 +1,127 @@
+"""The fused env-step KERNEL SOURCE on the CPU: phc_b200/csrc/env_step.cu (kernel + layout helpers, verbatim), phc_math.cuh and
+the reductions of phc_common.cuh are compiled with g++ against a small emulation of the CUDA constructs they use
+(tests/emu/: one warp = 32 threads, barrier-based warp collectives, mbarrier / TMA bulk copy stand-ins) and run on the goldens
+of the UNMODIFIED reference -- the same comparisons tests/test_gpu_env_step.py / test_gpu_getup.py make on the B200, here without
+a GPU.  The arguments are assembled by the product's own ops.EnvStepPlan (on host tensors).  Tolerances as on the GPU."""
+import os
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+
+from phc_b200 import _lib, ops, synthetic as syn          # noqa: E402
+from tests.helpers import close, env_state_from, load, motion_data_from   # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    import build_emu
+    import host_plan
+    return host_plan.Emu(build_emu.build(str(tmp_path_factory.mktemp("emu")))), host_plan
+
+
+def smpl_cfg(**kw):
+    base = dict(key_bodies=syn.SMPL_KEY_BODIES, reset_bodies=syn.SMPL_RESET_BODIES, dof_subset=syn.SMPL_DOF_SUBSET)
+    base.update(kw)
+    return ops.EnvStepConfig(**base)
+
+
+def make_plan(hp, m, st, cfg, **kw):
+    mlib = hp.host_pack(m.gts, m.grs, m.gvs, m.gavs, m.lengths, m.num_frames, m.dts, m.length_starts)
+    s = st
+    with hp.host_mode():
+        return ops.EnvStepPlan(cfg, mlib, s.body_state.clone(), s.dof_state.clone(), s.dof_force.clone(), s.progress.clone(), s.motion_ids.clone(),
+                               s.start_times.clone(), s.start_offsets.clone(), s.global_offset.clone(), amp_obs_buf=s.amp_hist.clone(),
+                               with_ref_buffers=kw.pop("with_ref_buffers", True), **kw)
+
+
+def check(plan, exp, tag, ref_buffers=True):
+    close(plan.obs, exp["obs"], atol=2e-6, what=f"{tag} obs")
+    close(plan.rew, exp["rew"], what=f"{tag} rew")
+    close(plan.reward_raw, exp["reward_raw"], what=f"{tag} reward_raw")
+    close(plan.reset, exp["reset"], what=f"{tag} reset")
+    close(plan.terminate, exp["terminate"], what=f"{tag} terminate")
+    close(plan.amp_obs_buf, exp["amp_obs_buf"], what=f"{tag} amp_obs_buf")
+    if ref_buffers:
+        for k in ("ref_body_pos", "ref_body_rot", "ref_body_vel"):
+            close(getattr(plan, k), exp[k], what=f"{tag} {k}")
+
+
+@pytest.mark.parametrize("tag,in_tag,kw", [("A", "A", {}), ("B", "B", {}), ("C", "A", dict(upright=False, local_root_obs=False)),
+                                            ("D", "B", dict(term_use_mean=True))])
+def test_kernel_source_vs_reference_golden(emu, tag, in_tag, kw):
+    e, hp = emu
+    g = load("envstep.npz")
+    plan = make_plan(hp, motion_data_from(g), env_state_from(g, in_tag), smpl_cfg(**kw))
+    e.run(plan, "smpl")
+    check(plan, {k: g[f"{tag}_out_{k}"] for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf", "ref_body_pos", "ref_body_rot", "ref_body_vel")}, tag)
+
+
+def test_generic_instantiation_matches_too(emu):
+    e, hp = emu
+    g = load("envstep.npz")
+    plan = make_plan(hp, motion_data_from(g), env_state_from(g, "B"), smpl_cfg())
+    e.run(plan, "generic")
+    check(plan, {k: g[f"B_out_{k}"] for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf", "ref_body_pos", "ref_body_rot", "ref_body_vel")}, "B generic")
+
+
+def test_future_tracks_instantiation(emu):
+    e, hp = emu
+    g = load("fut.npz")
+    st = syn.EnvState(**{k: g[f"in_{k}"] for k in syn.EnvState.__dataclass_fields__})
+    plan = make_plan(hp, motion_data_from(g), st, smpl_cfg(time_steps=3, traj_dt=1 / 10))
+    e.run(plan, "fut")
+    check(plan, {k: g[f"out_{k}"] for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf")}, "fut", ref_buffers=False)
+    close(plan.ref_body_pos[0], g["out_ref_body_pos"][0], what="fut ref_body_pos env 0")
+
+
+def test_getup_instantiation_vs_reference_golden(emu):
+    e, hp = emu
+    g = load("getup.npz")
+    st = syn.EnvState(**{k: g[f"in_{k}"] for k in syn.EnvState.__dataclass_fields__})
+    pg, cc, ph = g["in_point_goal"].clone(), g["in_cycle_counter"].to(torch.int32).clone(), g["in_cycle_phase"].clone()
+    plan = make_plan(hp, motion_data_from(g), st, smpl_cfg(zero_out_far=True, cycle_motion=True, max_episode_length=15), point_goal=pg,
+                     cycle_counter=cc, cycle_phase=ph)
+    e.run(plan, "getup")
+    exp = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    check(plan, exp, "getup")
+    k = plan._keep
+    close(k["start_times"], exp["start_times"], what="getup start_times")
+    close(k["start_offsets"], exp["start_offsets"], what="getup start_offsets")
+    close(k["global_offset"], exp["global_offset"], what="getup global_offset")
+    close(pg, exp["point_goal"], what="getup point_goal")
+    assert torch.equal(cc.long(), exp["cycle_counter"].long())
+
+
+def test_specialised_instantiation_and_pose_cache(emu):
+    """Two consecutive steps through the pose cache: step 1 (generic, fills the cache with the pose interpolated for its
+    observation), step 2 through the FAST instantiation (reward pose from the cache, ring slot, bulk rows) against the generic
+    instantiation without cache on the same inputs -- the arithmetic is the same source, so the results agree to rounding."""
+    e, hp = emu
+    n = 12
+    m = syn.make_motions(n, seed=5, min_frames=30, max_frames=50)
+    st = syn.make_env_state(m, n, seed=5, max_progress=20)
+    bs = hp.round4(13 * 24)
+    cache = torch.zeros(n, bs)
+    warm = make_plan(hp, m, st, smpl_cfg(), with_ref_buffers=False, ref_cache=cache)
+    e.run(warm, "smpl")                                         # cache := pose at (progress + 1) dt
+    st2 = syn.EnvState(**{**{k: getattr(st, k) for k in st.__dataclass_fields__}, "progress": st.progress + 1})
+    ref_plan = make_plan(hp, m, st2, smpl_cfg())
+    e.run(ref_plan, "smpl")
+    fast = make_plan(hp, m, st2, smpl_cfg(), with_ref_buffers=False, ref_cache=cache.clone(), reward_from_cache=True, amp_ring=True)
+    fast.advance_ring()
+    assert fast.args.flags == e.lib.emu_fast_flags()
+    e.run(fast, "fast")
+    close(fast.obs, ref_plan.obs, atol=2e-6, what="fast obs")
+    close(fast.rew, ref_plan.rew, what="fast rew")
+    close(fast.reward_raw, ref_plan.reward_raw, what="fast reward_raw")
+    assert torch.equal(fast.reset, ref_plan.reset) and torch.equal(fast.terminate, ref_plan.terminate)
+    close(fast.amp_obs_buf[:, fast.ring_head], ref_plan.amp_obs_buf[:, 0], what="fast AMP ring slot")
+    close(fast.ref_cache[:, :13 * 24].view(n, 24, 13)[..., 0:3], ref_plan.ref_body_pos, what="fast pose cache")
+    assert float(fast.obs_full_row_pad_max if hasattr(fast, "obs_full_row_pad_max") else 0.0) == 0.0
