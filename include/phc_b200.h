@@ -176,8 +176,10 @@ PHC_API int phc_motion_state(const PhcMotionLib* lib, const int64_t* motion_ids,
                                              wrap-around of _compute_reset (:1120-1146); pass_time = progress >= max_len - 1 */
 
 #define PHC_MAX_KEY_BODIES 8
-#define PHC_MAX_BODIES 32      /* one body per lane in the fused step kernel */
-#define PHC_MAX_AMP_JOINTS 32
+#define PHC_MAX_BODIES 64      /* J + E; up to PHC_LANE_BODIES the staged one-body-per-lane kernels run, beyond it the strided
+                                  ones (env_step_wide.cu: Unitree G1 38 + 1, SMPL-X 52) */
+#define PHC_LANE_BODIES 32
+#define PHC_MAX_AMP_JOINTS 64
 
 typedef struct PhcStepArgs {
   /* ---- simulator state (inputs; contract of Humanoid._setup_tensors, humanoid.py:179-247) ---- */

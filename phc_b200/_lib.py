@@ -26,8 +26,9 @@ PHC_FLAG_CYCLE_MOTION = 1 << 10
 PHC_FLAG_NO_SPECIALISE = 1 << 11
 PHC_ACT_NONE, PHC_ACT_RELU, PHC_ACT_SILU, PHC_ACT_SILU_BWD = 0, 1, 2, 3
 PHC_MAX_KEY_BODIES = 8
-PHC_MAX_BODIES = 32
-PHC_MAX_AMP_JOINTS = 32
+PHC_MAX_BODIES = 64
+PHC_LANE_BODIES = 32
+PHC_MAX_AMP_JOINTS = 64
 PHC_MAX_EXT_BODIES = 8
 
 _p = C.c_void_p

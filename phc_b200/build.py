@@ -28,7 +28,9 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 SOURCES = {
     "phc_api.cu": [],
     "env_step.cu": ["-fmad=false"] if os.environ.get("PHC_ENV_FMAD", "1") == "0" else [],
+    "env_step_wide.cu": [],
     "motion.cu": ["-fmad=false"],
+    "motion_wide.cu": ["-fmad=false"],
     "motion_load.cu": ["-fmad=false"],
     "ppo_scalars.cu": ["-fmad=false"],
     "gemm.cu": [],

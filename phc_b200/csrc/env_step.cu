@@ -583,6 +583,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
 extern "C" void phc_set_error(const char* msg);   // phc_api.cu
 extern "C" int phc_check_cuda(cudaError_t e, const char* what);
 extern "C" void phc_count_launches(int n);
+extern "C" int phc_env_step_wide_launch(const PhcStepArgs* a, int obs_dim, int self_dim, int amp_dim, void* stream);   // env_step_wide.cu
 
 extern "C" int phc_self_obs_dim(int32_t J, uint32_t flags) {
   return ((flags & PHC_FLAG_ROOT_HEIGHT_OBS) ? 1 : 0) + 15 * J - 3;
@@ -616,7 +617,8 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
   }
   const int E = a->lib.num_ext_bodies, DR = a->lib.num_dofs;
   if (E < 0 || E > PHC_MAX_EXT_BODIES || DR < 0) { phc_set_error("phc_env_step: bad num_ext_bodies / num_dofs"); return PHC_ERR_INVALID_ARG; }
-  if (J + E > PHC_MAX_BODIES || DR > 3 * 32) { phc_set_error("phc_env_step: more than 32 bodies (incl. extend bodies) needs the multi-body-per-lane path (not built yet)"); return PHC_ERR_UNSUPPORTED; }
+  if (J + E > PHC_MAX_BODIES) { phc_set_error("phc_env_step: more than PHC_MAX_BODIES bodies (incl. extend bodies)"); return PHC_ERR_UNSUPPORTED; }
+  const bool wide = J + E > PHC_LANE_BODIES || DR > 3 * PHC_LANE_BODIES;      // strided kernel of env_step_wide.cu
   for (int e2 = 0; e2 < E; ++e2)
     if (a->ext_parent[e2] < 0 || a->ext_parent[e2] >= J) { phc_set_error("phc_env_step: ext_parent out of range"); return PHC_ERR_INVALID_ARG; }
   if (T > 4) { phc_set_error("phc_env_step: time_steps > 4 not supported"); return PHC_ERR_UNSUPPORTED; }
@@ -646,6 +648,7 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
   if (a->amp_out && (a->amp_steps < 1 || a->amp_out_stride < (int64_t)(a->amp_hist_in ? a->amp_steps : 1) * amp_dim)) {
     phc_set_error("phc_env_step: amp_out_stride / amp_steps inconsistent"); return PHC_ERR_INVALID_ARG;
   }
+  if (wide) return phc_env_step_wide_launch(a, obs_dim, self_dim, amp_dim, stream);
   // the obs row is staged over [reward slots | simulator block] when it fits (always for T == 1)
   const bool alias_obs = (2 * a->lib.body_stride + round4(J * kBodyRec) >= round4(obs_dim));   // incl. the row pad
   const bool obs_row_aligned = ((reinterpret_cast<uintptr_t>(a->obs) & 7) == 0);

@@ -10,14 +10,13 @@
 #include "../../include/phc_b200.h"
 #include "phc_common.cuh"
 #include "phc_math.cuh"
+#include "motion_sample.cuh"
 
 extern "C" void phc_set_error(const char* msg);
 extern "C" int phc_check_cuda(cudaError_t e, const char* what);
 extern "C" void phc_count_launches(int n);
 
 namespace phc {
-
-constexpr int kRec = 13;
 
 __global__ void motion_pack_kernel(const float* __restrict__ gts, const float* __restrict__ grs,
                                    const float* __restrict__ gvs, const float* __restrict__ gavs,
@@ -61,59 +60,6 @@ __global__ void motion_pack_dofs_kernel(const float* __restrict__ dof_pos, const
     fj[i] = c < D ? dof_pos[f * D + c] : (c < 2 * D ? dof_vel[f * D + (c - D)] : 0.0f);
   }
 }
-
-struct BodyS { V3 p; Q4 q; V3 v; V3 w; };
-__device__ __forceinline__ BodyS ld_body(const float* s) {
-  BodyS b;
-  b.p = v3(s[0], s[1], s[2]); b.q = q4(s[3], s[4], s[5], s[6]); b.v = v3(s[7], s[8], s[9]); b.w = v3(s[10], s[11], s[12]);
-  return b;
-}
-
-// One reference-motion sample for lane `j`: blended body record + joint (dof) position/velocity of joint j-1.
-struct MotionSample { BodyS body; V3 dof_pos; V3 dof_vel; };
-
-__device__ __forceinline__ MotionSample sample_motion(const PhcMotionLib& lib, int64_t mid, float time, V3 off, int j,
-                                                      bool want_joint) {
-  const Bracket b = frame_bracket(time, lib.motion_len[mid], lib.motion_num_frames[mid], lib.motion_dt[mid]);
-  const int64_t r0 = lib.length_starts[mid] + b.i0, r1 = lib.length_starts[mid] + b.i1;
-  const float bl = b.blend, omb = 1.0f - bl;
-  const int jb = j < lib.num_bodies + lib.num_ext_bodies ? j : 0;     // lanes that only carry a dof read body 0 (unused)
-  const BodyS a0 = ld_body(lib.frames_body + r0 * lib.body_stride + jb * kRec);
-  const BodyS a1 = ld_body(lib.frames_body + r1 * lib.body_stride + jb * kRec);
-  MotionSample s;
-  s.body.p = lerp3(a0.p, a1.p, omb, bl) + off;
-  s.body.v = lerp3(a0.v, a1.v, omb, bl);
-  s.body.w = lerp3(a0.w, a1.w, omb, bl);
-  s.body.q = slerp(a0.q, a1.q, bl);
-  s.dof_pos = v3(0.f, 0.f, 0.f);
-  s.dof_vel = v3(0.f, 0.f, 0.f);
-  if (want_joint && lib.frames_joint && lib.num_dofs > 0) {
-    // hinge-joint robot: lane j carries dof j; dof_pos and dof_vel are both interpolated linearly (motion_lib_real.py:283-285)
-    if (j < lib.num_dofs) {
-      const float* j0 = lib.frames_joint + r0 * lib.joint_stride;
-      const float* j1 = lib.frames_joint + r1 * lib.joint_stride;
-      s.dof_pos.x = lerp1(j0[j], j1[j], omb, bl);
-      s.dof_vel.x = lerp1(j0[lib.num_dofs + j], j1[lib.num_dofs + j], omb, bl);
-    }
-  } else if (want_joint && lib.frames_joint) {
-    const int J = lib.num_bodies;
-    const float* j0 = lib.frames_joint + r0 * lib.joint_stride;
-    const float* j1 = lib.frames_joint + r1 * lib.joint_stride;
-    const Q4 l0 = q4(j0[4 * j], j0[4 * j + 1], j0[4 * j + 2], j0[4 * j + 3]);
-    const Q4 l1 = q4(j1[4 * j], j1[4 * j + 1], j1[4 * j + 2], j1[4 * j + 3]);
-    const Q4 lq = slerp(l0, l1, bl);
-    if (j > 0) {
-      s.dof_pos = quat_to_exp_map(lq);
-      const float* d0 = j0 + 4 * J + 3 * (j - 1);
-      const float* d1 = j1 + 4 * J + 3 * (j - 1);
-      s.dof_vel = lerp3(v3(d0[0], d0[1], d0[2]), v3(d1[0], d1[1], d1[2]), omb, bl);
-    }
-  }
-  return s;
-}
-
-__device__ __forceinline__ void st3g(float* d, V3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
-__device__ __forceinline__ void st4g(float* d, Q4 q) { d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w; }
 
 __global__ void __launch_bounds__(128)
 motion_state_kernel(const __grid_constant__ PhcMotionLib lib, const int64_t* __restrict__ ids,
@@ -369,10 +315,23 @@ static int check_lib(const PhcMotionLib* lib, const char* who) {
                                                                      : phc_motion_joint_stride(lib->num_bodies)))) {
     phc_set_error("motion library strides do not match num_bodies / num_ext_bodies / num_dofs (use phc_motion_pack[_dofs])"); return PHC_ERR_INVALID_ARG;
   }
-  if (lib->num_bodies + lib->num_ext_bodies > 32 || lib->num_dofs > 32) { phc_set_error("more than 32 bodies (incl. extend bodies) or hinge dofs: not supported yet"); return PHC_ERR_UNSUPPORTED; }
+  if (lib->num_bodies + lib->num_ext_bodies > PHC_MAX_BODIES || lib->num_dofs > 2 * PHC_MAX_BODIES) {
+    phc_set_error("more than PHC_MAX_BODIES bodies (incl. extend bodies) or 2 * PHC_MAX_BODIES hinge dofs"); return PHC_ERR_UNSUPPORTED;
+  }
   (void)who;
   return PHC_OK;
 }
+// more than one body (or hinge dof) per lane: the strided kernels of motion_wide.cu
+static bool is_wide(const PhcMotionLib* lib) { return lib->num_bodies + lib->num_ext_bodies > PHC_LANE_BODIES || lib->num_dofs > PHC_LANE_BODIES; }
+extern "C" int phc_motion_state_wide_launch(const PhcMotionLib* lib, const int64_t* ids, const float* times, const float* offset,
+                                            int64_t n, const PhcMotionStateOut* out, void* stream);
+extern "C" int phc_amp_obs_demo_wide_launch(const PhcMotionLib* lib, const int64_t* ids, const float* times0, int64_t n, int32_t first_step,
+                                            int32_t num_steps, float dt, uint32_t flags, const int32_t* key_bodies, int32_t nk,
+                                            const int32_t* amp_joints, int32_t nj, float* out, int64_t out_stride,
+                                            const int64_t* only_where, int32_t slot_offset, void* stream);
+extern "C" int phc_set_env_state_wide_launch(const PhcMotionLib* lib, const int64_t* ids, const float* times, const float* offset,
+                                             const int64_t* only_where, int64_t n, float* body_state, int32_t bodies_per_env,
+                                             float* dof_state, void* stream);
 
 extern "C" int phc_motion_state(const PhcMotionLib* lib, const int64_t* ids, const float* times, const float* offset,
                                 int64_t n, const PhcMotionStateOut* out, void* stream) {
@@ -381,6 +340,7 @@ extern "C" int phc_motion_state(const PhcMotionLib* lib, const int64_t* ids, con
   if (!ids || !times || !out || n < 0) { phc_set_error("phc_motion_state: bad arguments"); return PHC_ERR_INVALID_ARG; }
   if ((out->dof_pos || out->dof_vel) && !lib->frames_joint) { phc_set_error("phc_motion_state: dof outputs need frames_joint"); return PHC_ERR_INVALID_ARG; }
   if (n == 0) return PHC_OK;
+  if (is_wide(lib)) return phc_motion_state_wide_launch(lib, ids, times, offset, n, out, stream);
   const int wpb = 4;
   const int64_t grid = (n + wpb - 1) / wpb;
   phc::motion_state_kernel<<<(unsigned)grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(*lib, ids, times, offset, n, *out); phc_count_launches(1);
@@ -400,6 +360,8 @@ extern "C" int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* ids, con
   const int A = lib->num_dofs > 0 ? phc_amp_obs_dim_robot(lib->num_dofs, nk, flags) : phc_amp_obs_dim(nj, nk, flags);
   if (out_stride < (int64_t)num_steps * A) { phc_set_error("phc_amp_obs_demo: out_stride too small"); return PHC_ERR_INVALID_ARG; }
   if (n == 0) return PHC_OK;
+  if (is_wide(lib)) return phc_amp_obs_demo_wide_launch(lib, ids, times0, n, first_step, num_steps, dt, flags, key_bodies, nk, amp_joints, nj, out,
+                                                         out_stride, only_where, slot_offset, stream);
   phc::AmpDemoArgs a;
   a.lib = *lib; a.ids = ids; a.times0 = times0; a.n = n; a.first_step = first_step; a.num_steps = num_steps; a.dt = dt;
   a.flags = flags; a.num_key_bodies = nk; a.num_amp_joints = nj;
@@ -420,6 +382,7 @@ extern "C" int phc_set_env_state(const PhcMotionLib* lib, const int64_t* ids, co
   if (!ids || !times || !body_state || n < 0 || bodies_per_env < lib->num_bodies) { phc_set_error("phc_set_env_state: bad arguments"); return PHC_ERR_INVALID_ARG; }
   if (dof_state && !lib->frames_joint) { phc_set_error("phc_set_env_state: dof_state needs frames_joint"); return PHC_ERR_INVALID_ARG; }
   if (n == 0) return PHC_OK;
+  if (is_wide(lib)) return phc_set_env_state_wide_launch(lib, ids, times, offset, only_where, n, body_state, bodies_per_env, dof_state, stream);
   const int wpb = 4;
   phc::set_env_state_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       *lib, ids, times, offset, only_where, n, body_state, bodies_per_env, dof_state); phc_count_launches(1);

@@ -2,8 +2,8 @@
 
 The translation unit is: the emulation prelude (tests/emu/cuda_emu_prelude.h, phc_common_emu.cuh) + `warp_sum` / `warp_sum4`
 cut verbatim out of phc_b200/csrc/phc_common.cuh + include/phc_b200.h + phc_b200/csrc/phc_math.cuh + the `namespace phc { ... }`
-part of phc_b200/csrc/env_step.cu (layout helpers and `env_step_kernel`, verbatim) + a launcher that runs one warp (32
-std::threads) per env.  Nothing of the kernel is restated here."""
+part of phc_b200/csrc/env_step.cu (layout helpers and `env_step_kernel`, verbatim) + the same part of env_step_wide.cu (the strided kernel for more than 32 bodies)
++ a launcher that runs one warp (32 std::threads) per env.  Nothing of the kernel is restated here."""
 import os
 import re
 import shutil
@@ -42,6 +42,22 @@ extern "C" int emu_env_step(const PhcStepArgs* a, int obs_dim, int self_dim, int
     case 3: emu_launch<1, 0, false, false>(*a, obs_dim, self_dim, amp_dim, alias_obs, state_bulk_ok); return 0;
     case 4: emu_launch<4, 0, false, false>(*a, obs_dim, self_dim, amp_dim, alias_obs, state_bulk_ok); return 0;
     case 5: emu_launch<1, 0, true, false>(*a, obs_dim, self_dim, amp_dim, alias_obs, state_bulk_ok); return 0;
+    case 6:      // env_step_wide.cu: strided bodies, no staging
+      for (int env = 0; env < a->num_envs; ++env) {
+        EmuWarp warp;
+        emu_warp = &warp;
+        std::vector<std::thread> lanes;
+        for (int lane = 0; lane < 32; ++lane)
+          lanes.emplace_back([&, lane] {
+            emu_lane = lane;
+            threadIdx.x = (unsigned)((env % phc::wide::kWarps) * 32 + lane); threadIdx.y = threadIdx.z = 0;
+            blockIdx.x = (unsigned)(env / phc::wide::kWarps); blockIdx.y = blockIdx.z = 0;
+            phc::wide::env_step_wide_kernel(*a, obs_dim, self_dim, amp_dim);
+          });
+        for (auto& t : lanes) t.join();
+      }
+      emu_warp = nullptr;
+      return 0;
   }
   return -1;
 }
@@ -59,11 +75,110 @@ def assemble() -> str:
     k1 = step.index("}  // namespace phc") + len("}  // namespace phc")
     kernel = step[k0:k1]
     assert "env_step_kernel(" in kernel and "<<<" not in kernel
+    w = open(os.path.join(CSRC, "env_step_wide.cu")).read()
+    w0 = w.index("namespace phc {")
+    w1 = w.index("}  // namespace phc") + len("}  // namespace phc")
+    wide = w[w0:w1]
+    assert "env_step_wide_kernel(" in wide and "<<<" not in wide
     return "\n".join([
         '#include "cuda_emu_prelude.h"', '#include "phc_common_emu.cuh"',
         "namespace phc {", reductions, "}",
         f'#include "{os.path.join(ROOT, "include", "phc_b200.h")}"', f'#include "{os.path.join(CSRC, "phc_math.cuh")}"',
-        kernel, LAUNCHER])
+        kernel, wide, LAUNCHER])
+
+
+MOTION_LAUNCHER = r'''
+template <class F>
+static void emu_warps(int64_t n_warps, F&& body) {      // one warp (32 threads) at a time, 4 warps per block like the launches
+  for (int64_t w = 0; w < n_warps; ++w) {
+    EmuWarp warp;
+    emu_warp = &warp;
+    std::vector<std::thread> lanes;
+    for (int lane = 0; lane < 32; ++lane)
+      lanes.emplace_back([&, lane] {
+        emu_lane = lane;
+        blockDim.x = 128; blockDim.y = blockDim.z = 1;
+        threadIdx.x = (unsigned)((w % 4) * 32 + lane); threadIdx.y = threadIdx.z = 0;
+        blockIdx.x = (unsigned)(w / 4); blockIdx.y = blockIdx.z = 0;
+        body();
+      });
+    for (auto& t : lanes) t.join();
+  }
+  emu_warp = nullptr;
+}
+
+extern "C" int emu_motion_state(const PhcMotionLib* lib, const int64_t* ids, const float* times, const float* offset, int64_t n,
+                                const PhcMotionStateOut* out, int wide) {
+  if (wide) emu_warps(n, [&] { phc::wide::motion_state_wide_kernel(*lib, ids, times, offset, n, *out); });
+  else emu_warps(n, [&] { phc::motion_state_kernel(*lib, ids, times, offset, n, *out); });
+  return 0;
+}
+
+extern "C" int emu_amp_obs_demo(const PhcMotionLib* lib, const int64_t* ids, const float* times0, int64_t n, int32_t first_step,
+                                int32_t num_steps, float dt, uint32_t flags, const int32_t* key_bodies, int32_t nk,
+                                const int32_t* amp_joints, int32_t nj, float* out, int64_t out_stride, const int64_t* only_where,
+                                int32_t slot_offset, int wide) {
+  const int32_t so = ((slot_offset % num_steps) + num_steps) % num_steps;
+  if (wide) {
+    phc::wide::AmpDemoWideArgs a;
+    a.lib = *lib; a.ids = ids; a.times0 = times0; a.n = n; a.first_step = first_step; a.num_steps = num_steps; a.dt = dt;
+    a.flags = flags; a.num_key_bodies = nk; a.num_amp_joints = nj; a.out = out; a.out_stride = out_stride; a.only_where = only_where;
+    for (int i = 0; i < PHC_MAX_AMP_JOINTS; ++i) a.amp_joints[i] = i < nj ? amp_joints[i] : -1;
+    for (int i = 0; i < PHC_MAX_KEY_BODIES; ++i) a.key_bodies[i] = i < nk ? key_bodies[i] : -1;
+    a.slot_offset = so;
+    emu_warps(n * num_steps, [&] { phc::wide::amp_demo_wide_kernel(a); });
+  } else {
+    phc::AmpDemoArgs a;
+    a.lib = *lib; a.ids = ids; a.times0 = times0; a.n = n; a.first_step = first_step; a.num_steps = num_steps; a.dt = dt;
+    a.flags = flags; a.num_key_bodies = nk; a.num_amp_joints = nj; a.out = out; a.out_stride = out_stride; a.only_where = only_where;
+    for (int i = 0; i < PHC_MAX_AMP_JOINTS; ++i) a.amp_joints[i] = i < nj ? amp_joints[i] : -1;
+    for (int i = 0; i < PHC_MAX_KEY_BODIES; ++i) a.key_bodies[i] = i < nk ? key_bodies[i] : -1;
+    a.slot_offset = so;
+    emu_warps(n * num_steps, [&] { phc::amp_demo_kernel(a); });
+  }
+  return 0;
+}
+
+extern "C" int emu_set_env_state(const PhcMotionLib* lib, const int64_t* ids, const float* times, const float* offset,
+                                 const int64_t* only_where, int64_t n, float* body_state, int32_t bpe, float* dof_state, int wide) {
+  if (wide) emu_warps(n, [&] { phc::wide::set_env_state_wide_kernel(*lib, ids, times, offset, only_where, n, body_state, bpe, dof_state); });
+  else emu_warps(n, [&] { phc::set_env_state_kernel(*lib, ids, times, offset, only_where, n, body_state, bpe, dof_state); });
+  return 0;
+}
+'''
+
+
+def assemble_motion() -> str:
+    """motion.cu (lane-per-body kernels) + motion_wide.cu (strided kernels) + the shared motion_sample.cuh, verbatim."""
+    def kernels(fname):
+        t = open(os.path.join(CSRC, fname)).read()
+        k0 = t.index("namespace phc {")
+        k1 = t.index("}  // namespace phc") + len("}  // namespace phc")
+        body = t[k0:k1]
+        assert "<<<" not in body
+        return body
+    m = kernels("motion.cu")
+    # the pack / gather / bookkeeping / export kernels use plain thread indexing (no warp structure): not emulated here
+    return "\n".join([
+        '#include "cuda_emu_prelude.h"', '#include "phc_common_emu.cuh"',
+        f'#include "{os.path.join(ROOT, "include", "phc_b200.h")}"', f'#include "{os.path.join(CSRC, "phc_math.cuh")}"',
+        f'#include "{os.path.join(CSRC, "motion_sample.cuh")}"',
+        m, kernels("motion_wide.cu"), MOTION_LAUNCHER])
+
+
+def build_motion(out_dir: str) -> str:
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    src = os.path.join(out_dir, "motion_emu.cpp")
+    with open(src, "w") as f:
+        f.write(assemble_motion())
+    so = os.path.join(out_dir, "libmotion_emu.so")
+    r = subprocess.run([gxx, "-O1", "-std=c++20", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I" + HERE, src, "-o", so, "-lm"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("motion emulation build failed:\n" + r.stderr[:6000])
+    return so
 
 
 def build(out_dir: str) -> str:
@@ -85,3 +200,4 @@ if __name__ == "__main__":
     import tempfile
     d = tempfile.mkdtemp()
     print(build(d))
+    print(build_motion(d))

@@ -25,12 +25,13 @@
 #define __shared__
 
 struct EmuDim3 { unsigned x, y, z; };
-static thread_local EmuDim3 threadIdx, blockIdx;
+static thread_local EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
 static thread_local int emu_lane;
 
 struct float2 { float x, y; };
 static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
 struct int4 { int x, y, z, w; };
+struct float4 { float x, y, z, w; };
 static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
 
 struct EmuWarp {

@@ -125,3 +125,68 @@ def test_specialised_instantiation_and_pose_cache(emu):
     close(fast.amp_obs_buf[:, fast.ring_head], ref_plan.amp_obs_buf[:, 0], what="fast AMP ring slot")
     close(fast.ref_cache[:, :13 * 24].view(n, 24, 13)[..., 0:3], ref_plan.ref_body_pos, what="fast pose cache")
     assert float(fast.obs_full_row_pad_max if hasattr(fast, "obs_full_row_pad_max") else 0.0) == 0.0
+
+
+# ---- env_step_wide.cu: the strided kernel for more than 32 bodies (and, as a cross-check, for the 24-body goldens) ----------
+@pytest.mark.parametrize("tag,in_tag,kw", [("A", "A", {}), ("B", "B", {}), ("C", "A", dict(upright=False, local_root_obs=False)),
+                                            ("D", "B", dict(term_use_mean=True))])
+def test_wide_kernel_on_the_24_body_goldens(emu, tag, in_tag, kw):
+    e, hp = emu
+    g = load("envstep.npz")
+    plan = make_plan(hp, motion_data_from(g), env_state_from(g, in_tag), smpl_cfg(**kw))
+    e.run(plan, "wide")
+    check(plan, {k: g[f"{tag}_out_{k}"] for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf", "ref_body_pos", "ref_body_rot", "ref_body_vel")}, f"wide {tag}")
+
+
+def test_wide_kernel_smplx_52_bodies_vs_reference_golden(emu):
+    e, hp = emu
+    g = load("smplx.npz")
+    st = syn.EnvState(**{k: g[f"in_{k}"] for k in syn.EnvState.__dataclass_fields__})
+    cfg = ops.EnvStepConfig(key_bodies=syn.SMPLX_KEY_BODIES, reset_bodies=None, dof_subset=None)
+    plan = make_plan(hp, motion_data_from(g), st, cfg)
+    assert plan.obs.shape[1] == 1 + 15 * 52 - 3 + 24 * 52
+    e.run(plan, "wide")
+    check(plan, {k: g[f"out_{k}"] for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf", "ref_body_pos", "ref_body_rot", "ref_body_vel")}, "smplx")
+
+
+def test_wide_kernel_g1_39_bodies_vs_reference_golden(emu):
+    e, hp = emu
+    g = load("g1.npz")
+    f = lambda k: g["tab_" + k]
+    cfg = ops.EnvStepConfig(key_bodies=syn.G1_KEY_BODIES, reset_bodies=None, dof_subset=None, ext_parents=syn.G1_EXT_PARENTS, ext_pos=syn.G1_EXT_POS)
+    for tag in ("A", "B"):
+        st = syn.EnvState(**{k: g[f"{tag}_in_{k}"] for k in syn.EnvState.__dataclass_fields__})
+        mlib = hp.host_pack(f("gts_t"), f("grs_t"), f("gvs_t"), f("gavs_t"), f("lengths"), f("num_frames"), f("dts"), f("length_starts"),
+                            num_ext=1, num_dofs=syn.G1_NUM_DOFS)
+        with hp.host_mode():
+            plan = ops.EnvStepPlan(cfg, mlib, st.body_state.clone(), st.dof_state.clone(), st.dof_force.clone(), st.progress.clone(),
+                                   st.motion_ids.clone(), st.start_times.clone(), st.start_offsets.clone(), st.global_offset.clone(),
+                                   amp_obs_buf=st.amp_hist.clone(), with_ref_buffers=True)
+        assert plan.obs.shape[1] == 1 + 15 * 38 - 3 + 24 * 38 and plan.amp_dim == 13 + 2 * 37 + 12
+        e.run(plan, "wide")
+        check(plan, {k: g[f"{tag}_out_{k}"] for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf", "ref_body_pos", "ref_body_rot", "ref_body_vel")}, f"g1 {tag}")
+
+
+def test_wide_kernel_pose_cache_and_obs_only(emu):
+    """Pose cache through the wide kernel (step 1 fills it, step 2 reads the reward pose from it) and the masked observation-only
+    launch of the reset path, against the same kernel without cache / mask."""
+    e, hp = emu
+    g = load("smplx.npz")
+    st = syn.EnvState(**{k: g[f"in_{k}"] for k in syn.EnvState.__dataclass_fields__})
+    m = motion_data_from(g)
+    n, J = st.body_state.shape[0], 52
+    cfg = ops.EnvStepConfig(key_bodies=syn.SMPLX_KEY_BODIES, reset_bodies=None, dof_subset=None)
+    cache = torch.zeros(n, hp.round4(13 * J))
+    e.run(make_plan(hp, m, st, cfg, with_ref_buffers=False, ref_cache=cache), "wide")
+    st2 = syn.EnvState(**{**{k: getattr(st, k) for k in st.__dataclass_fields__}, "progress": st.progress + 1})
+    plain = make_plan(hp, m, st2, cfg)
+    e.run(plain, "wide")
+    cached = make_plan(hp, m, st2, cfg, with_ref_buffers=False, ref_cache=cache, reward_from_cache=True)
+    e.run(cached, "wide")
+    for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf"):
+        assert torch.equal(getattr(cached, k), getattr(plain, k)), k            # same source, same operands: bit-identical
+    mask = torch.zeros(n, dtype=torch.int64)
+    mask[1::3] = 1
+    only = make_plan(hp, m, st2, cfg, obs=torch.full_like(plain.obs, 7.0).contiguous(), only_where=mask, obs_only=True, with_amp=False)
+    e.run(only, "wide")
+    assert torch.equal(only.obs[mask.bool()], plain.obs[mask.bool()]) and bool((only.obs[~mask.bool()] == 7.0).all())

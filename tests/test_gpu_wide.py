@@ -1,0 +1,51 @@
+"""GPU parity of the strided kernels for more than 32 bodies (env_step_wide.cu, motion_wide.cu): Unitree G1 (38 + 1 bodies, 37
+hinge dofs) and SMPL-X (52 bodies) against the goldens of the unmodified reference.
+
+OPT-IN (PHC_TEST_WIDE=1): these kernels were written after this round's GPU budget was spent; they are validated against the
+same goldens through the CPU emulation of their source (tests/test_env_step_emu_cpu.py, tests/test_motion_emu_cpu.py) and
+have not run on hardware yet.  The first GPU session runs this file and then drops the switch."""
+import os
+
+import pytest
+import torch
+
+from phc_b200 import ops, synthetic as syn
+from tests.helpers import close, load, motion_data_from
+from tests.test_gpu_env_step import check_against, run_cuda_step
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("PHC_TEST_WIDE", "0") != "1", reason="opt-in: PHC_TEST_WIDE=1 (not yet run on hardware)")]
+DEV = "cuda:0"
+KEYS = ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf", "ref_body_pos", "ref_body_rot", "ref_body_vel")
+
+
+def test_smplx_env_step_vs_reference_golden():
+    g = load("smplx.npz")
+    st = syn.EnvState(**{k: g[f"in_{k}"] for k in syn.EnvState.__dataclass_fields__})
+    cfg = ops.EnvStepConfig(key_bodies=syn.SMPLX_KEY_BODIES, reset_bodies=None, dof_subset=None)
+    plan = run_cuda_step(motion_data_from(g), st, cfg)
+    check_against(plan, {k: g[f"out_{k}"] for k in KEYS}, "smplx")
+
+
+def _g1_lib(g):
+    f = lambda k: g["tab_" + k].to(DEV)
+    return ops.pack_robot_motion_lib(f("gts_t"), f("grs_t"), f("gvs_t"), f("gavs_t"), f("dof_pos"), f("dvs"), syn.G1_NUM_BODIES, f("lengths"),
+                                     f("num_frames"), f("dts"), f("length_starts"))
+
+
+def test_g1_env_step_motion_state_and_demo_vs_reference_golden():
+    g = load("g1.npz")
+    mlib = _g1_lib(g)
+    res = ops.motion_state(mlib, g["ms_ids"].to(DEV), g["ms_times"].to(DEV), g["ms_offset"].to(DEV))
+    for k in ("root_pos", "root_rot", "dof_pos", "root_vel", "root_ang_vel", "dof_vel", "rg_pos", "rb_rot", "body_vel", "body_ang_vel",
+              "rg_pos_t", "rg_rot_t", "body_vel_t", "body_ang_vel_t"):
+        close(res[k].cpu(), g["ms_out_" + k], what="g1 motion_state " + k)
+    cfg = ops.EnvStepConfig(key_bodies=syn.G1_KEY_BODIES, reset_bodies=None, dof_subset=None, ext_parents=syn.G1_EXT_PARENTS, ext_pos=syn.G1_EXT_POS)
+    for tag in ("A", "B"):
+        st = syn.EnvState(**{k: g[f"{tag}_in_{k}"] for k in syn.EnvState.__dataclass_fields__}).to(DEV)
+        plan = ops.EnvStepPlan(cfg, mlib, st.body_state, st.dof_state, st.dof_force, st.progress, st.motion_ids, st.start_times, st.start_offsets,
+                               st.global_offset, amp_obs_buf=st.amp_hist.clone(), with_ref_buffers=True)
+        plan.run()
+        torch.cuda.synchronize()
+        check_against(plan, {k: g[f"{tag}_out_{k}"] for k in KEYS}, f"g1 {tag}")
+    demo = ops.amp_obs_demo(mlib, cfg, g["demo_ids"].to(DEV), g["demo_t0"].to(DEV))
+    close(demo.cpu(), g["demo_out"], rtol=1e-4, atol=2e-5, what="g1 amp_obs_demo")
