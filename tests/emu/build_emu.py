@@ -181,6 +181,69 @@ def build_motion(out_dir: str) -> str:
     return so
 
 
+LOAD_LAUNCHER = r'''
+namespace phc { namespace load { alignas(16) unsigned char smem_raw[1 << 17]; } }     // the kernel's dynamic shared memory
+
+extern "C" int emu_motion_load(const double* quat, const double* trans, const double* offsets, const int32_t* parents, const double* heading,
+                               const int64_t* starts, const int64_t* nframes, const double* fps, int64_t F, int32_t M, int32_t J, float* gts,
+                               float* grs, float* lrs, float* gvs, float* gavs, float* dvs, double* pos64, double* rawang, int32_t* frame_clip) {
+  using namespace phc::load;
+  FkArgs fa;
+  fa.quat = quat; fa.trans = trans; fa.offsets = offsets; fa.parents = parents; fa.heading = heading; fa.starts = starts; fa.nframes = nframes;
+  fa.fps = fps; fa.F = F; fa.M = M; fa.J = J; fa.gts = gts; fa.grs = grs; fa.lrs = lrs; fa.dvs = dvs; fa.pos64 = pos64; fa.rawang = rawang;
+  fa.frame_clip = frame_clip;
+  for (int64_t f = 0; f < F; ++f) {                 // motion_fk_kernel: one warp per frame, kWarps warps per block
+    EmuWarp warp;
+    emu_warp = &warp;
+    std::vector<std::thread> lanes;
+    for (int lane = 0; lane < 32; ++lane)
+      lanes.emplace_back([&, lane] {
+        emu_lane = lane;
+        blockDim.x = kWarps * 32;
+        threadIdx.x = (unsigned)((f % kWarps) * 32 + lane); blockIdx.x = (unsigned)(f / kWarps);
+        motion_fk_kernel(fa);
+      });
+    for (auto& t : lanes) t.join();
+  }
+  emu_warp = nullptr;
+  FilterArgs fl;
+  fl.pos64 = pos64; fl.rawang = rawang; fl.frame_clip = frame_clip; fl.starts = starts; fl.nframes = nframes; fl.fps = fps; fl.F = F; fl.J = J;
+  fl.gvs = gvs; fl.gavs = gavs;
+  {   // the taps exactly as phc_motion_load builds them
+    double sum = 0.0;
+    for (int k = -kRadius; k <= kRadius; ++k) { fl.taps.w[k + kRadius] = exp(-0.5 / (2.0 * 2.0) * (double)k * (double)k); sum += fl.taps.w[k + kRadius]; }
+    for (int k = 0; k <= 2 * kRadius; ++k) fl.taps.w[k] /= sum;
+  }
+  blockDim.x = 256;                                 // motion_filter_kernel: one thread per (frame, body), no cooperation
+  for (int64_t i = 0; i < F * J; ++i) { blockIdx.x = (unsigned)(i / 256); threadIdx.x = (unsigned)(i % 256); motion_filter_kernel(fl); }
+  return 0;
+}
+'''
+
+
+def build_load(out_dir: str) -> str:
+    """motion_load.cu (the loader kernels), verbatim."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    t = open(os.path.join(CSRC, "motion_load.cu")).read()
+    k0 = t.index("namespace phc {")
+    k1 = t.index("}  // namespace phc") + len("}  // namespace phc")
+    body = t[k0:k1]
+    assert "<<<" not in body and "motion_fk_kernel" in body
+    src = os.path.join(out_dir, "motion_load_emu.cpp")
+    with open(src, "w") as f:
+        f.write("\n".join(['#include "cuda_emu_prelude.h"', '#include "phc_common_emu.cuh"', "using std::max; using std::min;",
+                           f'#include "{os.path.join(ROOT, "include", "phc_b200.h")}"', f'#include "{os.path.join(CSRC, "phc_math.cuh")}"',
+                           body, LOAD_LAUNCHER]))
+    so = os.path.join(out_dir, "libmotion_load_emu.so")
+    r = subprocess.run([gxx, "-O1", "-std=c++20", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I" + HERE, src, "-o", so, "-lm"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("loader emulation build failed:\n" + r.stderr[:6000])
+    return so
+
+
 def build(out_dir: str) -> str:
     gxx = shutil.which("g++")
     if gxx is None:
@@ -201,3 +264,4 @@ if __name__ == "__main__":
     d = tempfile.mkdtemp()
     print(build(d))
     print(build_motion(d))
+    print(build_load(d))

@@ -165,3 +165,29 @@ def test_set_env_state_writes_the_motion_state(emu, name, ext, wide):
     close(dof[m][..., 0], g["ms_out_dof_pos"][m], what="dof pos")
     close(dof[m][..., 1], g["ms_out_dof_vel"][m], what="dof vel")
     assert bool((body[~m] == 9.0).all()) and bool((dof[~m] == 9.0).all()) and bool((body[:, J:] == 9.0).all())
+
+
+# ---- motion_load.cu (the loader) on the CPU against the golden of the real MotionLibSMPL.load_motion_with_skeleton ---------
+def test_loader_kernels_vs_reference_golden(tmp_path):
+    import shutil
+    import numpy as np
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    import build_emu
+    lib = C.CDLL(build_emu.build_load(str(tmp_path)))
+    lib.emu_motion_load.argtypes = [P] * 8 + [C.c_int64, C.c_int32, C.c_int32] + [P] * 9
+    z = np.load(os.path.join(HERE, "golden", "load.npz"))
+    q, t = np.ascontiguousarray(z["pose_quat_global"], np.float64), np.ascontiguousarray(z["root_trans"], np.float64)
+    off, par = np.ascontiguousarray(z["offsets"], np.float64), np.ascontiguousarray(z["parents"], np.int32)
+    head, nf, fps = np.ascontiguousarray(z["heading"], np.float64), np.ascontiguousarray(z["num_frames"], np.int64), np.ascontiguousarray(z["fps"], np.float64)
+    starts = np.ascontiguousarray(np.cumsum(nf) - nf, np.int64)
+    F, J, M = q.shape[0], q.shape[1], len(nf)
+    out = {k: np.zeros((F, J if k != "dvs" else J - 1, w), np.float32) for k, w in (("gts", 3), ("grs", 4), ("lrs", 4), ("gvs", 3), ("gavs", 3), ("dvs", 3))}
+    pos64, rawang, clip = np.zeros((F, J, 3)), np.zeros((F, J, 3)), np.zeros(F, np.int32)
+    ptr = lambda a: a.ctypes.data_as(P)
+    assert lib.emu_motion_load(ptr(q), ptr(t), ptr(off), ptr(par), ptr(head), ptr(starts), ptr(nf), ptr(fps), F, M, J, ptr(out["gts"]), ptr(out["grs"]),
+                               ptr(out["lrs"]), ptr(out["gvs"]), ptr(out["gavs"]), ptr(out["dvs"]), ptr(pos64), ptr(rawang), ptr(clip)) == 0
+    assert np.array_equal(clip, np.repeat(np.arange(M), nf))
+    for k in ("gts", "grs", "lrs", "gvs", "gavs"):
+        close(torch.from_numpy(out[k]), torch.from_numpy(z[k]), rtol=1e-6, atol=1e-6, what=f"loader {k}")
+    close(torch.from_numpy(out["dvs"]), torch.from_numpy(z["dvs"]), rtol=1e-5, atol=2e-5, what="loader dvs")
