@@ -20,10 +20,10 @@ template <int T_MAX, int JT, bool GETUP, bool FAST>
 static void emu_launch(const PhcStepArgs& a, int obs_dim, int self_dim, int amp_dim, bool alias_obs, bool state_bulk_ok) {
   for (int env = 0; env < a.num_envs; ++env) {
     EmuWarp warp;
-    emu_warp = &warp;
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; ++lane)
       lanes.emplace_back([&, lane] {
+        emu_warp = &warp;
         emu_lane = lane;
         threadIdx.x = (unsigned)((env % phc::kWarpsPerCta) * 32 + lane); threadIdx.y = threadIdx.z = 0;
         blockIdx.x = (unsigned)(env / phc::kWarpsPerCta); blockIdx.y = blockIdx.z = 0;
@@ -31,7 +31,6 @@ static void emu_launch(const PhcStepArgs& a, int obs_dim, int self_dim, int amp_
       });
     for (auto& t : lanes) t.join();
   }
-  emu_warp = nullptr;
 }
 
 extern "C" int emu_env_step(const PhcStepArgs* a, int obs_dim, int self_dim, int amp_dim, int alias_obs, int state_bulk_ok, int variant) {
@@ -45,10 +44,10 @@ extern "C" int emu_env_step(const PhcStepArgs* a, int obs_dim, int self_dim, int
     case 6:      // env_step_wide.cu: strided bodies, no staging
       for (int env = 0; env < a->num_envs; ++env) {
         EmuWarp warp;
-        emu_warp = &warp;
         std::vector<std::thread> lanes;
         for (int lane = 0; lane < 32; ++lane)
           lanes.emplace_back([&, lane] {
+            emu_warp = &warp;
             emu_lane = lane;
             threadIdx.x = (unsigned)((env % phc::wide::kWarps) * 32 + lane); threadIdx.y = threadIdx.z = 0;
             blockIdx.x = (unsigned)(env / phc::wide::kWarps); blockIdx.y = blockIdx.z = 0;
@@ -56,8 +55,7 @@ extern "C" int emu_env_step(const PhcStepArgs* a, int obs_dim, int self_dim, int
           });
         for (auto& t : lanes) t.join();
       }
-      emu_warp = nullptr;
-      return 0;
+          return 0;
   }
   return -1;
 }
@@ -92,10 +90,10 @@ template <class F>
 static void emu_warps(int64_t n_warps, F&& body) {      // one warp (32 threads) at a time, 4 warps per block like the launches
   for (int64_t w = 0; w < n_warps; ++w) {
     EmuWarp warp;
-    emu_warp = &warp;
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; ++lane)
       lanes.emplace_back([&, lane] {
+        emu_warp = &warp;
         emu_lane = lane;
         blockDim.x = 128; blockDim.y = blockDim.z = 1;
         threadIdx.x = (unsigned)((w % 4) * 32 + lane); threadIdx.y = threadIdx.z = 0;
@@ -104,7 +102,6 @@ static void emu_warps(int64_t n_warps, F&& body) {      // one warp (32 threads)
       });
     for (auto& t : lanes) t.join();
   }
-  emu_warp = nullptr;
 }
 
 extern "C" int emu_motion_state(const PhcMotionLib* lib, const int64_t* ids, const float* times, const float* offset, int64_t n,
@@ -194,10 +191,10 @@ extern "C" int emu_motion_load(const double* quat, const double* trans, const do
   fa.frame_clip = frame_clip;
   for (int64_t f = 0; f < F; ++f) {                 // motion_fk_kernel: one warp per frame, kWarps warps per block
     EmuWarp warp;
-    emu_warp = &warp;
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; ++lane)
       lanes.emplace_back([&, lane] {
+        emu_warp = &warp;
         emu_lane = lane;
         blockDim.x = kWarps * 32;
         threadIdx.x = (unsigned)((f % kWarps) * 32 + lane); blockIdx.x = (unsigned)(f / kWarps);
@@ -205,7 +202,6 @@ extern "C" int emu_motion_load(const double* quat, const double* trans, const do
       });
     for (auto& t : lanes) t.join();
   }
-  emu_warp = nullptr;
   FilterArgs fl;
   fl.pos64 = pos64; fl.rawang = rawang; fl.frame_clip = frame_clip; fl.starts = starts; fl.nframes = nframes; fl.fps = fps; fl.F = F; fl.J = J;
   fl.gvs = gvs; fl.gavs = gavs;
@@ -244,6 +240,64 @@ def build_load(out_dir: str) -> str:
     return so
 
 
+SCALARS_LAUNCHER = r'''
+template <class F>
+static void emu_blocks(int grid, int threads, F&& body) {     // block-level kernels: every thread of a block runs concurrently
+  for (int b = 0; b < grid; ++b) {
+    std::vector<EmuWarp> warps((threads + 31) / 32);
+    std::barrier<> block_bar(threads);
+    emu_block_bar = &block_bar;
+    std::vector<std::thread> ts;
+    for (int t = 0; t < threads; ++t)
+      ts.emplace_back([&, t] {
+        emu_warp = &warps[t / 32];
+        emu_lane = t % 32;
+        blockDim.x = (unsigned)threads; gridDim.x = (unsigned)grid;
+        threadIdx.x = (unsigned)t; blockIdx.x = (unsigned)b;
+        body();
+      });
+    for (auto& t : ts) t.join();
+  }
+  emu_block_bar = nullptr;
+}
+
+extern "C" int emu_gae(const float* fdones, const float* values, const float* rewards, const float* next_values, int32_t T, int64_t N,
+                       float gamma, float tau, float* advs, float* returns) {
+  emu_blocks((int)((N + 31) / 32), 1024, [&] { phc::gae_kernel(fdones, values, rewards, next_values, T, N, gamma, tau, advs, returns); });
+  return 0;
+}
+
+extern "C" int emu_adv_norm(const float* returns, const float* values, int64_t n, int32_t normalize, float* advs, double* workspace) {
+  const int g = phc::adv_grid(n);
+  emu_blocks(g, phc::kAdvBlock, [&] { phc::adv_partial_kernel(returns, values, n, advs, workspace); });
+  if (normalize) emu_blocks(g, phc::kAdvBlock, [&] { phc::adv_apply_kernel(advs, n, workspace, g); });
+  return g;
+}
+'''
+
+
+def build_scalars(out_dir: str) -> str:
+    """ppo_scalars.cu (GAE scan, advantage normalisation), verbatim; `__shared__` variables become function-local statics."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    t = open(os.path.join(CSRC, "ppo_scalars.cu")).read()
+    k0 = t.index("namespace phc {")
+    k1 = t.index("}  // namespace phc") + len("}  // namespace phc")
+    body = t[k0:k1]
+    assert "<<<" not in body and "gae_kernel" in body
+    src = os.path.join(out_dir, "ppo_scalars_emu.cpp")
+    with open(src, "w") as f:
+        f.write("\n".join(['#include "cuda_emu_prelude.h"', "#undef __shared__", "#define __shared__ static",
+                           f'#include "{os.path.join(ROOT, "include", "phc_b200.h")}"', body, SCALARS_LAUNCHER]))
+    so = os.path.join(out_dir, "libppo_scalars_emu.so")
+    r = subprocess.run([gxx, "-O1", "-std=c++20", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I" + HERE, src, "-o", so, "-lm"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("ppo_scalars emulation build failed:\n" + r.stderr[:6000])
+    return so
+
+
 def build(out_dir: str) -> str:
     gxx = shutil.which("g++")
     if gxx is None:
@@ -265,3 +319,4 @@ if __name__ == "__main__":
     print(build(d))
     print(build_motion(d))
     print(build_load(d))
+    print(build_scalars(d))

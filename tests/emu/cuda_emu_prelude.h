@@ -36,24 +36,28 @@ static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); ret
 
 struct EmuWarp {
   std::barrier<> bar{32};
-  uint32_t xch[32];
+  uint64_t xch[32];
 };
-static EmuWarp* emu_warp = nullptr;          // warps run one at a time (the kernel has no block-level synchronisation)
+static thread_local EmuWarp* emu_warp = nullptr;     // the warp this (lane) thread belongs to
+static std::barrier<>* emu_block_bar = nullptr;      // __syncthreads() of the block being emulated (block-level kernels only)
+static inline void __syncthreads() { emu_block_bar->arrive_and_wait(); }
 
 static inline void __syncwarp() { emu_warp->bar.arrive_and_wait(); }
 template <class T>
-static inline T emu_exchange(T v, int src) {
-  static_assert(sizeof(T) == 4, "32-bit shuffles only");
-  uint32_t u;
-  std::memcpy(&u, &v, 4);
+static inline T emu_exchange(T v, int src) {        // a lane outside 0..31 reads its own value (shfl_down / shfl_up at the edge)
+  static_assert(sizeof(T) == 4 || sizeof(T) == 8, "32- and 64-bit shuffles");
+  uint64_t u = 0;
+  std::memcpy(&u, &v, sizeof(T));
   emu_warp->xch[emu_lane] = u;
   emu_warp->bar.arrive_and_wait();
-  const uint32_t r = emu_warp->xch[src & 31];
+  const uint64_t r = emu_warp->xch[(src < 0 || src > 31) ? emu_lane : src];
   emu_warp->bar.arrive_and_wait();
   T o;
-  std::memcpy(&o, &r, 4);
+  std::memcpy(&o, &r, sizeof(T));
   return o;
 }
+static inline float __shfl_down_sync(unsigned, float v, int o) { return emu_exchange(v, emu_lane + o); }
+static inline double __shfl_xor_sync(unsigned, double v, int o) { return emu_exchange(v, emu_lane ^ o); }
 static inline float __shfl_xor_sync(unsigned, float v, int o) { return emu_exchange(v, emu_lane ^ o); }
 static inline int __shfl_xor_sync(unsigned, int v, int o) { return emu_exchange(v, emu_lane ^ o); }
 static inline float __shfl_sync(unsigned, float v, int src) { return emu_exchange(v, src); }
@@ -61,7 +65,7 @@ static inline int __shfl_sync(unsigned, int v, int src) { return emu_exchange(v,
 static inline bool __any_sync(unsigned, bool p) {
   emu_warp->xch[emu_lane] = p ? 1u : 0u;
   emu_warp->bar.arrive_and_wait();
-  uint32_t any = 0;
+  uint64_t any = 0;
   for (int i = 0; i < 32; ++i) any |= emu_warp->xch[i];
   emu_warp->bar.arrive_and_wait();
   return any != 0;
