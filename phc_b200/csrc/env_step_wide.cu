@@ -2,8 +2,8 @@
 // dofs, phc/data/cfg/robot/unitree_g1.yaml) and SMPL-X (52 bodies, phc/data/cfg/robot/smplx_humanoid.yaml).  Same entry point
 // and the same semantics as env_step.cu (phc_env_step dispatches here when J + E > 32): reward + reset at the current motion
 // time, self + task observation v6 (T <= 4 future samples) at the next one, AMP observation (+ window shift), pose cache,
-// ref_* side buffers, im_eval extras, masked / observation-only launches.  Not supported here: the getup extras
-// (PHC_FLAG_ZERO_OUT_FAR / PHC_FLAG_CYCLE_MOTION).
+// ref_* side buffers, im_eval extras, masked / observation-only launches, and the getup extras (PHC_FLAG_ZERO_OUT_FAR /
+// PHC_FLAG_CYCLE_MOTION: env_im_x_getup_mcp.yaml) with the semantics documented at env_step.cu's GETUP variant.
 //
 // Deliberately the SIMPLE formulation: one warp per env, bodies strided over the lanes (j = lane, lane + 32), every record read
 // straight from global memory through L1 / L2 and every output written straight to its row -- no shared-memory staging, no TMA.
@@ -84,6 +84,41 @@ env_step_wide_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, c
   const float* frames = a.lib.frames_body;
   float* const g_cache = a.ref_cache ? a.ref_cache + (size_t)env * BS : nullptr;
 
+  // getup extras: motion parameters of the OBSERVATION time (re-based when the clip wraps this step, humanoid_im.py:1120-1146)
+  const bool zof = flags & PHC_FLAG_ZERO_OUT_FAR;
+  const bool cyc = (flags & PHC_FLAG_CYCLE_MOTION) && !obs_only;
+  float t_start_o = t_start, t_off_o = t_off;
+  V3 goff_o = goff;
+  int cc = a.cycle_counter ? a.cycle_counter[env] : 0;
+  bool rebased = false;
+  if (cyc) {
+    cc = cc - 1 < 0 ? 0 : cc - 1;                    // _update_cycle_count (humanoid_im.py:1076-1079)
+    const float t_now0 = PHC_ADD(PHC_ADD(PHC_MUL((float)progress, a.dt), t_start), t_off);
+    if (t_now0 >= m_len) {
+      t_off_o = -PHC_MUL((float)progress, a.dt);
+      const float grid = 1.0f / 30.0f;               // sample_time_interval (motion_lib_base.py:414-423)
+      const long long k = (long long)((a.cycle_phase[env] * m_len) / grid);
+      t_start_o = (float)k * grid;
+      const Bracket32 b = frame_bracket32(t_start_o, m_len, (int)m_nf, m_dt);     // get_root_pos_smpl (:522-547)
+      const float* r0 = frames + (size_t)(m_start + b.i0) * BS;
+      const float* r1 = frames + (size_t)(m_start + b.i1) * BS;
+      const float omb = 1.0f - b.blend;
+      goff_o.x = g_state[0] - lerp1(r0[0], r1[0], omb, b.blend);
+      goff_o.y = g_state[1] - lerp1(r0[1], r1[1], omb, b.blend);
+      cc = 60;
+      rebased = true;
+      __syncwarp();          // every lane has read the old start / offset values before lane 0 replaces them
+      if (lane == 0) {
+        a.start_times[env] = t_start_o;
+        a.start_offsets[env] = t_off_o;
+        a.global_offset[3 * env + 0] = goff_o.x;
+        a.global_offset[3 * env + 1] = goff_o.y;
+      }
+    }
+    __syncwarp();            // ... and the old counter before lane 0 stores the new one
+    if (lane == 0 && a.cycle_counter) a.cycle_counter[env] = cc;
+  }
+
   // heading frame of the simulated root
   const V3 root_p = v3(g_state[0], g_state[1], g_state[2]);
   Q4 root_q = q4(g_state[3], g_state[4], g_state[5], g_state[6]);
@@ -102,8 +137,14 @@ env_step_wide_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, c
     if (!from_cache) br = frame_bracket32(t_now, m_len, (int)m_nf, m_dt);
     const float* f0 = frames + (size_t)(m_start + br.i0) * BS;
     const float* f1 = frames + (size_t)(m_start + br.i1) * BS;
-    float e_pos = 0.f, e_rot = 0.f, e_vel = 0.f, e_ang = 0.f, mp = 0.f, cnt = 0.f, sum = 0.f;
+    float e_pos = 0.f, e_rot = 0.f, e_vel = 0.f, e_ang = 0.f, mp = 0.f, cnt = 0.f, sum = 0.f, dist_root = 0.f;
     bool over = false;
+    // a clip that wrapped this step: the reset test sees the pose at the re-based time (humanoid_im.py:1142, :1148)
+    Bracket32 bt;
+    bt.i0 = 0; bt.i1 = 0; bt.blend = 0.f;
+    if (rebased) bt = frame_bracket32(PHC_ADD(PHC_ADD(PHC_MUL((float)progress, a.dt), t_start_o), t_off_o), m_len, (int)m_nf, m_dt);
+    const float* q0 = frames + (size_t)(m_start + bt.i0) * BS;
+    const float* q1 = frames + (size_t)(m_start + bt.i1) * BS;
     for (int jj = lane; jj < J + E; jj += 32) {
       const bool is_body = jj < J;
       Body sim;
@@ -126,9 +167,17 @@ env_step_wide_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, c
         e_ang += (dw.x * dw.x + dw.y * dw.y + dw.z * dw.z) / 3.0f;
         const float dist = sqrtf(sp);
         mp += dist;
+        if (jj == 0) dist_root = dist;
+        float dist_t = dist;
+        if (rebased) {
+          const V3 pr = lerp3(v3(q0[jj * kRec], q0[jj * kRec + 1], q0[jj * kRec + 2]), v3(q1[jj * kRec], q1[jj * kRec + 1], q1[jj * kRec + 2]),
+                              1.0f - bt.blend, bt.blend) + goff_o;
+          const V3 d2 = pr - sim.p;
+          dist_t = sqrtf(d2.x * d2.x + d2.y * d2.y + d2.z * d2.z);
+        }
         const float thr = a.term_thresh[jj];
-        if (thr < INFINITY) { cnt += 1.0f; sum += dist; }
-        over = over || (dist > thr);
+        if (thr < INFINITY) { cnt += 1.0f; sum += dist_t; }
+        over = over || (dist_t > thr);
       }
     }
     if (a.mpjpe) {         // flags.im_eval extras (humanoid_im.py:674-680)
@@ -158,7 +207,13 @@ env_step_wide_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, c
       float rew = a.w_pos * r_pos + a.w_rot * r_rot + a.w_vel * r_vel + a.w_ang_vel * r_ang;
       const bool has_power = flags & PHC_FLAG_POWER_REWARD;
       float* raw = a.reward_raw + (size_t)env * (has_power ? 5 : 4);
-      raw[0] = r_pos; raw[1] = r_rot; raw[2] = r_vel; raw[3] = r_ang;
+      float w0 = r_pos, w1 = r_rot, w2 = r_vel, w3 = r_ang;
+      if (zof) {            // point-goal mix (humanoid_im.py:890-905); lane 0 tracked the root
+        const float pg = fminf(a.point_goal[env] - dist_root, 1.0f / 3.0f) * 9.0f;
+        if (dist_root > 0.25f) { rew = pg; w0 = pg; w1 = 0.0f; w2 = 0.0f; w3 = 0.0f; }
+        else { rew = pg + rew * 0.5f; w0 = pg + r_pos * 0.5f; w1 = 0.0f + r_rot * 0.5f; w2 = 0.0f + r_vel * 0.5f; w3 = 0.0f + r_ang * 0.5f; }
+      }
+      raw[0] = w0; raw[1] = w1; raw[2] = w2; raw[3] = w3;
       if (has_power) {
         float pr = -a.power_coef * power;
         if (progress <= 3) pr = 0.0f;
@@ -166,7 +221,8 @@ env_step_wide_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, c
         raw[4] = pr;
       }
       a.rew[env] = rew;
-      const bool pass_time = t_now >= m_len;
+      bool pass_time = t_now >= m_len;
+      if (cyc) pass_time = progress >= (int64_t)a.max_episode_length - 1;      // pass_time_max (humanoid_im.py:1120-1124)
       int64_t terminated = 0;
       if (flags & PHC_FLAG_EARLY_TERM) {
         bool f = fallen && (progress > 1);
@@ -174,7 +230,7 @@ env_step_wide_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, c
         terminated = f ? 1 : 0;
       }
       int64_t reset = pass_time ? 1 : terminated;
-      if (a.cycle_counter && !pass_time && a.cycle_counter[env] > 0) { reset = 0; terminated = 0; }
+      if (a.cycle_counter && !pass_time && cc > 0) { reset = 0; terminated = 0; }      // cc: this lane's own read (+ update)
       a.reset[env] = reset;
       a.terminate[env] = terminated;
     }
@@ -232,26 +288,43 @@ env_step_wide_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, c
   for (int t = 0; t < T; ++t) {                // compute_imitation_observations_v6 (humanoid_im.py:1308-1358)
     float tn = PHC_MUL((float)(progress + 1), a.dt);
     if (T > 1) tn = PHC_ADD(tn, PHC_MUL((float)t, a.traj_dt));
-    tn = PHC_ADD(PHC_ADD(tn, t_start), t_off);
+    tn = PHC_ADD(PHC_ADD(tn, t_start_o), t_off_o);
     const Bracket32 b = frame_bracket32(tn, m_len, (int)m_nf, m_dt);
     const float* f0 = frames + (size_t)(m_start + b.i0) * BS;
     const float* f1 = frames + (size_t)(m_start + b.i1) * BS;
     float* tb = g_obs + self_dim + t * 24 * J;
+    float dist_o = 0.0f;         // zero_out_far: |root_pos - reference root| at the observation time (humanoid_im.py:783-796)
+    if (zof && t == 0) {
+      const V3 rr = lerp3(v3(f0[0], f0[1], f0[2]), v3(f1[0], f1[1], f1[2]), 1.0f - b.blend, b.blend) + goff_o;
+      const V3 dr = root_p - rr;
+      dist_o = sqrtf(dr.x * dr.x + dr.y * dr.y + dr.z * dr.z);
+      if (lane == 0) a.point_goal[env] = dist_o;
+    }
     const int last = (t == 0 && g_cache) ? J + E : J;      // the pose cache also keeps the extend bodies of the first sample
     for (int jj = lane; jj < last; jj += 32) {
-      const Body ref = blend(f0 + jj * kRec, f1 + jj * kRec, b.blend, goff);
+      const Body ref = blend(f0 + jj * kRec, f1 + jj * kRec, b.blend, goff_o);
       if (t == 0 && g_cache) {
         float* c = g_cache + jj * kRec;
         put3(c, ref.p); c[3] = ref.q.x; c[4] = ref.q.y; c[5] = ref.q.z; c[6] = ref.q.w; put3(c + 7, ref.v); put3(c + 10, ref.w);
       }
       if (jj >= J) continue;               // extend bodies: reward only, no observation columns
       const Body sim = ld_body(g_state + jj * kRec);
-      put3(tb + 3 * jj, qrot_z(hinv, ref.p - sim.p));
-      put6(tb + 3 * J + 6 * jj, tan_norm(qmul_zr(qmul_zl(hinv, qmul(ref.q, qconj(sim.q))), hq)));
-      put3(tb + 9 * J + 3 * jj, qrot_z(hinv, ref.v - sim.v));
-      put3(tb + 12 * J + 3 * jj, qrot_z(hinv, ref.w - sim.w));
-      put3(tb + 15 * J + 3 * jj, qrot_z(hinv, ref.p - root_p));
-      put6(tb + 18 * J + 6 * jj, tan_norm(qmul_zl(hinv, ref.q)));
+      Body ro = ref;               // what the observation sees as reference (cache / ref_* buffers keep `ref`)
+      if (zof && t == 0) {
+        if (dist_o > a.close_distance) {
+          if (jj > 0) { ro.p = sim.p; ro.q = sim.q; }
+          ro.v = sim.v; ro.w = sim.w;
+        }
+        if (dist_o > a.far_distance && jj == 0)
+          ro.p = v3((ref.p.x - sim.p.x) / dist_o * a.far_distance + sim.p.x, (ref.p.y - sim.p.y) / dist_o * a.far_distance + sim.p.y,
+                    (ref.p.z - sim.p.z) / dist_o * a.far_distance + sim.p.z);
+      }
+      put3(tb + 3 * jj, qrot_z(hinv, ro.p - sim.p));
+      put6(tb + 3 * J + 6 * jj, tan_norm(qmul_zr(qmul_zl(hinv, qmul(ro.q, qconj(sim.q))), hq)));
+      put3(tb + 9 * J + 3 * jj, qrot_z(hinv, ro.v - sim.v));
+      put3(tb + 12 * J + 3 * jj, qrot_z(hinv, ro.w - sim.w));
+      put3(tb + 15 * J + 3 * jj, qrot_z(hinv, ro.p - root_p));
+      put6(tb + 18 * J + 6 * jj, tan_norm(qmul_zl(hinv, ro.q)));
       if (t == 0) {     // side buffers of _compute_task_obs(save_buffer=True)
         const size_t bj = (size_t)env * J + jj;
         if (a.ref_body_pos) put3(a.ref_body_pos + 3 * bj, ref.p);
@@ -273,10 +346,6 @@ extern "C" void phc_count_launches(int n);
 // called by phc_env_step (env_step.cu) after its argument validation, when J + E > PHC_LANE_BODIES
 extern "C" int phc_env_step_wide_launch(const PhcStepArgs* a, int obs_dim, int self_dim, int amp_dim, void* stream) {
   using namespace phc::wide;
-  if (a->flags & (PHC_FLAG_ZERO_OUT_FAR | PHC_FLAG_CYCLE_MOTION)) {
-    phc_set_error("phc_env_step: zero_out_far / cycle_motion are not built for more than 32 bodies");
-    return PHC_ERR_UNSUPPORTED;
-  }
   const int grid = (a->num_envs + kWarps - 1) / kWarps;
   env_step_wide_kernel<<<grid, kWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(*a, obs_dim, self_dim, amp_dim);
   phc_count_launches(1);

@@ -572,14 +572,15 @@ def gen_reset():
 
 
 # ------------------------------------------------------------------------------------------------
-def gen_getup():
+def gen_getup(J=24, name="getup.npz", seed=4):
     """env_im_getup_mcp.yaml (the configuration HumanoidImMCP trains in): zero_out_far + cycle_motion, zero_out_far_train False.
     The real HumanoidIm._compute_reward (:873-948), _compute_reset (:1117-1190 incl. the clip wrap-around :1123-1146) and
     _compute_observations (zero_out_far overwrites :783-796).  The uniform numbers sample_time_interval draws for the wrapping
     envs are reproduced by re-seeding torch's generator and stored as the `cycle_phase` input."""
-    m = syn.make_motions(48, seed=4, min_frames=16, max_frames=40)
-    N = 48
-    st = syn.make_env_state(m, N, seed=2, max_progress=20, with_offset=True)
+    N = 48 if J == 24 else 24
+    m = syn.make_motions(N, seed=seed, num_bodies=J, min_frames=16, max_frames=40)
+    A = 196 if J == 24 else 1 + 12 + 9 * (J - 1) + 3 * 4
+    st = syn.make_env_state(m, N, seed=2, amp_dim=A, max_progress=20, with_offset=True)
     g = torch.Generator().manual_seed(9)
     # the simulated state was generated around reference + global_offset: moving the offset moves the reference away
     st.global_offset[0:10, :2] += torch.randn(10, 2, generator=g) * 4.0        # far: beyond far_distance for most
@@ -588,6 +589,12 @@ def gen_getup():
     cc_in = torch.tensor([0, 0, 0, 1, 2, 7], dtype=torch.int)[torch.randint(0, 6, (N,), generator=g)]
     point_goal = torch.rand(N, generator=g) * 6
     env = build_ref_env(m, st)
+    if J != 24:          # SMPL-X shapes (env_im_x_getup_mcp.yaml), set up as in gen_smplx
+        env.humanoid_type = "smplx"
+        env._reset_bodies_id = torch.arange(J)
+        env._key_body_ids = torch.tensor(syn.SMPLX_KEY_BODIES)
+        env.dof_subset, env._has_dof_subset = torch.tensor([]).long(), False
+        env._dof_names = [f"j{i}" for i in range(1, J)]
     env.zero_out_far, env.zero_out_far_train, env.cycle_motion, env.cycle_motion_xp = True, False, True, False
     env.close_distance, env.far_distance = 0.25, 3
     env.max_episode_length = 15
@@ -619,7 +626,12 @@ def gen_getup():
     d.update(motion_tables_dict(m))
     print("getup golden: wrapping envs", int(wrap.sum()), "far (reward)", int((d["out_reward_raw"][:, 1] == 0).sum()),
           "resets", int(env.reset_buf.sum()))
-    save("getup.npz", d)
+    save(name, d)
+
+
+def gen_getup_smplx():
+    """The getup configuration at SMPL-X shapes (env_im_x_getup_mcp.yaml: 52 bodies, zero_out_far + cycle_motion)."""
+    gen_getup(J=52, name="getup_smplx.npz", seed=14)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -698,3 +710,4 @@ if __name__ == "__main__":
     gen_reset()
     gen_g1()
     gen_smplx()
+    gen_getup_smplx()

@@ -190,3 +190,36 @@ def test_wide_kernel_pose_cache_and_obs_only(emu):
     only = make_plan(hp, m, st2, cfg, obs=torch.full_like(plain.obs, 7.0).contiguous(), only_where=mask, obs_only=True, with_amp=False)
     e.run(only, "wide")
     assert torch.equal(only.obs[mask.bool()], plain.obs[mask.bool()]) and bool((only.obs[~mask.bool()] == 7.0).all())
+
+
+def test_wide_kernel_getup_smplx_vs_reference_golden(emu):
+    """env_im_x_getup_mcp.yaml: zero_out_far + cycle_motion at 52 bodies through the strided kernel."""
+    e, hp = emu
+    g = load("getup_smplx.npz")
+    st = syn.EnvState(**{k: g[f"in_{k}"] for k in syn.EnvState.__dataclass_fields__})
+    pg, cc, ph = g["in_point_goal"].clone(), g["in_cycle_counter"].to(torch.int32).clone(), g["in_cycle_phase"].clone()
+    cfg = ops.EnvStepConfig(key_bodies=syn.SMPLX_KEY_BODIES, reset_bodies=None, dof_subset=None, zero_out_far=True, cycle_motion=True, max_episode_length=15)
+    plan = make_plan(hp, motion_data_from(g), st, cfg, point_goal=pg, cycle_counter=cc, cycle_phase=ph)
+    e.run(plan, "wide")
+    exp = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    check(plan, exp, "getup smplx")
+    k = plan._keep
+    close(k["start_times"], exp["start_times"], what="start_times")
+    close(k["start_offsets"], exp["start_offsets"], what="start_offsets")
+    close(k["global_offset"], exp["global_offset"], what="global_offset")
+    close(pg, exp["point_goal"], what="point_goal")
+    assert torch.equal(cc.long(), exp["cycle_counter"].long())
+
+
+def test_wide_kernel_getup_on_the_24_body_golden(emu):
+    e, hp = emu
+    g = load("getup.npz")
+    st = syn.EnvState(**{k: g[f"in_{k}"] for k in syn.EnvState.__dataclass_fields__})
+    pg, cc, ph = g["in_point_goal"].clone(), g["in_cycle_counter"].to(torch.int32).clone(), g["in_cycle_phase"].clone()
+    plan = make_plan(hp, motion_data_from(g), st, smpl_cfg(zero_out_far=True, cycle_motion=True, max_episode_length=15), point_goal=pg,
+                     cycle_counter=cc, cycle_phase=ph)
+    e.run(plan, "wide")
+    exp = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    check(plan, exp, "getup (wide kernel)")
+    close(plan._keep["global_offset"], exp["global_offset"], what="global_offset")
+    assert torch.equal(cc.long(), exp["cycle_counter"].long())

@@ -49,3 +49,22 @@ def test_g1_env_step_motion_state_and_demo_vs_reference_golden():
         check_against(plan, {k: g[f"{tag}_out_{k}"] for k in KEYS}, f"g1 {tag}")
     demo = ops.amp_obs_demo(mlib, cfg, g["demo_ids"].to(DEV), g["demo_t0"].to(DEV))
     close(demo.cpu(), g["demo_out"], rtol=1e-4, atol=2e-5, what="g1 amp_obs_demo")
+
+
+def test_smplx_getup_vs_reference_golden():
+    """env_im_x_getup_mcp.yaml: zero_out_far + cycle_motion at 52 bodies."""
+    g = load("getup_smplx.npz")
+    st = syn.EnvState(**{k: g[f"in_{k}"] for k in syn.EnvState.__dataclass_fields__}).to(DEV)
+    from tests.test_gpu_env_step import pack
+    mlib = pack(motion_data_from(g))
+    pg, cc, ph = g["in_point_goal"].to(DEV).clone(), g["in_cycle_counter"].to(DEV).to(torch.int32).clone(), g["in_cycle_phase"].to(DEV).clone()
+    cfg = ops.EnvStepConfig(key_bodies=syn.SMPLX_KEY_BODIES, reset_bodies=None, dof_subset=None, zero_out_far=True, cycle_motion=True, max_episode_length=15)
+    plan = ops.EnvStepPlan(cfg, mlib, st.body_state, st.dof_state, st.dof_force, st.progress, st.motion_ids, st.start_times, st.start_offsets,
+                           st.global_offset, amp_obs_buf=st.amp_hist.clone(), with_ref_buffers=True, point_goal=pg, cycle_counter=cc, cycle_phase=ph)
+    plan.run()
+    torch.cuda.synchronize()
+    exp = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    check_against(plan, exp, "getup smplx")
+    close(st.global_offset.cpu(), exp["global_offset"], what="global_offset")
+    close(pg.cpu(), exp["point_goal"], what="point_goal")
+    assert torch.equal(cc.cpu().long(), exp["cycle_counter"].long())

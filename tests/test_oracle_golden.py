@@ -350,3 +350,19 @@ def test_reset_path_pieces_match_reference():
     ln = g["tab_lengths"][g["motion_ids"]]
     t = ((g["phase"] * ln) / (1 / 30)).long() * (1 / 30)          # the arithmetic phc_reset_bookkeeping implements
     assert torch.equal(t, g["sampled_times"])
+
+
+def test_env_step_getup_smplx_shapes():
+    """The getup configuration at SMPL-X shapes (env_im_x_getup_mcp.yaml), tests/golden/getup_smplx.npz."""
+    from phc_b200 import synthetic as syn
+    g = load("getup_smplx.npz")
+    st = {k[3:]: v for k, v in g.items() if k.startswith("in_")}
+    cfg = O.StepConfig(key_bodies=syn.SMPLX_KEY_BODIES, reset_bodies=None, dof_subset=None)
+    out = O.env_step_getup(tables_from(g), cfg, st["body_state"], st["dof_state"], st["dof_force"], st["progress"], st["motion_ids"],
+                           st["start_times"], st["start_offsets"], st["global_offset"], st["amp_hist"], st["point_goal"], st["cycle_counter"],
+                           st["cycle_phase"], max_episode_length=15)
+    assert int(g["in_wrap"].sum()) >= 5 and int((g["out_reward_raw"][:, 1] != 0).sum()) >= 2
+    for k in ("start_times", "start_offsets", "global_offset", "point_goal", "rew", "reward_raw", "ref_body_pos", "ref_body_rot", "ref_body_vel",
+              "amp_obs_buf", "reset", "terminate"):
+        close(out[k], g["out_" + k], what=f"getup smplx {k}")
+    close(out["obs"], g["out_obs"], atol=2e-6, what="getup smplx obs")
