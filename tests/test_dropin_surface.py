@@ -78,3 +78,29 @@ def test_dropin_rebinds_both_import_spellings():
         assert eval("HumanoidIm", vars(ref_env)) is HumanoidIm          # what parse_task.py:60 does
     finally:
         ref_env.HumanoidIm, ref_agent.AMPAgent, ref_agent_short.AMPAgent, ref_mcp.HumanoidImMCP = saved
+
+
+@needs_ref
+def test_install_on_import_rebinds_when_the_reference_modules_load_later():
+    """The sitecustomize route: the hook is registered BEFORE the reference modules are imported (as when `python
+    phc/run_hydra.py` starts) and rebinds the classes right after each module body ran -- checked in a fresh interpreter."""
+    import subprocess
+    code = r'''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import ref_shim; ref_shim.install()                      # stands in for the reference's own (absent) dependencies
+import phc_b200.dropin as d
+d.install_on_import()                                     # what sitecustomize.py does
+assert not any(m in sys.modules for m in ("phc.env.tasks.humanoid_im", "learning.amp_agent"))
+import phc.env.tasks.humanoid_im as ref_env              # parse_task.py:29-38 spelling
+import learning.amp_agent as ref_agent                   # run_hydra.py:57-64 spelling
+import learning.im_amp as im_amp                          # class IMAmpAgent(amp_agent.AMPAgent)
+from phc_b200.env.humanoid_im import HumanoidIm
+from phc_b200.learning.amp_agent import AMPAgent
+assert ref_env.HumanoidIm is HumanoidIm and eval("HumanoidIm", vars(ref_env)) is HumanoidIm
+assert ref_agent.AMPAgent is AMPAgent
+assert AMPAgent in im_amp.IMAmpAgent.__mro__, im_amp.IMAmpAgent.__mro__
+print("OK")
+''' % (os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
