@@ -298,6 +298,79 @@ def build_scalars(out_dir: str) -> str:
     return so
 
 
+UPDATE_LAUNCHER = r'''
+template <class F>
+static void emu_grid(int gx, int gy, int bx, int by, F&& body) {     // 2-D grids / blocks, every thread of a block concurrent
+  const int threads = bx * by;
+  for (int b = 0; b < gx * gy; ++b) {
+    std::vector<EmuWarp> warps((threads + 31) / 32);
+    std::barrier<> block_bar(threads);
+    emu_block_bar = &block_bar;
+    std::vector<std::thread> ts;
+    for (int t = 0; t < threads; ++t)
+      ts.emplace_back([&, t] {
+        emu_warp = &warps[t / 32];
+        emu_lane = t % 32;
+        blockDim.x = (unsigned)bx; blockDim.y = (unsigned)by; gridDim.x = (unsigned)gx; gridDim.y = (unsigned)gy;
+        threadIdx.x = (unsigned)(t % bx); threadIdx.y = (unsigned)(t / bx); blockIdx.x = (unsigned)(b % gx); blockIdx.y = (unsigned)(b / gx);
+        body();
+      });
+    for (auto& t : ts) t.join();
+  }
+  emu_block_bar = nullptr;
+}
+
+extern "C" int emu_rms_apply(const float* x, int64_t ldx, int64_t n, int32_t d, const double* mean, const double* var, float eps, int32_t unnorm,
+                             float* y, int64_t ldy, const int64_t* row_idx) {
+  emu_grid(2, 1, 256, 1, [&] { phc::rms_apply_kernel(x, ldx, n, d, mean, var, eps, unnorm, y, ldy, row_idx); });      // grid-stride: any grid
+  return 0;
+}
+extern "C" int emu_rms_update(const float* x, int64_t ldx, int64_t n, int32_t d, double* mean, double* var, double* count, double* acc,
+                              const int64_t* row_idx) {
+  for (int i = 0; i < 2 * d; ++i) acc[i] = 0.0;                                     // cudaMemsetAsync of phc_rms_update
+  int gy = (int)((n + 1023) / 1024); if (gy > 32) gy = 32; if (gy < 1) gy = 1;
+  emu_grid((d + 31) / 32, gy, 32, 32, [&] { phc::rms_moments_kernel(x, ldx, n, d, acc, row_idx); });
+  emu_grid(1, 1, 1024, 1, [&] { phc::rms_merge_kernel(acc, n, d, mean, var, count); });
+  return 0;
+}
+extern "C" int emu_disc_reward(const float* logit, int64_t ld, const float* task, int64_t n, float scale, float w_task, float w_disc,
+                               float* disc_r, float* combined) {
+  emu_grid(2, 1, 256, 1, [&] { phc::disc_reward_kernel(logit, ld, task, n, scale, w_task, w_disc, disc_r, combined); });
+  return 0;
+}
+extern "C" int emu_gaussian_sample(const float* mu, int64_t ldmu, const float* logstd, const float* noise, int64_t n, int32_t A, float* actions,
+                                   float* neglogp, float* mus, float* sigmas) {
+  emu_grid((int)((n + 3) / 4), 1, 128, 1, [&] { phc::gaussian_sample_kernel(mu, ldmu, logstd, noise, n, A, actions, neglogp, mus, sigmas); });
+  return 0;
+}
+'''
+
+
+def build_update(out_dir: str) -> str:
+    """ppo_update.cu (RunningMeanStd, Gaussian head, losses, optimiser kernels), verbatim; a few of them get launchers here."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not available")
+    t = open(os.path.join(CSRC, "ppo_update.cu")).read()
+    k0 = t.index("namespace phc {")
+    k1 = t.index("}  // namespace phc") + len("}  // namespace phc")
+    body = t[k0:k1]
+    assert "<<<" not in body and "rms_apply_kernel" in body
+    src = os.path.join(out_dir, "ppo_update_emu.cpp")
+    with open(src, "w") as f:
+        f.write("\n".join(['#include "cuda_emu_prelude.h"', "#undef __shared__", "#define __shared__ static",
+                           f'#include "{os.path.join(ROOT, "include", "phc_b200.h")}"',
+                           "namespace phc { static inline float silu_f(float x) { return x / (1.0f + expf(-x)); }",
+                           "static inline float silu_grad_f(float z) { const float sg = 1.0f / (1.0f + expf(-z)); return sg * (1.0f + z * (1.0f - sg)); } }",
+                           body, UPDATE_LAUNCHER]))
+    so = os.path.join(out_dir, "libppo_update_emu.so")
+    r = subprocess.run([gxx, "-O1", "-std=c++20", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I" + HERE, src, "-o", so, "-lm"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("ppo_update emulation build failed:\n" + r.stderr[:8000])
+    return so
+
+
 def build(out_dir: str) -> str:
     gxx = shutil.which("g++")
     if gxx is None:
@@ -320,3 +393,4 @@ if __name__ == "__main__":
     print(build_motion(d))
     print(build_load(d))
     print(build_scalars(d))
+    print(build_update(d))

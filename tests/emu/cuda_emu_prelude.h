@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -70,3 +71,13 @@ static inline bool __any_sync(unsigned, bool p) {
   emu_warp->bar.arrive_and_wait();
   return any != 0;
 }
+
+// atomicAdd: one global lock (the emulation is about values, not contention)
+static std::mutex emu_atomic_mutex;
+template <class T>
+static inline T atomicAdd(T* p, T v) { std::lock_guard<std::mutex> g(emu_atomic_mutex); const T o = *p; *p = o + v; return o; }
+
+// round-to-nearest intrinsics: plain operations under -ffp-contract=off
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
