@@ -338,6 +338,34 @@ extern "C" int emu_disc_reward(const float* logit, int64_t ld, const float* task
   emu_grid(2, 1, 256, 1, [&] { phc::disc_reward_kernel(logit, ld, task, n, scale, w_task, w_disc, disc_r, combined); });
   return 0;
 }
+extern "C" int emu_ppo_actor_grad(const float* mu, int64_t ldmu, const float* logstd, const float* actions, const float* old_neglogp, const float* adv,
+                                  const float* old_mu, const float* old_sigma, int64_t n, int32_t A, float e_clip, float bound_coef, float inv_batch,
+                                  float* dmu, int64_t lddmu, float* stats) {
+  emu_grid(3, 1, 256, 1, [&] { phc::ppo_actor_grad_kernel(mu, ldmu, logstd, actions, old_neglogp, adv, old_mu, old_sigma, n, A, e_clip, bound_coef,
+                                                          inv_batch, dmu, lddmu, stats); });
+  return 0;
+}
+extern "C" int emu_ppo_critic_grad(const float* v, int64_t ldv, const float* ret, int64_t n, float coef, float inv_batch, float* dv, int64_t lddv, float* stats) {
+  emu_grid(2, 1, 256, 1, [&] { phc::ppo_critic_grad_kernel(v, ldv, ret, n, coef, inv_batch, dv, lddv, stats); });
+  return 0;
+}
+extern "C" int emu_disc_logit_grad(const float* logit, int64_t ld, int64_t n_agent, int64_t n_demo, float coef, float* dlogit, int64_t ldd, float* stats) {
+  emu_grid(2, 1, 256, 1, [&] { phc::disc_logit_grad_kernel(logit, ld, n_agent, n_demo, coef, dlogit, ldd, stats); });
+  return 0;
+}
+extern "C" int emu_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, double* sumsq, float grad_scale, float max_norm, float lr,
+                             float beta1, float beta2, float eps, int64_t step) {
+  *sumsq = 0.0;
+  emu_grid(2, 1, 256, 1, [&] { phc::sumsq_kernel(g, n, sumsq); });
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);      // as phc_adam_step
+  emu_grid(2, 1, 256, 1, [&] { phc::adam_clip_kernel(p, g, m, v, n, sumsq, grad_scale, max_norm, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2)); });
+  return 0;
+}
+extern "C" int emu_mcp_combine(const float* w, int64_t ldw, const float* prim, int64_t ldp, int64_t prim_stride, int64_t n, int32_t K, int32_t A,
+                               int32_t discrete, float* out, int64_t ldo) {
+  emu_grid(2, 1, 256, 1, [&] { phc::mcp_combine_kernel(w, ldw, prim, ldp, prim_stride, n, K, A, discrete, out, ldo); });
+  return 0;
+}
 extern "C" int emu_gaussian_sample(const float* mu, int64_t ldmu, const float* logstd, const float* noise, int64_t n, int32_t A, float* actions,
                                    float* neglogp, float* mus, float* sigmas) {
   emu_grid((int)((n + 3) / 4), 1, 128, 1, [&] { phc::gaussian_sample_kernel(mu, ldmu, logstd, noise, n, A, actions, neglogp, mus, sigmas); });

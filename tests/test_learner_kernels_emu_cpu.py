@@ -1,6 +1,9 @@
-"""The GAE scan and the advantage normalisation (phc_b200/csrc/ppo_scalars.cu, verbatim) on the CPU: block-level emulation
-(tests/emu/: every thread of a 1024- / 256-thread block is a std::thread, __syncthreads = a block barrier, `__shared__` =
-function-local statics) against CommonAgent.discount_values / _calc_advs of the unmodified reference (tests/golden/learn.npz)."""
+"""The learner's non-GEMM kernels on the CPU (phc_b200/csrc/ppo_scalars.cu and ppo_update.cu, verbatim): block-level emulation
+(tests/emu/: every thread of a block is a std::thread, __syncthreads = a block barrier, `__shared__` = function-local statics,
+atomicAdd = a lock) against the unmodified reference where it has the function (tests/golden/learn.npz: discount_values,
+_calc_advs, RunningMeanStd, _calc_disc_rewards / _combine_rewards; mcp.npz: HumanoidImMCP's mixing), against autograd of the
+pinned loss functions for the gradient kernels, and against torch for the rl_games pieces (Gaussian head, clip + Adam).  The
+tensor-core GEMMs are the one part of the learner that cannot be emulated this way."""
 import ctypes as C
 import os
 import sys
@@ -130,3 +133,101 @@ def test_gaussian_head_kernel_self_pinned(upd):
     ref = -torch.distributions.Normal(mu, logstd.exp().expand_as(mu)).log_prob(act).sum(-1)
     close(nlp, ref, rtol=1e-5, atol=1e-4, what="neglogp")
     assert torch.equal(mus, mu) and torch.allclose(sig, logstd.exp().expand_as(mu))
+
+
+def _bind_more(upd):
+    upd.emu_ppo_actor_grad.argtypes = [P, C.c_int64, P, P, P, P, P, P, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, P, C.c_int64, P]
+    upd.emu_ppo_critic_grad.argtypes = [P, C.c_int64, P, C.c_int64, C.c_float, C.c_float, P, C.c_int64, P]
+    upd.emu_disc_logit_grad.argtypes = [P, C.c_int64, C.c_int64, C.c_int64, C.c_float, P, C.c_int64, P]
+    upd.emu_clip_adam.argtypes = [P, P, P, P, C.c_int64, P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64]
+    upd.emu_mcp_combine.argtypes = [P, C.c_int64, P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, P, C.c_int64]
+    return upd
+
+
+def test_ppo_loss_gradient_kernels_vs_autograd_of_the_pinned_losses(upd):
+    """phc_ppo_actor_grad / phc_ppo_critic_grad / phc_disc_logit_grad against autograd of the oracle's loss functions (which
+    tests/test_oracle_golden.py pins to CommonAgent._actor_loss / _critic_loss / bound_loss and AMPAgent._disc_loss): the
+    gradients the kernels hand to the GEMM chain and the statistics they accumulate."""
+    from oracle import phc_oracle as O
+    upd = _bind_more(upd)
+    gen = torch.Generator().manual_seed(4)
+    n, A = 77, 69
+    mu = (torch.randn(n, A, generator=gen) * 0.7).requires_grad_(True)           # some |mu| > 1: the bound loss is active
+    logstd = torch.full((A,), -2.9)
+    sigma = logstd.exp().expand(n, A)
+    old_mu = mu.detach() + 0.02 * torch.randn(n, A, generator=gen)
+    actions = old_mu + sigma * torch.randn(n, A, generator=gen)
+    old_nlp = O.gaussian_neglogp(actions, old_mu, sigma, logstd.expand(n, A))
+    adv = torch.randn(n, generator=gen)
+    e_clip, bound_coef = 0.2, 10.0
+    nlp = O.gaussian_neglogp(actions, mu, sigma, logstd.expand(n, A))
+    a_loss, b_loss = O.actor_loss(old_nlp, nlp, adv, e_clip), O.bound_loss(mu)
+    (a_loss.mean() + bound_coef * b_loss.mean()).backward()
+    dmu, stats = torch.zeros(n, A), torch.zeros(16)
+    c = lambda t: t.detach().float().contiguous()
+    mu_c, act_c, onlp_c, adv_c, omu_c, osig_c = c(mu), c(actions), c(old_nlp), c(adv), c(old_mu), c(sigma)
+    upd.emu_ppo_actor_grad(mu_c.data_ptr(), A, logstd.data_ptr(), act_c.data_ptr(), onlp_c.data_ptr(), adv_c.data_ptr(), omu_c.data_ptr(),
+                           osig_c.data_ptr(), n, A, e_clip, bound_coef, 1.0 / n, dmu.data_ptr(), A, stats.data_ptr())
+    close(dmu, mu.grad, rtol=2e-4, atol=1e-6, what="d loss / d mu")
+    close(stats[0], a_loss.sum().detach(), rtol=1e-4, atol=1e-4, what="sum actor loss")
+    close(stats[1], b_loss.sum().detach(), rtol=1e-4, atol=1e-5, what="sum bound loss")
+    close(stats[3] / n, O.policy_kl(mu.detach(), sigma, old_mu, sigma), rtol=1e-3, atol=1e-5, what="kl")
+    # critic
+    v = torch.randn(n, 1, generator=gen).requires_grad_(True)
+    ret = torch.randn(n, 1, generator=gen)
+    (5.0 * O.critic_loss(v, ret).mean()).backward()
+    dv = torch.zeros(n, 1)
+    v_c, r_c = c(v), c(ret.reshape(-1))
+    upd.emu_ppo_critic_grad(v_c.data_ptr(), 1, r_c.data_ptr(), n, 5.0, 1.0 / n, dv.data_ptr(), 1, stats.data_ptr())
+    close(dv, v.grad, rtol=1e-5, atol=1e-7, what="d loss / d value")
+    close(stats[5], O.critic_loss(v, ret).sum().detach(), rtol=1e-5, atol=1e-5, what="sum critic loss")
+    # discriminator prediction loss: 0.5 * (BCE(agent+replay, 0) + BCE(demo, 1)) (amp_agent.py:737-743)
+    na, nd = 48, 24
+    logit = (torch.randn(na + nd, 1, generator=gen) * 2).requires_grad_(True)
+    bce = torch.nn.functional.binary_cross_entropy_with_logits
+    loss = 0.5 * (bce(logit[:na], torch.zeros(na, 1)) + bce(logit[na:], torch.ones(nd, 1)))
+    (5.0 * loss).backward()
+    dl = torch.zeros(na + nd, 1)
+    l_c = c(logit)
+    upd.emu_disc_logit_grad(l_c.data_ptr(), 1, na, nd, 5.0, dl.data_ptr(), 1, stats.data_ptr())
+    close(dl, logit.grad, rtol=1e-5, atol=1e-7, what="d loss / d logit")
+    close(0.5 * (stats[6] / na + stats[7] / nd), loss.detach(), rtol=1e-5, atol=1e-6, what="disc prediction loss")
+    assert int(stats[8]) == int((logit[:na] < 0).sum()) and int(stats[9]) == int((logit[na:] > 0).sum())
+
+
+def test_clip_and_adam_kernels_vs_torch(upd):
+    """torch.nn.utils.clip_grad_norm_(50) + torch.optim.Adam(lr, eps 1e-8) over three steps (amp_agent.py:670-679)."""
+    upd = _bind_more(upd)
+    gen = torch.Generator().manual_seed(6)
+    n = 5000
+    p0 = torch.randn(n, generator=gen)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=2e-3, eps=1e-8)
+    p, m, v = p0.clone(), torch.zeros(n), torch.zeros(n)
+    sumsq = torch.zeros(1, dtype=torch.float64)
+    for step in range(1, 4):
+        g = torch.randn(n, generator=gen) * (3.0 if step == 2 else 0.3)      # step 2 is clipped (norm ~212 > 50)
+        ref.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([ref], 50.0)
+        opt.step()
+        upd.emu_clip_adam(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, sumsq.data_ptr(), 1.0, 50.0, 2e-3, 0.9, 0.999, 1e-8, step)
+        close(p, ref.detach(), rtol=1e-5, atol=1e-6, what=f"parameters after step {step}")
+
+
+def test_mcp_combine_kernel_vs_reference_golden(upd):
+    """HumanoidImMCP.step's mixing (humanoid_im_mcp.py:64-82, golden from the real class): bit-exact in both modes."""
+    import numpy as np
+    from oracle import mcp_oracle as mo
+    upd = _bind_more(upd)
+    z = np.load(os.path.join(HERE, "golden", "mcp.npz"))
+    sd = {k[len("model/"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("model/")}
+    K = int(z["num_prim"])
+    mean, var = torch.from_numpy(z["rms_mean"]).float(), torch.from_numpy(z["rms_var"]).float()
+    cur = torch.clamp((torch.from_numpy(z["obs_buf"]) - mean) / torch.sqrt(var + 1e-05), -5.0, 5.0)
+    prim = torch.stack(mo.pnn_forward(sd, cur, K), dim=0).contiguous()          # [K, n, A]: the primitives' outputs
+    n, A = prim.shape[1], prim.shape[2]
+    w = torch.from_numpy(z["weights"]).float().contiguous()
+    for discrete, key in ((0, "actions"), (1, "actions_discrete")):
+        out = torch.zeros(n, A)
+        upd.emu_mcp_combine(w.data_ptr(), K, prim.data_ptr(), A, n * A, n, K, A, discrete, out.data_ptr(), A)
+        assert torch.equal(out, torch.from_numpy(z[key])), key
