@@ -43,7 +43,20 @@ static thread_local EmuWarp* emu_warp = nullptr;     // the warp this (lane) thr
 static std::barrier<>* emu_block_bar = nullptr;      // __syncthreads() of the block being emulated (block-level kernels only)
 static inline void __syncthreads() { emu_block_bar->arrive_and_wait(); }
 
-static inline void __syncwarp() { emu_warp->bar.arrive_and_wait(); }
+// PHC_EMU_CHAOS=1: every lane dawdles for a random few microseconds after each collective, so lanes drift as far apart as the
+// program allows -- missing __syncwarp()s then show up as wrong results instead of hiding behind near-lock-step execution.
+#include <chrono>
+#include <cstdlib>
+#include <random>
+static inline void emu_chaos() {
+  static const bool on = [] { const char* v = std::getenv("PHC_EMU_CHAOS"); return v && v[0] == '1'; }();
+  if (!on) return;
+  static thread_local std::minstd_rand rng{std::random_device{}()};
+  const unsigned r = rng() % 8;
+  if (r < 3) std::this_thread::sleep_for(std::chrono::microseconds(20 * (r + 1)));
+  else if (r < 5) std::this_thread::yield();
+}
+static inline void __syncwarp() { emu_warp->bar.arrive_and_wait(); emu_chaos(); }
 template <class T>
 static inline T emu_exchange(T v, int src) {        // a lane outside 0..31 reads its own value (shfl_down / shfl_up at the edge)
   static_assert(sizeof(T) == 4 || sizeof(T) == 8, "32- and 64-bit shuffles");
@@ -53,6 +66,7 @@ static inline T emu_exchange(T v, int src) {        // a lane outside 0..31 read
   emu_warp->bar.arrive_and_wait();
   const uint64_t r = emu_warp->xch[(src < 0 || src > 31) ? emu_lane : src];
   emu_warp->bar.arrive_and_wait();
+  emu_chaos();
   T o;
   std::memcpy(&o, &r, sizeof(T));
   return o;

@@ -223,3 +223,17 @@ def test_wide_kernel_getup_on_the_24_body_golden(emu):
     check(plan, exp, "getup (wide kernel)")
     close(plan._keep["global_offset"], exp["global_offset"], what="global_offset")
     assert torch.equal(cc.long(), exp["cycle_counter"].long())
+
+
+def test_chaos_mode_subset():
+    """The same emulation with every lane dawdling randomly after each collective (PHC_EMU_CHAOS=1, read when the emulation
+    library loads, hence a fresh process): lanes drift as far apart as the synchronisation allows, so a missing __syncwarp()
+    turns into a wrong result.  Runs the cases with the most cross-lane traffic."""
+    import subprocess
+    if os.environ.get("PHC_EMU_CHAOS") == "1":
+        pytest.skip("already inside the chaos run")
+    env = dict(os.environ, PHC_EMU_CHAOS="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider", "-k",
+                        "getup or specialised or wide_kernel_on_the_24_body_goldens or golden[B"], capture_output=True, text=True, env=env,
+                       cwd=os.path.dirname(HERE), timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
