@@ -68,3 +68,41 @@ def test_smplx_getup_vs_reference_golden():
     close(st.global_offset.cpu(), exp["global_offset"], what="global_offset")
     close(pg.cpu(), exp["point_goal"], what="point_goal")
     assert torch.equal(cc.cpu().long(), exp["cycle_counter"].long())
+
+
+def test_g1_task_rollout_and_agent_epoch():
+    """HumanoidIm with Unitree G1 shaped robot tables (38 bodies + 1 extend body, 37 hinge dofs): reset / step against the
+    oracle, then one AMPAgent epoch -- every kernel of the path on the strided variants."""
+    from oracle import phc_oracle as O
+    from phc_b200.env.humanoid_im import HumanoidIm, RLGPUEnv
+    from phc_b200.learning.amp_agent import AMPAgent
+    n = 64
+    m = syn.make_robot_motions(n, seed=8, num_bodies=syn.G1_NUM_BODIES, num_dofs=syn.G1_NUM_DOFS, ext_parents=syn.G1_EXT_PARENTS,
+                               ext_pos=syn.G1_EXT_POS, min_frames=40, max_frames=90)
+    ext = [dict(parent=p, pos=q) for p, q in zip(syn.G1_EXT_PARENTS, syn.G1_EXT_POS)]
+    task = HumanoidIm({"env": {"num_envs": n, "key_body_ids": syn.G1_KEY_BODIES}, "motion_data": m, "seed": 8, "extend_config": ext,
+                       "humanoid_type": "g1"})
+    J, D = syn.G1_NUM_BODIES, syn.G1_NUM_DOFS
+    assert task.get_obs_size() == 1 + 15 * J - 3 + 24 * J and task.get_action_size() == D
+    task.reset()
+    hist = task._amp_obs_buf.cpu().clone()
+    task.step(None)
+    torch.cuda.synchronize()
+    tab = O.RobotTables(m.gts_t, m.grs_t, m.gvs_t, m.gavs_t, m.dof_pos, m.dvs, m.lengths, m.num_frames, m.dts, m.length_starts, J)
+    cfg = O.StepConfig(key_bodies=syn.G1_KEY_BODIES, reset_bodies=None, dof_subset=None)
+    exp = O.env_step_robot(tab, cfg, syn.G1_EXT_PARENTS, syn.G1_EXT_POS, task._rigid_body_state_reshaped.cpu(), task._dof_state.cpu(),
+                           task.dof_force_tensor.cpu(), task.progress_buf.cpu(), task._sampled_motion_ids.cpu(), task._motion_start_times.cpu(),
+                           torch.zeros(n), torch.zeros(n, 3), hist)
+    close(task.obs_buf.cpu(), exp["obs"], atol=2e-6, what="task obs")
+    close(task.rew_buf.cpu(), exp["rew"], what="task rew")
+    close(task.reset_buf.cpu(), exp["reset"], what="task reset")
+    close(task._amp_obs_buf.cpu(), exp["amp_obs_buf"], what="task amp window")
+    agent = AMPAgent("t", {"vec_env": RLGPUEnv(task), "horizon_length": 8, "minibatch_size": 256, "amp_minibatch_size": 64, "mini_epochs": 2,
+                           "amp_obs_demo_buffer_size": 2048, "amp_replay_buffer_size": 2048, "amp_batch_size": 128,
+                           "network": {"mlp": {"units": [128, 64], "activation": "relu"}, "disc": {"units": [128, 64], "activation": "relu"}}})
+    agent.obs = agent.env_reset()
+    agent._init_amp_demo_buf()
+    p0 = agent.model.params.clone()
+    agent.train_epoch()
+    torch.cuda.synchronize()
+    assert torch.isfinite(agent.model.params).all() and not torch.equal(agent.model.params, p0)
