@@ -237,3 +237,26 @@ def test_chaos_mode_subset():
                         "getup or specialised or wide_kernel_on_the_24_body_goldens or golden[B"], capture_output=True, text=True, env=env,
                        cwd=os.path.dirname(HERE), timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_wide_kernel_future_tracks_and_eval_extras(emu):
+    """The strided kernel on fut.npz (T = 3) and its im_eval extras (mpjpe, body_pos_gt) against the oracle."""
+    from oracle import phc_oracle as O
+    from tests.helpers import smpl_step_config, tables_from
+    e, hp = emu
+    g = load("fut.npz")
+    st = syn.EnvState(**{k: g[f"in_{k}"] for k in syn.EnvState.__dataclass_fields__})
+    plan = make_plan(hp, motion_data_from(g), st, smpl_cfg(time_steps=3, traj_dt=1 / 10), with_eval_extras=True)
+    e.run(plan, "wide")
+    check(plan, {k: g[f"out_{k}"] for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf")}, "wide fut", ref_buffers=False)
+    exp = O.env_step(tables_from(g), smpl_step_config(time_steps=3, traj_dt=1 / 10), st.body_state, st.dof_state, st.dof_force, st.progress,
+                     st.motion_ids, st.start_times, st.start_offsets, st.global_offset, st.amp_hist)
+    close(plan.mpjpe, exp["mpjpe"], what="mpjpe")
+    close(plan.body_pos_gt, exp["body_pos_gt"], what="body_pos_gt")
+    for k in ("ref_body_pos", "ref_body_rot", "ref_body_vel"):
+        close(getattr(plan, k), exp[k], what=k)
+    # and the staged kernel's extras on the same inputs
+    plan2 = make_plan(hp, motion_data_from(g), st, smpl_cfg(time_steps=3, traj_dt=1 / 10), with_eval_extras=True)
+    e.run(plan2, "fut")
+    close(plan2.mpjpe, exp["mpjpe"], what="mpjpe (staged kernel)")
+    close(plan2.body_pos_gt, exp["body_pos_gt"], what="body_pos_gt (staged kernel)")
