@@ -342,6 +342,29 @@ PHC_API int phc_gemm_tc5(const float* A_hi, const float* A_lo, int64_t lda, int3
                  int64_t ldb, int32_t b_kmajor, float* C, float* C_hi /* optional: split copies of C for the next GEMM */,
                  float* C_lo, int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha, const float* bias, int32_t act,
                  float* aux, int64_t ldaux, int32_t accumulate, int32_t k_splits, void* stream);
+/* The same GEMM with the 3xTF32 operand split done in SHARED memory (gemm_tc5s.cu): plain fp32 operands, no pre-split
+ * copies; TMA tensor stores (reduce-add for accumulate / split-K).  A, B, C 16-byte aligned; lda, ldb, ldc multiples of 4.
+ * phc_gemm_group runs up to PHC_GEMM_GROUP_MAX independent problems (e.g. the same layer of actor, critic and
+ * discriminator: network_builder.py:105-124 builds three separate nn.Sequential stacks that the reference evaluates one
+ * after the other) as ONE persistent launch over the union of their tiles. */
+#define PHC_GEMM_GROUP_MAX 6
+typedef struct PhcGemmDesc {
+  const float* A; int64_t lda; int32_t a_kmajor;
+  const float* B; int64_t ldb; int32_t b_kmajor;
+  float* C; int64_t ldc;
+  int32_t M, N, K;
+  float alpha;
+  const float* bias;        /* optional [N] */
+  int32_t act;              /* PHC_ACT_* */
+  float* aux; int64_t ldaux;
+  int32_t accumulate, k_splits;
+} PhcGemmDesc;
+PHC_API int phc_gemm_group(const PhcGemmDesc* problems, int32_t count, void* stream);
+PHC_API int phc_gemm_tc5s(const float* A, int64_t lda, int32_t a_kmajor, const float* B, int64_t ldb, int32_t b_kmajor, float* C,
+                  int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha, const float* bias, int32_t act,
+                  float* aux, int64_t ldaux, int32_t accumulate, int32_t k_splits, void* stream);
+/* tile configuration switch (tests / tools): 1 = 128 x 128 tile per CTA, 2 = 256 x 128 tile per CTA pair, 0 = default */
+PHC_API int phc_gemm_tc5s_set_ctas(int32_t ctas);
 /* out[n] (+)= alpha * sum_m X[m*ld + n]   (bias gradients) */
 PHC_API int phc_colsum(const float* X, int64_t ld, int32_t M, int32_t N, float alpha, float* out, int32_t accumulate,
                void* stream);

@@ -72,6 +72,14 @@ class PhcStepArgs(C.Structure):
     ]
 
 
+class PhcGemmDesc(C.Structure):
+    _fields_ = [("A", _p), ("lda", C.c_int64), ("a_kmajor", C.c_int32), ("B", _p), ("ldb", C.c_int64), ("b_kmajor", C.c_int32),
+                ("C", _p), ("ldc", C.c_int64), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("alpha", C.c_float),
+                ("bias", _p), ("act", C.c_int32), ("aux", _p), ("ldaux", C.c_int64), ("accumulate", C.c_int32), ("k_splits", C.c_int32)]
+
+
+PHC_GEMM_GROUP_MAX = 6
+
 # name -> (restype, argtypes); must list every symbol include/phc_b200.h declares (tests check this)
 SIGNATURES = {
     "phc_version": (C.c_int, []),
@@ -106,6 +114,10 @@ SIGNATURES = {
     "phc_split_tf32": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, _p, _p, C.c_int64, _p]),
     "phc_gemm_tc5": (C.c_int, [_p, _p, C.c_int64, C.c_int32, _p, _p, C.c_int64, C.c_int32, _p, _p, _p, C.c_int64, C.c_int32, C.c_int32,
                                C.c_int32, C.c_float, _p, C.c_int32, _p, C.c_int64, C.c_int32, C.c_int32, _p]),
+    "phc_gemm_group": (C.c_int, [C.POINTER(PhcGemmDesc), C.c_int32, _p]),
+    "phc_gemm_tc5s": (C.c_int, [_p, C.c_int64, C.c_int32, _p, C.c_int64, C.c_int32, _p, C.c_int64, C.c_int32, C.c_int32,
+                                C.c_int32, C.c_float, _p, C.c_int32, _p, C.c_int64, C.c_int32, C.c_int32, _p]),
+    "phc_gemm_tc5s_set_ctas": (C.c_int, [C.c_int32]),
     "phc_colsum": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p, C.c_int32, _p]),
     "phc_rms_apply": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, _p, _p, C.c_float, C.c_int32, _p, C.c_int64, _p, _p]),
     "phc_rms_workspace_bytes": (C.c_int64, [C.c_int32]),

@@ -35,6 +35,7 @@ SOURCES = {
     "ppo_scalars.cu": ["-fmad=false"],
     "gemm.cu": [],
     "gemm_tc5.cu": [],
+    "gemm_tc5s.cu": [],
     "ppo_update.cu": [],
 }
 

@@ -198,7 +198,7 @@ class MLPEngine:
         # "tc5" (default): tcgen05 / TMEM / TMA 3xTF32 (gemm_tc5.cu); "mma": warp-level mma.sync 3xTF32 (gemm.cu), kept as
         # the cross-check implementation (PHC_GEMM=mma)
         self.backend = backend or os.environ.get("PHC_GEMM", "tc5")
-        assert self.backend in ("mma", "tc5")
+        assert self.backend in ("mma", "tc5", "tc5s")
         self._companions: Dict[Tuple[int, Tuple[int, ...], Tuple[int, ...]], Tuple[torch.Tensor, torch.Tensor]] = {}
         if self.backend == "tc5":
             net.refresh_split()
@@ -254,7 +254,8 @@ class MLPEngine:
             if rc:
                 _lib.check(rc, "phc_gemm_tc5")
             return (Ch, Cl) if Ch is not None else None
-        rc = self.lib.phc_gemm(A.data_ptr(), lda, 1 if a_k else 0, B.data_ptr(), ldb, 1 if b_k else 0, C.data_ptr(),
+        fn = self.lib.phc_gemm_tc5s if self.backend == "tc5s" else self.lib.phc_gemm
+        rc = fn(A.data_ptr(), lda, 1 if a_k else 0, B.data_ptr(), ldb, 1 if b_k else 0, C.data_ptr(),
                                C.stride(0), M, N, K, alpha, _ptr(bias), act, _ptr(mask),
                                mask.stride(0) if mask is not None else 0, 1 if accumulate else 0, k_splits, _stream())
         if rc:

@@ -35,7 +35,8 @@ def test_ctypes_struct_layout_matches_header_order():
     """Field order of the ctypes mirrors follows the header (guards against silent ABI drift)."""
     from phc_b200 import _lib
     src = open(os.path.join(ROOT, "include", "phc_b200.h")).read()
-    for cname, cls in (("PhcMotionLib", _lib.PhcMotionLib), ("PhcMotionStateOut", _lib.PhcMotionStateOut), ("PhcStepArgs", _lib.PhcStepArgs)):
+    for cname, cls in (("PhcMotionLib", _lib.PhcMotionLib), ("PhcMotionStateOut", _lib.PhcMotionStateOut), ("PhcStepArgs", _lib.PhcStepArgs),
+                       ("PhcGemmDesc", _lib.PhcGemmDesc)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), src, re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []
