@@ -326,6 +326,13 @@ PHC_API int phc_adv_norm(const float* returns, const float* values, int64_t n, i
 #define PHC_ACT_RELU 1
 #define PHC_ACT_SILU 2
 #define PHC_ACT_SILU_BWD 3
+/* phc_gemm_tc5s / phc_gemm_group only -- the ReLU mask as ONE BIT per element instead of re-reading the fp32 activations in
+ * the backward pass (32x less traffic): aux is then a uint32 array [M, ldaux] (ldaux in words, >= ceil(N / 32)), bit j of
+ * word (m, n / 32) belongs to column n = 32 * (n / 32) + j.
+ *   PHC_ACT_RELU_BITS : out = relu(x); aux (optional) receives the bits (x > 0)
+ *   PHC_ACT_MASK_BITS : out *= bit     (aux required, read) */
+#define PHC_ACT_RELU_BITS 4
+#define PHC_ACT_MASK_BITS 5
 /* C[M,N] (+)= epi(alpha * sum_k A(m,k) B(n,k)).  a_kmajor: A(m,k) = A[m*lda + k] (else A[k*lda + m]); b_kmajor: B(n,k) =
  * B[n*ldb + k] (else B[k*ldb + n]).  Forward Y = X W^T: (1,1); input gradient dX = dY W: (1,0); weight gradient
  * dW = dY^T X: (0,0).  Epilogue in order: *alpha, +bias[n], activation `act` / aux (above), then store or atomic
@@ -347,7 +354,7 @@ PHC_API int phc_gemm_tc5(const float* A_hi, const float* A_lo, int64_t lda, int3
  * phc_gemm_group runs up to PHC_GEMM_GROUP_MAX independent problems (e.g. the same layer of actor, critic and
  * discriminator: network_builder.py:105-124 builds three separate nn.Sequential stacks that the reference evaluates one
  * after the other) as ONE persistent launch over the union of their tiles. */
-#define PHC_GEMM_GROUP_MAX 6
+#define PHC_GEMM_GROUP_MAX 8
 typedef struct PhcGemmDesc {
   const float* A; int64_t lda; int32_t a_kmajor;
   const float* B; int64_t ldb; int32_t b_kmajor;

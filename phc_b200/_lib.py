@@ -24,7 +24,7 @@ PHC_FLAG_REWARD_FROM_CACHE = 1 << 8
 PHC_FLAG_ZERO_OUT_FAR = 1 << 9
 PHC_FLAG_CYCLE_MOTION = 1 << 10
 PHC_FLAG_NO_SPECIALISE = 1 << 11
-PHC_ACT_NONE, PHC_ACT_RELU, PHC_ACT_SILU, PHC_ACT_SILU_BWD = 0, 1, 2, 3
+PHC_ACT_NONE, PHC_ACT_RELU, PHC_ACT_SILU, PHC_ACT_SILU_BWD, PHC_ACT_RELU_BITS, PHC_ACT_MASK_BITS = 0, 1, 2, 3, 4, 5
 PHC_MAX_KEY_BODIES = 8
 PHC_MAX_BODIES = 64
 PHC_LANE_BODIES = 32
@@ -78,7 +78,7 @@ class PhcGemmDesc(C.Structure):
                 ("bias", _p), ("act", C.c_int32), ("aux", _p), ("ldaux", C.c_int64), ("accumulate", C.c_int32), ("k_splits", C.c_int32)]
 
 
-PHC_GEMM_GROUP_MAX = 6
+PHC_GEMM_GROUP_MAX = 8
 
 # name -> (restype, argtypes); must list every symbol include/phc_b200.h declares (tests check this)
 SIGNATURES = {

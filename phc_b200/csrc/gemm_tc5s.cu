@@ -51,9 +51,12 @@ struct Cfg {
   static constexpr int B_ROWS = BN / CTAS;
   static constexpr int B_TILE = B_ROWS * BK * 4;
   static constexpr int RAW = A_TILE + B_TILE;         // bytes TMA writes per stage
-  static constexpr int STAGE = 2 * RAW;               // + the lo tiles
-  static constexpr int STAGES = CTAS == 1 ? 3 : 4;
-  static constexpr int SMEM = STAGES * STAGE + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // the raw ring (TMA prefetch depth) is decoupled from the lo ring: a lo tile lives only from its split to the MMAs of its
+  // k-block, so two lo slots suffice while 4 (6) raw stages cover the L2 -> shared-memory latency (the first version kept
+  // raw + lo together, 3 stages of 64 KB: one in MMA, one in split, ONE in flight -> 1630 cycles per k-block instead of 768)
+  static constexpr int RAW_STAGES = CTAS == 1 ? 4 : 6;
+  static constexpr int LO_STAGES = 2;
+  static constexpr int SMEM = (RAW_STAGES + LO_STAGES) * RAW + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct Prob {
@@ -115,11 +118,13 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
   using C = Cfg<CTAS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* epi_smem = smem + C::STAGES * C::STAGE;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPI_BYTES);
-  uint64_t* split_bar = full_bar + C::STAGES;
-  uint64_t* empty_bar = split_bar + C::STAGES;
-  uint64_t* tmem_full = empty_bar + C::STAGES;      // [2]
+  uint8_t* lo_smem = smem + C::RAW_STAGES * C::RAW;
+  uint8_t* epi_smem = lo_smem + C::LO_STAGES * C::RAW;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPI_BYTES);     // [R] TMA bytes landed (local)
+  uint64_t* raw_empty = full_bar + C::RAW_STAGES;                            // [R] MMAs that read the raw stage are done
+  uint64_t* lo_full = raw_empty + C::RAW_STAGES;                             // [L] lo slot written (all splitter warps; leader's copy)
+  uint64_t* lo_empty = lo_full + C::LO_STAGES;                               // [L] MMAs that read the lo slot are done
+  uint64_t* tmem_full = lo_empty + C::LO_STAGES;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;             // [2] (pair mode: the leader's copies are the ones waited on)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -129,11 +134,8 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
   const int unit = blockIdx.x / CTAS, num_units = gridDim.x / CTAS;     // a unit = one CTA or one CTA pair
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(full_bar + s, 1);
-      mbar_init(split_bar + s, NUM_SPLIT_WARPS * CTAS);
-      mbar_init(empty_bar + s, 1);
-    }
+    for (int s = 0; s < C::RAW_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(raw_empty + s, 1); }
+    for (int s = 0; s < C::LO_STAGES; ++s) { mbar_init(lo_full + s, NUM_SPLIT_WARPS * CTAS); mbar_init(lo_empty + s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 4 * CTAS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -159,9 +161,9 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
         const CUtensorMap* tB = &P.tmB[tl.g];
         const int nb0 = tl.n0 + (int)rank * C::B_ROWS;
         for (int i = 0; i < tl.nkb; ++i, ++it) {
-          const int s = it % C::STAGES;
-          if (it >= (uint32_t)C::STAGES) mbar_wait(empty_bar + s, ((it / C::STAGES) - 1) & 1);
-          uint8_t* st = smem + s * C::STAGE;
+          const int s = it % C::RAW_STAGES;
+          if (it >= (uint32_t)C::RAW_STAGES) mbar_wait(raw_empty + s, ((it / C::RAW_STAGES) - 1) & 1);
+          uint8_t* st = smem + s * C::RAW;
           const int k0 = (tl.kb_begin + i) * BK;
           mbar_expect_tx(full_bar + s, C::RAW);
           if (q.a_k) tma_load_2d(st, tA, full_bar + s, k0, tl.m0);
@@ -195,18 +197,17 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int i = 0; i < tl.nkb; ++i, ++it) {
-          const int s = it % C::STAGES;
-          const uint32_t ph = (it / C::STAGES) & 1;
-          mbar_wait(full_bar + s, ph);                              // own raw tiles (the peer's are implied by its splitters)
-          mbar_wait(split_bar + s, ph);                             // lo tiles of both CTAs written and fenced
+          const int s = it % C::RAW_STAGES, l = it % C::LO_STAGES;
+          mbar_wait(full_bar + s, (it / C::RAW_STAGES) & 1);        // own raw tiles (the peer's are implied by its splitters)
+          mbar_wait(lo_full + l, (it / C::LO_STAGES) & 1);          // lo tiles of both CTAs written and fenced
           tc_fence_after();
-          const uint32_t st = s32(smem + s * C::STAGE);
+          const uint32_t st = s32(smem + s * C::RAW), sl = s32(lo_smem + l * C::RAW);
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
             const uint64_t dAh = smem_desc(st + kk * a_step, a_lbo, a_sbo, a_lt);
-            const uint64_t dAl = smem_desc(st + C::RAW + kk * a_step, a_lbo, a_sbo, a_lt);
+            const uint64_t dAl = smem_desc(sl + kk * a_step, a_lbo, a_sbo, a_lt);
             const uint64_t dBh = smem_desc(st + A_TILE + kk * b_step, b_lbo, b_sbo, b_lt);
-            const uint64_t dBl = smem_desc(st + C::RAW + A_TILE + kk * b_step, b_lbo, b_sbo, b_lt);
+            const uint64_t dBl = smem_desc(sl + A_TILE + kk * b_step, b_lbo, b_sbo, b_lt);
             const uint32_t first = (i > 0 || kk > 0) ? 1u : 0u;
             if (CTAS == 2) {
               umma_tf32_2cta(tmem_d, dAl, dBh, idesc, first);
@@ -218,7 +219,8 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
               umma_tf32(tmem_d, dAh, dBh, idesc, 1u);
             }
           }
-          if (CTAS == 2) umma_commit_2cta(empty_bar + s); else umma_commit(empty_bar + s);     // frees the stage (both CTAs)
+          if (CTAS == 2) { umma_commit_2cta(raw_empty + s); umma_commit_2cta(lo_empty + l); }      // frees both slots (in both CTAs)
+          else { umma_commit(raw_empty + s); umma_commit(lo_empty + l); }
         }
         if (CTAS == 2) umma_commit_2cta(tmem_full + acc); else umma_commit(tmem_full + acc);
       }
@@ -233,18 +235,20 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
     for (int t = unit; t < P.total_tiles; t += num_units) {
       const Tile tl = decode<CTAS>(P, t, (int)rank);
       for (int i = 0; i < tl.nkb; ++i, ++it) {
-        const int s = it % C::STAGES;
-        mbar_wait(full_bar + s, (it / C::STAGES) & 1);
-        const uint32_t raw = s32(smem + s * C::STAGE) + (uint32_t)tid * 16u;
+        const int s = it % C::RAW_STAGES, l = it % C::LO_STAGES;
+        mbar_wait(full_bar + s, (it / C::RAW_STAGES) & 1);
+        const uint32_t raw = s32(smem + s * C::RAW) + (uint32_t)tid * 16u;
+        const uint32_t lo = s32(lo_smem + l * C::RAW) + (uint32_t)tid * 16u;
         float4 v[PER];
 #pragma unroll
         for (int j = 0; j < PER; ++j) v[j] = lds128(raw + j * NT * 16);
+        if (it >= (uint32_t)C::LO_STAGES) mbar_wait(lo_empty + l, ((it / C::LO_STAGES) - 1) & 1);   // the MMAs of k-block it - 2 are done
 #pragma unroll
         for (int j = 0; j < PER; ++j)
-          sts128(raw + C::RAW + j * NT * 16, split_lo(v[j].x), split_lo(v[j].y), split_lo(v[j].z), split_lo(v[j].w));
+          sts128(lo + j * NT * 16, split_lo(v[j].x), split_lo(v[j].y), split_lo(v[j].z), split_lo(v[j].w));
         fence_proxy_async_smem();                              // generic-proxy writes -> visible to the tensor core's reads
         __syncwarp();
-        if (lane == 0) { if (CTAS == 2) mbar_arrive_remote_leader(split_bar + s); else mbar_arrive(split_bar + s); }
+        if (lane == 0) { if (CTAS == 2) mbar_arrive_remote_leader(lo_full + l); else mbar_arrive(lo_full + l); }
       }
     }
   } else {
@@ -263,13 +267,19 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
       const int act = q.act;
       const float alpha = q.alpha;
       const float* bias = (q.bias && tl.z == 0) ? q.bias : nullptr;
-      float* arow = q.aux ? q.aux + (long long)m * q.ldaux : nullptr;
+      float* arow = (q.aux && act < PHC_ACT_RELU_BITS) ? q.aux + (long long)m * q.ldaux : nullptr;
       const bool aux_vec = arow && ((q.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(q.aux) & 15) == 0);
       if (tl.nkb > 0) {
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           const int nb = tl.n0 + c0;
           if (nb >= q.N) break;                                  // warp-uniform
+          // loads that do not depend on the accumulator go first: the bias slice of this chunk (one coalesced load, handed
+          // round by shuffles) and, for the bit-mask modes, this row's 32 sign bits
+          const float bias_l = (bias && nb + lane < q.N) ? bias[nb + lane] : 0.0f;
+          uint32_t* bits = (act >= PHC_ACT_RELU_BITS && q.aux && row_ok)
+                               ? reinterpret_cast<uint32_t*>(q.aux) + (long long)m * q.ldaux + (nb >> 5) : nullptr;
+          const uint32_t mbits = (act == PHC_ACT_MASK_BITS && bits) ? *bits : 0u;
           uint32_t r[32];
           tmem_ld32(tmem_base + acc * BN + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
           if (c0 + 32 >= BN || nb + 32 >= q.N) {                 // last chunk read: hand the accumulator back before the math / store
@@ -281,11 +291,19 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = alpha * __uint_as_float(r[j]);
-            if (bias && nb + j < q.N) x += bias[nb + j];
-            if (act == PHC_ACT_RELU) x = fmaxf(x, 0.f);
+            if (bias) x += __shfl_sync(0xffffffffu, bias_l, j);
+            if (act == PHC_ACT_RELU || act == PHC_ACT_RELU_BITS) x = fmaxf(x, 0.f);
             v[j] = x;
           }
-          if (act == PHC_ACT_SILU) {
+          if (act == PHC_ACT_RELU_BITS) {                        // ReLU forward: 1 bit per element for the backward pass
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+            if (bits) *bits = w;
+          } else if (act == PHC_ACT_MASK_BITS) {                 // ReLU backward from the saved bits
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ((mbits >> j) & 1u) ? v[j] : 0.f;
+          } else if (act == PHC_ACT_SILU) {
             if (arow && row_ok) {                                // pre-activation out
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -378,7 +396,8 @@ extern "C" int phc_gemm_group(const PhcGemmDesc* d, int32_t count, void* stream)
     for (const void* p : {(const void*)g.A, (const void*)g.B, (const void*)g.C})
       if (reinterpret_cast<uintptr_t>(p) & 15) { phc_set_error("phc_gemm_group: A, B, C must be 16-byte aligned"); return PHC_ERR_INVALID_ARG; }
     int ks = g.k_splits < 1 ? 1 : g.k_splits;
-    if (g.act < 0 || g.act > PHC_ACT_SILU_BWD || (g.act == PHC_ACT_SILU_BWD && !g.aux)) { phc_set_error("phc_gemm_group: bad activation code"); return PHC_ERR_INVALID_ARG; }
+    if (g.act < 0 || g.act > PHC_ACT_MASK_BITS || ((g.act == PHC_ACT_SILU_BWD || g.act == PHC_ACT_MASK_BITS) && !g.aux)) { phc_set_error("phc_gemm_group: bad activation code"); return PHC_ERR_INVALID_ARG; }
+    if (g.act >= PHC_ACT_RELU_BITS && g.aux && ((reinterpret_cast<uintptr_t>(g.aux) & 3) || g.ldaux < (g.N + 31) / 32)) { phc_set_error("phc_gemm_group: bit-mask aux needs ldaux >= ceil(N / 32) words"); return PHC_ERR_INVALID_ARG; }
     if (ks > 1 && (!g.accumulate || g.act || g.aux)) { phc_set_error("phc_gemm_group: split-K needs accumulate=1 and a linear epilogue"); return PHC_ERR_INVALID_ARG; }
     Prob& q = P.p[n];
     q.bias = g.bias; q.aux = g.aux; q.ldaux = g.ldaux; q.M = g.M; q.N = g.N; q.K = g.K; q.alpha = g.alpha; q.act = g.act;

@@ -349,8 +349,12 @@ class AMPAgent:
         """CommonAgent.get_action_values (common_agent.py:262-288): normalise, actor + critic forward, sample."""
         N = self.num_actors
         x = self._preproc_obs(obs["obs"], out=self._x_roll)
-        mu = self.engine.forward(self.model.actor, x, self._ws_actor_roll)
-        val = self.engine.forward(self.model.critic, x, self._ws_critic_roll)
+        if self.engine.backend == "tc5s":          # actor and critic layer by layer in the same launches
+            self.engine.forward_group([(self.model.actor, x, self._ws_actor_roll), (self.model.critic, x, self._ws_critic_roll)])
+            mu, val = self._ws_actor_roll["out"], self._ws_critic_roll["out"]
+        else:
+            mu = self.engine.forward(self.model.actor, x, self._ws_actor_roll)
+            val = self.engine.forward(self.model.critic, x, self._ws_critic_roll)
         torch.randn(self._noise.shape, out=self._noise)
         res = {"actions": torch.empty(N, self.actions_num, device=self.device),
                "neglogpacs": torch.empty(N, device=self.device),
@@ -508,6 +512,29 @@ class AMPAgent:
         net.grads.zero_()
 
         T = self.timer
+        if eng.backend == "tc5s":
+            self._update_grouped(ds, idx, B, Bd, A, inv_b, st)
+        else:
+            self._update_sequential(ds, idx, B, Bd, A, inv_b, st)
+
+        # ---- all-reduce, clip, Adam -----------------------------------------------------------------------------
+        t_opt = T("update.optim")
+        t_opt.__enter__()
+        grad_scale = D.allreduce_grad_bucket(net.grads) if self.multi_gpu else 1.0
+        self.opt_step += 1
+        _lib.check(lib.phc_grad_sumsq(net.grads.data_ptr(), net.num_floats, self._gsumsq.data_ptr(), st))
+        _lib.check(lib.phc_adam_step(net.params.data_ptr(), net.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                     net.num_floats, self._gsumsq.data_ptr(), grad_scale,
+                                     self.grad_norm if self.truncate_grads else 0.0, self.last_lr, 0.9, 0.999, 1e-8,
+                                     self.opt_step, st))
+        if eng.backend == "tc5":
+            net.refresh_split()                    # hi/lo operand copies of the updated weights
+        t_opt.__exit__()
+        self._last_B, self._last_Bd = B, Bd
+
+    def _update_sequential(self, ds, idx, B, Bd, A, inv_b, st) -> None:
+        """Forward / losses / backward one network after the other, one launch per GEMM (mma.sync and pre-split tcgen05 back ends)."""
+        lib, net, eng, T = self._lib, self.model, self.engine, self.timer
         # ---- actor / critic ----------------------------------------------------------------------------------
         with T("update.preproc_obs"):
             x = self._preproc_obs(ds["obs"], use_temp=self.temp_running_mean, out=self._x_mb, row_idx=idx)
@@ -552,20 +579,116 @@ class AMPAgent:
                     _lib.check(lib.phc_axpy2d(net.weight(l).data_ptr(), l.in_pad, net.weight(l, True).data_ptr(), l.in_pad, l.out_dim,
                                               l.in_dim, 2.0 * self._disc_coef * self._disc_weight_decay, self._stats[12:].data_ptr(), st))
 
-        # ---- all-reduce, clip, Adam -----------------------------------------------------------------------------
-        t_opt = T("update.optim")
-        t_opt.__enter__()
-        grad_scale = D.allreduce_grad_bucket(net.grads) if self.multi_gpu else 1.0
-        self.opt_step += 1
-        _lib.check(lib.phc_grad_sumsq(net.grads.data_ptr(), net.num_floats, self._gsumsq.data_ptr(), st))
-        _lib.check(lib.phc_adam_step(net.params.data_ptr(), net.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                                     net.num_floats, self._gsumsq.data_ptr(), grad_scale,
-                                     self.grad_norm if self.truncate_grads else 0.0, self.last_lr, 0.9, 0.999, 1e-8,
-                                     self.opt_step, st))
-        if eng.backend == "tc5":
-            net.refresh_split()                    # hi/lo operand copies of the updated weights
-        t_opt.__exit__()
-        self._last_B, self._last_Bd = B, Bd
+
+    def _loss_grads(self, ds, idx, B, Bd, A, inv_b, st, mu, val, logits) -> None:
+        lib, net = self._lib, self.model
+        actions, old_nlp, adv = ds["actions"][idx], ds["old_logp_actions"][idx], ds["advantages"][idx]
+        old_mu, old_sigma, rets = ds["mu"][idx], ds["sigma"][idx], ds["returns"][idx].reshape(-1)
+        dmu, dv, dl = self._ws_actor["dout"], self._ws_critic["dout"], self._ws_disc["dout"]
+        _lib.check(lib.phc_ppo_actor_grad(mu.data_ptr(), mu.stride(0), net.sigma.data_ptr(), actions.data_ptr(), old_nlp.data_ptr(),
+                                          adv.data_ptr(), old_mu.data_ptr(), old_sigma.data_ptr(), B, A, self.e_clip,
+                                          self.bounds_loss_coef, inv_b, dmu.data_ptr(), dmu.stride(0), self._stats.data_ptr(), st))
+        _lib.check(lib.phc_ppo_critic_grad(val.data_ptr(), val.stride(0), rets.data_ptr(), B, self.critic_coef, inv_b,
+                                           dv.data_ptr(), dv.stride(0), self._stats.data_ptr(), st))
+        _lib.check(lib.phc_disc_logit_grad(logits.data_ptr(), logits.stride(0), 2 * Bd, Bd, self._disc_coef, dl.data_ptr(),
+                                           dl.stride(0), self._stats.data_ptr(), st))
+
+    def _update_grouped(self, ds, idx, B, Bd, A, inv_b, st) -> None:
+        """The same minibatch with the grouped GEMM (phc_gemm_group): actor, critic and discriminator advance layer by layer
+        TOGETHER -- one persistent launch per layer index forward (3 problems), one per layer index backward (dW and dX of the
+        three networks plus the step of the gradient-penalty chain that is ready: up to 8 problems) -- instead of ~30 separate
+        GEMM launches whose tile counts each leave a partial last wave on the 148 SMs."""
+        lib, net, eng, T = self._lib, self.model, self.engine, self.timer
+        with T("update.preproc_obs"):
+            x = self._preproc_obs(ds["obs"], use_temp=self.temp_running_mean, out=self._x_mb, row_idx=idx)
+        with T("update.disc_preproc"):
+            aidx = idx[:Bd]
+            xa = self._amp_mb
+            self._preproc_amp_obs(ds["amp_obs"], xa[0:Bd], row_idx=aidx)
+            self._preproc_amp_obs(self._amp_replay_src, xa[Bd:2 * Bd], row_idx=ds["amp_obs_replay_idx"][aidx])
+            self._preproc_amp_obs(self._amp_obs_demo_buffer.data, xa[2 * Bd:3 * Bd], row_idx=ds["amp_obs_demo_idx"][aidx])
+        self._grouped_core(x, xa, Bd, st, lambda: self._loss_grads(ds, idx, B, Bd, A, inv_b, st, self._ws_actor["out"], self._ws_critic["out"],
+                                                                   self._ws_disc["out"]))
+
+    def _grouped_core(self, x, xa, Bd, st, loss_fn) -> None:
+        """forward (grouped) -> loss_fn() writes d loss / d outputs into the workspaces' `dout` -> backward (grouped, with the
+        gradient-penalty chain merged in) -> discriminator regularisers.  x / xa are the normalised, zero-padded inputs."""
+        lib, net, eng, T = self._lib, self.model, self.engine, self.timer
+        stacks = [(net.actor, x, self._ws_actor), (net.critic, x, self._ws_critic), (net.disc, xa, self._ws_disc)]
+        with T("update.forward"):
+            eng.forward_group(stacks)
+        with T("update.losses"):
+            loss_fn()
+            for stk, _, ws in stacks:
+                if stk.head_relu:                       # MCP composer: activation after the head
+                    silu = stk.activation == "silu"
+                    aux = ws["z_out"] if silu else ws["out"]
+                    _lib.check(lib.phc_act_backward(ws["dout"].data_ptr(), ws["dout"].stride(0), aux.data_ptr(), aux.stride(0), ws["dout"].shape[0],
+                                                    stk.out_dim, _lib.PHC_ACT_SILU if silu else _lib.PHC_ACT_RELU, st))
+        with T("update.backward"):
+            gp = self._gp_steps(xa[2 * Bd:3 * Bd], Bd, st)
+            depth = max(len(stk.layers) for stk, _, _ in stacks)
+            for k in range(max(depth, len(gp))):
+                descs, sums = [], []
+                for stk, xin, ws in stacks:
+                    li = len(stk.layers) - 1 - k
+                    if li >= 0:
+                        dw, dx = eng.bwd_descs(stk, li, xin, ws)
+                        descs += [dw, dx]
+                        l = stk.layers[li]
+                        dY = ws["dout"] if li == len(stk.layers) - 1 else ws["dh"][li]
+                        sums.append((dY, dY.shape[0], l.out_dim, net.bias(l, grad=True)))
+                after = None
+                if k < len(gp):
+                    gdescs, after = gp[k]
+                    descs += gdescs
+                eng.run_group(descs)
+                for dY, rows, n, out in sums:
+                    eng.colsum(dY, rows, n, out)
+                if after is not None:
+                    after()
+            head = net.disc.head
+            _lib.check(lib.phc_axpy2d(net.weight(head).data_ptr(), head.in_pad, net.weight(head, True).data_ptr(), head.in_pad, 1,
+                                      head.in_dim, 2.0 * self._disc_coef * self._disc_logit_reg, self._stats[11:].data_ptr(), st))
+            if self._disc_weight_decay != 0:
+                for l in net.disc.layers:
+                    _lib.check(lib.phc_axpy2d(net.weight(l).data_ptr(), l.in_pad, net.weight(l, True).data_ptr(), l.in_pad, l.out_dim,
+                                              l.in_dim, 2.0 * self._disc_coef * self._disc_weight_decay, self._stats[12:].data_ptr(), st))
+
+    def _gp_steps(self, x_demo: torch.Tensor, Bd: int, st):
+        """The gradient-penalty chain of _disc_grad_penalty_backward as a list of steps [(problems, after-hook)] that
+        _update_grouped merges into its per-layer launches: L input-gradient GEMMs down to g = d logit / d x, the penalty
+        itself (phc_scale_sumsq), then per layer the weight-gradient and the forward-form GEMM of the backward chain."""
+        lib, net, eng = self._lib, self.model, self.engine
+        from .networks import group_splits
+        hid, head = net.disc.hidden, net.disc.head
+        L = len(hid)
+        ws = self._ws_disc
+        h_demo = [h[2 * Bd:3 * Bd] for h in ws["h"]]
+        bits = [hb[2 * Bd:3 * Bd] for hb in ws["hbits"]] if "hbits" in ws else None
+        mask = lambda i: dict(act=_lib.PHC_ACT_MASK_BITS, aux=bits[i]) if bits is not None else dict(aux=h_demo[i])
+        u, e, g = self._gp_u, self._gp_e, self._gp_g
+        _lib.check(lib.phc_relu_mask_row(h_demo[L - 1].data_ptr(), h_demo[L - 1].stride(0), net.weight(head).data_ptr(), Bd,
+                                         hid[L - 1].out_dim, u[L - 1].data_ptr(), u[L - 1].stride(0), st))
+        steps = []
+        for li in range(L - 1, 0, -1):
+            l = hid[li]
+            steps.append(([eng.gdesc(u[li], True, net.weight(l), False, u[li - 1], Bd, l.in_dim, l.out_dim, **mask(li - 1))], None))
+        l0 = hid[0]
+        c = self._disc_coef * self._disc_grad_penalty
+
+        def penalty():
+            _lib.check(lib.phc_scale_sumsq(g.data_ptr(), g.stride(0), Bd, l0.in_dim, 2.0 * c / Bd, self._stats[10:].data_ptr(), st))
+        steps.append(([eng.gdesc(u[0], True, net.weight(l0), False, g, Bd, l0.in_dim, l0.out_dim)], penalty))
+        for li in range(L):
+            l = hid[li]
+            src = g if li == 0 else e[li - 1]
+            after = None
+            if li == L - 1:
+                after = lambda: eng.colsum(e[L - 1], Bd, hid[L - 1].out_dim, net.weight(head, True))
+            steps.append(([eng.gdesc(u[li], False, src, False, net.weight(l, True), l.out_dim, l.in_dim, Bd, accumulate=True, k_splits=group_splits(Bd)),
+                           eng.gdesc(src, True, net.weight(l), True, e[li], Bd, l.out_dim, l.in_dim, **mask(li))], after))
+        return steps
 
     def _disc_grad_penalty_backward(self, x_demo: torch.Tensor, h_demo, Bd: int) -> None:
         """Gradient penalty 5 * mean_b ||d logit_b / d x_b||^2 on the demo rows (amp_agent.py:749-768), hand-derived for

@@ -187,6 +187,14 @@ def _splits(tiles: int, K: int) -> int:
     return int(max(1, min(want, K // 512, 64)))
 
 
+def group_splits(K: int) -> int:
+    """split-K factor of a weight-gradient problem inside a grouped launch (K = batch rows): about 32 k-blocks of 32 rows per
+    split, so a dW tile costs about as much as a dX / forward tile of the same launch (the static tile striding then balances)."""
+    env = os.environ.get("PHC_DW_KB_PER_SPLIT")
+    per = int(env) if env else 32
+    return int(max(1, min(64, round(((K + 31) // 32) / per))))
+
+
 class MLPEngine:
     """Forward / backward of the MLP stacks through phc_gemm, with per-batch-size activation workspaces."""
 
@@ -261,6 +269,61 @@ class MLPEngine:
         if rc:
             _lib.check(rc, "phc_gemm")
 
+    # -- grouped launches (tc5s only): one persistent kernel over the tiles of up to PHC_GEMM_GROUP_MAX independent GEMMs ------
+    def gdesc(self, A, a_k, B, b_k, C, M, N, K, alpha=1.0, bias=None, act=0, aux=None, accumulate=False, k_splits=1):
+        return _lib.PhcGemmDesc(A.data_ptr(), A.stride(0), 1 if a_k else 0, B.data_ptr(), B.stride(0), 1 if b_k else 0, C.data_ptr(),
+                                C.stride(0), M, N, K, alpha, _ptr(bias), act, _ptr(aux), aux.stride(0) if aux is not None else 0,
+                                1 if accumulate else 0, k_splits)
+
+    def fwd_desc(self, st: MLPStack, li: int, x: torch.Tensor, ws: Dict[str, torch.Tensor]):
+        """Layer li of the forward pass of stack st on batch x / workspace ws (the same epilogues as forward())."""
+        net, l, B = self.net, st.layers[li], x.shape[0]
+        inp = x if li == 0 else ws["h"][li - 1]
+        silu = st.activation == "silu"
+        if li < len(st.hidden):
+            out = ws["h"][li]
+            act = _lib.PHC_ACT_SILU if silu else (_lib.PHC_ACT_RELU_BITS if "hbits" in ws else _lib.PHC_ACT_RELU)
+            aux = ws["z"][li] if silu else (ws["hbits"][li] if "hbits" in ws else None)
+        else:
+            out = ws["out"]
+            act = _lib.PHC_ACT_NONE if not st.head_relu else (_lib.PHC_ACT_SILU if silu else (_lib.PHC_ACT_RELU_BITS if "obits" in ws else _lib.PHC_ACT_RELU))
+            aux = None if not st.head_relu else (ws["z_out"] if silu else ws.get("obits"))
+        return self.gdesc(inp, True, net.weight(l), True, out, B, l.out_dim, l.in_dim, bias=net.bias(l), act=act, aux=aux)
+
+    def bwd_descs(self, st: MLPStack, li: int, x: torch.Tensor, ws: Dict[str, torch.Tensor], dx: Optional[torch.Tensor] = None):
+        """(dW, dX) problems of layer li: dW[out, in] += dY^T X (split-K, reduce-add into the gradient bucket) and
+        dX = (dY W) * act'(layer below).  dX is None for the first layer unless `dx` is given."""
+        net, l, B = self.net, st.layers[li], x.shape[0]
+        dY = ws["dout"] if li == len(st.layers) - 1 else ws["dh"][li]
+        inp = x if li == 0 else ws["h"][li - 1]
+        dw = self.gdesc(dY, False, inp, False, net.weight(l, grad=True), l.out_dim, l.in_dim, B, accumulate=True, k_splits=group_splits(B))
+        dxd = None
+        if li > 0:
+            if st.activation == "silu":
+                dxd = self.gdesc(dY, True, net.weight(l), False, ws["dh"][li - 1], B, l.in_dim, l.out_dim, act=_lib.PHC_ACT_SILU_BWD, aux=ws["z"][li - 1])
+            elif "hbits" in ws:
+                dxd = self.gdesc(dY, True, net.weight(l), False, ws["dh"][li - 1], B, l.in_dim, l.out_dim, act=_lib.PHC_ACT_MASK_BITS, aux=ws["hbits"][li - 1])
+            else:
+                dxd = self.gdesc(dY, True, net.weight(l), False, ws["dh"][li - 1], B, l.in_dim, l.out_dim, aux=ws["h"][li - 1])
+        elif dx is not None:
+            dxd = self.gdesc(dY, True, net.weight(l), False, dx, B, l.in_dim, l.out_dim)
+        return dw, dxd
+
+    def run_group(self, descs) -> None:
+        descs = [d for d in descs if d is not None]
+        for i in range(0, len(descs), _lib.PHC_GEMM_GROUP_MAX):
+            part = descs[i:i + _lib.PHC_GEMM_GROUP_MAX]
+            arr = (_lib.PhcGemmDesc * len(part))(*part)
+            rc = self.lib.phc_gemm_group(arr, len(part), _stream())
+            if rc:
+                _lib.check(rc, "phc_gemm_group")
+
+    def forward_group(self, items) -> None:
+        """items: [(stack, x, ws)]: the stacks advance layer by layer together, one grouped launch per layer index."""
+        depth = max(len(st.layers) for st, _, _ in items)
+        for li in range(depth):
+            self.run_group([self.fwd_desc(st, li, x, ws) for st, x, ws in items if li < len(st.layers)])
+
     def colsum(self, X, M, N, out, alpha=1.0, accumulate=True):
         rc = self.lib.phc_colsum(X.data_ptr(), X.stride(0), M, N, alpha, out.data_ptr(), 1 if accumulate else 0, _stream())
         if rc:
@@ -274,6 +337,10 @@ class MLPEngine:
             z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.dev)
             ws = {"h": [z(batch, round4(l.out_dim)) for l in st.hidden], "out": z(batch, round4(st.out_dim)),
                   "dh": [z(batch, round4(l.out_dim)) for l in st.hidden], "dout": z(batch, round4(st.out_dim))}
+            if st.activation == "relu" and self.backend == "tc5s":     # ReLU backward from 1 bit per element (PHC_ACT_RELU_BITS)
+                ws["hbits"] = [torch.zeros(batch, (l.out_dim + 31) // 32, dtype=torch.int32, device=self.dev) for l in st.hidden]
+                if st.head_relu:
+                    ws["obits"] = torch.zeros(batch, (st.out_dim + 31) // 32, dtype=torch.int32, device=self.dev)
             if st.activation == "silu":          # SiLU backward needs the pre-activations
                 ws["z"] = [z(batch, round4(l.out_dim)) for l in st.hidden]
                 if st.head_relu:
@@ -289,10 +356,11 @@ class MLPEngine:
         ws["x_split"] = cur_split
         ws["h_split"] = []
         silu = st.activation == "silu"
+        bits = ws.get("hbits")
         for i, (l, h) in enumerate(zip(st.hidden, ws["h"])):
             cur_split = self.gemm(cur, True, net.weight(l), True, h, B, l.out_dim, l.in_dim, bias=net.bias(l),
-                                  act=_lib.PHC_ACT_SILU if silu else _lib.PHC_ACT_RELU, mask=ws["z"][i] if silu else None,
-                                  a_split=cur_split, split_out=True)
+                                  act=_lib.PHC_ACT_SILU if silu else (_lib.PHC_ACT_RELU_BITS if bits else _lib.PHC_ACT_RELU),
+                                  mask=ws["z"][i] if silu else (bits[i] if bits else None), a_split=cur_split, split_out=True)
             ws["h_split"].append(cur_split)
             cur = h
         l = st.head
@@ -329,6 +397,9 @@ class MLPEngine:
                 if st.activation == "silu":
                     nsplit = self.gemm(dcur, True, net.weight(l), False, ws["dh"][li - 1], B, l.in_dim, l.out_dim,
                                        mask=ws["z"][li - 1], act=_lib.PHC_ACT_SILU_BWD, a_split=dsplit, split_out=True)
+                elif ws.get("hbits"):
+                    nsplit = self.gemm(dcur, True, net.weight(l), False, ws["dh"][li - 1], B, l.in_dim, l.out_dim,
+                                       mask=ws["hbits"][li - 1], act=_lib.PHC_ACT_MASK_BITS)
                 else:
                     nsplit = self.gemm(dcur, True, net.weight(l), False, ws["dh"][li - 1], B, l.in_dim, l.out_dim, mask=acts[li],
                                        a_split=dsplit, split_out=True)

@@ -29,10 +29,27 @@ def run_cuda_minibatch(net, batch, cfg, backend=None):
     ag._gp_g = z(Bd, round4(net.amp_dim))
     wa, wc, wd = eng.workspace("a", net.actor, B), eng.workspace("c", net.critic, B), eng.workspace("d", net.disc, 3 * Bd)
     net.grads.zero_()
-    mu = eng.forward(net.actor, x, wa)
-    val = eng.forward(net.critic, x, wc)
     t = {k: batch[k].to(dev).contiguous() for k in ("actions", "old_neglogp", "advantages", "old_mu", "old_sigma")}
     rets = batch["returns"].to(dev).reshape(-1).contiguous()
+    if eng.backend == "tc5s":          # the grouped path of AMPAgent._update_grouped on the same pre-normalised inputs
+        from phc_b200.learning.amp_agent import PhaseTimer
+        ag._ws_actor, ag._ws_critic, ag._ws_disc, ag.timer = wa, wc, wd, PhaseTimer(False)
+        ag._disc_logit_reg, ag._disc_weight_decay = cfg["disc_logit_reg"], cfg["disc_weight_decay"]
+
+        def losses():
+            mu, val, logits = wa["out"], wc["out"], wd["out"]
+            _lib.check(lib.phc_ppo_actor_grad(mu.data_ptr(), mu.stride(0), net.sigma.data_ptr(), t["actions"].data_ptr(), t["old_neglogp"].data_ptr(),
+                                              t["advantages"].data_ptr(), t["old_mu"].data_ptr(), t["old_sigma"].data_ptr(), B, A, cfg["e_clip"],
+                                              cfg["bounds_loss_coef"], 1.0 / B, wa["dout"].data_ptr(), wa["dout"].stride(0), ag._stats.data_ptr(), None))
+            _lib.check(lib.phc_ppo_critic_grad(val.data_ptr(), val.stride(0), rets.data_ptr(), B, cfg["critic_coef"], 1.0 / B,
+                                               wc["dout"].data_ptr(), wc["dout"].stride(0), ag._stats.data_ptr(), None))
+            _lib.check(lib.phc_disc_logit_grad(logits.data_ptr(), logits.stride(0), 2 * Bd, Bd, cfg["disc_coef"], wd["dout"].data_ptr(),
+                                               wd["dout"].stride(0), ag._stats.data_ptr(), None))
+        ag._grouped_core(x, xa, Bd, None, losses)
+        mu, val = wa["out"], wc["out"]
+        return _finish(ag, net, lib, cfg, mu, val, A, B, Bd, dev)
+    mu = eng.forward(net.actor, x, wa)
+    val = eng.forward(net.critic, x, wc)
     _lib.check(lib.phc_ppo_actor_grad(mu.data_ptr(), mu.stride(0), net.sigma.data_ptr(), t["actions"].data_ptr(), t["old_neglogp"].data_ptr(),
                                       t["advantages"].data_ptr(), t["old_mu"].data_ptr(), t["old_sigma"].data_ptr(), B, A, cfg["e_clip"],
                                       cfg["bounds_loss_coef"], 1.0 / B, wa["dout"].data_ptr(), wa["dout"].stride(0), ag._stats.data_ptr(), None))
@@ -51,6 +68,10 @@ def run_cuda_minibatch(net, batch, cfg, backend=None):
     for l in net.disc.layers:
         _lib.check(lib.phc_axpy2d(net.weight(l).data_ptr(), l.in_pad, net.weight(l, True).data_ptr(), l.in_pad, l.out_dim, l.in_dim,
                                   2.0 * cfg["disc_coef"] * cfg["disc_weight_decay"], ag._stats[12:].data_ptr(), None))
+    return _finish(ag, net, lib, cfg, mu, val, A, B, Bd, dev)
+
+
+def _finish(ag, net, lib, cfg, mu, val, A, B, Bd, dev):
     torch.cuda.synchronize()
     grads = {}
     for l in net.all_layers():

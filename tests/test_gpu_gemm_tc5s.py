@@ -135,3 +135,27 @@ def test_ppo_shapes_against_fp64_on_device():
     bound = dY.double().abs().T @ A[:, :K].double().abs()
     ratio = float(((G[:, :K].double() - exp).abs() / bound).max())
     assert ratio < 4e-6, ratio
+
+
+def test_relu_sign_bits_forward_and_masked_backward():
+    """PHC_ACT_RELU_BITS writes one bit per element (x > 0); PHC_ACT_MASK_BITS applies it: the same results as the fp32-mask path."""
+    g = torch.Generator().manual_seed(7)
+    M, N, K = 333, 200, 96
+    A, B, bias = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / math.sqrt(K), torch.randn(N, generator=g)
+    W = (N + 31) // 32
+    H, Hb = torch.zeros(M, round4(N), device=DEV), torch.zeros(M, round4(N), device=DEV)
+    bits = torch.zeros(M, W + 1, dtype=torch.int32, device=DEV)           # one spare word per row: ldaux > ceil(N / 32)
+    tc5s(padded(A), True, padded(B), True, H, M, N, K, bias=bias.to(DEV), act=_lib.PHC_ACT_RELU)
+    tc5s(padded(A), True, padded(B), True, Hb, M, N, K, bias=bias.to(DEV), act=_lib.PHC_ACT_RELU_BITS, aux=bits)
+    assert torch.equal(H, Hb)
+    cols = torch.arange(N, device=DEV)
+    got = (bits[:, cols // 32] >> (cols % 32)) & 1
+    assert torch.equal(got.bool(), H[:, :N] > 0)
+    assert int(bits[:, W].abs().sum()) == 0
+    if N % 32:      # bits beyond column N stay clear
+        assert int(((bits[:, W - 1].long() & 0xFFFFFFFF) >> (N % 32)).sum()) == 0
+    dY, Wt = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g) / math.sqrt(K)
+    D1, D2 = torch.zeros(M, round4(N), device=DEV), torch.zeros(M, round4(N), device=DEV)
+    tc5s(padded(dY), True, padded(Wt), False, D1, M, N, K, aux=H)                                  # fp32 mask (aux > 0)
+    tc5s(padded(dY), True, padded(Wt), False, D2, M, N, K, act=_lib.PHC_ACT_MASK_BITS, aux=bits)   # bit mask
+    assert torch.equal(D1, D2)

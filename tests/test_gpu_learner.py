@@ -153,7 +153,7 @@ CFG = dict(e_clip=0.2, critic_coef=5.0, entropy_coef=0.0, bounds_loss_coef=10.0,
            disc_grad_penalty=5.0, disc_weight_decay=0.0001, grad_norm=50.0, learning_rate=2e-5, truncate_grads=True)
 
 
-@pytest.mark.parametrize("backend", ["tc5", "mma"])
+@pytest.mark.parametrize("backend", ["tc5", "mma", "tc5s", "tc5s-1cta"])
 @pytest.mark.parametrize("B,Bd,obs,act,amp,units,activation",
                          [(512, 128, 934, 69, 1960, (256, 128), "relu"), (16384, 4096, 934, 69, 1960, (1024, 512), "relu"),
                           (300, 100, 50, 7, 30, (64, 32), "relu"),
@@ -179,7 +179,12 @@ def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units, activa
     batch = _rand_batch(B, Bd, obs, act, amp, seed=B, mu_fn=lambda x: mu_fn(lattice_inputs(x)))
     for k in ("obs_n", "amp_agent", "amp_replay", "amp_demo"):
         batch[k] = lattice_inputs(batch[k])
-    got = run_cuda_minibatch(net, batch, CFG, backend=backend)
+    if backend.startswith("tc5s"):      # grouped launches (AMPAgent._grouped_core), CTA-pair tiles or one-CTA tiles
+        _lib.check(_lib.load().phc_gemm_tc5s_set_ctas(1 if backend.endswith("1cta") else 2))
+    try:
+        got = run_cuda_minibatch(net, batch, CFG, backend=backend.split("-")[0])
+    finally:
+        _lib.load().phc_gemm_tc5s_set_ctas(0)
     # near-exact (fp64) reference; the loss is evaluated at OUR policy mean (see ppo_oracle.minibatch_update: sigma = e^-2.9
     # turns an fp32-level difference in mu into a 150x larger one in neglogp), the forward pass itself is compared below
     exp = PO.minibatch_update(sd, batch, CFG, n_hidden=len(units), dtype=torch.float64, mu_override=got["mu"].cpu().double(),

@@ -1,9 +1,8 @@
 """GPU parity of the strided kernels for more than 32 bodies (env_step_wide.cu, motion_wide.cu): Unitree G1 (38 + 1 bodies, 37
 hinge dofs) and SMPL-X (52 bodies) against the goldens of the unmodified reference.
 
-OPT-IN (PHC_TEST_WIDE=1): these kernels were written after this round's GPU budget was spent; they are validated against the
-same goldens through the CPU emulation of their source (tests/test_env_step_emu_cpu.py, tests/test_motion_emu_cpu.py) and
-have not run on hardware yet.  The first GPU session runs this file and then drops the switch."""
+First run on a B200 in round 2 (gpurun session 1: 4 passed); the CPU emulation of the same kernel sources
+(tests/test_env_step_emu_cpu.py, tests/test_motion_emu_cpu.py) checks them against the same goldens without a GPU."""
 import os
 
 import pytest
@@ -13,7 +12,7 @@ from phc_b200 import ops, synthetic as syn
 from tests.helpers import close, load, motion_data_from
 from tests.test_gpu_env_step import check_against, run_cuda_step
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("PHC_TEST_WIDE", "0") != "1", reason="opt-in: PHC_TEST_WIDE=1 (not yet run on hardware)")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 KEYS = ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf", "ref_body_pos", "ref_body_rot", "ref_body_vel")
 
