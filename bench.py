@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--num-envs", type=int, default=NUM_ENVS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-points", action="store_true", help="skip the 16384 / 65536-env points of the env-step roofline")
     return ap.parse_args()
 
 
@@ -372,6 +373,89 @@ def env_kernel_roofline(task, peak_gbs: float, peak_src: str, iters: int = 40):
                       "median of 5; kernel_us_event_pair = median of %d single launches, one event pair each" % (iters, iters, iters, iters)}
 
 
+def measured_peak_tf32():
+    """Dense TF32 tensor peak to hold the 3xTF32 GEMMs against: MEASURED_PEAKS.json has no TF32 entry, so half of the measured
+    cuBLAS bf16 rate (kind::tf32 issues at half the kind::f16 rate: tcgen05 K = 8 vs 16 per instruction at the same cycle cost).
+    The sustained figure, because the GEMMs run back to back inside a long step (B200_PROFILING.md)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return 0.5 * float(j["bf16_tflops_sustained"]), "0.5 x measured bf16_tflops_sustained (MEASURED_PEAKS.json); burst would be 0.5 x %.0f" % float(j["bf16_tflops"])
+        except Exception:
+            pass
+    return 0.5 * 1400.0, "0.5 x fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md)"
+
+
+def gemm_roofline(agent, iters: int = 20):
+    """Tensor-pipe roofline of the learner's dominant kernel (phc::tc5::smem_split::gemm_tc5s_kernel): the three grouped
+    forward launches of one minibatch (layer 1 / layer 2 / heads of actor + critic at 16384 rows and discriminator at 12288
+    rows) and the grouped backward launches, timed back to back with CUDA events on the launching stream.  achieved = 3 x
+    algorithmic fp32 FLOPs (3xTF32: three tensor-core products per fp32 product) / time."""
+    eng, net = agent.engine, agent.model
+    if eng.backend != "tc5s":
+        return None
+    x, xa, Bd = agent._x_mb, agent._amp_mb, agent._amp_minibatch_size
+    stacks = [(net.actor, x, agent._ws_actor), (net.critic, x, agent._ws_critic), (net.disc, xa, agent._ws_disc)]
+    depth = max(len(st.layers) for st, _, _ in stacks)
+    bwd = []
+    for k in range(depth):
+        descs = []
+        for st, xin, ws in stacks:
+            li = len(st.layers) - 1 - k
+            if li >= 0:
+                descs += [d for d in eng.bwd_descs(st, li, xin, ws) if d is not None]
+        bwd.append(descs)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        f0 = eng.gemm_flops
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3 / iters
+        return sec, (eng.gemm_flops - f0) / iters
+
+    t_f, fl_f = timed(lambda: eng.forward_group(stacks))
+    t_b, fl_b = timed(lambda: [eng.run_group(d) for d in bwd])
+    net.grads.zero_()
+    peak, src = measured_peak_tf32()
+    ach = 3.0 * (fl_f + fl_b) / (t_f + t_b) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "kernel": "phc::tc5::smem_split::gemm_tc5s_kernel (grouped forward + backward launches of one minibatch)",
+            "forward_us": t_f * 1e6, "forward_tflops": 3.0 * fl_f / t_f / 1e12, "backward_us": t_b * 1e6,
+            "backward_tflops": 3.0 * fl_b / t_b / 1e12, "algorithmic_fp32_flops_per_minibatch": fl_f + fl_b,
+            "fp32_equivalent_tflops": (fl_f + fl_b) / (t_f + t_b) / 1e12, "peak_source": src,
+            "timing": "%d x [3 forward launches] and %d x [3 backward launches] of the bench minibatch, one CUDA-event pair each; operands (2.1 GB experience "
+                      "buffer aside) are the minibatch workspaces, ~0.5 GB, larger than L2" % (iters, iters)}
+
+
+def env_roofline_points(device, rank, peak_gbs, peak_src, sizes=(16384, 65536)):
+    """The same fused env-step kernel at larger batches (several waves: launch ramp and tail amortised), 4096 clips shared by the envs."""
+    from phc_b200 import synthetic as syn
+    from phc_b200.env.humanoid_im import HumanoidIm
+    pts = []
+    motion = syn.make_motions(4096, seed=rank)
+    for n in sizes:
+        try:
+            task = HumanoidIm({"env": {"num_envs": n}, "motion_data": motion, "seed": rank}, device_type="cuda", device_id=device.index)
+            task.reset()
+            for _ in range(3):
+                task.step(None)
+            r = env_kernel_roofline(task, peak_gbs, peak_src, iters=20)
+            pts.append({"num_envs": n, "kernel_us": r["kernel_us"], "achieved": r["achieved"], "frac": r["frac"]})
+            del task
+            torch.cuda.empty_cache()
+        except Exception as e:          # diagnostic extra: never fails the bench line
+            pts.append({"num_envs": n, "error": str(e)[:200]})
+    return pts
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -413,10 +497,16 @@ def main():
     peak, peak_src = measured_peak_gbs()
     roof = env_kernel_roofline(task, peak, peak_src) if rank == 0 else None
     note("roofline kernel timed")
+    roof_gemm = gemm_roofline(agent) if rank == 0 else None
+    note("gemm roofline timed")
     if world > 1:
         torch.distributed.barrier()
     del agent, task
     torch.cuda.empty_cache()
+    if roof is not None and not args.no_points:
+        roof["points"] = [{"num_envs": args.num_envs, "kernel_us": roof["kernel_us"], "achieved": roof["achieved"], "frac": roof["frac"]}] + \
+            env_roofline_points(device, rank, peak, peak_src)
+        note("roofline points timed")
 
     e2e = None
     if not args.no_e2e:
@@ -444,7 +534,7 @@ def main():
                            "parallelism": f"dp{world} (env shards, 1 NCCL all-reduce per minibatch)",
                            "arithmetic": "fp32 throughout (the reference trains with mixed_precision: False): env kernels fp32, MLP GEMMs 3xTF32 on tcgen05 with fp32 accumulation",
                            "l2": "inputs larger than L2: 2.1 GB experience buffer + ~1 GB frame tables per epoch; the roofline kernel is timed with an explicit L2 flush"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "roofline_gemm": roof_gemm, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -94,7 +94,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm)
 env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const int self_dim, const int amp_dim,
                 const bool alias_obs_rt, const bool state_bulk_ok_rt) {
   extern __shared__ __align__(128) float smem[];
+  // the warp index through a shuffle: the compiler then KNOWS it (and the env index, and every pointer derived from it) is
+  // warp-uniform, keeps them in uniform registers and issues the bulk copies straight from there instead of wrapping each
+  // one in a vote + R2UR.BROADCAST loop
+#ifdef PHC_EXP_NO_UNIFORM_WARP      // A/B build (tools/ab_env.sh): the round-1 form
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#else
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+#endif
   const int env = blockIdx.x * kWarpsPerCta + warp;
   if (env >= a.num_envs) return;                       // whole warp exits together; no block-level barrier is used
   if (!FAST && a.only_where && a.only_where[env] == 0) return;  // masked subset (reset path)

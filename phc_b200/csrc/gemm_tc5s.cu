@@ -128,7 +128,8 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
   uint64_t* tmem_empty = tmem_full + 2;             // [2] (pair mode: the leader's copies are the ones waited on)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;     // shfl: provably warp-uniform
+  const bool elected = elect_one();                 // the one lane of each warp that issues TMA / tcgen05 / barrier arrivals
   const uint32_t rank = (CTAS == 2) ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   const int unit = blockIdx.x / CTAS, num_units = gridDim.x / CTAS;     // a unit = one CTA or one CTA pair
@@ -151,37 +152,39 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    // ===================== TMA producer: raw fp32 tiles =====================
-    if (lane == 0) {
-      uint32_t it = 0;                                        // k-block counter, continues across tiles
-      for (int t = unit; t < P.total_tiles; t += num_units) {
-        const Tile tl = decode<CTAS>(P, t, (int)rank);
-        const Prob& q = P.p[tl.g];
-        const CUtensorMap* tA = &P.tmA[tl.g];
-        const CUtensorMap* tB = &P.tmB[tl.g];
-        const int nb0 = tl.n0 + (int)rank * C::B_ROWS;
-        for (int i = 0; i < tl.nkb; ++i, ++it) {
-          const int s = it % C::RAW_STAGES;
-          if (it >= (uint32_t)C::RAW_STAGES) mbar_wait(raw_empty + s, ((it / C::RAW_STAGES) - 1) & 1);
-          uint8_t* st = smem + s * C::RAW;
-          const int k0 = (tl.kb_begin + i) * BK;
+    // ===================== TMA producer: raw fp32 tiles (whole warp walks the loop, the elected lane issues) =====================
+    uint32_t it = 0;                                          // k-block counter, continues across tiles
+    for (int t = unit; t < P.total_tiles; t += num_units) {
+      const Tile tl = decode<CTAS>(P, t, (int)rank);
+      const Prob& q = P.p[tl.g];
+      const CUtensorMap* tA = &P.tmA[tl.g];
+      const CUtensorMap* tB = &P.tmB[tl.g];
+      const int nb0 = tl.n0 + (int)rank * C::B_ROWS;
+      const bool ak = q.a_k != 0, bk = q.b_k != 0;
+      for (int i = 0; i < tl.nkb; ++i, ++it) {
+        const int s = it % C::RAW_STAGES;
+        if (it >= (uint32_t)C::RAW_STAGES) mbar_wait(raw_empty + s, ((it / C::RAW_STAGES) - 1) & 1);
+        uint8_t* st = smem + s * C::RAW;
+        const int k0 = (tl.kb_begin + i) * BK;
+        if (elected) {
           mbar_expect_tx(full_bar + s, C::RAW);
-          if (q.a_k) tma_load_2d(st, tA, full_bar + s, k0, tl.m0);
+          if (ak) tma_load_2d(st, tA, full_bar + s, k0, tl.m0);
           else {
 #pragma unroll
             for (int j = 0; j < BM / 32; ++j) tma_load_2d(st + j * 4096, tA, full_bar + s, tl.m0 + 32 * j, k0);
           }
-          if (q.b_k) tma_load_2d(st + A_TILE, tB, full_bar + s, k0, nb0);
+          if (bk) tma_load_2d(st + A_TILE, tB, full_bar + s, k0, nb0);
           else {
 #pragma unroll
             for (int j = 0; j < C::B_ROWS / 32; ++j) tma_load_2d(st + A_TILE + j * 4096, tB, full_bar + s, nb0 + 32 * j, k0);
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 5) {
-    // ===================== MMA issuer (one thread of the leader CTA) =====================
-    if (lane == 0 && leader) {
+    // ===================== MMA issuer (leader CTA; whole warp walks the loop, the elected lane issues) =====================
+    if (leader) {
       uint32_t it = 0, lt = 0;
       for (int t = unit; t < P.total_tiles; t += num_units, ++lt) {
         const Tile tl = decode<CTAS>(P, t, 0);
@@ -209,20 +212,26 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
             const uint64_t dBh = smem_desc(st + A_TILE + kk * b_step, b_lbo, b_sbo, b_lt);
             const uint64_t dBl = smem_desc(sl + A_TILE + kk * b_step, b_lbo, b_sbo, b_lt);
             const uint32_t first = (i > 0 || kk > 0) ? 1u : 0u;
-            if (CTAS == 2) {
-              umma_tf32_2cta(tmem_d, dAl, dBh, idesc, first);
-              umma_tf32_2cta(tmem_d, dAh, dBl, idesc, 1u);
-              umma_tf32_2cta(tmem_d, dAh, dBh, idesc, 1u);
-            } else {
-              umma_tf32(tmem_d, dAl, dBh, idesc, first);
-              umma_tf32(tmem_d, dAh, dBl, idesc, 1u);
-              umma_tf32(tmem_d, dAh, dBh, idesc, 1u);
+            if (elected) {
+              if (CTAS == 2) {
+                umma_tf32_2cta(tmem_d, dAl, dBh, idesc, first);
+                umma_tf32_2cta(tmem_d, dAh, dBl, idesc, 1u);
+                umma_tf32_2cta(tmem_d, dAh, dBh, idesc, 1u);
+              } else {
+                umma_tf32(tmem_d, dAl, dBh, idesc, first);
+                umma_tf32(tmem_d, dAh, dBl, idesc, 1u);
+                umma_tf32(tmem_d, dAh, dBh, idesc, 1u);
+              }
             }
           }
-          if (CTAS == 2) { umma_commit_2cta(raw_empty + s); umma_commit_2cta(lo_empty + l); }      // frees both slots (in both CTAs)
-          else { umma_commit(raw_empty + s); umma_commit(lo_empty + l); }
+          if (elected) {
+            if (CTAS == 2) { umma_commit_2cta(raw_empty + s); umma_commit_2cta(lo_empty + l); }      // frees both slots (in both CTAs)
+            else { umma_commit(raw_empty + s); umma_commit(lo_empty + l); }
+          }
+          __syncwarp();
         }
-        if (CTAS == 2) umma_commit_2cta(tmem_full + acc); else umma_commit(tmem_full + acc);
+        if (elected) { if (CTAS == 2) umma_commit_2cta(tmem_full + acc); else umma_commit(tmem_full + acc); }
+        __syncwarp();
       }
     }
   } else if (warp >= 6) {
@@ -248,7 +257,7 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
           sts128(lo + j * NT * 16, split_lo(v[j].x), split_lo(v[j].y), split_lo(v[j].z), split_lo(v[j].w));
         fence_proxy_async_smem();                              // generic-proxy writes -> visible to the tensor core's reads
         __syncwarp();
-        if (lane == 0) { if (CTAS == 2) mbar_arrive_remote_leader(lo_full + l); else mbar_arrive(lo_full + l); }
+        if (elected) { if (CTAS == 2) mbar_arrive_remote_leader(lo_full + l); else mbar_arrive(lo_full + l); }
       }
     }
   } else {
@@ -285,7 +294,7 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
           if (c0 + 32 >= BN || nb + 32 >= q.N) {                 // last chunk read: hand the accumulator back before the math / store
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { if (CTAS == 2 && !leader) mbar_arrive_remote_leader(tmem_empty + acc); else mbar_arrive(tmem_empty + acc); }
+            if (elected) { if (CTAS == 2 && !leader) mbar_arrive_remote_leader(tmem_empty + acc); else mbar_arrive(tmem_empty + acc); }
           }
           float v[32];
 #pragma unroll
@@ -333,14 +342,14 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
           // stage the 32 x 32 chunk (row = lane) in the 128-byte-swizzled layout the C tensor map expects
           uint8_t* buf = my_buf + (chunk & 1) * EPI_BUF;
           ++chunk;
-          if (lane == 0) bulk_wait_group_read<1>();              // the store issued two chunks ago has read this buffer
+          if (elected) bulk_wait_group_read<1>();                // the store issued two chunks ago has read this buffer (same lane issues and waits)
           __syncwarp();
           const uint32_t brow = s32(buf) + (uint32_t)lane * 128u;
 #pragma unroll
           for (int c = 0; c < 8; ++c) sts128(brow + ((uint32_t)(c ^ (lane & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elected) {
             if (q.accumulate) tma_reduce_add_2d(tC, buf, nb, tl.m0 + warp * 32);
             else tma_store_2d(tC, buf, nb, tl.m0 + warp * 32);
             bulk_commit_group();
@@ -349,10 +358,10 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
       } else {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if (CTAS == 2 && !leader) mbar_arrive_remote_leader(tmem_empty + acc); else mbar_arrive(tmem_empty + acc); }
+        if (elected) { if (CTAS == 2 && !leader) mbar_arrive_remote_leader(tmem_empty + acc); else mbar_arrive(tmem_empty + acc); }
       }
     }
-    if (lane == 0) bulk_wait_group_read<0>();                    // staging buffers must outlive the stores' reads
+    if (elected) bulk_wait_group_read<0>();                    // staging buffers must outlive the stores' reads
     tc_fence_before();
   }
   __syncthreads();

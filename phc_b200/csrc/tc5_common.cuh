@@ -47,6 +47,17 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
 
+// One elected lane of a fully converged warp (elect.sync).  The tcgen05 / TMA issue code is written as WARP-UNIFORM code --
+// every lane waits on the barriers and computes the (identical) descriptors, only the issuing instructions sit under this
+// predicate.  Under `if (lane == 0)` the compiler has to treat everything computed inside as thread-varying and wraps every
+// uniform-register operand of UTCHMMA / UTMALDG / UTCBAR in a vote + R2UR.BROADCAST "waterfall" loop: ~100 issue cycles per MMA,
+// which bounded the round-1 kernels at 1200-1600 cycles per k-block against 768 cycles of tensor work.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // explicit shared-space 16-byte accesses (32-bit shared addresses: no generic-address resolution in the hot loops)
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;

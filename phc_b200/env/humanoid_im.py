@@ -47,6 +47,12 @@ class SyntheticSim:
         self._k = 0
         self.h2d_bytes_per_step = (self.rigid_body_state.numel() + self.dof_state.numel() + self.dof_force.numel()) * 4 if host_bank else 0
 
+    def set_env_state(self, mask: torch.Tensor, rigid_body_state: torch.Tensor, dof_state: torch.Tensor) -> None:
+        """Backend hook of HumanoidIm.reset (Humanoid._reset_env_tensors, humanoid.py:590-621): apply the state HumanoidIm wrote
+        into the rows of `rigid_body_state` / `dof_state` flagged by `mask` to the simulation.  The synthetic stand-in has no
+        dynamics to reset -- its next snapshot replaces every row anyway -- so there is nothing to do."""
+        return
+
     def simulate(self, actions: Optional[torch.Tensor]) -> None:
         k = self._k = (self._k + 1) % self._body.shape[0]
         self.rigid_body_state.copy_(self._body[k], non_blocking=True)
@@ -74,7 +80,7 @@ class HumanoidIm:
         self.power_coefficient = float(env.get("power_coefficient", 0.0005))
         self._fut_tracks = bool(env.get("fut_tracks", False))
         self._num_traj_samples = int(env.get("numTrajSamples", 3)) if self._fut_tracks else 1
-        self._traj_sample_timestep = 1.0 / float(env.get("trajSampleTimestepInv", 3)) if self._fut_tracks else 0.0
+        self._traj_sample_timestep = 1.0 / float(env.get("trajSampleTimestepInv", 30)) if self._fut_tracks else 0.0
         self.shape_resampling_interval = int(env.get("shape_resampling_interval", 500))
         self.temp_running_mean = True
         self.getup_schedule = False
@@ -140,6 +146,10 @@ class HumanoidIm:
         self.sim = cfg.get("sim") or SyntheticSim(m, self.num_envs, self.device, seed=int(cfg.get("seed", 0)),
                                                   host_bank=bool(cfg.get("host_sim_bank", False)),
                                                   amp_dim=13 + 2 * self.num_dof + 3 * len(key_bodies) if robot else 196)
+        if not hasattr(self.sim, "set_env_state"):
+            raise TypeError("simulator backend lacks set_env_state(mask, rigid_body_state, dof_state): without it an episode reset would only "
+                            "rewrite observation-side tensors and the physics would keep running from the old state (INTEGRATION.md, "
+                            "'Simulator backend')")
         self._rigid_body_state_reshaped = self.sim.rigid_body_state
         self._rigid_body_pos = self._rigid_body_state_reshaped[..., :J, 0:3]
         self._rigid_body_rot = self._rigid_body_state_reshaped[..., :J, 3:7]
@@ -223,7 +233,7 @@ class HumanoidIm:
     def get_task_obs_size_detail(self):
         """humanoid_im.py:522-537: what the network builders read from the task."""
         env = self.cfg.get("env", self.cfg)
-        return {"target": self._plan.task_dim, "fut_tracks": False, "num_traj_samples": 1, "obs_v": env.get("obs_v", 6),
+        return {"target": self._plan.task_dim, "fut_tracks": self._fut_tracks, "num_traj_samples": self._num_traj_samples, "obs_v": env.get("obs_v", 6),
                 "models_path": env.get("models", []), "num_prim": env.get("num_prim", 2),
                 "training_prim": env.get("training_prim", 1), "actors_to_load": env.get("actors_to_load", 2),
                 "has_lateral": env.get("has_lateral", True)}
@@ -269,12 +279,14 @@ class HumanoidIm:
             self.extras["body_pos"] = self._rigid_body_pos
             self.extras["body_pos_gt"] = self._plan.body_pos_gt
 
-    # kept for API parity: the pieces are produced together by the fused launch
+    # kept for API parity.  Reward, reset and observations of a step are produced TOGETHER by the one fused launch of
+    # post_physics_step; these entry points therefore do nothing more (re-launching would advance the AMP ring, decrement
+    # _cycle_counter and overwrite _point_goal a second time) and hand back the buffers that launch filled.
     def _compute_reward(self, actions=None):
-        self._plan.run()
+        return self.rew_buf
 
     def _compute_reset(self):
-        return
+        return self.reset_buf
 
     def _compute_observations(self, env_ids=None):
         self._set_mask(env_ids)
@@ -299,12 +311,17 @@ class HumanoidIm:
         itself; outside a step this re-runs it for the current simulator state (all envs, as the reference's env_ids=None)."""
         if env_ids is not None:
             raise NotImplementedError("per-env AMP recomputation outside the fused step: reset paths use phc_amp_obs_demo")
-        self._plan.run()
-        return self._amp_obs_buf[:, 0]
+        return self._amp_obs_buf[:, 0]          # slot 0 of the window = the vector the last fused launch wrote
 
     # ---- reset --------------------------------------------------------------------------------------------------
     def _set_mask(self, env_ids) -> None:
         m = self._reset_mask
+        if env_ids is not None and not torch.is_tensor(env_ids):      # the reference also passes lists (done_indices = [], amp_agent.py:314)
+            env_ids = torch.as_tensor(env_ids, dtype=torch.int64, device=self.device).reshape(-1)
+            m.zero_()
+            if env_ids.numel():
+                m[env_ids] = 1
+            return
         if env_ids is None:
             m.fill_(1)
         elif env_ids.dtype in (torch.bool, torch.uint8, torch.float32) and env_ids.shape == m.shape:
@@ -340,6 +357,9 @@ class HumanoidIm:
                                          self._global_offset.data_ptr(), self._reset_mask.data_ptr(), self.num_envs,
                                          self._rigid_body_state_reshaped.data_ptr(), self.sim.bodies_per_env,
                                          self._dof_state.data_ptr(), st), "phc_set_env_state")
+        # _reset_env_tensors (humanoid.py:590-621): the backend pushes the new root / dof state of the flagged envs into the simulation
+        # (Isaac Gym: set_actor_root_state_tensor_indexed + set_dof_state_tensor_indexed on mask.nonzero() in ITS reset path)
+        self.sim.set_env_state(self._reset_mask, self._rigid_body_state_reshaped, self._dof_state)
         # _compute_observations(env_ids)
         self._plan_reset_obs.run()
         # _init_amp_obs: current + history slots from the reference motion at t0 - k dt
@@ -356,8 +376,12 @@ class HumanoidIm:
     # ---- discriminator demo observations ------------------------------------------------------------------------
     def fetch_amp_obs_demo(self, num_samples: int) -> torch.Tensor:
         """HumanoidAMP.fetch_amp_obs_demo (humanoid_amp.py:215-230): AMP windows of random reference-motion states."""
-        ids = torch.randint(0, self._motion_lib.num_motions, (num_samples,), device=self.device)
-        t0 = (torch.rand(num_samples, device=self.device) * self._motion_lib.lengths[ids]).float()
+        sample = getattr(self._motion_data, "sample_motions", None)
+        if sample is not None:         # MotionLibBase.sample_motions: multinomial over _sampling_batch_prob (Auto-PMCP re-weights it)
+            ids = sample(num_samples).to(self.device, torch.int64)
+        else:                          # plain tables (synthetic data): every clip equally likely, as an un-weighted library
+            ids = torch.randint(0, self._motion_lib.num_motions, (num_samples,), device=self.device)
+        t0 = self._sample_time(ids).float()          # HumanoidIm._sample_time -> sample_time_interval (humanoid_im.py:661-663)
         demo = ops.amp_obs_demo(self._motion_lib, self.step_cfg, ids, t0)
         return demo.view(num_samples, self.get_num_amp_obs())
 

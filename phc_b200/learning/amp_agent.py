@@ -236,6 +236,13 @@ class AMPAgent:
         self.world = D.world_size() if self.multi_gpu else 1
 
         netcfg = cfg["network"]
+        if netcfg.get("name", "amp") == "amp_mcp":
+            # AMPMCPBuilder (amp_network_mcp_builder.py:33-59): has_softmax defaults to TRUE there (appends nn.Softmax) and
+            # ending_act False strips the final activation.  Both shipped MCP configs set has_softmax: False, ending_act: True
+            # (im_mcp.yaml:15-16, im_mcp_big.yaml:15-16) -- the composer built here; anything else must not be built silently.
+            if bool(netcfg.get("has_softmax", True)) or not bool(netcfg.get("ending_act", True)):
+                raise NotImplementedError("amp_mcp composer: only has_softmax: False with ending_act: True (im_mcp.yaml / im_mcp_big.yaml) "
+                                          "is implemented; set them explicitly in the network config")
         self.model = AMPNetwork(self.obs_dim, self.actions_num, self.amp_obs_dim, netcfg["mlp"]["units"],
                                 netcfg["disc"]["units"], netcfg["mlp"]["activation"], netcfg.get("sigma_init", -2.9),
                                 device=self.device, seed=int(cfg["seed"]),

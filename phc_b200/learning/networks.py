@@ -208,6 +208,7 @@ class MLPEngine:
         self.backend = backend or os.environ.get("PHC_GEMM", "tc5")
         assert self.backend in ("mma", "tc5", "tc5s")
         self._companions: Dict[Tuple[int, Tuple[int, ...], Tuple[int, ...]], Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.gemm_flops = 0.0          # algorithmic fp32 FLOPs (2 M N K) of every grouped launch so far (bench.py reads it)
         if self.backend == "tc5":
             net.refresh_split()
 
@@ -313,6 +314,7 @@ class MLPEngine:
         descs = [d for d in descs if d is not None]
         for i in range(0, len(descs), _lib.PHC_GEMM_GROUP_MAX):
             part = descs[i:i + _lib.PHC_GEMM_GROUP_MAX]
+            self.gemm_flops += sum(2.0 * d.M * d.N * d.K for d in part)
             arr = (_lib.PhcGemmDesc * len(part))(*part)
             rc = self.lib.phc_gemm_group(arr, len(part), _stream())
             if rc:

@@ -216,7 +216,8 @@ def test_humanoid_im_mcp_task_and_agent_epoch():
 
     agent = AMPAgent("t", {"vec_env": RLGPUEnv(task), "horizon_length": 8, "minibatch_size": 256, "amp_minibatch_size": 64,
                            "mini_epochs": 2, "amp_obs_demo_buffer_size": 2048, "amp_replay_buffer_size": 2048, "amp_batch_size": 128,
-                           "network": {"name": "amp_mcp", "mlp": {"units": [128, 64], "activation": "relu"},
+                           "network": {"name": "amp_mcp", "has_softmax": False, "ending_act": True,     # im_mcp.yaml:15-16
+                                       "mlp": {"units": [128, 64], "activation": "relu"},
                                        "disc": {"units": [128, 64], "activation": "relu"}}})
     assert agent.model.kind == "amp_mcp" and agent.model.action_dim == K and agent.model.actor.head_relu
     assert "a2c_network.composer.4.weight" in agent.model.state_dict()
