@@ -257,6 +257,10 @@ typedef struct PhcStepArgs {
   /* ---- flags.im_eval extras of HumanoidIm.post_physics_step (humanoid_im.py:674-680); NULL = skip ---- */
   float* mpjpe;                /* [N] mean over the J bodies of |body_pos - reference pos| at the current motion time      */
   float* body_pos_gt;          /* [N, J, 3] that reference pose's positions (extras['body_pos_gt'])                        */
+  /* ---- AMP ring with the head kept ON THE DEVICE (appended; NULL = the host passes amp_out already offset to the slot) ----
+   * When non-NULL, amp_out is the ring base and this step's vector goes to slot *ring_head of every env.  Lets a whole rollout
+   * (whose slot changes every step) be captured once as a CUDA graph; phc_ring_advance moves the head between steps. */
+  const int32_t* ring_head;
 } PhcStepArgs;
 
 /* Sizes implied by a configuration (so callers can allocate): */
@@ -290,6 +294,18 @@ PHC_API int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* motion_ids,
  *   out[n, k, :] = ring[n, (head + k) % S, :]. */
 PHC_API int phc_amp_window_export(const float* ring, int64_t ring_stride, int64_t n, int32_t num_steps, int32_t amp_dim,
                           int32_t head, float* out, int64_t out_stride, void* stream);
+
+/* The same two calls with the ring rotation / head read from DEVICE memory (`*_dev` non-NULL overrides the integer argument),
+ * and the one-thread kernel that moves the head one slot back before a step: *head = (*head - 1 + num_slots) % num_slots. */
+PHC_API int phc_amp_obs_demo_ring(const PhcMotionLib* lib, const int64_t* motion_ids, const float* times0, int64_t n,
+                          int32_t first_step, int32_t num_steps, float dt, uint32_t flags, const int32_t* key_bodies,
+                          int32_t num_key_bodies, const int32_t* amp_joints, int32_t num_amp_joints, float* out, int64_t out_stride,
+                          const int64_t* only_where, int32_t slot_offset, const int32_t* slot_offset_dev, void* stream);
+PHC_API int phc_amp_window_export_ring(const float* ring, int64_t ring_stride, int64_t n, int32_t num_steps, int32_t amp_dim,
+                               int32_t head, const int32_t* head_dev, float* out, int64_t out_stride, void* stream);
+PHC_API int phc_ring_advance(int32_t* head, int32_t num_slots, void* stream);
+/* adds n to the launch counter phc_launch_count() reports (a replayed CUDA graph launches kernels the library did not see) */
+PHC_API void phc_launch_count_add(int64_t n);
 
 /* Reset path (HumanoidAMP._set_env_state, humanoid_amp.py:605-637 fed by _sample_ref_state, humanoid_im.py:1000-1023):
  * write the reference pose at (motion_ids[e], times[e]) (+offset) into the simulator tensors of every env e with

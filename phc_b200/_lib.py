@@ -68,7 +68,7 @@ class PhcStepArgs(C.Structure):
         ("ref_body_pos", _p), ("ref_body_rot", _p), ("ref_body_vel", _p), ("ref_body_ang_vel", _p),
         ("ref_cache", _p),
         ("close_distance", C.c_float), ("far_distance", C.c_float), ("max_episode_length", C.c_int32), ("point_goal", _p),
-        ("cycle_phase", _p), ("mpjpe", _p), ("body_pos_gt", _p),
+        ("cycle_phase", _p), ("mpjpe", _p), ("body_pos_gt", _p), ("ring_head", _p),
     ]
 
 
@@ -104,6 +104,11 @@ SIGNATURES = {
     "phc_env_step_fast_launches": (C.c_int64, []),
     "phc_amp_obs_demo": (C.c_int, [C.POINTER(PhcMotionLib), _p, _p, C.c_int64, C.c_int32, C.c_int32, C.c_float,
                                    C.c_uint32, _p, C.c_int32, _p, C.c_int32, _p, C.c_int64, _p, C.c_int32, _p]),
+    "phc_amp_obs_demo_ring": (C.c_int, [C.POINTER(PhcMotionLib), _p, _p, C.c_int64, C.c_int32, C.c_int32, C.c_float,
+                                        C.c_uint32, _p, C.c_int32, _p, C.c_int32, _p, C.c_int64, _p, C.c_int32, _p, _p]),
+    "phc_amp_window_export_ring": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, _p, C.c_int64, _p]),
+    "phc_ring_advance": (C.c_int, [_p, C.c_int32, _p]),
+    "phc_launch_count_add": (None, [C.c_int64]),
     "phc_amp_window_export": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, C.c_int64, _p]),
     "phc_set_env_state": (C.c_int, [C.POINTER(PhcMotionLib), _p, _p, _p, _p, C.c_int64, _p, C.c_int32, _p, _p]),
     "phc_gae": (C.c_int, [_p, _p, _p, _p, C.c_int32, C.c_int64, C.c_float, C.c_float, _p, _p, _p]),

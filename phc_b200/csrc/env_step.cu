@@ -469,7 +469,9 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   }
   // rows leave shared memory as TMA bulk stores (one instruction per row) when source, destination and size are 16-byte
   // granular; otherwise with per-lane coalesced stores; all rows of the env go out together at the end.
-  float* const g_amp = ((FAST || a.amp_out) && !obs_only) ? a.amp_out + (size_t)env * a.amp_out_stride : nullptr;
+  // ring mode with the head on the device (PhcStepArgs.ring_head): this step's vector goes to slot *ring_head of the env's ring
+  float* const g_amp = ((FAST || a.amp_out) && !obs_only)
+                           ? a.amp_out + (size_t)env * a.amp_out_stride + (a.ring_head ? (size_t)(*a.ring_head) * (size_t)amp_dim : (size_t)0) : nullptr;
   const bool amp_bulk = FAST ? true : (g_amp && !a.amp_hist_in && (amp_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(g_amp) & 15) == 0);
   __syncwarp();   // the reward slots and the simulator block are consumed: the obs row may overwrite them
 

@@ -237,7 +237,7 @@ env_step_wide_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, c
 
     // ================= AMP observation of the simulated character -> slot 0 of its window ============================
     if (a.amp_out) {
-      float* g_amp = a.amp_out + (size_t)env * a.amp_out_stride;
+      float* g_amp = a.amp_out + (size_t)env * a.amp_out_stride + (a.ring_head ? (size_t)(*a.ring_head) * (size_t)amp_dim : (size_t)0);
       if (a.amp_hist_in) {      // newest-first window shift, oldest slot first so that the in-place form is safe
         const float* h = a.amp_hist_in + (size_t)env * a.amp_out_stride;
         for (int s = a.amp_steps - 2; s >= 0; --s)

@@ -383,7 +383,10 @@ static bool make_map(CUtensorMap* tm, const float* base, int64_t ld, uint64_t in
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int g_ctas = 0;      // 0: not decided yet (env PHC_TC5S_CTAS = 1 | 2, default 2)
+// 0: not decided yet (env PHC_TC5S_CTAS = 1 | 2).  Default 1: measured on the PPO shapes (profiles/gemm_microbench_r2c.log) the
+// 128 x 128 one-CTA tiles reach 560-680 TF/s of tensor work, the 256 x 128 CTA-pair tiles 350-410 -- with N = 128 the pair
+// saves no operand traffic worth its cross-CTA barrier round trips; it stays in the tree as an opt-in, parity-tested variant.
+static int g_ctas = 0;
 
 }  // namespace smem_split
 }  // namespace tc5
@@ -392,7 +395,7 @@ static int g_ctas = 0;      // 0: not decided yet (env PHC_TC5S_CTAS = 1 | 2, de
 extern "C" int phc_gemm_group(const PhcGemmDesc* d, int32_t count, void* stream) {
   using namespace phc::tc5::smem_split;
   if (!d || count < 1 || count > MAX_PROBLEMS) { phc_set_error("phc_gemm_group: 1 <= count <= PHC_GEMM_GROUP_MAX problems"); return PHC_ERR_INVALID_ARG; }
-  if (!g_ctas) { const char* v = getenv("PHC_TC5S_CTAS"); g_ctas = (v && v[0] == '1') ? 1 : 2; }
+  if (!g_ctas) { const char* v = getenv("PHC_TC5S_CTAS"); g_ctas = (v && v[0] == '2') ? 2 : 1; }
   const int ctas = g_ctas;
   static Params P;      // host staging (launches are serialised by the caller's stream order; the struct is copied at launch)
   memset(&P.p, 0, sizeof(P.p));

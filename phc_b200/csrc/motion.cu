@@ -122,6 +122,7 @@ struct AmpDemoArgs {
   int64_t out_stride;
   const int64_t* only_where;
   int32_t slot_offset;      // ring rotation: logical step k is written to physical slot (k + slot_offset) % num_steps
+  const int32_t* slot_offset_dev;   // optional: the rotation read from device memory (the ring head HumanoidIm keeps on the device)
 };
 
 // warp per (sample, history step): motion sample at t0 - (first_step + k) dt, then build_amp_observations_smpl
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(128) amp_demo_kernel(const __grid_constant__ A
   const Q4 root_q = upright ? r.q : strip_base_rot(r.q);
   const Q4 hinv = quat_about_z(-heading_angle(root_q));
   const int nj = a.num_amp_joints, nk = a.num_key_bodies;
-  const int kp = (k + a.slot_offset) % a.num_steps;
+  const int kp = (k + (a.slot_offset_dev ? *a.slot_offset_dev : a.slot_offset)) % a.num_steps;
   const int row = has_h + 12 + (D > 0 ? 2 * D : 9 * nj) + 3 * nk;
   float* o = a.out + si * a.out_stride + (int64_t)kp * row + (has_h ? 1 : 0);
   if (D > 0) {       // build_amp_observations_robot (humanoid_amp.py:1062-1104): raw hinge angles and velocities
@@ -250,8 +251,9 @@ set_env_state_kernel(const __grid_constant__ PhcMotionLib lib, const int64_t* __
 }
 
 // AMP ring -> newest-first window: out[n, k, :] = ring[n, (head + k) % S, :]   (pure copy, float4 when A % 4 == 0)
-__global__ void amp_window_export_kernel(const float* __restrict__ ring, int64_t ring_stride, int64_t n, int S, int A, int head,
-                                         float* __restrict__ out, int64_t out_stride) {
+__global__ void amp_window_export_kernel(const float* __restrict__ ring, int64_t ring_stride, int64_t n, int S, int A, int head_arg,
+                                         const int32_t* __restrict__ head_dev, float* __restrict__ out, int64_t out_stride) {
+  const int head = head_dev ? *head_dev : head_arg;
   if ((A & 3) == 0 && (ring_stride & 3) == 0 && (out_stride & 3) == 0) {
     const int A4 = A >> 2;
     const int64_t total = n * S * A4;
@@ -328,7 +330,7 @@ extern "C" int phc_motion_state_wide_launch(const PhcMotionLib* lib, const int64
 extern "C" int phc_amp_obs_demo_wide_launch(const PhcMotionLib* lib, const int64_t* ids, const float* times0, int64_t n, int32_t first_step,
                                             int32_t num_steps, float dt, uint32_t flags, const int32_t* key_bodies, int32_t nk,
                                             const int32_t* amp_joints, int32_t nj, float* out, int64_t out_stride,
-                                            const int64_t* only_where, int32_t slot_offset, void* stream);
+                                            const int64_t* only_where, int32_t slot_offset, const int32_t* slot_offset_dev, void* stream);
 extern "C" int phc_set_env_state_wide_launch(const PhcMotionLib* lib, const int64_t* ids, const float* times, const float* offset,
                                              const int64_t* only_where, int64_t n, float* body_state, int32_t bodies_per_env,
                                              float* dof_state, void* stream);
@@ -351,6 +353,15 @@ extern "C" int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* ids, con
                                 int32_t first_step, int32_t num_steps, float dt, uint32_t flags,
                                 const int32_t* key_bodies, int32_t nk, const int32_t* amp_joints, int32_t nj, float* out,
                                 int64_t out_stride, const int64_t* only_where, int32_t slot_offset, void* stream) {
+  return phc_amp_obs_demo_ring(lib, ids, times0, n, first_step, num_steps, dt, flags, key_bodies, nk, amp_joints, nj, out, out_stride, only_where,
+                               slot_offset, nullptr, stream);
+}
+
+extern "C" int phc_amp_obs_demo_ring(const PhcMotionLib* lib, const int64_t* ids, const float* times0, int64_t n,
+                                     int32_t first_step, int32_t num_steps, float dt, uint32_t flags,
+                                     const int32_t* key_bodies, int32_t nk, const int32_t* amp_joints, int32_t nj, float* out,
+                                     int64_t out_stride, const int64_t* only_where, int32_t slot_offset, const int32_t* slot_offset_dev,
+                                     void* stream) {
   int rc = check_lib(lib, "phc_amp_obs_demo");
   if (rc) return rc;
   if (!lib->frames_joint) { phc_set_error("phc_amp_obs_demo: needs frames_joint"); return PHC_ERR_INVALID_ARG; }
@@ -361,12 +372,13 @@ extern "C" int phc_amp_obs_demo(const PhcMotionLib* lib, const int64_t* ids, con
   if (out_stride < (int64_t)num_steps * A) { phc_set_error("phc_amp_obs_demo: out_stride too small"); return PHC_ERR_INVALID_ARG; }
   if (n == 0) return PHC_OK;
   if (is_wide(lib)) return phc_amp_obs_demo_wide_launch(lib, ids, times0, n, first_step, num_steps, dt, flags, key_bodies, nk, amp_joints, nj, out,
-                                                         out_stride, only_where, slot_offset, stream);
+                                                         out_stride, only_where, slot_offset, slot_offset_dev, stream);
   phc::AmpDemoArgs a;
   a.lib = *lib; a.ids = ids; a.times0 = times0; a.n = n; a.first_step = first_step; a.num_steps = num_steps; a.dt = dt;
   a.flags = flags; a.num_key_bodies = nk; a.num_amp_joints = nj;
   for (int i = 0; i < PHC_MAX_AMP_JOINTS; ++i) a.amp_joints[i] = i < nj ? amp_joints[i] : -1; a.out = out; a.out_stride = out_stride; a.only_where = only_where;
   a.slot_offset = ((slot_offset % num_steps) + num_steps) % num_steps;
+  a.slot_offset_dev = slot_offset_dev;
   for (int i = 0; i < PHC_MAX_KEY_BODIES; ++i) a.key_bodies[i] = i < nk ? key_bodies[i] : -1;
   const int wpb = 4;
   const int64_t warps = n * num_steps;
@@ -391,6 +403,21 @@ extern "C" int phc_set_env_state(const PhcMotionLib* lib, const int64_t* ids, co
 
 extern "C" int phc_amp_window_export(const float* ring, int64_t ring_stride, int64_t n, int32_t num_steps, int32_t amp_dim,
                                      int32_t head, float* out, int64_t out_stride, void* stream) {
+  return phc_amp_window_export_ring(ring, ring_stride, n, num_steps, amp_dim, head, nullptr, out, out_stride, stream);
+}
+
+namespace phc {
+__global__ void ring_advance_kernel(int32_t* head, int32_t slots) { *head = (*head - 1 + slots) % slots; }
+}  // namespace phc
+
+extern "C" int phc_ring_advance(int32_t* head, int32_t num_slots, void* stream) {
+  if (!head || num_slots < 1) { phc_set_error("phc_ring_advance: bad arguments"); return PHC_ERR_INVALID_ARG; }
+  phc::ring_advance_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(head, num_slots); phc_count_launches(1);
+  return phc_check_cuda(cudaGetLastError(), "ring_advance_kernel launch");
+}
+
+extern "C" int phc_amp_window_export_ring(const float* ring, int64_t ring_stride, int64_t n, int32_t num_steps, int32_t amp_dim,
+                                          int32_t head, const int32_t* head_dev, float* out, int64_t out_stride, void* stream) {
   if (!ring || !out || n < 0 || num_steps < 1 || amp_dim < 1 || head < 0 || head >= num_steps ||
       ring_stride < (int64_t)num_steps * amp_dim || out_stride < (int64_t)num_steps * amp_dim) {
     phc_set_error("phc_amp_window_export: bad arguments"); return PHC_ERR_INVALID_ARG;
@@ -398,7 +425,7 @@ extern "C" int phc_amp_window_export(const float* ring, int64_t ring_stride, int
   if (n == 0) return PHC_OK;
   if ((reinterpret_cast<uintptr_t>(ring) | reinterpret_cast<uintptr_t>(out)) & 15) { phc_set_error("phc_amp_window_export: buffers must be 16-byte aligned"); return PHC_ERR_INVALID_ARG; }
   int64_t g = (n * num_steps * amp_dim / 4 + 255) / 256; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1;
-  phc::amp_window_export_kernel<<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(ring, ring_stride, n, num_steps, amp_dim, head, out, out_stride); phc_count_launches(1);
+  phc::amp_window_export_kernel<<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(ring, ring_stride, n, num_steps, amp_dim, head, head_dev, out, out_stride); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "amp_window_export_kernel launch");
 }
 

@@ -81,6 +81,7 @@ struct AmpDemoWideArgs {
   int64_t out_stride;
   const int64_t* only_where;
   int32_t slot_offset;
+  const int32_t* slot_offset_dev;
 };
 
 // warp per (sample, history step): motion sample at t0 - (first_step + k) dt, then build_amp_observations_smpl / _robot
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(128) amp_demo_wide_kernel(const __grid_constan
   const Q4 root_q = upright ? r.q : strip_base_rot(r.q);
   const Q4 hinv = quat_about_z(-heading_angle(root_q));
   const int nj = a.num_amp_joints, nk = a.num_key_bodies;
-  const int kp = (k + a.slot_offset) % a.num_steps;
+  const int kp = (k + (a.slot_offset_dev ? *a.slot_offset_dev : a.slot_offset)) % a.num_steps;
   const int row = has_h + 12 + (D > 0 ? 2 * D : 9 * nj) + 3 * nk;
   float* o = a.out + si * a.out_stride + (int64_t)kp * row + (has_h ? 1 : 0);
   if (lane == 0) {
@@ -182,13 +183,14 @@ extern "C" int phc_motion_state_wide_launch(const PhcMotionLib* lib, const int64
 extern "C" int phc_amp_obs_demo_wide_launch(const PhcMotionLib* lib, const int64_t* ids, const float* times0, int64_t n, int32_t first_step,
                                             int32_t num_steps, float dt, uint32_t flags, const int32_t* key_bodies, int32_t nk,
                                             const int32_t* amp_joints, int32_t nj, float* out, int64_t out_stride,
-                                            const int64_t* only_where, int32_t slot_offset, void* stream) {
+                                            const int64_t* only_where, int32_t slot_offset, const int32_t* slot_offset_dev, void* stream) {
   phc::wide::AmpDemoWideArgs a;
   a.lib = *lib; a.ids = ids; a.times0 = times0; a.n = n; a.first_step = first_step; a.num_steps = num_steps; a.dt = dt;
   a.flags = flags; a.num_key_bodies = nk; a.num_amp_joints = nj; a.out = out; a.out_stride = out_stride; a.only_where = only_where;
   for (int i = 0; i < PHC_MAX_AMP_JOINTS; ++i) a.amp_joints[i] = i < nj ? amp_joints[i] : -1;
   for (int i = 0; i < PHC_MAX_KEY_BODIES; ++i) a.key_bodies[i] = i < nk ? key_bodies[i] : -1;
   a.slot_offset = ((slot_offset % num_steps) + num_steps) % num_steps;
+  a.slot_offset_dev = slot_offset_dev;
   const int wpb = 4;
   const int64_t warps = n * num_steps;
   phc::wide::amp_demo_wide_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);

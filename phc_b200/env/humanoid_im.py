@@ -29,6 +29,9 @@ class SyntheticSim:
     With `host_bank=True` the bank lives in pinned host memory and every step pays the host->device copy (the
     end-to-end measurement of bench.py); otherwise snapshots are device resident."""
 
+    graph_safe = True      # simulate() only enqueues copies on the current stream: a rollout over this backend can be a CUDA graph
+                           # (bank size 4 divides the rollout lengths in use, so every rollout sees the same snapshot sequence)
+
     def __init__(self, motion: syn.MotionData, num_envs: int, device, seed: int = 0, bank: int = 4, host_bank: bool = False,
                  amp_dim: int = 196, amp_steps: int = 10):
         self.device = torch.device(device)
@@ -191,7 +194,9 @@ class HumanoidIm:
         self._ref_cache = torch.zeros(N, int(self._motion_lib.frames_body.shape[1]), device=dev) if self._use_ref_cache else None
         # flags.im_eval (humanoid_im.py:674-680; also selects the mean-distance termination, :1180): extras['mpjpe'], body_pos(_gt)
         self.im_eval = bool(cfg.get("im_eval", False))
-        self._plan = ops.EnvStepPlan(cycle_counter=self._cycle_counter, with_ref_buffers=not self._use_ref_cache,
+        # the ring head lives on the device: a rollout step then differs from the next in nothing the host passes
+        self._ring_head = torch.zeros(1, dtype=torch.int32, device=dev) if self._amp_use_ring else None
+        self._plan = ops.EnvStepPlan(cycle_counter=self._cycle_counter, with_ref_buffers=not self._use_ref_cache, ring_head_dev=self._ring_head,
                                      with_eval_extras=self.im_eval,
                                      amp_ring=self._amp_use_ring, ref_cache=self._ref_cache,
                                      reward_from_cache=self._use_ref_cache, **common)
@@ -252,13 +257,13 @@ class HumanoidIm:
     def _amp_obs_buf(self) -> torch.Tensor:
         """Newest-first AMP window [N, S, A] (the reference attribute of that name), materialised from the ring."""
         if self._amp_use_ring:
-            ops.amp_window_export(self._amp_store, self._plan.ring_head, self._amp_window)
+            ops.amp_window_export(self._amp_store, self._ring_head, self._amp_window)
         return self._amp_window
 
     def export_amp_obs(self, out: torch.Tensor) -> torch.Tensor:
         """Write extras['amp_obs'] ([N, S*A], newest first) straight into `out` (e.g. the agent's experience-buffer row)."""
         if self._amp_use_ring:
-            return ops.amp_window_export(self._amp_store, self._plan.ring_head, out)
+            return ops.amp_window_export(self._amp_store, self._ring_head, out)
         out.copy_(self._amp_store.view(out.shape))
         return out
 
@@ -365,7 +370,7 @@ class HumanoidIm:
         # _init_amp_obs: current + history slots from the reference motion at t0 - k dt
         ops.amp_obs_demo(ml, self.step_cfg, self._sampled_motion_ids, self._motion_start_times, first_step=0,
                          num_steps=self._num_amp_obs_steps, out=self._amp_store, only_where=self._reset_mask,
-                         slot_offset=self._plan.ring_head if self._amp_use_ring else 0)
+                         slot_offset=0, slot_offset_dev=self._ring_head)
         return self.obs_buf
 
     def resample_motions(self):

@@ -232,6 +232,7 @@ class AMPAgent:
         # multi-GPU: one process per GPU, gradients summed over NCCL and scaled by 1/world (replaces Horovod,
         # phc/run_hydra.py:114-128 / amp_agent.py:668)
         self.multi_gpu = bool(cfg.get("multi_gpu", False)) and D.is_multi()
+        self._reducer = D.GradReducer(self.device)
         self.rank = torch.distributed.get_rank() if self.multi_gpu else 0
         self.world = D.world_size() if self.multi_gpu else 1
 
@@ -265,6 +266,11 @@ class AMPAgent:
 
         self._init_buffers()
         self.timer = PhaseTimer(os.environ.get("PHC_PHASE_TIMING", "0") == "1")
+        # a simulator backend has to declare that its simulate() is capturable (SyntheticSim does; Isaac Gym's gym.simulate is not)
+        self._graph_rollout = (bool(cfg.get("graph_rollout", True)) and os.environ.get("PHC_GRAPH_ROLLOUT", "1") != "0" and
+                               bool(getattr(getattr(task, "sim", None), "graph_safe", False)) and
+                               self.horizon_length % int(getattr(task.sim, "_body", torch.zeros(1)).shape[0]) == 0)
+        self._rollout_graph, self._rollout_out, self._rollout_calls, self._rollout_graph_launches = None, None, 0, 0
         self.epoch_num = 0
         self.frame = 0
         self.obs = None
@@ -396,6 +402,31 @@ class AMPAgent:
         return obs, rewards.unsqueeze(1), dones, infos
 
     def play_steps(self) -> Dict[str, torch.Tensor]:
+        """The rollout of one epoch.  The 32 steps are launch-bound when issued one call at a time (~35 short kernels per step
+        against ~0.4 ms of GPU work), and nothing in them depends on the host: reset masks instead of index lists, the AMP ring
+        head on the device, in-place carried state.  So the first rollout runs eagerly (lazy one-time initialisations), the
+        second is captured into ONE CUDA graph and every later one is a single graph launch (`graph_rollout: False` in the
+        config or PHC_GRAPH_ROLLOUT=0 keeps the eager loop; the phase timer needs the eager loop too)."""
+        if not self._graph_rollout or self.timer.enabled:
+            return self._play_steps_eager()
+        if self._rollout_graph is not None:
+            self._rollout_graph.replay()
+            self._lib.phc_launch_count_add(self._rollout_graph_launches)
+            return self._rollout_out
+        self._rollout_calls += 1
+        if self._rollout_calls < 2:
+            return self._play_steps_eager()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        l0 = self._lib.phc_launch_count()
+        with torch.cuda.graph(g):
+            out = self._play_steps_eager()
+        self._rollout_graph_launches = self._lib.phc_launch_count() - l0
+        self._rollout_graph, self._rollout_out = g, out
+        g.replay()                                   # the capture recorded the work without running it
+        return out
+
+    def _play_steps_eager(self) -> Dict[str, torch.Tensor]:
         """AMPAgent.play_steps (amp_agent.py:309-397).  Episode resets are handed to the env as the done MASK of the
         previous step (no nonzero() / host sync on the path)."""
         self.set_eval()
@@ -431,8 +462,8 @@ class AMPAgent:
                 next_vals *= (1.0 - terminated.unsqueeze(-1))
                 eb["next_values"][n].copy_(next_vals)
             not_dones = 1.0 - self.dones.float()
-            self.current_rewards = (self.current_rewards + rewards.squeeze(1)) * not_dones
-            self.current_lengths = (self.current_lengths + 1) * not_dones
+            self.current_rewards.add_(rewards.squeeze(1)).mul_(not_dones)      # in place: state carried across (graph-replayed) rollouts
+            self.current_lengths.add_(1).mul_(not_dones)
             done_mask = self.dones
 
         mb_fdones = eb["dones"]
@@ -507,37 +538,85 @@ class AMPAgent:
     def calc_gradients(self, input_dict: Dict[str, torch.Tensor]) -> None:
         """One PPO/AMP minibatch: forward, losses, backward into the flat gradient bucket, all-reduce, clip, Adam.
         input_dict carries `idx` (rows of the epoch dataset) instead of materialised copies of the big tensors
-        (AMPDataset._get_item gathers ~0.5 GB per minibatch of which 3/4 of the AMP rows are dropped afterwards)."""
-        self.set_train()
-        lib, net, eng = self._lib, self.model, self.engine
-        ds = self.dataset
+        (AMPDataset._get_item gathers ~0.5 GB per minibatch of which 3/4 of the AMP rows are dropped afterwards).
+        train_epoch runs the same three stages software-pipelined (see _minibatch_pipeline)."""
         idx = input_dict["idx"]
+        prepared = self._prepare_minibatch(idx) if self.engine.backend == "tc5s" else None
+        self._compute_gradients(idx, prepared)
+        scale = self._reducer.begin(self.model.grads) if self.multi_gpu else 1.0
+        if self.multi_gpu:
+            self._reducer.end()
+        self._optimizer_step(scale)
+
+    def _prepare_minibatch(self, idx: torch.Tensor):
+        """Everything of a minibatch that does not depend on the weights: gather + normalise the observation and the three AMP row
+        blocks into the update workspaces (and fold the batch into the running statistics, as RunningMeanStd.forward does in train
+        mode).  Split off so that train_epoch can issue it for minibatch i + 1 while the gradient all-reduce of minibatch i runs."""
+        self.set_train()
+        ds, T = self.dataset, self.timer
+        Bd = self._amp_minibatch_size
+        with T("update.preproc_obs"):
+            x = self._preproc_obs(ds["obs"], use_temp=self.temp_running_mean, out=self._x_mb, row_idx=idx)
+        with T("update.disc_preproc"):
+            aidx = idx[:Bd]
+            xa = self._amp_mb
+            self._preproc_amp_obs(ds["amp_obs"], xa[0:Bd], row_idx=aidx)
+            self._preproc_amp_obs(self._amp_replay_src, xa[Bd:2 * Bd], row_idx=ds["amp_obs_replay_idx"][aidx])
+            self._preproc_amp_obs(self._amp_obs_demo_buffer.data, xa[2 * Bd:3 * Bd], row_idx=ds["amp_obs_demo_idx"][aidx])
+        return x, xa
+
+    def _compute_gradients(self, idx: torch.Tensor, prepared=None) -> None:
+        self.set_train()
+        net, eng, ds = self.model, self.engine, self.dataset
         B, Bd, A = idx.shape[0], self._amp_minibatch_size, self.actions_num
         inv_b = 1.0 / B
         st = _stream()
         self._stats.zero_()
         net.grads.zero_()
-
-        T = self.timer
         if eng.backend == "tc5s":
-            self._update_grouped(ds, idx, B, Bd, A, inv_b, st)
+            x, xa = prepared if prepared is not None else self._prepare_minibatch(idx)
+            self._grouped_core(x, xa, Bd, st, lambda: self._loss_grads(ds, idx, B, Bd, A, inv_b, st, self._ws_actor["out"], self._ws_critic["out"],
+                                                                       self._ws_disc["out"]))
         else:
             self._update_sequential(ds, idx, B, Bd, A, inv_b, st)
-
-        # ---- all-reduce, clip, Adam -----------------------------------------------------------------------------
-        t_opt = T("update.optim")
-        t_opt.__enter__()
-        grad_scale = D.allreduce_grad_bucket(net.grads) if self.multi_gpu else 1.0
-        self.opt_step += 1
-        _lib.check(lib.phc_grad_sumsq(net.grads.data_ptr(), net.num_floats, self._gsumsq.data_ptr(), st))
-        _lib.check(lib.phc_adam_step(net.params.data_ptr(), net.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                                     net.num_floats, self._gsumsq.data_ptr(), grad_scale,
-                                     self.grad_norm if self.truncate_grads else 0.0, self.last_lr, 0.9, 0.999, 1e-8,
-                                     self.opt_step, st))
-        if eng.backend == "tc5":
-            net.refresh_split()                    # hi/lo operand copies of the updated weights
-        t_opt.__exit__()
         self._last_B, self._last_Bd = B, Bd
+
+    def _optimizer_step(self, grad_scale: float) -> None:
+        lib, net, st = self._lib, self.model, _stream()
+        with self.timer("update.optim"):
+            self.opt_step += 1
+            _lib.check(lib.phc_grad_sumsq(net.grads.data_ptr(), net.num_floats, self._gsumsq.data_ptr(), st))
+            _lib.check(lib.phc_adam_step(net.params.data_ptr(), net.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                         net.num_floats, self._gsumsq.data_ptr(), grad_scale,
+                                         self.grad_norm if self.truncate_grads else 0.0, self.last_lr, 0.9, 0.999, 1e-8,
+                                         self.opt_step, st))
+            if self.engine.backend == "tc5":
+                net.refresh_split()                    # hi/lo operand copies of the updated weights
+
+    def _minibatch_pipeline(self) -> None:
+        """The mini_epochs x num_minibatches updates of an epoch (amp_agent.py:460-483), software-pipelined: the gradient
+        all-reduce of minibatch i is issued on a side stream and, while it runs over NVLink, the compute stream already gathers
+        and normalises the rows of minibatch i + 1 (weight-independent, ~0.3 ms); Adam(i) follows once the reduced bucket is
+        back.  The collective leaves the critical path without splitting the single flat all-reduce per minibatch."""
+        mb = self.minibatch_size
+        grouped = self.engine.backend == "tc5s"
+
+        def indices():
+            for _ in range(self.mini_epochs_num):
+                for i in range(self.num_minibatches):
+                    yield self._idx_buf[i * mb:(i + 1) * mb]
+                self._idx_buf = torch.randperm(self.batch_size, device=self.device)
+        it = indices()
+        idx = next(it, None)
+        prepared = self._prepare_minibatch(idx) if (grouped and idx is not None) else None
+        while idx is not None:
+            self._compute_gradients(idx, prepared)
+            scale = self._reducer.begin(self.model.grads) if self.multi_gpu else 1.0
+            idx = next(it, None)                       # (a new permutation is drawn here at mini-epoch boundaries)
+            prepared = self._prepare_minibatch(idx) if (grouped and idx is not None) else None
+            if self.multi_gpu:
+                self._reducer.end()
+            self._optimizer_step(scale)
 
     def _update_sequential(self, ds, idx, B, Bd, A, inv_b, st) -> None:
         """Forward / losses / backward one network after the other, one launch per GEMM (mma.sync and pre-split tcgen05 back ends)."""
@@ -600,25 +679,12 @@ class AMPAgent:
         _lib.check(lib.phc_disc_logit_grad(logits.data_ptr(), logits.stride(0), 2 * Bd, Bd, self._disc_coef, dl.data_ptr(),
                                            dl.stride(0), self._stats.data_ptr(), st))
 
-    def _update_grouped(self, ds, idx, B, Bd, A, inv_b, st) -> None:
-        """The same minibatch with the grouped GEMM (phc_gemm_group): actor, critic and discriminator advance layer by layer
-        TOGETHER -- one persistent launch per layer index forward (3 problems), one per layer index backward (dW and dX of the
-        three networks plus the step of the gradient-penalty chain that is ready: up to 8 problems) -- instead of ~30 separate
-        GEMM launches whose tile counts each leave a partial last wave on the 148 SMs."""
-        lib, net, eng, T = self._lib, self.model, self.engine, self.timer
-        with T("update.preproc_obs"):
-            x = self._preproc_obs(ds["obs"], use_temp=self.temp_running_mean, out=self._x_mb, row_idx=idx)
-        with T("update.disc_preproc"):
-            aidx = idx[:Bd]
-            xa = self._amp_mb
-            self._preproc_amp_obs(ds["amp_obs"], xa[0:Bd], row_idx=aidx)
-            self._preproc_amp_obs(self._amp_replay_src, xa[Bd:2 * Bd], row_idx=ds["amp_obs_replay_idx"][aidx])
-            self._preproc_amp_obs(self._amp_obs_demo_buffer.data, xa[2 * Bd:3 * Bd], row_idx=ds["amp_obs_demo_idx"][aidx])
-        self._grouped_core(x, xa, Bd, st, lambda: self._loss_grads(ds, idx, B, Bd, A, inv_b, st, self._ws_actor["out"], self._ws_critic["out"],
-                                                                   self._ws_disc["out"]))
-
     def _grouped_core(self, x, xa, Bd, st, loss_fn) -> None:
-        """forward (grouped) -> loss_fn() writes d loss / d outputs into the workspaces' `dout` -> backward (grouped, with the
+        """The minibatch with the grouped GEMM (phc_gemm_group): actor, critic and discriminator advance layer by layer TOGETHER --
+        one persistent launch per layer index forward (3 problems), one per layer index backward (dW and dX of the three networks
+        plus the step of the gradient-penalty chain that is ready: up to 8 problems) -- instead of ~30 separate GEMM launches whose
+        tile counts each leave a partial last wave on the 148 SMs.
+        forward (grouped) -> loss_fn() writes d loss / d outputs into the workspaces' `dout` -> backward (grouped, with the
         gradient-penalty chain merged in) -> discriminator regularisers.  x / xa are the normalised, zero-padded inputs."""
         lib, net, eng, T = self._lib, self.model, self.engine, self.timer
         stacks = [(net.actor, x, self._ws_actor), (net.critic, x, self._ws_critic), (net.disc, xa, self._ws_disc)]
@@ -803,10 +869,7 @@ class AMPAgent:
         self.set_train()
         self.prepare_dataset(batch_dict)
         _prep.__exit__()
-        for _ in range(self.mini_epochs_num):
-            for i in range(self.num_minibatches):
-                self.calc_gradients({"idx": self._idx_buf[i * self.minibatch_size:(i + 1) * self.minibatch_size]})
-            self._idx_buf = torch.randperm(self.batch_size, device=self.device)
+        self._minibatch_pipeline()
         with self.timer("epoch.replay_store"):
             self._store_replay_amp_obs(batch_dict["amp_obs"])
         self.post_epoch(self.epoch_num)

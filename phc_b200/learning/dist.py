@@ -36,6 +36,31 @@ def allreduce_grad_bucket(bucket: torch.Tensor) -> float:
     return 1.0 / dist.get_world_size()
 
 
+class GradReducer:
+    """The per-minibatch gradient all-reduce, issued OFF the compute stream: begin() makes a side stream wait for the backward
+    pass, enqueues the collective there and returns at once (with the 1/world scale for the optimiser); end() makes the compute
+    stream wait for it.  Whatever the caller enqueues on the compute stream in between overlaps the collective."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+
+    def begin(self, bucket: torch.Tensor) -> float:
+        if not is_multi():
+            return 1.0
+        if self.stream is None:                        # CPU tensors (gloo tests)
+            dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
+        else:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
+        return 1.0 / dist.get_world_size()
+
+    def end(self) -> None:
+        if is_multi() and self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+
 def broadcast_params(bucket: torch.Tensor, src: int = 0) -> None:
     if is_multi():
         dist.broadcast(bucket, src)

@@ -203,9 +203,10 @@ class MLPEngine:
         self.lib = _lib.load()
         self.dev = net.device
         self._ws: Dict[Tuple[str, int], Dict[str, torch.Tensor]] = {}
-        # "tc5" (default): tcgen05 / TMEM / TMA 3xTF32 (gemm_tc5.cu); "mma": warp-level mma.sync 3xTF32 (gemm.cu), kept as
-        # the cross-check implementation (PHC_GEMM=mma)
-        self.backend = backend or os.environ.get("PHC_GEMM", "tc5")
+        # "tc5s" (default): grouped tcgen05 / TMEM / TMA 3xTF32 with the operand split in shared memory (gemm_tc5s.cu);
+        # "tc5": the round-1 kernel with operands pre-split in global memory (gemm_tc5.cu); "mma": warp-level mma.sync 3xTF32
+        # (gemm.cu).  The latter two stay as cross-check implementations (PHC_GEMM=tc5 | mma)
+        self.backend = backend or os.environ.get("PHC_GEMM", "tc5s")
         assert self.backend in ("mma", "tc5", "tc5s")
         self._companions: Dict[Tuple[int, Tuple[int, ...], Tuple[int, ...]], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.gemm_flops = 0.0          # algorithmic fp32 FLOPs (2 M N K) of every grouped launch so far (bench.py reads it)

@@ -279,12 +279,14 @@ class EnvStepPlan:
                  only_where: Optional[torch.Tensor] = None, obs_only: bool = False, amp_ring: bool = False,
                  ref_cache: Optional[torch.Tensor] = None, reward_from_cache: bool = False,
                  point_goal: Optional[torch.Tensor] = None, cycle_phase: Optional[torch.Tensor] = None,
-                 with_eval_extras: bool = False):
+                 with_eval_extras: bool = False, ring_head_dev: Optional[torch.Tensor] = None):
         """ref_cache: [N, body_stride] pose cache (PhcStepArgs.ref_cache): every run() stores the reference pose interpolated
         for the first observation sample; reward_from_cache=True makes run() take the reward-time reference pose from it
         (valid for HumanoidIm's step / reset sequence, see include/phc_b200.h).
         amp_ring=True: `amp_obs_buf` is a ring -- each run() writes only the newest vector into slot `ring_head`
-        (advance with advance_ring() before the step); otherwise the reference's window shift is done in the kernel."""
+        (advance with advance_ring() before the step); otherwise the reference's window shift is done in the kernel.
+        ring_head_dev: int32 [1] device tensor holding the ring head (PhcStepArgs.ring_head): the slot is then read on the device and
+        advance_ring() is a one-thread kernel, so consecutive steps differ in nothing the host passes (CUDA-graph capturable)."""
         lib = _lib.load()
         self._lib = lib
         self.cfg, self.mlib = cfg, mlib
@@ -345,6 +347,11 @@ class EnvStepPlan:
             amp_hist_in = self.amp_obs_buf             # in-place shift, the reference's semantics
         self.amp_ring = bool(amp_ring and with_amp)
         self.ring_head = 0
+        self.ring_head_dev = None
+        if ring_head_dev is not None:
+            assert self.amp_ring and ring_head_dev.dtype == torch.int32 and ring_head_dev.is_cuda and ring_head_dev.numel() == 1
+            self.ring_head_dev = ring_head_dev
+            self.ring_head = None            # lives on the device only
         self.ref_body_pos = torch.zeros(N, J, 3, device=dev) if with_ref_buffers else None
         self.ref_body_rot = torch.zeros(N, J, 4, device=dev) if with_ref_buffers else None
         self.ref_body_vel = torch.zeros(N, J, 3, device=dev) if with_ref_buffers else None
@@ -419,6 +426,7 @@ class EnvStepPlan:
             assert tuple(ref_cache.shape) == (N, int(mlib.frames_body.shape[1])), f"ref_cache: expected {(N, int(mlib.frames_body.shape[1]))}"
         self.ref_cache = ref_cache
         a.ref_cache = _ptr(ref_cache)
+        a.ring_head = _ptr(self.ring_head_dev)
         self.args = a
         self._args_ref = C.byref(a)
         self.refresh_motion_params()
@@ -431,6 +439,9 @@ class EnvStepPlan:
     def advance_ring(self) -> int:
         """Move the ring head one slot back (the slot that will receive this step's AMP vector) and re-point amp_out."""
         S = self.cfg.amp_steps
+        if self.ring_head_dev is not None:
+            _lib.check(self._lib.phc_ring_advance(self.ring_head_dev.data_ptr(), S, _stream()), "phc_ring_advance")
+            return -1
         self.ring_head = (self.ring_head - 1) % S
         self.args.amp_out = self.amp_obs_buf.data_ptr() + self.ring_head * self.amp_dim * 4
         return self.ring_head
@@ -443,7 +454,7 @@ class EnvStepPlan:
 
 def amp_obs_demo(mlib: PackedMotionLib, cfg: EnvStepConfig, motion_ids: torch.Tensor, times0: torch.Tensor,
                  first_step: int = 0, num_steps: Optional[int] = None, out: Optional[torch.Tensor] = None,
-                 only_where: Optional[torch.Tensor] = None, slot_offset: int = 0) -> torch.Tensor:
+                 only_where: Optional[torch.Tensor] = None, slot_offset: int = 0, slot_offset_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """build_amp_obs_demo (humanoid_amp.py:253-284; first_step=0) / _init_amp_obs_ref (:575-603; first_step=1)."""
     lib = _lib.load()
     dev = mlib.device
@@ -463,22 +474,24 @@ def amp_obs_demo(mlib: PackedMotionLib, cfg: EnvStepConfig, motion_ids: torch.Te
     kb = (C.c_int32 * len(cfg.key_bodies))(*[int(b) for b in cfg.key_bodies])
     aj = (C.c_int32 * max(1, len(joints)))(*[int(j) for j in joints])
     with torch.cuda.device(dev):
-        _lib.check(lib.phc_amp_obs_demo(C.byref(mlib.c), ids.data_ptr(), t0.data_ptr(), n, first_step, S, cfg.dt,
-                                        cfg.flags(), C.cast(kb, C.c_void_p), len(cfg.key_bodies), C.cast(aj, C.c_void_p),
-                                        len(joints), out.data_ptr(), out.stride(0),
-                                        None if only_where is None else _req(only_where, torch.int64, "only_where", dev).data_ptr(),
-                                        int(slot_offset), _stream()), "phc_amp_obs_demo")
+        _lib.check(lib.phc_amp_obs_demo_ring(C.byref(mlib.c), ids.data_ptr(), t0.data_ptr(), n, first_step, S, cfg.dt,
+                                             cfg.flags(), C.cast(kb, C.c_void_p), len(cfg.key_bodies), C.cast(aj, C.c_void_p),
+                                             len(joints), out.data_ptr(), out.stride(0),
+                                             None if only_where is None else _req(only_where, torch.int64, "only_where", dev).data_ptr(),
+                                             int(slot_offset), _ptr(slot_offset_dev), _stream()), "phc_amp_obs_demo")
     return out
 
 
-def amp_window_export(ring: torch.Tensor, head: int, out: torch.Tensor) -> torch.Tensor:
-    """out[n, k, :] = ring[n, (head + k) % S, :] -- newest-first AMP window from the ring (phc_amp_window_export)."""
+def amp_window_export(ring: torch.Tensor, head, out: torch.Tensor) -> torch.Tensor:
+    """out[n, k, :] = ring[n, (head + k) % S, :] -- newest-first AMP window from the ring (phc_amp_window_export).
+    `head`: an int, or the int32 [1] device tensor that holds it."""
     lib = _lib.load()
     n, S, A = ring.shape
     _req(ring, torch.float32, "ring")
     assert out.dtype == torch.float32 and out.is_cuda and out.shape[0] == n and out.stride(-1) == 1 and out.numel() == n * S * A
-    _lib.check(lib.phc_amp_window_export(ring.data_ptr(), ring.stride(0), n, S, A, int(head), out.data_ptr(), out.stride(0), _stream()),
-               "phc_amp_window_export")
+    dev_head = head if torch.is_tensor(head) else None
+    _lib.check(lib.phc_amp_window_export_ring(ring.data_ptr(), ring.stride(0), n, S, A, 0 if dev_head is not None else int(head), _ptr(dev_head),
+                                              out.data_ptr(), out.stride(0), _stream()), "phc_amp_window_export")
     return out
 
 

@@ -15,6 +15,14 @@ def _worker(rank, world, port, q):
     assert D.is_multi() and D.world_size() == world and D.rank_seed(5) == 5 + rank
     g = torch.full((1000,), float(rank + 1))
     scale = D.allreduce_grad_bucket(g)
+    # the pipelined form the agent uses: begin() issues the collective (off the compute stream on CUDA), the caller does
+    # weight-independent work of the next minibatch, end() joins; on CPU tensors it degenerates to the blocking call
+    red = D.GradReducer("cpu")
+    g2 = torch.full((1000,), float(2 * rank + 1))
+    s2 = red.begin(g2)
+    overlap_work = torch.arange(10).sum()          # stands for _prepare_minibatch(i + 1)
+    red.end()
+    assert s2 == 0.5 and float((g2 * s2)[0]) == 2.0 and int(overlap_work) == 45
     p = torch.full((10,), float(rank))
     D.broadcast_params(p)
     rms = types.SimpleNamespace(running_mean=torch.full((4,), float(rank), dtype=torch.float64),
@@ -48,4 +56,6 @@ def test_single_process_is_noop():
     from phc_b200.learning import dist as D
     g = torch.ones(8)
     assert D.allreduce_grad_bucket(g) == 1.0 and D.world_size() == 1 and not D.is_multi()
+    red = D.GradReducer("cpu")
+    assert red.begin(g) == 1.0 and red.end() is None and float(g.sum()) == 8.0
     assert D.max_over_ranks(3.0, "cpu") == 3.0

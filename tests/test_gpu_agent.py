@@ -100,6 +100,36 @@ def test_agent_epoch_small():
     assert torch.equal(agent.model.state_dict()["a2c_network._disc_logits.weight"], sd["model"]["a2c_network._disc_logits.weight"])
 
 
+def test_graph_replayed_rollout_equals_eager_rollout():
+    """AMPAgent.play_steps as ONE CUDA graph (second rollout captured, later ones replayed) against the eager loop: same seeds,
+    same generator state -> the same experience buffer, bit for bit, epoch after epoch (resets, AMP ring head on the device,
+    carried episode statistics and the random draws inside the graph included)."""
+    n = 96
+    cfgs = {"horizon_length": 8, "minibatch_size": 256, "amp_minibatch_size": 64, "mini_epochs": 1, "amp_obs_demo_buffer_size": 1024,
+            "amp_replay_buffer_size": 1024, "amp_batch_size": 128,
+            "network": {"mlp": {"units": [64, 32], "activation": "relu"}, "disc": {"units": [64, 32], "activation": "relu"}}}
+    agents = []
+    for graphed in (False, True):
+        _, task = make_task(n, seed=5)
+        torch.manual_seed(1234)
+        ag = AMPAgent("t", dict(cfgs, vec_env=RLGPUEnv(task), graph_rollout=graphed))
+        ag.obs = ag.env_reset()
+        ag._init_amp_demo_buf()
+        agents.append(ag)
+    assert agents[1]._graph_rollout and not agents[0]._graph_rollout
+    for epoch in range(4):
+        outs = []
+        for ag in agents:
+            torch.manual_seed(77 + epoch)
+            ag.set_eval()
+            bd = ag.play_steps()
+            torch.cuda.synchronize()
+            outs.append({k: v.clone() for k, v in ag.experience_buffer.items()} | {"returns": bd["returns"].clone(), "cur_rew": ag.current_rewards.clone()})
+        for k in outs[0]:
+            assert torch.equal(outs[0][k], outs[1][k]), f"epoch {epoch}: {k} differs between the eager and the graph-replayed rollout"
+    assert agents[1]._rollout_graph is not None and agents[1]._rollout_graph_launches > 8 * 10
+
+
 def test_ref_pose_cache_is_bit_identical_to_reinterpolation():
     """PHC_FLAG_REWARD_FROM_CACHE (the pose interpolated for the observation of step s is the reward-time pose of step
     s+1) against re-interpolating every step: identical bits over a rollout with resets in between."""
