@@ -100,6 +100,116 @@ def test_agent_epoch_small():
     assert torch.equal(agent.model.state_dict()["a2c_network._disc_logits.weight"], sd["model"]["a2c_network._disc_logits.weight"])
 
 
+@pytest.mark.parametrize("n", [4096, 16384])
+def test_specialised_step_kernel_matches_oracle_at_bench_sizes(n):
+    """The kernel bench.py's roofline object times -- env_step_kernel<1, 24, false, FAST=true> at 4096 envs (and the 16384-env
+    point) -- against the pinned oracle over three consecutive steps (pose cache, AMP ring with the head on the device,
+    per-env motion records): observations, reward terms, reset / terminate flags (bit-exact) and the AMP window."""
+    from phc_b200 import _lib
+    lib = _lib.load()
+    m = syn.make_motions(min(n, 4096), seed=17, min_frames=40, max_frames=90)       # 16384 envs share 4096 clips
+    task = HumanoidIm({"env": {"num_envs": n}, "motion_data": m, "seed": 17})
+    tab, cfg = oracle_tables(m), smpl_step_config()
+    torch.manual_seed(3)
+    task.reset()
+    torch.cuda.synchronize()
+    ids, t0 = task._sampled_motion_ids.cpu(), task._motion_start_times.cpu()
+    f0 = lib.phc_env_step_fast_launches()
+    for step in range(3):
+        hist = task._amp_obs_buf.cpu().clone()
+        task.step(None)
+        torch.cuda.synchronize()
+        exp = O.env_step(tab, cfg, task._rigid_body_state_reshaped.cpu(), task._dof_state.cpu(), task.dof_force_tensor.cpu(),
+                         task.progress_buf.cpu(), ids, t0, torch.zeros(n), torch.zeros(n, 3), hist)
+        close(task.obs_buf.cpu(), exp["obs"], atol=2e-6, what=f"obs (step {step}, {n} envs)")
+        close(task.rew_buf.cpu(), exp["rew"], what=f"rew (step {step})")
+        close(task.reward_raw.cpu(), exp["reward_raw"], what=f"reward_raw (step {step})")
+        assert torch.equal(task.reset_buf.cpu(), exp["reset"]) and torch.equal(task._terminate_buf.cpu(), exp["terminate"]), f"step {step}: reset / terminate"
+        close(task._amp_obs_buf.cpu(), exp["amp_obs_buf"], what=f"amp window (step {step})")
+    assert lib.phc_env_step_fast_launches() - f0 == 3, "the steady-state launches must take the specialised instantiation"
+
+
+def test_rollout_dataset_and_minibatch_gather_path_vs_oracle():
+    """what happens BETWEEN the rollout and the gradient -- discount_values, the combined reward,
+    prepare_dataset (advantage / value normalisation, swap_and_flatten01), the index-composed minibatch (rows addressed through
+    idx, replay / demo rows through composed indices, gathered inside the normalisation kernels) -- replayed on the CPU with
+    plain torch indexing from the SAME experience buffer and fed to the pinned oracle update; losses and every parameter
+    gradient must agree with what the agent's pipelined minibatch produced."""
+    from oracle import ppo_oracle as PO
+    n, T, mb, Bd = 64, 8, 256, 64
+    m, task = make_task(n, seed=9)
+    net_cfg = {"mlp": {"units": [128, 64], "activation": "relu"}, "disc": {"units": [128, 64], "activation": "relu"}}
+    agent = AMPAgent("t", {"vec_env": RLGPUEnv(task), "horizon_length": T, "minibatch_size": mb, "amp_minibatch_size": Bd, "mini_epochs": 1,
+                           "amp_obs_demo_buffer_size": 1024, "amp_replay_buffer_size": 1024, "amp_batch_size": 128, "network": net_cfg,
+                           "graph_rollout": False})
+    agent.obs = agent.env_reset()
+    agent._init_amp_demo_buf()
+    agent.train_epoch()                                   # statistics, replay buffer and weights leave their initial state
+    cpu = lambda t: t.detach().cpu().clone()
+    bd = agent.play_steps()
+    torch.cuda.synchronize()
+    eb = {k: cpu(v) for k, v in agent.experience_buffer.items()}
+    # --- rollout side on the CPU: rewards, GAE, returns
+    rew = agent._task_reward_w * eb["rewards"] + agent._disc_reward_w * cpu(bd["disc_rewards"]).view(n, T, 1).transpose(0, 1)
+    adv = O.gae(eb["dones"], eb["values"], rew, eb["next_values"], agent.gamma, agent.tau)
+    flat = lambda t: t.transpose(0, 1).reshape(n * T, *t.shape[2:])
+    close(cpu(bd["mb_advs"]), flat(adv), rtol=1e-4, atol=1e-5, what="GAE advantages of the rollout")
+    returns, values = flat(adv + eb["values"]), flat(eb["values"])
+    # --- the epoch's bookkeeping exactly as train_epoch does it, then ONE pipelined minibatch
+    agent._update_amp_demos()
+    N = bd["amp_obs"].shape[0]
+    bd["amp_obs_demo_idx"] = agent._amp_obs_demo_buffer.sample_indices(N)
+    agent._amp_replay_src = agent._amp_replay_buffer.data
+    bd["amp_obs_replay_idx"] = agent._amp_replay_buffer.sample_indices(N)
+    vms = agent.value_mean_std
+    v_mean, v_var, v_cnt = cpu(vms.running_mean), cpu(vms.running_var), cpu(vms.count)
+    agent.set_train()
+    agent.prepare_dataset(bd)
+    ds = agent.dataset
+    exp_adv = O.normalize_advantages(returns, values)
+    close(cpu(ds["advantages"]), exp_adv, rtol=1e-4, atol=1e-5, what="normalised advantages")
+    close(cpu(ds["old_values"]), O.rms_normalize(values, v_mean, v_var), rtol=1e-5, atol=1e-6, what="normalised old values")
+    v_mean2, v_var2, _ = O.rms_update(v_mean, v_var, v_cnt, values.double())
+    exp_ret = O.rms_normalize(returns, v_mean2, v_var2)   # the second call sees the statistics the first one updated
+    close(cpu(ds["returns"]), exp_ret, rtol=1e-4, atol=1e-5, what="normalised returns")
+    idx = agent._idx_buf[:mb]
+    obs_mean, obs_var = cpu(agent.running_mean_std_temp.running_mean), cpu(agent.running_mean_std_temp.running_var)
+    a_mean, a_var, a_cnt = cpu(agent._amp_input_mean_std.running_mean), cpu(agent._amp_input_mean_std.running_var), cpu(agent._amp_input_mean_std.count)
+    sd = {k: cpu(v) for k, v in agent.model.state_dict().items()}
+    replay_rows, demo_rows = cpu(agent._amp_replay_buffer.data), cpu(agent._amp_obs_demo_buffer.data)
+    prepared = agent._prepare_minibatch(idx)
+    agent._compute_gradients(idx, prepared)
+    torch.cuda.synchronize()
+    # --- the same minibatch with plain indexing
+    i = idx.cpu()
+    ia = i[:Bd]
+    amp_flat = flat(eb["amp_obs"])
+    blocks = [amp_flat[ia], replay_rows[cpu(bd["amp_obs_replay_idx"])[ia]], demo_rows[cpu(bd["amp_obs_demo_idx"])[ia]]]
+    normed = []
+    for blk in blocks:                                     # three RunningMeanStd.forward calls in train mode: normalise, then update
+        normed.append(O.rms_normalize(blk, a_mean, a_var))
+        a_mean, a_var, a_cnt = O.rms_update(a_mean, a_var, a_cnt, blk.double())
+    batch = dict(obs_n=O.rms_normalize(flat(eb["obses"])[i], obs_mean, obs_var), actions=flat(eb["actions"])[i], old_neglogp=flat(eb["neglogpacs"])[i],
+                 advantages=exp_adv[i], old_mu=flat(eb["mus"])[i], old_sigma=flat(eb["sigmas"])[i], returns=exp_ret[i],
+                 amp_agent=normed[0], amp_replay=normed[1], amp_demo=normed[2])
+    close(cpu(prepared[0])[:, :agent.obs_dim], batch["obs_n"], rtol=1e-5, atol=1e-6, what="gathered + normalised observations")
+    close(cpu(prepared[1])[:, :agent.amp_obs_dim], torch.cat(normed), rtol=1e-5, atol=2e-6, what="gathered + normalised AMP rows [agent | replay | demo]")
+    cfg = dict(e_clip=agent.e_clip, critic_coef=agent.critic_coef, entropy_coef=agent.entropy_coef, bounds_loss_coef=agent.bounds_loss_coef,
+               disc_coef=agent._disc_coef, disc_logit_reg=agent._disc_logit_reg, disc_grad_penalty=agent._disc_grad_penalty,
+               disc_weight_decay=agent._disc_weight_decay, grad_norm=agent.grad_norm, learning_rate=agent.last_lr, truncate_grads=True)
+    exp = PO.minibatch_update(sd, batch, cfg, n_hidden=2, dtype=torch.float64, mu_override=cpu(agent._ws_actor["out"])[:, :agent.actions_num].double())
+    r = agent.train_result_dict()
+    close(torch.tensor(r["critic_loss"]), exp["c_loss"].float(), rtol=2e-4, atol=1e-5, what="critic loss")
+    close(torch.tensor(r["actor_loss"]), exp["a_loss"].float(), rtol=1e-3, atol=1e-4, what="actor loss")
+    close(torch.tensor(r["disc_grad_penalty"]), exp["disc"]["disc_grad_penalty"].float(), rtol=1e-3, atol=1e-6, what="gradient penalty")
+    net = agent.model
+    for l in net.all_layers():
+        for kind, got in (("weight", net.weight(l, True)[:, :l.in_dim]), ("bias", net.bias(l, True))):
+            ge = exp["grads"][f"a2c_network.{l.name}.{kind}"]
+            err, sc = float((cpu(got).double() - ge).abs().max()), float(ge.abs().max()) + 1e-30
+            assert err <= 2e-3 * sc, f"gradient of {l.name}.{kind}: {err:.3e} vs scale {sc:.3e}"   # a mis-routed row would be O(1)
+
+
 def test_graph_replayed_rollout_equals_eager_rollout():
     """AMPAgent.play_steps as ONE CUDA graph (second rollout captured, later ones replayed) against the eager loop: same seeds,
     same generator state -> the same experience buffer, bit for bit, epoch after epoch (resets, AMP ring head on the device,
