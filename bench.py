@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-points", action="store_true", help="skip the 16384 / 65536-env points of the env-step roofline")
+    ap.add_argument("--workload", default="smpl", choices=sorted(WORKLOADS), help="configuration of the headline numbers (default: the one the metric is quoted on)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary configurations (H1, PNN big nets) reported as extra_configs")
     return ap.parse_args()
 
 
@@ -268,14 +270,35 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------------------------
 # the B200 arm
 # ----------------------------------------------------------------------------------------------------------------
-def build_agent(num_envs: int, device, rank: int, world: int, host_bank: bool):
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on (and what the driver's default run measures)
+    "smpl": dict(desc="SMPL 24 bodies, obs 934, AMP 10x196, im.yaml nets (1024-512)", envs=NUM_ENVS, algo_bytes=ALGO_BYTES_PER_ENV_STEP,
+                 kernel="phc::env_step_kernel<1, 24, false, true>"),
+    # configs[4]: Unitree H1, 20 bodies + 3 extend bodies in the reward, 19 hinge dofs, obs 778, AMP 10x63 (env_im_h1_phc.yaml, unitree_h1.yaml)
+    "h1": dict(desc="Unitree H1 20 bodies + 3 extend bodies, 19 hinge dofs, obs 778, AMP 10x63, im.yaml nets (1024-512)", envs=4096, algo_bytes=7528,
+               kernel="phc::env_step_kernel<1, 0, false, false> (run-time body count)"),
+    # configs[3]: PHC+ progressive network, 4 primitive columns of im_pnn_big.yaml nets (6 hidden layers, SiLU), 8192 envs
+    "pnn_big": dict(desc="SMPL 24 bodies, amp_pnn network: 4 primitive columns (training column 0) of 2048-1536-1024-1024-512-512 SiLU, disc 1024-512 ReLU "
+                         "(im_pnn_big.yaml)", envs=8192, algo_bytes=ALGO_BYTES_PER_ENV_STEP, kernel="phc::env_step_kernel<1, 24, false, true>"),
+}
+
+
+def build_agent(num_envs: int, device, rank: int, world: int, host_bank: bool, workload: str = "smpl"):
     from phc_b200 import synthetic as syn
     from phc_b200.env.humanoid_im import HumanoidIm, RLGPUEnv
     from phc_b200.learning.amp_agent import AMPAgent
-    motion = syn.make_motions(num_envs, seed=rank)                       # one clip per env, seed + rank (run_hydra.py:121)
+    cfg = {"multi_gpu": world > 1, "seed": 0, "device": str(device)}
+    if workload == "h1":
+        motion = syn.make_robot_motions(num_envs, seed=rank)
+    else:
+        motion = syn.make_motions(num_envs, seed=rank)                   # one clip per env, seed + rank (run_hydra.py:121)
+    if workload == "pnn_big":
+        cfg["network"] = {"name": "amp_pnn", "num_prim": 4, "training_prim": 0, "mlp": {"units": [2048, 1536, 1024, 1024, 512, 512], "activation": "silu"},
+                          "disc": {"units": [1024, 512], "activation": "relu"}}
     task = HumanoidIm({"env": {"num_envs": num_envs}, "motion_data": motion, "seed": rank, "host_sim_bank": host_bank},
                       device_type="cuda", device_id=device.index)
-    agent = AMPAgent("bench", {"vec_env": RLGPUEnv(task), "multi_gpu": world > 1, "seed": 0, "device": str(device)})
+    cfg["vec_env"] = RLGPUEnv(task)
+    agent = AMPAgent("bench", cfg)
     agent.obs = agent.env_reset()
     agent._init_amp_demo_buf()
     return agent, task
@@ -310,7 +333,8 @@ def timed_epochs(agent, steps: int, warmup: int, world: int, read_result: bool):
     return ms / steps, launches
 
 
-def env_kernel_roofline(task, peak_gbs: float, peak_src: str, iters: int = 40):
+def env_kernel_roofline(task, peak_gbs: float, peak_src: str, iters: int = 40, algo_bytes: int = ALGO_BYTES_PER_ENV_STEP,
+                         kernel: str = "phc::env_step_kernel<1, 24, false, true>"):
     """Average duration of the fused env-step kernel with inputs coming from HBM (L2 flushed by a 256 MB write before every
     launch), CUDA events on the launching stream.  Two measurements:
       * `kernel_us` (used for `achieved`): K x [flush, kernel] and K x [flush] are each bracketed by ONE event pair and the
@@ -358,15 +382,15 @@ def env_kernel_roofline(task, peak_gbs: float, peak_src: str, iters: int = 40):
             traffic = int(tj["dram_bytes_per_launch"])
     except Exception:
         traffic = None
-    achieved = ALGO_BYTES_PER_ENV_STEP * N / t / 1e9
+    achieved = algo_bytes * N / t / 1e9
     # what the launch really moves per env at J=24: inputs 1248 (state) + 1248 (cached reference pose of the reward time)
     # + 2 x 1248 (observation bracket) + 552 + 276 (dof) + 56 (scalars, env_motion); outputs 3744 (obs row incl. 8 pad bytes)
     # + 40 (reward/reset) + 784 (AMP ring slot) + 1248 (pose cache for the next step = the ref_* buffers)
     actual = 1248 + 1248 + 2 * 1248 + 552 + 276 + 56 + 3744 + 40 + 784 + 1248
     return {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
-            "kernel": "phc::env_step_kernel<1, 24, false, true>", "kernel_us": t * 1e6, "kernel_us_event_pair": t_pair * 1e6,
-            "frac_event_pair": ALGO_BYTES_PER_ENV_STEP * N / t_pair / 1e9 / peak_gbs,
-            "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * N,
+            "kernel": kernel, "kernel_us": t * 1e6, "kernel_us_event_pair": t_pair * 1e6,
+            "frac_event_pair": algo_bytes * N / t_pair / 1e9 / peak_gbs,
+            "algorithmic_bytes_per_launch": algo_bytes * N,
             "bytes_moved_per_launch_incl_amp_slot_and_pose_cache": actual * N, "achieved_incl_extras_gbs": actual * N / t / 1e9,
             "peak_source": peak_src,
             "timing": "L2 flushed before each launch; kernel_us = (%d x [flush, kernel] - %d x [flush]) / %d, one CUDA-event pair per batch, "
@@ -456,6 +480,30 @@ def env_roofline_points(device, rank, peak_gbs, peak_src, sizes=(16384, 65536)):
     return pts
 
 
+def run_extra_config(name: str, device, rank: int, world: int, peak_gbs: float, peak_src: str, steps: int = 2, warmup: int = 3):
+    """One of the other BASELINE.json configurations, measured the same way as the headline (device-resident simulator snapshots,
+    CUDA events around `steps` epochs after `warmup`) and reported inside the same JSON line (`extra_configs`)."""
+    w = WORKLOADS[name]
+    try:
+        agent, task = build_agent(w["envs"], device, rank, world, host_bank=False, workload=name)
+        ms, launches = timed_epochs(agent, steps, warmup, world, read_result=False)
+        out = {"workload": f"PPO epoch: {w['envs']} envs/GPU x 32 steps, {w['desc']}, minibatch 16384 x 6 mini-epochs", "num_envs_per_gpu": w["envs"],
+               "value": HORIZON * w["envs"] * world / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+               "gpu_launches": int(launches), "dtype": "f32"}
+        if rank == 0:
+            r = env_kernel_roofline(task, peak_gbs, peak_src, iters=20, algo_bytes=w["algo_bytes"], kernel=w["kernel"])
+            out["roofline"] = {k: r[k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel", "kernel_us", "algorithmic_bytes_per_launch")}
+            g = gemm_roofline(agent, iters=5)
+            if g is not None:
+                out["roofline_gemm"] = {k: g[k] for k in ("bound", "achieved", "peak", "unit", "frac", "forward_us", "backward_us")}
+        del agent, task
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:          # a secondary measurement never fails the headline line
+        torch.cuda.empty_cache()
+        return {"workload": name, "error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -479,7 +527,10 @@ def main():
 
     sampler = ClockSampler(local)
     note("building agent (device-resident simulator snapshots)")
-    agent, task = build_agent(args.num_envs, device, rank, world, host_bank=False)
+    wl = WORKLOADS[args.workload]
+    if args.workload != "smpl" and args.num_envs == NUM_ENVS:
+        args.num_envs = wl["envs"]
+    agent, task = build_agent(args.num_envs, device, rank, world, host_bank=False, workload=args.workload)
     note("agent built; timed epochs")
     if rank == 0:
         sampler.start()
@@ -495,7 +546,7 @@ def main():
     value = env_steps / (sec_per_step * 1e-3)
 
     peak, peak_src = measured_peak_gbs()
-    roof = env_kernel_roofline(task, peak, peak_src) if rank == 0 else None
+    roof = env_kernel_roofline(task, peak, peak_src, algo_bytes=wl["algo_bytes"], kernel=wl["kernel"]) if rank == 0 else None
     note("roofline kernel timed")
     roof_gemm = gemm_roofline(agent) if rank == 0 else None
     note("gemm roofline timed")
@@ -510,7 +561,7 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        agent2, task2 = build_agent(args.num_envs, device, rank, world, host_bank=True)
+        agent2, task2 = build_agent(args.num_envs, device, rank, world, host_bank=True, workload=args.workload)
         note("e2e agent built (pinned host snapshots)")
         ms2, _ = timed_epochs(agent2, max(1, args.steps), max(3, args.warmup) if args.warmup >= 3 else args.warmup, world, read_result=True)
         e2e = {"value": env_steps / (ms2 * 1e-3), "unit": "env-steps/s", "ms_per_step": ms2,
@@ -519,6 +570,18 @@ def main():
         del agent2, task2
         torch.cuda.empty_cache()
         note(f"e2e arm done: {ms2:.1f} ms/epoch")
+
+    extras = []
+    if not args.no_extras and args.workload == "smpl":
+        # the other BASELINE.json configurations: H1 (configs[4]) and the PNN big nets at 8192 envs (configs[3]) on one GPU; at 8 ranks the
+        # 16384-envs-over-8 split of configs[2] (2048 envs per rank instead of the weak-scaling 4096)
+        names = ["h1", "pnn_big"] if world == 1 else []
+        for nm in names:
+            extras.append(run_extra_config(nm, device, rank, world, peak, peak_src))
+            note(f"extra config {nm} done")
+        if world == 8:
+            WORKLOADS["smpl_2048"] = dict(WORKLOADS["smpl"], envs=2048, desc=WORKLOADS["smpl"]["desc"] + " -- 16384 envs sharded over 8 GPUs (BASELINE configs[2])")
+            extras.append(run_extra_config("smpl_2048", device, rank, world, peak, peak_src))
 
     if rank == 0:
         cpu = None
@@ -530,11 +593,11 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": sec_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_string(args.num_envs),
+                "config": {"workload": workload_string(args.num_envs) if args.workload == "smpl" else f"PPO epoch: {args.num_envs} envs/GPU x 32 steps, {wl['desc']}, minibatch 16384 x 6 mini-epochs",
                            "parallelism": f"dp{world} (env shards, 1 NCCL all-reduce per minibatch)",
                            "arithmetic": "fp32 throughout (the reference trains with mixed_precision: False): env kernels fp32, MLP GEMMs 3xTF32 on tcgen05 with fp32 accumulation",
                            "l2": "inputs larger than L2: 2.1 GB experience buffer + ~1 GB frame tables per epoch; the roofline kernel is timed with an explicit L2 flush"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "roofline_gemm": roof_gemm, "cpu_baseline": cpu}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "roofline_gemm": roof_gemm, "cpu_baseline": cpu, "extra_configs": extras}
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -388,6 +388,14 @@ PHC_API int phc_gemm_tc5s(const float* A, int64_t lda, int32_t a_kmajor, const f
                   float* aux, int64_t ldaux, int32_t accumulate, int32_t k_splits, void* stream);
 /* tile configuration switch (tests / tools): 1 = 128 x 128 tile per CTA, 2 = 256 x 128 tile per CTA pair, 0 = default */
 PHC_API int phc_gemm_tc5s_set_ctas(int32_t ctas);
+/* Humanoid._action_to_pd_targets (phc/env/tasks/humanoid.py:1711-1713) as pre_physics_step applies it (:1540-1556):
+ *   out[e, d] = pd_action_offset[d] + pd_action_scale[d] * action(e, d)        (product rounded, then the sum)
+ * dof_of_action (device int32 [num_dofs], optional): reduce_action -- the action column that drives dof d, or -1 (action 0);
+ * NULL needs num_actions == num_dofs.  zero_mask (device uint8 [num_dofs], optional): dofs forced to 0 afterwards
+ * (_freeze_hand / _freeze_toe).  The result is what the backend hands to gym.set_dof_position_target_tensor. */
+PHC_API int phc_pd_targets(const float* actions, int64_t lda, int64_t n, int32_t num_dofs, int32_t num_actions,
+                   const int32_t* dof_of_action, const float* offset, const float* scale, const uint8_t* zero_mask,
+                   float* out, int64_t ldo, void* stream);
 /* out[n] (+)= alpha * sum_m X[m*ld + n]   (bias gradients) */
 PHC_API int phc_colsum(const float* X, int64_t ld, int32_t M, int32_t N, float alpha, float* out, int32_t accumulate,
                void* stream);

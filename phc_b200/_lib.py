@@ -137,6 +137,7 @@ SIGNATURES = {
     "phc_scale_sumsq": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, _p, _p]),
     "phc_axpy2d": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.c_int64, C.c_int32, C.c_float, _p, _p]),
     "phc_mcp_combine": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, C.c_int64, _p]),
+    "phc_pd_targets": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _p, _p, _p, _p, _p, C.c_int64, _p]),
     "phc_act_backward": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _p]),
     "phc_grad_sumsq": (C.c_int, [_p, C.c_int64, _p, _p]),
     "phc_adam_step": (C.c_int, [_p, _p, _p, _p, C.c_int64, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,

@@ -344,6 +344,31 @@ __global__ void mcp_combine_kernel(const float* __restrict__ w, int64_t ldw, con
   }
 }
 
+// Humanoid._action_to_pd_targets (humanoid.py:1711-1713) with the surrounding pre_physics_step logic (:1540-1556):
+//   pd_tar = pd_action_offset + pd_action_scale * action      (product rounded, then the sum: torch evaluates it as two ops)
+// reduce_action: the policy emits only the dofs listed in action_idx, all others see action 0 (-> the offset);
+// zero_mask: dofs of frozen hands / toes are forced to 0 after the affine map.
+__global__ void pd_targets_kernel(const float* __restrict__ act, int64_t lda, int64_t n, int D, int A,
+                                  const int32_t* __restrict__ dof_of_action, const float* __restrict__ offset,
+                                  const float* __restrict__ scale, const uint8_t* __restrict__ zero_mask, float* __restrict__ out,
+                                  int64_t ldo) {
+  const int64_t total = n * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D;
+    const int d = (int)(i - r * D);
+    float a;
+    if (dof_of_action) {          // reduce_action: dof_of_action[d] = column of the action that drives dof d, or -1
+      const int c = dof_of_action[d];
+      a = c >= 0 ? act[r * lda + c] : 0.0f;
+    } else {
+      a = d < A ? act[r * lda + d] : 0.0f;
+    }
+    float t = __fadd_rn(offset[d], __fmul_rn(scale[d], a));
+    if (zero_mask && zero_mask[d]) t = 0.0f;
+    out[r * ldo + d] = t;
+  }
+}
+
 // backward of the activation that ends the MCP composer (amp_network_mcp_builder.py:57-63, ending_act):
 // ReLU: dy[r, c] = aux[r, c] > 0 ? dy[r, c] : 0 (aux = output);  SiLU: dy[r, c] *= silu'(aux[r, c]) (aux = pre-activation)
 __global__ void act_backward_kernel(float* __restrict__ dy, int64_t ldd, const float* __restrict__ y, int64_t ldy, int64_t n, int d,
@@ -485,6 +510,21 @@ extern "C" int phc_mcp_combine(const float* weights, int64_t ldw, const float* p
   if (!weights || !prim || !out || n < 0 || K < 1 || A < 1 || ldw < K || ldp < A || ldo < A) { phc_set_error("phc_mcp_combine: bad arguments"); return PHC_ERR_INVALID_ARG; }
   mcp_combine_kernel<<<ew_grid(n * A), 256, 0, ST(stream)>>>(weights, ldw, prim, ldp, prim_stride, n, K, A, discrete, out, ldo); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "mcp_combine_kernel");
+}
+
+extern "C" int phc_pd_targets(const float* actions, int64_t lda, int64_t n, int32_t num_dofs, int32_t num_actions,
+                              const int32_t* dof_of_action, const float* offset, const float* scale, const uint8_t* zero_mask,
+                              float* out, int64_t ldo, void* stream) {
+  if (!actions || !offset || !scale || !out || n < 0 || num_dofs < 1 || num_actions < 1 || lda < num_actions || ldo < num_dofs ||
+      (!dof_of_action && num_actions != num_dofs)) {
+    phc_set_error("phc_pd_targets: bad arguments (without dof_of_action the action must have one column per dof)");
+    return PHC_ERR_INVALID_ARG;
+  }
+  if (n == 0) return PHC_OK;
+  int64_t g = (n * num_dofs + 255) / 256; if (g > 148 * 8) g = 148 * 8;
+  phc::pd_targets_kernel<<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(actions, lda, n, num_dofs, num_actions, dof_of_action, offset, scale,
+                                                                                  zero_mask, out, ldo); phc_count_launches(1);
+  return phc_check_cuda(cudaGetLastError(), "pd_targets_kernel launch");
 }
 
 extern "C" int phc_act_backward(float* dy, int64_t ldd, const float* aux, int64_t ldaux, int64_t n, int32_t d, int32_t act, void* stream) {

@@ -15,8 +15,9 @@ d.install_on_import()`) that runs before the script's imports:
   phc.env.tasks.humanoid_im_mcp.HumanoidImMCP (+ short name)                 -> phc_b200.env.humanoid_im_mcp.HumanoidImMCP
   learning.amp_agent.AMPAgent / phc.learning.amp_agent.AMPAgent              -> phc_b200.learning.amp_agent.AMPAgent
 so `IMAmpAgent(AMPAgent)` (learning/im_amp.py) and `eval("HumanoidIm")` resolve to the B200 implementations.  `install()` does
-the same rebinding immediately for modules that are already imported (what the tests use).  Isaac Gym stays the reference's:
-the task receives it through cfg["sim"].
+the same rebinding immediately for modules that are already imported (what the tests use).  Isaac Gym stays the reference's: the
+rebinding keeps the original task class as `_RefHumanoidIm` and registers a backend factory that instantiates it as the owner of
+gym / sim / assets (phc_b200/env/backends.py); a backend can also be handed over directly as cfg["sim_backend"].
 """
 from __future__ import annotations
 
@@ -42,9 +43,28 @@ def _rebind(module) -> int:
     for names, attrs in _TARGETS.items():
         if module.__name__ in names:
             for attr, spec in attrs.items():
-                setattr(module, attr, _resolve(spec))
+                new = _resolve(spec)
+                old = getattr(module, attr, None)
+                if old is not None and old is not new:
+                    setattr(module, "_Ref" + attr, old)          # the reference's own class stays reachable (physics owner, see below)
+                setattr(module, attr, new)
                 n += 1
+            if "HumanoidIm" in attrs and getattr(module, "_RefHumanoidIm", None) is not None:
+                _register_isaacgym_factory(module._RefHumanoidIm)
     return n
+
+
+def _register_isaacgym_factory(ref_cls) -> None:
+    """parse_task.py:60 constructs the task with `eval(args.task)(cfg=cfg, sim_params=..., physics_engine=..., device_type=...,
+    device_id=..., headless=...)` and nothing else: the B200 HumanoidIm then needs a simulator backend from somewhere.  This factory
+    builds the reference's ORIGINAL task class with the same arguments -- it owns gym, sim, the actors and the asset data -- and wraps
+    it as the backend (phc_b200.env.backends.IsaacGymBackend); its observation / reward / reset code is never called."""
+    from .env import backends
+
+    def factory(cfg, sim_params, physics_engine, device_type, device_id, headless):
+        return backends.IsaacGymBackend(ref_cls(cfg=cfg, sim_params=sim_params, physics_engine=physics_engine, device_type=device_type,
+                                                device_id=device_id, headless=headless))
+    backends.register_backend_factory(factory)
 
 
 def install() -> int:

@@ -20,8 +20,33 @@ from typing import Dict, Optional, Sequence
 
 import torch
 
+from collections.abc import Mapping
+
 from .. import _lib, ops, synthetic as syn
 from ..ops import _ptr, _stream
+from . import backends
+
+
+class _Extras(dict):
+    """`extras` of the task with the reference's `amp_obs` entry (humanoid_amp.py:207-208: the flattened newest-first AMP window,
+    [N, S*A]) materialised from the ring only when somebody reads it; phc_b200's own agent takes `amp_obs_export` instead and has the
+    window written straight into its experience buffer."""
+
+    def __init__(self, task):
+        super().__init__()
+        self._task = task
+
+    def __getitem__(self, k):
+        if k == "amp_obs" and not dict.__contains__(self, k):
+            t = self._task
+            return t._amp_obs_buf.view(t.num_envs, -1)
+        return super().__getitem__(k)
+
+    def __contains__(self, k):
+        return k == "amp_obs" or super().__contains__(k)
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
 
 
 class SyntheticSim:
@@ -71,13 +96,21 @@ class HumanoidIm:
                  headless: bool = True):
         env = cfg.get("env", cfg)
         self.cfg = cfg
+        robot_cfg = cfg.get("robot", {}) or {}
+
+        def rcfg(key, default):       # robot-level switches: cfg.robot.<key> as run_hydra.py builds the tree (humanoid.py:285-330), else top level
+            return robot_cfg.get(key, cfg.get(key, default)) if isinstance(robot_cfg, Mapping) else cfg.get(key, default)
+        self._rcfg = rcfg
         self.device = torch.device(f"{device_type}:{device_id}" if device_type == "cuda" else device_type)
         torch.cuda.set_device(self.device)
         self.headless = headless
         self.num_envs = int(env.get("num_envs", 3072))
-        self.dt = float(env.get("controlFrequencyInv", 2)) * float(cfg.get("sim_dt", 1.0 / 60.0))
+        # dt = control_freq_inv * sim_params.dt (humanoid.py:74-76); sim_params is Isaac Gym's object when the reference constructs us
+        sim_block = cfg.get("sim", None)
+        sim_dt = getattr(sim_params, "dt", None) or (sim_block.get("dt") if isinstance(sim_block, Mapping) else None) or cfg.get("sim_dt", 1.0 / 60.0)
+        self.dt = float(env.get("controlFrequencyInv", 2)) * float(sim_dt)
         self.max_episode_length = int(env.get("episode_length", 300))
-        self.humanoid_type = cfg.get("humanoid_type", "smpl")
+        self.humanoid_type = rcfg("humanoid_type", "smpl")
         self._num_amp_obs_steps = int(env.get("numAMPObsSteps", 10))
         self.power_reward = bool(env.get("power_reward", True))
         self.power_coefficient = float(env.get("power_coefficient", 0.0005))
@@ -104,9 +137,17 @@ class HumanoidIm:
             raise NotImplementedError("cycle_motion_xp / zero_out_far_train (random re-placement, humanoid_im.py:966-980, :1131-1140) "
                                       "are not on the fused path; the shipped getup config has both off")
 
+        # ---- simulator backend: explicit object, the synthetic stand-in for synthetic motion data, or the registered factory ----
+        sim = cfg.get("sim_backend", None)
+        if sim is None and sim_block is not None and not isinstance(sim_block, Mapping):
+            sim = sim_block                           # round-1 spelling: the backend object under cfg["sim"] (the reference keeps physx settings there)
+        synthetic_data = isinstance(cfg.get("motion_data", None), (syn.MotionData, syn.RobotMotionData))
+        if sim is None and not synthetic_data:
+            sim = backends.make_backend(cfg, sim_params, physics_engine, device_type, device_id, headless)
         # ---- motion library (tables as MotionLibBase keeps them) -> packed device format -----------------------
-        m = cfg["motion_data"]
-        self._motion_data = m
+        m = cfg.get("motion_data", None)
+        if m is None:
+            m = self._load_motion(env, sim)           # Humanoid._load_motion (humanoid_im.py:300-360): MotionLibSMPL on env.motion_file
         d = m.to(self.device) if hasattr(m, "to") else m
         robot = hasattr(d, "gts_t")            # hinge-joint robot tables (phc/utils/motion_lib_real.py): h1 / g1
         if robot:
@@ -125,16 +166,17 @@ class HumanoidIm:
         self.num_bodies = J
         self.num_dof = self._motion_lib.dofs
         # cfg.robot.extend_config (humanoid_im.py:74-82): parent body index + position in the parent frame
-        ext = cfg.get("extend_config", [dict(parent=p, pos=q) for p, q in zip(syn.H1_EXT_PARENTS, syn.H1_EXT_POS)] if robot else [])
-        self.extend_body_parent_ids = [int(e["parent"]) for e in ext]
+        ext = rcfg("extend_config", [dict(parent=p, pos=q) for p, q in zip(syn.H1_EXT_PARENTS, syn.H1_EXT_POS)] if robot else [])
+        body_names = rcfg("body_names", None) or getattr(sim, "body_names", None)        # the reference names parents (extend_config.parent_name)
+        self.extend_body_parent_ids = [int(e["parent"]) if "parent" in e else list(body_names).index(e["parent_name"]) for e in ext]
         self.extend_body_pos_in_parent = [list(e["pos"]) for e in ext]
         self.num_extend_bodies = len(ext)
         key_bodies = env.get("key_body_ids", syn.H1_KEY_BODIES if robot else (syn.SMPL_KEY_BODIES if J == 24 else [J - 1]))
         reset_bodies = env.get("reset_body_ids", syn.SMPL_RESET_BODIES if (J == 24 and not robot) else None)
-        dof_subset = env.get("dof_subset", syn.SMPL_DOF_SUBSET if (J == 24 and not robot and cfg.get("has_dof_subset", True)) else None)
+        dof_subset = env.get("dof_subset", syn.SMPL_DOF_SUBSET if (J == 24 and not robot and rcfg("has_dof_subset", True)) else None)
         self.step_cfg = ops.EnvStepConfig(
             dt=self.dt, time_steps=self._num_traj_samples, traj_dt=self._traj_sample_timestep,
-            upright=bool(cfg.get("has_upright_start", True)), local_root_obs=bool(env.get("local_root_obs", True)),
+            upright=bool(rcfg("has_upright_start", True)), local_root_obs=bool(env.get("local_root_obs", True)),
             root_height_obs=bool(env.get("root_height_obs", True)), power_reward=self.power_reward,
             power_coef=self.power_coefficient, early_term=bool(env.get("enableEarlyTermination", True)),
             key_bodies=key_bodies, reset_bodies=reset_bodies, term_dist=float(env.get("terminationDistance", 0.25)),
@@ -146,9 +188,9 @@ class HumanoidIm:
         self._key_body_ids, self._reset_bodies_id, self.dof_subset = key_bodies, reset_bodies, dof_subset
 
         # ---- simulator backend and its tensors (Humanoid._setup_tensors) ---------------------------------------
-        self.sim = cfg.get("sim") or SyntheticSim(m, self.num_envs, self.device, seed=int(cfg.get("seed", 0)),
-                                                  host_bank=bool(cfg.get("host_sim_bank", False)),
-                                                  amp_dim=13 + 2 * self.num_dof + 3 * len(key_bodies) if robot else 196)
+        self.sim = sim if sim is not None else SyntheticSim(m, self.num_envs, self.device, seed=int(cfg.get("seed", 0)),
+                                                             host_bank=bool(cfg.get("host_sim_bank", False)),
+                                                             amp_dim=13 + 2 * self.num_dof + 3 * len(key_bodies) if robot else 196)
         if not hasattr(self.sim, "set_env_state"):
             raise TypeError("simulator backend lacks set_env_state(mask, rigid_body_state, dof_state): without it an episode reset would only "
                             "rewrite observation-side tensors and the physics would keep running from the old state (INTEGRATION.md, "
@@ -174,7 +216,7 @@ class HumanoidIm:
         self._reset_mask = torch.zeros(N, dtype=i64, device=dev)
         self._point_goal = torch.zeros(N, device=dev)                 # humanoid_im.py:95
         self._cycle_phase = torch.zeros(N, device=dev)                # uniform numbers for clips that wrap this step
-        self.extras: Dict[str, torch.Tensor] = {}
+        self.extras: Dict[str, torch.Tensor] = _Extras(self)
 
         common = dict(cfg=self.step_cfg, mlib=self._motion_lib, body_state=self._rigid_body_state_reshaped,
                       dof_state=self._dof_state, dof_force=self.dof_force_tensor, progress=self.progress_buf,
@@ -218,6 +260,8 @@ class HumanoidIm:
         self._lib = _lib.load()
         self._kb = (C.c_int32 * len(key_bodies))(*[int(b) for b in key_bodies])
         self.actions = None
+        if hasattr(self.sim, "pd_action_offset"):         # the backend knows the dof limits (Humanoid._build_pd_action_offset_scale)
+            self.set_pd_action_map(self.sim.pd_action_offset, self.sim.pd_action_scale)
 
     # ---- sizes (Humanoid.get_obs_size & co) --------------------------------------------------------------------
     def get_obs_size(self):
@@ -247,9 +291,43 @@ class HumanoidIm:
         return (self.get_obs_size(),)
 
     # ---- step ---------------------------------------------------------------------------------------------------
+    def set_pd_action_map(self, offset: torch.Tensor, scale: torch.Tensor, action_idx=None, zero_dofs=()) -> None:
+        """The affine action -> PD-target map of Humanoid._build_pd_action_offset_scale (humanoid.py:1331-1380; built from the
+        asset's dof limits, so the backend supplies it): `_pd_action_offset`, `_pd_action_scale` [num_dof]; `action_idx` (reduce_action:
+        the dofs the policy drives); `zero_dofs`: dof indices frozen at 0 (_freeze_hand / _freeze_toe).  Once set, step() turns the
+        policy output into PD targets on the device (phc_pd_targets) before it reaches the backend's simulate()."""
+        D = self.num_dof
+        self._pd_action_offset = offset.to(self.device, torch.float32).contiguous()
+        self._pd_action_scale = scale.to(self.device, torch.float32).contiguous()
+        assert self._pd_action_offset.shape == (D,) and self._pd_action_scale.shape == (D,)
+        self._pd_dof_of_action = None
+        if action_idx is not None:
+            m = torch.full((D,), -1, dtype=torch.int32)
+            m[torch.as_tensor(action_idx, dtype=torch.long)] = torch.arange(len(action_idx), dtype=torch.int32)
+            self._pd_dof_of_action = m.to(self.device)
+        self._pd_zero = None
+        if len(zero_dofs):
+            z = torch.zeros(D, dtype=torch.uint8)
+            z[torch.as_tensor(list(zero_dofs), dtype=torch.long)] = 1
+            self._pd_zero = z.to(self.device)
+        self._pd_tar = torch.zeros(self.num_envs, D, device=self.device)
+
+    def _action_to_pd_targets(self, action: torch.Tensor) -> torch.Tensor:
+        """humanoid.py:1711-1713 (+ the reduce_action scatter and the frozen dofs of pre_physics_step, :1540-1556)."""
+        if getattr(self, "_pd_action_offset", None) is None:
+            raise ops.PhcError("_action_to_pd_targets: call set_pd_action_map(offset, scale, ...) first (the backend owns the dof limits)")
+        a = action if (action.dtype == torch.float32 and action.stride(-1) == 1) else action.float().contiguous()
+        _lib.check(self._lib.phc_pd_targets(a.data_ptr(), a.stride(0), a.shape[0], self.num_dof, a.shape[1], _ptr(self._pd_dof_of_action),
+                                            self._pd_action_offset.data_ptr(), self._pd_action_scale.data_ptr(), _ptr(self._pd_zero),
+                                            self._pd_tar.data_ptr(), self._pd_tar.stride(0), _stream()), "phc_pd_targets")
+        return self._pd_tar
+
     def step(self, actions: torch.Tensor) -> None:
-        """BaseTask.step (base_task.py:216-234): pre-physics + simulate (backend), then post_physics_step."""
+        """BaseTask.step (base_task.py:216-234): pre-physics + simulate (backend), then post_physics_step.  With a PD action map
+        set the backend receives PD targets (what pre_physics_step hands to gym.set_dof_position_target_tensor), else the raw actions."""
         self.actions = actions
+        if actions is not None and getattr(self, "_pd_action_offset", None) is not None:
+            actions = self._action_to_pd_targets(actions)
         self.sim.simulate(actions)
         self.post_physics_step()
 
@@ -373,8 +451,48 @@ class HumanoidIm:
                          slot_offset=0, slot_offset_dev=self._ring_head)
         return self.obs_buf
 
+    def _load_motion(self, env, sim):
+        """Humanoid._load_motion for humanoid_type smpl (humanoid_im.py:300-341): MotionLibSMPL over env.motion_file, one clip per env
+        loaded with the per-env skeleton trees / shapes / limb weights the simulator side built from its assets."""
+        from ..motion_lib import MotionLibSMPL
+        motion_file = env.get("motion_file", self.cfg.get("motion_file", None))
+        if motion_file is None:
+            raise KeyError("HumanoidIm: cfg has neither `motion_data` (pre-built tables) nor env.motion_file")
+        for need in ("skeleton_trees", "humanoid_shapes", "humanoid_limb_and_weights"):
+            if not hasattr(sim, need):
+                raise TypeError(f"HumanoidIm: loading {motion_file!r} needs the backend's `{need}` (Humanoid keeps them per env, humanoid.py:780-860)")
+        self.seq_motions = bool(env.get("seq_motions", False))
+        self.max_len = int(env.get("max_len", -1)) if "max_len" in env else -1
+        self._min_motion_len = int(env.get("min_length", -1))
+        test = bool(self.cfg.get("test", False))
+        lib = MotionLibSMPL(dict(motion_file=motion_file, device=self.device, fix_height=0, min_length=self._min_motion_len, max_length=self.max_len,
+                                 im_eval=bool(self.cfg.get("im_eval", False)), multi_thread=False, smpl_type=self._rcfg("humanoid_type", "smpl"),
+                                 randomrize_heading=True, step_dt=self.dt, test=test))
+        self._motion_train_lib = self._motion_eval_lib = lib
+        lib.load_motions(skeleton_trees=sim.skeleton_trees, gender_betas=torch.as_tensor(sim.humanoid_shapes).cpu(),
+                         limb_weights=torch.as_tensor(sim.humanoid_limb_and_weights).cpu(), random_sample=(not test) and (not self.seq_motions),
+                         max_len=-1 if test else self.max_len)
+        return lib
+
     def resample_motions(self):
-        """After `_sampled_motion_ids` changed: refresh the per-env motion parameter records of both launch plans."""
+        """HumanoidIm.resample_motions (humanoid_im.py:369-394).  With a loadable library (`MotionLibSMPL.load_motions`): sample and load a
+        new set of clips on the device, re-point both launch plans at the new tables, keep every humanoid where it stands
+        (`_global_offset[:, :2] = root xy - reference root xy at the env's current motion time`), reset all envs.  With fixed tables
+        (synthetic data) only the per-env motion records are refreshed (`_sampled_motion_ids` may have been edited)."""
+        lib = self._motion_data
+        if hasattr(lib, "load_motions") and hasattr(self.sim, "skeleton_trees"):
+            test = bool(self.cfg.get("test", False))
+            lib.load_motions(skeleton_trees=self.sim.skeleton_trees, gender_betas=torch.as_tensor(self.sim.humanoid_shapes).cpu(),
+                             limb_weights=torch.as_tensor(self.sim.humanoid_limb_and_weights).cpu(),
+                             random_sample=(not test) and (not getattr(self, "seq_motions", False)), max_len=-1 if test else getattr(self, "max_len", -1))
+            self._motion_lib = lib.packed
+            for plan in (self._plan, self._plan_reset_obs):
+                plan.set_motion_lib(self._motion_lib)
+            t = self.progress_buf.float() * self.dt + self._motion_start_times + self._motion_start_times_offset
+            root = ops.motion_state(self._motion_lib, self._sampled_motion_ids, t.contiguous(), want_dof=False)["root_pos"]   # get_root_pos_smpl
+            self._global_offset[:, :2] = self._rigid_body_state_reshaped[:, 0, :2] - root[:, :2]
+            self.reset()
+            return
         self._plan.refresh_motion_params()
         self._plan_reset_obs.refresh_motion_params()
 

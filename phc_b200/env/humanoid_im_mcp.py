@@ -69,5 +69,7 @@ class HumanoidImMCP(HumanoidIm):
     def step(self, weights: torch.Tensor) -> None:
         actions = self.compose_actions(weights)
         self.actions = actions
+        if getattr(self, "_pd_action_offset", None) is not None:        # mixed action -> PD targets (humanoid.py:1711-1713)
+            actions = self._action_to_pd_targets(actions)
         self.sim.simulate(actions)
         self.post_physics_step()

@@ -192,7 +192,7 @@ class AMPAgent:
             cfg["network"].update(config["network"])
         self.config = cfg
         self.base_name = base_name
-        self.vec_env = cfg["vec_env"]
+        self.vec_env = cfg.get("vec_env") or self._create_vec_env(cfg)
         task = self.vec_env.env.task
         self.device = torch.device(cfg.get("device", task.device))
         self.ppo_device = self.device
@@ -236,7 +236,7 @@ class AMPAgent:
         self.rank = torch.distributed.get_rank() if self.multi_gpu else 0
         self.world = D.world_size() if self.multi_gpu else 1
 
-        netcfg = cfg["network"]
+        netcfg = cfg["network"] = self._network_spec(cfg["network"])
         if netcfg.get("name", "amp") == "amp_mcp":
             # AMPMCPBuilder (amp_network_mcp_builder.py:33-59): has_softmax defaults to TRUE there (appends nn.Softmax) and
             # ending_act False strips the final activation.  Both shipped MCP configs set has_softmax: False, ending_act: True
@@ -278,6 +278,48 @@ class AMPAgent:
         self.set_eval()
 
     # ------------------------------------------------------------------------------------------------------
+    # what rl_games hands to an agent (run_hydra.py:199-262, rl_games 1.1.4 a2c_common.A2CBase.__init__)
+    # ------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _create_vec_env(cfg):
+        """rl_games builds the agent from `config['env_name']` / `config['env_config']`: A2CBase creates the vectorised env with
+        `vecenv.create_vec_env(env_name, num_actors, **env_config)`, which looks the name up in the registries run_hydra.py fills
+        (`vecenv.register('RLGPU', ...)`, `env_configurations.register('rlgpu', {'env_creator': ..., 'vecenv_type': 'RLGPU'})`,
+        run_hydra.py:238-240).  The same lookup here: rl_games' registry when the package is importable, else the small registry of
+        phc_b200.learning.vecenv_registry (what the tests use).  The result has to expose `.env.task` like the reference's RLGPUEnv."""
+        name = cfg.get("env_name")
+        if name is None:
+            raise KeyError("AMPAgent: config carries neither `vec_env` nor `env_name` (rl_games' params['config']['env_name'])")
+        num_actors, env_config = cfg.get("num_actors", 0), dict(cfg.get("env_config", {}) or {})
+        from . import vecenv_registry as R
+        if name in R.configurations:
+            return R.create_vec_env(name, num_actors, **env_config)
+        try:
+            from rl_games.common import vecenv
+        except ImportError:
+            raise KeyError(f"AMPAgent: env_name {name!r} is not registered (phc_b200.learning.vecenv_registry.register) and rl_games is not importable")
+        return vecenv.create_vec_env(name, num_actors, **env_config)
+
+    @staticmethod
+    def _network_spec(net):
+        """config['network']: a plain dict (this package, tests) or what rl_games' Runner puts there -- a model object whose builder
+        keeps the yaml block (`model.network_builder.params`, rl_games 1.1.4 model_builder.py / network_builder.py).  Returns the dict
+        {name, mlp: {units, activation}, disc: {units, activation}, ...} the B200 networks are built from."""
+        if isinstance(net, dict):
+            return net
+        for holder in (net, getattr(net, "network_builder", None), getattr(net, "model", None)):
+            p = getattr(holder, "params", None)
+            if isinstance(p, dict) and "mlp" in p:
+                spec = {"mlp": dict(p["mlp"]), "disc": dict(p.get("disc", p["mlp"])), "name": getattr(holder, "name", p.get("name", "amp"))}
+                for k in ("has_softmax", "ending_act", "num_prim", "training_prim"):
+                    if k in p:
+                        spec[k] = p[k]
+                space = p.get("space", {}).get("continuous", {})
+                if "sigma_init" in space:
+                    spec["sigma_init"] = space["sigma_init"].get("val", -2.9)
+                return spec
+        raise TypeError("AMPAgent: config['network'] is neither a dict nor an rl_games model / network builder with a `params` block")
+
     def set_eval(self):
         for r in (self.running_mean_std, self.value_mean_std, self._amp_input_mean_std):
             if r is not None:

@@ -431,6 +431,15 @@ class EnvStepPlan:
         self._args_ref = C.byref(a)
         self.refresh_motion_params()
 
+    def set_motion_lib(self, mlib: PackedMotionLib) -> None:
+        """Re-point the plan at a re-loaded motion library of the same character (HumanoidIm.resample_motions): new frame tables,
+        new per-env motion records; every other pointer of the launch stays."""
+        if mlib.num_bodies != self.mlib.num_bodies or mlib.num_ext_bodies != self.mlib.num_ext_bodies or mlib.dofs != self.mlib.dofs:
+            raise PhcError("set_motion_lib: the new library must describe the same character (bodies / extend bodies / dofs)")
+        self.mlib = mlib
+        self.args.lib = mlib.c
+        self.refresh_motion_params()
+
     def refresh_motion_params(self) -> None:
         """Re-gather the per-env motion parameters; call whenever `motion_ids` (HumanoidIm._sampled_motion_ids) changes."""
         _lib.check(self._lib.phc_env_motion_gather(C.byref(self.mlib.c), self._keep["motion_ids"].data_ptr(), self.N,

@@ -121,7 +121,9 @@ def test_specialised_step_kernel_matches_oracle_at_bench_sizes(n):
         torch.cuda.synchronize()
         exp = O.env_step(tab, cfg, task._rigid_body_state_reshaped.cpu(), task._dof_state.cpu(), task.dof_force_tensor.cpu(),
                          task.progress_buf.cpu(), ids, t0, torch.zeros(n), torch.zeros(n, 3), hist)
-        close(task.obs_buf.cpu(), exp["obs"], atol=2e-6, what=f"obs (step {step}, {n} envs)")
+        # 15 M observation entries per step at 16384 envs: the velocity-difference columns subtract O(30 m/s) operands, one ulp of
+        # which (3.8e-6) survives the cancellation in a handful of entries -- atol 5e-6 here, 2e-6 in the small-batch tests
+        close(task.obs_buf.cpu(), exp["obs"], atol=5e-6, what=f"obs (step {step}, {n} envs)")
         close(task.rew_buf.cpu(), exp["rew"], what=f"rew (step {step})")
         close(task.reward_raw.cpu(), exp["reward_raw"], what=f"reward_raw (step {step})")
         assert torch.equal(task.reset_buf.cpu(), exp["reset"]) and torch.equal(task._terminate_buf.cpu(), exp["terminate"]), f"step {step}: reset / terminate"

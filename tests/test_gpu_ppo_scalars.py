@@ -44,3 +44,41 @@ def test_gae_linearity_full_size():
     close(a12.cpu(), (a1 + 2 * a2).cpu(), rtol=1e-4, atol=1e-4, what="linearity")
     adv = ops.adv_norm((a1 + v).reshape(-1), v.reshape(-1))
     assert abs(float(adv.mean())) < 1e-4 and abs(float(adv.std()) - 1.0) < 1e-4
+
+
+def test_pd_targets_bit_exact_incl_reduce_action_and_frozen_dofs():
+    """phc_pd_targets = Humanoid._action_to_pd_targets (humanoid.py:1711-1713) as pre_physics_step uses it (:1540-1556): the
+    affine map, the reduce_action scatter (actions_full[:, action_idx] = actions) and the frozen hand / toe dofs; bit-exact
+    against the torch expressions of the reference evaluated on the CPU."""
+    from phc_b200 import synthetic as syn
+    from phc_b200.env.humanoid_im import HumanoidIm
+    n = 300
+    task = HumanoidIm({"env": {"num_envs": n}, "motion_data": syn.make_motions(8, seed=0, min_frames=20, max_frames=30), "seed": 0})
+    D = task.num_dof
+    g = torch.Generator().manual_seed(4)
+    off, sc = torch.randn(D, generator=g), torch.rand(D, generator=g) * 3 + 0.1
+    act = torch.randn(n, D, generator=g)
+    task.set_pd_action_map(off, sc)
+    got = task._action_to_pd_targets(act.to(task.device))
+    torch.cuda.synchronize()
+    assert torch.equal(got.cpu(), off + sc * act)
+    # reduce_action + frozen toes / hands
+    idx = torch.randperm(D, generator=g)[:40].sort().values
+    frozen = [3, 4, 5, 60, 61, 62]
+    task.set_pd_action_map(off, sc, action_idx=idx.tolist(), zero_dofs=frozen)
+    a2 = torch.randn(n, 40, generator=g)
+    got = task._action_to_pd_targets(a2.to(task.device))
+    torch.cuda.synchronize()
+    full = torch.zeros(n, D)
+    full[:, idx] = a2
+    exp = off + sc * full
+    exp[:, frozen] = 0
+    assert torch.equal(got.cpu(), exp)
+    # step() hands the targets (not the raw action) to the backend
+    seen = {}
+    orig = task.sim.simulate
+    task.sim.simulate = lambda a: (seen.__setitem__("a", a.clone()), orig(a))[1]
+    task.reset()
+    task.step(a2.to(task.device))
+    torch.cuda.synchronize()
+    assert torch.equal(seen["a"].cpu(), exp)
