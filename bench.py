@@ -292,7 +292,9 @@ def build_agent(num_envs: int, device, rank: int, world: int, host_bank: bool, w
         motion = syn.make_robot_motions(num_envs, seed=rank)
     else:
         motion = syn.make_motions(num_envs, seed=rank)                   # one clip per env, seed + rank (run_hydra.py:121)
-    if workload == "pnn_big":
+    if workload.startswith("pnn_big"):
+        if workload == "pnn_big_tf32":
+            cfg["mlp_precision"] = "tf32"
         cfg["network"] = {"name": "amp_pnn", "num_prim": 4, "training_prim": 0, "mlp": {"units": [2048, 1536, 1024, 1024, 512, 512], "activation": "silu"},
                           "disc": {"units": [1024, 512], "activation": "relu"}}
     task = HumanoidIm({"env": {"num_envs": num_envs}, "motion_data": motion, "seed": rank, "host_sim_bank": host_bank},
@@ -449,11 +451,12 @@ def gemm_roofline(agent, iters: int = 20):
     t_b, fl_b = timed(lambda: [eng.run_group(d) for d in bwd])
     net.grads.zero_()
     peak, src = measured_peak_tf32()
-    ach = 3.0 * (fl_f + fl_b) / (t_f + t_b) / 1e12
+    passes = 1.0 if eng.precision == "tf32" else 3.0          # tensor-core products per fp32 product
+    ach = passes * (fl_f + fl_b) / (t_f + t_b) / 1e12
     return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
             "kernel": "phc::tc5::smem_split::gemm_tc5s_kernel (grouped forward + backward launches of one minibatch)",
-            "forward_us": t_f * 1e6, "forward_tflops": 3.0 * fl_f / t_f / 1e12, "backward_us": t_b * 1e6,
-            "backward_tflops": 3.0 * fl_b / t_b / 1e12, "algorithmic_fp32_flops_per_minibatch": fl_f + fl_b,
+            "forward_us": t_f * 1e6, "forward_tflops": passes * fl_f / t_f / 1e12, "backward_us": t_b * 1e6,
+            "backward_tflops": passes * fl_b / t_b / 1e12, "tensor_products_per_fp32_product": passes, "algorithmic_fp32_flops_per_minibatch": fl_f + fl_b,
             "fp32_equivalent_tflops": (fl_f + fl_b) / (t_f + t_b) / 1e12, "peak_source": src,
             "timing": "%d x [3 forward launches] and %d x [3 backward launches] of the bench minibatch, one CUDA-event pair each; operands (2.1 GB experience "
                       "buffer aside) are the minibatch workspaces, ~0.5 GB, larger than L2" % (iters, iters)}
@@ -489,7 +492,7 @@ def run_extra_config(name: str, device, rank: int, world: int, peak_gbs: float, 
         ms, launches = timed_epochs(agent, steps, warmup, world, read_result=False)
         out = {"workload": f"PPO epoch: {w['envs']} envs/GPU x 32 steps, {w['desc']}, minibatch 16384 x 6 mini-epochs", "num_envs_per_gpu": w["envs"],
                "value": HORIZON * w["envs"] * world / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
-               "gpu_launches": int(launches), "dtype": "f32"}
+               "gpu_launches": int(launches), "dtype": "tf32 single pass (MLPs), f32 elsewhere" if name.endswith("_tf32") else "f32"}
         if rank == 0:
             r = env_kernel_roofline(task, peak_gbs, peak_src, iters=20, algo_bytes=w["algo_bytes"], kernel=w["kernel"])
             out["roofline"] = {k: r[k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel", "kernel_us", "algorithmic_bytes_per_launch")}
@@ -575,7 +578,9 @@ def main():
     if not args.no_extras and args.workload == "smpl":
         # the other BASELINE.json configurations: H1 (configs[4]) and the PNN big nets at 8192 envs (configs[3]) on one GPU; at 8 ranks the
         # 16384-envs-over-8 split of configs[2] (2048 envs per rank instead of the weak-scaling 4096)
-        names = ["h1", "pnn_big"] if world == 1 else []
+        WORKLOADS["pnn_big_tf32"] = dict(WORKLOADS["pnn_big"], desc=WORKLOADS["pnn_big"]["desc"] + "; MLP GEMMs in the opt-in single-pass TF32 mode "
+                                         "(bf16-class: 8-bit exponent, 10-bit mantissa, fp32 accumulate) instead of 3xTF32")
+        names = ["h1", "pnn_big", "pnn_big_tf32"] if world == 1 else []
         for nm in names:
             extras.append(run_extra_config(nm, device, rank, world, peak, peak_src))
             note(f"extra config {nm} done")

@@ -386,6 +386,16 @@ PHC_API int phc_gemm_group(const PhcGemmDesc* problems, int32_t count, void* str
 PHC_API int phc_gemm_tc5s(const float* A, int64_t lda, int32_t a_kmajor, const float* B, int64_t ldb, int32_t b_kmajor, float* C,
                   int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha, const float* bias, int32_t act,
                   float* aux, int64_t ldaux, int32_t accumulate, int32_t k_splits, void* stream);
+/* Arithmetic of phc_gemm_tc5s / phc_gemm_group (process-wide switch, read at launch):
+ *   PHC_GEMM_FP32_3XTF32      (default) three tensor-core products per fp32 product, fp32-equivalent (the parity path: the
+ *                             reference trains with mixed_precision: False);
+ *   PHC_GEMM_TF32_SINGLE_PASS one tcgen05 kind::tf32 product: operands truncated to 10 mantissa bits, fp32 accumulate, ~1e-3
+ *                             relative -- the reduced-precision tensor-core mode BASELINE.json configs[3] asks for (bf16-class: the
+ *                             same 8-bit exponent, 3 more mantissa bits than bf16), 3x fewer tensor instructions and no split pass.
+ *                             OPT-IN, with its own tolerance (tests/test_gpu_gemm_tc5s.py); nothing in the parity tests uses it. */
+#define PHC_GEMM_FP32_3XTF32 0
+#define PHC_GEMM_TF32_SINGLE_PASS 1
+PHC_API int phc_gemm_set_precision(int32_t mode);
 /* tile configuration switch (tests / tools): 1 = 128 x 128 tile per CTA, 2 = 256 x 128 tile per CTA pair, 0 = default */
 PHC_API int phc_gemm_tc5s_set_ctas(int32_t ctas);
 /* Humanoid._action_to_pd_targets (phc/env/tasks/humanoid.py:1711-1713) as pre_physics_step applies it (:1540-1556):

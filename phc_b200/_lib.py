@@ -79,6 +79,7 @@ class PhcGemmDesc(C.Structure):
 
 
 PHC_GEMM_GROUP_MAX = 8
+PHC_GEMM_FP32_3XTF32, PHC_GEMM_TF32_SINGLE_PASS = 0, 1
 
 # name -> (restype, argtypes); must list every symbol include/phc_b200.h declares (tests check this)
 SIGNATURES = {
@@ -123,6 +124,7 @@ SIGNATURES = {
     "phc_gemm_tc5s": (C.c_int, [_p, C.c_int64, C.c_int32, _p, C.c_int64, C.c_int32, _p, C.c_int64, C.c_int32, C.c_int32,
                                 C.c_int32, C.c_float, _p, C.c_int32, _p, C.c_int64, C.c_int32, C.c_int32, _p]),
     "phc_gemm_tc5s_set_ctas": (C.c_int, [C.c_int32]),
+    "phc_gemm_set_precision": (C.c_int, [C.c_int32]),
     "phc_colsum": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p, C.c_int32, _p]),
     "phc_rms_apply": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, _p, _p, C.c_float, C.c_int32, _p, C.c_int64, _p, _p]),
     "phc_rms_workspace_bytes": (C.c_int64, [C.c_int32]),

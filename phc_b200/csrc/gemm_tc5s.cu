@@ -75,6 +75,7 @@ struct alignas(64) Params {
   CUtensorMap tmC[MAX_PROBLEMS];
   Prob p[MAX_PROBLEMS];
   int count, total_tiles;
+  int single_pass;      // 1: one tensor-core product per fp32 product (plain TF32, ~1e-3 relative): no lo tiles, no splitters
 };
 
 struct Tile { int g, m0, n0, kb_begin, nkb, z; };
@@ -202,7 +203,7 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
         for (int i = 0; i < tl.nkb; ++i, ++it) {
           const int s = it % C::RAW_STAGES, l = it % C::LO_STAGES;
           mbar_wait(full_bar + s, (it / C::RAW_STAGES) & 1);        // own raw tiles (the peer's are implied by its splitters)
-          mbar_wait(lo_full + l, (it / C::LO_STAGES) & 1);          // lo tiles of both CTAs written and fenced
+          if (!P.single_pass) mbar_wait(lo_full + l, (it / C::LO_STAGES) & 1);   // lo tiles of both CTAs written and fenced
           tc_fence_after();
           const uint32_t st = s32(smem + s * C::RAW), sl = s32(lo_smem + l * C::RAW);
 #pragma unroll
@@ -213,7 +214,9 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
             const uint64_t dBl = smem_desc(sl + A_TILE + kk * b_step, b_lbo, b_sbo, b_lt);
             const uint32_t first = (i > 0 || kk > 0) ? 1u : 0u;
             if (elected) {
-              if (CTAS == 2) {
+              if (P.single_pass) {
+                if (CTAS == 2) umma_tf32_2cta(tmem_d, dAh, dBh, idesc, first); else umma_tf32(tmem_d, dAh, dBh, idesc, first);
+              } else if (CTAS == 2) {
                 umma_tf32_2cta(tmem_d, dAl, dBh, idesc, first);
                 umma_tf32_2cta(tmem_d, dAh, dBl, idesc, 1u);
                 umma_tf32_2cta(tmem_d, dAh, dBh, idesc, 1u);
@@ -225,8 +228,8 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
             }
           }
           if (elected) {
-            if (CTAS == 2) { umma_commit_2cta(raw_empty + s); umma_commit_2cta(lo_empty + l); }      // frees both slots (in both CTAs)
-            else { umma_commit(raw_empty + s); umma_commit(lo_empty + l); }
+            if (CTAS == 2) { umma_commit_2cta(raw_empty + s); if (!P.single_pass) umma_commit_2cta(lo_empty + l); }   // frees both slots (in both CTAs)
+            else { umma_commit(raw_empty + s); if (!P.single_pass) umma_commit(lo_empty + l); }
           }
           __syncwarp();
         }
@@ -241,7 +244,7 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
     constexpr int PER = C::RAW / 16 / NT;                     // float4 per thread per stage (8 or 6)
     static_assert(PER * NT * 16 == C::RAW, "stage does not divide over the splitter threads");
     uint32_t it = 0;
-    for (int t = unit; t < P.total_tiles; t += num_units) {
+    for (int t = unit; !P.single_pass && t < P.total_tiles; t += num_units) {
       const Tile tl = decode<CTAS>(P, t, (int)rank);
       for (int i = 0; i < tl.nkb; ++i, ++it) {
         const int s = it % C::RAW_STAGES, l = it % C::LO_STAGES;
@@ -387,6 +390,7 @@ static bool make_map(CUtensorMap* tm, const float* base, int64_t ld, uint64_t in
 // 128 x 128 one-CTA tiles reach 560-680 TF/s of tensor work, the 256 x 128 CTA-pair tiles 350-410 -- with N = 128 the pair
 // saves no operand traffic worth its cross-CTA barrier round trips; it stays in the tree as an opt-in, parity-tested variant.
 static int g_ctas = 0;
+static int g_single_pass = 0;
 
 }  // namespace smem_split
 }  // namespace tc5
@@ -433,7 +437,7 @@ extern "C" int phc_gemm_group(const PhcGemmDesc* d, int32_t count, void* stream)
     ++n;
   }
   if (n == 0) return PHC_OK;
-  P.count = n; P.total_tiles = tiles;
+  P.count = n; P.total_tiles = tiles; P.single_pass = g_single_pass;
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
   const int units = num_sms / ctas;
@@ -479,6 +483,12 @@ extern "C" int phc_gemm_tc5s(const float* A, int64_t lda, int32_t a_kmajor, cons
   d.M = M; d.N = N; d.K = K; d.alpha = alpha; d.bias = bias; d.act = act; d.aux = aux; d.ldaux = ldaux;
   d.accumulate = accumulate; d.k_splits = k_splits;
   return phc_gemm_group(&d, 1, stream);
+}
+
+extern "C" int phc_gemm_set_precision(int32_t mode) {      // PHC_GEMM_FP32_3XTF32 (default) | PHC_GEMM_TF32_SINGLE_PASS
+  if (mode != PHC_GEMM_FP32_3XTF32 && mode != PHC_GEMM_TF32_SINGLE_PASS) { phc_set_error("phc_gemm_set_precision: unknown mode"); return PHC_ERR_INVALID_ARG; }
+  phc::tc5::smem_split::g_single_pass = mode == PHC_GEMM_TF32_SINGLE_PASS;
+  return PHC_OK;
 }
 
 extern "C" int phc_gemm_tc5s_set_ctas(int32_t ctas) {      // A/B switch for tests and tools (1 or 2; 0 = back to the environment default)

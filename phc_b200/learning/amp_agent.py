@@ -252,7 +252,8 @@ class AMPAgent:
                                 training_prim=int(netcfg.get("training_prim", task_detail(task, "training_prim", 0))))
         if self.multi_gpu:
             D.broadcast_params(self.model.params, 0)
-        self.engine = MLPEngine(self.model)
+        # mlp_precision: "fp32" (3xTF32, the reference's mixed_precision: False) or "tf32" (single tensor-core pass, opt-in)
+        self.engine = MLPEngine(self.model, precision=str(cfg.get("mlp_precision", "fp32")))
         n = self.model.num_floats
         self.exp_avg = torch.zeros(n, device=self.device)
         self.exp_avg_sq = torch.zeros(n, device=self.device)

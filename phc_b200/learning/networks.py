@@ -198,7 +198,13 @@ def group_splits(K: int) -> int:
 class MLPEngine:
     """Forward / backward of the MLP stacks through phc_gemm, with per-batch-size activation workspaces."""
 
-    def __init__(self, net: AMPNetwork, backend: Optional[str] = None):
+    _mode_set = None       # the library's precision switch is process wide: remember what was set last
+
+    def __init__(self, net: AMPNetwork, backend: Optional[str] = None, precision: str = "fp32"):
+        """precision: "fp32" = 3xTF32, fp32-equivalent (default, the parity path); "tf32" = one tensor-core pass per product
+        (PHC_GEMM_TF32_SINGLE_PASS, ~1e-3 relative, tc5s back end only): the reduced-precision mode of BASELINE.json configs[3]."""
+        assert precision in ("fp32", "tf32")
+        self.precision = precision
         self.net = net
         self.lib = _lib.load()
         self.dev = net.device
@@ -208,6 +214,8 @@ class MLPEngine:
         # (gemm.cu).  The latter two stay as cross-check implementations (PHC_GEMM=tc5 | mma)
         self.backend = backend or os.environ.get("PHC_GEMM", "tc5s")
         assert self.backend in ("mma", "tc5", "tc5s")
+        if precision == "tf32" and self.backend != "tc5s":
+            raise ValueError("precision='tf32' (single tensor-core pass) exists on the tc5s back end only")
         self._companions: Dict[Tuple[int, Tuple[int, ...], Tuple[int, ...]], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.gemm_flops = 0.0          # algorithmic fp32 FLOPs (2 M N K) of every grouped launch so far (bench.py reads it)
         if self.backend == "tc5":
@@ -264,6 +272,8 @@ class MLPEngine:
             if rc:
                 _lib.check(rc, "phc_gemm_tc5")
             return (Ch, Cl) if Ch is not None else None
+        if self.backend == "tc5s":
+            self._set_mode()
         fn = self.lib.phc_gemm_tc5s if self.backend == "tc5s" else self.lib.phc_gemm
         rc = fn(A.data_ptr(), lda, 1 if a_k else 0, B.data_ptr(), ldb, 1 if b_k else 0, C.data_ptr(),
                                C.stride(0), M, N, K, alpha, _ptr(bias), act, _ptr(mask),
@@ -311,7 +321,14 @@ class MLPEngine:
             dxd = self.gdesc(dY, True, net.weight(l), False, dx, B, l.in_dim, l.out_dim)
         return dw, dxd
 
+    def _set_mode(self) -> None:
+        mode = _lib.PHC_GEMM_TF32_SINGLE_PASS if self.precision == "tf32" else _lib.PHC_GEMM_FP32_3XTF32
+        if MLPEngine._mode_set != mode:
+            _lib.check(self.lib.phc_gemm_set_precision(mode), "phc_gemm_set_precision")
+            MLPEngine._mode_set = mode
+
     def run_group(self, descs) -> None:
+        self._set_mode()
         descs = [d for d in descs if d is not None]
         for i in range(0, len(descs), _lib.PHC_GEMM_GROUP_MAX):
             part = descs[i:i + _lib.PHC_GEMM_GROUP_MAX]

@@ -159,3 +159,32 @@ def test_relu_sign_bits_forward_and_masked_backward():
     tc5s(padded(dY), True, padded(Wt), False, D1, M, N, K, aux=H)                                  # fp32 mask (aux > 0)
     tc5s(padded(dY), True, padded(Wt), False, D2, M, N, K, act=_lib.PHC_ACT_MASK_BITS, aux=bits)   # bit mask
     assert torch.equal(D1, D2)
+
+
+def test_single_pass_tf32_mode_has_its_own_tolerance_and_switches_back():
+    """PHC_GEMM_TF32_SINGLE_PASS (opt-in, BASELINE configs[3]): one tcgen05 product per fp32 product -- operands truncated to tf32,
+    fp32 accumulation: |err| <= 2.5e-3 |A||B|^T (two truncations of 2^-10 each), all three layer forms; switching back restores the
+    fp32-equivalent results bit for bit."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(13)
+    M, N, K = 700, 300, 934
+    A, B, bias = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / math.sqrt(K), torch.randn(N, generator=g)
+    C3, C1, C3b = (torch.zeros(M, round4(N), device=DEV) for _ in range(3))
+    tc5s(padded(A), True, padded(B), True, C3, M, N, K, bias=bias.to(DEV))
+    _lib.check(lib.phc_gemm_set_precision(_lib.PHC_GEMM_TF32_SINGLE_PASS))
+    try:
+        tc5s(padded(A), True, padded(B), True, C1, M, N, K, bias=bias.to(DEV))
+        r_fwd = gemm_close(C1[:, :N], A, B, "tf32 single pass fwd", extra=lambda e, b: (e + bias.double(), b + bias.double().abs()), tol=2.5e-3)
+        dY, W = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g) / math.sqrt(K)
+        D = torch.zeros(M, round4(N), device=DEV)
+        tc5s(padded(dY), True, padded(W), False, D, M, N, K)
+        gemm_close(D[:, :N], dY, W.T.contiguous(), "tf32 single pass dX", tol=2.5e-3)
+        dYt, X = torch.randn(2048, 69, generator=g), torch.randn(2048, 512, generator=g)
+        G = torch.zeros(69, 512, device=DEV)
+        tc5s(padded(dYt), False, padded(X), False, G, 69, 512, 2048, accumulate=True, k_splits=4)
+        gemm_close(G, dYt.T.contiguous(), X.T.contiguous(), "tf32 single pass dW", tol=2.5e-3)
+        assert r_fwd > 2e-5, "the single-pass mode must really skip the correction products"
+    finally:
+        _lib.check(lib.phc_gemm_set_precision(_lib.PHC_GEMM_FP32_3XTF32))
+    tc5s(padded(A), True, padded(B), True, C3b, M, N, K, bias=bias.to(DEV))
+    assert torch.equal(C3, C3b)
