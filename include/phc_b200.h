@@ -168,6 +168,7 @@ PHC_API int phc_motion_state(const PhcMotionLib* lib, const int64_t* motion_ids,
 #define PHC_FLAG_TERM_USE_MEAN (1u << 6)   /* flags.im_eval and not strict_eval: mean-distance criterion */
 #define PHC_FLAG_OBS_ONLY (1u << 7)        /* _compute_observations(env_ids) of the reset path: write obs (+ref_*) only */
 #define PHC_FLAG_REWARD_FROM_CACHE (1u << 8) /* reward / reset read the reference pose from ref_cache (see PhcStepArgs) */
+#define PHC_FLAG_SUBSET_REWARD (1u << 12)   /* env.full_body_reward: False -- tracking reward over the tracked bodies only */
 #define PHC_FLAG_NO_SPECIALISE (1u << 11)  /* never take the compile-time specialised kernel (A/B runs, bit-identity tests) */
 /* env_im_getup_mcp.yaml -- the configuration HumanoidImMCP trains in (time_steps 1, SMPL joints): */
 #define PHC_FLAG_ZERO_OUT_FAR (1u << 9)   /* env.zero_out_far (zero_out_far_train False): point-goal reward mix (humanoid_im.py:890-905),
@@ -261,6 +262,20 @@ typedef struct PhcStepArgs {
    * When non-NULL, amp_out is the ring base and this step's vector goes to slot *ring_head of every env.  Lets a whole rollout
    * (whose slot changes every step) be captured once as a CUDA graph; phc_ring_advance moves the head between steps. */
   const int32_t* ring_head;
+  /* ---- tracked-body subsets, occlusion training, shape columns (appended; all zero / NULL = the plain full-body configuration) ----
+   * env.trackBodies (humanoid_im.py:64-66, :762-770; env_vr.yaml:38-39: Head + both hands): the task observation is built over the
+   * K = num_track tracked bodies only (24 K T columns, body j sits at position track_slot[j]); with PHC_FLAG_SUBSET_REWARD
+   * (env.full_body_reward: False, :926-935) the tracking reward averages over the same subset.  occlusion [N, K] (uint8; K = J when
+   * num_track == 0) is random_occlu_idx of _occl_training (:797-804): an occluded tracked body shows the SIMULATED pose as its
+   * reference in the task observation.  shape_params [N, num_shape] / limb_weights [N, num_limb] are the has_shape_obs /
+   * has_limb_weight_obs columns appended to the self observation (humanoid.py:2043-2047; robot/smpl_humanoid_shape.yaml). */
+  int32_t num_track;
+  int8_t track_slot[PHC_MAX_BODIES];
+  const uint8_t* occlusion;
+  const float* shape_params;
+  int32_t num_shape;
+  const float* limb_weights;
+  int32_t num_limb;
 } PhcStepArgs;
 
 /* Sizes implied by a configuration (so callers can allocate): */

@@ -161,8 +161,10 @@ def strip_base_rot(q: Tensor) -> Tensor:
 # K1  self observation   (reference: phc/env/tasks/humanoid.py:1994-2050)
 # ----------------------------------------------------------------------------------------------
 def self_obs(body_pos: Tensor, body_rot: Tensor, body_vel: Tensor, body_ang_vel: Tensor,
-             local_root_obs: bool = True, root_height_obs: bool = True, upright: bool = True) -> Tensor:
-    """compute_humanoid_observations_smpl_max without shape / limb-weight columns.  [N,J,*] -> [N, 1+15J-3]."""
+             local_root_obs: bool = True, root_height_obs: bool = True, upright: bool = True,
+             shape_params: Optional[Tensor] = None, limb_weights: Optional[Tensor] = None) -> Tensor:
+    """compute_humanoid_observations_smpl_max (humanoid.py:1994-2050).  [N,J,*] -> [N, 1+15J-3 (+ shape columns + limb-weight columns)];
+    shape_params / limb_weights are the has_smpl_params / has_limb_weight_params tails (:2043-2047)."""
     N, J, _ = body_pos.shape
     root_pos = body_pos[:, 0]
     root_rot = body_rot[:, 0]
@@ -180,6 +182,10 @@ def self_obs(body_pos: Tensor, body_rot: Tensor, body_vel: Tensor, body_ang_vel:
     if root_height_obs:
         cols.append(root_pos[:, 2:3])
     cols += [lp, lr, lv, lw]
+    if shape_params is not None:
+        cols.append(shape_params)
+    if limb_weights is not None:
+        cols.append(limb_weights)
     return torch.cat(cols, dim=-1)
 
 
@@ -331,7 +337,10 @@ class StepConfig:
     def __init__(self, dt=1.0 / 30.0, upright=True, local_root_obs=True, root_height_obs=True,
                  rwd=DEFAULT_RWD, power_reward=True, power_coef=0.0005, early_term=True, no_collision=False,
                  use_mean=False, key_bodies=(7, 3, 22, 17), reset_bodies=None, term_dist=0.25,
-                 dof_subset=None, time_steps=1, traj_dt=0.0, num_amp_steps=10):
+                 dof_subset=None, time_steps=1, traj_dt=0.0, num_amp_steps=10, track_bodies=None, full_body_reward=True):
+        # env.trackBodies / env.full_body_reward (humanoid_im.py:64-66, :926-935): body ids of the tracked subset (None = all)
+        self.track_bodies = None if track_bodies is None else list(track_bodies)
+        self.full_body_reward = full_body_reward
         self.dt, self.upright, self.local_root_obs, self.root_height_obs = dt, upright, local_root_obs, root_height_obs
         self.rwd, self.power_reward, self.power_coef = dict(rwd), power_reward, power_coef
         self.early_term, self.no_collision, self.use_mean = early_term, no_collision, use_mean
@@ -341,9 +350,11 @@ class StepConfig:
 
 def env_step(tab: MotionTables, cfg: StepConfig, body_state: Tensor, dof_state: Tensor, dof_force: Tensor,
              progress: Tensor, motion_ids: Tensor, start_times: Tensor, start_offsets: Tensor,
-             global_offset: Tensor, amp_hist: Tensor) -> Dict[str, Tensor]:
+             global_offset: Tensor, amp_hist: Tensor, occlusion: Optional[Tensor] = None, shape_params: Optional[Tensor] = None,
+             limb_weights: Optional[Tensor] = None) -> Dict[str, Tensor]:
     """One post-physics env step on [N,J,13] rigid-body state (progress already incremented).
-    amp_hist: [N,S,A] newest-first window BEFORE this step; returned 'amp_obs_buf' is the window after."""
+    amp_hist: [N,S,A] newest-first window BEFORE this step; returned 'amp_obs_buf' is the window after.
+    occlusion [N, K] bool: random_occlu_idx of _occl_training (humanoid_im.py:797-804); shape_params / limb_weights: self-obs tails."""
     N, J, _ = body_state.shape
     bp, br, bv, bw = body_state[..., 0:3], body_state[..., 3:7], body_state[..., 7:10], body_state[..., 10:13]
     dof_pos, dof_vel = dof_state[..., 0], dof_state[..., 1]
@@ -352,7 +363,10 @@ def env_step(tab: MotionTables, cfg: StepConfig, body_state: Tensor, dof_state: 
     # reward + reset at the CURRENT motion time (humanoid_im.py:879, :1118)
     t_now = progress * cfg.dt + start_times + start_offsets
     ref = motion_state(tab, motion_ids, t_now, global_offset)
-    rew, raw = imitation_reward(bp, br, bv, bw, ref["rg_pos"], ref["rb_rot"], ref["body_vel"], ref["body_ang_vel"], cfg.rwd)
+    tb = list(range(J)) if cfg.track_bodies is None else cfg.track_bodies
+    rs = list(range(J)) if cfg.full_body_reward else tb            # humanoid_im.py:912-935
+    rew, raw = imitation_reward(bp[:, rs], br[:, rs], bv[:, rs], bw[:, rs], ref["rg_pos"][:, rs], ref["rb_rot"][:, rs], ref["body_vel"][:, rs],
+                                ref["body_ang_vel"][:, rs], cfg.rwd)
     if cfg.power_reward:
         pw = power_reward(dof_force, dof_vel, progress, cfg.power_coef)
         rew = rew + pw
@@ -364,7 +378,11 @@ def env_step(tab: MotionTables, cfg: StepConfig, body_state: Tensor, dof_state: 
     rb = list(range(J)) if cfg.reset_bodies is None else list(cfg.reset_bodies)
     td = torch.full((J,), cfg.term_dist) if not torch.is_tensor(cfg.term_dist) else cfg.term_dist
     pass_time = t_now >= tab.lengths[motion_ids]
-    out["reset"], out["terminate"] = im_reset(progress, bp[:, rb], ref["rg_pos"][:, rb], pass_time, td[rb],
+    ref_reset = ref["rg_pos"][:, rb].clone()
+    if occlusion is not None:        # humanoid_im.py:1180-1181: an occluded body cannot fail the distance test (indexed by BODY id there)
+        oc_rb = occlusion.bool()[:, rb]
+        ref_reset[oc_rb] = bp[:, rb][oc_rb]
+    out["reset"], out["terminate"] = im_reset(progress, bp[:, rb], ref_reset, pass_time, td[rb],
                                               cfg.early_term, cfg.no_collision, cfg.use_mean)
 
     # observation for the NEXT step (humanoid_im.py:744-754)
@@ -372,9 +390,15 @@ def env_step(tab: MotionTables, cfg: StepConfig, body_state: Tensor, dof_state: 
     t_next = ((progress[:, None] + 1) * cfg.dt + torch.arange(T)[None, :] * cfg.traj_dt
               + start_times[:, None] + start_offsets[:, None]).flatten()
     refn = motion_state(tab, motion_ids.repeat_interleave(T), t_next, global_offset.repeat_interleave(T, dim=0))
-    so = self_obs(bp, br, bv, bw, cfg.local_root_obs, cfg.root_height_obs, cfg.upright)
-    to = task_obs_v6(bp[:, 0], br[:, 0], bp, br, bv, bw, refn["rg_pos"], refn["rb_rot"], refn["body_vel"],
-                     refn["body_ang_vel"], T, cfg.upright)
+    so = self_obs(bp, br, bv, bw, cfg.local_root_obs, cfg.root_height_obs, cfg.upright, shape_params, limb_weights)
+    # tracked subset of the simulated and the reference bodies (humanoid_im.py:762-770), then the occlusion overwrite (:797-804)
+    sub = lambda x: x[:, tb]
+    r_pos, r_rot, r_vel, r_ang = (sub(refn[k]).clone() for k in ("rg_pos", "rb_rot", "body_vel", "body_ang_vel"))
+    if occlusion is not None:
+        assert T == 1
+        oc = occlusion.bool()
+        r_pos[oc], r_rot[oc], r_vel[oc], r_ang[oc] = sub(bp)[oc], sub(br)[oc], sub(bv)[oc], sub(bw)[oc]
+    to = task_obs_v6(bp[:, 0], br[:, 0], sub(bp), sub(br), sub(bv), sub(bw), r_pos, r_rot, r_vel, r_ang, T, cfg.upright)
     out["obs"] = torch.cat((so, to), dim=-1)
     out["ref_body_pos"] = refn["rg_pos"].view(N, T, J, 3)[:, 0]
     out["ref_body_rot"] = refn["rb_rot"].view(N, T, J, 4)[:, 0]

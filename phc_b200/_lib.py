@@ -24,6 +24,7 @@ PHC_FLAG_REWARD_FROM_CACHE = 1 << 8
 PHC_FLAG_ZERO_OUT_FAR = 1 << 9
 PHC_FLAG_CYCLE_MOTION = 1 << 10
 PHC_FLAG_NO_SPECIALISE = 1 << 11
+PHC_FLAG_SUBSET_REWARD = 1 << 12
 PHC_ACT_NONE, PHC_ACT_RELU, PHC_ACT_SILU, PHC_ACT_SILU_BWD, PHC_ACT_RELU_BITS, PHC_ACT_MASK_BITS = 0, 1, 2, 3, 4, 5
 PHC_MAX_KEY_BODIES = 8
 PHC_MAX_BODIES = 64
@@ -69,6 +70,8 @@ class PhcStepArgs(C.Structure):
         ("ref_cache", _p),
         ("close_distance", C.c_float), ("far_distance", C.c_float), ("max_episode_length", C.c_int32), ("point_goal", _p),
         ("cycle_phase", _p), ("mpjpe", _p), ("body_pos_gt", _p), ("ring_head", _p),
+        ("num_track", C.c_int32), ("track_slot", C.c_int8 * PHC_MAX_BODIES), ("occlusion", _p), ("shape_params", _p), ("num_shape", C.c_int32),
+        ("limb_weights", _p), ("num_limb", C.c_int32),
     ]
 
 

@@ -324,6 +324,12 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   const bool has_ext = E > 0 && lane >= J && lane < J + E;   // robots: lanes J..J+E-1 carry the "extend" bodies (reward only)
   const int j = has_body ? lane : 0;
   const int jr = (has_body || has_ext) ? lane : 0;           // record of the reference pose this lane tracks
+  // env.trackBodies: body j is the slot-th of K tracked bodies (task observation, optionally the reward); K = J, slot = j without a subset
+  const bool subset = !FAST && a.num_track > 0;
+  const int K = subset ? a.num_track : J;
+  const int slot = subset ? (has_body ? (int)a.track_slot[j] : -1) : j;
+  const bool tracked = has_body && slot >= 0;
+  const bool sub_rew = !FAST && (flags & PHC_FLAG_SUBSET_REWARD);
   BodyRec sim = load_body(s_state + (has_ext ? a.ext_parent[lane - J] : j) * kBodyRec);   // stride-13 words: bank-conflict free
   if (has_ext) {   // parent_rot * pos_in_parent + parent_pos, rotation = the parent's (humanoid_im.py:917-919)
     const V3 off = v3(a.ext_pos[lane - J][0], a.ext_pos[lane - J][1], a.ext_pos[lane - J][2]);
@@ -359,6 +365,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
           e_ang = (dw.x * dw.x + dw.y * dw.y + dw.z * dw.z) / 3.0f;
           dist = sqrtf(sp);
         }
+        if (sub_rew && !tracked) { e_pos = 0.f; e_rot = 0.f; e_vel = 0.f; e_ang = 0.f; }   // reward over the tracked subset (the reset test keeps `dist`)
       }
     }
     if (!FAST && a.mpjpe) {        // flags.im_eval extras (humanoid_im.py:674-680): mean per-joint position error + the pose it is against
@@ -366,6 +373,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
       if (lane == 0) a.mpjpe[env] = mp;
     }
     float dist_t = dist;           // the distance the termination test sees
+    if (!FAST && a.occlusion && has_body && a.occlusion[(size_t)env * K + slot]) dist_t = 0.0f;   // an occluded body cannot fail it (humanoid_im.py:1180-1181)
     if (GETUP && rebased) {
       // the clip wrapped this step: the reference's reset test re-queries the pose at the re-based time (humanoid_im.py:1142,
       // :1148).  Rare (once per clip length): positions straight from the frame table, no staging.
@@ -393,7 +401,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     // exp(-k * mean) (one expf sequence for the warp instead of four on lane 0) and hand it to lane 0
     const float e4 = warp_sum4(e_pos, e_rot, e_vel, e_ang, lane);
     const int sel = lane >> 3;
-    const float den = sel < 2 ? (float)(J + E) : (float)J;
+    const float den = sub_rew ? (float)K : (sel < 2 ? (float)(J + E) : (float)J);
     const float kc = sel == 0 ? a.k_pos : (sel == 1 ? a.k_rot : (sel == 2 ? a.k_vel : a.k_ang_vel));
     const float r_mine = expf(-kc * (e4 / den));
     const float r_pos = __shfl_sync(0xffffffffu, r_mine, 0), r_rot = __shfl_sync(0xffffffffu, r_mine, 8);
@@ -495,6 +503,12 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
       st6(o, tn); st3(o + 6, lv); st3(o + 9, lw);
     }
   }
+  if (!FAST && (a.shape_params || a.limb_weights)) {          // has_shape_obs / has_limb_weight_obs columns (humanoid.py:2043-2047)
+    float* o_ext = s_obs + base0 + 15 * J - 3;
+    const int ns = a.shape_params ? a.num_shape : 0, nl = a.limb_weights ? a.num_limb : 0;
+    for (int c = lane; c < ns; c += 32) o_ext[c] = a.shape_params[(size_t)env * ns + c];
+    for (int c = lane; c < nl; c += 32) o_ext[ns + c] = a.limb_weights[(size_t)env * nl + c];
+  }
   // task observation v6 for each of the T reference samples (the self observation above did not need the frames)
   mbar_wait(bar_o, 0);
   float* const g_cache = (FAST || a.ref_cache) ? a.ref_cache + (size_t)env * BS : nullptr;
@@ -518,6 +532,14 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
         st3(c, ref.p); c[3] = ref.q.x; c[4] = ref.q.y; c[5] = ref.q.z; c[6] = ref.q.w; st3(c + 7, ref.v); st3(c + 10, ref.w);
       }
       if (!has_body) continue;         // extend bodies: reward only, no observation columns
+      if (t == 0) {     // side buffers of _compute_task_obs(save_buffer=True): every body, tracked or not
+        const size_t bj = (size_t)env * J + j;
+        if (!FAST && a.ref_body_pos) st3(a.ref_body_pos + 3 * bj, ref.p);
+        if (!FAST && a.ref_body_vel) st3(a.ref_body_vel + 3 * bj, ref.v);
+        if (!FAST && a.ref_body_ang_vel) st3(a.ref_body_ang_vel + 3 * bj, ref.w);
+        if (!FAST && a.ref_body_rot) { float* d = a.ref_body_rot + 4 * bj; d[0] = ref.q.x; d[1] = ref.q.y; d[2] = ref.q.z; d[3] = ref.q.w; }
+      }
+      if (!tracked) continue;          // env.trackBodies: only the tracked bodies have task-observation columns
       BodyRec ro = ref;                // what the observation sees as reference (the cache / ref_* buffers keep `ref`)
       if (zof && t == 0) {             // humanoid_im.py:783-796
         const V3 dr = root_p - rroot;
@@ -531,20 +553,16 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
                     (ref.p.z - sim.p.z) / dist * a.far_distance + sim.p.z);
         if (lane == 0) a.point_goal[env] = dist;
       }
-      float* tb = s_obs + self_dim + t * 24 * J;
-      st3(tb + 3 * j, qrot_z(hinv, ro.p - sim.p));
-      st6(tb + 3 * J + 6 * j, tan_norm(qmul_zr(qmul_zl(hinv, qmul(ro.q, qconj(sim.q))), hq)));
-      st3(tb + 9 * J + 3 * j, qrot_z(hinv, ro.v - sim.v));
-      st3(tb + 12 * J + 3 * j, qrot_z(hinv, ro.w - sim.w));
-      st3(tb + 15 * J + 3 * j, qrot_z(hinv, ro.p - root_p));
-      st6(tb + 18 * J + 6 * j, tan_norm(qmul_zl(hinv, ro.q)));
-      if (t == 0) {     // side buffers of _compute_task_obs(save_buffer=True)
-        const size_t bj = (size_t)env * J + j;
-        if (!FAST && a.ref_body_pos) st3(a.ref_body_pos + 3 * bj, ref.p);
-        if (!FAST && a.ref_body_vel) st3(a.ref_body_vel + 3 * bj, ref.v);
-        if (!FAST && a.ref_body_ang_vel) st3(a.ref_body_ang_vel + 3 * bj, ref.w);
-        if (!FAST && a.ref_body_rot) { float* d = a.ref_body_rot + 4 * bj; d[0] = ref.q.x; d[1] = ref.q.y; d[2] = ref.q.z; d[3] = ref.q.w; }
+      if (!FAST && a.occlusion && t == 0 && a.occlusion[(size_t)env * K + slot]) {   // _occl_training (humanoid_im.py:797-804)
+        ro.p = sim.p; ro.q = sim.q; ro.v = sim.v; ro.w = sim.w;
       }
+      float* tb = s_obs + self_dim + t * 24 * K;
+      st3(tb + 3 * slot, qrot_z(hinv, ro.p - sim.p));
+      st6(tb + 3 * K + 6 * slot, tan_norm(qmul_zr(qmul_zl(hinv, qmul(ro.q, qconj(sim.q))), hq)));
+      st3(tb + 9 * K + 3 * slot, qrot_z(hinv, ro.v - sim.v));
+      st3(tb + 12 * K + 3 * slot, qrot_z(hinv, ro.w - sim.w));
+      st3(tb + 15 * K + 3 * slot, qrot_z(hinv, ro.p - root_p));
+      st6(tb + 18 * K + 6 * slot, tan_norm(qmul_zl(hinv, ro.q)));
     }
   }
   // ---- rows leave shared memory ---------------------------------------------------------------------------------
@@ -649,8 +667,18 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
   }
   if (a->env_motion && (reinterpret_cast<uintptr_t>(a->env_motion) & 15)) { phc_set_error("phc_env_step: env_motion must be 16-byte aligned"); return PHC_ERR_INVALID_ARG; }
   if (reinterpret_cast<uintptr_t>(a->dof_state) & 7) { phc_set_error("phc_env_step: dof_state must be 8-byte aligned"); return PHC_ERR_INVALID_ARG; }
-  const int self_dim = phc_self_obs_dim(J, a->flags);
-  const int obs_dim = self_dim + phc_task_obs_dim(J, T);
+  const int n_shape = a->shape_params ? a->num_shape : 0, n_limb = a->limb_weights ? a->num_limb : 0;
+  if (a->num_track < 0 || a->num_track > J || n_shape < 0 || n_limb < 0) { phc_set_error("phc_env_step: bad num_track / num_shape / num_limb"); return PHC_ERR_INVALID_ARG; }
+  if (a->num_track > 0) {
+    int seen = 0;
+    for (int b = 0; b < J; ++b) if (a->track_slot[b] >= 0) { if (a->track_slot[b] >= a->num_track) { phc_set_error("phc_env_step: track_slot out of range"); return PHC_ERR_INVALID_ARG; } ++seen; }
+    if (seen != a->num_track) { phc_set_error("phc_env_step: track_slot must name exactly num_track bodies"); return PHC_ERR_INVALID_ARG; }
+  }
+  if (a->occlusion && a->num_track > 0) { phc_set_error("phc_env_step: occlusion training needs every body tracked (the reference indexes random_occlu_idx by body id, humanoid_im.py:1181)"); return PHC_ERR_UNSUPPORTED; }
+  const bool widened = a->num_track > 0 || a->occlusion || n_shape > 0 || n_limb > 0 || (a->flags & PHC_FLAG_SUBSET_REWARD);
+  if (widened && (wide || E > 0)) { phc_set_error("phc_env_step: tracked-body subsets / occlusion / shape columns are built for <= 32-body humanoids without extend bodies"); return PHC_ERR_UNSUPPORTED; }
+  const int self_dim = phc_self_obs_dim(J, a->flags) + n_shape + n_limb;
+  const int obs_dim = self_dim + phc_task_obs_dim(a->num_track > 0 ? a->num_track : J, T);
   const int amp_dim = !a->amp_out ? 0 : (DR > 0 ? phc_amp_obs_dim_robot(DR, a->num_key_bodies, a->flags)
                                                  : phc_amp_obs_dim(a->num_amp_joints, a->num_key_bodies, a->flags));
   if (a->obs_stride < obs_dim) { phc_set_error("phc_env_step: obs_stride smaller than the observation"); return PHC_ERR_INVALID_ARG; }
@@ -685,7 +713,7 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
   // the steady-state launch of the shipped SMPL configuration takes the compile-time specialisation (see kFastFlags)
   const int obs_pad_h = round4(obs_dim);
   static const bool fast_allowed = [] { const char* v = getenv("PHC_ENV_FAST"); return !(v && v[0] == '0'); }();   // A/B switch
-  const bool fast = fast_allowed && !getup && T == 1 && J == 24 && E == 0 && DR == 0 && a->flags == kFastFlags && !a->only_where && a->env_motion &&
+  const bool fast = fast_allowed && !widened && !getup && T == 1 && J == 24 && E == 0 && DR == 0 && a->flags == kFastFlags && !a->only_where && a->env_motion &&
                     a->dof_force && state_bulk_ok && alias_obs && a->ref_cache && (reinterpret_cast<uintptr_t>(a->ref_cache) & 15) == 0 &&
                     !a->ref_body_pos && !a->ref_body_rot && !a->ref_body_vel && !a->ref_body_ang_vel &&
                     a->amp_out && !a->amp_hist_in && (amp_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(a->amp_out) & 15) == 0 &&

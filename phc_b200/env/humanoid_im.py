@@ -174,6 +174,36 @@ class HumanoidIm:
         key_bodies = env.get("key_body_ids", syn.H1_KEY_BODIES if robot else (syn.SMPL_KEY_BODIES if J == 24 else [J - 1]))
         reset_bodies = env.get("reset_body_ids", syn.SMPL_RESET_BODIES if (J == 24 and not robot) else None)
         dof_subset = env.get("dof_subset", syn.SMPL_DOF_SUBSET if (J == 24 and not robot and rcfg("has_dof_subset", True)) else None)
+        # env.trackBodies / env.reset_bodies (names or ids; humanoid_im.py:64-66): the tracked subset of env_vr.yaml; reset bodies default
+        # to the tracked ones.  env.full_body_reward False = the reward follows the subset (:926-935)
+        names = list(rcfg("body_names", None) or getattr(sim, "body_names", None) or (syn.SMPL_BODY_NAMES if (J == 24 and not robot) else []))
+        to_ids = lambda lst: [names.index(b) if isinstance(b, str) else int(b) for b in lst]
+        track = env.get("trackBodies", None)
+        self._track_bodies_id = None if track is None or len(track) in (0, J) else to_ids(track)
+        if "reset_bodies" in env:
+            reset_bodies = to_ids(env["reset_bodies"])
+        elif self._track_bodies_id is not None and "reset_body_ids" not in env:
+            reset_bodies = list(self._track_bodies_id)
+        self._full_body_reward = bool(env.get("full_body_reward", True))
+        # _occl_training (:96-97, :797-804, :1081-1092): which tracked bodies are hidden from the policy this step
+        self._occl_training = bool(env.get("occlusion_training", False))
+        self._occl_training_prob = float(env.get("occlusion_training_prob", 0.1))
+        self.random_occlu_idx = self.random_occlu_count = None
+        if self._occl_training:
+            if self._track_bodies_id is not None:
+                raise NotImplementedError("occlusion_training with a tracked-body subset: the reference indexes random_occlu_idx by body id in the "
+                                          "reset test (humanoid_im.py:1181), which only works with every body tracked")
+            self.random_occlu_idx = torch.zeros(self.num_envs, J, dtype=torch.bool, device=self.device)
+            self.random_occlu_count = torch.zeros(self.num_envs, J, dtype=torch.int64, device=self.device)
+        # has_shape_obs / has_weight_obs (humanoid.py:271-274, :1469-1470): per-env body shape (gender + betas = humanoid_shapes[:, :-6] for the
+        # SMPL family) and limb lengths / weights appended to the self observation; the simulator side owns both
+        self._has_shape_obs, self._has_limb_weight_obs = bool(rcfg("has_shape_obs", False)), bool(rcfg("has_weight_obs", False))
+        shape_params = limb_weights = None
+        if self._has_shape_obs:
+            hs = torch.as_tensor(sim.humanoid_shapes, dtype=torch.float32).to(self.device)
+            shape_params = (hs[:, :-6] if self.humanoid_type in ("smpl", "smplh", "smplx") else hs).contiguous()
+        if self._has_limb_weight_obs:
+            limb_weights = torch.as_tensor(sim.humanoid_limb_and_weights, dtype=torch.float32).to(self.device).contiguous()
         self.step_cfg = ops.EnvStepConfig(
             dt=self.dt, time_steps=self._num_traj_samples, traj_dt=self._traj_sample_timestep,
             upright=bool(rcfg("has_upright_start", True)), local_root_obs=bool(env.get("local_root_obs", True)),
@@ -183,7 +213,7 @@ class HumanoidIm:
             dof_subset=dof_subset, amp_steps=self._num_amp_obs_steps, ext_parents=self.extend_body_parent_ids,
             ext_pos=self.extend_body_pos_in_parent, zero_out_far=self.zero_out_far, close_distance=self.close_distance,
             far_distance=self.far_distance, cycle_motion=self.cycle_motion, max_episode_length=self.max_episode_length,
-            specialise=bool(cfg.get("specialised_step", True)),
+            specialise=bool(cfg.get("specialised_step", True)), track_bodies=self._track_bodies_id, full_body_reward=self._full_body_reward,
             term_use_mean=bool(cfg.get("im_eval", False)) and not bool(env.get("strict_eval", False)))   # humanoid_im.py:1180
         self._key_body_ids, self._reset_bodies_id, self.dof_subset = key_bodies, reset_bodies, dof_subset
 
@@ -222,7 +252,8 @@ class HumanoidIm:
                       dof_state=self._dof_state, dof_force=self.dof_force_tensor, progress=self.progress_buf,
                       motion_ids=self._sampled_motion_ids, start_times=self._motion_start_times,
                       start_offsets=self._motion_start_times_offset, global_offset=self._global_offset,
-                      point_goal=self._point_goal, cycle_phase=self._cycle_phase)
+                      point_goal=self._point_goal, cycle_phase=self._cycle_phase, occlusion=self.random_occlu_idx, shape_params=shape_params,
+                      limb_weights=limb_weights)
         # AMP history: a RING [N, S, A] (one 784-byte slot written per step) instead of the reference's per-step shift of
         # the whole window (humanoid_amp.py:662-670); the newest-first window is exported on demand (`_amp_obs_buf`,
         # `export_amp_obs`).  amp_window_shift=True in cfg restores the in-kernel reference-style shift.
@@ -353,6 +384,8 @@ class HumanoidIm:
             self._plan.advance_ring()
         if self.cycle_motion:
             self._cycle_phase.uniform_()        # what sample_time_interval would draw for the clips that wrap (motion_lib_base.py:415)
+        if self._occl_training:
+            self._update_occl_training()        # pre_physics_step of the reference (humanoid_im.py:1063-1066)
         self._plan.run()
         self.extras["terminate"] = self._terminate_buf
         self.extras["reward_raw"] = self.reward_raw
@@ -361,6 +394,21 @@ class HumanoidIm:
             self.extras["mpjpe"] = self._plan.mpjpe
             self.extras["body_pos"] = self._rigid_body_pos
             self.extras["body_pos_gt"] = self._plan.body_pos_gt
+
+    def _update_occl_training(self) -> None:
+        """HumanoidIm._update_occl_training (humanoid_im.py:1081-1092), statement for statement -- including its last two lines, which
+        overwrite the sampled pattern with "bodies 0..8 hidden, 9..23 visible" in the reference as shipped."""
+        occu = torch.ones(self.num_envs, self.random_occlu_idx.shape[1], device=self.device) * self._occl_training_prob
+        idx = torch.bernoulli(occu).bool()
+        idx[:, 0] = False
+        n = int(idx.shape[0] * idx.shape[1])
+        draw = torch.randint(30, 60, (n,), device=self.device).view_as(idx)            # reference: randint of the selected shape (one host sync)
+        self.random_occlu_count[:] = torch.where(idx, draw, self.random_occlu_count)
+        self.random_occlu_count -= 1
+        self.random_occlu_count.clamp_(min=0)
+        self.random_occlu_idx[:] = self.random_occlu_count > 0
+        self.random_occlu_idx[:] = True
+        self.random_occlu_idx[:, 9:24] = False
 
     # kept for API parity.  Reward, reset and observations of a step are produced TOGETHER by the one fused launch of
     # post_physics_step; these entry points therefore do nothing more (re-launching would advance the AMP ring, decrement

@@ -243,6 +243,10 @@ class EnvStepConfig:
     cycle_motion: bool = False         # env.cycle_motion
     max_episode_length: int = 300      # env.episode_length
     specialise: bool = True            # False: PHC_FLAG_NO_SPECIALISE (always the generic kernel instantiation)
+    # env.trackBodies / env.full_body_reward (humanoid_im.py:64-66, :926-935; env_vr.yaml): body ids whose reference enters the task
+    # observation (None = all) and whether the tracking reward still averages over every body
+    track_bodies: Optional[Sequence[int]] = None
+    full_body_reward: bool = True
 
     def flags(self) -> int:
         f = 0
@@ -250,7 +254,8 @@ class EnvStepConfig:
                         (self.root_height_obs, PHC_FLAG_ROOT_HEIGHT_OBS), (self.power_reward, PHC_FLAG_POWER_REWARD),
                         (self.early_term, PHC_FLAG_EARLY_TERM), (self.no_collision, PHC_FLAG_NO_COLLISION),
                         (self.term_use_mean, PHC_FLAG_TERM_USE_MEAN), (self.zero_out_far, _lib.PHC_FLAG_ZERO_OUT_FAR),
-                        (self.cycle_motion, _lib.PHC_FLAG_CYCLE_MOTION), (not self.specialise, _lib.PHC_FLAG_NO_SPECIALISE)):
+                        (self.cycle_motion, _lib.PHC_FLAG_CYCLE_MOTION), (not self.specialise, _lib.PHC_FLAG_NO_SPECIALISE),
+                        (not self.full_body_reward, _lib.PHC_FLAG_SUBSET_REWARD)):
             if on:
                 f |= bit
         return f
@@ -279,7 +284,8 @@ class EnvStepPlan:
                  only_where: Optional[torch.Tensor] = None, obs_only: bool = False, amp_ring: bool = False,
                  ref_cache: Optional[torch.Tensor] = None, reward_from_cache: bool = False,
                  point_goal: Optional[torch.Tensor] = None, cycle_phase: Optional[torch.Tensor] = None,
-                 with_eval_extras: bool = False, ring_head_dev: Optional[torch.Tensor] = None):
+                 with_eval_extras: bool = False, ring_head_dev: Optional[torch.Tensor] = None, occlusion: Optional[torch.Tensor] = None,
+                 shape_params: Optional[torch.Tensor] = None, limb_weights: Optional[torch.Tensor] = None):
         """ref_cache: [N, body_stride] pose cache (PhcStepArgs.ref_cache): every run() stores the reference pose interpolated
         for the first observation sample; reward_from_cache=True makes run() take the reward-time reference pose from it
         (valid for HumanoidIm's step / reset sequence, see include/phc_b200.h).
@@ -308,8 +314,13 @@ class EnvStepPlan:
         if reward_from_cache:
             assert ref_cache is not None and not obs_only
             flags |= _lib.PHC_FLAG_REWARD_FROM_CACHE
-        self.self_dim = lib.phc_self_obs_dim(J, flags)
-        self.task_dim = lib.phc_task_obs_dim(J, cfg.time_steps)
+        # occlusion [N, K] uint8 / bool (random_occlu_idx), shape_params [N, ns] / limb_weights [N, nl]: the has_shape_obs /
+        # has_limb_weight_obs tails of the self observation (humanoid.py:2043-2047)
+        K = J if cfg.track_bodies is None else len(cfg.track_bodies)
+        ns = 0 if shape_params is None else int(shape_params.shape[1])
+        nl = 0 if limb_weights is None else int(limb_weights.shape[1])
+        self.self_dim = lib.phc_self_obs_dim(J, flags) + ns + nl
+        self.task_dim = lib.phc_task_obs_dim(K, cfg.time_steps)
         self.obs_dim = self.self_dim + self.task_dim
         robot = mlib.num_dofs > 0
         joints = [] if robot else cfg.amp_joint_list(J)
@@ -427,6 +438,29 @@ class EnvStepPlan:
         self.ref_cache = ref_cache
         a.ref_cache = _ptr(ref_cache)
         a.ring_head = _ptr(self.ring_head_dev)
+        if cfg.track_bodies is not None:
+            tb = [int(b) for b in cfg.track_bodies]
+            if len(set(tb)) != len(tb) or any(b < 0 or b >= J for b in tb):
+                raise PhcError("EnvStepConfig.track_bodies: distinct body ids in [0, J)")
+            a.num_track = len(tb)
+            for b in range(_lib.PHC_MAX_BODIES):
+                a.track_slot[b] = -1
+            for pos, b in enumerate(tb):
+                a.track_slot[b] = pos
+        if occlusion is not None:
+            if occlusion.dtype == torch.bool:
+                occlusion = occlusion.view(torch.uint8)
+            k["occlusion"] = _req(occlusion, torch.uint8, "occlusion", dev)
+            assert tuple(occlusion.shape) == (N, K)
+            a.occlusion = k["occlusion"].data_ptr()
+        if shape_params is not None:
+            k["shape_params"] = _req(shape_params, f32, "shape_params", dev)
+            assert shape_params.shape[0] == N
+            a.shape_params, a.num_shape = k["shape_params"].data_ptr(), ns
+        if limb_weights is not None:
+            k["limb_weights"] = _req(limb_weights, f32, "limb_weights", dev)
+            assert limb_weights.shape[0] == N
+            a.limb_weights, a.num_limb = k["limb_weights"].data_ptr(), nl
         self.args = a
         self._args_ref = C.byref(a)
         self.refresh_motion_params()

@@ -69,8 +69,10 @@ class Emu:
         real = _lib.load()
         J, T = a.lib.num_bodies, a.time_steps
         E, DR = a.lib.num_ext_bodies, a.lib.num_dofs
-        self_dim = real.phc_self_obs_dim(J, a.flags)
-        obs_dim = self_dim + real.phc_task_obs_dim(J, T)
+        n_shape = a.num_shape if a.shape_params else 0
+        n_limb = a.num_limb if a.limb_weights else 0
+        self_dim = real.phc_self_obs_dim(J, a.flags) + n_shape + n_limb
+        obs_dim = self_dim + real.phc_task_obs_dim(a.num_track if a.num_track > 0 else J, T)
         amp_dim = 0 if not a.amp_out else (real.phc_amp_obs_dim_robot(DR, a.num_key_bodies, a.flags) if DR > 0
                                            else real.phc_amp_obs_dim(a.num_amp_joints, a.num_key_bodies, a.flags))
         # the launcher's derived arguments (phc_env_step in env_step.cu)

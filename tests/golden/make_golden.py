@@ -276,6 +276,51 @@ def gen_envstep():
     save("envstep.npz", cases)
 
 
+def gen_vr():
+    """env_vr.yaml (trackBodies = reset_bodies = Head + both hands, humanoid_im.py:64-66) with the subset reward (full_body_reward:
+    False, :926-935) and the shape / limb-weight columns of robot/smpl_humanoid_shape.yaml (humanoid.py:2043-2047) [E]; the same subset
+    with the full-body reward [F]; occlusion training on the full body (:797-804 in the observation, :1180-1181 in the reset test --
+    random_occlu_idx is indexed by BODY id there, so the reference only supports it with every body tracked) [G]; all through the
+    real _compute_reward / _compute_reset / _compute_observations."""
+    N = 24
+    m = syn.make_motions(N, seed=6, min_frames=12, max_frames=24)
+    st = syn.make_env_state(m, N, seed=5, max_progress=20, with_offset=True, blend_jitter=True)
+    track = [syn.SMPL_BODY_NAMES.index(n) for n in ("Head", "L_Hand", "R_Hand")]
+    g = torch.Generator().manual_seed(8)
+    cases = {}
+    for tag, subset, subset_reward, occl, shape in (("E", True, True, False, True), ("F", True, False, False, False), ("G", False, False, True, False)):
+        env = build_ref_env(m, st)
+        J = env.num_bodies
+        K = len(track) if subset else J
+        if subset:
+            env._track_bodies_id = torch.tensor(track)
+            env._reset_bodies_id = torch.tensor(track)
+        env._full_body_reward = not subset_reward
+        env.ref_body_pos_subset = torch.zeros(N, K, 3)
+        ns = nl = 0
+        if shape:
+            env._has_shape_obs, env._has_limb_weight_obs = True, True
+            env.humanoid_shapes = torch.randn(N, 17, generator=g)
+            env.humanoid_limb_and_weights = torch.randn(N, 10, generator=g)
+            ns, nl = 11, 10          # the observation takes humanoid_shapes[:, :-6] (humanoid.py:1469): gender + 10 betas
+            cases[f"{tag}_shape"], cases[f"{tag}_limb"] = env.humanoid_shapes, env.humanoid_limb_and_weights
+        if occl:
+            env._occl_training = True
+            env.random_occlu_idx = torch.rand(N, K, generator=g) < 0.4
+            env.random_occlu_idx[:, 0] = False
+            cases[f"{tag}_occlusion"] = env.random_occlu_idx
+        env.self_obs_buf = torch.zeros(N, 1 + J * 15 - 3 + ns + nl)
+        env.obs_buf = torch.zeros(N, 1 + J * 15 - 3 + ns + nl + K * 24)
+        out = run_ref_step(env)
+        for k, v in out.items():
+            cases[f"{tag}_out_{k}"] = v
+    for f in st.__dataclass_fields__:
+        cases[f"in_{f}"] = getattr(st, f)
+    cases["track"] = torch.tensor(track)
+    cases.update(motion_tables_dict(m))
+    save("vr.npz", cases)
+
+
 # ------------------------------------------------------------------------------------------------
 def gen_learn():
     import phc.learning.common_agent as ca
@@ -711,3 +756,4 @@ if __name__ == "__main__":
     gen_g1()
     gen_smplx()
     gen_getup_smplx()
+    gen_vr()

@@ -63,6 +63,27 @@ def test_kernel_source_vs_reference_golden(emu, tag, in_tag, kw):
     check(plan, {k: g[f"{tag}_out_{k}"] for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf", "ref_body_pos", "ref_body_rot", "ref_body_vel")}, tag)
 
 
+@pytest.mark.parametrize("tag", ["E", "F", "G"])
+def test_tracked_subset_occlusion_and_shape_columns(emu, tag):
+    """vr.npz (make_golden.gen_vr, the unmodified reference): env_vr.yaml's Head + hands subset with the subset reward and the shape /
+    limb-weight columns (E), the subset with the full-body reward (F), occlusion training (G) -- through the generic instantiation."""
+    e, hp = emu
+    g = load("vr.npz")
+    track = g["track"].tolist()
+    subset = tag in ("E", "F")
+    cfg = smpl_cfg(track_bodies=track if subset else None, reset_bodies=track if subset else syn.SMPL_RESET_BODIES, full_body_reward=tag != "E")
+    st = syn.EnvState(**{k: g[f"in_{k}"] for k in syn.EnvState.__dataclass_fields__})
+    kw = {}
+    if tag == "E":
+        kw = dict(shape_params=g["E_shape"][:, :-6].contiguous(), limb_weights=g["E_limb"].contiguous())
+    if tag == "G":
+        kw = dict(occlusion=g["G_occlusion"].contiguous())
+    plan = make_plan(hp, motion_data_from(g), st, cfg, **kw)
+    assert plan.obs.shape[1] == g[f"{tag}_out_obs"].shape[1]
+    e.run(plan, "generic")
+    check(plan, {k: g[f"{tag}_out_{k}"] for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf", "ref_body_pos", "ref_body_rot", "ref_body_vel")}, tag)
+
+
 def test_generic_instantiation_matches_too(emu):
     e, hp = emu
     g = load("envstep.npz")

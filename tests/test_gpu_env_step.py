@@ -237,3 +237,61 @@ def test_reset_path_pieces_vs_reference_golden():
     assert bool((off.cpu()[m] == 0).all()) and bool((goff.cpu()[m] == 0).all()) and bool((cc.cpu()[m] == 0).all())
     assert bool((prog.cpu()[m] == 0).all()) and bool((rst.cpu()[m] == 0).all()) and bool((term.cpu()[m] == 0).all())
     assert float(off.cpu()[~m][0]) == 7.0 and int(prog.cpu()[~m][0]) == 9
+
+
+@pytest.mark.parametrize("tag", ["E", "F", "G"])
+def test_tracked_subset_occlusion_and_shape_columns_vs_reference_golden(tag):
+    """vr.npz from the unmodified reference (make_golden.gen_vr): env_vr.yaml's trackBodies = reset_bodies = Head + both hands with the
+    subset reward and the shape / limb-weight columns of smpl_humanoid_shape.yaml (E), the subset with the full-body reward (F),
+    occlusion training on the full body in observation and reset test (G)."""
+    g = load("vr.npz")
+    track = g["track"].tolist()
+    subset = tag in ("E", "F")
+    cfg = smpl_cfg(track_bodies=track if subset else None, reset_bodies=track if subset else syn.SMPL_RESET_BODIES, full_body_reward=tag != "E")
+    st = syn.EnvState(**{k: g[f"in_{k}"] for k in syn.EnvState.__dataclass_fields__})
+    kw = {}
+    if tag == "E":
+        kw = dict(shape_params=g["E_shape"][:, :-6].contiguous().to(DEV), limb_weights=g["E_limb"].to(DEV))
+    if tag == "G":
+        kw = dict(occlusion=g["G_occlusion"].to(DEV))
+    plan = run_cuda_step(motion_data_from(g), st, cfg, **kw)
+    assert plan.obs.shape[1] == g[f"{tag}_out_obs"].shape[1]
+    check_against(plan, {k: g[f"{tag}_out_{k}"] for k in ("obs", "rew", "reward_raw", "reset", "terminate", "amp_obs_buf", "ref_body_pos",
+                                                          "ref_body_rot", "ref_body_vel")}, tag)
+
+
+def test_humanoid_im_reads_track_bodies_and_occlusion_from_the_env_config():
+    """env_vr.yaml through the task class: trackBodies / reset_bodies by NAME, full_body_reward False; and occlusion_training on the full
+    body (the pattern _update_occl_training leaves behind) -- the step agrees with the oracle fed the same options."""
+    from oracle import phc_oracle as O
+    from phc_b200.env.humanoid_im import HumanoidIm
+    from tests.helpers import oracle_tables, smpl_step_config
+    n = 96
+    m = syn.make_motions(n, seed=12, min_frames=40, max_frames=80)
+    vr = ["Head", "L_Hand", "R_Hand"]
+    ids = [syn.SMPL_BODY_NAMES.index(b) for b in vr]
+    task = HumanoidIm({"env": {"num_envs": n, "trackBodies": vr, "reset_bodies": vr, "full_body_reward": False}, "motion_data": m, "seed": 1})
+    assert task.get_task_obs_size() == 3 * 24 and task.get_obs_size() == 358 + 72 and task._reset_bodies_id == ids
+    task.reset()
+    for _ in range(2):
+        hist = task._amp_obs_buf.cpu().clone()
+        task.step(None)
+        torch.cuda.synchronize()
+        exp = O.env_step(oracle_tables(m), smpl_step_config(track_bodies=ids, reset_bodies=ids, full_body_reward=False), task._rigid_body_state_reshaped.cpu(),
+                         task._dof_state.cpu(), task.dof_force_tensor.cpu(), task.progress_buf.cpu(), task._sampled_motion_ids.cpu(),
+                         task._motion_start_times.cpu(), torch.zeros(n), torch.zeros(n, 3), hist)
+        close(task.obs_buf.cpu(), exp["obs"], atol=2e-6, what="vr obs")
+        close(task.rew_buf.cpu(), exp["rew"], what="vr rew")
+        assert torch.equal(task.reset_buf.cpu(), exp["reset"]) and torch.equal(task._terminate_buf.cpu(), exp["terminate"])
+    occ = HumanoidIm({"env": {"num_envs": n, "occlusion_training": True}, "motion_data": m, "seed": 1})
+    occ.reset()
+    hist = occ._amp_obs_buf.cpu().clone()
+    occ.step(None)
+    torch.cuda.synchronize()
+    pattern = occ.random_occlu_idx.cpu()
+    assert pattern[:, :9].all() and not pattern[:, 9:].any()          # what the reference's _update_occl_training ends with
+    exp = O.env_step(oracle_tables(m), smpl_step_config(), occ._rigid_body_state_reshaped.cpu(), occ._dof_state.cpu(), occ.dof_force_tensor.cpu(),
+                     occ.progress_buf.cpu(), occ._sampled_motion_ids.cpu(), occ._motion_start_times.cpu(), torch.zeros(n), torch.zeros(n, 3), hist,
+                     occlusion=pattern)
+    close(occ.obs_buf.cpu(), exp["obs"], atol=2e-6, what="occlusion obs")
+    assert torch.equal(occ.reset_buf.cpu(), exp["reset"])

@@ -7,6 +7,9 @@ import numpy as np
 import torch
 
 from oracle import phc_oracle as O
+import pytest
+
+from phc_b200 import synthetic as syn
 from tests.helpers import close, env_state_from, load, smpl_step_config, tables_from
 
 
@@ -366,3 +369,34 @@ def test_env_step_getup_smplx_shapes():
               "amp_obs_buf", "reset", "terminate"):
         close(out[k], g["out_" + k], what=f"getup smplx {k}")
     close(out["obs"], g["out_obs"], atol=2e-6, what="getup smplx obs")
+
+
+def _vr_case(g, tag):
+    """vr.npz (make_golden.gen_vr): E = Head + hands subset, subset reward, shape + limb-weight columns; F = the subset with the
+    full-body reward; G = every body tracked, occlusion training."""
+    track = g["track"].tolist()
+    subset = tag in ("E", "F")
+    cfg = smpl_step_config(track_bodies=track if subset else None, reset_bodies=track if subset else syn.SMPL_RESET_BODIES,
+                           full_body_reward=tag != "E")
+    kw = {}
+    if tag == "E":
+        kw = dict(shape_params=g["E_shape"][:, :-6], limb_weights=g["E_limb"])
+    if tag == "G":
+        kw = dict(occlusion=g["G_occlusion"])
+    return cfg, kw
+
+
+@pytest.mark.parametrize("tag", ["E", "F", "G"])
+def test_env_step_tracked_subset_occlusion_shape_columns(tag):
+    g = load("vr.npz")
+    cfg, kw = _vr_case(g, tag)
+    st = {k[3:]: v for k, v in g.items() if k.startswith("in_")}
+    out = O.env_step(tables_from(g), cfg, st["body_state"], st["dof_state"], st["dof_force"], st["progress"], st["motion_ids"], st["start_times"],
+                     st["start_offsets"], st["global_offset"], st["amp_hist"], **kw)
+    close(out["obs"], g[f"{tag}_out_obs"], atol=2e-6, what=f"{tag} obs")
+    close(out["rew"], g[f"{tag}_out_rew"], what=f"{tag} rew")
+    close(out["reward_raw"], g[f"{tag}_out_reward_raw"], what=f"{tag} reward_raw")
+    assert torch.equal(out["reset"], g[f"{tag}_out_reset"]) and torch.equal(out["terminate"], g[f"{tag}_out_terminate"])
+    close(out["ref_body_pos"], g[f"{tag}_out_ref_body_pos"], what=f"{tag} ref_body_pos")
+    if tag == "G":
+        assert g["G_occlusion"].any()
