@@ -14,6 +14,7 @@ d.install_on_import()`) that runs before the script's imports:
   phc.env.tasks.humanoid_im.HumanoidIm / env.tasks.humanoid_im.HumanoidIm   -> phc_b200.env.humanoid_im.HumanoidIm
   phc.env.tasks.humanoid_im_mcp.HumanoidImMCP (+ short name)                 -> phc_b200.env.humanoid_im_mcp.HumanoidImMCP
   learning.amp_agent.AMPAgent / phc.learning.amp_agent.AMPAgent              -> phc_b200.learning.amp_agent.AMPAgent
+  learning.im_amp.IMAmpAgent / phc.learning.im_amp.IMAmpAgent                -> phc_b200.learning.im_amp.IMAmpAgent
 so `IMAmpAgent(AMPAgent)` (learning/im_amp.py) and `eval("HumanoidIm")` resolve to the B200 implementations.  `install()` does
 the same rebinding immediately for modules that are already imported (what the tests use).  Isaac Gym stays the reference's: the
 rebinding keeps the original task class as `_RefHumanoidIm` and registers a backend factory that instantiates it as the owner of
@@ -30,6 +31,8 @@ _TARGETS: Dict[Tuple[str, ...], Dict[str, str]] = {
     ("phc.env.tasks.humanoid_im", "env.tasks.humanoid_im"): {"HumanoidIm": "phc_b200.env.humanoid_im:HumanoidIm"},
     ("phc.env.tasks.humanoid_im_mcp", "env.tasks.humanoid_im_mcp"): {"HumanoidImMCP": "phc_b200.env.humanoid_im_mcp:HumanoidImMCP"},
     ("phc.learning.amp_agent", "learning.amp_agent"): {"AMPAgent": "phc_b200.learning.amp_agent:AMPAgent"},
+    # run_hydra.py:259 registers `im_amp.IMAmpAgent` as the 'im_amp' algorithm: the mirror keeps eval / _post_step_eval / get_action
+    ("phc.learning.im_amp", "learning.im_amp"): {"IMAmpAgent": "phc_b200.learning.im_amp:IMAmpAgent"},
 }
 
 

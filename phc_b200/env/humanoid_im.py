@@ -148,6 +148,7 @@ class HumanoidIm:
         m = cfg.get("motion_data", None)
         if m is None:
             m = self._load_motion(env, sim)           # Humanoid._load_motion (humanoid_im.py:300-360): MotionLibSMPL on env.motion_file
+        self._motion_data = m
         d = m.to(self.device) if hasattr(m, "to") else m
         robot = hasattr(d, "gts_t")            # hinge-joint robot tables (phc/utils/motion_lib_real.py): h1 / g1
         if robot:
@@ -386,6 +387,12 @@ class HumanoidIm:
             self._cycle_phase.uniform_()        # what sample_time_interval would draw for the clips that wrap (motion_lib_base.py:415)
         if self._occl_training:
             self._update_occl_training()        # pre_physics_step of the reference (humanoid_im.py:1063-1066)
+        if getattr(self, "_eval_mode", False):
+            self._plan_eval.run()
+            self.extras["terminate"] = self._terminate_buf
+            self.extras["reward_raw"] = self.reward_raw
+            self.extras["mpjpe"], self.extras["body_pos"], self.extras["body_pos_gt"] = self._plan_eval.mpjpe, self._rigid_body_pos, self._plan_eval.body_pos_gt
+            return
         self._plan.run()
         self.extras["terminate"] = self._terminate_buf
         self.extras["reward_raw"] = self.reward_raw
@@ -479,6 +486,8 @@ class HumanoidIm:
         lib, ml, st = self._lib, self._motion_lib, _stream()
         # new start time (sample_time_interval) + cleared counters of the selected envs: one launch
         phase = torch.rand(self.num_envs, device=self.device)
+        if getattr(self, "_eval_mode", False) or bool(self.cfg.get("test", False)):
+            phase.zero_()                                 # flags.test: motion_times[:] = 0 (humanoid_im.py:1010-1011)
         _lib.check(lib.phc_reset_bookkeeping(self._reset_mask.data_ptr(), phase.data_ptr(), self._plan._env_motion.data_ptr(), self.num_envs,
                                              self._motion_start_times.data_ptr(), self._motion_start_times_offset.data_ptr(),
                                              self._global_offset.data_ptr(), self._cycle_counter.data_ptr(), self.progress_buf.data_ptr(),
@@ -522,20 +531,28 @@ class HumanoidIm:
                          max_len=-1 if test else self.max_len)
         return lib
 
+    def _reload_motions(self, random_sample: bool, start_idx: int = 0) -> None:
+        """MotionLib.load_motions with the simulator side's per-env assets, then both launch plans re-pointed at the new tables."""
+        lib = self._motion_data
+        test = bool(self.cfg.get("test", False))
+        lib.load_motions(skeleton_trees=self.sim.skeleton_trees, gender_betas=torch.as_tensor(self.sim.humanoid_shapes).cpu(),
+                         limb_weights=torch.as_tensor(self.sim.humanoid_limb_and_weights).cpu(), random_sample=random_sample, start_idx=start_idx,
+                         max_len=-1 if (test or not random_sample) else getattr(self, "max_len", -1))
+        self._motion_lib = lib.packed
+        self._motion_version = getattr(self, "_motion_version", 0) + 1      # a graph-captured rollout of the agent has to be re-captured
+        for plan in (self._plan, self._plan_reset_obs, getattr(self, "_plan_eval", None)):
+            if plan is not None:
+                plan.set_motion_lib(self._motion_lib)
+
     def resample_motions(self):
         """HumanoidIm.resample_motions (humanoid_im.py:369-394).  With a loadable library (`MotionLibSMPL.load_motions`): sample and load a
-        new set of clips on the device, re-point both launch plans at the new tables, keep every humanoid where it stands
+        new set of clips on the device, re-point the launch plans at the new tables, keep every humanoid where it stands
         (`_global_offset[:, :2] = root xy - reference root xy at the env's current motion time`), reset all envs.  With fixed tables
         (synthetic data) only the per-env motion records are refreshed (`_sampled_motion_ids` may have been edited)."""
         lib = self._motion_data
         if hasattr(lib, "load_motions") and hasattr(self.sim, "skeleton_trees"):
             test = bool(self.cfg.get("test", False))
-            lib.load_motions(skeleton_trees=self.sim.skeleton_trees, gender_betas=torch.as_tensor(self.sim.humanoid_shapes).cpu(),
-                             limb_weights=torch.as_tensor(self.sim.humanoid_limb_and_weights).cpu(),
-                             random_sample=(not test) and (not getattr(self, "seq_motions", False)), max_len=-1 if test else getattr(self, "max_len", -1))
-            self._motion_lib = lib.packed
-            for plan in (self._plan, self._plan_reset_obs):
-                plan.set_motion_lib(self._motion_lib)
+            self._reload_motions(random_sample=(not test) and (not getattr(self, "seq_motions", False)))
             t = self.progress_buf.float() * self.dt + self._motion_start_times + self._motion_start_times_offset
             root = ops.motion_state(self._motion_lib, self._sampled_motion_ids, t.contiguous(), want_dof=False)["root_pos"]   # get_root_pos_smpl
             self._global_offset[:, :2] = self._rigid_body_state_reshaped[:, 0, :2] - root[:, :2]
@@ -543,6 +560,44 @@ class HumanoidIm:
             return
         self._plan.refresh_motion_params()
         self._plan_reset_obs.refresh_motion_params()
+
+    # ---- evaluation (IMAmpAgent.eval, im_amp.py:136-242) ----------------------------------------------------------
+    def begin_seq_motion_samples(self):
+        """humanoid_im.py:468-472: clips in dataset order from the start (not sampled), all envs reset at motion time 0."""
+        self.start_idx = 0
+        self._reload_motions(random_sample=False, start_idx=0)
+        self.reset()
+
+    def forward_motion_samples(self):
+        """humanoid_im.py:474-477: the next num_envs clips of the dataset."""
+        self.start_idx += self.num_envs
+        self._reload_motions(random_sample=False, start_idx=self.start_idx)
+        self.reset()
+
+    def set_eval_mode(self, on: bool, termination_distance: float = 0.5) -> None:
+        """What IMAmpAgent.eval switches on the task and back (im_amp.py:160-184, :226-238): every termination distance 0.5 (UHC's),
+        mean-distance termination unless strict_eval (`flags.im_eval`, humanoid_im.py:1180), the mpjpe / body_pos_gt extras, no clip
+        cycling, no far-reference handling, resets at motion time 0 (`flags.test`, :1010-1011).  Implemented as a second launch plan over
+        the SAME buffers, built once; `step()` uses it while the mode is on."""
+        self._eval_mode = bool(on)
+        if on and getattr(self, "_plan_eval", None) is None:
+            import dataclasses
+            env = self.cfg.get("env", self.cfg)
+            J = self.num_bodies
+            rb = list(self._reset_bodies_id) if self._reset_bodies_id is not None else list(range(J))
+            if len(rb) > 15 and env.get("eval_body_ids") is not None:        # "Following UHC": the eval subset for full-body tracking (:182-183)
+                rb = [int(b) for b in env["eval_body_ids"]]
+            cfg_eval = dataclasses.replace(self.step_cfg, term_dist=float(termination_distance), reset_bodies=rb, cycle_motion=False, zero_out_far=False,
+                                           term_use_mean=not bool(env.get("strict_eval", False)), specialise=False)
+            p = self._plan
+            self._plan_eval = ops.EnvStepPlan(cfg_eval, self._motion_lib, self._rigid_body_state_reshaped, self._dof_state, self.dof_force_tensor,
+                                              self.progress_buf, self._sampled_motion_ids, self._motion_start_times, self._motion_start_times_offset,
+                                              self._global_offset, cycle_counter=self._cycle_counter, obs=self.obs_buf, rew=self.rew_buf,
+                                              reward_raw=self.reward_raw, reset=self.reset_buf, terminate=self._terminate_buf,
+                                              amp_obs_buf=self._amp_store, amp_ring=self._amp_use_ring, ring_head_dev=self._ring_head,
+                                              ref_cache=self._ref_cache, reward_from_cache=self._use_ref_cache, with_eval_extras=True,
+                                              occlusion=self.random_occlu_idx, shape_params=p._keep.get("shape_params"),
+                                              limb_weights=p._keep.get("limb_weights"))
 
     # ---- discriminator demo observations ------------------------------------------------------------------------
     def fetch_amp_obs_demo(self, num_samples: int) -> torch.Tensor:

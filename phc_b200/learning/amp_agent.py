@@ -271,7 +271,7 @@ class AMPAgent:
         self._graph_rollout = (bool(cfg.get("graph_rollout", True)) and os.environ.get("PHC_GRAPH_ROLLOUT", "1") != "0" and
                                bool(getattr(getattr(task, "sim", None), "graph_safe", False)) and
                                self.horizon_length % int(getattr(task.sim, "_body", torch.zeros(1)).shape[0]) == 0)
-        self._rollout_graph, self._rollout_out, self._rollout_calls, self._rollout_graph_launches = None, None, 0, 0
+        self._rollout_graph, self._rollout_out, self._rollout_calls, self._rollout_graph_launches, self._rollout_graph_version = None, None, 0, 0, 0
         self.epoch_num = 0
         self.frame = 0
         self.obs = None
@@ -452,6 +452,10 @@ class AMPAgent:
         config or PHC_GRAPH_ROLLOUT=0 keeps the eager loop; the phase timer needs the eager loop too)."""
         if not self._graph_rollout or self.timer.enabled:
             return self._play_steps_eager()
+        version = getattr(self.vec_env.env.task, "_motion_version", 0)
+        if self._rollout_graph is not None and version != self._rollout_graph_version:
+            self._rollout_graph = self._rollout_out = None      # the motion tables were re-loaded: the captured launches point at the old ones
+            self._rollout_calls = 1
         if self._rollout_graph is not None:
             self._rollout_graph.replay()
             self._lib.phc_launch_count_add(self._rollout_graph_launches)
@@ -465,7 +469,7 @@ class AMPAgent:
         with torch.cuda.graph(g):
             out = self._play_steps_eager()
         self._rollout_graph_launches = self._lib.phc_launch_count() - l0
-        self._rollout_graph, self._rollout_out = g, out
+        self._rollout_graph, self._rollout_out, self._rollout_graph_version = g, out, version
         g.replay()                                   # the capture recorded the work without running it
         return out
 
@@ -864,7 +868,16 @@ class AMPAgent:
         return dict(disc_loss=total, disc_grad_penalty=r["disc_grad_penalty"], disc_logit_loss=r["disc_logit_loss"],
                     disc_agent_acc=r["disc_agent_acc"], disc_demo_acc=r["disc_demo_acc"])
 
+    def eval(self) -> Dict[str, float]:
+        """CommonAgent.eval (common_agent.py:187-189): nothing to evaluate at this level; IMAmpAgent (im_amp.py) overrides it."""
+        return {}
+
     def pre_epoch(self, epoch_num: int) -> None:
+        task = self.vec_env.env.task
+        # AMPAgent.pre_epoch (amp_agent.py:506-516): a new set of clips every shape_resampling_interval epochs ("+ 1 to evade the evaluations")
+        if (getattr(task, "humanoid_type", "") in ("smpl", "smplh", "smplx") and hasattr(getattr(task, "_motion_data", None), "load_motions")
+                and hasattr(task.sim, "skeleton_trees") and epoch_num > 1 and epoch_num % int(task.shape_resampling_interval) == 1):
+            task.resample_motions()
         if self.normalize_input:
             self.running_mean_std_temp = self.running_mean_std.frozen_copy()   # amp_agent.py:527-528
 

@@ -150,3 +150,68 @@ def test_parse_task_style_construction_train_epoch_and_resample():
         backends.register_backend_factory(None)
         R.configurations.pop("rlgpu", None)
         R.vecenv_config.pop("RLGPU", None)
+
+
+def test_im_amp_eval_sweep_bookkeeping_matches_the_reference_procedure():
+    """IMAmpAgent.eval (im_amp.py:136-242) with the bookkeeping on the device (phc_b200/learning/im_amp.py) against the reference's own
+    procedure restated literally -- per-step lists of info['mpjpe'] / terminate stacked and sliced per clip on the host
+    (_post_step_eval, im_amp.py:244-363) -- fed the same recorded steps: success rate, per-clip MPJPE, failed keys."""
+    from phc_b200.learning.im_amp import IMAmpAgent
+    n_env, n_clips = 8, 20
+    owners = []
+    backends.register_backend_factory(lambda cfg, *a: owners.append(FakeGymOwner(cfg["env"]["num_envs"], "cuda:0")) or owners[-1])
+    try:
+        cfg = _hydra_cfg()
+        cfg["env"]["num_envs"] = n_env
+        cfg["env"]["motion_file"] = _clip_file(n_clips, seed=11)
+        task = HumanoidIm(cfg=cfg, sim_params=SimpleNamespace(dt=1.0 / 60.0), physics_engine="physx", device_type="cuda", device_id=0, headless=True)
+        from phc_b200.env.humanoid_im import RLGPUEnv
+        agent = IMAmpAgent("run", {"vec_env": RLGPUEnv(task), "horizon_length": 8, "minibatch_size": 64, "amp_minibatch_size": 16, "mini_epochs": 1,
+                                   "amp_obs_demo_buffer_size": 256, "amp_replay_buffer_size": 256, "amp_batch_size": 32,
+                                   "network": {"mlp": {"units": [64, 32], "activation": "relu"}, "disc": {"units": [64, 32], "activation": "relu"}}})
+        agent.obs = agent.env_reset()
+        rec = []                                               # what the reference's lists would hold
+        real_step = agent.env_eval_step
+
+        def spy(env, actions):
+            out = real_step(env, actions)
+            lib = task._motion_data
+            rec.append(dict(term=out[3]["terminate"].clone().cpu(), mpjpe=out[3]["mpjpe"].clone().cpu(), steps=lib.get_motion_num_steps().cpu(),
+                            ids=lib._curr_motion_ids.clone().cpu(), start=task.start_idx))
+            return out
+        agent.env_eval_step = spy
+        info = agent.eval()
+        assert set(info) == {"eval/success_rate", "eval/mpjpe_all", "eval/mpjpe_succ"} and task._eval_mode is False
+        # --- the reference procedure on the recorded steps
+        num_unique = n_clips
+        term_mem, mpjpe_all, cur, state, mp = [], [], 0, torch.zeros(n_env, dtype=torch.bool), []
+        for r in rec:
+            state |= (cur <= r["steps"] - 1) & (r["term"] != 0)
+            if (~state).sum() > 0:
+                hit = (r["ids"] == num_unique - 1)
+                if hit.sum() > 0:
+                    bound = int(hit.nonzero()[0]) + 1
+                    curr_max = int(r["steps"][:bound][~state[:bound]].max()) if (~state[:bound]).sum() > 0 else cur - 1
+                else:
+                    curr_max = int(r["steps"][~state].max())
+                if cur >= curr_max:
+                    curr_max = cur + 1
+            else:
+                curr_max = int(r["steps"].max())
+            mp.append(r["mpjpe"])
+            cur += 1
+            if cur >= curr_max or int(state.sum()) == n_env:
+                cur = 0
+                term_mem.append(state.clone())
+                allm = torch.stack(mp)
+                mpjpe_all.append(torch.stack([allm[:(int(i) - 1), e].mean() for e, i in enumerate(r["steps"])]))
+                state, mp = torch.zeros(n_env, dtype=torch.bool), []
+        term = torch.cat(term_mem)[:num_unique]
+        per_clip = torch.cat(mpjpe_all)[:num_unique]
+        assert len(term_mem) == 3                                # 20 clips, 8 at a time
+        assert abs(info["eval/success_rate"] - float(1 - term.float().mean())) < 1e-6
+        assert abs(info["eval/mpjpe_all"] - float(per_clip.mean()) * 1000) < 1e-2 * max(1.0, float(per_clip.mean()) * 1000) * 1e-2 + 1e-3
+        if (~term).any():
+            assert abs(info["eval/mpjpe_succ"] - float(per_clip[~term].mean()) * 1000) < 1e-3 + 1e-4 * float(per_clip[~term].mean()) * 1000
+    finally:
+        backends.register_backend_factory(None)
