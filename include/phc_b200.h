@@ -434,6 +434,12 @@ PHC_API int phc_rms_apply(const float* x, int64_t ldx, int64_t n, int32_t d, con
                   int32_t unnorm, float* y, int64_t ldy, const int64_t* row_idx /* [n] or NULL: y[r] = f(x[row_idx[r]]),
                   the minibatch gather of AMPDataset._get_item (amp_datasets.py:81-94) fused in */, void* stream);
 /* ... and its train-mode statistics update (parallel-variance merge of the batch mean / unbiased var, :56-68). */
+/* phc_rms_apply (with mean_apply / var_apply: the live statistics, or the frozen copy of AMPAgent._preproc_obs(use_temp), amp_agent.py:535-552)
+ * and phc_rms_update of the live statistics (mean, var, count) in ONE pass over the gathered rows: RunningMeanStd.forward in train mode
+ * normalises with the statistics as they are and folds the batch in afterwards (running_mean_std.py:99-107).  mean_apply may alias mean. */
+PHC_API int phc_rms_apply_update(const float* x, int64_t ldx, int64_t n, int32_t d, const double* mean_apply, const double* var_apply, float eps,
+                         float* y, int64_t ldy, const int64_t* row_idx, double* mean, double* var, double* count, void* workspace,
+                         void* stream);
 PHC_API int64_t phc_rms_workspace_bytes(int32_t d);
 PHC_API int phc_rms_update(const float* x, int64_t ldx, int64_t n, int32_t d, double* mean, double* var, double* count,
                    void* workspace, const int64_t* row_idx /* [n] or NULL, as in phc_rms_apply */, void* stream);

@@ -130,6 +130,7 @@ SIGNATURES = {
     "phc_gemm_set_precision": (C.c_int, [C.c_int32]),
     "phc_colsum": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p, C.c_int32, _p]),
     "phc_rms_apply": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, _p, _p, C.c_float, C.c_int32, _p, C.c_int64, _p, _p]),
+    "phc_rms_apply_update": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, _p, _p, C.c_float, _p, C.c_int64, _p, _p, _p, _p, _p, _p]),
     "phc_rms_workspace_bytes": (C.c_int64, [C.c_int32]),
     "phc_rms_update": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, _p, _p, _p, _p, _p, _p]),
     "phc_gaussian_sample": (C.c_int, [_p, C.c_int64, _p, _p, C.c_int64, C.c_int32, _p, _p, _p, _p, _p]),

@@ -75,6 +75,52 @@ __global__ void __launch_bounds__(1024) rms_moments_kernel(const float* __restri
   }
 }
 
+// One pass over the (gathered) rows: y = clamp((x - m) / sqrt(v + eps), +-5) with the statistics (m, v) given for the APPLY, and the
+// fp64 column moments of the raw rows accumulated for the UPDATE of the live statistics -- RunningMeanStd.forward in train mode
+// ("update After normalization", running_mean_std.py:99-107) and AMPAgent._preproc_obs with the frozen temp copy (amp_agent.py:535-552)
+// read the rows once instead of twice.  Thread (tx, ty): column blockIdx.x * 32 + tx, rows ty, ty + 32, ... of the block's row strip;
+// a warp reads 128 contiguous bytes of one row per instruction, four rows in flight per thread.
+__global__ void __launch_bounds__(1024) rms_apply_moments_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int d,
+                                                                 const double* __restrict__ mean_a, const double* __restrict__ var_a, float eps,
+                                                                 float* __restrict__ y, int64_t ldy, const int64_t* __restrict__ row_idx,
+                                                                 double* __restrict__ acc) {
+  __shared__ double s1[32][33], s2[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double a = 0.0, b = 0.0;
+  if (c < d) {
+    const float m = (float)mean_a[c];
+    const float sd = sqrtf((float)var_a[c] + eps);
+    const int64_t stride = 32 * (int64_t)gridDim.y;
+    int64_t r = (int64_t)blockIdx.y * 32 + threadIdx.y;
+    for (; r + 3 * stride < n; r += 4 * stride) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int64_t rr = r + u * stride; v[u] = x[(row_idx ? row_idx[rr] : rr) * ldx + c]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        y[(r + u * stride) * ldy + c] = fminf(fmaxf((v[u] - m) / sd, -5.0f), 5.0f);
+        const double dv = (double)v[u];
+        a += dv; b += dv * dv;
+      }
+    }
+    for (; r < n; r += stride) {
+      const float v = x[(row_idx ? row_idx[r] : r) * ldx + c];
+      y[r * ldy + c] = fminf(fmaxf((v - m) / sd, -5.0f), 5.0f);
+      const double dv = (double)v;
+      a += dv; b += dv * dv;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < d) {
+    double ta = 0.0, tb = 0.0;
+    for (int i = 0; i < 32; ++i) { ta += s1[i][threadIdx.x]; tb += s2[i][threadIdx.x]; }
+    atomicAdd(acc + c, ta);
+    atomicAdd(acc + d + c, tb);
+  }
+}
+
 // parallel-variance merge of the batch moments into the fp64 running stats (running_mean_std.py:56-68, :99-107)
 __global__ void __launch_bounds__(1024) rms_merge_kernel(const double* __restrict__ acc, int64_t n, int d,
                                                          double* __restrict__ mean, double* __restrict__ var,
@@ -413,6 +459,21 @@ extern "C" int phc_rms_update(const float* x, int64_t ldx, int64_t n, int32_t d,
   rms_moments_kernel<<<dim3((d + 31) / 32, gy), dim3(32, 32), 0, ST(stream)>>>(x, ldx, n, d, acc, row_idx); phc_count_launches(1);
   rms_merge_kernel<<<1, 1024, 0, ST(stream)>>>(acc, n, d, mean, var, count); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "rms_update kernels");
+}
+
+extern "C" int phc_rms_apply_update(const float* x, int64_t ldx, int64_t n, int32_t d, const double* mean_apply, const double* var_apply,
+                                    float eps, float* y, int64_t ldy, const int64_t* row_idx, double* mean, double* var, double* count,
+                                    void* workspace, void* stream) {
+  if (!x || !mean_apply || !var_apply || !y || !mean || !var || !count || !workspace || n < 2 || d < 1 || ldx < d || ldy < d) {
+    phc_set_error("phc_rms_apply_update: bad arguments (needs n >= 2)"); return PHC_ERR_INVALID_ARG;
+  }
+  double* acc = static_cast<double*>(workspace);
+  cudaMemsetAsync(acc, 0, (size_t)2 * d * sizeof(double), ST(stream));
+  int gy = (int)((n + 255) / 256); if (gy > 24) gy = 24; if (gy < 1) gy = 1;
+  rms_apply_moments_kernel<<<dim3((d + 31) / 32, gy), dim3(32, 32), 0, ST(stream)>>>(x, ldx, n, d, mean_apply, var_apply, eps, y, ldy, row_idx, acc);
+  phc_count_launches(1);
+  rms_merge_kernel<<<1, 1024, 0, ST(stream)>>>(acc, n, d, mean, var, count); phc_count_launches(1);
+  return phc_check_cuda(cudaGetLastError(), "rms_apply_update kernels");
 }
 
 extern "C" int phc_gaussian_sample(const float* mu, int64_t ldmu, const float* logstd, const float* noise, int64_t n,

@@ -114,6 +114,19 @@ class RunningMeanStd:
             _lib.check(rc, "phc_rms_apply")
         return out
 
+    def apply_update(self, x: torch.Tensor, out: torch.Tensor, row_idx: Optional[torch.Tensor] = None, n: Optional[int] = None,
+                     apply_stats: Optional["RunningMeanStd"] = None) -> torch.Tensor:
+        """apply() with `apply_stats` (default: these statistics, as they are BEFORE the update) and update() of these statistics in one
+        pass over the rows (phc_rms_apply_update): RunningMeanStd.forward in train mode / _preproc_obs(use_temp=True)."""
+        n = (x.shape[0] if row_idx is None else row_idx.shape[0]) if n is None else n
+        a = self if apply_stats is None else apply_stats
+        rc = self._lib.phc_rms_apply_update(x.data_ptr(), x.stride(0), n, self.size, a.running_mean.data_ptr(), a.running_var.data_ptr(), a.epsilon,
+                                            out.data_ptr(), out.stride(0), _ptr(row_idx), self.running_mean.data_ptr(), self.running_var.data_ptr(),
+                                            self.count.data_ptr(), self._ws.data_ptr(), _stream())
+        if rc:
+            _lib.check(rc, "phc_rms_apply_update")
+        return out
+
     def update(self, x: torch.Tensor, n: Optional[int] = None, row_idx: Optional[torch.Tensor] = None) -> None:
         n = (x.shape[0] if row_idx is None else row_idx.shape[0]) if n is None else n
         rc = self._lib.phc_rms_update(x.data_ptr(), x.stride(0), n, self.size, self.running_mean.data_ptr(),
@@ -384,16 +397,19 @@ class AMPAgent:
             out[:, :self.obs_dim] = src
             return out
         rms = self.running_mean_std_temp if use_temp else self.running_mean_std
-        rms.apply(obs_batch, out, row_idx=row_idx)
-        if self.running_mean_std.training and not self.running_mean_std.frozen:
-            self.running_mean_std.update(obs_batch, row_idx=row_idx)      # statistics of the RAW rows, gathered in-kernel
+        if self.running_mean_std.training and not self.running_mean_std.frozen and n >= 2:
+            # normalise with `rms` and fold the RAW rows into the live statistics in the same pass (rows gathered in-kernel)
+            self.running_mean_std.apply_update(obs_batch, out, row_idx=row_idx, apply_stats=rms)
+        else:
+            rms.apply(obs_batch, out, row_idx=row_idx)
         return out
 
     def _preproc_amp_obs(self, amp_obs: torch.Tensor, out: torch.Tensor, row_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
         if self._normalize_amp_input:
-            self._amp_input_mean_std.apply(amp_obs, out, row_idx=row_idx)
             if self._amp_input_mean_std.training:
-                self._amp_input_mean_std.update(amp_obs, row_idx=row_idx)
+                self._amp_input_mean_std.apply_update(amp_obs, out, row_idx=row_idx)
+            else:
+                self._amp_input_mean_std.apply(amp_obs, out, row_idx=row_idx)
         else:
             out[:, :self.amp_obs_dim] = amp_obs if row_idx is None else amp_obs[row_idx]
         return out

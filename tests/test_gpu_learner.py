@@ -225,3 +225,33 @@ def test_minibatch_update_vs_autograd_oracle(B, Bd, obs, act, amp, units, activa
         d = (got["new_params"][k].double().cpu() - pe.double()).abs()
         assert float(d[well].max()) <= 0.02 * lr + 1e-7 * float(pe.abs().max()), f"adam {k}: {float(d[well].max()):.3e}"
         assert float(d.max()) <= 2.1 * lr, f"adam (near-zero gradient entries) {k}: {float(d.max()):.3e}"
+
+
+def test_fused_rms_apply_update_equals_apply_then_update():
+    """phc_rms_apply_update (one pass: normalise with given statistics + fold the raw rows into the live ones) against phc_rms_apply
+    followed by phc_rms_update, with a row gather and with a frozen copy as the apply statistics (AMPAgent._preproc_obs(use_temp=True))."""
+    from phc_b200.learning.amp_agent import RunningMeanStd
+    g = torch.Generator().manual_seed(3)
+    n_src, n, d = 5000, 3001, 934
+    x = (torch.randn(n_src, d, generator=g) * 3 + 1).to(DEV)
+    idx = torch.randint(0, n_src, (n,), generator=g).to(DEV)
+    a, b = RunningMeanStd(d, DEV), RunningMeanStd(d, DEV)
+    for r in (a, b):
+        r.running_mean.copy_(torch.randn(d, generator=g).double())
+        r.running_var.copy_((torch.rand(d, generator=g) + 0.5).double())
+        r.count.fill_(777.0)
+    frozen = a.frozen_copy()
+    frozen.running_mean += 0.25                                  # the temp copy differs from the live statistics
+    ya, yb = torch.zeros(n, round4(d), device=DEV), torch.zeros(n, round4(d), device=DEV)
+    frozen.apply(x, ya, row_idx=idx)
+    a.update(x, row_idx=idx)
+    b.apply_update(x, yb, row_idx=idx, apply_stats=frozen)
+    torch.cuda.synchronize()
+    assert torch.equal(ya, yb)
+    close(b.running_mean.cpu(), a.running_mean.cpu(), rtol=1e-12, atol=1e-12, what="running mean")
+    close(b.running_var.cpu(), a.running_var.cpu(), rtol=1e-11, atol=1e-12, what="running var")
+    assert float(b.count) == float(a.count) == 777.0 + n
+    # and against the reference formula on the CPU
+    rows = x[idx].cpu()
+    exp = O.rms_normalize(rows, frozen.running_mean.cpu(), frozen.running_var.cpu())
+    close(yb[:, :d].cpu(), exp, rtol=1e-6, atol=1e-6, what="normalised rows")
