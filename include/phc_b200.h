@@ -457,6 +457,13 @@ PHC_API int phc_ppo_actor_grad(const float* mu, int64_t ldmu, const float* logst
 /* CommonAgent._critic_loss with clip_value False (:576-587): dv = coef*2*(v-ret)*inv_batch; stats[5] += sum (ret-v)^2 */
 PHC_API int phc_ppo_critic_grad(const float* v, int64_t ldv, const float* ret, int64_t n, float coef, float inv_batch, float* dv,
                         int64_t lddv, float* stats, void* stream);
+/* phc_ppo_actor_grad + phc_ppo_critic_grad on an INDEX-COMPOSED minibatch: actions / old_neglogp / adv / old_mu / old_sigma / ret are the
+ * epoch's dataset arrays ([batch_size, ...], AMPDataset.values_dict, amp_datasets.py:81-101) and minibatch row r is their row row_idx[r];
+ * mu / v / dmu / dv are in minibatch order.  Replaces six gather passes (`values_dict[k][idx]`) per minibatch. */
+PHC_API int phc_ppo_grads_gather(const float* mu, int64_t ldmu, const float* logstd, const float* actions, const float* old_neglogp,
+                         const float* adv, const float* old_mu, const float* old_sigma, const float* v, int64_t ldv, const float* ret,
+                         const int64_t* row_idx, int64_t n, int32_t A, float e_clip, float bound_coef, float critic_coef, float inv_batch,
+                         float* dmu, int64_t lddmu, float* dv, int64_t lddv, float* stats, void* stream);
 /* AMPAgent._disc_loss prediction part (amp_agent.py:739-743, :791-804): rows [0,n_agent) are agent+replay logits
  * (target 0), rows [n_agent, n_agent+n_demo) demo logits (target 1); dlogit = coef*0.5*dBCE/n.
  * stats[6] += sum softplus(agent) [7] += sum softplus(-demo) [8] += #(agent<0) [9] += #(demo>0) */

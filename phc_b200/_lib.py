@@ -136,6 +136,8 @@ SIGNATURES = {
     "phc_gaussian_sample": (C.c_int, [_p, C.c_int64, _p, _p, C.c_int64, C.c_int32, _p, _p, _p, _p, _p]),
     "phc_ppo_actor_grad": (C.c_int, [_p, C.c_int64, _p, _p, _p, _p, _p, _p, C.c_int64, C.c_int32, C.c_float, C.c_float,
                                      C.c_float, _p, C.c_int64, _p, _p]),
+    "phc_ppo_grads_gather": (C.c_int, [_p, C.c_int64, _p, _p, _p, _p, _p, _p, _p, C.c_int64, _p, _p, C.c_int64, C.c_int32, C.c_float, C.c_float,
+                                       C.c_float, C.c_float, _p, C.c_int64, _p, C.c_int64, _p, _p]),
     "phc_ppo_critic_grad": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.c_float, C.c_float, _p, C.c_int64, _p, _p]),
     "phc_disc_logit_grad": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int64, C.c_float, _p, C.c_int64, _p, _p]),
     "phc_disc_reward": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.c_float, C.c_float, C.c_float, _p, _p, _p]),

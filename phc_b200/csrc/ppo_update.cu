@@ -181,30 +181,34 @@ ppo_actor_grad_kernel(const float* __restrict__ mu, int64_t ldmu, const float* _
                       const float* __restrict__ actions, const float* __restrict__ old_neglogp,
                       const float* __restrict__ adv, const float* __restrict__ old_mu,
                       const float* __restrict__ old_sigma, int64_t n, int A, float e_clip, float bound_coef,
-                      float inv_batch, float* __restrict__ dmu, int64_t lddmu, float* __restrict__ stats) {
+                      float inv_batch, float* __restrict__ dmu, int64_t lddmu, float* __restrict__ stats,
+                      const int64_t* __restrict__ row_idx = nullptr) {
+  // row_idx (optional): the minibatch is INDEX-COMPOSED -- actions / old_neglogp / adv / old_mu / old_sigma are the epoch's dataset
+  // arrays and row r of the minibatch is their row row_idx[r] (mu / dmu are in minibatch order); saves six gather passes per minibatch.
   // one warp per row, rows strided over the grid; the five batch statistics are accumulated per warp, folded per block in
   // shared memory and leave with ONE atomic per block and statistic (per-row atomics on five addresses serialise: 140 us)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   float st[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; r < n; r += warps_total) {
+    const int64_t rs = row_idx ? row_idx[r] : r;          // row of the dataset arrays
     float acc = 0.f, ls = 0.f, bl = 0.f, kl = 0.f;
     for (int j = lane; j < A; j += 32) {
       const float m = mu[r * ldmu + j];
       const float l = logstd[j];
       const float sg = expf(l);
-      const float z = (actions[r * A + j] - m) / sg;
+      const float z = (actions[rs * A + j] - m) / sg;
       acc += z * z;
       ls += l;
       const float hi = fmaxf(m - 1.0f, 0.f), lo = fminf(m + 1.0f, 0.f);
       bl += lo * lo + hi * hi;
-      const float so = old_sigma[r * A + j], mo = old_mu[r * A + j];
+      const float so = old_sigma[rs * A + j], mo = old_mu[rs * A + j];
       kl += logf(so / sg + 1e-5f) + (sg * sg + (mo - m) * (mo - m)) / (2.0f * (so * so + 1e-5f)) - 0.5f;
     }
     acc = wsum(acc); ls = wsum(ls); bl = wsum(bl); kl = wsum(kl);
     const float nlp = 0.5f * acc + 0.5f * 1.8378770664093453f * (float)A + ls;
-    const float ad = adv[r];
-    const float ratio = expf(old_neglogp[r] - nlp);
+    const float ad = adv[rs];
+    const float ratio = expf(old_neglogp[rs] - nlp);
     const float s1 = -ad * ratio;
     const float s2 = -ad * fminf(fmaxf(ratio, 1.0f - e_clip), 1.0f + e_clip);
     const float a_loss = fmaxf(s1, s2);
@@ -213,7 +217,7 @@ ppo_actor_grad_kernel(const float* __restrict__ mu, int64_t ldmu, const float* _
     for (int j = lane; j < A; j += 32) {
       const float m = mu[r * ldmu + j];
       const float sg = expf(logstd[j]);
-      const float dn = -(actions[r * A + j] - m) / (sg * sg);            // d neglogp / d mu
+      const float dn = -(actions[rs * A + j] - m) / (sg * sg);           // d neglogp / d mu
       const float hi = fmaxf(m - 1.0f, 0.f), lo = fminf(m + 1.0f, 0.f);
       dmu[r * lddmu + j] = inv_batch * (g_nlp * dn + bound_coef * 2.0f * (hi + lo));
     }
@@ -237,10 +241,10 @@ ppo_actor_grad_kernel(const float* __restrict__ mu, int64_t ldmu, const float* _
 // critic: c_loss = (ret - v)^2 (clip_value False); dv = coef * 2 (v - ret) / batch.   stats[5] += sum c_loss
 __global__ void ppo_critic_grad_kernel(const float* __restrict__ v, int64_t ldv, const float* __restrict__ ret, int64_t n,
                                        float coef, float inv_batch, float* __restrict__ dv, int64_t lddv,
-                                       float* __restrict__ stats) {
+                                       float* __restrict__ stats, const int64_t* __restrict__ row_idx = nullptr) {
   float loss = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float d = v[i * ldv] - ret[i];
+    const float d = v[i * ldv] - ret[row_idx ? row_idx[i] : i];
     loss += d * d;
     dv[i * lddv] = coef * 2.0f * d * inv_batch;
   }
@@ -495,6 +499,22 @@ extern "C" int phc_ppo_actor_grad(const float* mu, int64_t ldmu, const float* lo
   ppo_actor_grad_kernel<<<(unsigned)((n + 7) / 8 < 148 * 4 ? (n + 7) / 8 : 148 * 4), 256, 0, ST(stream)>>>(mu, ldmu, logstd, actions, old_neglogp, adv, old_mu, old_sigma, n, A,
                                                                          e_clip, bound_coef, inv_batch, dmu, lddmu, stats); phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "ppo_actor_grad_kernel");
+}
+
+extern "C" int phc_ppo_grads_gather(const float* mu, int64_t ldmu, const float* logstd, const float* actions, const float* old_neglogp,
+                                    const float* adv, const float* old_mu, const float* old_sigma, const float* v, int64_t ldv,
+                                    const float* ret, const int64_t* row_idx, int64_t n, int32_t A, float e_clip, float bound_coef,
+                                    float critic_coef, float inv_batch, float* dmu, int64_t lddmu, float* dv, int64_t lddv, float* stats,
+                                    void* stream) {
+  if (!mu || !logstd || !actions || !old_neglogp || !adv || !old_mu || !old_sigma || !v || !ret || !row_idx || !dmu || !dv || !stats || n < 0 ||
+      A < 1 || ldmu < A || lddmu < A || ldv < 1 || lddv < 1) {
+    phc_set_error("phc_ppo_grads_gather: bad arguments"); return PHC_ERR_INVALID_ARG;
+  }
+  if (n == 0) return PHC_OK;
+  ppo_actor_grad_kernel<<<(unsigned)((n + 7) / 8 < 148 * 4 ? (n + 7) / 8 : 148 * 4), 256, 0, ST(stream)>>>(mu, ldmu, logstd, actions, old_neglogp, adv, old_mu, old_sigma, n, A,
+                                                                         e_clip, bound_coef, inv_batch, dmu, lddmu, stats, row_idx); phc_count_launches(1);
+  ppo_critic_grad_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(v, ldv, ret, n, critic_coef, inv_batch, dv, lddv, stats, row_idx); phc_count_launches(1);
+  return phc_check_cuda(cudaGetLastError(), "ppo_grads_gather kernels");
 }
 
 extern "C" int phc_ppo_critic_grad(const float* v, int64_t ldv, const float* ret, int64_t n, float coef, float inv_batch,

@@ -730,15 +730,16 @@ class AMPAgent:
 
 
     def _loss_grads(self, ds, idx, B, Bd, A, inv_b, st, mu, val, logits) -> None:
+        """d loss / d (mu, value, logit) of the minibatch `idx`: the dataset arrays are addressed through idx inside the kernels."""
         lib, net = self._lib, self.model
-        actions, old_nlp, adv = ds["actions"][idx], ds["old_logp_actions"][idx], ds["advantages"][idx]
-        old_mu, old_sigma, rets = ds["mu"][idx], ds["sigma"][idx], ds["returns"][idx].reshape(-1)
         dmu, dv, dl = self._ws_actor["dout"], self._ws_critic["dout"], self._ws_disc["dout"]
-        _lib.check(lib.phc_ppo_actor_grad(mu.data_ptr(), mu.stride(0), net.sigma.data_ptr(), actions.data_ptr(), old_nlp.data_ptr(),
-                                          adv.data_ptr(), old_mu.data_ptr(), old_sigma.data_ptr(), B, A, self.e_clip,
-                                          self.bounds_loss_coef, inv_b, dmu.data_ptr(), dmu.stride(0), self._stats.data_ptr(), st))
-        _lib.check(lib.phc_ppo_critic_grad(val.data_ptr(), val.stride(0), rets.data_ptr(), B, self.critic_coef, inv_b,
-                                           dv.data_ptr(), dv.stride(0), self._stats.data_ptr(), st))
+        arr = [ds[k] if ds[k].is_contiguous() else ds[k].contiguous() for k in ("actions", "old_logp_actions", "advantages", "mu", "sigma", "returns")]
+        for k, t in zip(("actions", "old_logp_actions", "advantages", "mu", "sigma", "returns"), arr):
+            ds[k] = t                                    # (flattened views of the experience buffer are made contiguous once per epoch)
+        _lib.check(lib.phc_ppo_grads_gather(mu.data_ptr(), mu.stride(0), net.sigma.data_ptr(), arr[0].data_ptr(), arr[1].data_ptr(), arr[2].data_ptr(),
+                                            arr[3].data_ptr(), arr[4].data_ptr(), val.data_ptr(), val.stride(0), arr[5].data_ptr(), idx.data_ptr(), B, A,
+                                            self.e_clip, self.bounds_loss_coef, self.critic_coef, inv_b, dmu.data_ptr(), dmu.stride(0), dv.data_ptr(),
+                                            dv.stride(0), self._stats.data_ptr(), st), "phc_ppo_grads_gather")
         _lib.check(lib.phc_disc_logit_grad(logits.data_ptr(), logits.stride(0), 2 * Bd, Bd, self._disc_coef, dl.data_ptr(),
                                            dl.stride(0), self._stats.data_ptr(), st))
 
