@@ -396,7 +396,11 @@ typedef struct PhcGemmDesc {
   int32_t act;              /* PHC_ACT_* */
   float* aux; int64_t ldaux;
   int32_t accumulate, k_splits;
+  const float* B_lo;        /* optional: the 3xTF32 low part of B, same layout and ldb, made by phc_split_lo (weights: split once per
+                             * optimizer step instead of once per tile visit); NULL = the kernel splits B's tiles itself */
 } PhcGemmDesc;
+/* lo[i] = rna_tf32(x[i] - trunc_tf32(x[i])): the second TF32 term of every fp32 value, what the GEMM's splitter warps compute per tile */
+PHC_API int phc_split_lo(const float* x, float* lo, int64_t n, void* stream);
 PHC_API int phc_gemm_group(const PhcGemmDesc* problems, int32_t count, void* stream);
 PHC_API int phc_gemm_tc5s(const float* A, int64_t lda, int32_t a_kmajor, const float* B, int64_t ldb, int32_t b_kmajor, float* C,
                   int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha, const float* bias, int32_t act,

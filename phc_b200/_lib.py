@@ -78,7 +78,8 @@ class PhcStepArgs(C.Structure):
 class PhcGemmDesc(C.Structure):
     _fields_ = [("A", _p), ("lda", C.c_int64), ("a_kmajor", C.c_int32), ("B", _p), ("ldb", C.c_int64), ("b_kmajor", C.c_int32),
                 ("C", _p), ("ldc", C.c_int64), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("alpha", C.c_float),
-                ("bias", _p), ("act", C.c_int32), ("aux", _p), ("ldaux", C.c_int64), ("accumulate", C.c_int32), ("k_splits", C.c_int32)]
+                ("bias", _p), ("act", C.c_int32), ("aux", _p), ("ldaux", C.c_int64), ("accumulate", C.c_int32), ("k_splits", C.c_int32),
+                ("B_lo", _p)]
 
 
 PHC_GEMM_GROUP_MAX = 8
@@ -124,6 +125,7 @@ SIGNATURES = {
     "phc_gemm_tc5": (C.c_int, [_p, _p, C.c_int64, C.c_int32, _p, _p, C.c_int64, C.c_int32, _p, _p, _p, C.c_int64, C.c_int32, C.c_int32,
                                C.c_int32, C.c_float, _p, C.c_int32, _p, C.c_int64, C.c_int32, C.c_int32, _p]),
     "phc_gemm_group": (C.c_int, [C.POINTER(PhcGemmDesc), C.c_int32, _p]),
+    "phc_split_lo": (C.c_int, [_p, _p, C.c_int64, _p]),
     "phc_gemm_tc5s": (C.c_int, [_p, C.c_int64, C.c_int32, _p, C.c_int64, C.c_int32, _p, C.c_int64, C.c_int32, C.c_int32,
                                 C.c_int32, C.c_float, _p, C.c_int32, _p, C.c_int64, C.c_int32, C.c_int32, _p]),
     "phc_gemm_tc5s_set_ctas": (C.c_int, [C.c_int32]),

@@ -54,19 +54,19 @@ def _newer(src_files, target) -> bool:
     return any(os.path.getmtime(s) > t for s in src_files)
 
 
-def build_variant(name: str, env_step_flags) -> str:
-    """Experiment builds (tools/ab_env.sh): the same library with extra -D flags on env_step.cu, written to
+def build_variant(name: str, flags, source: str = "env_step.cu") -> str:
+    """Experiment builds (tools/ab_env.sh, tools/gpu_r2_s9.sh): the same library with extra -D flags on ONE source file, written to
     lib/alt_<name>/libphc_b200.so; selected at run time with PHC_LIB_PATH.  Never the default."""
     out_dir = os.path.join(OUT_DIR, f"alt_{name}")
     os.makedirs(out_dir, exist_ok=True)
     nvcc = _nvcc()
-    obj = os.path.join(out_dir, "env_step.o")
-    r = subprocess.run([nvcc] + ARCH + COMMON + list(env_step_flags) + ["-c", os.path.join(CSRC, "env_step.cu"), "-o", obj],
+    obj = os.path.join(out_dir, source.replace(".cu", ".o"))
+    r = subprocess.run([nvcc] + ARCH + COMMON + SOURCES[source] + list(flags) + ["-c", os.path.join(CSRC, source), "-o", obj],
                        capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError(f"nvcc failed on env_step.cu ({name}):\n{r.stderr}")
+        raise RuntimeError(f"nvcc failed on {source} ({name}):\n{r.stderr}")
     build()
-    objs = [obj if s == "env_step.cu" else os.path.join(OBJ_DIR, s.replace(".cu", ".o")) for s in SOURCES]
+    objs = [obj if s == source else os.path.join(OBJ_DIR, s.replace(".cu", ".o")) for s in SOURCES]
     lib = os.path.join(out_dir, "libphc_b200.so")
     r = subprocess.run([nvcc] + ARCH + ["-shared", "-o", lib] + objs + ["-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:

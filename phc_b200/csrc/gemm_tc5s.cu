@@ -50,13 +50,23 @@ template <int CTAS>
 struct Cfg {
   static constexpr int B_ROWS = BN / CTAS;
   static constexpr int B_TILE = B_ROWS * BK * 4;
-  static constexpr int RAW = A_TILE + B_TILE;         // bytes TMA writes per stage
-  // the raw ring (TMA prefetch depth) is decoupled from the lo ring: a lo tile lives only from its split to the MMAs of its
-  // k-block, so two lo slots suffice while 4 (6) raw stages cover the L2 -> shared-memory latency (the first version kept
-  // raw + lo together, 3 stages of 64 KB: one in MMA, one in split, ONE in flight -> 1630 cycles per k-block instead of 768)
-  static constexpr int RAW_STAGES = CTAS == 1 ? 4 : 6;
+  static constexpr int RAW = A_TILE + B_TILE;         // bytes of the raw A and B tiles of a stage
+  // A stage of the TMA ring is [A raw | B raw | B lo]: the B lo tile either arrives by TMA (weights: a pre-split `lo` copy of the
+  // parameter bucket exists, PhcGemmDesc.B_lo) or is written by the splitters; only the A lo tile -- always produced here -- lives in
+  // its own two-slot ring (a lo tile is needed only from its split to the MMAs of its k-block).  The ring depth is what shared memory
+  // leaves: 3 (5) stages of 48 (32) KB.
+  // -DPHC_TC5S_BLO_IN_RING (A/B build): the layout this replaced -- stages hold the raw tiles only (4 / 6 of them), both lo tiles go to
+  // the lo ring, B_lo is ignored.
+#ifdef PHC_TC5S_BLO_IN_RING
+  static constexpr bool BLO_IN_STAGE = false;
+#else
+  static constexpr bool BLO_IN_STAGE = true;
+#endif
+  static constexpr int STAGE = BLO_IN_STAGE ? A_TILE + 2 * B_TILE : RAW;
+  static constexpr int LO_SLOT = BLO_IN_STAGE ? A_TILE : RAW;
+  static constexpr int RAW_STAGES = BLO_IN_STAGE ? (CTAS == 1 ? 3 : 5) : (CTAS == 1 ? 4 : 6);
   static constexpr int LO_STAGES = 2;
-  static constexpr int SMEM = (RAW_STAGES + LO_STAGES) * RAW + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM = RAW_STAGES * STAGE + LO_STAGES * LO_SLOT + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct Prob {
@@ -65,13 +75,14 @@ struct Prob {
   long long ldaux;
   int M, N, K;
   float alpha;
-  int act, accumulate, k_splits, a_k, b_k;
+  int act, accumulate, k_splits, a_k, b_k, has_blo;
   int tiles_m, tiles_n, kb_total, kb_per, tile_begin, tile_count;
 };
 
 struct alignas(64) Params {
   CUtensorMap tmA[MAX_PROBLEMS];
   CUtensorMap tmB[MAX_PROBLEMS];
+  CUtensorMap tmBlo[MAX_PROBLEMS];      // pre-split lo copy of B (weights), when the problem has one
   CUtensorMap tmC[MAX_PROBLEMS];
   Prob p[MAX_PROBLEMS];
   int count, total_tiles;
@@ -113,14 +124,16 @@ __device__ __forceinline__ float split_lo(float x) {
 #endif
 }
 
-template <int CTAS>
+// SINGLE: one tensor-core pass per product (PHC_GEMM_TF32_SINGLE_PASS) -- a compile-time variant so the 3xTF32 issue loop carries
+// no run-time mode test
+template <int CTAS, bool SINGLE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc5s_kernel(const __grid_constant__ Params P) {
   using C = Cfg<CTAS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* lo_smem = smem + C::RAW_STAGES * C::RAW;
-  uint8_t* epi_smem = lo_smem + C::LO_STAGES * C::RAW;
+  uint8_t* lo_smem = smem + C::RAW_STAGES * C::STAGE;          // A lo ring
+  uint8_t* epi_smem = lo_smem + C::LO_STAGES * C::LO_SLOT;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPI_BYTES);     // [R] TMA bytes landed (local)
   uint64_t* raw_empty = full_bar + C::RAW_STAGES;                            // [R] MMAs that read the raw stage are done
   uint64_t* lo_full = raw_empty + C::RAW_STAGES;                             // [L] lo slot written (all splitter warps; leader's copy)
@@ -144,7 +157,10 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
   }
   if (warp == 5) { if (CTAS == 2) tmem_alloc_2cta(tmem_slot, 2 * BN); else tmem_alloc(tmem_slot, 2 * BN); }
   if (warp == 4 && lane == 0) {
-    for (int g = 0; g < P.count; ++g) { prefetch_tensormap(&P.tmA[g]); prefetch_tensormap(&P.tmB[g]); prefetch_tensormap(&P.tmC[g]); }
+    for (int g = 0; g < P.count; ++g) {
+      prefetch_tensormap(&P.tmA[g]); prefetch_tensormap(&P.tmB[g]); prefetch_tensormap(&P.tmC[g]);
+      if (P.p[g].has_blo) prefetch_tensormap(&P.tmBlo[g]);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -160,15 +176,16 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
       const Prob& q = P.p[tl.g];
       const CUtensorMap* tA = &P.tmA[tl.g];
       const CUtensorMap* tB = &P.tmB[tl.g];
+      const CUtensorMap* tBlo = &P.tmBlo[tl.g];
       const int nb0 = tl.n0 + (int)rank * C::B_ROWS;
-      const bool ak = q.a_k != 0, bk = q.b_k != 0;
+      const bool ak = q.a_k != 0, bk = q.b_k != 0, blo = q.has_blo != 0 && !SINGLE && C::BLO_IN_STAGE;
       for (int i = 0; i < tl.nkb; ++i, ++it) {
         const int s = it % C::RAW_STAGES;
         if (it >= (uint32_t)C::RAW_STAGES) mbar_wait(raw_empty + s, ((it / C::RAW_STAGES) - 1) & 1);
-        uint8_t* st = smem + s * C::RAW;
+        uint8_t* st = smem + s * C::STAGE;
         const int k0 = (tl.kb_begin + i) * BK;
         if (elected) {
-          mbar_expect_tx(full_bar + s, C::RAW);
+          mbar_expect_tx(full_bar + s, blo ? C::RAW + C::B_TILE : C::RAW);
           if (ak) tma_load_2d(st, tA, full_bar + s, k0, tl.m0);
           else {
 #pragma unroll
@@ -178,6 +195,14 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
           else {
 #pragma unroll
             for (int j = 0; j < C::B_ROWS / 32; ++j) tma_load_2d(st + A_TILE + j * 4096, tB, full_bar + s, nb0 + 32 * j, k0);
+          }
+          if (blo) {                                     // the pre-split lo tile of the weights, same boxes, into the stage's B lo area
+            uint8_t* sb = st + A_TILE + C::B_TILE;
+            if (bk) tma_load_2d(sb, tBlo, full_bar + s, k0, nb0);
+            else {
+#pragma unroll
+              for (int j = 0; j < C::B_ROWS / 32; ++j) tma_load_2d(sb + j * 4096, tBlo, full_bar + s, nb0 + 32 * j, k0);
+            }
           }
         }
         __syncwarp();
@@ -203,18 +228,18 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
         for (int i = 0; i < tl.nkb; ++i, ++it) {
           const int s = it % C::RAW_STAGES, l = it % C::LO_STAGES;
           mbar_wait(full_bar + s, (it / C::RAW_STAGES) & 1);        // own raw tiles (the peer's are implied by its splitters)
-          if (!P.single_pass) mbar_wait(lo_full + l, (it / C::LO_STAGES) & 1);   // lo tiles of both CTAs written and fenced
+          if (!SINGLE) mbar_wait(lo_full + l, (it / C::LO_STAGES) & 1);   // lo tiles of both CTAs written and fenced
           tc_fence_after();
-          const uint32_t st = s32(smem + s * C::RAW), sl = s32(lo_smem + l * C::RAW);
+          const uint32_t st = s32(smem + s * C::STAGE), sl = s32(lo_smem + l * C::LO_SLOT);
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
             const uint64_t dAh = smem_desc(st + kk * a_step, a_lbo, a_sbo, a_lt);
             const uint64_t dAl = smem_desc(sl + kk * a_step, a_lbo, a_sbo, a_lt);
             const uint64_t dBh = smem_desc(st + A_TILE + kk * b_step, b_lbo, b_sbo, b_lt);
-            const uint64_t dBl = smem_desc(sl + A_TILE + kk * b_step, b_lbo, b_sbo, b_lt);
+            const uint64_t dBl = smem_desc((C::BLO_IN_STAGE ? st + A_TILE + C::B_TILE : sl + A_TILE) + kk * b_step, b_lbo, b_sbo, b_lt);
             const uint32_t first = (i > 0 || kk > 0) ? 1u : 0u;
             if (elected) {
-              if (P.single_pass) {
+              if (SINGLE) {
                 if (CTAS == 2) umma_tf32_2cta(tmem_d, dAh, dBh, idesc, first); else umma_tf32(tmem_d, dAh, dBh, idesc, first);
               } else if (CTAS == 2) {
                 umma_tf32_2cta(tmem_d, dAl, dBh, idesc, first);
@@ -228,8 +253,8 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
             }
           }
           if (elected) {
-            if (CTAS == 2) { umma_commit_2cta(raw_empty + s); if (!P.single_pass) umma_commit_2cta(lo_empty + l); }   // frees both slots (in both CTAs)
-            else { umma_commit(raw_empty + s); if (!P.single_pass) umma_commit(lo_empty + l); }
+            if (CTAS == 2) { umma_commit_2cta(raw_empty + s); if (!SINGLE) umma_commit_2cta(lo_empty + l); }   // frees both slots (in both CTAs)
+            else { umma_commit(raw_empty + s); if (!SINGLE) umma_commit(lo_empty + l); }
           }
           __syncwarp();
         }
@@ -241,23 +266,38 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
     // ===================== splitters: lo tile of every landed stage =====================
     const int tid = threadIdx.x - 6 * 32;
     constexpr int NT = NUM_SPLIT_WARPS * 32;
-    constexpr int PER = C::RAW / 16 / NT;                     // float4 per thread per stage (8 or 6)
-    static_assert(PER * NT * 16 == C::RAW, "stage does not divide over the splitter threads");
+    constexpr int PER_A = A_TILE / 16 / NT, PER_B = C::B_TILE / 16 / NT;      // float4 per thread: 4 of A, 4 (2) of B
+    static_assert(PER_A * NT * 16 == A_TILE && PER_B * NT * 16 == C::B_TILE, "tiles do not divide over the splitter threads");
     uint32_t it = 0;
-    for (int t = unit; !P.single_pass && t < P.total_tiles; t += num_units) {
+    for (int t = unit; !SINGLE && t < P.total_tiles; t += num_units) {
       const Tile tl = decode<CTAS>(P, t, (int)rank);
+      const bool split_b = P.p[tl.g].has_blo == 0 || !C::BLO_IN_STAGE;          // activations as B: their lo tile is made here, into the stage itself
       for (int i = 0; i < tl.nkb; ++i, ++it) {
         const int s = it % C::RAW_STAGES, l = it % C::LO_STAGES;
         mbar_wait(full_bar + s, (it / C::RAW_STAGES) & 1);
-        const uint32_t raw = s32(smem + s * C::RAW) + (uint32_t)tid * 16u;
-        const uint32_t lo = s32(lo_smem + l * C::RAW) + (uint32_t)tid * 16u;
-        float4 v[PER];
+        const uint32_t raw = s32(smem + s * C::STAGE) + (uint32_t)tid * 16u;
+        const uint32_t lo = s32(lo_smem + l * C::LO_SLOT) + (uint32_t)tid * 16u;
+        float4 va[PER_A], vb[PER_B];
 #pragma unroll
-        for (int j = 0; j < PER; ++j) v[j] = lds128(raw + j * NT * 16);
+        for (int j = 0; j < PER_A; ++j) va[j] = lds128(raw + j * NT * 16);
+        if (split_b) {
+#pragma unroll
+          for (int j = 0; j < PER_B; ++j) vb[j] = lds128(raw + A_TILE + j * NT * 16);
+          if (C::BLO_IN_STAGE) {
+#pragma unroll
+            for (int j = 0; j < PER_B; ++j)                // the stage is this k-block's own: no further wait
+              sts128(raw + A_TILE + C::B_TILE + j * NT * 16, split_lo(vb[j].x), split_lo(vb[j].y), split_lo(vb[j].z), split_lo(vb[j].w));
+          }
+        }
         if (it >= (uint32_t)C::LO_STAGES) mbar_wait(lo_empty + l, ((it / C::LO_STAGES) - 1) & 1);   // the MMAs of k-block it - 2 are done
+        if (!C::BLO_IN_STAGE) {
 #pragma unroll
-        for (int j = 0; j < PER; ++j)
-          sts128(lo + j * NT * 16, split_lo(v[j].x), split_lo(v[j].y), split_lo(v[j].z), split_lo(v[j].w));
+          for (int j = 0; j < PER_B; ++j)
+            sts128(lo + A_TILE + j * NT * 16, split_lo(vb[j].x), split_lo(vb[j].y), split_lo(vb[j].z), split_lo(vb[j].w));
+        }
+#pragma unroll
+        for (int j = 0; j < PER_A; ++j)
+          sts128(lo + j * NT * 16, split_lo(va[j].x), split_lo(va[j].y), split_lo(va[j].z), split_lo(va[j].w));
         fence_proxy_async_smem();                              // generic-proxy writes -> visible to the tensor core's reads
         __syncwarp();
         if (elected) { if (CTAS == 2) mbar_arrive_remote_leader(lo_full + l); else mbar_arrive(lo_full + l); }
@@ -417,7 +457,8 @@ extern "C" int phc_gemm_group(const PhcGemmDesc* d, int32_t count, void* stream)
     if (ks > 1 && (!g.accumulate || g.act || g.aux)) { phc_set_error("phc_gemm_group: split-K needs accumulate=1 and a linear epilogue"); return PHC_ERR_INVALID_ARG; }
     Prob& q = P.p[n];
     q.bias = g.bias; q.aux = g.aux; q.ldaux = g.ldaux; q.M = g.M; q.N = g.N; q.K = g.K; q.alpha = g.alpha; q.act = g.act;
-    q.accumulate = g.accumulate ? 1 : 0; q.a_k = g.a_kmajor ? 1 : 0; q.b_k = g.b_kmajor ? 1 : 0;
+    q.accumulate = g.accumulate ? 1 : 0; q.a_k = g.a_kmajor ? 1 : 0; q.b_k = g.b_kmajor ? 1 : 0; q.has_blo = g.B_lo ? 1 : 0;
+    if (g.B_lo && (reinterpret_cast<uintptr_t>(g.B_lo) & 15)) { phc_set_error("phc_gemm_group: B_lo must be 16-byte aligned"); return PHC_ERR_INVALID_ARG; }
     q.tiles_m = (g.M + BM * ctas - 1) / (BM * ctas);
     q.tiles_n = (g.N + BN - 1) / BN;
     q.kb_total = (g.K + BK - 1) / BK;
@@ -432,6 +473,9 @@ extern "C" int phc_gemm_group(const PhcGemmDesc* d, int32_t count, void* stream)
                     : make_map(&P.tmA[n], g.A, g.lda, (uint64_t)g.M, (uint64_t)g.K, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     ok = ok && (q.b_k ? make_map(&P.tmB[n], g.B, g.ldb, (uint64_t)g.K, (uint64_t)g.N, 32, brows, CU_TENSOR_MAP_SWIZZLE_128B)
                       : make_map(&P.tmB[n], g.B, g.ldb, (uint64_t)g.N, (uint64_t)g.K, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    if (g.B_lo)
+      ok = ok && (q.b_k ? make_map(&P.tmBlo[n], g.B_lo, g.ldb, (uint64_t)g.K, (uint64_t)g.N, 32, brows, CU_TENSOR_MAP_SWIZZLE_128B)
+                        : make_map(&P.tmBlo[n], g.B_lo, g.ldb, (uint64_t)g.N, (uint64_t)g.K, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     ok = ok && make_map(&P.tmC[n], g.C, g.ldc, (uint64_t)g.N, (uint64_t)g.M, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
     if (!ok) { phc_set_error("phc_gemm_group: cuTensorMapEncodeTiled failed"); return PHC_ERR_CUDA; }
     ++n;
@@ -452,24 +496,20 @@ extern "C" int phc_gemm_group(const PhcGemmDesc* d, int32_t count, void* stream)
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cfg.dynamicSmemBytes = Cfg<2>::SMEM;
-    static bool done = false;
-    if (!done) {
-      e = cudaFuncSetAttribute(gemm_tc5s_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM);
-      if (e != cudaSuccess) return phc_check_cuda(e, "cudaFuncSetAttribute(gemm_tc5s<2>)");
-      done = true;
-    }
-    e = cudaLaunchKernelEx(&cfg, gemm_tc5s_kernel<2>, P);
   } else {
     cfg.attrs = nullptr; cfg.numAttrs = 0;
     cfg.dynamicSmemBytes = Cfg<1>::SMEM;
-    static bool done = false;
-    if (!done) {
-      e = cudaFuncSetAttribute(gemm_tc5s_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM);
-      if (e != cudaSuccess) return phc_check_cuda(e, "cudaFuncSetAttribute(gemm_tc5s<1>)");
-      done = true;
-    }
-    e = cudaLaunchKernelEx(&cfg, gemm_tc5s_kernel<1>, P);
   }
+  using Kernel = void (*)(const Params);
+  static const Kernel kernels[4] = {gemm_tc5s_kernel<1, false>, gemm_tc5s_kernel<1, true>, gemm_tc5s_kernel<2, false>, gemm_tc5s_kernel<2, true>};
+  static bool smem_set[4] = {false, false, false, false};
+  const int ki = (ctas == 2 ? 2 : 0) + (g_single_pass ? 1 : 0);
+  if (!smem_set[ki]) {
+    e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kernels[ki]), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+    if (e != cudaSuccess) return phc_check_cuda(e, "cudaFuncSetAttribute(gemm_tc5s)");
+    smem_set[ki] = true;
+  }
+  e = cudaLaunchKernelEx(&cfg, kernels[ki], P);
   if (e != cudaSuccess) return phc_check_cuda(e, "cudaLaunchKernelEx(gemm_tc5s)");
   phc_count_launches(1);
   return phc_check_cuda(cudaGetLastError(), "gemm_tc5s_kernel launch");
@@ -481,8 +521,26 @@ extern "C" int phc_gemm_tc5s(const float* A, int64_t lda, int32_t a_kmajor, cons
   PhcGemmDesc d;
   d.A = A; d.lda = lda; d.a_kmajor = a_kmajor; d.B = B; d.ldb = ldb; d.b_kmajor = b_kmajor; d.C = C; d.ldc = ldc;
   d.M = M; d.N = N; d.K = K; d.alpha = alpha; d.bias = bias; d.act = act; d.aux = aux; d.ldaux = ldaux;
-  d.accumulate = accumulate; d.k_splits = k_splits;
+  d.accumulate = accumulate; d.k_splits = k_splits; d.B_lo = nullptr;
   return phc_gemm_group(&d, 1, stream);
+}
+
+namespace phc { namespace tc5 { namespace smem_split {
+__global__ void split_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) lo[i] = split_lo(x[i]);
+}
+}}}
+
+extern "C" int phc_split_lo(const float* x, float* lo, int64_t n, void* stream) {
+  if (n < 0 || (n > 0 && (!x || !lo))) { phc_set_error("phc_split_lo: NULL buffer"); return PHC_ERR_INVALID_ARG; }
+  if (n == 0) return PHC_OK;
+  const int threads = 256;
+  int64_t blocks = (n + threads - 1) / threads;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  phc::tc5::smem_split::split_lo_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(x, lo, n);
+  phc_count_launches(1);
+  return phc_check_cuda(cudaGetLastError(), "split_lo_kernel launch");
 }
 
 extern "C" int phc_gemm_set_precision(int32_t mode) {      // PHC_GEMM_FP32_3XTF32 (default) | PHC_GEMM_TF32_SINGLE_PASS

@@ -202,7 +202,7 @@ class AMPAgent:
         cfg = copy.deepcopy(DEFAULT_CONFIG)
         cfg.update({k: v for k, v in config.items() if k != "network"})
         if "network" in config:
-            cfg["network"].update(config["network"])
+            cfg["network"].update(self._network_spec(config["network"]))     # a dict, or rl_games' model / builder object
         self.config = cfg
         self.base_name = base_name
         self.vec_env = cfg.get("vec_env") or self._create_vec_env(cfg)
@@ -265,6 +265,7 @@ class AMPAgent:
                                 training_prim=int(netcfg.get("training_prim", task_detail(task, "training_prim", 0))))
         if self.multi_gpu:
             D.broadcast_params(self.model.params, 0)
+            self.model._lo_version = -1                 # the collective wrote the bucket behind torch's version counter
         # mlp_precision: "fp32" (3xTF32, the reference's mixed_precision: False) or "tf32" (single tensor-core pass, opt-in)
         self.engine = MLPEngine(self.model, precision=str(cfg.get("mlp_precision", "fp32")))
         n = self.model.num_floats
@@ -473,6 +474,7 @@ class AMPAgent:
             self._rollout_graph = self._rollout_out = None      # the motion tables were re-loaded: the captured launches point at the old ones
             self._rollout_calls = 1
         if self._rollout_graph is not None:
+            self.engine.wlo(self.model.critic.layers[0])        # weights written since the last launch (checkpoint load): re-split first
             self._rollout_graph.replay()
             self._lib.phc_launch_count_add(self._rollout_graph_launches)
             return self._rollout_out
@@ -655,6 +657,8 @@ class AMPAgent:
                                          self.opt_step, st))
             if self.engine.backend == "tc5":
                 net.refresh_split()                    # hi/lo operand copies of the updated weights
+            elif self.engine.backend == "tc5s" and self.engine.presplit and self.engine.precision != "tf32":
+                net.refresh_split_lo()                 # the weights' low TF32 term, once per step instead of once per tile visit
 
     def _minibatch_pipeline(self) -> None:
         """The mini_epochs x num_minibatches updates of an epoch (amp_agent.py:460-483), software-pipelined: the gradient
@@ -810,13 +814,13 @@ class AMPAgent:
         steps = []
         for li in range(L - 1, 0, -1):
             l = hid[li]
-            steps.append(([eng.gdesc(u[li], True, net.weight(l), False, u[li - 1], Bd, l.in_dim, l.out_dim, **mask(li - 1))], None))
+            steps.append(([eng.gdesc(u[li], True, net.weight(l), False, u[li - 1], Bd, l.in_dim, l.out_dim, b_lo=eng.wlo(l), **mask(li - 1))], None))
         l0 = hid[0]
         c = self._disc_coef * self._disc_grad_penalty
 
         def penalty():
             _lib.check(lib.phc_scale_sumsq(g.data_ptr(), g.stride(0), Bd, l0.in_dim, 2.0 * c / Bd, self._stats[10:].data_ptr(), st))
-        steps.append(([eng.gdesc(u[0], True, net.weight(l0), False, g, Bd, l0.in_dim, l0.out_dim)], penalty))
+        steps.append(([eng.gdesc(u[0], True, net.weight(l0), False, g, Bd, l0.in_dim, l0.out_dim, b_lo=eng.wlo(l0))], penalty))
         for li in range(L):
             l = hid[li]
             src = g if li == 0 else e[li - 1]
@@ -824,7 +828,7 @@ class AMPAgent:
             if li == L - 1:
                 after = lambda: eng.colsum(e[L - 1], Bd, hid[L - 1].out_dim, net.weight(head, True))
             steps.append(([eng.gdesc(u[li], False, src, False, net.weight(l, True), l.out_dim, l.in_dim, Bd, accumulate=True, k_splits=group_splits(Bd)),
-                           eng.gdesc(src, True, net.weight(l), True, e[li], Bd, l.out_dim, l.in_dim, **mask(li))], after))
+                           eng.gdesc(src, True, net.weight(l), True, e[li], Bd, l.out_dim, l.in_dim, b_lo=eng.wlo(l), **mask(li))], after))
         return steps
 
     def _disc_grad_penalty_backward(self, x_demo: torch.Tensor, h_demo, Bd: int) -> None:

@@ -122,7 +122,7 @@ extern "C" int emu_amp_obs_demo(const PhcMotionLib* lib, const int64_t* ids, con
     a.flags = flags; a.num_key_bodies = nk; a.num_amp_joints = nj; a.out = out; a.out_stride = out_stride; a.only_where = only_where;
     for (int i = 0; i < PHC_MAX_AMP_JOINTS; ++i) a.amp_joints[i] = i < nj ? amp_joints[i] : -1;
     for (int i = 0; i < PHC_MAX_KEY_BODIES; ++i) a.key_bodies[i] = i < nk ? key_bodies[i] : -1;
-    a.slot_offset = so;
+    a.slot_offset = so; a.slot_offset_dev = nullptr;
     emu_warps(n * num_steps, [&] { phc::wide::amp_demo_wide_kernel(a); });
   } else {
     phc::AmpDemoArgs a;
@@ -130,7 +130,7 @@ extern "C" int emu_amp_obs_demo(const PhcMotionLib* lib, const int64_t* ids, con
     a.flags = flags; a.num_key_bodies = nk; a.num_amp_joints = nj; a.out = out; a.out_stride = out_stride; a.only_where = only_where;
     for (int i = 0; i < PHC_MAX_AMP_JOINTS; ++i) a.amp_joints[i] = i < nj ? amp_joints[i] : -1;
     for (int i = 0; i < PHC_MAX_KEY_BODIES; ++i) a.key_bodies[i] = i < nk ? key_bodies[i] : -1;
-    a.slot_offset = so;
+    a.slot_offset = so; a.slot_offset_dev = nullptr;
     emu_warps(n * num_steps, [&] { phc::amp_demo_kernel(a); });
   }
   return 0;

@@ -38,7 +38,9 @@ def test_reset_then_step_match_oracle():
     bp, br, bv, bw = body[..., 0:3], body[..., 3:7], body[..., 7:10], body[..., 10:13]
     exp_obs = torch.cat((O.self_obs(bp, br, bv, bw), O.task_obs_v6(bp[:, 0], br[:, 0], bp, br, bv, bw, nxt["rg_pos"], nxt["rb_rot"],
                                                                      nxt["body_vel"], nxt["body_ang_vel"])), dim=-1)
-    close(obs.cpu(), exp_obs, atol=2e-6, what="obs after reset")
+    # 5e-6: env_step.cu is compiled with FMA contraction on, the oracle rounds every product; the angular-velocity differences (values
+    # of order 1-10, rotated into the heading frame) carry a few ulps of that (seen: 1 of 186800 entries at 3.1e-6)
+    close(obs.cpu(), exp_obs, atol=5e-6, what="obs after reset")
 
     # one env step on a fresh simulator snapshot
     hist = task._amp_obs_buf.cpu().clone()
@@ -46,7 +48,7 @@ def test_reset_then_step_match_oracle():
     torch.cuda.synchronize()
     exp = O.env_step(tab, cfg, task._rigid_body_state_reshaped.cpu(), task._dof_state.cpu(), task.dof_force_tensor.cpu(),
                      task.progress_buf.cpu(), ids, t0, torch.zeros(n), torch.zeros(n, 3), hist)
-    close(task.obs_buf.cpu(), exp["obs"], atol=2e-6, what="obs")
+    close(task.obs_buf.cpu(), exp["obs"], atol=5e-6, what="obs")
     close(task.rew_buf.cpu(), exp["rew"], what="rew")
     close(task.reset_buf.cpu(), exp["reset"], what="reset")
     close(task._amp_obs_buf.cpu(), exp["amp_obs_buf"], what="amp window")

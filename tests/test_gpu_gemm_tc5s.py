@@ -188,3 +188,52 @@ def test_single_pass_tf32_mode_has_its_own_tolerance_and_switches_back():
         _lib.check(lib.phc_gemm_set_precision(_lib.PHC_GEMM_FP32_3XTF32))
     tc5s(padded(A), True, padded(B), True, C3b, M, N, K, bias=bias.to(DEV))
     assert torch.equal(C3, C3b)
+
+
+def _group(descs):
+    lib = _lib.load()
+    arr = (_lib.PhcGemmDesc * len(descs))(*descs)
+    _lib.check(lib.phc_gemm_group(arr, len(descs), None), "phc_gemm_group")
+    torch.cuda.synchronize()
+
+
+def _desc(A, a_k, B, b_k, Cm, M, N, K, bias=None, act=0, aux=None, b_lo=None):
+    return _lib.PhcGemmDesc(A.data_ptr(), A.stride(0), int(a_k), B.data_ptr(), B.stride(0), int(b_k), Cm.data_ptr(), Cm.stride(0), M, N, K, 1.0,
+                            None if bias is None else bias.data_ptr(), act, None if aux is None else aux.data_ptr(),
+                            0 if aux is None else aux.stride(0), 0, 1, None if b_lo is None else b_lo.data_ptr())
+
+
+def test_presplit_weight_operand_is_bit_identical_to_the_in_kernel_split():
+    """PhcGemmDesc.B_lo (phc_split_lo of the weights, loaded by TMA) against the splitter warps' own lo tile: the same numbers go to
+    the tensor core, so the products are equal bit for bit -- K-major B (forward), MN-major B (input gradient), ragged edges, and one
+    grouped launch that mixes problems with and without a pre-split operand."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    cases = []
+    for (M, N, K, b_k) in [(300, 200, 934, True), (256, 936, 1024, False), (4096, 512, 1024, True), (130, 69, 100, False), (5, 3, 7, True)]:
+        A = padded(torch.randn(M, K, generator=g))
+        B = padded(torch.randn(N, K, generator=g) if b_k else torch.randn(K, N, generator=g))
+        # lo over the whole padded allocation, like the parameter bucket
+        flatB = B._base if B._base is not None else B
+        lo_full = torch.empty_like(flatB)
+        _lib.check(lib.phc_split_lo(flatB.data_ptr(), lo_full.data_ptr(), flatB.numel(), None), "phc_split_lo")
+        lo = lo_full[:, :B.shape[1]] if lo_full.dim() == 2 else lo_full
+        assert lo.stride(0) == B.stride(0)
+        # phc_split_lo restated on the host: lo = rna_tf32(x - trunc_tf32(x))
+        xb = flatB.cpu().view(torch.int32)
+        hi = (xb & -8192).view(torch.float32)
+        d = (flatB.cpu() - hi).view(torch.int32)
+        ref = ((d + 0x1000) & -8192).view(torch.float32)
+        assert torch.equal(lo_full.cpu(), ref)
+        C0, C1 = torch.zeros(M, round4(N), device=DEV), torch.zeros(M, round4(N), device=DEV)
+        cases.append((A, B, lo, C0, C1, M, N, K, b_k))
+    for A, B, lo, C0, C1, M, N, K, b_k in cases:
+        _group([_desc(A, True, B, b_k, C0, M, N, K)])
+        _group([_desc(A, True, B, b_k, C1, M, N, K, b_lo=lo)])
+        assert torch.equal(C0, C1), (M, N, K, b_k)
+    # mixed group: problems 0, 2, 4 pre-split, 1 and 3 not
+    for c in cases:
+        c[4].zero_()
+    _group([_desc(A, True, B, b_k, C1, M, N, K, b_lo=lo if i % 2 == 0 else None) for i, (A, B, lo, C0, C1, M, N, K, b_k) in enumerate(cases)])
+    for A, B, lo, C0, C1, M, N, K, b_k in cases:
+        assert torch.equal(C0, C1), ("group", M, N, K, b_k)
