@@ -417,6 +417,9 @@ PHC_API int phc_gemm_tc5s(const float* A, int64_t lda, int32_t a_kmajor, const f
 PHC_API int phc_gemm_set_precision(int32_t mode);
 /* tile configuration switch (tests / tools): 1 = 128 x 128 tile per CTA, 2 = 256 x 128 tile per CTA pair, 0 = default */
 PHC_API int phc_gemm_tc5s_set_ctas(int32_t ctas);
+/* tile order of the one-CTA kernel (tests / tools): 1 = tiles drawn from a global counter (default; env PHC_TC5S_SCHED=static turns it
+ * off), 0 = static striding (tile t on CTA t mod grid), -1 = back to the default */
+PHC_API int phc_gemm_tc5s_set_sched(int32_t mode);
 /* Humanoid._action_to_pd_targets (phc/env/tasks/humanoid.py:1711-1713) as pre_physics_step applies it (:1540-1556):
  *   out[e, d] = pd_action_offset[d] + pd_action_scale[d] * action(e, d)        (product rounded, then the sum)
  * dof_of_action (device int32 [num_dofs], optional): reduce_action -- the action column that drives dof d, or -1 (action 0);
@@ -428,6 +431,11 @@ PHC_API int phc_pd_targets(const float* actions, int64_t lda, int64_t n, int32_t
 /* out[n] (+)= alpha * sum_m X[m*ld + n]   (bias gradients) */
 PHC_API int phc_colsum(const float* X, int64_t ld, int32_t M, int32_t N, float alpha, float* out, int32_t accumulate,
                void* stream);
+/* the same for up to PHC_GEMM_GROUP_MAX matrices in ONE launch (the bias gradients of all stacks at one layer depth):
+ * out[n] += alpha * sum_m X[m, n] (always accumulating: `out` holds zeros or earlier contributions).  X 16-byte aligned, ld a multiple
+ * of 4 floats and >= N rounded up to 4 (the 4-padded activation workspaces). */
+typedef struct PhcColsumDesc { const float* X; int64_t ld; int32_t M, N; float alpha; float* out; } PhcColsumDesc;
+PHC_API int phc_colsum_group(const PhcColsumDesc* problems, int32_t count, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Learner-side element-wise / reduction kernels (between the GEMMs of the PPO + AMP update)

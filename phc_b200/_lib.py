@@ -82,6 +82,10 @@ class PhcGemmDesc(C.Structure):
                 ("B_lo", _p)]
 
 
+class PhcColsumDesc(C.Structure):
+    _fields_ = [("X", _p), ("ld", C.c_int64), ("M", C.c_int32), ("N", C.c_int32), ("alpha", C.c_float), ("out", _p)]
+
+
 PHC_GEMM_GROUP_MAX = 8
 PHC_GEMM_FP32_3XTF32, PHC_GEMM_TF32_SINGLE_PASS = 0, 1
 
@@ -129,7 +133,9 @@ SIGNATURES = {
     "phc_gemm_tc5s": (C.c_int, [_p, C.c_int64, C.c_int32, _p, C.c_int64, C.c_int32, _p, C.c_int64, C.c_int32, C.c_int32,
                                 C.c_int32, C.c_float, _p, C.c_int32, _p, C.c_int64, C.c_int32, C.c_int32, _p]),
     "phc_gemm_tc5s_set_ctas": (C.c_int, [C.c_int32]),
+    "phc_gemm_tc5s_set_sched": (C.c_int, [C.c_int32]),
     "phc_gemm_set_precision": (C.c_int, [C.c_int32]),
+    "phc_colsum_group": (C.c_int, [C.POINTER(PhcColsumDesc), C.c_int32, _p]),
     "phc_colsum": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p, C.c_int32, _p]),
     "phc_rms_apply": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, _p, _p, C.c_float, C.c_int32, _p, C.c_int64, _p, _p]),
     "phc_rms_apply_update": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int32, _p, _p, C.c_float, _p, C.c_int64, _p, _p, _p, _p, _p, _p]),

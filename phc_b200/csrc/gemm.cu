@@ -234,7 +234,85 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
   }
 }
 
+// grouped column sums: up to PHC_GEMM_GROUP_MAX matrices in one launch (the bias gradients of every stack at one layer depth).
+// A block is 8 rows x 32 lanes, each lane owns 4 consecutive columns (one 16-byte load per row): 128 columns x 256 rows per block,
+// 8 independent loads in flight per thread; the 8 row partials meet in shared memory and leave as one atomicAdd per column.
+struct ColsumGroup {
+  const float* X[PHC_GEMM_GROUP_MAX];
+  float* out[PHC_GEMM_GROUP_MAX];
+  int64_t ld[PHC_GEMM_GROUP_MAX];
+  int32_t M[PHC_GEMM_GROUP_MAX], N[PHC_GEMM_GROUP_MAX], block_begin[PHC_GEMM_GROUP_MAX + 1], col_chunks[PHC_GEMM_GROUP_MAX];
+  float alpha[PHC_GEMM_GROUP_MAX];
+  int32_t count;
+};
+constexpr int CS_ROWS = 256;
+
+__global__ void __launch_bounds__(256) colsum_group_kernel(const __grid_constant__ ColsumGroup G) {
+  __shared__ float4 part[8][32];
+  int g = 0;
+  while (g + 1 < G.count && (int)blockIdx.x >= G.block_begin[g + 1]) ++g;
+  const int b = blockIdx.x - G.block_begin[g];
+  const int cc = b % G.col_chunks[g], rc = b / G.col_chunks[g];
+  const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c0 = cc * 128 + lane * 4;
+  const int N = G.N[g], M = G.M[g];
+  const int64_t ld = G.ld[g];
+  const float* __restrict__ X = G.X[g];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c0 < N) {
+    const int r_end = min(M, (rc + 1) * CS_ROWS);
+    int r = rc * CS_ROWS + ry;
+    for (; r + 56 < r_end; r += 64) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(X + (int64_t)(r + 8 * u) * ld + c0));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    for (; r < r_end; r += 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(X + (int64_t)r * ld + c0));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  part[ry][lane] = acc;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int c = cc * 128 + threadIdx.x;
+    if (c < N) {
+      const float* p = reinterpret_cast<const float*>(&part[0][0]) + threadIdx.x;
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += p[i * 128];
+      atomicAdd(G.out[g] + c, t * G.alpha[g]);
+    }
+  }
+}
+
 }  // namespace phc
+
+extern "C" int phc_colsum_group(const PhcColsumDesc* d, int32_t count, void* stream) {
+  if (!d || count < 1 || count > PHC_GEMM_GROUP_MAX) { phc_set_error("phc_colsum_group: 1 <= count <= PHC_GEMM_GROUP_MAX problems"); return PHC_ERR_INVALID_ARG; }
+  phc::ColsumGroup G;
+  int n = 0, blocks = 0;
+  for (int i = 0; i < count; ++i) {
+    const PhcColsumDesc& q = d[i];
+    if (!q.X || !q.out || q.M < 0 || q.N < 0) { phc_set_error("phc_colsum_group: bad problem (NULL pointer or negative size)"); return PHC_ERR_INVALID_ARG; }
+    if ((q.ld & 3) || q.ld < ((q.N + 3) & ~3) || (reinterpret_cast<uintptr_t>(q.X) & 15)) {
+      phc_set_error("phc_colsum_group: X must be 16-byte aligned with a leading dimension that is a multiple of 4 floats and >= N rounded up to 4");
+      return PHC_ERR_INVALID_ARG;
+    }
+    if (q.M == 0 || q.N == 0) continue;
+    G.X[n] = q.X; G.out[n] = q.out; G.ld[n] = q.ld; G.M[n] = q.M; G.N[n] = q.N; G.alpha[n] = q.alpha;
+    G.col_chunks[n] = (q.N + 127) / 128;
+    G.block_begin[n] = blocks;
+    blocks += G.col_chunks[n] * ((q.M + phc::CS_ROWS - 1) / phc::CS_ROWS);
+    ++n;
+  }
+  if (n == 0) return PHC_OK;
+  G.block_begin[n] = blocks; G.count = n;
+  phc::colsum_group_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(G); phc_count_launches(1);
+  return phc_check_cuda(cudaGetLastError(), "colsum_group_kernel launch");
+}
 
 extern "C" int phc_gemm(const float* A, int64_t lda, int32_t a_kmajor, const float* B, int64_t ldb, int32_t b_kmajor,
                         float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha, const float* bias,

@@ -46,27 +46,30 @@ constexpr int EPI_BUF = 32 * 32 * 4;                  // one 32 x 32 fp32 chunk 
 constexpr int EPI_BYTES = 4 * 2 * EPI_BUF;            // 4 warps, double buffered
 constexpr int MAX_PROBLEMS = PHC_GEMM_GROUP_MAX;
 
+constexpr int SCHED_DEPTH = 4;      // tile ids in flight between the producer warp and the slowest consumer role
+
 template <int CTAS>
 struct Cfg {
   static constexpr int B_ROWS = BN / CTAS;
   static constexpr int B_TILE = B_ROWS * BK * 4;
   static constexpr int RAW = A_TILE + B_TILE;         // bytes of the raw A and B tiles of a stage
-  // A stage of the TMA ring is [A raw | B raw | B lo]: the B lo tile either arrives by TMA (weights: a pre-split `lo` copy of the
-  // parameter bucket exists, PhcGemmDesc.B_lo) or is written by the splitters; only the A lo tile -- always produced here -- lives in
-  // its own two-slot ring (a lo tile is needed only from its split to the MMAs of its k-block).  The ring depth is what shared memory
-  // leaves: 3 (5) stages of 48 (32) KB.
-  // -DPHC_TC5S_BLO_IN_RING (A/B build): the layout this replaced -- stages hold the raw tiles only (4 / 6 of them), both lo tiles go to
-  // the lo ring, B_lo is ignored.
-#ifdef PHC_TC5S_BLO_IN_RING
-  static constexpr bool BLO_IN_STAGE = false;
-#else
+  // Default layout: the TMA ring holds the raw tiles only (4 / 6 stages of 32 / 24 KB), both lo tiles go to the two-slot lo ring (a lo
+  // tile is needed only from its split to the MMAs of its k-block).
+  // -DPHC_TC5S_BLO_IN_STAGE (A/B build, measured and not adopted -- profiles/gemm_r2_ab_layout.md): a stage is [A raw | B raw | B lo]
+  // and the B lo tile may arrive by TMA from a pre-split copy of the weights (PhcGemmDesc.B_lo) instead of being made by the
+  // splitters; the lo ring then holds A lo only.  Shared memory leaves 3 (5) such stages: single GEMMs gain 4-8 % from the halved
+  // splitter traffic, the grouped launches of the learner lose 2-4 % to the shallower ring and the 50 % higher L2 -> shared-memory
+  // traffic.  In the default layout B_lo is accepted and ignored.
+#ifdef PHC_TC5S_BLO_IN_STAGE
   static constexpr bool BLO_IN_STAGE = true;
+#else
+  static constexpr bool BLO_IN_STAGE = false;
 #endif
   static constexpr int STAGE = BLO_IN_STAGE ? A_TILE + 2 * B_TILE : RAW;
   static constexpr int LO_SLOT = BLO_IN_STAGE ? A_TILE : RAW;
   static constexpr int RAW_STAGES = BLO_IN_STAGE ? (CTAS == 1 ? 3 : 5) : (CTAS == 1 ? 4 : 6);
   static constexpr int LO_STAGES = 2;
-  static constexpr int SMEM = RAW_STAGES * STAGE + LO_STAGES * LO_SLOT + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM = RAW_STAGES * STAGE + LO_STAGES * LO_SLOT + EPI_BYTES + 1024 /*align slack*/ + 320 /*barriers, scheduler ring*/;
 };
 
 struct Prob {
@@ -86,6 +89,7 @@ struct alignas(64) Params {
   CUtensorMap tmC[MAX_PROBLEMS];
   Prob p[MAX_PROBLEMS];
   int count, total_tiles;
+  unsigned int* sched;  // dynamic tile scheduler: {next tile, CTAs done} in global memory (both zero between launches); NULL = static striding
   int single_pass;      // 1: one tensor-core product per fp32 product (plain TF32, ~1e-3 relative): no lo tiles, no splitters
 };
 
@@ -140,7 +144,15 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
   uint64_t* lo_empty = lo_full + C::LO_STAGES;                               // [L] MMAs that read the lo slot are done
   uint64_t* tmem_full = lo_empty + C::LO_STAGES;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;             // [2] (pair mode: the leader's copies are the ones waited on)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* sched_full = tmem_empty + 2;            // [SCHED_DEPTH] tile id published by the producer warp
+  uint64_t* sched_empty = sched_full + SCHED_DEPTH; // [SCHED_DEPTH] every consumer warp has read it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_empty + SCHED_DEPTH);
+  volatile int* sched_tile = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [SCHED_DEPTH]
+  // Tile order.  Static: unit u takes tiles u, u + units, ...  Dynamic (one-CTA tiles): the producer warp draws the next tile from a
+  // global counter and hands it to the other roles through a small shared-memory ring, so a CTA that got long tiles (the K = 1960
+  // discriminator layer next to K = 934 actor / critic tiles in one launch) or shares its SM with another stream's kernel simply
+  // draws fewer of them.
+  const bool dyn = CTAS == 1 && P.sched != nullptr;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;     // shfl: provably warp-uniform
   const bool elected = elect_one();                 // the one lane of each warp that issues TMA / tcgen05 / barrier arrivals
@@ -152,6 +164,7 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
     for (int s = 0; s < C::RAW_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(raw_empty + s, 1); }
     for (int s = 0; s < C::LO_STAGES; ++s) { mbar_init(lo_full + s, NUM_SPLIT_WARPS * CTAS); mbar_init(lo_empty + s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 4 * CTAS); }
+    for (int a = 0; a < SCHED_DEPTH; ++a) { mbar_init(sched_full + a, 1); mbar_init(sched_empty + a, SINGLE ? 5 : 5 + NUM_SPLIT_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -167,11 +180,40 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
   if (CTAS == 2) cluster_sync_all();                // peer barriers initialised, both TMEM halves allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // i-th tile of this CTA for a consumer role (MMA, splitters, epilogue): the whole warp waits, one lane acknowledges
+  auto consumer_tile = [&](uint32_t i) -> int {
+    if (!dyn) return unit + (int)i * num_units;
+    const uint32_t a = i % SCHED_DEPTH;
+    mbar_wait(sched_full + a, (i / SCHED_DEPTH) & 1);
+    const int t = sched_tile[a];
+    __syncwarp();
+    if (elected) mbar_arrive(sched_empty + a);
+    return t;
+  };
 
   if (warp == 4) {
     // ===================== TMA producer: raw fp32 tiles (whole warp walks the loop, the elected lane issues) =====================
     uint32_t it = 0;                                          // k-block counter, continues across tiles
-    for (int t = unit; t < P.total_tiles; t += num_units) {
+    auto draw = [&]() -> int {                                // next tile from the global counter (one atomic per warp)
+      int v = 0;
+      if (elected) v = (int)atomicAdd(P.sched, 1u);
+      return __shfl_sync(0xffffffffu, v, __ffs(__ballot_sync(0xffffffffu, elected)) - 1);
+    };
+    int t_next = dyn ? draw() : 0;
+    for (uint32_t ti = 0;; ++ti) {
+      int t;
+      if (dyn) {
+        t = t_next;
+        const uint32_t a = ti % SCHED_DEPTH;
+        if (ti >= (uint32_t)SCHED_DEPTH) mbar_wait(sched_empty + a, ((ti / SCHED_DEPTH) - 1) & 1);
+        if (elected) { sched_tile[a] = t; mbar_arrive(sched_full + a); }      // (the terminating id is published too)
+        __syncwarp();
+        if (t >= P.total_tiles) break;
+        t_next = draw();                                      // in flight while this tile's loads are issued
+      } else {
+        t = unit + (int)ti * num_units;
+        if (t >= P.total_tiles) break;
+      }
       const Tile tl = decode<CTAS>(P, t, (int)rank);
       const Prob& q = P.p[tl.g];
       const CUtensorMap* tA = &P.tmA[tl.g];
@@ -211,8 +253,10 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
   } else if (warp == 5) {
     // ===================== MMA issuer (leader CTA; whole warp walks the loop, the elected lane issues) =====================
     if (leader) {
-      uint32_t it = 0, lt = 0;
-      for (int t = unit; t < P.total_tiles; t += num_units, ++lt) {
+      uint32_t it = 0;
+      for (uint32_t lt = 0;; ++lt) {
+        const int t = consumer_tile(lt);
+        if (t >= P.total_tiles) break;
         const Tile tl = decode<CTAS>(P, t, 0);
         const Prob& q = P.p[tl.g];
         const bool ak = q.a_k != 0, bk = q.b_k != 0;
@@ -269,7 +313,9 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
     constexpr int PER_A = A_TILE / 16 / NT, PER_B = C::B_TILE / 16 / NT;      // float4 per thread: 4 of A, 4 (2) of B
     static_assert(PER_A * NT * 16 == A_TILE && PER_B * NT * 16 == C::B_TILE, "tiles do not divide over the splitter threads");
     uint32_t it = 0;
-    for (int t = unit; !SINGLE && t < P.total_tiles; t += num_units) {
+    for (uint32_t lt = 0; !SINGLE; ++lt) {
+      const int t = consumer_tile(lt);
+      if (t >= P.total_tiles) break;
       const Tile tl = decode<CTAS>(P, t, (int)rank);
       const bool split_b = P.p[tl.g].has_blo == 0 || !C::BLO_IN_STAGE;          // activations as B: their lo tile is made here, into the stage itself
       for (int i = 0; i < tl.nkb; ++i, ++it) {
@@ -306,8 +352,10 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
   } else {
     // ===================== epilogue warps 0..3: TMEM -> registers -> swizzled smem chunk -> TMA store =====================
     uint8_t* my_buf = epi_smem + warp * 2 * EPI_BUF;
-    uint32_t lt = 0, chunk = 0;
-    for (int t = unit; t < P.total_tiles; t += num_units, ++lt) {
+    uint32_t chunk = 0;
+    for (uint32_t lt = 0;; ++lt) {
+      const int t = consumer_tile(lt);
+      if (t >= P.total_tiles) break;
       const Tile tl = decode<CTAS>(P, t, (int)rank);
       const Prob& q = P.p[tl.g];
       const CUtensorMap* tC = &P.tmC[tl.g];
@@ -413,6 +461,8 @@ gemm_tc5s_kernel(const __grid_constant__ Params P) {
     tc_fence_after();
     if (CTAS == 2) tmem_dealloc_2cta(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN);
   }
+  // the last CTA to get here puts both counters back to zero for the next launch (every CTA has drawn its terminating tile by now)
+  if (dyn && threadIdx.x == 0 && atomicInc(P.sched + 1, gridDim.x - 1) == gridDim.x - 1) { __threadfence(); P.sched[0] = 0u; }
 }
 
 // 2-D fp32 tensor map; inner dimension = the contiguous one
@@ -431,6 +481,11 @@ static bool make_map(CUtensorMap* tm, const float* base, int64_t ld, uint64_t in
 // saves no operand traffic worth its cross-CTA barrier round trips; it stays in the tree as an opt-in, parity-tested variant.
 static int g_ctas = 0;
 static int g_single_pass = 0;
+static int g_sched = -1;      // -1: not decided yet (env PHC_TC5S_SCHED = static | dynamic; default dynamic), 0 static, 1 dynamic
+// {next tile, CTAs done} pairs of the dynamic scheduler, zero at load time and put back to zero by every launch's last CTA; launches
+// rotate through them so that two launches in flight on different streams do not share a pair
+constexpr int SCHED_SLOTS = 64;
+__device__ unsigned int g_sched_counters[SCHED_SLOTS][2];
 
 }  // namespace smem_split
 }  // namespace tc5
@@ -482,6 +537,19 @@ extern "C" int phc_gemm_group(const PhcGemmDesc* d, int32_t count, void* stream)
   }
   if (n == 0) return PHC_OK;
   P.count = n; P.total_tiles = tiles; P.single_pass = g_single_pass;
+  if (g_sched < 0) { const char* v = getenv("PHC_TC5S_SCHED"); g_sched = (v && v[0] == 's') ? 0 : 1; }
+  P.sched = nullptr;
+  if (g_sched == 1 && ctas == 1) {
+    static unsigned int* base = nullptr;
+    static unsigned int launch_no = 0;
+    if (!base) {
+      void* p = nullptr;
+      cudaError_t es = cudaGetSymbolAddress(&p, g_sched_counters);
+      if (es != cudaSuccess) return phc_check_cuda(es, "cudaGetSymbolAddress(g_sched_counters)");
+      base = static_cast<unsigned int*>(p);
+    }
+    P.sched = base + 2 * (launch_no++ % SCHED_SLOTS);
+  }
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
   const int units = num_sms / ctas;
@@ -546,6 +614,12 @@ extern "C" int phc_split_lo(const float* x, float* lo, int64_t n, void* stream) 
 extern "C" int phc_gemm_set_precision(int32_t mode) {      // PHC_GEMM_FP32_3XTF32 (default) | PHC_GEMM_TF32_SINGLE_PASS
   if (mode != PHC_GEMM_FP32_3XTF32 && mode != PHC_GEMM_TF32_SINGLE_PASS) { phc_set_error("phc_gemm_set_precision: unknown mode"); return PHC_ERR_INVALID_ARG; }
   phc::tc5::smem_split::g_single_pass = mode == PHC_GEMM_TF32_SINGLE_PASS;
+  return PHC_OK;
+}
+
+extern "C" int phc_gemm_tc5s_set_sched(int32_t mode) {     // tile order of the one-CTA kernel: 0 static striding, 1 dynamic (global counter), -1 default
+  if (mode < -1 || mode > 1) { phc_set_error("phc_gemm_tc5s_set_sched: -1, 0 or 1"); return PHC_ERR_INVALID_ARG; }
+  phc::tc5::smem_split::g_sched = mode;
   return PHC_OK;
 }
 

@@ -784,8 +784,7 @@ class AMPAgent:
                     gdescs, after = gp[k]
                     descs += gdescs
                 eng.run_group(descs)
-                for dY, rows, n, out in sums:
-                    eng.colsum(dY, rows, n, out)
+                eng.colsum_group(sums)
                 if after is not None:
                     after()
             head = net.disc.head

@@ -232,7 +232,8 @@ class MLPEngine:
         if precision == "tf32" and self.backend != "tc5s":
             raise ValueError("precision='tf32' (single tensor-core pass) exists on the tc5s back end only")
         self._companions: Dict[Tuple[int, Tuple[int, ...], Tuple[int, ...]], Tuple[torch.Tensor, torch.Tensor]] = {}
-        self.presplit = os.environ.get("PHC_TC5S_PRESPLIT", "1") != "0"
+        # pre-split weight operand (PhcGemmDesc.B_lo): only the -DPHC_TC5S_BLO_IN_STAGE build of the library uses it (measured, not adopted)
+        self.presplit = os.environ.get("PHC_TC5S_PRESPLIT", "0") == "1"
         self.gemm_flops = 0.0          # algorithmic fp32 FLOPs (2 M N K) of every grouped launch so far (bench.py reads it)
         if self.backend == "tc5":
             net.refresh_split()
@@ -369,6 +370,15 @@ class MLPEngine:
         rc = self.lib.phc_colsum(X.data_ptr(), X.stride(0), M, N, alpha, out.data_ptr(), 1 if accumulate else 0, _stream())
         if rc:
             _lib.check(rc, "phc_colsum")
+
+    def colsum_group(self, items) -> None:
+        """items: [(X, M, N, out)] -- out[n] += sum_m X[m, n] for all of them in one launch (phc_colsum_group)."""
+        for i in range(0, len(items), _lib.PHC_GEMM_GROUP_MAX):
+            part = items[i:i + _lib.PHC_GEMM_GROUP_MAX]
+            arr = (_lib.PhcColsumDesc * len(part))(*[_lib.PhcColsumDesc(X.data_ptr(), X.stride(0), M, N, 1.0, out.data_ptr()) for X, M, N, out in part])
+            rc = self.lib.phc_colsum_group(arr, len(part), _stream())
+            if rc:
+                _lib.check(rc, "phc_colsum_group")
 
     # -- workspaces ----------------------------------------------------------------------------------------------
     def workspace(self, tag: str, st: MLPStack, batch: int) -> Dict[str, torch.Tensor]:

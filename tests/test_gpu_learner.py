@@ -76,6 +76,28 @@ def test_gemm_weight_grad_form(M, N, K, splits):
     assert float(cerr.max()) < 2e-6, f"colsum: {float(cerr.max()):.3e}"
 
 
+def test_grouped_colsum_matches_fp64_column_sums():
+    """phc_colsum_group: bias gradients of several stacks in one launch; ragged row / column counts, single columns, accumulation on
+    top of existing content, the fp32 criterion |err| <= tol * sum |x|."""
+    g = torch.Generator().manual_seed(5)
+    eng = MLPEngine(AMPNetwork(8, 2, 8, (4,), (4,), device=DEV))
+    shapes = [(16384, 1024), (16384, 69), (12288, 1), (300, 130), (7, 5), (257, 512), (1000, 934), (1, 1960), (33, 3)]     # > 8: two launches
+    items, refs = [], []
+    for M, N in shapes:
+        X = torch.randn(M, N, generator=g) * 2 + 0.5
+        Xp = padded(X)
+        Xp[:, N:] = 7.0                                # pad columns must not leak into the sums
+        out = torch.full((round4(N),), 0.25, device=DEV)
+        items.append((Xp, M, N, out))
+        refs.append((X.double().sum(0) + 0.25, X.double().abs().sum(0) + 0.25))
+    eng.colsum_group(items)
+    torch.cuda.synchronize()
+    for (Xp, M, N, out), (e, b) in zip(items, refs):
+        err = (out[:N].double().cpu() - e).abs() / b
+        assert float(err.max()) < 2e-6, f"colsum_group {M}x{N}: {float(err.max()):.3e}"
+        assert float((out[N:] - 0.25).abs().sum()) == 0.0
+
+
 def test_running_mean_std_vs_reference_golden():
     from phc_b200.learning.amp_agent import RunningMeanStd
     g = load("learn.npz")
@@ -236,9 +258,10 @@ def test_fused_rms_apply_update_equals_apply_then_update():
     x = (torch.randn(n_src, d, generator=g) * 3 + 1).to(DEV)
     idx = torch.randint(0, n_src, (n,), generator=g).to(DEV)
     a, b = RunningMeanStd(d, DEV), RunningMeanStd(d, DEV)
+    mean0, var0 = torch.randn(d, generator=g).double(), (torch.rand(d, generator=g) + 0.5).double()
     for r in (a, b):
-        r.running_mean.copy_(torch.randn(d, generator=g).double())
-        r.running_var.copy_((torch.rand(d, generator=g) + 0.5).double())
+        r.running_mean.copy_(mean0)
+        r.running_var.copy_(var0)
         r.count.fill_(777.0)
     frozen = a.frozen_copy()
     frozen.running_mean += 0.25                                  # the temp copy differs from the live statistics
