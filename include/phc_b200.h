@@ -417,6 +417,9 @@ PHC_API int phc_gemm_tc5s(const float* A, int64_t lda, int32_t a_kmajor, const f
 PHC_API int phc_gemm_set_precision(int32_t mode);
 /* tile configuration switch (tests / tools): 1 = 128 x 128 tile per CTA, 2 = 256 x 128 tile per CTA pair, 0 = default */
 PHC_API int phc_gemm_tc5s_set_ctas(int32_t ctas);
+/* tile shape of the one-CTA kernel (tests / tools): 256 = 128 x 256 x 16 tiles (gemm_tc5w.cu, default; env PHC_TC5_TILE=128 selects the
+ * other), 128 = 128 x 128 x 32 tiles (gemm_tc5s.cu), 0 = back to the default.  The CTA-pair configuration always uses gemm_tc5s.cu. */
+PHC_API int phc_gemm_tc5s_set_tile(int32_t width);
 /* tile order of the one-CTA kernel (tests / tools): 1 = tiles drawn from a global counter (default; env PHC_TC5S_SCHED=static turns it
  * off), 0 = static striding (tile t on CTA t mod grid), -1 = back to the default */
 PHC_API int phc_gemm_tc5s_set_sched(int32_t mode);

@@ -134,6 +134,7 @@ SIGNATURES = {
                                 C.c_int32, C.c_float, _p, C.c_int32, _p, C.c_int64, C.c_int32, C.c_int32, _p]),
     "phc_gemm_tc5s_set_ctas": (C.c_int, [C.c_int32]),
     "phc_gemm_tc5s_set_sched": (C.c_int, [C.c_int32]),
+    "phc_gemm_tc5s_set_tile": (C.c_int, [C.c_int32]),
     "phc_gemm_set_precision": (C.c_int, [C.c_int32]),
     "phc_colsum_group": (C.c_int, [C.POINTER(PhcColsumDesc), C.c_int32, _p]),
     "phc_colsum": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p, C.c_int32, _p]),

@@ -27,6 +27,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # (phc_math.cuh explains which and why; PHC_ENV_FMAD=0 builds the step kernel without any contraction for A/B checks).
 SOURCES = {
     "phc_api.cu": [],
+    "gemm_tc5w.cu": [],
     "env_step.cu": ["-fmad=false"] if os.environ.get("PHC_ENV_FMAD", "1") == "0" else [],
     "env_step_wide.cu": [],
     "motion.cu": ["-fmad=false"],

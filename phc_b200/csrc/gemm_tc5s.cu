@@ -481,6 +481,7 @@ static bool make_map(CUtensorMap* tm, const float* base, int64_t ld, uint64_t in
 // saves no operand traffic worth its cross-CTA barrier round trips; it stays in the tree as an opt-in, parity-tested variant.
 static int g_ctas = 0;
 static int g_single_pass = 0;
+static int g_tile = 0;        // 0: not decided yet (env PHC_TC5_TILE = 128 | 256; default 256 = gemm_tc5w.cu), else the tile width
 static int g_sched = -1;      // -1: not decided yet (env PHC_TC5S_SCHED = static | dynamic; default dynamic), 0 static, 1 dynamic
 // {next tile, CTAs done} pairs of the dynamic scheduler, zero at load time and put back to zero by every launch's last CTA; launches
 // rotate through them so that two launches in flight on different streams do not share a pair
@@ -491,14 +492,11 @@ __device__ unsigned int g_sched_counters[SCHED_SLOTS][2];
 }  // namespace tc5
 }  // namespace phc
 
-extern "C" int phc_gemm_group(const PhcGemmDesc* d, int32_t count, void* stream) {
+extern "C" int phc_gemm_group_wide(const PhcGemmDesc* d, int32_t count, int32_t single_pass, int32_t dynamic_sched, void* stream);
+
+static int validate_group(const PhcGemmDesc* d, int32_t count) {
   using namespace phc::tc5::smem_split;
   if (!d || count < 1 || count > MAX_PROBLEMS) { phc_set_error("phc_gemm_group: 1 <= count <= PHC_GEMM_GROUP_MAX problems"); return PHC_ERR_INVALID_ARG; }
-  if (!g_ctas) { const char* v = getenv("PHC_TC5S_CTAS"); g_ctas = (v && v[0] == '2') ? 2 : 1; }
-  const int ctas = g_ctas;
-  static Params P;      // host staging (launches are serialised by the caller's stream order; the struct is copied at launch)
-  memset(&P.p, 0, sizeof(P.p));
-  int tiles = 0, n = 0;
   for (int i = 0; i < count; ++i) {
     const PhcGemmDesc& g = d[i];
     if (!g.A || !g.B || !g.C || g.M < 0 || g.N < 0 || g.K < 1) { phc_set_error("phc_gemm_group: bad problem (NULL operand or negative size)"); return PHC_ERR_INVALID_ARG; }
@@ -506,14 +504,34 @@ extern "C" int phc_gemm_group(const PhcGemmDesc* d, int32_t count, void* stream)
     if ((g.lda & 3) || (g.ldb & 3) || (g.ldc & 3)) { phc_set_error("phc_gemm_group: leading dimensions must be multiples of 4 floats (TMA strides are 16-byte multiples)"); return PHC_ERR_INVALID_ARG; }
     for (const void* p : {(const void*)g.A, (const void*)g.B, (const void*)g.C})
       if (reinterpret_cast<uintptr_t>(p) & 15) { phc_set_error("phc_gemm_group: A, B, C must be 16-byte aligned"); return PHC_ERR_INVALID_ARG; }
-    int ks = g.k_splits < 1 ? 1 : g.k_splits;
+    const int ks = g.k_splits < 1 ? 1 : g.k_splits;
     if (g.act < 0 || g.act > PHC_ACT_MASK_BITS || ((g.act == PHC_ACT_SILU_BWD || g.act == PHC_ACT_MASK_BITS) && !g.aux)) { phc_set_error("phc_gemm_group: bad activation code"); return PHC_ERR_INVALID_ARG; }
     if (g.act >= PHC_ACT_RELU_BITS && g.aux && ((reinterpret_cast<uintptr_t>(g.aux) & 3) || g.ldaux < (g.N + 31) / 32)) { phc_set_error("phc_gemm_group: bit-mask aux needs ldaux >= ceil(N / 32) words"); return PHC_ERR_INVALID_ARG; }
     if (ks > 1 && (!g.accumulate || g.act || g.aux)) { phc_set_error("phc_gemm_group: split-K needs accumulate=1 and a linear epilogue"); return PHC_ERR_INVALID_ARG; }
+    if (g.B_lo && (reinterpret_cast<uintptr_t>(g.B_lo) & 15)) { phc_set_error("phc_gemm_group: B_lo must be 16-byte aligned"); return PHC_ERR_INVALID_ARG; }
+  }
+  return PHC_OK;
+}
+
+extern "C" int phc_gemm_group(const PhcGemmDesc* d, int32_t count, void* stream) {
+  using namespace phc::tc5::smem_split;
+  const int vrc = validate_group(d, count);
+  if (vrc != PHC_OK) return vrc;
+  if (!g_ctas) { const char* v = getenv("PHC_TC5S_CTAS"); g_ctas = (v && v[0] == '2') ? 2 : 1; }
+  if (g_sched < 0) { const char* v = getenv("PHC_TC5S_SCHED"); g_sched = (v && v[0] == 's') ? 0 : 1; }
+  if (!g_tile) { const char* v = getenv("PHC_TC5_TILE"); g_tile = (v && v[0] == '1') ? 128 : 256; }
+  const int ctas = g_ctas;
+  if (g_tile == 256 && ctas == 1) return phc_gemm_group_wide(d, count, g_single_pass, g_sched, stream);      // gemm_tc5w.cu
+  static Params P;      // host staging (launches are serialised by the caller's stream order; the struct is copied at launch)
+  memset(&P.p, 0, sizeof(P.p));
+  int tiles = 0, n = 0;
+  for (int i = 0; i < count; ++i) {
+    const PhcGemmDesc& g = d[i];
+    if (g.M == 0 || g.N == 0) continue;
+    int ks = g.k_splits < 1 ? 1 : g.k_splits;
     Prob& q = P.p[n];
     q.bias = g.bias; q.aux = g.aux; q.ldaux = g.ldaux; q.M = g.M; q.N = g.N; q.K = g.K; q.alpha = g.alpha; q.act = g.act;
     q.accumulate = g.accumulate ? 1 : 0; q.a_k = g.a_kmajor ? 1 : 0; q.b_k = g.b_kmajor ? 1 : 0; q.has_blo = g.B_lo ? 1 : 0;
-    if (g.B_lo && (reinterpret_cast<uintptr_t>(g.B_lo) & 15)) { phc_set_error("phc_gemm_group: B_lo must be 16-byte aligned"); return PHC_ERR_INVALID_ARG; }
     q.tiles_m = (g.M + BM * ctas - 1) / (BM * ctas);
     q.tiles_n = (g.N + BN - 1) / BN;
     q.kb_total = (g.K + BK - 1) / BK;
@@ -537,7 +555,6 @@ extern "C" int phc_gemm_group(const PhcGemmDesc* d, int32_t count, void* stream)
   }
   if (n == 0) return PHC_OK;
   P.count = n; P.total_tiles = tiles; P.single_pass = g_single_pass;
-  if (g_sched < 0) { const char* v = getenv("PHC_TC5S_SCHED"); g_sched = (v && v[0] == 's') ? 0 : 1; }
   P.sched = nullptr;
   if (g_sched == 1 && ctas == 1) {
     static unsigned int* base = nullptr;
@@ -614,6 +631,12 @@ extern "C" int phc_split_lo(const float* x, float* lo, int64_t n, void* stream) 
 extern "C" int phc_gemm_set_precision(int32_t mode) {      // PHC_GEMM_FP32_3XTF32 (default) | PHC_GEMM_TF32_SINGLE_PASS
   if (mode != PHC_GEMM_FP32_3XTF32 && mode != PHC_GEMM_TF32_SINGLE_PASS) { phc_set_error("phc_gemm_set_precision: unknown mode"); return PHC_ERR_INVALID_ARG; }
   phc::tc5::smem_split::g_single_pass = mode == PHC_GEMM_TF32_SINGLE_PASS;
+  return PHC_OK;
+}
+
+extern "C" int phc_gemm_tc5s_set_tile(int32_t width) {     // 128: this file's 128 x 128 x 32 tiles; 256: gemm_tc5w.cu's 128 x 256 x 16; 0 = default
+  if (width != 0 && width != 128 && width != 256) { phc_set_error("phc_gemm_tc5s_set_tile: 0, 128 or 256"); return PHC_ERR_INVALID_ARG; }
+  phc::tc5::smem_split::g_tile = width;
   return PHC_OK;
 }
 

@@ -15,12 +15,16 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.fixture(params=[1, 2], autouse=True)
+@pytest.fixture(params=[(1, 256), (1, 128), (2, 128)], ids=["wide128x256x16", "cta128x128x32", "pair256x128x32"], autouse=True)
 def ctas(request):
+    """The three tile configurations behind phc_gemm_group: gemm_tc5w.cu (default), gemm_tc5s.cu one-CTA and CTA-pair."""
     lib = _lib.load()
-    _lib.check(lib.phc_gemm_tc5s_set_ctas(request.param))
-    yield request.param
+    n, tile = request.param
+    _lib.check(lib.phc_gemm_tc5s_set_ctas(n))
+    _lib.check(lib.phc_gemm_tc5s_set_tile(tile))
+    yield n
     lib.phc_gemm_tc5s_set_ctas(0)
+    lib.phc_gemm_tc5s_set_tile(0)
 
 
 def tc5s(A, a_k, B, b_k, Cm, M, N, K, alpha=1.0, bias=None, act=0, aux=None, accumulate=False, k_splits=1):
@@ -237,3 +241,27 @@ def test_presplit_weight_operand_is_bit_identical_to_the_in_kernel_split():
     _group([_desc(A, True, B, b_k, C1, M, N, K, b_lo=lo if i % 2 == 0 else None) for i, (A, B, lo, C0, C1, M, N, K, b_k) in enumerate(cases)])
     for A, B, lo, C0, C1, M, N, K, b_k in cases:
         assert torch.equal(C0, C1), ("group", M, N, K, b_k)
+
+
+def test_dynamic_and_static_tile_order_give_the_same_products(ctas):
+    """phc_gemm_tc5s_set_sched: tiles drawn from the global counter (default) vs static striding.  A tile's arithmetic does not depend
+    on which CTA computes it, so plain stores are bit-identical; many more tiles than CTAs, tiles of very different length in one
+    group, and repeated launches (the counters must be back at zero after every launch)."""
+    if ctas != 1:
+        pytest.skip("the CTA-pair kernel has static striding only")
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(21)
+    probs = []
+    for (M, N, K) in [(4096, 1024, 934), (3000, 512, 1960), (128, 69, 512), (700, 1, 64)]:
+        A, B = padded(torch.randn(M, K, generator=g)), padded(torch.randn(N, K, generator=g))
+        probs.append((A, B, M, N, K, torch.zeros(M, round4(N), device=DEV), torch.zeros(M, round4(N), device=DEV)))
+    try:
+        _lib.check(lib.phc_gemm_tc5s_set_sched(0))
+        _group([_desc(A, True, B, True, C0, M, N, K) for A, B, M, N, K, C0, C1 in probs])
+        _lib.check(lib.phc_gemm_tc5s_set_sched(1))
+        for _ in range(70):                                     # more launches than counter slots
+            _group([_desc(A, True, B, True, C1, M, N, K) for A, B, M, N, K, C0, C1 in probs])
+        for A, B, M, N, K, C0, C1 in probs:
+            assert torch.equal(C0, C1), (M, N, K)
+    finally:
+        lib.phc_gemm_tc5s_set_sched(-1)

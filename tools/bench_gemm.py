@@ -37,15 +37,17 @@ def run(name, M, N, K, a_k, b_k, splits=1, mask=False, split_out=False):
     _lib.check(lib.phc_split_lo(B.data_ptr(), Blo.data_ptr(), B.numel(), None))
     acc = 1 if splits > 1 else 0
     variants = [("persist", {}), ("plain", {"PHC_TC5_PERSIST": "0"}), ("pair", {"PHC_TC5_PAIR": "1"}),
-                ("pairp", {"PHC_TC5_PAIRP": "1"}), ("mma.sync", None), ("s1", 1), ("s1p", "presplit1"), ("s2", 2), ("s2p", "presplit2")]
+                ("pairp", {"PHC_TC5_PAIRP": "1"}), ("mma.sync", None), ("s1", 1), ("w", 3), ("s1p", "presplit1"), ("s2", 2), ("s2p", "presplit2")]
     out = []
     for vname, env in variants:
         if only and vname not in only.split(","):
             continue
         if isinstance(env, int):
-            lib.phc_gemm_tc5s_set_ctas(env)
+            lib.phc_gemm_tc5s_set_ctas(1 if env == 3 else env)
+            lib.phc_gemm_tc5s_set_tile(256 if env == 3 else 128)
         if isinstance(env, str):
             lib.phc_gemm_tc5s_set_ctas(int(env[-1]))
+            lib.phc_gemm_tc5s_set_tile(128)
         for k in ("PHC_TC5_PERSIST", "PHC_TC5_PAIR", "PHC_TC5_PAIRP"):
             os.environ.pop(k, None)
         if isinstance(env, dict):
