@@ -369,6 +369,16 @@ class AMPAgent:
         self._x_mb = z(B, self.obs_pad)
         self._ws_actor = self.engine.workspace("actor", self.model.actor, B)
         self._ws_critic = self.engine.workspace("critic", self.model.critic, B)
+        # The critic is not needed inside the rollout loop: values and next-values enter only GAE, after the last step.  With the
+        # grouped GEMM back end they are evaluated afterwards on the stored obses / next_obses, minibatch-sized chunks of both in the
+        # same launches (2 x 8 chunks of 16384 rows instead of 2 x 32 batches of 4096 rows).  Row results do not depend on the
+        # batching, so this is the same arithmetic (tests/test_gpu_agent.py compares against the per-step path bit for bit).
+        self._defer_critic = (self.engine.backend == "tc5s" and bool(cfg.get("deferred_critic", True)) and
+                              os.environ.get("PHC_DEFER_CRITIC", "1") != "0")
+        if self._defer_critic:
+            self._x_mb2 = z(B, self.obs_pad)
+            self._ws_critic2 = self.engine.workspace("critic2", self.model.critic, B)
+            self._term_steps = z(T, N)
         self._amp_mb = z(3 * Bd, self.amp_pad)           # rows: [agent | replay | demo]
         self._ws_disc = self.engine.workspace("disc", self.model.disc, 3 * Bd)
         du = self.model.disc.hidden
@@ -418,11 +428,16 @@ class AMPAgent:
     # ------------------------------------------------------------------------------------------------------
     # rollout
     # ------------------------------------------------------------------------------------------------------
-    def get_action_values(self, obs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-        """CommonAgent.get_action_values (common_agent.py:262-288): normalise, actor + critic forward, sample."""
+    def get_action_values(self, obs: Dict[str, torch.Tensor], with_value: bool = True) -> Dict[str, torch.Tensor]:
+        """CommonAgent.get_action_values (common_agent.py:262-288): normalise, actor + critic forward, sample.
+        with_value=False (rollout with the deferred critic): actor only, no "values" entry."""
         N = self.num_actors
         x = self._preproc_obs(obs["obs"], out=self._x_roll)
-        if self.engine.backend == "tc5s":          # actor and critic layer by layer in the same launches
+        val = None
+        if not with_value:
+            self.engine.forward_group([(self.model.actor, x, self._ws_actor_roll)])
+            mu = self._ws_actor_roll["out"]
+        elif self.engine.backend == "tc5s":        # actor and critic layer by layer in the same launches
             self.engine.forward_group([(self.model.actor, x, self._ws_actor_roll), (self.model.critic, x, self._ws_critic_roll)])
             mu, val = self._ws_actor_roll["out"], self._ws_critic_roll["out"]
         else:
@@ -438,8 +453,27 @@ class AMPAgent:
                                            res["mus"].data_ptr(), res["sigmas"].data_ptr(), _stream())
         if rc:
             _lib.check(rc, "phc_gaussian_sample")
-        res["values"] = self._unnorm_value(val[:, :1])
+        if val is not None:
+            res["values"] = self._unnorm_value(val[:, :1])
         return res
+
+    def _rollout_values(self) -> None:
+        """values / next_values of the whole rollout from the stored obses / next_obses (see _defer_critic)."""
+        eb, critic = self.experience_buffer, self.model.critic
+        total, B = self.horizon_length * self.num_actors, self.minibatch_size
+        flat = lambda t: t.reshape(total, t.shape[-1])
+        o, no, v, nv = flat(eb["obses"]), flat(eb["next_obses"]), flat(eb["values"]), flat(eb["next_values"])
+        for s in range(0, total, B):
+            n = min(B, total - s)
+            x1 = self._preproc_obs(o[s:s + n], out=self._x_mb[:n])
+            x2 = self._preproc_obs(no[s:s + n], out=self._x_mb2[:n])
+            self.engine.forward_group([(critic, x1, self._ws_critic), (critic, x2, self._ws_critic2)])
+            for ws, dst in ((self._ws_critic, v), (self._ws_critic2, nv)):
+                if self.normalize_value:
+                    self.value_mean_std.apply(ws["out"][:n, :1], dst[s:s + n], unnorm=True)
+                else:
+                    dst[s:s + n].copy_(ws["out"][:n, :1])
+        eb["next_values"].mul_((1.0 - self._term_steps).unsqueeze(-1))
 
     def _unnorm_value(self, v: torch.Tensor) -> torch.Tensor:
         out = torch.empty(v.shape[0], 1, device=self.device)
@@ -505,9 +539,10 @@ class AMPAgent:
                 self.obs = self.env_reset(done_mask)
             with T("rollout.policy"):
                 eb["obses"][n].copy_(self.obs["obs"])
-                res = self.get_action_values(self.obs)
+                res = self.get_action_values(self.obs, with_value=not self._defer_critic)
                 for k in ("actions", "neglogpacs", "values", "mus", "sigmas"):
-                    eb[k][n].copy_(res[k])
+                    if k in res:
+                        eb[k][n].copy_(res[k])
             with T("rollout.env_step"):
                 self.obs, rewards, self.dones, infos = self.env_step(res["actions"])
             with T("rollout.store"):
@@ -523,14 +558,20 @@ class AMPAgent:
                 rr = infos["reward_raw"].mean(dim=0)
                 reward_raw = rr if reward_raw is None else reward_raw + rr
             with T("rollout.critic_next"):
-                next_vals = self._eval_critic(self.obs)
-                next_vals *= (1.0 - terminated.unsqueeze(-1))
-                eb["next_values"][n].copy_(next_vals)
+                if self._defer_critic:
+                    self._term_steps[n].copy_(terminated)
+                else:
+                    next_vals = self._eval_critic(self.obs)
+                    next_vals *= (1.0 - terminated.unsqueeze(-1))
+                    eb["next_values"][n].copy_(next_vals)
             not_dones = 1.0 - self.dones.float()
             self.current_rewards.add_(rewards.squeeze(1)).mul_(not_dones)      # in place: state carried across (graph-replayed) rollouts
             self.current_lengths.add_(1).mul_(not_dones)
             done_mask = self.dones
 
+        if self._defer_critic:
+            with T("rollout.critic_batched"):
+                self._rollout_values()
         mb_fdones = eb["dones"]
         with T("rollout.disc_reward"):
             amp_rewards = self._calc_amp_rewards(eb["amp_obs"])

@@ -244,6 +244,45 @@ def test_graph_replayed_rollout_equals_eager_rollout():
     assert agents[1]._rollout_graph is not None and agents[1]._rollout_graph_launches > 8 * 10
 
 
+def test_deferred_critic_rollout_equals_per_step_critic():
+    """values / next_values evaluated after the loop on the stored obses / next_obses (chunks of the minibatch size, obs and next-obs
+    chunks in the same grouped launches) against the reference's order (critic inside every step, amp_agent.py:329-372): row results
+    of the GEMM do not depend on the batching -> the same experience buffer, returns and advantages bit for bit; the ragged last
+    chunk (8 x 96 = 768 rows in chunks of 256 / 3 x 96 = 288 rows in chunks of 256) included."""
+    n = 96
+    for horizon in (8, 3):
+        cfgs = {"horizon_length": horizon, "minibatch_size": 256 if horizon == 8 else 96, "amp_minibatch_size": 64, "mini_epochs": 1,
+                "amp_obs_demo_buffer_size": 1024, "amp_replay_buffer_size": 1024, "amp_batch_size": 128, "graph_rollout": False,
+                "network": {"mlp": {"units": [64, 32], "activation": "relu"}, "disc": {"units": [64, 32], "activation": "relu"}}}
+        agents = []
+        for deferred in (False, True):
+            _, task = make_task(n, seed=5)
+            torch.manual_seed(1234)
+            ag = AMPAgent("t", dict(cfgs, vec_env=RLGPUEnv(task), deferred_critic=deferred))
+            if horizon == 3:
+                ag.minibatch_size = 256                 # 288 rows in chunks of 256: the workspaces below are re-made for it
+                ag._x_mb = torch.zeros(256, ag.obs_pad, device=ag.device)
+                ag._ws_critic = ag.engine.workspace("critic", ag.model.critic, 256)
+                if deferred:
+                    ag._x_mb2 = torch.zeros(256, ag.obs_pad, device=ag.device)
+                    ag._ws_critic2 = ag.engine.workspace("critic2", ag.model.critic, 256)
+            ag.obs = ag.env_reset()
+            ag._init_amp_demo_buf()
+            agents.append(ag)
+        assert agents[1]._defer_critic and not agents[0]._defer_critic
+        for epoch in range(2):
+            outs = []
+            for ag in agents:
+                torch.manual_seed(77 + epoch)
+                ag.set_eval()
+                bd = ag.play_steps()
+                torch.cuda.synchronize()
+                outs.append({k: v.clone() for k, v in ag.experience_buffer.items()} | {"returns": bd["returns"].clone(), "advs": bd["mb_advs"].clone()})
+            assert float(outs[0]["next_values"].abs().sum()) > 0
+            for k in outs[0]:
+                assert torch.equal(outs[0][k], outs[1][k]), f"horizon {horizon} epoch {epoch}: {k} differs between the per-step and the deferred critic"
+
+
 def test_ref_pose_cache_is_bit_identical_to_reinterpolation():
     """PHC_FLAG_REWARD_FROM_CACHE (the pose interpolated for the observation of step s is the reward-time pose of step
     s+1) against re-interpolating every step: identical bits over a rollout with resets in between."""
