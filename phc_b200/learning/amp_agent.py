@@ -373,7 +373,7 @@ class AMPAgent:
         # grouped GEMM back end they are evaluated afterwards on the stored obses / next_obses, minibatch-sized chunks of both in the
         # same launches (2 x 8 chunks of 16384 rows instead of 2 x 32 batches of 4096 rows).  Row results do not depend on the
         # batching, so this is the same arithmetic (tests/test_gpu_agent.py compares against the per-step path bit for bit).
-        self._defer_critic = (self.engine.backend == "tc5s" and bool(cfg.get("deferred_critic", True)) and
+        self._defer_critic = (self.engine.backend == "tc5s" and bool(self.config.get("deferred_critic", True)) and
                               os.environ.get("PHC_DEFER_CRITIC", "1") != "0")
         if self._defer_critic:
             self._x_mb2 = z(B, self.obs_pad)

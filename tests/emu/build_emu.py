@@ -333,6 +333,20 @@ extern "C" int emu_rms_update(const float* x, int64_t ldx, int64_t n, int32_t d,
   emu_grid(1, 1, 1024, 1, [&] { phc::rms_merge_kernel(acc, n, d, mean, var, count); });
   return 0;
 }
+extern "C" int emu_rms_apply_update_vec(const float* x, int64_t ldx, int64_t n, int32_t d, const double* mean_a, const double* var_a, float eps,
+                                       float* y, int64_t ldy, const int64_t* row_idx, double* mean, double* var, double* count, double* acc,
+                                       int32_t V, int32_t rows_per_block, int32_t moments) {
+  for (int i = 0; i < 2 * d; ++i) acc[i] = 0.0;
+  const int cb = (d + 32 * V - 1) / (32 * V), gy = (int)((n + rows_per_block - 1) / rows_per_block);
+  emu_grid(cb, gy, 256, 1, [&] {
+    if (V == 4 && moments) phc::rms_apply_vec_kernel<4, true>(x, ldx, n, d, mean_a, var_a, eps, y, ldy, row_idx, acc, rows_per_block);
+    else if (V == 4) phc::rms_apply_vec_kernel<4, false>(x, ldx, n, d, mean_a, var_a, eps, y, ldy, row_idx, nullptr, rows_per_block);
+    else if (moments) phc::rms_apply_vec_kernel<2, true>(x, ldx, n, d, mean_a, var_a, eps, y, ldy, row_idx, acc, rows_per_block);
+    else phc::rms_apply_vec_kernel<2, false>(x, ldx, n, d, mean_a, var_a, eps, y, ldy, row_idx, nullptr, rows_per_block);
+  });
+  if (moments) emu_grid(1, 1, 1024, 1, [&] { phc::rms_merge_kernel(acc, n, d, mean, var, count); });
+  return 0;
+}
 extern "C" int emu_disc_reward(const float* logit, int64_t ld, const float* task, int64_t n, float scale, float w_task, float w_disc,
                                float* disc_r, float* combined) {
   emu_grid(2, 1, 256, 1, [&] { phc::disc_reward_kernel(logit, ld, task, n, scale, w_task, w_disc, disc_r, combined); });

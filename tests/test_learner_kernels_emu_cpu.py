@@ -70,6 +70,7 @@ def upd(tmp_path_factory):
     lib = C.CDLL(build_emu.build_update(str(tmp_path_factory.mktemp("uemu"))))
     lib.emu_rms_apply.argtypes = [P, C.c_int64, C.c_int64, C.c_int32, P, P, C.c_float, C.c_int32, P, C.c_int64, P]
     lib.emu_rms_update.argtypes = [P, C.c_int64, C.c_int64, C.c_int32, P, P, P, P, P]
+    lib.emu_rms_apply_update_vec.argtypes = [P, C.c_int64, C.c_int64, C.c_int32, P, P, C.c_float, P, C.c_int64, P, P, P, P, P, C.c_int32, C.c_int32, C.c_int32]
     lib.emu_disc_reward.argtypes = [P, C.c_int64, P, C.c_int64, C.c_float, C.c_float, C.c_float, P, P]
     lib.emu_gaussian_sample.argtypes = [P, C.c_int64, P, P, C.c_int64, C.c_int32, P, P, P, P]
     return lib
@@ -105,6 +106,33 @@ def test_running_mean_std_kernels_vs_reference_golden(upd):
     yf = torch.zeros_like(x1)
     upd.emu_rms_apply(x1.data_ptr(), d, x1.shape[0], d, mean.data_ptr(), var.data_ptr(), 1e-5, 0, yf.data_ptr(), d, None)
     assert torch.equal(yg, yf[idx])
+
+
+@pytest.mark.parametrize("V,d,ld", [(4, 70, 72), (2, 70, 70), (4, 130, 132), (2, 5, 6)])
+def test_vectorised_normalise_and_moments_equal_the_scalar_kernels(upd, V, d, ld):
+    """rms_apply_vec_kernel (V columns per lane, gathered rows, fp64 moments through shared memory) against rms_apply_kernel +
+    rms_moments_kernel: the normalised rows bit for bit (ragged last vector, pad columns untouched), the merged statistics to fp64
+    rounding; both the apply-only and the apply + update form."""
+    g = torch.Generator().manual_seed(V * 100 + d)
+    n_src, n = 90, 77
+    x = torch.zeros(n_src, ld)
+    x[:, :d] = torch.randn(n_src, d, generator=g) * 3 + 1
+    idx = torch.randint(0, n_src, (n,), generator=g)
+    mean_a, var_a = torch.randn(d, generator=g).double(), (torch.rand(d, generator=g) + 0.5).double()
+    ys, yv, yv2 = torch.zeros(n, ld), torch.full((n, ld), 9.0), torch.full((n, ld), 9.0)
+    upd.emu_rms_apply(x.data_ptr(), ld, n, d, mean_a.data_ptr(), var_a.data_ptr(), 1e-5, 0, ys.data_ptr(), ld, idx.data_ptr())
+    st = [(torch.full((d,), 0.3, dtype=torch.float64), torch.full((d,), 1.7, dtype=torch.float64), torch.full((), 50.0, dtype=torch.float64)) for _ in range(2)]
+    acc = torch.zeros(2 * d, dtype=torch.float64)
+    upd.emu_rms_update(x.data_ptr(), ld, n, d, st[0][0].data_ptr(), st[0][1].data_ptr(), st[0][2].data_ptr(), acc.data_ptr(), idx.data_ptr())
+    upd.emu_rms_apply_update_vec(x.data_ptr(), ld, n, d, mean_a.data_ptr(), var_a.data_ptr(), 1e-5, yv.data_ptr(), ld, idx.data_ptr(),
+                                 st[1][0].data_ptr(), st[1][1].data_ptr(), st[1][2].data_ptr(), acc.data_ptr(), V, 32, 1)
+    assert torch.equal(yv[:, :d], ys[:, :d]) and bool((yv[:, d:] == 9.0).all())
+    close(st[1][0], st[0][0], rtol=1e-13, atol=1e-13, what="mean")
+    close(st[1][1], st[0][1], rtol=1e-12, atol=1e-13, what="var")
+    assert float(st[1][2]) == float(st[0][2]) == 50.0 + n
+    upd.emu_rms_apply_update_vec(x.data_ptr(), ld, n, d, mean_a.data_ptr(), var_a.data_ptr(), 1e-5, yv2.data_ptr(), ld, idx.data_ptr(),
+                                 None, None, None, acc.data_ptr(), V, 64, 0)
+    assert torch.equal(yv2[:, :d], ys[:, :d]) and bool((yv2[:, d:] == 9.0).all())
 
 
 def test_disc_reward_kernel_vs_reference_golden(upd):

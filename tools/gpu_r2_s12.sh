@@ -20,8 +20,5 @@ print('value',d['value'],'ms',d['ms_per_step'],'gemm',d['roofline_gemm']['achiev
   echo "== phase breakdown (eager rollout, CUDA-event phases)"
   PHC_PHASE_TIMING=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-points --no-extras 2>&1 | grep -E "phase_ms|value arm"
 } > gpurun_out/s12.log 2>&1
-for v in s1 w; do
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:gemm_tc5 -s 3 -c 3 -o gpurun_out/gemm_r2d_$v -f python tools/profile_gemm.py $v > gpurun_out/s12_ncu_$v.log 2>&1
-done
 ls -la gpurun_out | tail -4
 cat gpurun_out/s12.log
