@@ -336,12 +336,14 @@ def timed_epochs(agent, steps: int, warmup: int, world: int, read_result: bool):
 
 
 def env_kernel_roofline(task, peak_gbs: float, peak_src: str, iters: int = 40, algo_bytes: int = ALGO_BYTES_PER_ENV_STEP,
-                         kernel: str = "phc::env_step_kernel<1, 24, false, true>"):
+                         kernel: str = "phc::packed::env_step_packed_kernel"):
     """Average duration of the fused env-step kernel with inputs coming from HBM (L2 flushed by a 256 MB write before every
     launch), CUDA events on the launching stream.  Two measurements:
       * `kernel_us` (used for `achieved`): K x [flush, kernel] and K x [flush] are each bracketed by ONE event pair and the
         difference is divided by K -- the per-event-pair overhead (a few microseconds, comparable to the kernel itself)
-        cancels, the launch rate is what the GPU front end sustains back to back, as in the rollout;
+        cancels, the launch rate is what the GPU front end sustains back to back, as in the rollout.  The flush is a plain torch
+        fill_; the env step is launched the way the product always launches it (programmatic stream serialisation, the kernel
+        waits on griddepcontrol.wait before its first global-memory access);
       * `kernel_us_event_pair`: the median of K single launches each inside its own event pair (includes that overhead)."""
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=task.device)
     times = []
@@ -374,7 +376,8 @@ def env_kernel_roofline(task, peak_gbs: float, peak_src: str, iters: int = 40, a
         t_fk = batch(True)
         diffs.append((t_fk - t_f) / iters)
     t = statistics.median(diffs)
-    if not (0.2 * t_pair < t < t_pair):          # the differential estimate must be sane; otherwise report the conservative one
+    sane = 0.2 * t_pair < t < t_pair             # the differential estimate must be sane; otherwise report the conservative one
+    if not sane:
         t = t_pair
     N = task.num_envs
     traffic = None            # DRAM bytes per launch from the committed ncu --set full capture of this kernel at this size
@@ -391,12 +394,15 @@ def env_kernel_roofline(task, peak_gbs: float, peak_src: str, iters: int = 40, a
     actual = 1248 + 1248 + 2 * 1248 + 552 + 276 + 56 + 3744 + 40 + 784 + 1248
     return {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
             "kernel": kernel, "kernel_us": t * 1e6, "kernel_us_event_pair": t_pair * 1e6,
+            "kernel_us_differential_raw": statistics.median(diffs) * 1e6, "differential_used": sane,
             "frac_event_pair": algo_bytes * N / t_pair / 1e9 / peak_gbs,
             "algorithmic_bytes_per_launch": algo_bytes * N,
             "bytes_moved_per_launch_incl_amp_slot_and_pose_cache": actual * N, "achieved_incl_extras_gbs": actual * N / t / 1e9,
             "peak_source": peak_src,
-            "timing": "L2 flushed before each launch; kernel_us = (%d x [flush, kernel] - %d x [flush]) / %d, one CUDA-event pair per batch, "
-                      "median of 5; kernel_us_event_pair = median of %d single launches, one event pair each" % (iters, iters, iters, iters)}
+            "timing": "L2 flushed (torch fill_ of 256 MB) before each launch; kernel_us = (%d x [flush, kernel] - %d x [flush]) / %d, one "
+                      "CUDA-event pair per batch, median of 5; the env step is a programmatic-dependent launch as everywhere in the product "
+                      "(PHC_ENV_PDL=0 gives the plain stream-ordered launch: +2.4 us at 4096 envs, profiles/ab_env_r2.log); "
+                      "kernel_us_event_pair = median of %d single launches, one event pair each" % (iters, iters, iters, iters)}
 
 
 def measured_peak_tf32():

@@ -291,6 +291,9 @@ PHC_API int phc_env_step(const PhcStepArgs* args, void* stream);
  * given, no env mask, no ref_body_* buffers, AMP ring slot / obs rows / pose cache movable as 16-byte granular bulk copies).
  * Diagnostic: lets a caller (and the tests) see that its buffers qualify.  PHC_ENV_FAST=0 in the environment disables it. */
 PHC_API int64_t phc_env_step_fast_launches(void);
+/* phc_env_step is launched with programmatic stream serialisation (PDL): its CTAs may become resident, and set up their shared
+ * memory barriers, while the previous kernel of the stream is finishing; the kernel executes griddepcontrol.wait before its first
+ * global-memory access, so ordering is exactly that of a plain launch.  PHC_ENV_PDL=0 in the environment switches the attribute off. */
 
 /* build_amp_obs_demo (humanoid_amp.py:253-284) and the history re-initialisation of _init_amp_obs_ref
  * (:575-603): AMP observations of the REFERENCE motion at t0 - (first_step + k)*dt, k = 0..num_steps-1,

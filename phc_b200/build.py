@@ -29,6 +29,7 @@ SOURCES = {
     "phc_api.cu": [],
     "gemm_tc5w.cu": [],
     "env_step.cu": ["-fmad=false"] if os.environ.get("PHC_ENV_FMAD", "1") == "0" else [],
+    "env_step_packed.cu": [],
     "env_step_wide.cu": [],
     "motion.cu": ["-fmad=false"],
     "motion_wide.cu": ["-fmad=false"],
@@ -55,19 +56,23 @@ def _newer(src_files, target) -> bool:
     return any(os.path.getmtime(s) > t for s in src_files)
 
 
-def build_variant(name: str, flags, source: str = "env_step.cu") -> str:
-    """Experiment builds (tools/ab_env.sh, tools/gpu_r2_s9.sh): the same library with extra -D flags on ONE source file, written to
-    lib/alt_<name>/libphc_b200.so; selected at run time with PHC_LIB_PATH.  Never the default."""
+def build_variant(name: str, flags, source="env_step.cu") -> str:
+    """Experiment builds (tools/ab_env.sh, tools/gpu_r2_s9.sh): the same library with extra -D flags on ONE source file (or a
+    list of them), written to lib/alt_<name>/libphc_b200.so; selected at run time with PHC_LIB_PATH.  Never the default."""
     out_dir = os.path.join(OUT_DIR, f"alt_{name}")
     os.makedirs(out_dir, exist_ok=True)
     nvcc = _nvcc()
-    obj = os.path.join(out_dir, source.replace(".cu", ".o"))
-    r = subprocess.run([nvcc] + ARCH + COMMON + SOURCES[source] + list(flags) + ["-c", os.path.join(CSRC, source), "-o", obj],
-                       capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"nvcc failed on {source} ({name}):\n{r.stderr}")
+    sources = [source] if isinstance(source, str) else list(source)
+    alt = {}
+    for src in sources:
+        obj = os.path.join(out_dir, src.replace(".cu", ".o"))
+        r = subprocess.run([nvcc] + ARCH + COMMON + SOURCES[src] + list(flags) + ["-c", os.path.join(CSRC, src), "-o", obj],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src} ({name}):\n{r.stderr}")
+        alt[src] = obj
     build()
-    objs = [obj if s == source else os.path.join(OBJ_DIR, s.replace(".cu", ".o")) for s in SOURCES]
+    objs = [alt.get(s, os.path.join(OBJ_DIR, s.replace(".cu", ".o"))) for s in SOURCES]
     lib = os.path.join(out_dir, "libphc_b200.so")
     r = subprocess.run([nvcc] + ARCH + ["-shared", "-o", lib] + objs + ["-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:

@@ -18,6 +18,7 @@
 #include "../../include/phc_b200.h"
 #include "phc_common.cuh"
 #include "phc_math.cuh"
+#include "env_step_shared.cuh"
 
 namespace phc {
 
@@ -26,8 +27,6 @@ namespace phc {
 #endif
 constexpr int kWarpsPerCta = PHC_EXP_WARPS;
 constexpr int kMinCtasPerSm = 28 / PHC_EXP_WARPS;   // 28 envs resident per SM: 4096 envs = one wave on 148 SMs
-constexpr int kBodyRec = 13;
-
 struct StepLayout {      // per-warp shared-memory carve-up, in floats (all multiples of 4 -> 16-byte aligned)
   int rslots;            // 2 frame slots of the reward bracket            | the observation row (T == 1) is
   int state;             // J*13 rounded up: the env's simulator block     | staged over these two regions once
@@ -37,8 +36,6 @@ struct StepLayout {      // per-warp shared-memory carve-up, in floats (all mult
   int obs;               // separate obs row (0 when it aliases rslots+state)
   int total;             // sum + 4 (mbarrier)
 };
-
-__host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
 
 __host__ __device__ inline StepLayout make_layout(int J, int T, int body_stride, int A, int obs_dim, bool alias_obs, int D = 0) {
   StepLayout L;
@@ -52,32 +49,6 @@ __host__ __device__ inline StepLayout make_layout(int J, int T, int body_stride,
   return L;
 }
 
-struct BodyRec { V3 p; Q4 q; V3 v; V3 w; };
-
-__device__ __forceinline__ BodyRec load_body(const float* s) {
-  BodyRec b;
-  b.p = v3(s[0], s[1], s[2]);
-  b.q = q4(s[3], s[4], s[5], s[6]);
-  b.v = v3(s[7], s[8], s[9]);
-  b.w = v3(s[10], s[11], s[12]);
-  return b;
-}
-
-// two-frame blend of one body: lerp pos(+offset)/vel/angvel, slerp rot (motion_lib_base.py:474-488)
-__device__ __forceinline__ BodyRec blend_body(const float* s0, const float* s1, float bl, V3 off) {
-  const BodyRec a = load_body(s0), b = load_body(s1);
-  const float omb = 1.0f - bl;
-  BodyRec r;
-  r.p = lerp3(a.p, b.p, omb, bl) + off;
-  r.v = lerp3(a.v, b.v, omb, bl);
-  r.w = lerp3(a.w, b.w, omb, bl);
-  r.q = slerp(a.q, b.q, bl);
-  return r;
-}
-
-__device__ __forceinline__ void st3(float* d, V3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
-__device__ __forceinline__ void st6(float* d, TanNorm t) { st3(d, t.t); st3(d + 3, t.n); }
-
 // JT > 0: the body count is a compile-time constant (24 = SMPL, 20 = H1): record strides, segment offsets of the observation
 // row and the shared-memory carve-up fold into immediates; JT == 0 is the generic runtime-J build.
 // GETUP: the env_im_getup_mcp.yaml extras (PHC_FLAG_ZERO_OUT_FAR / PHC_FLAG_CYCLE_MOTION, T == 1, spherical joints).  A template
@@ -86,9 +57,6 @@ __device__ __forceinline__ void st6(float* d, TanNorm t) { st3(d, t.t); st3(d + 
 // kFastFlags, pose cache on, no env mask, per-env motion records given, every row movable as a TMA bulk copy, no ref_*
 // side buffers.  All of that becomes compile-time, so the flag tests, the non-cache reward path, the row-store fallbacks and
 // their predicates / branches leave the instruction stream (the arithmetic is the same code, operation for operation).
-constexpr uint32_t kFastFlags = PHC_FLAG_UPRIGHT | PHC_FLAG_LOCAL_ROOT_OBS | PHC_FLAG_ROOT_HEIGHT_OBS | PHC_FLAG_POWER_REWARD |
-                                PHC_FLAG_EARLY_TERM | PHC_FLAG_REWARD_FROM_CACHE;
-
 template <int T_MAX, int JT, bool GETUP = false, bool FAST = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm)
 env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const int self_dim, const int amp_dim,
@@ -104,7 +72,17 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
 #endif
   const int env = blockIdx.x * kWarpsPerCta + warp;
   if (env >= a.num_envs) return;                       // whole warp exits together; no block-level barrier is used
-  if (!FAST && a.only_where && a.only_where[env] == 0) return;  // masked subset (reset path)
+#if defined(PHC_EXP_EXIT) && PHC_EXP_EXIT == 1      // floor experiment: launch + CTA ramp only
+  grid_dependency_wait();
+  return;
+#endif
+#ifdef PHC_EXP_TIMELINE
+  if (lane == 0 && g_timeline) g_timeline[(size_t)env * 8 + 7] = smid();
+#endif
+  if (!FAST && a.only_where) {                         // masked subset (reset path): the mask is the previous kernel's output
+    grid_dependency_wait();
+    if (a.only_where[env] == 0) return;
+  }
   const uint32_t flags = FAST ? kFastFlags : a.flags;
   const bool alias_obs = FAST ? true : alias_obs_rt;
   const bool state_bulk_ok = FAST ? true : state_bulk_ok_rt;
@@ -139,29 +117,31 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     mbar_init(bar, 1);
     mbar_init(bar_o, 1);
     mbar_init_fence();
-    if (state_bulk_ok) {
-      mbar_expect_tx(bar, state_bytes);
-      bulk_g2s(s_state, g_state, state_bytes, bar);
-    }
-    if (from_cache) {
-      mbar_expect_tx(bar, frame_bytes);
-      bulk_g2s(s_rslots, a.ref_cache + (size_t)env * BS, frame_bytes, bar);
-      mbar_arrive(bar);                    // nothing else lands on this barrier (else: arrive once the reward frames are issued)
-    }
   }
-  __syncwarp();
+  // Programmatic dependent launch: everything above (CTA placement, shared-memory carve-up, barrier setup) may run while the
+  // previous kernel of the stream is still finishing; no global memory is touched before this wait returns (= the previous
+  // grid has completed and its writes are visible).  A no-op when the launch carries no programmatic dependency.
+  grid_dependency_wait();
+  PHC_TL(0);
+  auto issue_env_blocks = [&]() {
+    if (lane == 0) {
+      if (state_bulk_ok) {
+        mbar_expect_tx(bar, state_bytes);
+        bulk_g2s(s_state, g_state, state_bytes, bar);
+      }
+      if (from_cache) {
+        mbar_expect_tx(bar, frame_bytes);
+        bulk_g2s(s_rslots, a.ref_cache + (size_t)env * BS, frame_bytes, bar);
+        mbar_arrive(bar);                  // nothing else lands on this barrier (else: arrive once the reward frames are issued)
+      }
+    }
+    __syncwarp();
+  };
+#ifndef PHC_EXP_SCALARS_FIRST
+  issue_env_blocks();
+#endif
 
   // ---- every load that depends only on the env index is issued first (one DRAM round trip for all of them) ----------
-  const float2* g_dof = reinterpret_cast<const float2*>(a.dof_state) + (size_t)env * D;
-  const float* g_force = (FAST || a.dof_force) ? a.dof_force + (size_t)env * D : nullptr;
-  float2 dof_pv[3];                                   // D <= 93 for J <= 32: at most 3 dofs per lane
-  float dof_f[3];
-#pragma unroll
-  for (int u = 0; u < 3; ++u) {
-    const int d = lane + 32 * u;
-    dof_pv[u] = (d < D) ? g_dof[d] : make_float2(0.f, 0.f);
-    dof_f[u] = (g_force && d < D) ? g_force[d] : 0.f;
-  }
   const int64_t progress = a.progress[env];
   const float t_start = a.start_times[env], t_off = a.start_offsets[env];
   const V3 goff = v3(a.global_offset[3 * env + 0], a.global_offset[3 * env + 1], a.global_offset[3 * env + 2]);
@@ -174,6 +154,19 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     const int64_t mid = a.motion_ids[env];
     m_len = a.lib.motion_len[mid]; m_dt = a.lib.motion_dt[mid];
     m_nf = a.lib.motion_num_frames[mid]; m_start = a.lib.length_starts[mid];
+  }
+#ifdef PHC_EXP_SCALARS_FIRST       // the few scalar requests ahead of the 2.5 KB blocks in the memory system's queues
+  issue_env_blocks();
+#endif
+  const float2* g_dof = reinterpret_cast<const float2*>(a.dof_state) + (size_t)env * D;
+  const float* g_force = (FAST || a.dof_force) ? a.dof_force + (size_t)env * D : nullptr;
+  float2 dof_pv[3];                                   // D <= 93 for J <= 32: at most 3 dofs per lane
+  float dof_f[3];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int d = lane + 32 * u;
+    dof_pv[u] = (d < D) ? g_dof[d] : make_float2(0.f, 0.f);
+    dof_f[u] = (g_force && d < D) ? g_force[d] : 0.f;
   }
 
   // Motion parameters of the OBSERVATION time: the step's own, unless the clip wraps this step (cycle_motion) -- then the
@@ -299,6 +292,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     }
   };
   issue_frames();
+  PHC_TL(1);
   if (!state_bulk_ok) {      // bodies_per_env not a multiple of 4: rows are only 4-byte aligned
     for (int i = lane; i < J * kBodyRec; i += 32) s_state[i] = g_state[i];
   }
@@ -318,6 +312,12 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   mbar_wait(bar, 0);
   // without the cache the reward bracket may alias observation slots: phase A then needs those copies too
   if (!from_cache && !obs_only) mbar_wait(bar_o, 0);
+  PHC_TL(2);
+#if defined(PHC_EXP_EXIT) && PHC_EXP_EXIT == 2      // floor experiment: launch + every input landed in shared memory, nothing else
+  mbar_wait(bar_o, 0);
+  if (dof_pv[0].x + dof_f[0] + power == 123.456f) a.rew[env] = 0.f;
+  return;
+#endif
 
   // ================= phase A: everything that reads the reward slots / simulator block =======================
   const bool has_body = lane < J;
@@ -482,6 +482,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
                            ? a.amp_out + (size_t)env * a.amp_out_stride + (a.ring_head ? (size_t)(*a.ring_head) * (size_t)amp_dim : (size_t)0) : nullptr;
   const bool amp_bulk = FAST ? true : (g_amp && !a.amp_hist_in && (amp_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(g_amp) & 15) == 0);
   __syncwarp();   // the reward slots and the simulator block are consumed: the obs row may overwrite them
+  PHC_TL(3);
 
   // ================= phase B: observation row (reads only registers + the observation slots) =================
   if (lane == 0 && has_h) s_obs[0] = root_p.z;
@@ -511,6 +512,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   }
   // task observation v6 for each of the T reference samples (the self observation above did not need the frames)
   mbar_wait(bar_o, 0);
+  PHC_TL(4);
   float* const g_cache = (FAST || a.ref_cache) ? a.ref_cache + (size_t)env * BS : nullptr;
   const bool cache_bulk = FAST ? true : (g_cache && T_MAX == 1);     // single sample: the blended pose is staged over its own frame slot
   V3 rroot = v3(0.f, 0.f, 0.f);
@@ -572,6 +574,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   if (obs_bulk && lane < obs_pad - obs_dim) s_obs[obs_dim + lane] = 0.f;      // the row's pad columns are written as zeros
   if (obs_bulk || cache_bulk || amp_bulk) fence_async_smem();
   __syncwarp();
+  PHC_TL(5);
   if (lane == 0 && (obs_bulk || cache_bulk || amp_bulk)) {
     if (amp_bulk) bulk_s2g(g_amp, s_amp, (uint32_t)amp_dim * 4u);
     if (obs_bulk) bulk_s2g(g_obs, s_obs, (uint32_t)obs_pad * 4u);
@@ -600,6 +603,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
   }
   // the shared-memory rows must outlive the bulk reads: the issuing lane waits before the warp (and so the CTA) may retire
   if (lane == 0 && (amp_bulk || obs_bulk || cache_bulk)) bulk_wait_read0();
+  PHC_TL(6);
 }
 
 }  // namespace phc
@@ -611,6 +615,7 @@ extern "C" void phc_set_error(const char* msg);   // phc_api.cu
 extern "C" int phc_check_cuda(cudaError_t e, const char* what);
 extern "C" void phc_count_launches(int n);
 extern "C" int phc_env_step_wide_launch(const PhcStepArgs* a, int obs_dim, int self_dim, int amp_dim, void* stream);   // env_step_wide.cu
+extern "C" int phc_env_step_packed_launch(const PhcStepArgs* a, int amp_dim, int pdl, void* stream);                    // env_step_packed.cu
 
 extern "C" int phc_self_obs_dim(int32_t J, uint32_t flags) {
   return ((flags & PHC_FLAG_ROOT_HEIGHT_OBS) ? 1 : 0) + 15 * J - 3;
@@ -622,6 +627,13 @@ extern "C" int phc_amp_obs_dim(int32_t nj, int32_t nk, uint32_t flags) {
 extern "C" int phc_amp_obs_dim_robot(int32_t D, int32_t nk, uint32_t flags) {
   return ((flags & PHC_FLAG_ROOT_HEIGHT_OBS) ? 1 : 0) + 12 + 2 * D + 3 * nk;
 }
+
+#ifdef PHC_EXP_TIMELINE
+extern "C" PHC_API int phc_exp_set_timeline(void* buf) {
+  unsigned long long* p = static_cast<unsigned long long*>(buf);
+  return phc_check_cuda(cudaMemcpyToSymbol(phc::g_timeline, &p, sizeof(p)), "phc_exp_set_timeline");
+}
+#endif
 
 static int64_t g_fast_launches = 0;
 extern "C" int64_t phc_env_step_fast_launches(void) { return g_fast_launches; }
@@ -706,12 +718,20 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
       if (e != cudaSuccess) return phc_check_cuda(e, "cudaFuncSetAttribute(env_step_kernel)");                       \
       smem_limit = smem;                                                                                             \
     }                                                                                                                \
-    env_step_kernel<TM, JJ, __VA_ARGS__><<<grid, kWarpsPerCta * 32, smem, st>>>(*a, obs_dim, self_dim, amp_dim, alias_obs,    \
-                                                                        state_bulk_ok);                              \
+    cudaLaunchConfig_t lc = {};                                                                                      \
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(kWarpsPerCta * 32); lc.dynamicSmemBytes = smem; lc.stream = st; \
+    cudaLaunchAttribute la[1];                                                                                       \
+    la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                   \
+    la[0].val.programmaticStreamSerializationAllowed = 1;                                                            \
+    lc.attrs = la; lc.numAttrs = pdl_allowed ? 1 : 0;                                                                \
+    e = cudaLaunchKernelEx(&lc, env_step_kernel<TM, JJ, __VA_ARGS__>, *a, obs_dim, self_dim, amp_dim, alias_obs, state_bulk_ok); \
+    if (e != cudaSuccess) return phc_check_cuda(e, "cudaLaunchKernelEx(env_step_kernel)");                           \
     phc_count_launches(1);                                                                                           \
   } while (0)
   // the steady-state launch of the shipped SMPL configuration takes the compile-time specialisation (see kFastFlags)
   const int obs_pad_h = round4(obs_dim);
+  // PHC_ENV_PDL=0: plain stream-ordered launches (A/B switch; the kernel's griddepcontrol.wait is then a no-op)
+  static const bool pdl_allowed = [] { const char* v = getenv("PHC_ENV_PDL"); return !(v && v[0] == '0'); }();
   static const bool fast_allowed = [] { const char* v = getenv("PHC_ENV_FAST"); return !(v && v[0] == '0'); }();   // A/B switch
   const bool fast = fast_allowed && !widened && !getup && T == 1 && J == 24 && E == 0 && DR == 0 && a->flags == kFastFlags && !a->only_where && a->env_motion &&
                     a->dof_force && state_bulk_ok && alias_obs && a->ref_cache && (reinterpret_cast<uintptr_t>(a->ref_cache) & 15) == 0 &&
@@ -719,6 +739,13 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
                     a->amp_out && !a->amp_hist_in && (amp_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(a->amp_out) & 15) == 0 &&
                     (a->amp_out_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(a->obs) & 15) == 0 && a->obs_stride >= obs_pad_h &&
                     (a->obs_stride & 3) == 0 && a->num_key_bodies > 0;
+  // ... and, with the env count a multiple of 4, the packed mapping of env_step_packed.cu (4 envs per 3 warps: no idle lanes);
+  // PHC_ENV_PACKED=0 keeps the one-warp-per-env specialisation (A/B switch, bit-identity tests)
+  static const bool packed_allowed = [] { const char* v = getenv("PHC_ENV_PACKED"); return !(v && v[0] == '0'); }();
+  if (fast && packed_allowed && (a->num_envs & 3) == 0 && a->num_amp_joints <= 24 && obs_dim == 934) {
+    ++g_fast_launches;
+    return phc_env_step_packed_launch(a, amp_dim, pdl_allowed ? 1 : 0, stream);
+  }
   if (fast) { PHC_LAUNCH_STEP(1, 24, false, true); ++g_fast_launches; }
   else if (getup && J == 24) PHC_LAUNCH_STEP(1, 24, true);                      // env_im_getup_mcp.yaml
   else if (getup) PHC_LAUNCH_STEP(1, 0, true);

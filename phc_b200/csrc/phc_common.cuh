@@ -61,6 +61,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// Programmatic dependent launch (PTX griddepcontrol): block until the grid(s) this launch programmatically depends on have
+// completed and flushed their writes; returns immediately for a launch without such a dependency.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Activation codes of the GEMM epilogues (include/phc_b200.h PHC_ACT_*): SiLU x*sigmoid(x) with accurate expf + IEEE division
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float silu_grad_f(float z) {        // d/dz z*s(z) = s(z) * (1 + z * (1 - s(z)))

@@ -86,6 +86,16 @@ static inline bool __any_sync(unsigned, bool p) {
   return any != 0;
 }
 
+static inline unsigned __ballot_sync(unsigned, bool p) {
+  emu_warp->xch[emu_lane] = p ? 1u : 0u;
+  emu_warp->bar.arrive_and_wait();
+  unsigned m = 0;
+  for (int i = 0; i < 32; ++i) m |= (unsigned)(emu_warp->xch[i] & 1u) << i;
+  emu_warp->bar.arrive_and_wait();
+  emu_chaos();
+  return m;
+}
+
 // atomicAdd: one global lock (the emulation is about values, not contention)
 static std::mutex emu_atomic_mutex;
 template <class T>

@@ -17,6 +17,7 @@ static inline void mbar_arrive(uint64_t* bar) { emu_bar(bar)->arrivals.fetch_sub
 static inline bool mbar_try_wait(uint64_t* bar, uint32_t) { return emu_bar(bar)->arrivals.load() <= 0 && emu_bar(bar)->tx.load() <= 0; }
 static inline void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) std::this_thread::yield(); emu_chaos(); }
 static inline void fence_async_smem() {}
+static inline void grid_dependency_wait() {}      // programmatic dependent launch: nothing precedes the emulated launch
 static inline void bulk_s2g(void* dst, const void* src, uint32_t bytes) { std::memcpy(dst, src, bytes); }
 static inline void bulk_commit() {}
 static inline void bulk_wait_read0() {}

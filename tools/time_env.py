@@ -17,4 +17,4 @@ task = HumanoidIm({"env": {"num_envs": n}, "motion_data": syn.make_motions(n, se
 task.reset()
 peak, src = bench.measured_peak_gbs()
 r = bench.env_kernel_roofline(task, peak, src, iters=iters)
-print(json.dumps({k: r[k] for k in ("kernel_us", "kernel_us_event_pair", "achieved", "frac", "frac_event_pair")} | {"num_envs": n}))
+print(json.dumps({k: r[k] for k in ("kernel_us", "kernel_us_event_pair", "kernel_us_differential_raw", "achieved", "frac", "frac_event_pair")} | {"num_envs": n}))
