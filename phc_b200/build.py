@@ -29,7 +29,7 @@ SOURCES = {
     "phc_api.cu": [],
     "gemm_tc5w.cu": [],
     "env_step.cu": ["-fmad=false"] if os.environ.get("PHC_ENV_FMAD", "1") == "0" else [],
-    "env_step_packed.cu": [],
+    "env_step_fast.cu": [],
     "env_step_wide.cu": [],
     "motion.cu": ["-fmad=false"],
     "motion_wide.cu": ["-fmad=false"],

@@ -615,7 +615,7 @@ extern "C" void phc_set_error(const char* msg);   // phc_api.cu
 extern "C" int phc_check_cuda(cudaError_t e, const char* what);
 extern "C" void phc_count_launches(int n);
 extern "C" int phc_env_step_wide_launch(const PhcStepArgs* a, int obs_dim, int self_dim, int amp_dim, void* stream);   // env_step_wide.cu
-extern "C" int phc_env_step_packed_launch(const PhcStepArgs* a, int amp_dim, int pdl, void* stream);                    // env_step_packed.cu
+extern "C" int phc_env_step_fast_launch(const PhcStepArgs* a, int amp_dim, int pdl, void* stream);                      // env_step_fast.cu
 
 extern "C" int phc_self_obs_dim(int32_t J, uint32_t flags) {
   return ((flags & PHC_FLAG_ROOT_HEIGHT_OBS) ? 1 : 0) + 15 * J - 3;
@@ -739,12 +739,12 @@ extern "C" int phc_env_step(const PhcStepArgs* a, void* stream) {
                     a->amp_out && !a->amp_hist_in && (amp_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(a->amp_out) & 15) == 0 &&
                     (a->amp_out_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(a->obs) & 15) == 0 && a->obs_stride >= obs_pad_h &&
                     (a->obs_stride & 3) == 0 && a->num_key_bodies > 0;
-  // ... and, with the env count a multiple of 4, the packed mapping of env_step_packed.cu (4 envs per 3 warps: no idle lanes);
-  // PHC_ENV_PACKED=0 keeps the one-warp-per-env specialisation (A/B switch, bit-identity tests)
-  static const bool packed_allowed = [] { const char* v = getenv("PHC_ENV_PACKED"); return !(v && v[0] == '0'); }();
-  if (fast && packed_allowed && (a->num_envs & 3) == 0 && a->num_amp_joints <= 24 && obs_dim == 934) {
+  // ... in the form of env_step_fast.cu (the same arithmetic with the phases ordered by input arrival); PHC_ENV_FASTK=0 keeps the
+  // FAST instantiation of the kernel above (A/B switch, bit-identity tests)
+  static const bool fastk_allowed = [] { const char* v = getenv("PHC_ENV_FASTK"); return !(v && v[0] == '0'); }();
+  if (fast && fastk_allowed && a->num_amp_joints <= 32 && obs_dim == 934) {
     ++g_fast_launches;
-    return phc_env_step_packed_launch(a, amp_dim, pdl_allowed ? 1 : 0, stream);
+    return phc_env_step_fast_launch(a, amp_dim, pdl_allowed ? 1 : 0, stream);
   }
   if (fast) { PHC_LAUNCH_STEP(1, 24, false, true); ++g_fast_launches; }
   else if (getup && J == 24) PHC_LAUNCH_STEP(1, 24, true);                      // env_im_getup_mcp.yaml

@@ -15,7 +15,7 @@ CSRC = os.path.join(ROOT, "phc_b200", "csrc")
 
 LAUNCHER = r'''
 namespace phc { alignas(128) float smem[1 << 16]; }      // the kernel's `extern __shared__ float smem[]`
-namespace phc { namespace packed { alignas(128) float smem[1 << 16]; } }
+namespace phc { namespace fast { alignas(128) float smem[1 << 16]; } }
 
 template <int T_MAX, int JT, bool GETUP, bool FAST>
 static void emu_launch(const PhcStepArgs& a, int obs_dim, int self_dim, int amp_dim, bool alias_obs, bool state_bulk_ok) {
@@ -42,24 +42,21 @@ extern "C" int emu_env_step(const PhcStepArgs* a, int obs_dim, int self_dim, int
     case 3: emu_launch<1, 0, false, false>(*a, obs_dim, self_dim, amp_dim, alias_obs, state_bulk_ok); return 0;
     case 4: emu_launch<4, 0, false, false>(*a, obs_dim, self_dim, amp_dim, alias_obs, state_bulk_ok); return 0;
     case 5: emu_launch<1, 0, true, false>(*a, obs_dim, self_dim, amp_dim, alias_obs, state_bulk_ok); return 0;
-    case 7: {    // env_step_packed.cu: 4 envs per CTA of 96 threads (3 warps), CTA barriers between the phases
-      const int stride = phc::packed::env_stride(amp_dim);
-      for (int b = 0; b < a->num_envs / phc::packed::kEnvsPerCta; ++b) {
-        std::vector<EmuWarp> warps(3);
-        std::barrier<> block_bar(phc::packed::kThreads);
-        emu_block_bar = &block_bar;
-        std::vector<std::thread> ts;
-        for (int t = 0; t < phc::packed::kThreads; ++t)
-          ts.emplace_back([&, t] {
-            emu_warp = &warps[t / 32];
-            emu_lane = t % 32;
-            blockDim.x = (unsigned)phc::packed::kThreads; threadIdx.x = (unsigned)t; threadIdx.y = threadIdx.z = 0;
-            blockIdx.x = (unsigned)b; blockIdx.y = blockIdx.z = 0;
-            phc::packed::env_step_packed_kernel(*a, amp_dim, stride);
+    case 7: {    // env_step_fast.cu: the steady-state kernel with the phases ordered by input arrival (one warp per env)
+      const int stride = phc::fast::env_stride(amp_dim);
+      for (int env = 0; env < a->num_envs; ++env) {
+        EmuWarp warp;
+        std::vector<std::thread> lanes;
+        for (int lane = 0; lane < 32; ++lane)
+          lanes.emplace_back([&, lane] {
+            emu_warp = &warp;
+            emu_lane = lane;
+            threadIdx.x = (unsigned)((env % phc::fast::kWarps) * 32 + lane); threadIdx.y = threadIdx.z = 0;
+            blockIdx.x = (unsigned)(env / phc::fast::kWarps); blockIdx.y = blockIdx.z = 0;
+            phc::fast::env_step_fast_kernel(*a, amp_dim, stride);
           });
-        for (auto& t : ts) t.join();
+        for (auto& t : lanes) t.join();
       }
-      emu_block_bar = nullptr;
       return 0;
     }
     case 6:      // env_step_wide.cu: strided bodies, no staging
@@ -94,11 +91,11 @@ def assemble() -> str:
     k1 = step.index("}  // namespace phc") + len("}  // namespace phc")
     kernel = step[k0:k1]
     assert "env_step_kernel(" in kernel and "<<<" not in kernel
-    pk = open(os.path.join(CSRC, "env_step_packed.cu")).read()
+    pk = open(os.path.join(CSRC, "env_step_fast.cu")).read()
     p0 = pk.index("namespace phc {")
     p1 = pk.index("}  // namespace phc") + len("}  // namespace phc")
-    packed = pk[p0:p1]
-    assert "env_step_packed_kernel(" in packed and "<<<" not in packed
+    fastk = pk[p0:p1]
+    assert "env_step_fast_kernel(" in fastk and "<<<" not in fastk
     w = open(os.path.join(CSRC, "env_step_wide.cu")).read()
     w0 = w.index("namespace phc {")
     w1 = w.index("}  // namespace phc") + len("}  // namespace phc")
@@ -109,7 +106,7 @@ def assemble() -> str:
         "namespace phc {", reductions, "}",
         f'#include "{os.path.join(ROOT, "include", "phc_b200.h")}"', f'#include "{os.path.join(CSRC, "phc_math.cuh")}"',
         f'#include "{os.path.join(CSRC, "env_step_shared.cuh")}"',
-        kernel, packed, wide, LAUNCHER])
+        kernel, fastk, wide, LAUNCHER])
 
 
 MOTION_LAUNCHER = r'''

@@ -56,7 +56,7 @@ def host_mode():
 
 
 class Emu:
-    VARIANTS = {"smpl": 0, "fast": 1, "getup": 2, "generic": 3, "fut": 4, "getup_generic": 5, "wide": 6, "packed": 7}
+    VARIANTS = {"smpl": 0, "fast": 1, "getup": 2, "generic": 3, "fut": 4, "getup_generic": 5, "wide": 6, "fastk": 7}
 
     def __init__(self, so_path):
         self.lib = C.CDLL(so_path)

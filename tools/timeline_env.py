@@ -21,7 +21,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 task = HumanoidIm({"env": {"num_envs": n}, "motion_data": syn.make_motions(n, seed=0), "seed": 0})
 task.reset()
 lib = _lib.load()
-for fn in (lib.phc_exp_set_timeline, lib.phc_exp_set_timeline_packed):      # one buffer pointer per kernel source file
+for fn in (lib.phc_exp_set_timeline, lib.phc_exp_set_timeline_fast):      # one buffer pointer per kernel source file
     fn.argtypes = [C.c_void_p]
     fn.restype = C.c_int
 tl = torch.zeros(n, 8, dtype=torch.int64, device="cuda")
@@ -31,7 +31,7 @@ for i in range(6):
     flush.fill_(float(i))
     task._plan.run()
 _lib.check(lib.phc_exp_set_timeline(tl.data_ptr()))
-_lib.check(lib.phc_exp_set_timeline_packed(tl.data_ptr()))
+_lib.check(lib.phc_exp_set_timeline_fast(tl.data_ptr()))
 runs = []
 for i in range(5):
     task.sim.simulate(None)
