@@ -273,13 +273,13 @@ def run_reference_arm(args):
 WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on (and what the driver's default run measures)
     "smpl": dict(desc="SMPL 24 bodies, obs 934, AMP 10x196, im.yaml nets (1024-512)", envs=NUM_ENVS, algo_bytes=ALGO_BYTES_PER_ENV_STEP,
-                 kernel="phc::env_step_kernel<1, 24, false, true>"),
+                 kernel="phc::fast::env_step_fast_kernel"),
     # configs[4]: Unitree H1, 20 bodies + 3 extend bodies in the reward, 19 hinge dofs, obs 778, AMP 10x63 (env_im_h1_phc.yaml, unitree_h1.yaml)
     "h1": dict(desc="Unitree H1 20 bodies + 3 extend bodies, 19 hinge dofs, obs 778, AMP 10x63, im.yaml nets (1024-512)", envs=4096, algo_bytes=7528,
                kernel="phc::env_step_kernel<1, 0, false, false> (run-time body count)"),
     # configs[3]: PHC+ progressive network, 4 primitive columns of im_pnn_big.yaml nets (6 hidden layers, SiLU), 8192 envs
     "pnn_big": dict(desc="SMPL 24 bodies, amp_pnn network: 4 primitive columns (training column 0) of 2048-1536-1024-1024-512-512 SiLU, disc 1024-512 ReLU "
-                         "(im_pnn_big.yaml)", envs=8192, algo_bytes=ALGO_BYTES_PER_ENV_STEP, kernel="phc::env_step_kernel<1, 24, false, true>"),
+                         "(im_pnn_big.yaml)", envs=8192, algo_bytes=ALGO_BYTES_PER_ENV_STEP, kernel="phc::fast::env_step_fast_kernel"),
 }
 
 
@@ -336,7 +336,7 @@ def timed_epochs(agent, steps: int, warmup: int, world: int, read_result: bool):
 
 
 def env_kernel_roofline(task, peak_gbs: float, peak_src: str, iters: int = 40, algo_bytes: int = ALGO_BYTES_PER_ENV_STEP,
-                         kernel: str = "phc::packed::env_step_packed_kernel"):
+                         kernel: str = "phc::fast::env_step_fast_kernel"):
     """Average duration of the fused env-step kernel with inputs coming from HBM (L2 flushed by a 256 MB write before every
     launch), CUDA events on the launching stream.  Two measurements:
       * `kernel_us` (used for `achieved`): K x [flush, kernel] and K x [flush] are each bracketed by ONE event pair and the

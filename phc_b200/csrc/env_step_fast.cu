@@ -14,6 +14,8 @@
 // because its head must not overwrite inputs that are still unread: floats [0, 356) in their own region, floats [356, 936) over
 // the consumed [simulator block | cached pose] (356 * 4 bytes is the last 16-byte boundary below the self / task seam at 358).
 // One warp per env, lane = body, 4 warps per CTA, 7 CTAs per SM (28 envs per SM: 4096 envs are one wave on 148 SMs).
+// A/B knobs kept for tools/gpu_r2_s19.sh / s20.sh (both measured WORSE, profiles/env_step_r2_*.log): PHC_EXP_CACHE_LATE requests
+// the cached pose together with the bracket, PHC_EXP_SCALARS_FIRST puts the scalar requests ahead of the simulator block.
 // Launch conditions: exactly those of the FAST instantiation (phc_env_step checks them); reference functions replaced: as
 // env_step.cu (include/phc_b200.h, PhcStepArgs).
 #include <cuda_runtime.h>
@@ -81,11 +83,13 @@ env_step_fast_kernel(const __grid_constant__ PhcStepArgs a, const int amp_dim, c
 #endif
 
   // ---- requests in the order the phases need them: simulator block, scalars, [cached pose], dof rows ----------------------------
+#ifndef PHC_EXP_SCALARS_FIRST
   if (lane == 0) {
     mbar_arrive_expect_tx(bar_s, kBlockBytes);
     bulk_g2s(s_state, a.body_state + (size_t)env * a.bodies_per_env * kBodyRec, kBlockBytes, bar_s);
   }
   __syncwarp();
+#endif
   const int64_t progress = a.progress[env];
   const float t_start = a.start_times[env], t_off = a.start_offsets[env];
   const V3 goff = v3(a.global_offset[3 * env + 0], a.global_offset[3 * env + 1], a.global_offset[3 * env + 2]);
@@ -93,6 +97,13 @@ env_step_fast_kernel(const __grid_constant__ PhcStepArgs a, const int amp_dim, c
   const float m_len = __int_as_float(em.x), m_dt = __int_as_float(em.y);
   const int m_nf = em.z;
   const int64_t m_start = em.w;
+#ifdef PHC_EXP_SCALARS_FIRST
+  if (lane == 0) {
+    mbar_arrive_expect_tx(bar_s, kBlockBytes);
+    bulk_g2s(s_state, a.body_state + (size_t)env * a.bodies_per_env * kBodyRec, kBlockBytes, bar_s);
+  }
+  __syncwarp();
+#endif
 #ifndef PHC_EXP_CACHE_LATE
   if (lane == 0) {
     mbar_arrive_expect_tx(bar_c, kBlockBytes);

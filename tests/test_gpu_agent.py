@@ -347,6 +347,37 @@ def test_shipped_config_takes_the_specialised_step_kernel():
     close(env._ref_cache.cpu(), fast["cache"].cpu(), what="fast vs generic pose cache")
 
 
+def test_arrival_ordered_step_kernel_is_bit_identical_to_the_fast_instantiation(tmp_path):
+    """env_step_fast.cu (what phc_env_step launches for the shipped steady state) against env_step_kernel<1, 24, false, true> on the
+    device: the same seeded three steps in two fresh processes (PHC_ENV_FASTK is read once per process), every output bit for bit."""
+    import os
+    import subprocess
+    import sys
+    script = (
+        "import sys, torch\n"
+        "from phc_b200 import synthetic as syn\n"
+        "from phc_b200.env.humanoid_im import HumanoidIm\n"
+        "n = 1000\n"
+        "m = syn.make_motions(n, seed=23, min_frames=30, max_frames=70)\n"
+        "task = HumanoidIm({'env': {'num_envs': n}, 'motion_data': m, 'seed': 23})\n"
+        "torch.manual_seed(5); task.reset(); out = []\n"
+        "for step in range(3):\n"
+        "    task.step(None); torch.cuda.synchronize()\n"
+        "    out.append({k: getattr(task, k).cpu().clone() for k in ('obs_buf', 'rew_buf', 'reward_raw', 'reset_buf', '_terminate_buf', '_amp_obs_buf', '_ref_cache')})\n"
+        "torch.save(out, sys.argv[1])\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("1", "0"):
+        f = str(tmp_path / f"fastk{flag}.pt")
+        r = subprocess.run([sys.executable, "-c", script, f], env=dict(os.environ, PHC_ENV_FASTK=flag, PYTHONPATH=root), cwd=root,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(torch.load(f))
+    for step, (a, b) in enumerate(zip(*outs)):
+        for k in a:
+            assert torch.equal(a[k], b[k]), f"step {step}: {k} differs between env_step_fast_kernel and the FAST instantiation"
+
+
 def test_im_eval_extras_match_oracle():
     """flags.im_eval: extras['mpjpe'] / 'body_pos_gt' (humanoid_im.py:674-680) and the mean-distance termination, against the oracle."""
     n = 130

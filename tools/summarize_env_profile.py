@@ -13,6 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, tag = sys.argv[1], sys.argv[2]
 n_env = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
+kregex = sys.argv[4] if len(sys.argv) > 4 else "env_step_kernel"
 
 
 def page(name, *extra):
@@ -57,7 +58,7 @@ for op, v in per_op.items():
 
 out = os.path.join(ROOT, "profiles", f"env_step_{tag}_ncu.md")
 with open(out, "w") as f:
-    f.write(f"# {kernel.split('(')[0]} -- ncu --set full ({tag})\n\nCommand: `ncu --set full --clock-control none --import-source on -k regex:env_step_kernel "
+    f.write(f"# {kernel.split('(')[0]} -- ncu --set full ({tag})\n\nCommand: `ncu --set full --clock-control none --import-source on -k regex:{kregex} "
             f"-s 6 -c 1 python tools/profile_env.py {n_env} 12` ({n_env} envs, one clip per env, L2 flushed before each launch); summary by "
             "`tools/summarize_env_profile.py`.\n\n| metric | value | unit |\n|---|---:|---|\n")
     for w in want:
