@@ -347,9 +347,11 @@ def test_shipped_config_takes_the_specialised_step_kernel():
     close(env._ref_cache.cpu(), fast["cache"].cpu(), what="fast vs generic pose cache")
 
 
-def test_arrival_ordered_step_kernel_is_bit_identical_to_the_fast_instantiation(tmp_path):
+def test_arrival_ordered_step_kernel_matches_the_fast_instantiation(tmp_path):
     """env_step_fast.cu (what phc_env_step launches for the shipped steady state) against env_step_kernel<1, 24, false, true> on the
-    device: the same seeded three steps in two fresh processes (PHC_ENV_FASTK is read once per process), every output bit for bit."""
+    device: the same seeded three steps in two fresh processes (PHC_ENV_FASTK is read once per process).  The two kernels are the same
+    source expressions (bit-identical in the -ffp-contract=off CPU emulation, tests/test_env_step_emu_cpu.py); on the device nvcc
+    contracts mul + add pairs per kernel, so floats agree to rounding (the fast-vs-generic tolerance), integers exactly."""
     import os
     import subprocess
     import sys
@@ -375,7 +377,10 @@ def test_arrival_ordered_step_kernel_is_bit_identical_to_the_fast_instantiation(
         outs.append(torch.load(f))
     for step, (a, b) in enumerate(zip(*outs)):
         for k in a:
-            assert torch.equal(a[k], b[k]), f"step {step}: {k} differs between env_step_fast_kernel and the FAST instantiation"
+            if a[k].dtype.is_floating_point:
+                close(a[k], b[k], atol=2e-6, what=f"step {step}: {k}, env_step_fast_kernel vs the FAST instantiation")
+            else:
+                assert torch.equal(a[k], b[k]), f"step {step}: {k} differs between env_step_fast_kernel and the FAST instantiation"
 
 
 def test_im_eval_extras_match_oracle():
