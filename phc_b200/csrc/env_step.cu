@@ -137,9 +137,7 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     }
     __syncwarp();
   };
-#ifndef PHC_EXP_SCALARS_FIRST
   issue_env_blocks();
-#endif
 
   // ---- every load that depends only on the env index is issued first (one DRAM round trip for all of them) ----------
   const int64_t progress = a.progress[env];
@@ -155,9 +153,6 @@ env_step_kernel(const __grid_constant__ PhcStepArgs a, const int obs_dim, const 
     m_len = a.lib.motion_len[mid]; m_dt = a.lib.motion_dt[mid];
     m_nf = a.lib.motion_num_frames[mid]; m_start = a.lib.length_starts[mid];
   }
-#ifdef PHC_EXP_SCALARS_FIRST       // the few scalar requests ahead of the 2.5 KB blocks in the memory system's queues
-  issue_env_blocks();
-#endif
   const float2* g_dof = reinterpret_cast<const float2*>(a.dof_state) + (size_t)env * D;
   const float* g_force = (FAST || a.dof_force) ? a.dof_force + (size_t)env * D : nullptr;
   float2 dof_pv[3];                                   // D <= 93 for J <= 32: at most 3 dofs per lane
