@@ -1,18 +1,22 @@
 // Fused env step, steady state of the shipped SMPL configuration, with the phases ordered by INPUT ARRIVAL.
 //
-// What the per-warp timeline of env_step_kernel<1, 24, false, true> showed (tools/timeline_env.py, profiles/env_step_r2_*): at
-// 4096 envs the launch is one wave; every warp asks for its simulator block, its cached reference pose and its dof rows at
-// t = 0 (13.7 MB in flight), its few scalars queue behind them, and nothing computes until ~2-4 us after entry; the observation
-// frames, whose addresses need those scalars, are requested only then.  This kernel is the same arithmetic (env_step_shared.cuh,
-// phc_math.cuh: operation for operation, the same warp reductions -> bit-identical outputs) in an order in which each phase needs
-// only what has been asked for first:
-//   phase 1  [simulator block]            heading frame, SELF observation, AMP observation of the simulated character
+// What the per-warp timeline of env_step_kernel<1, 24, false, true> showed (tools/timeline_env.py, profiles/env_step_r2_timeline.md):
+// at 4096 envs the launch is one wave; every warp asks for its simulator block, its cached reference pose and its dof rows at
+// t = 0 (13.7 MB in flight), its few scalars queue behind them, and -- a warp issues in order -- nothing computed until the first
+// USE of those scalars (the frame bracket, in front of everything else) was satisfied, 2-5 us after entry.  This kernel is the same
+// source expressions (env_step_shared.cuh, phc_math.cuh: operation for operation, the same warp reductions; bit-identical to the
+// FAST instantiation in the -ffp-contract=off CPU emulation, to rounding on the device where nvcc contracts per kernel) in an order
+// in which each phase needs only what was asked for first:
+//   phase 1a [simulator block]            heading frame, SELF observation                          (humanoid.py:1994-2050)
+//            -- first use of the scalar loads: frame bracket, the bracket's copies are issued; dof rows staged --
+//   phase 1b [+ dof rows]                 AMP observation of the simulated character                (humanoid_amp.py:980-1060)
 //   phase 2  [+ cached reference pose]    tracking errors, termination vote, reward / reset        (humanoid_im.py:1523-1608)
 //   phase 3  [+ observation bracket]      blend, pose-cache row for the next step, TASK observation (humanoid_im.py:1308-1358)
 // with one mbarrier per input, the simulator block requested before anything else, and the rows leaving as soon as they are
 // complete (AMP slot + the first 356 floats of the observation row after phase 1).  The observation row is staged in two pieces
 // because its head must not overwrite inputs that are still unread: floats [0, 356) in their own region, floats [356, 936) over
 // the consumed [simulator block | cached pose] (356 * 4 bytes is the last 16-byte boundary below the self / task seam at 358).
+// Measured (same box, L2 flushed, PDL launch): 12.3 -> 10.8 us at 4096 envs, 39.5 -> 36.9 us at 16384.
 // One warp per env, lane = body, 4 warps per CTA, 7 CTAs per SM (28 envs per SM: 4096 envs are one wave on 148 SMs).
 // A/B knobs kept for tools/gpu_r2_s19.sh / s20.sh (both measured WORSE, profiles/env_step_r2_*.log): PHC_EXP_CACHE_LATE requests
 // the cached pose together with the bracket, PHC_EXP_SCALARS_FIRST puts the scalar requests ahead of the simulator block.
