@@ -120,13 +120,16 @@ def test_getup_instantiation_vs_reference_golden(emu):
     assert torch.equal(cc.long(), exp["cycle_counter"].long())
 
 
-def test_specialised_instantiation_and_pose_cache(emu):
-    """Two consecutive steps through the pose cache: step 1 (generic, fills the cache with the pose interpolated for its
+@pytest.mark.parametrize("frames", [(30, 50), (4, 12)])
+def test_specialised_instantiation_and_pose_cache(emu, frames):
+    """(The second parametrisation uses clips of 4-12 frames with progress up to 20: most envs are past the end of their clip, where
+    the bracket collapses onto the last frame -- one copy for both slots -- and pass_time resets fire.)
+    Two consecutive steps through the pose cache: step 1 (generic, fills the cache with the pose interpolated for its
     observation), step 2 through the FAST instantiation (reward pose from the cache, ring slot, bulk rows) against the generic
     instantiation without cache on the same inputs -- the arithmetic is the same source, so the results agree to rounding."""
     e, hp = emu
     n = 12
-    m = syn.make_motions(n, seed=5, min_frames=30, max_frames=50)
+    m = syn.make_motions(n, seed=5, min_frames=frames[0], max_frames=frames[1])
     st = syn.make_env_state(m, n, seed=5, max_progress=20)
     bs = hp.round4(13 * 24)
     cache = torch.zeros(n, bs)
